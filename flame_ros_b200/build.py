@@ -1,0 +1,55 @@
+"""In-tree build of libflame_b200.so with nvcc for sm_100a (no JIT cache, no pip install)."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libflame_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-cudart", "static",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (looked at $NVCC, /usr/local/cuda/bin/nvcc, PATH)")
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + [os.path.join(HERE, "..", "include", "flame_b200.h")]
+    return any(os.path.getmtime(s) > t for s in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/flame_b200.cu -> lib/libflame_b200.so. Returns the library path."""
+    if not force and not is_stale():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB_PATH, os.path.join(CSRC, "flame_b200.cu")]
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,359 @@
+"""ctypes binding of libflame_b200.so (include/flame_b200.h) and a thin numpy-facing wrapper.
+
+This is the host-side mirror used by the tests and bench.py; every call goes through the C-ABI that
+the C++ `flame::Flame` shim (include/flame/flame.h) uses.  There is no CPU fallback: if the shared
+library is missing or no CUDA device is present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+NUM_COUNTERS = 8
+STATUS_NAMES = ["SUCCESS", "FAIL_REF_PATCH_GRADIENT", "FAIL_AMBIGUOUS_MATCH", "FAIL_MAX_COST",
+                "FAIL_MAX_VAR", "FAIL_MAX_DROPOUTS", "FAIL_OUT_OF_IMAGE", "NO_PARALLAX", "SKIPPED"]
+PROF_SOLVE, PROF_IDEPTH, PROF_UPLOAD, PROF_ASSEMBLY, PROF_INTERP = range(5)
+
+# every symbol include/flame_b200.h declares (tests/test_capi_symbols.py checks this list against
+# the header and the built library)
+SYMBOLS = [
+    "fb_create", "fb_destroy", "fb_last_error", "fb_sync", "fb_version", "fb_host_alloc",
+    "fb_host_free", "fb_set_intrinsics", "fb_set_epi_params", "fb_default_epi_params",
+    "fb_default_nltgv2_params", "fb_default_tri_filter_params", "fb_graph_set", "fb_graph_data_set",
+    "fb_graph_state_set", "fb_graph_state_get", "fb_graph_x_get_all", "fb_nltgv2_solve", "fb_costs",
+    "fb_frame_set", "fb_frame_pose_set", "fb_pool_reserve", "fb_pool_upload", "fb_frame_from_pool",
+    "fb_features_set", "fb_features_get", "fb_idepth_update", "fb_idepth_counters",
+    "fb_project_features", "fb_graph_bind_features", "fb_graph_data_from_features", "fb_mesh_set",
+    "fb_interpolate", "fb_profile_enable", "fb_profile_reset", "fb_profile_get", "fb_launch_count",
+    "fb_last_solver_variant",
+]
+
+
+class FlameError(RuntimeError):
+    pass
+
+
+class NLTGV2Params(C.Structure):
+    """flame::Params::rparams (/root/reference/src/flame_nodelet.cc:256-259)."""
+    _fields_ = [("data_factor", C.c_float), ("step_x", C.c_float), ("step_q", C.c_float),
+                ("theta", C.c_float), ("x_min", C.c_float), ("x_max", C.c_float)]
+
+
+class EpiParams(C.Structure):
+    """flame::Params::{fparams,zparams,max_dropouts} (/root/reference/src/flame_nodelet.cc:227-245)."""
+    _fields_ = [("win_size", C.c_int), ("min_grad_mag", C.c_float), ("epipolar_line_var", C.c_float),
+                ("max_dropouts", C.c_int), ("search_sigma", C.c_float), ("max_cost", C.c_float),
+                ("ambiguity_ratio", C.c_float), ("ambiguity_radius", C.c_int),
+                ("pixel_noise_var", C.c_float), ("meas_var_max", C.c_float),
+                ("idepth_min", C.c_float), ("idepth_max", C.c_float), ("max_search_px", C.c_int),
+                ("min_parallax", C.c_float)]
+
+
+class TriFilterParams(C.Structure):
+    """output/filter_* (/root/reference/src/flame_nodelet.cc:182-206)."""
+    _fields_ = [("do_oblique", C.c_int), ("oblique_normal_thresh", C.c_float),
+                ("oblique_idepth_diff_factor", C.c_float), ("oblique_idepth_diff_abs", C.c_float),
+                ("do_edge_length", C.c_int), ("edge_length_thresh", C.c_float),
+                ("do_idepth", C.c_int), ("min_triangle_idepth", C.c_float)]
+
+
+_LIB = None
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load_library(build_if_missing=True):
+    """dlopen libflame_b200.so (building it in-tree with nvcc when absent/stale and allowed)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if build_if_missing and _build.is_stale():
+        try:
+            _build.build()
+        except Exception as exc:  # stale-but-present library is still usable on a box without nvcc
+            if not os.path.exists(path):
+                raise FlameError("libflame_b200.so is missing and could not be built: %s" % exc)
+    if not os.path.exists(path):
+        raise FlameError("libflame_b200.so not found at %s (run __graft_entry__.build())" % path)
+    lib = C.CDLL(path)
+    lib.fb_create.restype = C.c_void_p
+    lib.fb_create.argtypes = [C.c_int] * 8 + [C.c_void_p]
+    lib.fb_destroy.restype = None
+    lib.fb_destroy.argtypes = [C.c_void_p]
+    lib.fb_last_error.restype = C.c_char_p
+    lib.fb_last_error.argtypes = [C.c_void_p]
+    lib.fb_host_alloc.restype = C.c_void_p
+    lib.fb_host_alloc.argtypes = [C.c_size_t]
+    lib.fb_host_free.restype = None
+    lib.fb_host_free.argtypes = [C.c_void_p]
+    lib.fb_launch_count.restype = C.c_int64
+    lib.fb_launch_count.argtypes = [C.c_void_p]
+    for name in ("fb_default_epi_params", "fb_default_nltgv2_params", "fb_default_tri_filter_params"):
+        getattr(lib, name).restype = None
+    P = C.c_void_p
+    I = C.c_int
+    sigs = {
+        "fb_sync": [P], "fb_set_intrinsics": [P, I, P], "fb_set_epi_params": [P, P],
+        "fb_graph_set": [P, I, I, I, P, P, P, P], "fb_graph_data_set": [P, I, P, P],
+        "fb_graph_state_set": [P, I, P, P, P], "fb_graph_state_get": [P, I, P, P, P, P],
+        "fb_graph_x_get_all": [P, P], "fb_nltgv2_solve": [P, I, P, I],
+        "fb_costs": [P, I, C.c_float, P, P], "fb_frame_set": [P, I, I, P, I, P],
+        "fb_frame_pose_set": [P, I, I, P], "fb_pool_reserve": [P, I], "fb_pool_upload": [P, I, P, I],
+        "fb_frame_from_pool": [P, I, I, I, P], "fb_features_set": [P, I, I, P, P, P, P, P, P],
+        "fb_features_get": [P, I, P, P, P, P, P, P], "fb_idepth_update": [P, P],
+        "fb_idepth_counters": [P, I, P], "fb_project_features": [P, I, I, P, P, P, P],
+        "fb_graph_bind_features": [P, I, P], "fb_graph_data_from_features": [P, I],
+        "fb_mesh_set": [P, I, I, P], "fb_interpolate": [P, I, P, P, P],
+        "fb_profile_enable": [P, I], "fb_profile_reset": [P], "fb_profile_get": [P, I, P, P, P],
+        "fb_last_solver_variant": [P], "fb_version": [],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def default_nltgv2_params():
+    p = NLTGV2Params()
+    load_library().fb_default_nltgv2_params(C.byref(p))
+    return p
+
+
+def default_epi_params():
+    p = EpiParams()
+    load_library().fb_default_epi_params(C.byref(p))
+    return p
+
+
+def default_tri_filter_params():
+    p = TriFilterParams()
+    load_library().fb_default_tri_filter_params(C.byref(p))
+    return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+class PinnedBuffer:
+    """Page-locked host memory from fb_host_alloc exposed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self._lib = load_library()
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._p = self._lib.fb_host_alloc(nbytes)
+        if not self._p:
+            raise FlameError("fb_host_alloc(%d) failed" % nbytes)
+        buf = (C.c_uint8 * nbytes).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            self._lib.fb_host_free(self._p)
+            self._p = None
+
+
+class Context:
+    """A batch of `n_streams` FLaME hot-path states on one GPU (wraps fb_ctx)."""
+
+    def __init__(self, n_streams=1, width=640, height=480, n_slots=8, max_features=8192,
+                 max_vertices=8192, max_edges=24576, device=0, cuda_stream=None):
+        self._lib = load_library()
+        self.S, self.W, self.H, self.n_slots = n_streams, width, height, n_slots
+        self.max_features, self.max_vertices, self.max_edges = max_features, max_vertices, max_edges
+        self._h = self._lib.fb_create(device, n_streams, width, height, n_slots, max_features,
+                                      max_vertices, max_edges, cuda_stream)
+        if not self._h:
+            raise FlameError(self._lib.fb_last_error(None).decode())
+        self._nV = [0] * n_streams
+        self._nE = [0] * n_streams
+        self._nF = [0] * n_streams
+        self._nT = [0] * n_streams
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise FlameError("libflame_b200 error %d: %s" % (rc, self._lib.fb_last_error(self._h).decode()))
+
+    # ------------------------------------------------------------------ configuration
+    def sync(self):
+        self._ck(self._lib.fb_sync(self._h))
+
+    def set_intrinsics(self, stream, K):
+        K = _f32(np.asarray(K).reshape(9))
+        self._ck(self._lib.fb_set_intrinsics(self._h, stream, _ptr(K)))
+
+    def set_epi_params(self, p):
+        self._ck(self._lib.fb_set_epi_params(self._h, C.byref(p)))
+
+    # ------------------------------------------------------------------ graph / solver
+    def graph_set(self, stream, pos, edges, alpha, beta):
+        pos, edges, alpha, beta = _f32(pos), _i32(edges), _f32(alpha), _f32(beta)
+        V, E = pos.shape[0], edges.shape[0]
+        self._ck(self._lib.fb_graph_set(self._h, stream, V, E, _ptr(pos), _ptr(edges), _ptr(alpha), _ptr(beta)))
+        self._nV[stream], self._nE[stream] = V, E
+
+    def graph_data_set(self, stream, z, wt=None):
+        z, wt = _f32(z), _f32(wt)
+        assert z.shape[0] == self._nV[stream]
+        self._ck(self._lib.fb_graph_data_set(self._h, stream, _ptr(z), _ptr(wt)))
+
+    def graph_state_set(self, stream, x=None, w=None, q=None):
+        x, w, q = _f32(x), _f32(w), _f32(q)
+        self._ck(self._lib.fb_graph_state_set(self._h, stream, _ptr(x), _ptr(w), _ptr(q)))
+
+    def graph_state_get(self, stream):
+        V, E = self._nV[stream], self._nE[stream]
+        x = np.zeros(V, np.float32)
+        w = np.zeros((V, 2), np.float32)
+        q = np.zeros((E, 3), np.float32)
+        xb = np.zeros((V, 3), np.float32)
+        self._ck(self._lib.fb_graph_state_get(self._h, stream, _ptr(x), _ptr(w), _ptr(q), _ptr(xb)))
+        return dict(x=x, w1=w[:, 0].copy(), w2=w[:, 1].copy(), q1=q[:, 0].copy(), q2=q[:, 1].copy(),
+                    q3=q[:, 2].copy(), xb=xb[:, 0].copy(), w1b=xb[:, 1].copy(), w2b=xb[:, 2].copy())
+
+    def graph_x_get_all(self, out=None):
+        if out is None:
+            out = np.zeros((self.S, self.max_vertices), np.float32)
+        self._ck(self._lib.fb_graph_x_get_all(self._h, _ptr(out)))
+        return out
+
+    def nltgv2_solve(self, iters, params=None, variant=0):
+        p = params if params is not None else default_nltgv2_params()
+        self._ck(self._lib.fb_nltgv2_solve(self._h, iters, C.byref(p), variant))
+
+    def last_solver_variant(self):
+        return self._lib.fb_last_solver_variant(self._h)
+
+    def costs(self, stream, data_factor=0.15):
+        s, d = C.c_double(0), C.c_double(0)
+        self._ck(self._lib.fb_costs(self._h, stream, data_factor, C.byref(s), C.byref(d)))
+        return s.value, d.value
+
+    # ------------------------------------------------------------------ frames / features
+    def frame_set(self, stream, slot, gray, pose):
+        assert gray.dtype == np.uint8 and gray.ndim == 2 and gray.shape == (self.H, self.W)
+        assert gray.strides[1] == 1
+        pose = _f32(pose)
+        self._ck(self._lib.fb_frame_set(self._h, stream, slot, _ptr(gray), gray.strides[0], _ptr(pose)))
+
+    def frame_pose_set(self, stream, slot, pose):
+        pose = _f32(pose)
+        self._ck(self._lib.fb_frame_pose_set(self._h, stream, slot, _ptr(pose)))
+
+    def pool_reserve(self, n):
+        self._ck(self._lib.fb_pool_reserve(self._h, n))
+
+    def pool_upload(self, idx, gray):
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        self._ck(self._lib.fb_pool_upload(self._h, idx, _ptr(gray), gray.strides[0]))
+
+    def frame_from_pool(self, stream, slot, idx, pose):
+        pose = _f32(pose)
+        self._ck(self._lib.fb_frame_from_pool(self._h, stream, slot, idx, _ptr(pose)))
+
+    def features_set(self, stream, u_ref, ref_slot, mu, var, dropouts=None, alive=None):
+        u_ref, ref_slot, mu, var = _f32(u_ref), _i32(ref_slot), _f32(mu), _f32(var)
+        dropouts, alive = _i32(dropouts), _i32(alive)
+        N = ref_slot.shape[0]
+        self._ck(self._lib.fb_features_set(self._h, stream, N, _ptr(u_ref), _ptr(ref_slot), _ptr(mu),
+                                           _ptr(var), _ptr(dropouts), _ptr(alive)))
+        self._nF[stream] = N
+
+    def features_get(self, stream):
+        N = self._nF[stream]
+        out = dict(mu=np.zeros(N, np.float32), var=np.zeros(N, np.float32),
+                   dropouts=np.zeros(N, np.int32), alive=np.zeros(N, np.int32),
+                   status=np.zeros(N, np.int32), u_cmp=np.zeros((N, 2), np.float32))
+        self._ck(self._lib.fb_features_get(self._h, stream, _ptr(out["mu"]), _ptr(out["var"]),
+                                           _ptr(out["dropouts"]), _ptr(out["alive"]),
+                                           _ptr(out["status"]), _ptr(out["u_cmp"])))
+        return out
+
+    def idepth_update(self, cmp_slot):
+        cmp_slot = _i32(np.broadcast_to(np.asarray(cmp_slot, np.int32), (self.S,)))
+        self._ck(self._lib.fb_idepth_update(self._h, _ptr(cmp_slot)))
+
+    def idepth_counters(self, stream):
+        c = np.zeros(NUM_COUNTERS, np.int32)
+        self._ck(self._lib.fb_idepth_counters(self._h, stream, _ptr(c)))
+        return c
+
+    def project_features(self, stream, cur_slot):
+        N = self._nF[stream]
+        u = np.zeros((N, 2), np.float32)
+        mu = np.zeros(N, np.float32)
+        var = np.zeros(N, np.float32)
+        valid = np.zeros(N, np.int32)
+        self._ck(self._lib.fb_project_features(self._h, stream, cur_slot, _ptr(u), _ptr(mu), _ptr(var), _ptr(valid)))
+        return u, mu, var, valid
+
+    # ------------------------------------------------------------------ assembly / interpolation
+    def graph_bind_features(self, stream, vertex_feature):
+        vf = _i32(vertex_feature)
+        assert vf.shape[0] == self._nV[stream]
+        self._ck(self._lib.fb_graph_bind_features(self._h, stream, _ptr(vf)))
+
+    def graph_data_from_features(self, adaptive_weights=False):
+        self._ck(self._lib.fb_graph_data_from_features(self._h, 1 if adaptive_weights else 0))
+
+    def mesh_set(self, stream, tris):
+        tris = _i32(tris)
+        self._ck(self._lib.fb_mesh_set(self._h, stream, tris.shape[0], _ptr(tris)))
+        self._nT[stream] = tris.shape[0]
+
+    def interpolate(self, stream, filter_params=None):
+        out = np.zeros((self.H, self.W), np.float32)
+        valid = np.zeros(max(self._nT[stream], 1), np.uint8)
+        fp = C.byref(filter_params) if filter_params is not None else None
+        self._ck(self._lib.fb_interpolate(self._h, stream, fp, _ptr(out), _ptr(valid)))
+        return out, valid[:self._nT[stream]]
+
+    # ------------------------------------------------------------------ profiling
+    def profile_enable(self, on=True):
+        self._ck(self._lib.fb_profile_enable(self._h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._ck(self._lib.fb_profile_reset(self._h))
+
+    def profile_get(self, section):
+        ms, calls, launches = C.c_float(0), C.c_int64(0), C.c_int64(0)
+        self._ck(self._lib.fb_profile_get(self._h, section, C.byref(ms), C.byref(calls), C.byref(launches)))
+        return ms.value, calls.value, launches.value
+
+    def launch_count(self):
+        return self._lib.fb_launch_count(self._h)

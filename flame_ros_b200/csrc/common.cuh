@@ -1,0 +1,118 @@
+// common.cuh -- shared declarations for libflame_b200 (sm_100a).
+//
+// Float discipline (DESIGN.md "Numerics"): this translation unit is compiled with --fmad=false, so
+// a fused multiply-add happens only where fmaf() is written.  Every kernel spells its arithmetic in
+// the order documented in DESIGN.md so results are reproducible run to run and comparable with the
+// test oracle bit for bit.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/flame_b200.h"
+
+#define FB_MAX_WIN 15
+#define FB_MAX_SEARCH 256
+#define FB_GEO_STRIDE 16  // floats per (stream, slot) geometry record: A[9] b[3] e[3] pad
+
+struct ProfSection {
+  std::vector<cudaEvent_t> ev;  // begin/end pairs not yet folded into total_ms
+  double total_ms = 0.0;
+  int64_t calls = 0;
+  int64_t launches = 0;
+};
+
+struct fb_ctx {
+  int device = 0;
+  int S = 0, W = 0, H = 0, n_slots = 0, maxF = 0, maxV = 0, maxE = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  // ---- graph (per stream s: vertex base s*maxV, edge base s*maxE, incidence base s*2*maxE)
+  float4* vbar = nullptr;   // (xb, w1b, w2b, 0)         [S*maxV]
+  float* x = nullptr;       // planar primal state        [S*maxV] each
+  float* w1 = nullptr;
+  float* w2 = nullptr;
+  float* z = nullptr;       // data term
+  float* wt = nullptr;      // data weight
+  float4* ec = nullptr;     // (alpha, beta, dx, dy)      [S*maxE]
+  int2* eij = nullptr;      // (i, j) stream-local        [S*maxE]
+  float4* q4 = nullptr;     // (q1, q2, q3, 0)            [S*maxE]
+  int32_t* row = nullptr;   // CSR row pointers           [S*(maxV+1)]
+  int32_t* inc = nullptr;   // (edge<<1)|role             [S*2*maxE]
+  int32_t* nV = nullptr;    // device counts              [S]
+  int32_t* nE = nullptr;
+  std::vector<int32_t> hV, hE;       // host mirrors of the counts
+  int32_t* vfeat = nullptr; // vertex -> feature index    [S*maxV]
+  float2* vpos = nullptr;   // vertex pixel positions     [S*maxV]
+  double* costs = nullptr;  // [S*2]
+
+  // ---- persistent-cluster solver images (variant 2), rebuilt by fb_graph_set
+  struct ClusterPlan* plan = nullptr;
+
+  // ---- frames
+  uint8_t* imgs = nullptr;  // [S][n_slots][H][W]
+  std::vector<float> h_pose;  // [S][n_slots][7]
+  std::vector<float> h_K;     // [S][9]
+  float* d_pose = nullptr;    // [S][n_slots][7]
+  float* d_K = nullptr;       // [S][9]
+  int32_t* d_cmp = nullptr;   // [S]
+  float* d_geo = nullptr;     // [S][n_slots][FB_GEO_STRIDE]
+  uint8_t* pool = nullptr;    // device frame pool
+  int pool_n = 0;
+
+  // ---- features (per stream base s*maxF)
+  float2* f_uref = nullptr;
+  float* f_mu = nullptr;
+  float* f_var = nullptr;
+  int32_t* f_drop = nullptr;
+  int32_t* f_alive = nullptr;
+  int32_t* f_ref = nullptr;
+  int32_t* f_status = nullptr;
+  float2* f_ucmp = nullptr;
+  int32_t* nF = nullptr;       // [S]
+  std::vector<int32_t> hF;
+  int32_t* counters = nullptr; // [S][FB_NUM_COUNTERS]
+  fb_epi_params epi;
+
+  // ---- mesh / interpolation
+  int32_t* tri = nullptr;      // [S][maxT][3]
+  int maxT = 0;
+  std::vector<int32_t> hT;
+  int32_t* nT = nullptr;
+  uint8_t* tri_valid = nullptr;  // [S*maxT]
+  int32_t* owner = nullptr;      // [S][H*W] owning triangle per pixel
+  float* idmap = nullptr;        // [S][H*W]
+
+  // ---- CUDA-graph cache for the streaming solver
+  cudaGraphExec_t solve_exec = nullptr;
+  int solve_iters = 0;
+  fb_nltgv2_params solve_params{};
+  int last_variant = 0;
+
+  // ---- profiling
+  bool prof = false;
+  ProfSection sec[FB_PROF_NUM];
+  int64_t launches = 0;
+};
+
+#define FB_CUDA(ctx, call)                                                                  \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                     \
+      return FB_E_CUDA;                                                                     \
+    }                                                                                       \
+  } while (0)
+
+#define FB_FAIL(ctx, code, msg) \
+  do {                          \
+    (ctx)->err = (msg);         \
+    return (code);              \
+  } while (0)
+
+static inline int fb_div_up(int a, int b) { return (a + b - 1) / b; }

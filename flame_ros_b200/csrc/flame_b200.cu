@@ -1,0 +1,736 @@
+// flame_b200.cu -- C-ABI of libflame_b200.so (see include/flame_b200.h for the contract and the
+// reference interfaces each entry point replaces).  Host code is plain C++17; all arithmetic of the
+// hot path runs in the CUDA kernels of nltgv2*.cuh / epipolar.cuh / raster.cuh.  There is no CPU
+// fallback: every compute entry point launches kernels on ctx->stream.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+#include "epipolar.cuh"
+#include "nltgv2.cuh"
+#include "nltgv2_cluster.cuh"
+#include "raster.cuh"
+
+static std::string g_create_error;
+
+// ------------------------------------------------------------------------------------ helpers
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) {
+  return cudaMalloc((void**)p, sizeof(T) * (n ? n : 1));
+}
+
+static GraphView graph_view(fb_ctx* c) {
+  GraphView g;
+  g.vbar = c->vbar; g.x = c->x; g.w1 = c->w1; g.w2 = c->w2; g.z = c->z; g.wt = c->wt;
+  g.ec = c->ec; g.eij = c->eij; g.q4 = c->q4; g.row = c->row; g.inc = c->inc;
+  g.nV = c->nV; g.nE = c->nE; g.maxV = c->maxV; g.maxE = c->maxE;
+  return g;
+}
+
+struct ProfScope {
+  fb_ctx* c;
+  int sec;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int64_t l0;
+  ProfScope(fb_ctx* ctx, int section) : c(ctx), sec(section), l0(ctx->launches) {
+    if (c->prof) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, c->stream);
+    }
+  }
+  ~ProfScope() {
+    ProfSection& s = c->sec[sec];
+    s.calls++;
+    s.launches += c->launches - l0;
+    if (c->prof) {
+      cudaEventRecord(e1, c->stream);
+      s.ev.push_back(e0);
+      s.ev.push_back(e1);
+    }
+  }
+};
+
+static void prof_fold(fb_ctx* c, int section) {
+  ProfSection& s = c->sec[section];
+  for (size_t i = 0; i + 1 < s.ev.size(); i += 2) {
+    float ms = 0.f;
+    cudaEventSynchronize(s.ev[i + 1]);
+    if (cudaEventElapsedTime(&ms, s.ev[i], s.ev[i + 1]) == cudaSuccess) s.total_ms += ms;
+    cudaEventDestroy(s.ev[i]);
+    cudaEventDestroy(s.ev[i + 1]);
+  }
+  s.ev.clear();
+}
+
+#define CHECK_CTX(c) \
+  if (!(c)) return FB_E_ARG
+#define CHECK_STREAM(c, s) \
+  if ((s) < 0 || (s) >= (c)->S) FB_FAIL(c, FB_E_ARG, "stream index out of range")
+
+// ------------------------------------------------------------------------------------ lifecycle
+extern "C" int fb_version(void) { return 100; }
+
+extern "C" void fb_default_epi_params(fb_epi_params* p) {
+  // win 5 / min_grad 5 / line var 4 / dropouts 5: /root/reference/cfg/flame_nodelet.yaml:69-75
+  *p = fb_epi_params{5, 5.0f, 4.0f, 5, 2.0f, 400.0f, 1.5f, 2, 4.0f, 1.0f, 0.0f, 10.0f, 64, 0.5f};
+}
+extern "C" void fb_default_nltgv2_params(fb_nltgv2_params* p) {
+  // /root/reference/cfg/flame_nodelet.yaml:86-89
+  *p = fb_nltgv2_params{0.15f, 0.001f, 125.0f, 0.25f, 0.0f, 10.0f};
+}
+extern "C" void fb_default_tri_filter_params(fb_tri_filter_params* p) {
+  // /root/reference/cfg/flame_nodelet.yaml:31-46
+  *p = fb_tri_filter_params{1, 1.57f, 0.35f, 0.1f, 1, 0.333f, 1, 0.01f};
+}
+
+extern "C" const char* fb_last_error(const fb_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" void* fb_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void fb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+static void free_all(fb_ctx* c) {
+  cudaFree(c->vbar); cudaFree(c->x); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->z);
+  cudaFree(c->wt); cudaFree(c->ec); cudaFree(c->eij); cudaFree(c->q4); cudaFree(c->row);
+  cudaFree(c->inc); cudaFree(c->nV); cudaFree(c->nE); cudaFree(c->vfeat); cudaFree(c->vpos);
+  cudaFree(c->costs); cudaFree(c->imgs); cudaFree(c->d_pose); cudaFree(c->d_K);
+  cudaFree(c->d_cmp); cudaFree(c->d_geo); cudaFree(c->pool); cudaFree(c->f_uref);
+  cudaFree(c->f_mu); cudaFree(c->f_var); cudaFree(c->f_drop); cudaFree(c->f_alive);
+  cudaFree(c->f_ref); cudaFree(c->f_status); cudaFree(c->f_ucmp); cudaFree(c->nF);
+  cudaFree(c->counters); cudaFree(c->tri); cudaFree(c->nT); cudaFree(c->tri_valid);
+  cudaFree(c->owner); cudaFree(c->idmap);
+  cluster_plan_free(c);
+  if (c->solve_exec) cudaGraphExecDestroy(c->solve_exec);
+  for (int k = 0; k < FB_PROF_NUM; ++k)
+    for (cudaEvent_t e : c->sec[k].ev) cudaEventDestroy(e);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+}
+
+extern "C" fb_ctx* fb_create(int device, int n_streams, int width, int height, int n_slots,
+                             int max_features, int max_vertices, int max_edges,
+                             void* cuda_stream) {
+  if (n_streams < 1 || width < 16 || height < 16 || n_slots < 2 || n_slots > 1024 ||
+      max_features < 0 || max_vertices < 1 || max_edges < 0) {
+    g_create_error = "fb_create: bad argument";
+    return nullptr;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("fb_create: no CUDA device (") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                     "); libflame_b200 has no CPU fallback";
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) {
+    g_create_error = "fb_create: bad device index";
+    return nullptr;
+  }
+  fb_ctx* c = new fb_ctx();
+  c->device = device; c->S = n_streams; c->W = width; c->H = height; c->n_slots = n_slots;
+  c->maxF = max_features; c->maxV = max_vertices; c->maxE = max_edges;
+  c->maxT = 2 * max_vertices;
+  if (cuda_stream) {
+    c->stream = (cudaStream_t)cuda_stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      g_create_error = "fb_create: cudaStreamCreate failed";
+      delete c;
+      return nullptr;
+    }
+    c->own_stream = true;
+  }
+  const size_t S = n_streams, nv = S * max_vertices, ne = S * max_edges, nf = S * max_features;
+  const size_t npx = (size_t)width * height;
+  bool ok = true;
+  auto A = [&](cudaError_t r) { if (r != cudaSuccess) { ok = false; g_create_error = std::string("fb_create: ") + cudaGetErrorString(r); } };
+  A(dalloc(&c->vbar, nv)); A(dalloc(&c->x, nv)); A(dalloc(&c->w1, nv)); A(dalloc(&c->w2, nv));
+  A(dalloc(&c->z, nv)); A(dalloc(&c->wt, nv)); A(dalloc(&c->ec, ne)); A(dalloc(&c->eij, ne));
+  A(dalloc(&c->q4, ne)); A(dalloc(&c->row, S * (max_vertices + 1))); A(dalloc(&c->inc, 2 * ne));
+  A(dalloc(&c->nV, S)); A(dalloc(&c->nE, S)); A(dalloc(&c->vfeat, nv)); A(dalloc(&c->vpos, nv));
+  A(dalloc(&c->costs, 2 * S));
+  A(dalloc(&c->imgs, S * n_slots * npx)); A(dalloc(&c->d_pose, S * n_slots * 7));
+  A(dalloc(&c->d_K, S * 9)); A(dalloc(&c->d_cmp, S));
+  A(dalloc(&c->d_geo, S * n_slots * FB_GEO_STRIDE));
+  A(dalloc(&c->f_uref, nf)); A(dalloc(&c->f_mu, nf)); A(dalloc(&c->f_var, nf));
+  A(dalloc(&c->f_drop, nf)); A(dalloc(&c->f_alive, nf)); A(dalloc(&c->f_ref, nf));
+  A(dalloc(&c->f_status, nf)); A(dalloc(&c->f_ucmp, nf)); A(dalloc(&c->nF, S));
+  A(dalloc(&c->counters, S * FB_NUM_COUNTERS));
+  A(dalloc(&c->tri, S * (size_t)c->maxT * 3)); A(dalloc(&c->nT, S));
+  A(dalloc(&c->tri_valid, S * (size_t)c->maxT)); A(dalloc(&c->owner, S * npx));
+  A(dalloc(&c->idmap, S * npx));
+  if (!ok) {
+    free_all(c);
+    delete c;
+    return nullptr;
+  }
+  cudaMemsetAsync(c->nV, 0, sizeof(int32_t) * S, c->stream);
+  cudaMemsetAsync(c->nE, 0, sizeof(int32_t) * S, c->stream);
+  cudaMemsetAsync(c->nF, 0, sizeof(int32_t) * S, c->stream);
+  cudaMemsetAsync(c->nT, 0, sizeof(int32_t) * S, c->stream);
+  cudaMemsetAsync(c->counters, 0, sizeof(int32_t) * S * FB_NUM_COUNTERS, c->stream);
+  cudaMemsetAsync(c->vfeat, 0xff, sizeof(int32_t) * nv, c->stream);
+  cudaMemsetAsync(c->imgs, 0, S * n_slots * npx, c->stream);
+  c->hV.assign(S, 0); c->hE.assign(S, 0); c->hF.assign(S, 0); c->hT.assign(S, 0);
+  c->h_pose.assign(S * n_slots * 7, 0.f);
+  for (size_t k = 0; k < S * n_slots; ++k) c->h_pose[7 * k + 3] = 1.f;
+  c->h_K.assign(S * 9, 0.f);
+  for (size_t s = 0; s < S; ++s) {
+    float* K = &c->h_K[9 * s];
+    K[0] = K[4] = (float)width; K[2] = 0.5f * (width - 1); K[5] = 0.5f * (height - 1); K[8] = 1.f;
+  }
+  cudaMemcpyAsync(c->d_K, c->h_K.data(), sizeof(float) * S * 9, cudaMemcpyHostToDevice, c->stream);
+  fb_default_epi_params(&c->epi);
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    g_create_error = "fb_create: initialisation failed";
+    free_all(c);
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+extern "C" void fb_destroy(fb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_all(c);
+  delete c;
+}
+
+extern "C" int fb_sync(fb_ctx* c) {
+  CHECK_CTX(c);
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_set_intrinsics(fb_ctx* c, int s, const float K[9]) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (!K || !(K[0] > 0.f) || !(K[4] > 0.f)) FB_FAIL(c, FB_E_ARG, "fb_set_intrinsics: bad K");
+  memcpy(&c->h_K[9 * s], K, sizeof(float) * 9);
+  FB_CUDA(c, cudaMemcpyAsync(c->d_K + 9 * s, &c->h_K[9 * s], sizeof(float) * 9,
+                             cudaMemcpyHostToDevice, c->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_set_epi_params(fb_ctx* c, const fb_epi_params* p) {
+  CHECK_CTX(c);
+  if (!p || p->win_size < 3 || p->win_size > FB_MAX_WIN || (p->win_size & 1) == 0 ||
+      p->max_search_px < 8 || p->max_search_px > FB_MAX_SEARCH || p->ambiguity_radius < 0)
+    FB_FAIL(c, FB_E_ARG, "fb_set_epi_params: win_size must be odd in [3,15], max_search_px in [8,256]");
+  c->epi = *p;
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------ graph
+extern "C" int fb_graph_set(fb_ctx* c, int s, int V, int E, const float* pos,
+                            const int32_t* ij, const float* alpha, const float* beta) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (V < 0 || E < 0 || (V > 0 && !pos) || (E > 0 && (!ij || !alpha || !beta)))
+    FB_FAIL(c, FB_E_ARG, "fb_graph_set: null input");
+  if (V > c->maxV || E > c->maxE) FB_FAIL(c, FB_E_NOMEM, "fb_graph_set: V/E exceed context capacity");
+  std::vector<float4> ec(E);
+  std::vector<int2> eij(E);
+  std::vector<int32_t> row(V + 1, 0), inc(2 * (size_t)E);
+  for (int e = 0; e < E; ++e) {
+    const int i = ij[2 * e], j = ij[2 * e + 1];
+    if (i < 0 || j < 0 || i >= V || j >= V || i >= j)
+      FB_FAIL(c, FB_E_ARG, "fb_graph_set: edges must satisfy 0 <= i < j < V (canonical orientation)");
+    if (e > 0 && (ij[2 * e - 2] > i || (ij[2 * e - 2] == i && ij[2 * e - 1] >= j)))
+      FB_FAIL(c, FB_E_ARG, "fb_graph_set: edges must be sorted by (i,j) without duplicates");
+    // dx = pos_i - pos_j in fp32, once, so every kernel sees the same delta
+    ec[e] = make_float4(alpha[e], beta[e], pos[2 * i] - pos[2 * j], pos[2 * i + 1] - pos[2 * j + 1]);
+    eij[e] = make_int2(i, j);
+    row[i + 1]++;
+    row[j + 1]++;
+  }
+  for (int v = 0; v < V; ++v) row[v + 1] += row[v];
+  {
+    std::vector<int32_t> fill(row.begin(), row.begin() + V);
+    for (int e = 0; e < E; ++e) {
+      inc[fill[eij[e].x]++] = (e << 1);
+      inc[fill[eij[e].y]++] = (e << 1) | 1;
+    }
+  }
+  const size_t vb = (size_t)s * c->maxV, eb = (size_t)s * c->maxE;
+  cudaStream_t st = c->stream;
+  if (E) {
+    FB_CUDA(c, cudaMemcpyAsync(c->ec + eb, ec.data(), sizeof(float4) * E, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(c->eij + eb, eij.data(), sizeof(int2) * E, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(c->inc + 2 * eb, inc.data(), sizeof(int32_t) * 2 * E, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemsetAsync(c->q4 + eb, 0, sizeof(float4) * E, st));
+  }
+  FB_CUDA(c, cudaMemcpyAsync(c->row + (size_t)s * (c->maxV + 1), row.data(), sizeof(int32_t) * (V + 1), cudaMemcpyHostToDevice, st));
+  if (V) {
+    FB_CUDA(c, cudaMemcpyAsync(c->vpos + vb, pos, sizeof(float2) * V, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemsetAsync(c->vbar + vb, 0, sizeof(float4) * V, st));
+    FB_CUDA(c, cudaMemsetAsync(c->x + vb, 0, sizeof(float) * V, st));
+    FB_CUDA(c, cudaMemsetAsync(c->w1 + vb, 0, sizeof(float) * V, st));
+    FB_CUDA(c, cudaMemsetAsync(c->w2 + vb, 0, sizeof(float) * V, st));
+    FB_CUDA(c, cudaMemsetAsync(c->z + vb, 0, sizeof(float) * V, st));
+    std::vector<float> ones(V, 1.0f);
+    FB_CUDA(c, cudaMemcpyAsync(c->wt + vb, ones.data(), sizeof(float) * V, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemsetAsync(c->vfeat + vb, 0xff, sizeof(int32_t) * V, st));
+  }
+  c->hV[s] = V;
+  c->hE[s] = E;
+  FB_CUDA(c, cudaMemcpyAsync(c->nV + s, &c->hV[s], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  FB_CUDA(c, cudaMemcpyAsync(c->nE + s, &c->hE[s], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  int rc = cluster_plan_build(c, s, V, E, eij.data(), row.data(), inc.data());
+  if (rc != FB_OK) return rc;
+  // the staging vectors above are pageable: the runtime has copied them before returning
+  FB_CUDA(c, cudaStreamSynchronize(st));
+  return FB_OK;
+}
+
+extern "C" int fb_graph_data_set(fb_ctx* c, int s, const float* z, const float* wt) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  const int V = c->hV[s];
+  if (!z) FB_FAIL(c, FB_E_ARG, "fb_graph_data_set: null z");
+  const size_t vb = (size_t)s * c->maxV;
+  FB_CUDA(c, cudaMemcpyAsync(c->z + vb, z, sizeof(float) * V, cudaMemcpyHostToDevice, c->stream));
+  if (wt) {
+    FB_CUDA(c, cudaMemcpyAsync(c->wt + vb, wt, sizeof(float) * V, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    std::vector<float> ones(V, 1.0f);
+    FB_CUDA(c, cudaMemcpyAsync(c->wt + vb, ones.data(), sizeof(float) * V, cudaMemcpyHostToDevice, c->stream));
+  }
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_graph_state_set(fb_ctx* c, int s, const float* x, const float* w, const float* q) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  const int V = c->hV[s], E = c->hE[s];
+  const size_t vb = (size_t)s * c->maxV, eb = (size_t)s * c->maxE;
+  cudaStream_t st = c->stream;
+  std::vector<float> w1, w2;
+  std::vector<float4> q4;
+  if (x) FB_CUDA(c, cudaMemcpyAsync(c->x + vb, x, sizeof(float) * V, cudaMemcpyHostToDevice, st));
+  if (w) {
+    w1.resize(V); w2.resize(V);
+    for (int v = 0; v < V; ++v) { w1[v] = w[2 * v]; w2[v] = w[2 * v + 1]; }
+    FB_CUDA(c, cudaMemcpyAsync(c->w1 + vb, w1.data(), sizeof(float) * V, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(c->w2 + vb, w2.data(), sizeof(float) * V, cudaMemcpyHostToDevice, st));
+  }
+  if (q) {
+    q4.resize(E);
+    for (int e = 0; e < E; ++e) q4[e] = make_float4(q[3 * e], q[3 * e + 1], q[3 * e + 2], 0.f);
+    FB_CUDA(c, cudaMemcpyAsync(c->q4 + eb, q4.data(), sizeof(float4) * E, cudaMemcpyHostToDevice, st));
+  }
+  const int n = std::max(V, E);
+  if (n > 0) {
+    k_state_init<<<fb_div_up(n, 256), 256, 0, st>>>(graph_view(c), s, V, E, x ? 0 : 1, w ? 0 : 1, q ? 0 : 1);
+    c->launches++;
+    FB_CUDA(c, cudaGetLastError());
+  }
+  FB_CUDA(c, cudaStreamSynchronize(st));
+  return FB_OK;
+}
+
+extern "C" int fb_graph_state_get(fb_ctx* c, int s, float* x, float* w, float* q, float* xbar) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  const int V = c->hV[s], E = c->hE[s];
+  const size_t vb = (size_t)s * c->maxV, eb = (size_t)s * c->maxE;
+  cudaStream_t st = c->stream;
+  std::vector<float> w1(V), w2(V);
+  std::vector<float4> q4(E), vb4(V);
+  if (x) FB_CUDA(c, cudaMemcpyAsync(x, c->x + vb, sizeof(float) * V, cudaMemcpyDeviceToHost, st));
+  if (w) {
+    FB_CUDA(c, cudaMemcpyAsync(w1.data(), c->w1 + vb, sizeof(float) * V, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(c, cudaMemcpyAsync(w2.data(), c->w2 + vb, sizeof(float) * V, cudaMemcpyDeviceToHost, st));
+  }
+  if (q) FB_CUDA(c, cudaMemcpyAsync(q4.data(), c->q4 + eb, sizeof(float4) * E, cudaMemcpyDeviceToHost, st));
+  if (xbar) FB_CUDA(c, cudaMemcpyAsync(vb4.data(), c->vbar + vb, sizeof(float4) * V, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(c, cudaStreamSynchronize(st));
+  if (w) for (int v = 0; v < V; ++v) { w[2 * v] = w1[v]; w[2 * v + 1] = w2[v]; }
+  if (q) for (int e = 0; e < E; ++e) { q[3 * e] = q4[e].x; q[3 * e + 1] = q4[e].y; q[3 * e + 2] = q4[e].z; }
+  if (xbar) for (int v = 0; v < V; ++v) { xbar[3 * v] = vb4[v].x; xbar[3 * v + 1] = vb4[v].y; xbar[3 * v + 2] = vb4[v].z; }
+  return FB_OK;
+}
+
+extern "C" int fb_graph_x_get_all(fb_ctx* c, float* x_all) {
+  CHECK_CTX(c);
+  if (!x_all) FB_FAIL(c, FB_E_ARG, "fb_graph_x_get_all: null output");
+  FB_CUDA(c, cudaMemcpyAsync(x_all, c->x, sizeof(float) * (size_t)c->S * c->maxV, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+static int solve_streaming(fb_ctx* c, int iters, const fb_nltgv2_params* p) {
+  int maxv = 0, maxe = 0;
+  for (int s = 0; s < c->S; ++s) { maxv = std::max(maxv, c->hV[s]); maxe = std::max(maxe, c->hE[s]); }
+  if (maxv == 0) return FB_OK;
+  // The launch sequence is captured once per (iters, params, extent) and replayed as one graph.
+  static_assert(sizeof(fb_nltgv2_params) == 24, "params layout");
+  const bool reuse = c->solve_exec && c->solve_iters == iters &&
+                     memcmp(&c->solve_params, p, sizeof(*p)) == 0;
+  if (!reuse) {
+    if (c->solve_exec) { cudaGraphExecDestroy(c->solve_exec); c->solve_exec = nullptr; }
+    const GraphView g = graph_view(c);
+    // grid extents cover the context capacity so the captured graph survives topology changes
+    const dim3 ge(fb_div_up(std::max(c->maxE, 1), 256), c->S), gv(fb_div_up(c->maxV, 256), c->S);
+    const float tl = p->step_x * p->data_factor;
+    cudaGraph_t graph = nullptr;
+    FB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    for (int it = 0; it < iters; ++it) {
+      k_dual_edges<<<ge, 256, 0, c->stream>>>(g, p->step_q);
+      k_primal_vertices<<<gv, 256, 0, c->stream>>>(g, p->step_x, tl, p->theta, p->x_min, p->x_max);
+    }
+    FB_CUDA(c, cudaStreamEndCapture(c->stream, &graph));
+    cudaError_t e = cudaGraphInstantiate(&c->solve_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { c->solve_exec = nullptr; FB_FAIL(c, FB_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    c->solve_iters = iters;
+    c->solve_params = *p;
+  }
+  FB_CUDA(c, cudaGraphLaunch(c->solve_exec, c->stream));
+  c->launches += 2 * (int64_t)iters;
+  return FB_OK;
+}
+
+extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, int variant) {
+  CHECK_CTX(c);
+  if (!p || iters < 0 || variant < 0 || variant > 2) FB_FAIL(c, FB_E_ARG, "fb_nltgv2_solve: bad argument");
+  if (iters == 0) return FB_OK;
+  ProfScope ps(c, FB_PROF_SOLVE);
+  int v = variant;
+  if (v == 0) v = cluster_plan_ready(c) ? 2 : 1;
+  if (v == 2 && !cluster_plan_ready(c))
+    FB_FAIL(c, FB_E_STATE, "fb_nltgv2_solve: a graph of this context does not fit the cluster-resident solver");
+  c->last_variant = v;
+  if (v == 2) return solve_cluster(c, iters, p);
+  return solve_streaming(c, iters, p);
+}
+
+extern "C" int fb_last_solver_variant(const fb_ctx* c) { return c ? c->last_variant : 0; }
+
+extern "C" int fb_costs(fb_ctx* c, int s, float data_factor, double* smooth, double* data) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  FB_CUDA(c, cudaMemsetAsync(c->costs, 0, sizeof(double) * 2 * c->S, c->stream));
+  const dim3 grid(std::max(1, std::min(64, fb_div_up(std::max(c->maxE, c->maxV), 256))), c->S);
+  k_costs<<<grid, 256, 0, c->stream>>>(graph_view(c), data_factor, c->costs);
+  c->launches++;
+  FB_CUDA(c, cudaGetLastError());
+  std::vector<double> h(2 * c->S);
+  FB_CUDA(c, cudaMemcpyAsync(h.data(), c->costs, sizeof(double) * 2 * c->S, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (smooth) *smooth = h[2 * s];
+  if (data) *data = h[2 * s + 1];
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------ frames
+static int check_slot(fb_ctx* c, int s, int slot) {
+  CHECK_STREAM(c, s);
+  if (slot < 0 || slot >= c->n_slots) FB_FAIL(c, FB_E_ARG, "slot index out of range");
+  return FB_OK;
+}
+
+extern "C" int fb_frame_pose_set(fb_ctx* c, int s, int slot, const float pose[7]) {
+  CHECK_CTX(c);
+  int rc = check_slot(c, s, slot);
+  if (rc) return rc;
+  if (!pose) FB_FAIL(c, FB_E_ARG, "null pose");
+  memcpy(&c->h_pose[((size_t)s * c->n_slots + slot) * 7], pose, sizeof(float) * 7);
+  return FB_OK;
+}
+
+extern "C" int fb_frame_set(fb_ctx* c, int s, int slot, const uint8_t* gray, int pitch,
+                            const float pose[7]) {
+  CHECK_CTX(c);
+  int rc = check_slot(c, s, slot);
+  if (rc) return rc;
+  if (!gray || pitch < c->W) FB_FAIL(c, FB_E_ARG, "fb_frame_set: null image or pitch < width");
+  rc = fb_frame_pose_set(c, s, slot, pose);
+  if (rc) return rc;
+  ProfScope ps(c, FB_PROF_UPLOAD);
+  uint8_t* dst = c->imgs + ((size_t)s * c->n_slots + slot) * (size_t)c->W * c->H;
+  if (pitch == c->W) {
+    FB_CUDA(c, cudaMemcpyAsync(dst, gray, (size_t)c->W * c->H, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    FB_CUDA(c, cudaMemcpy2DAsync(dst, c->W, gray, pitch, c->W, c->H, cudaMemcpyHostToDevice, c->stream));
+  }
+  return FB_OK;
+}
+
+extern "C" int fb_pool_reserve(fb_ctx* c, int n) {
+  CHECK_CTX(c);
+  if (n < 0) FB_FAIL(c, FB_E_ARG, "fb_pool_reserve: negative size");
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->pool);
+  c->pool = nullptr;
+  c->pool_n = 0;
+  if (n) {
+    FB_CUDA(c, dalloc(&c->pool, (size_t)n * c->W * c->H));
+    c->pool_n = n;
+  }
+  return FB_OK;
+}
+
+extern "C" int fb_pool_upload(fb_ctx* c, int idx, const uint8_t* gray, int pitch) {
+  CHECK_CTX(c);
+  if (idx < 0 || idx >= c->pool_n || !gray || pitch < c->W) FB_FAIL(c, FB_E_ARG, "fb_pool_upload: bad argument");
+  FB_CUDA(c, cudaMemcpy2DAsync(c->pool + (size_t)idx * c->W * c->H, c->W, gray, pitch, c->W, c->H, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_frame_from_pool(fb_ctx* c, int s, int slot, int idx, const float pose[7]) {
+  CHECK_CTX(c);
+  int rc = check_slot(c, s, slot);
+  if (rc) return rc;
+  if (idx < 0 || idx >= c->pool_n) FB_FAIL(c, FB_E_ARG, "fb_frame_from_pool: bad pool index");
+  rc = fb_frame_pose_set(c, s, slot, pose);
+  if (rc) return rc;
+  const size_t fsz = (size_t)c->W * c->H;
+  FB_CUDA(c, cudaMemcpyAsync(c->imgs + ((size_t)s * c->n_slots + slot) * fsz, c->pool + (size_t)idx * fsz, fsz, cudaMemcpyDeviceToDevice, c->stream));
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------ features
+extern "C" int fb_features_set(fb_ctx* c, int s, int N, const float* u_ref, const int32_t* ref_slot,
+                               const float* mu, const float* var, const int32_t* dropouts,
+                               const int32_t* alive) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (N < 0 || N > c->maxF) FB_FAIL(c, FB_E_NOMEM, "fb_features_set: N exceeds context capacity");
+  if (N > 0 && (!u_ref || !ref_slot || !mu || !var)) FB_FAIL(c, FB_E_ARG, "fb_features_set: null input");
+  for (int f = 0; f < N; ++f)
+    if (ref_slot[f] < 0 || ref_slot[f] >= c->n_slots) FB_FAIL(c, FB_E_ARG, "fb_features_set: ref_slot out of range");
+  const size_t fb = (size_t)s * c->maxF;
+  cudaStream_t st = c->stream;
+  std::vector<int32_t> ones;
+  if (N) {
+    FB_CUDA(c, cudaMemcpyAsync(c->f_uref + fb, u_ref, sizeof(float2) * N, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(c->f_ref + fb, ref_slot, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(c->f_mu + fb, mu, sizeof(float) * N, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(c->f_var + fb, var, sizeof(float) * N, cudaMemcpyHostToDevice, st));
+    if (dropouts) FB_CUDA(c, cudaMemcpyAsync(c->f_drop + fb, dropouts, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    else FB_CUDA(c, cudaMemsetAsync(c->f_drop + fb, 0, sizeof(int32_t) * N, st));
+    if (alive) {
+      FB_CUDA(c, cudaMemcpyAsync(c->f_alive + fb, alive, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    } else {
+      ones.assign(N, 1);
+      FB_CUDA(c, cudaMemcpyAsync(c->f_alive + fb, ones.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    }
+    FB_CUDA(c, cudaMemsetAsync(c->f_status + fb, 0, sizeof(int32_t) * N, st));
+    FB_CUDA(c, cudaMemsetAsync(c->f_ucmp + fb, 0xff, sizeof(float2) * N, st));
+  }
+  c->hF[s] = N;
+  FB_CUDA(c, cudaMemcpyAsync(c->nF + s, &c->hF[s], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  FB_CUDA(c, cudaStreamSynchronize(st));
+  return FB_OK;
+}
+
+extern "C" int fb_features_get(fb_ctx* c, int s, float* mu, float* var, int32_t* dropouts,
+                               int32_t* alive, int32_t* status, float* u_cmp) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  const int N = c->hF[s];
+  const size_t fb = (size_t)s * c->maxF;
+  cudaStream_t st = c->stream;
+  if (N) {
+    if (mu) FB_CUDA(c, cudaMemcpyAsync(mu, c->f_mu + fb, sizeof(float) * N, cudaMemcpyDeviceToHost, st));
+    if (var) FB_CUDA(c, cudaMemcpyAsync(var, c->f_var + fb, sizeof(float) * N, cudaMemcpyDeviceToHost, st));
+    if (dropouts) FB_CUDA(c, cudaMemcpyAsync(dropouts, c->f_drop + fb, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+    if (alive) FB_CUDA(c, cudaMemcpyAsync(alive, c->f_alive + fb, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+    if (status) FB_CUDA(c, cudaMemcpyAsync(status, c->f_status + fb, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+    if (u_cmp) FB_CUDA(c, cudaMemcpyAsync(u_cmp, c->f_ucmp + fb, sizeof(float2) * N, cudaMemcpyDeviceToHost, st));
+  }
+  FB_CUDA(c, cudaStreamSynchronize(st));
+  return FB_OK;
+}
+
+static int upload_geometry(fb_ctx* c, const int32_t* cmp_slot) {
+  const size_t np = (size_t)c->S * c->n_slots * 7;
+  FB_CUDA(c, cudaMemcpyAsync(c->d_pose, c->h_pose.data(), sizeof(float) * np, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaMemcpyAsync(c->d_cmp, cmp_slot, sizeof(int32_t) * c->S, cudaMemcpyHostToDevice, c->stream));
+  k_epi_geometry<<<c->S, std::max(32, c->n_slots), 0, c->stream>>>(c->d_pose, c->d_K, c->d_cmp, c->n_slots, c->d_geo);
+  c->launches++;
+  FB_CUDA(c, cudaGetLastError());
+  return FB_OK;
+}
+
+extern "C" int fb_idepth_update(fb_ctx* c, const int32_t* cmp_slot) {
+  CHECK_CTX(c);
+  if (!cmp_slot) FB_FAIL(c, FB_E_ARG, "fb_idepth_update: null cmp_slot");
+  int maxf = 0;
+  for (int s = 0; s < c->S; ++s) {
+    if (cmp_slot[s] >= c->n_slots) FB_FAIL(c, FB_E_ARG, "fb_idepth_update: cmp_slot out of range");
+    if (cmp_slot[s] >= 0) maxf = std::max(maxf, c->hF[s]);
+  }
+  ProfScope ps(c, FB_PROF_IDEPTH);
+  int rc = upload_geometry(c, cmp_slot);
+  if (rc) return rc;
+  FB_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(int32_t) * c->S * FB_NUM_COUNTERS, c->stream));
+  if (maxf == 0) return FB_OK;
+  EpiArgs a;
+  a.imgs = c->imgs; a.geo = c->d_geo; a.cmp_slot = c->d_cmp; a.u_ref = c->f_uref;
+  a.ref_slot = c->f_ref; a.mu = c->f_mu; a.var = c->f_var; a.dropouts = c->f_drop;
+  a.alive = c->f_alive; a.status = c->f_status; a.u_cmp = c->f_ucmp; a.nF = c->nF;
+  a.counters = c->counters; a.W = c->W; a.H = c->H; a.n_slots = c->n_slots; a.maxF = c->maxF;
+  a.p = c->epi;
+  const int wpb = 8;
+  const size_t smem = sizeof(float) * wpb * (2 * c->epi.max_search_px + 2 * FB_MAX_WIN + 2);
+  const dim3 grid(fb_div_up(maxf, wpb), c->S);
+  k_epipolar_search<<<grid, wpb * 32, smem, c->stream>>>(a);
+  c->launches++;
+  FB_CUDA(c, cudaGetLastError());
+  return FB_OK;
+}
+
+extern "C" int fb_idepth_counters(fb_ctx* c, int s, int32_t counters[FB_NUM_COUNTERS]) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  FB_CUDA(c, cudaMemcpyAsync(counters, c->counters + s * FB_NUM_COUNTERS, sizeof(int32_t) * FB_NUM_COUNTERS, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_project_features(fb_ctx* c, int s, int cur_slot, float* u_cur, float* mu_cur,
+                                   float* var_cur, int32_t* valid) {
+  CHECK_CTX(c);
+  int rc = check_slot(c, s, cur_slot);
+  if (rc) return rc;
+  const int N = c->hF[s];
+  if (N == 0) return FB_OK;
+  std::vector<int32_t> cmp(c->S, -1);
+  cmp[s] = cur_slot;
+  rc = upload_geometry(c, cmp.data());
+  if (rc) return rc;
+  float2* d_u = nullptr; float *d_mu = nullptr, *d_var = nullptr; int32_t* d_valid = nullptr;
+  FB_CUDA(c, dalloc(&d_u, N)); FB_CUDA(c, dalloc(&d_mu, N)); FB_CUDA(c, dalloc(&d_var, N)); FB_CUDA(c, dalloc(&d_valid, N));
+  const size_t fb = (size_t)s * c->maxF;
+  k_project_features<<<fb_div_up(N, 256), 256, 0, c->stream>>>(c->d_geo, c->n_slots, s, N, c->W, c->H, c->f_uref + fb, c->f_ref + fb, c->f_mu + fb, c->f_var + fb, c->f_alive + fb, d_u, d_mu, d_var, d_valid);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && u_cur) e = cudaMemcpyAsync(u_cur, d_u, sizeof(float2) * N, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess && mu_cur) e = cudaMemcpyAsync(mu_cur, d_mu, sizeof(float) * N, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess && var_cur) e = cudaMemcpyAsync(var_cur, d_var, sizeof(float) * N, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess && valid) e = cudaMemcpyAsync(valid, d_valid, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_u); cudaFree(d_mu); cudaFree(d_var); cudaFree(d_valid);
+  FB_CUDA(c, e);
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------ assembly
+extern "C" int fb_graph_bind_features(fb_ctx* c, int s, const int32_t* vertex_feature) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (!vertex_feature) FB_FAIL(c, FB_E_ARG, "fb_graph_bind_features: null input");
+  const int V = c->hV[s];
+  FB_CUDA(c, cudaMemcpyAsync(c->vfeat + (size_t)s * c->maxV, vertex_feature, sizeof(int32_t) * V, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_graph_data_from_features(fb_ctx* c, int adaptive) {
+  CHECK_CTX(c);
+  ProfScope ps(c, FB_PROF_ASSEMBLY);
+  const dim3 grid(fb_div_up(c->maxV, 256), c->S);
+  k_data_from_features<<<grid, 256, 0, c->stream>>>(c->z, c->wt, c->vfeat, c->nV, c->maxV, c->f_mu, c->f_var, c->f_alive, c->nF, c->maxF, adaptive);
+  c->launches++;
+  FB_CUDA(c, cudaGetLastError());
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------ interpolation
+extern "C" int fb_mesh_set(fb_ctx* c, int s, int T, const int32_t* tri) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (T < 0 || T > c->maxT) FB_FAIL(c, FB_E_NOMEM, "fb_mesh_set: T exceeds capacity (2*max_vertices)");
+  if (T > 0 && !tri) FB_FAIL(c, FB_E_ARG, "fb_mesh_set: null triangles");
+  const int V = c->hV[s];
+  for (int k = 0; k < 3 * T; ++k)
+    if (tri[k] < 0 || tri[k] >= V) FB_FAIL(c, FB_E_ARG, "fb_mesh_set: vertex id out of range");
+  if (T) FB_CUDA(c, cudaMemcpyAsync(c->tri + (size_t)s * c->maxT * 3, tri, sizeof(int32_t) * 3 * T, cudaMemcpyHostToDevice, c->stream));
+  c->hT[s] = T;
+  FB_CUDA(c, cudaMemcpyAsync(c->nT + s, &c->hT[s], sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_interpolate(fb_ctx* c, int s, const fb_tri_filter_params* filter,
+                              float* idepthmap, uint8_t* tri_valid) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  const int T = c->hT[s];
+  const size_t npx = (size_t)c->W * c->H;
+  const size_t vb = (size_t)s * c->maxV;
+  int32_t* owner = c->owner + (size_t)s * npx;
+  float* map = c->idmap + (size_t)s * npx;
+  uint8_t* valid = c->tri_valid + (size_t)s * c->maxT;
+  const int32_t* tri = c->tri + (size_t)s * c->maxT * 3;
+  {
+    ProfScope ps(c, FB_PROF_INTERP);
+    FB_CUDA(c, cudaMemsetAsync(owner, 0x7f, sizeof(int32_t) * npx, c->stream));
+    if (T) {
+      fb_tri_filter_params fp;
+      fb_default_tri_filter_params(&fp);
+      float cos_thresh = 0.f;
+      if (filter) {
+        fp = *filter;
+        cos_thresh = (float)cos((double)fp.oblique_normal_thresh);
+      }
+      k_tri_validity<<<fb_div_up(T, 256), 256, 0, c->stream>>>(c->W, c->d_K + 9 * s, c->vpos + vb, c->x + vb, T, tri, fp, cos_thresh, filter ? 1 : 0, valid);
+      k_raster_claim<<<fb_div_up(T * 32, 256), 256, 0, c->stream>>>(c->W, c->H, c->vpos + vb, T, tri, valid, owner);
+      c->launches += 2;
+    }
+    k_raster_shade<<<fb_div_up((int)npx, 256), 256, 0, c->stream>>>(c->W, c->H, c->vpos + vb, c->x + vb, tri, owner, map);
+    c->launches++;
+    FB_CUDA(c, cudaGetLastError());
+  }
+  if (idepthmap) FB_CUDA(c, cudaMemcpyAsync(idepthmap, map, sizeof(float) * npx, cudaMemcpyDeviceToHost, c->stream));
+  if (tri_valid && T) FB_CUDA(c, cudaMemcpyAsync(tri_valid, valid, T, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------ profiling
+extern "C" int fb_profile_enable(fb_ctx* c, int enable) {
+  CHECK_CTX(c);
+  c->prof = enable != 0;
+  return FB_OK;
+}
+
+extern "C" int fb_profile_reset(fb_ctx* c) {
+  CHECK_CTX(c);
+  for (int k = 0; k < FB_PROF_NUM; ++k) {
+    prof_fold(c, k);
+    c->sec[k].total_ms = 0.0;
+    c->sec[k].calls = 0;
+    c->sec[k].launches = 0;
+  }
+  return FB_OK;
+}
+
+extern "C" int fb_profile_get(fb_ctx* c, int section, float* total_ms, int64_t* calls, int64_t* launches) {
+  CHECK_CTX(c);
+  if (section < 0 || section >= FB_PROF_NUM) FB_FAIL(c, FB_E_ARG, "fb_profile_get: bad section");
+  prof_fold(c, section);
+  if (total_ms) *total_ms = (float)c->sec[section].total_ms;
+  if (calls) *calls = c->sec[section].calls;
+  if (launches) *launches = c->sec[section].launches;
+  return FB_OK;
+}
+
+extern "C" int64_t fb_launch_count(const fb_ctx* c) { return c ? c->launches : 0; }

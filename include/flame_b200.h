@@ -1,0 +1,213 @@
+/*
+ * flame_b200.h -- C-ABI of the B200-native FLaME hot path (libflame_b200.so).
+ *
+ * This is the drop-in boundary below `flame::Flame` (include/flame/flame.h): plain pointers and
+ * sizes, no C++ / torch / OpenCV / Eigen types.  Every entry point names the reference interface
+ * it stands in for.  The reference tree (/root/reference) is only the ROS wrapper; the functions
+ * replaced here live in the external `flame` core library that the wrapper links
+ * (/root/reference/CMakeLists.txt:57, src/CMakeLists.txt:11), so citations give the wrapper's call
+ * site / parameter source for each one.
+ *
+ * A context owns a BATCH of `n_streams` independent camera streams of identical image size.  All
+ * compute entry points process every stream of the batch in one launch (block-diagonal layout);
+ * n_streams = 1 is the reference's single-camera use.  All work is enqueued on one CUDA stream
+ * (the caller's, or one the context creates); calls return after enqueueing unless documented as
+ * synchronising.  Host pointers are caller-owned and may be pageable (pinned is faster).
+ *
+ * Return values: 0 = OK, negative = error (FB_E_*); fb_last_error() returns a description.
+ * There is NO CPU fallback: without a CUDA device fb_create() fails.
+ */
+#ifndef FLAME_B200_H_
+#define FLAME_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_OK 0
+#define FB_E_ARG (-1)     /* bad argument / out of range */
+#define FB_E_CUDA (-2)    /* CUDA runtime error (see fb_last_error) */
+#define FB_E_STATE (-3)   /* call sequence error (e.g. solve before graph_set) */
+#define FB_E_NOMEM (-4)   /* capacity exceeded / allocation failure */
+
+typedef struct fb_ctx fb_ctx;
+
+/* flame::Params::rparams {data_factor, step_x, step_q, theta}
+ * (/root/reference/src/flame_nodelet.cc:256-259; defaults cfg/flame_nodelet.yaml:86-89). */
+typedef struct {
+  float data_factor; /* lambda, 0.15  */
+  float step_x;      /* tau,    0.001 */
+  float step_q;      /* sigma,  125   */
+  float theta;       /* theta,  0.25  */
+  float x_min;       /* box on inverse depth, 0  */
+  float x_max;       /* 10 */
+} fb_nltgv2_params;
+
+/* flame::Params::{fparams,zparams,max_dropouts}
+ * (/root/reference/src/flame_nodelet.cc:227,237-245; defaults cfg/flame_nodelet.yaml:69-75),
+ * plus the thresholds the reference does not expose (documented in DESIGN.md). */
+typedef struct {
+  int win_size;            /* 5, odd, <= 15 */
+  float min_grad_mag;      /* 5.0 */
+  float epipolar_line_var; /* 4.0 */
+  int max_dropouts;        /* 5 */
+  float search_sigma;      /* 2.0 */
+  float max_cost;          /* 400 (mean squared residual per patch sample) */
+  float ambiguity_ratio;   /* 1.5 */
+  int ambiguity_radius;    /* 2 */
+  float pixel_noise_var;   /* 4.0 */
+  float meas_var_max;      /* 1.0 */
+  float idepth_min;        /* 0.0 */
+  float idepth_max;        /* 10.0 */
+  int max_search_px;       /* 64, <= 256 */
+  float min_parallax;      /* 0.5 px per unit inverse depth */
+} fb_epi_params;
+
+/* Feature status codes; names follow the reference's failure counters
+ * (/root/reference/src/utils.cc:124-129, msg/FlameStats.msg:14-19). */
+enum {
+  FB_SUCCESS = 0,
+  FB_FAIL_REF_PATCH_GRADIENT = 1,
+  FB_FAIL_AMBIGUOUS_MATCH = 2,
+  FB_FAIL_MAX_COST = 3,
+  FB_FAIL_MAX_VAR = 4,
+  FB_FAIL_MAX_DROPOUTS = 5,
+  FB_FAIL_OUT_OF_IMAGE = 6,
+  FB_NO_PARALLAX = 7,
+  FB_NUM_COUNTERS = 8,
+  FB_SKIPPED = 8
+};
+
+/* Output filters of getFilteredInverseDepthMap (/root/reference/src/flame_nodelet.cc:182-206). */
+typedef struct {
+  int do_oblique;
+  float oblique_normal_thresh;
+  float oblique_idepth_diff_factor;
+  float oblique_idepth_diff_abs;
+  int do_edge_length;
+  float edge_length_thresh;
+  int do_idepth;
+  float min_triangle_idepth;
+} fb_tri_filter_params;
+
+/* ------------------------------------------------------------------ lifecycle
+ * Stands in for flame::Flame::Flame(width, height, K, Kinv, params)
+ * (/root/reference/src/flame_nodelet.cc:523-527).  Capacities are per stream.
+ * cuda_stream: a cudaStream_t to enqueue on, or NULL to create one. */
+fb_ctx* fb_create(int device, int n_streams, int width, int height, int n_slots,
+                  int max_features, int max_vertices, int max_edges, void* cuda_stream);
+void fb_destroy(fb_ctx* ctx);
+const char* fb_last_error(const fb_ctx* ctx); /* ctx may be NULL: error of the last failed fb_create */
+int fb_sync(fb_ctx* ctx);                     /* cudaStreamSynchronize */
+int fb_version(void);
+
+/* Pinned host memory for callers that want fast, truly asynchronous transfers. */
+void* fb_host_alloc(size_t bytes);
+void fb_host_free(void* p);
+
+int fb_set_intrinsics(fb_ctx* ctx, int stream, const float K[9]); /* row-major 3x3 pinhole */
+int fb_set_epi_params(fb_ctx* ctx, const fb_epi_params* p);
+void fb_default_epi_params(fb_epi_params* p);
+void fb_default_nltgv2_params(fb_nltgv2_params* p);
+void fb_default_tri_filter_params(fb_tri_filter_params* p);
+
+/* ------------------------------------------------------------------ NLTGV2-L1 solver
+ * Stands in for flame::optimizers::nltgv2_l1_graph_regularizer (graph types + step()), driven
+ * from inside flame::Flame::update (/root/reference/src/flame_nodelet.cc:634). */
+
+/* Topology (re)upload for one stream: V vertices at pixel positions pos_xy[2V], E canonical edges
+ * edge_ij[2E] (i<j, sorted by (i,j); i = source, j = target), per-edge weights. Builds the CSR
+ * incidence (ascending edge id per vertex). State is reset to zero; call fb_graph_state_set or
+ * fb_graph_data_set (+ init) afterwards. */
+int fb_graph_set(fb_ctx* ctx, int stream, int V, int E, const float* pos_xy,
+                 const int32_t* edge_ij, const float* alpha, const float* beta);
+/* Data term z[V] and data weight wt[V] (NULL = all ones). */
+int fb_graph_data_set(fb_ctx* ctx, int stream, const float* z, const float* wt);
+/* Warm start. x[V], w[2V] (w1,w2 interleaved), q[3E] (q1,q2,q3 interleaved).
+ * NULL x => x = z; NULL w/q => zeros.  The extragradient point is reset to (x, w). */
+int fb_graph_state_set(fb_ctx* ctx, int stream, const float* x, const float* w, const float* q);
+/* Copies state out (synchronises). Any pointer may be NULL. xbar[3V] = (xb,w1b,w2b) interleaved. */
+int fb_graph_state_get(fb_ctx* ctx, int stream, float* x, float* w, float* q, float* xbar);
+/* x of every stream into x_all[n_streams * max_vertices] (stream-major); synchronises. */
+int fb_graph_x_get_all(fb_ctx* ctx, float* x_all);
+/* `iters` Chambolle-Pock iterations on every stream's graph (one batched launch sequence).
+ * variant: 0 = auto, 1 = streaming (two kernels per iteration, any size),
+ *          2 = persistent thread-block-cluster kernel (graph resident in shared memory). */
+int fb_nltgv2_solve(fb_ctx* ctx, int iters, const fb_nltgv2_params* p, int variant);
+/* nltgv2_total_{smoothness,data}_cost (/root/reference/src/utils.cc:131-136); synchronises. */
+int fb_costs(fb_ctx* ctx, int stream, float data_factor, double* smoothness, double* data);
+
+/* ------------------------------------------------------------------ epipolar inverse-depth update
+ * Stands in for flame::stereo::inverse_depth_filter::{search,update} + InverseDepthMeasModel,
+ * i.e. the `update_idepths` stage of flame::Flame::update (/root/reference/src/utils.cc:150). */
+
+/* Upload one frame (gray uint8, `pitch` bytes per row) and its camera-in-world pose
+ * (qx,qy,qz,qw,tx,ty,tz; RDF optical frame, /root/reference/README.md:168-171) into a slot. */
+int fb_frame_set(fb_ctx* ctx, int stream, int slot, const uint8_t* gray, int pitch,
+                 const float pose[7]);
+/* Pose-only update of a slot (flame::Flame::updatePoseFramePoses,
+ * /root/reference/src/flame_nodelet.cc:474). */
+int fb_frame_pose_set(fb_ctx* ctx, int stream, int slot, const float pose[7]);
+/* Device-resident frame pool (bench `value` leg: inputs already in HBM before timing starts):
+ * fb_pool_upload stores a frame in pool entry `idx`; fb_frame_from_pool copies it device-to-device
+ * into a slot. */
+int fb_pool_reserve(fb_ctx* ctx, int n_entries);
+int fb_pool_upload(fb_ctx* ctx, int idx, const uint8_t* gray, int pitch);
+int fb_frame_from_pool(fb_ctx* ctx, int stream, int slot, int idx, const float pose[7]);
+
+/* Feature table of one stream (device resident). NULL dropouts => 0, NULL alive => 1. */
+int fb_features_set(fb_ctx* ctx, int stream, int N, const float* u_ref, const int32_t* ref_slot,
+                    const float* mu, const float* var, const int32_t* dropouts,
+                    const int32_t* alive);
+/* Copies out (synchronises); any pointer may be NULL. Backs flame::Flame::getRawIDepths
+ * (/root/reference/src/flame_nodelet.cc:721-723). */
+int fb_features_get(fb_ctx* ctx, int stream, float* mu, float* var, int32_t* dropouts,
+                    int32_t* alive, int32_t* status, float* u_cmp);
+/* One epipolar update of every live feature of every stream against that stream's comparison
+ * slot cmp_slot[s] (cmp_slot[s] < 0 skips stream s). */
+int fb_idepth_update(fb_ctx* ctx, const int32_t* cmp_slot);
+/* Status histogram of the last update of `stream` (synchronises):
+ * num_idepth_updates, num_fail_* (/root/reference/src/utils.cc:124-129). */
+int fb_idepth_counters(fb_ctx* ctx, int stream, int32_t counters[FB_NUM_COUNTERS]);
+/* Project live features into the frame held by cur_slot (project_features stage,
+ * /root/reference/src/utils.cc:151). Outputs are host arrays [N]; synchronises. */
+int fb_project_features(fb_ctx* ctx, int stream, int cur_slot, float* u_cur, float* mu_cur,
+                        float* var_cur, int32_t* valid);
+
+/* ------------------------------------------------------------------ data-term assembly (sync_graph)
+ * vertex_feature[V]: index of the feature that backs each vertex of `stream`'s graph. */
+int fb_graph_bind_features(fb_ctx* ctx, int stream, const int32_t* vertex_feature);
+/* For every stream: z[v] = mu[feature(v)], wt[v] = adaptive ? 1/var : 1
+ * (regularization/nltgv2/adaptive_data_weights, /root/reference/cfg/flame_nodelet.yaml:82).
+ * Vertices whose feature is dead keep their previous data term with weight 0. */
+int fb_graph_data_from_features(fb_ctx* ctx, int adaptive_weights);
+
+/* ------------------------------------------------------------------ mesh -> dense inverse depth
+ * Stands in for the `interpolate` stage + flame::Flame::getInverseDepthMap /
+ * getFilteredInverseDepthMap (/root/reference/src/flame_nodelet.cc:682-688). */
+int fb_mesh_set(fb_ctx* ctx, int stream, int T, const int32_t* tri /*[3T] vertex ids*/);
+/* Rasterise the current x of `stream` over its mesh. filter = NULL: no triangle filtering.
+ * idepthmap [H*W] host (NaN = no depth), tri_valid [T] host (may be NULL); synchronises. */
+int fb_interpolate(fb_ctx* ctx, int stream, const fb_tri_filter_params* filter, float* idepthmap,
+                   uint8_t* tri_valid);
+
+/* ------------------------------------------------------------------ profiling (CUDA events)
+ * Sections: 0 = nltgv2 solve, 1 = idepth update, 2 = frame upload, 3 = data assembly,
+ * 4 = interpolate. Times are accumulated between fb_profile_reset calls. */
+enum { FB_PROF_SOLVE = 0, FB_PROF_IDEPTH = 1, FB_PROF_UPLOAD = 2, FB_PROF_ASSEMBLY = 3,
+       FB_PROF_INTERP = 4, FB_PROF_NUM = 5 };
+int fb_profile_enable(fb_ctx* ctx, int enable);
+int fb_profile_reset(fb_ctx* ctx);
+/* Synchronises; total_ms = sum of device time of the section, launches = kernels launched. */
+int fb_profile_get(fb_ctx* ctx, int section, float* total_ms, int64_t* calls, int64_t* launches);
+/* Total kernels launched by this context since creation. */
+int64_t fb_launch_count(const fb_ctx* ctx);
+/* Which solver variant the last fb_nltgv2_solve used (1 or 2). */
+int fb_last_solver_variant(const fb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAME_B200_H_ */
