@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py -- FLaME hot path on B200: frames/s (and solver iterations/s) on synthetic 640x480 streams.
+
+A "step" is one frame of every stream of the batch through the hot path:
+    epipolar inverse-depth update of ~5k features  ->  data-term assembly  ->  50 NLTGV2-L1
+    primal-dual iterations on the 5k-vertex Delaunay graph (warm-started), every 5th step a new
+    poseframe re-initialises the feature filters (flame_ros_b200/workload.py).
+
+  python bench.py --gpus N --steps K --warmup W            GPU arm (one process per GPU under torchrun)
+  python bench.py --impl reference ...                     CPU arm: the oracle restatement of the
+                                                           reference's CPU algorithm on all host cores
+
+Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with inputs resident in HBM (CUDA-event
+timed, L2 flushed between steps); `e2e` = the same through the C-ABI with HOST buffers (pinned H2D of
+each frame, D2H of the vertex inverse depths, host wall clock per step).  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from flame_ros_b200 import workload as WL  # noqa: E402
+
+METRIC = "frames_per_second"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=8, help="independent streams per GPU (batched launch)")
+    ap.add_argument("--config", default="C2", choices=list(WL.CONFIGS))
+    ap.add_argument("--variant", type=int, default=0, help="solver variant: 0 auto, 1 streaming, 2 cluster")
+    ap.add_argument("--no-single", action="store_true", help="skip the extra single-stream measurement")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for s in self.samples if len(s) >= 6 for k in range(4) if s[2 + k] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+class GpuRun:
+    """One context with S streams of the workload; runs steps in `resident` or `e2e` mode."""
+
+    def __init__(self, capi, datas, device, cuda_stream, variant):
+        d0 = datas[0]
+        self.capi, self.datas, self.S, self.variant = capi, datas, len(datas), variant
+        V = max(d.V for d in datas)
+        E = max(d.E for d in datas)
+        self.ctx = capi.Context(self.S, d0.W, d0.H, WL.N_SLOTS, V, V, E, device=device, cuda_stream=cuda_stream)
+        self.params = capi.default_nltgv2_params()
+        self.iters = d0.iters
+        ctx = self.ctx
+        ctx.pool_reserve(self.S * WL.POOL_FRAMES)
+        for s, d in enumerate(datas):
+            ctx.set_intrinsics(s, d.K)
+            for k in range(WL.POOL_FRAMES):
+                ctx.pool_upload(s * WL.POOL_FRAMES + k, d.frames[k])
+            ctx.graph_set(s, d.u_ref, d.edges, d.alpha, d.beta)
+            z0 = np.full(d.V, WL.MU0, np.float32)
+            ctx.graph_data_set(s, z0)
+            ctx.graph_state_set(s)
+            ctx.graph_bind_features(s, np.arange(d.V, dtype=np.int32))
+            ctx.features_set(s, d.u_ref, np.zeros(d.V, np.int32), z0, np.full(d.V, WL.VAR0, np.float32))
+        # pinned staging for the e2e leg: one frame per stream + the vertex idepths coming back
+        self.h_frames = capi.PinnedBuffer((self.S, d0.H, d0.W), np.uint8)
+        self.h_ref = capi.PinnedBuffer((self.S, d0.H, d0.W), np.uint8)
+        self.h_x = capi.PinnedBuffer((self.S, V), np.float32)
+        self.maxV = V
+        self.cmp = np.full(self.S, WL.CMP_SLOT, np.int32)
+        ctx.sync()
+
+    def close(self):
+        self.ctx.sync()
+        for b in (self.h_frames, self.h_ref, self.h_x):
+            b.free()
+        self.ctx.close()
+
+    def step(self, k, e2e):
+        ctx = self.ctx
+        newpf, ref_slot, ref_idx, cmp_idx = WL.schedule(k)
+        for s, d in enumerate(self.datas):
+            if e2e:
+                if newpf:
+                    np.copyto(self.h_ref.array[s], d.frames[ref_idx])
+                    ctx.frame_set(s, ref_slot, self.h_ref.array[s], d.poses[ref_idx])
+                np.copyto(self.h_frames.array[s], d.frames[cmp_idx])     # "camera delivers a frame"
+                ctx.frame_set(s, WL.CMP_SLOT, self.h_frames.array[s], d.poses[cmp_idx])
+            else:
+                if newpf:
+                    ctx.frame_from_pool(s, ref_slot, s * WL.POOL_FRAMES + ref_idx, d.poses[ref_idx])
+                ctx.frame_from_pool(s, WL.CMP_SLOT, s * WL.POOL_FRAMES + cmp_idx, d.poses[cmp_idx])
+        if newpf:
+            ctx.features_reinit(ref_slot, WL.MU0, WL.VAR0)
+        ctx.idepth_update(self.cmp)
+        ctx.graph_data_from_features(False)
+        ctx.nltgv2_solve(self.iters, self.params, self.variant)
+        if e2e:
+            ctx.graph_x_get_all(self.h_x.array)   # D2H of the mesh vertex inverse depths; synchronises
+
+    def bytes_per_step(self):
+        d = self.datas[0]
+        h2d = self.S * (d.W * d.H + 28) * (1.0 + 1.0 / WL.EPOCH)
+        d2h = self.S * self.maxV * 4
+        return int(h2d), int(d2h)
+
+
+def run_gpu_leg(torch, run, steps, warmup, flush_buf, e2e, barrier):
+    """Returns (seconds over `steps` timed steps, launches in the timed region, solver ms, solver calls)."""
+    ctx = run.ctx
+    for k in range(warmup):
+        run.step(k, e2e)
+    ctx.sync()
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    barrier()
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count()
+    total = 0.0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        k = warmup + i
+        flush_buf.zero_()                      # evict L2 between timed steps (outside the timed bracket)
+        torch.cuda.synchronize()
+        if e2e:
+            t0 = time.perf_counter()
+            run.step(k, True)                  # ends with a synchronising D2H
+            total += time.perf_counter() - t0
+        else:
+            ev[i][0].record()
+            run.step(k, False)
+            ev[i][1].record()
+    torch.cuda.synchronize()
+    barrier()
+    if not e2e:
+        total = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    launches = ctx.launch_count() - l0
+    ms, calls, _ = ctx.profile_get(run.capi.PROF_SOLVE)
+    ctx.profile_enable(False)
+    return total, launches, ms, calls
+
+
+def gpu_main(args):
+    import torch
+    import torch.distributed as dist
+    from flame_ros_b200 import capi
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    capi.load_library()
+    S = args.streams
+    datas = [WL.StreamData(args.config, seed=rank * S + s) for s in range(S)]
+    stream_ptr = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    peak, peak_src = peaks()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    run = GpuRun(capi, datas, local_rank, stream_ptr, args.variant)
+    t_res, launches, solve_ms, solve_calls = run_gpu_leg(torch, run, args.steps, args.warmup, flush, False, barrier)
+    variant_used = run.ctx.last_solver_variant()
+    t_e2e, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, True, barrier)
+    h2d, d2h = run.bytes_per_step()
+    alg_bytes = sum(d.algorithmic_bytes_per_iter() for d in datas) * datas[0].iters
+    iters = datas[0].iters
+    run.close()
+    clocks = sampler.stop() if sampler else None
+
+    single = None
+    if not args.no_single and S > 1:
+        run1 = GpuRun(capi, datas[:1], local_rank, stream_ptr, args.variant)
+        t1, _, ms1, c1 = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, False, barrier)
+        t1e, _, _, _ = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, True, barrier)
+        run1.close()
+        t1, t1e = max_over_ranks(t1), max_over_ranks(t1e)
+        single = {"streams_per_gpu": 1, "value": world * args.steps / t1, "e2e": world * args.steps / t1e,
+                  "ms_per_step": 1e3 * t1 / args.steps, "unit": UNIT,
+                  "solver_us_per_frame": 1e3 * ms1 / max(c1, 1),
+                  "roofline_frac": (datas[0].algorithmic_bytes_per_iter() * iters / (1e6 * ms1 / max(c1, 1))) / peak}
+
+    t_res, t_e2e = max_over_ranks(t_res), max_over_ranks(t_e2e)
+    launches_all = int(sum_over_ranks(launches))
+    frames = world * S * args.steps
+    solve_ms_per_launch = solve_ms / max(solve_calls, 1)
+    achieved = alg_bytes / (solve_ms_per_launch * 1e-3) / 1e9 if solve_ms_per_launch > 0 else 0.0
+
+    out = None
+    if rank == 0:
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("solver_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": METRIC, "value": frames / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s (BASELINE configs[1]): synthetic %dx%d stream, %d features = %d Delaunay vertices, "
+                                   "%d PD iters/frame; x %d independent streams per GPU, one batched launch"
+                                   % (args.config, datas[0].W, datas[0].H, datas[0].V, datas[0].V, iters, S),
+                       "streams_per_gpu": S, "vertices": datas[0].V, "edges": datas[0].E, "pd_iters": iters,
+                       "solver_variant": {1: "streaming (2 kernels/iter, CUDA graph)", 2: "persistent cluster (DSMEM)"}.get(variant_used),
+                       "l2": "flushed between timed steps (256 MiB memset outside the timed bracket)",
+                       "timing": "value: CUDA events per step on the launching stream; e2e: host clock per step incl. H2D/D2H"},
+            "solver_iters_per_second": frames * iters / t_res,
+            "e2e": {"value": frames / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": launches_all,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_nltgv2_cluster" if variant_used == 2 else "k_dual_edges+k_primal_vertices",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_us": 1e3 * solve_ms_per_launch,
+                         "note": "algorithmic = (40E+64V) B/iter x iters x streams (SURVEY 8d); the cluster solver keeps the "
+                                 "graph in shared memory/registers across iterations, so achieved may exceed the HBM peak "
+                                 "while DRAM traffic (`traffic`) is ~1/iters of it"},
+        }
+        if single:
+            out["single_stream"] = single
+    if rank == 0 and world >= 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, datas, sample_steps=3)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+class CpuRun:
+    """The same schedule on the host through the oracle (oracle/flame_oracle.c): streams in parallel
+    Python threads (ctypes releases the GIL), OpenMP inside each call."""
+
+    def __init__(self, datas, cores):
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import oracle as O
+        self.O, self.datas, self.S = O, datas, len(datas)
+        self.lib_native = True
+        try:
+            O.load(native=True)
+        except Exception:
+            self.lib_native = False
+            O.load()
+        self.cores = cores
+        self.par = min(self.S, cores)
+        self.nthreads = max(1, cores // self.par)
+        self.pool = ThreadPoolExecutor(self.par)
+        self.ep, self.rp = O.EpiParams.default(), O.NLTGV2Params.default()
+        self.st = []
+        for d in datas:
+            V = d.V
+            z0 = np.full(V, WL.MU0, np.float32)
+            self.st.append(dict(imgs=np.zeros((WL.N_SLOTS, d.H, d.W), np.uint8), poses=np.zeros((WL.N_SLOTS, 7), np.float32),
+                                mu=z0.copy(), var=np.full(V, WL.VAR0, np.float32), drop=np.zeros(V, np.int32),
+                                alive=np.ones(V, np.int32), ref=np.zeros(V, np.int32),
+                                wt=np.ones(V, np.float32), z=z0.copy(), state=O.new_state(z0, d.E)))
+            self.st[-1]["poses"][:, 3] = 1.0
+
+    def _one(self, s, k):
+        O, d, st = self.O, self.datas[s], self.st[s]
+        newpf, ref_slot, ref_idx, cmp_idx = WL.schedule(k)
+        if newpf:
+            st["imgs"][ref_slot] = d.frames[ref_idx]
+            st["poses"][ref_slot] = d.poses[ref_idx]
+            st["mu"][:] = WL.MU0
+            st["var"][:] = WL.VAR0
+            st["drop"][:] = 0
+            st["alive"][:] = 1
+            st["ref"][:] = ref_slot
+        st["imgs"][WL.CMP_SLOT] = d.frames[cmp_idx]
+        st["poses"][WL.CMP_SLOT] = d.poses[cmp_idx]
+        O.idepth_update(st["imgs"], st["poses"], d.K, WL.CMP_SLOT, st["ref"], d.u_ref, st["mu"], st["var"],
+                        st["drop"], st["alive"], self.ep, nthreads=self.nthreads, native=self.lib_native)
+        alive = st["alive"] == 1
+        st["z"][alive] = st["mu"][alive]
+        st["wt"][:] = alive.astype(np.float32)
+        O.nltgv2_solve(d.u_ref, d.edges, d.alpha, d.beta, st["z"], st["wt"], st["state"], self.rp, d.iters,
+                       nthreads=self.nthreads, native=self.lib_native)
+
+    def step(self, k):
+        list(self.pool.map(lambda s: self._one(s, k), range(self.S)))
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(args, datas, sample_steps):
+    cores = host_cores()
+    run = CpuRun(datas, cores)
+    run.step(0)
+    t0 = time.perf_counter()
+    for k in range(1, 1 + sample_steps):
+        run.step(k)
+    dt = time.perf_counter() - t0
+    return {"value": len(datas) * sample_steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d steps x %d streams of the same workload after 1 warm-up step; oracle/flame_oracle.c "
+                      "(-O3 -march=native%s), %d streams in parallel x %d OpenMP threads; CPU baseline is this "
+                      "repo's restatement of FLaME, not robustrobotics/flame itself (source absent: parity unpinned)"
+                      % (sample_steps, len(datas), "" if run.lib_native else " unavailable: portable -O2 build",
+                         run.par, run.nthreads)}
+
+
+def reference_main(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    S = args.streams
+    datas = [WL.StreamData(args.config, seed=s) for s in range(S)]
+    cores = host_cores()
+    run = CpuRun(datas, cores)
+    # bounded sample: cap steps so the run stays within a few minutes on any host
+    steps, warmup = min(args.steps, 30), min(args.warmup, 5)
+    for k in range(warmup):
+        run.step(k)
+    t0 = time.perf_counter()
+    for k in range(warmup, warmup + steps):
+        run.step(k)
+    dt = time.perf_counter() - t0
+    frames = S * steps
+    val = frames / dt
+    sample = ("%d timed steps (of %d requested) x %d streams after %d warm-up; oracle restatement, %d streams in "
+              "parallel x %d OpenMP threads, %s build" % (steps, args.steps, S, warmup, run.par, run.nthreads,
+                                                           "-O3 -march=native" if run.lib_native else "portable -O2"))
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "%s (BASELINE configs[1]) x %d independent streams, CPU oracle restatement of the "
+                                  "reference algorithm (robustrobotics/flame source is not in /root/reference)"
+                                  % (args.config, S), "streams_per_gpu": S, "vertices": datas[0].V,
+                      "edges": datas[0].E, "pd_iters": datas[0].iters},
+           "solver_iters_per_second": frames * datas[0].iters / dt,
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        reference_main(a)
+    else:
+        gpu_main(a)

@@ -24,7 +24,7 @@ SYMBOLS = [
     "fb_default_nltgv2_params", "fb_default_tri_filter_params", "fb_graph_set", "fb_graph_data_set",
     "fb_graph_state_set", "fb_graph_state_get", "fb_graph_x_get_all", "fb_nltgv2_solve", "fb_costs",
     "fb_frame_set", "fb_frame_pose_set", "fb_pool_reserve", "fb_pool_upload", "fb_frame_from_pool",
-    "fb_features_set", "fb_features_get", "fb_idepth_update", "fb_idepth_counters",
+    "fb_features_set", "fb_features_get", "fb_features_reinit", "fb_idepth_update", "fb_idepth_counters",
     "fb_project_features", "fb_graph_bind_features", "fb_graph_data_from_features", "fb_mesh_set",
     "fb_interpolate", "fb_profile_enable", "fb_profile_reset", "fb_profile_get", "fb_launch_count",
     "fb_last_solver_variant",
@@ -105,7 +105,7 @@ def load_library(build_if_missing=True):
         "fb_costs": [P, I, C.c_float, P, P], "fb_frame_set": [P, I, I, P, I, P],
         "fb_frame_pose_set": [P, I, I, P], "fb_pool_reserve": [P, I], "fb_pool_upload": [P, I, P, I],
         "fb_frame_from_pool": [P, I, I, I, P], "fb_features_set": [P, I, I, P, P, P, P, P, P],
-        "fb_features_get": [P, I, P, P, P, P, P, P], "fb_idepth_update": [P, P],
+        "fb_features_get": [P, I, P, P, P, P, P, P], "fb_idepth_update": [P, P], "fb_features_reinit": [P, P, C.c_float, C.c_float],
         "fb_idepth_counters": [P, I, P], "fb_project_features": [P, I, I, P, P, P, P],
         "fb_graph_bind_features": [P, I, P], "fb_graph_data_from_features": [P, I],
         "fb_mesh_set": [P, I, I, P], "fb_interpolate": [P, I, P, P, P],
@@ -303,6 +303,10 @@ class Context:
                                            _ptr(out["dropouts"]), _ptr(out["alive"]),
                                            _ptr(out["status"]), _ptr(out["u_cmp"])))
         return out
+
+    def features_reinit(self, ref_slot, mu0, var0):
+        ref_slot = _i32(np.broadcast_to(np.asarray(ref_slot, np.int32), (self.S,)))
+        self._ck(self._lib.fb_features_reinit(self._h, _ptr(ref_slot), mu0, var0))
 
     def idepth_update(self, cmp_slot):
         cmp_slot = _i32(np.broadcast_to(np.asarray(cmp_slot, np.int32), (self.S,)))

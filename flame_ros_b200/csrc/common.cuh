@@ -116,3 +116,8 @@ struct fb_ctx {
   } while (0)
 
 static inline int fb_div_up(int a, int b) { return (a + b - 1) / b; }
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) {
+  return cudaMalloc((void**)p, sizeof(T) * (n ? n : 1));
+}

@@ -352,3 +352,20 @@ k_project_features(const float* __restrict__ geo, int n_slots, int s, int N, int
   var_cur[f] = var[f] * (r2 * r2);
   valid[f] = 1;
 }
+
+// Fresh filter state for every feature of the selected streams (ref_slot[s] < 0: leave untouched).
+__global__ void __launch_bounds__(256)
+k_features_reinit(const int32_t* __restrict__ new_ref, const int32_t* __restrict__ nF, int maxF,
+                  float mu0, float var0, float* mu, float* var, int32_t* dropouts, int32_t* alive,
+                  int32_t* ref_slot) {
+  const int s = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = new_ref[s];
+  if (r < 0 || f >= nF[s]) return;
+  const size_t fb = (size_t)s * maxF + f;
+  mu[fb] = mu0;
+  var[fb] = var0;
+  dropouts[fb] = 0;
+  alive[fb] = 1;
+  ref_slot[fb] = r;
+}

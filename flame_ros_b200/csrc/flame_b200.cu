@@ -17,18 +17,6 @@
 static std::string g_create_error;
 
 // ------------------------------------------------------------------------------------ helpers
-template <typename T>
-static cudaError_t dalloc(T** p, size_t n) {
-  return cudaMalloc((void**)p, sizeof(T) * (n ? n : 1));
-}
-
-static GraphView graph_view(fb_ctx* c) {
-  GraphView g;
-  g.vbar = c->vbar; g.x = c->x; g.w1 = c->w1; g.w2 = c->w2; g.z = c->z; g.wt = c->wt;
-  g.ec = c->ec; g.eij = c->eij; g.q4 = c->q4; g.row = c->row; g.inc = c->inc;
-  g.nV = c->nV; g.nE = c->nE; g.maxV = c->maxV; g.maxE = c->maxE;
-  return g;
-}
 
 struct ProfScope {
   fb_ctx* c;
@@ -556,6 +544,22 @@ extern "C" int fb_features_get(fb_ctx* c, int s, float* mu, float* var, int32_t*
     if (u_cmp) FB_CUDA(c, cudaMemcpyAsync(u_cmp, c->f_ucmp + fb, sizeof(float2) * N, cudaMemcpyDeviceToHost, st));
   }
   FB_CUDA(c, cudaStreamSynchronize(st));
+  return FB_OK;
+}
+
+extern "C" int fb_features_reinit(fb_ctx* c, const int32_t* ref_slot, float mu0, float var0) {
+  CHECK_CTX(c);
+  if (!ref_slot) FB_FAIL(c, FB_E_ARG, "fb_features_reinit: null ref_slot");
+  for (int s = 0; s < c->S; ++s)
+    if (ref_slot[s] >= c->n_slots) FB_FAIL(c, FB_E_ARG, "fb_features_reinit: ref_slot out of range");
+  if (c->maxF == 0) return FB_OK;
+  ProfScope ps(c, FB_PROF_ASSEMBLY);
+  // d_cmp doubles as the per-stream argument buffer (consumed by the kernel enqueued right after)
+  FB_CUDA(c, cudaMemcpyAsync(c->d_cmp, ref_slot, sizeof(int32_t) * c->S, cudaMemcpyHostToDevice, c->stream));
+  const dim3 grid(fb_div_up(c->maxF, 256), c->S);
+  k_features_reinit<<<grid, 256, 0, c->stream>>>(c->d_cmp, c->nF, c->maxF, mu0, var0, c->f_mu, c->f_var, c->f_drop, c->f_alive, c->f_ref);
+  c->launches++;
+  FB_CUDA(c, cudaGetLastError());
   return FB_OK;
 }
 

@@ -33,6 +33,14 @@ struct GraphView {
   int maxV, maxE;
 };
 
+static GraphView graph_view(fb_ctx* c) {
+  GraphView g;
+  g.vbar = c->vbar; g.x = c->x; g.w1 = c->w1; g.w2 = c->w2; g.z = c->z; g.wt = c->wt;
+  g.ec = c->ec; g.eij = c->eij; g.q4 = c->q4; g.row = c->row; g.inc = c->inc;
+  g.nV = c->nV; g.nE = c->nE; g.maxV = c->maxV; g.maxE = c->maxE;
+  return g;
+}
+
 __device__ __forceinline__ float fb_clamp1(float t) { return fminf(fmaxf(t, -1.0f), 1.0f); }
 
 // One thread per edge.  Algorithmic traffic per edge: eij 8 + ec 16 + q 16 r + 16 w + 2 gathers.

@@ -352,6 +352,15 @@ static int fbc_upload_plans(fb_ctx* c, int C) {
   for (int s = 0; s < c->S; ++s) {
     ClusterPlan::Topo& t = P->topo[s];
     if (!t.dirty) continue;
+    if (t.V == 0) {  // empty stream: its cluster exits on nV == 0, but keep the tables defined
+      std::fill(pad.begin(), pad.end(), 0);
+      FB_CUDA(c, cudaMemcpyAsync(P->vpart + (size_t)s * (FBC_MAXC + 1), pad.data(), sizeof(int32_t) * (FBC_MAXC + 1), cudaMemcpyHostToDevice, c->stream));
+      FB_CUDA(c, cudaMemcpyAsync(P->epart + (size_t)s * (FBC_MAXC + 1), pad.data(), sizeof(int32_t) * (FBC_MAXC + 1), cudaMemcpyHostToDevice, c->stream));
+      FB_CUDA(c, cudaStreamSynchronize(c->stream));
+      t.capV = t.capI = 0;
+      t.dirty = false;
+      continue;
+    }
     int capV = 0, capI = 0;
     if (!fbc_partition(t, C, vp, ep, capV, capI))
       FB_FAIL(c, FB_E_STATE, "cluster plan: partition infeasible");

@@ -1,0 +1,66 @@
+"""The benchmark workload (BASELINE.json configs[1], "C2"): per stream a synthetic 640x480
+random-texture image+pose stream, ~5k features = 5k Delaunay-graph vertices, and per frame one
+epipolar inverse-depth update of every feature followed by 50 warm-started NLTGV2-L1 primal-dual
+iterations on the graph.  Shared by bench.py's GPU arm and its CPU (`--impl reference`) arm so both
+see identical inputs and the identical per-step schedule.  Nothing here touches the oracle.
+"""
+import numpy as np
+
+from . import synth
+
+EPOCH = 5          # comparison frames per poseframe (poseframe_subsample_factor 6:
+                   # /root/reference/cfg/flame_nodelet.yaml:6 -> 1 poseframe + 5 updates)
+POOL_FRAMES = 12   # two poseframe epochs: [P0 c1..c5 | P1 c1..c5]
+MU0, VAR0 = 0.5, 0.25   # fresh-feature prior (inverse metres, variance)
+
+CONFIGS = {
+    # name: (W, H, K, detection win, n_vertices, iters)
+    "C2": (640, 480, synth.K_VGA, 8, 5000, 50),
+    "C3": (752, 480, synth.K_EUROC, 8, 5000, 50),
+    "C4": (1280, 720, synth.K_720P, 7, 20000, 100),
+    "tiny": (160, 120, np.array([[130.0, 0, 79.5], [0, 130.0, 59.5], [0, 0, 1]], np.float32), 8, 300, 10),
+}
+
+
+class StreamData:
+    """Everything one stream needs: frame pool, poses, features (= graph vertices), Delaunay graph."""
+
+    def __init__(self, config, seed):
+        W, H, K, win, nv, iters = CONFIGS[config]
+        self.W, self.H, self.K, self.iters = W, H, np.asarray(K, np.float32), iters
+        sc = synth.Scene(seed, tex_size=1024)
+        self.poses = synth.stream_poses(POOL_FRAMES)
+        # second epoch restarts from its own poseframe: same relative motion, different viewpoint
+        self.frames = np.stack([sc.render(self.K, self.poses[k], W, H)[0] for k in range(POOL_FRAMES)])
+        feats = synth.grid_features(W, H, win, border=8, seed=100 + seed)
+        if len(feats) < nv:
+            rng = np.random.default_rng(200 + seed)
+            have = {(int(x), int(y)) for x, y in feats}
+            extra = []
+            while len(feats) + len(extra) < nv:
+                p = (int(rng.integers(8, W - 8)), int(rng.integers(8, H - 8)))
+                if p not in have:
+                    have.add(p)
+                    extra.append(p)
+            feats = np.concatenate([feats, np.array(extra, np.float32).reshape(-1, 2)], axis=0)
+        self.u_ref = feats[:nv].astype(np.float32)
+        self.tris, self.edges = synth.delaunay(self.u_ref)
+        self.alpha, self.beta = synth.edge_weights(self.u_ref, self.edges)
+        self.V, self.E = len(self.u_ref), len(self.edges)
+
+    def algorithmic_bytes_per_iter(self):
+        """B_iter = 40 E + 64 V."""
+        return 40 * self.E + 64 * self.V
+
+
+def schedule(step):
+    """Per-step plan: (new_poseframe, ref_slot, ref_pool_idx, cmp_pool_idx). Slots 0/1 hold the two
+    alternating poseframes, slot 2 the current frame."""
+    epoch, j = divmod(step, EPOCH)
+    half = epoch % 2
+    base = half * (POOL_FRAMES // 2)
+    return (j == 0, half, base, base + 1 + j)
+
+
+CMP_SLOT = 2
+N_SLOTS = 3

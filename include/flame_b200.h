@@ -165,6 +165,10 @@ int fb_features_set(fb_ctx* ctx, int stream, int N, const float* u_ref, const in
  * (/root/reference/src/flame_nodelet.cc:721-723). */
 int fb_features_get(fb_ctx* ctx, int stream, float* mu, float* var, int32_t* dropouts,
                     int32_t* alive, int32_t* status, float* u_cmp);
+/* Device-side re-initialisation of every feature of every stream s with ref_slot[s] >= 0:
+ * mu = mu0, var = var0, dropouts = 0, alive = 1, ref_slot = ref_slot[s].  Emulates the detector
+ * handing a fresh feature set to the filter on a new poseframe without a host round trip. */
+int fb_features_reinit(fb_ctx* ctx, const int32_t* ref_slot, float mu0, float var0);
 /* One epipolar update of every live feature of every stream against that stream's comparison
  * slot cmp_slot[s] (cmp_slot[s] < 0 skips stream s). */
 int fb_idepth_update(fb_ctx* ctx, const int32_t* cmp_slot);
