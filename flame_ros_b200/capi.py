@@ -27,7 +27,7 @@ SYMBOLS = [
     "fb_features_set", "fb_features_get", "fb_features_reinit", "fb_idepth_update", "fb_idepth_counters",
     "fb_project_features", "fb_graph_bind_features", "fb_graph_data_from_features", "fb_mesh_set",
     "fb_interpolate", "fb_profile_enable", "fb_profile_reset", "fb_profile_get", "fb_launch_count",
-    "fb_last_solver_variant",
+    "fb_last_solver_variant", "fb_delaunay", "fb_hotpath_step",
 ]
 
 
@@ -57,6 +57,17 @@ class TriFilterParams(C.Structure):
                 ("oblique_idepth_diff_factor", C.c_float), ("oblique_idepth_diff_abs", C.c_float),
                 ("do_edge_length", C.c_int), ("edge_length_thresh", C.c_float),
                 ("do_idepth", C.c_int), ("min_triangle_idepth", C.c_float)]
+
+
+class StepDesc(C.Structure):
+    """fb_step_desc: one frame of every stream through the hot path in a single call."""
+    _fields_ = [("new_poseframe", C.c_int), ("ref_slot", C.c_int), ("cmp_slot", C.c_int),
+                ("ref_images", C.POINTER(C.c_void_p)), ("cmp_images", C.POINTER(C.c_void_p)),
+                ("ref_pool_idx", C.POINTER(C.c_int32)), ("cmp_pool_idx", C.POINTER(C.c_int32)),
+                ("ref_poses", C.POINTER(C.c_float)), ("cmp_poses", C.POINTER(C.c_float)),
+                ("mu0", C.c_float), ("var0", C.c_float), ("adaptive_weights", C.c_int),
+                ("iters", C.c_int), ("variant", C.c_int), ("rparams", NLTGV2Params),
+                ("x_out", C.POINTER(C.c_float))]
 
 
 _LIB = None
@@ -110,7 +121,7 @@ def load_library(build_if_missing=True):
         "fb_graph_bind_features": [P, I, P], "fb_graph_data_from_features": [P, I],
         "fb_mesh_set": [P, I, I, P], "fb_interpolate": [P, I, P, P, P],
         "fb_profile_enable": [P, I], "fb_profile_reset": [P], "fb_profile_get": [P, I, P, P, P],
-        "fb_last_solver_variant": [P], "fb_version": [],
+        "fb_last_solver_variant": [P], "fb_version": [], "fb_delaunay": [I, P, P, P, P, P], "fb_hotpath_step": [P, P],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -148,6 +159,21 @@ def _f32(a):
 
 def _i32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def delaunay(pts):
+    """Exact-predicate Delaunay triangulation (host code of libflame_b200; no GPU needed).
+    Returns (tris [T,3] int32, edges [E,2] int32 canonical)."""
+    lib = load_library()
+    pts = _f32(pts)
+    n = pts.shape[0]
+    tris = np.zeros((max(2 * n, 1), 3), np.int32)
+    edges = np.zeros((max(3 * n, 1), 2), np.int32)
+    nt, ne = C.c_int32(0), C.c_int32(0)
+    rc = lib.fb_delaunay(n, _ptr(pts), _ptr(tris), C.byref(nt), _ptr(edges), C.byref(ne))
+    if rc != 0:
+        raise FlameError("fb_delaunay: degenerate input (rc %d)" % rc)
+    return tris[:nt.value].copy(), edges[:ne.value].copy()
 
 
 class PinnedBuffer:
@@ -346,6 +372,10 @@ class Context:
         fp = C.byref(filter_params) if filter_params is not None else None
         self._ck(self._lib.fb_interpolate(self._h, stream, fp, _ptr(out), _ptr(valid)))
         return out, valid[:self._nT[stream]]
+
+    def hotpath_step(self, desc):
+        """desc: a StepDesc whose pointer fields the caller keeps alive."""
+        self._ck(self._lib.fb_hotpath_step(self._h, C.byref(desc)))
 
     # ------------------------------------------------------------------ profiling
     def profile_enable(self, on=True):

@@ -121,3 +121,29 @@ template <typename T>
 static cudaError_t dalloc(T** p, size_t n) {
   return cudaMalloc((void**)p, sizeof(T) * (n ? n : 1));
 }
+
+// Brackets a section with CUDA events (when profiling is enabled) and counts calls / launches.
+struct ProfScope {
+  fb_ctx* c;
+  int sec;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int64_t l0;
+  ProfScope(fb_ctx* ctx, int section) : c(ctx), sec(section), l0(ctx->launches) {
+    if (c->prof) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, c->stream);
+    }
+  }
+  ~ProfScope() {
+    ProfSection& s = c->sec[sec];
+    s.calls++;
+    s.launches += c->launches - l0;
+    if (c->prof) {
+      cudaEventRecord(e1, c->stream);
+      s.ev.push_back(e0);
+      s.ev.push_back(e1);
+    }
+  }
+};
+

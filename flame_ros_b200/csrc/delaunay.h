@@ -1,0 +1,348 @@
+// delaunay.h -- incremental (Bowyer-Watson) Delaunay triangulation of the graph vertices.
+//
+// Stands in for the `triangulate` stage of flame::Flame::update (timing key
+// /root/reference/src/utils.cc:154; the external flame core wraps Shewchuk's Triangle, which is not
+// in this image).  Host C++: the point set is a few thousand vertices and the work is
+// pointer-chasing, so it runs on the CPU overlapped with GPU work; the solver consumes its edge list.
+//
+// Robustness: vertex positions are snapped to a 1/64 px lattice and all predicates (orientation,
+// in-circle) are evaluated exactly in 64/128-bit integers, so co-circular grid detections and
+// collinear points cannot corrupt the structure.  The convex hull is closed with "ghost" triangles
+// (a hull edge + a vertex at infinity), which makes point location and cavity carving uniform.
+// Output: triangles (counter-clockwise in the y-down pixel frame's mathematical sense of the
+// stored coordinates), canonical edges (i<j, sorted by (i,j)).  Duplicate points are merged onto
+// the first occurrence and reported through `dup_of`.
+#pragma once
+
+#include <stdint.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace fbdel {
+
+typedef __int128 i128;
+
+struct Triangulator {
+  static const int GHOST = -1;
+  std::vector<int64_t> px, py;  // lattice coordinates
+  std::vector<int> tv;          // 3 vertices per triangle (ccw); ghost triangles hold GHOST at slot 2
+  std::vector<int> ta;          // ta[3t+k] = triangle across the edge (v[k], v[k+1])
+  std::vector<char> dead;
+  std::vector<int> free_list;
+  std::vector<int> dup_of;      // -1, or index of the earlier identical point
+  int last = 0;
+
+  static int64_t orient(int64_t ax, int64_t ay, int64_t bx, int64_t by, int64_t cx, int64_t cy) {
+    return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);  // > 0: c is to the left of a->b (ccw)
+  }
+  int64_t orientv(int a, int b, int c) const { return orient(px[a], py[a], px[b], py[b], px[c], py[c]); }
+
+  // > 0 iff p lies strictly inside the circumcircle of ccw triangle (a,b,c)
+  int incircle_sign(int a, int b, int c, int p) const {
+    const int64_t adx = px[a] - px[p], ady = py[a] - py[p];
+    const int64_t bdx = px[b] - px[p], bdy = py[b] - py[p];
+    const int64_t cdx = px[c] - px[p], cdy = py[c] - py[p];
+    const i128 al = (i128)(adx * adx + ady * ady);
+    const i128 bl = (i128)(bdx * bdx + bdy * bdy);
+    const i128 cl = (i128)(cdx * cdx + cdy * cdy);
+    const i128 det = al * (i128)(bdx * cdy - bdy * cdx) + bl * (i128)(cdx * ady - cdy * adx) +
+                     cl * (i128)(adx * bdy - ady * bdx);
+    return det > 0 ? 1 : (det < 0 ? -1 : 0);
+  }
+
+  // Does the (possibly ghost) triangle t conflict with point p (p inside its circumdisk)?
+  bool conflicts(int t, int p) const {
+    const int a = tv[3 * t], b = tv[3 * t + 1], c = tv[3 * t + 2];
+    if (c != GHOST) return incircle_sign(a, b, c, p) > 0;
+    // ghost (a,b,inf): the "disk" is the open half-plane to the left of a->b (outside the hull, which
+    // lies to the right of the reversed hull edge) plus the open segment ab
+    const int64_t o = orientv(a, b, p);
+    if (o > 0) return true;
+    if (o < 0) return false;
+    const int64_t dx = px[b] - px[a], dy = py[b] - py[a];
+    const int64_t t0 = (px[p] - px[a]) * dx + (py[p] - py[a]) * dy;
+    return t0 > 0 && t0 < dx * dx + dy * dy;
+  }
+
+  int new_tri(int a, int b, int c) {
+    int t;
+    if (!free_list.empty()) {
+      t = free_list.back();
+      free_list.pop_back();
+      dead[t] = 0;
+    } else {
+      t = (int)dead.size();
+      dead.push_back(0);
+      tv.resize(tv.size() + 3);
+      ta.resize(ta.size() + 3);
+    }
+    tv[3 * t] = a; tv[3 * t + 1] = b; tv[3 * t + 2] = c;
+    ta[3 * t] = ta[3 * t + 1] = ta[3 * t + 2] = -1;
+    return t;
+  }
+
+  // Walk from `last` toward p; returns a triangle that conflicts with p.
+  int locate(int p) const {
+    int t = last;
+    if (dead[t]) {
+      for (t = 0; t < (int)dead.size(); ++t)
+        if (!dead[t]) break;
+    }
+    for (int guard = 0; guard < 4 * (int)dead.size() + 64; ++guard) {
+      if (tv[3 * t + 2] == GHOST) {
+        if (conflicts(t, p)) return t;
+        // slide along the hull: move to the neighbouring ghost whose edge faces p
+        const int a = tv[3 * t], b = tv[3 * t + 1];
+        const int64_t dx = px[b] - px[a], dy = py[b] - py[a];
+        const int64_t t0 = (px[p] - px[a]) * dx + (py[p] - py[a]) * dy;
+        if (orientv(a, b, p) < 0) {
+          t = ta[3 * t];  // p is on the hull's side: step into the real triangle
+        } else {
+          t = (t0 <= 0) ? ta[3 * t + 2] : ta[3 * t + 1];  // collinear, beyond a or beyond b
+        }
+        continue;
+      }
+      bool moved = false;
+      for (int k = 0; k < 3; ++k) {
+        const int a = tv[3 * t + k], b = tv[3 * t + (k + 1) % 3];
+        if (orientv(a, b, p) < 0) {
+          t = ta[3 * t + k];
+          moved = true;
+          break;
+        }
+      }
+      if (!moved) return t;  // p inside or on the boundary of t: t's circumdisk contains p
+    }
+    // walking failed (should not happen): exhaustive search
+    for (int u = 0; u < (int)dead.size(); ++u)
+      if (!dead[u] && conflicts(u, p)) return u;
+    return -1;
+  }
+
+  std::vector<int> cavity, stack_, bnd_a, bnd_b, bnd_out, bnd_new;
+  std::vector<int> mark;
+
+  bool insert(int p) {
+    int t0 = locate(p);
+    if (t0 < 0) return false;
+    for (int k = 0; k < 3; ++k) {
+      const int v = tv[3 * t0 + k];
+      if (v != GHOST && px[v] == px[p] && py[v] == py[p]) return false;  // duplicate vertex
+    }
+    if (!conflicts(t0, p)) {
+      // p sits exactly on a vertex/edge whose triangle does not strictly contain it in its disk:
+      // look for any neighbour that conflicts (happens for points on shared edges / cocircular)
+      bool found = false;
+      for (int k = 0; k < 3 && !found; ++k) {
+        const int n = ta[3 * t0 + k];
+        if (n >= 0 && conflicts(n, p)) {
+          t0 = n;
+          found = true;
+        }
+      }
+      if (!found) {
+        for (int u = 0; u < (int)dead.size() && !found; ++u)
+          if (!dead[u] && conflicts(u, p)) {
+            t0 = u;
+            found = true;
+          }
+      }
+      if (!found) return false;  // duplicate of an existing vertex
+    }
+    if (mark.size() < dead.size()) mark.resize(dead.size(), 0);
+    cavity.clear();
+    stack_.clear();
+    stack_.push_back(t0);
+    mark[t0] = 1;
+    while (!stack_.empty()) {
+      const int t = stack_.back();
+      stack_.pop_back();
+      cavity.push_back(t);
+      for (int k = 0; k < 3; ++k) {
+        const int n = ta[3 * t + k];
+        if (n >= 0 && !mark[n] && conflicts(n, p)) {
+          mark[n] = 1;
+          stack_.push_back(n);
+        }
+      }
+    }
+    // boundary edges (a,b) of the cavity with the triangle outside
+    bnd_a.clear(); bnd_b.clear(); bnd_out.clear();
+    for (int t : cavity)
+      for (int k = 0; k < 3; ++k) {
+        const int n = ta[3 * t + k];
+        if (n < 0 || !mark[n]) {
+          bnd_a.push_back(tv[3 * t + k]);
+          bnd_b.push_back(tv[3 * t + (k + 1) % 3]);
+          bnd_out.push_back(n);
+        }
+      }
+    for (int t : cavity) {
+      mark[t] = 0;
+      dead[t] = 1;
+      free_list.push_back(t);
+    }
+    // fan of new triangles (a, b, p); ghost boundary edges keep GHOST in slot 2
+    const int nb = (int)bnd_a.size();
+    bnd_new.assign(nb, -1);
+    for (int i = 0; i < nb; ++i) {
+      const int a = bnd_a[i], b = bnd_b[i];
+      int t;
+      if (a == GHOST) t = new_tri(b, p, GHOST);        // edge (inf, b): new ghost (b, p, inf)
+      else if (b == GHOST) t = new_tri(p, a, GHOST);   // edge (a, inf): new ghost (p, a, inf)
+      else t = new_tri(a, b, p);
+      bnd_new[i] = t;
+      if (mark.size() < dead.size()) mark.resize(dead.size(), 0);
+      // link across the boundary edge
+      const int n = bnd_out[i];
+      int slot;
+      if (a == GHOST) slot = 2;        // (b,p,inf): edge (inf,b) is slot 2
+      else if (b == GHOST) slot = 1;   // (p,a,inf): edge (a,inf) is slot 1
+      else slot = 0;                   // (a,b,p): edge (a,b) is slot 0
+      ta[3 * t + slot] = n;
+      if (n >= 0)
+        for (int k = 0; k < 3; ++k) {
+          const int na = tv[3 * n + k], nbv = tv[3 * n + (k + 1) % 3];
+          if (na == b && nbv == a) ta[3 * n + k] = t;
+        }
+    }
+    // link the fan triangles to each other: edge (b,p) of one matches edge (p,a') of the next
+    for (int i = 0; i < nb; ++i) {
+      const int t = bnd_new[i];
+      for (int k = 0; k < 3; ++k) {
+        if (ta[3 * t + k] >= 0) continue;
+        const int ea = tv[3 * t + k], eb = tv[3 * t + (k + 1) % 3];
+        for (int j = 0; j < nb; ++j) {
+          if (j == i) continue;
+          const int u = bnd_new[j];
+          for (int m = 0; m < 3; ++m)
+            if (tv[3 * u + m] == eb && tv[3 * u + (m + 1) % 3] == ea) {
+              ta[3 * t + k] = u;
+              ta[3 * u + m] = t;
+            }
+        }
+      }
+    }
+    last = bnd_new[0];
+    return true;
+  }
+
+  // pts: n points (x,y) in pixels.  Returns false when all points are collinear / fewer than 3.
+  bool run(int n, const float* pts, std::vector<int>& tris, std::vector<int>& edges) {
+    tris.clear();
+    edges.clear();
+    px.resize(n);
+    py.resize(n);
+    dup_of.assign(n, -1);
+    for (int i = 0; i < n; ++i) {
+      px[i] = (int64_t)llroundf(pts[2 * i] * 64.0f);
+      py[i] = (int64_t)llroundf(pts[2 * i + 1] * 64.0f);
+    }
+    tv.clear(); ta.clear(); dead.clear(); free_list.clear(); mark.clear();
+    if (n < 3) return false;
+    // insertion order: snake over a coarse grid for walk locality (deterministic)
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    int64_t xmin = px[0], xmax = px[0], ymin = py[0], ymax = py[0];
+    for (int i = 1; i < n; ++i) {
+      xmin = std::min(xmin, px[i]); xmax = std::max(xmax, px[i]);
+      ymin = std::min(ymin, py[i]); ymax = std::max(ymax, py[i]);
+    }
+    int g = 1;
+    while (g * g * 4 < n) ++g;
+    const int64_t cw = std::max<int64_t>(1, (xmax - xmin) / g + 1), ch = std::max<int64_t>(1, (ymax - ymin) / g + 1);
+    std::vector<int64_t> key(n);
+    for (int i = 0; i < n; ++i) {
+      const int64_t cy = (py[i] - ymin) / ch;
+      int64_t cx = (px[i] - xmin) / cw;
+      if (cy & 1) cx = g - cx;
+      key[i] = ((cy * (g + 2) + cx) << 32) | (uint32_t)i;
+    }
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+    // seed triangle: first point, the next distinct point, the next non-collinear point
+    int i0 = order[0], i1 = -1, i2 = -1;
+    size_t k1 = 1;
+    for (; k1 < order.size(); ++k1)
+      if (px[order[k1]] != px[i0] || py[order[k1]] != py[i0]) {
+        i1 = order[k1];
+        break;
+      }
+    if (i1 < 0) return false;
+    size_t k2 = k1 + 1;
+    for (; k2 < order.size(); ++k2)
+      if (orientv(i0, i1, order[k2]) != 0) {
+        i2 = order[k2];
+        break;
+      }
+    if (i2 < 0) return false;
+    if (orientv(i0, i1, i2) < 0) std::swap(i1, i2);
+    const int t = new_tri(i0, i1, i2);
+    const int g0 = new_tri(i1, i0, GHOST), g1 = new_tri(i2, i1, GHOST), g2 = new_tri(i0, i2, GHOST);
+    ta[3 * t] = g0; ta[3 * t + 1] = g1; ta[3 * t + 2] = g2;
+    ta[3 * g0] = t; ta[3 * g1] = t; ta[3 * g2] = t;
+    // ghost (a,b,inf): slot 1 = edge (b,inf) -> ghost starting at ... , slot 2 = edge (inf,a)
+    // g0=(i1,i0): (b=i0,inf) continues to the ghost whose a == i0: g2=(i0,i2); (inf,a=i1): ghost whose b == i1: g1
+    ta[3 * g0 + 1] = g2; ta[3 * g0 + 2] = g1;
+    ta[3 * g1 + 1] = g0; ta[3 * g1 + 2] = g2;
+    ta[3 * g2 + 1] = g1; ta[3 * g2 + 2] = g0;
+    last = t;
+    std::vector<char> done(n, 0);
+    done[i0] = done[i1] = done[i2] = 1;
+    for (int idx : order) {
+      if (done[idx]) continue;
+      done[idx] = 1;
+      if (!insert(idx)) dup_of[idx] = -2;  // resolved below
+    }
+    // duplicates: map to the first vertex with identical lattice coordinates
+    {
+      bool any = false;
+      for (int i = 0; i < n; ++i) any |= dup_of[i] == -2;
+      if (any) {
+        std::vector<int> byc(n);
+        for (int i = 0; i < n; ++i) byc[i] = i;
+        std::sort(byc.begin(), byc.end(), [&](int a, int b) {
+          if (px[a] != px[b]) return px[a] < px[b];
+          if (py[a] != py[b]) return py[a] < py[b];
+          return a < b;
+        });
+        for (int k = 0; k < n;) {
+          int e = k;
+          int keep = -1;
+          while (e < n && px[byc[e]] == px[byc[k]] && py[byc[e]] == py[byc[k]]) {
+            if (dup_of[byc[e]] != -2 && keep < 0) keep = byc[e];
+            ++e;
+          }
+          for (int m = k; m < e; ++m)
+            if (dup_of[byc[m]] == -2) dup_of[byc[m]] = keep;
+          k = e;
+        }
+      }
+    }
+    for (int u = 0; u < (int)dead.size(); ++u) {
+      if (dead[u] || tv[3 * u + 2] == GHOST) continue;
+      tris.push_back(tv[3 * u]);
+      tris.push_back(tv[3 * u + 1]);
+      tris.push_back(tv[3 * u + 2]);
+    }
+    // canonical edge list
+    std::vector<uint64_t> ek;
+    ek.reserve(tris.size());
+    for (size_t k = 0; k < tris.size(); k += 3)
+      for (int m = 0; m < 3; ++m) {
+        int a = tris[k + m], b = tris[k + (m + 1) % 3];
+        if (a > b) std::swap(a, b);
+        ek.push_back(((uint64_t)a << 32) | (uint32_t)b);
+      }
+    std::sort(ek.begin(), ek.end());
+    ek.erase(std::unique(ek.begin(), ek.end()), ek.end());
+    edges.reserve(2 * ek.size());
+    for (uint64_t e : ek) {
+      edges.push_back((int)(e >> 32));
+      edges.push_back((int)(e & 0xffffffffu));
+    }
+    return true;
+  }
+};
+
+}  // namespace fbdel

@@ -9,6 +9,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "delaunay.h"
 #include "epipolar.cuh"
 #include "nltgv2.cuh"
 #include "nltgv2_cluster.cuh"
@@ -17,30 +18,6 @@
 static std::string g_create_error;
 
 // ------------------------------------------------------------------------------------ helpers
-
-struct ProfScope {
-  fb_ctx* c;
-  int sec;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  int64_t l0;
-  ProfScope(fb_ctx* ctx, int section) : c(ctx), sec(section), l0(ctx->launches) {
-    if (c->prof) {
-      cudaEventCreate(&e0);
-      cudaEventCreate(&e1);
-      cudaEventRecord(e0, c->stream);
-    }
-  }
-  ~ProfScope() {
-    ProfSection& s = c->sec[sec];
-    s.calls++;
-    s.launches += c->launches - l0;
-    if (c->prof) {
-      cudaEventRecord(e1, c->stream);
-      s.ev.push_back(e0);
-      s.ev.push_back(e1);
-    }
-  }
-};
 
 static void prof_fold(fb_ctx* c, int section) {
   ProfSection& s = c->sec[section];
@@ -388,6 +365,7 @@ static int solve_streaming(fb_ctx* c, int iters, const fb_nltgv2_params* p) {
     c->solve_iters = iters;
     c->solve_params = *p;
   }
+  ProfScope ps(c, FB_PROF_SOLVE);
   FB_CUDA(c, cudaGraphLaunch(c->solve_exec, c->stream));
   c->launches += 2 * (int64_t)iters;
   return FB_OK;
@@ -397,7 +375,6 @@ extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, 
   CHECK_CTX(c);
   if (!p || iters < 0 || variant < 0 || variant > 2) FB_FAIL(c, FB_E_ARG, "fb_nltgv2_solve: bad argument");
   if (iters == 0) return FB_OK;
-  ProfScope ps(c, FB_PROF_SOLVE);
   int v = variant;
   if (v == 0) v = cluster_plan_ready(c) ? 2 : 1;
   if (v == 2 && !cluster_plan_ready(c))
@@ -654,6 +631,59 @@ extern "C" int fb_graph_data_from_features(fb_ctx* c, int adaptive) {
   k_data_from_features<<<grid, 256, 0, c->stream>>>(c->z, c->wt, c->vfeat, c->nV, c->maxV, c->f_mu, c->f_var, c->f_alive, c->nF, c->maxF, adaptive);
   c->launches++;
   FB_CUDA(c, cudaGetLastError());
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------ batched frame
+extern "C" int fb_hotpath_step(fb_ctx* c, const fb_step_desc* d) {
+  CHECK_CTX(c);
+  if (!d || !d->cmp_poses || (!d->cmp_images && !d->cmp_pool_idx))
+    FB_FAIL(c, FB_E_ARG, "fb_hotpath_step: null descriptor field");
+  if (d->new_poseframe && (!d->ref_poses || (!d->ref_images && !d->ref_pool_idx)))
+    FB_FAIL(c, FB_E_ARG, "fb_hotpath_step: poseframe inputs missing");
+  int rc;
+  std::vector<int32_t> slots(c->S);
+  if (d->new_poseframe) {
+    for (int s = 0; s < c->S; ++s) {
+      rc = d->ref_images ? fb_frame_set(c, s, d->ref_slot, d->ref_images[s], c->W, d->ref_poses + 7 * s)
+                         : fb_frame_from_pool(c, s, d->ref_slot, d->ref_pool_idx[s], d->ref_poses + 7 * s);
+      if (rc) return rc;
+    }
+  }
+  for (int s = 0; s < c->S; ++s) {
+    rc = d->cmp_images ? fb_frame_set(c, s, d->cmp_slot, d->cmp_images[s], c->W, d->cmp_poses + 7 * s)
+                       : fb_frame_from_pool(c, s, d->cmp_slot, d->cmp_pool_idx[s], d->cmp_poses + 7 * s);
+    if (rc) return rc;
+  }
+  if (d->new_poseframe) {
+    std::fill(slots.begin(), slots.end(), d->ref_slot);
+    rc = fb_features_reinit(c, slots.data(), d->mu0, d->var0);
+    if (rc) return rc;
+  }
+  std::fill(slots.begin(), slots.end(), d->cmp_slot);
+  rc = fb_idepth_update(c, slots.data());
+  if (rc) return rc;
+  rc = fb_graph_data_from_features(c, d->adaptive_weights);
+  if (rc) return rc;
+  rc = fb_nltgv2_solve(c, d->iters, &d->rparams, d->variant);
+  if (rc) return rc;
+  if (d->x_out) return fb_graph_x_get_all(c, d->x_out);
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------ triangulation
+extern "C" int fb_delaunay(int n, const float* pts, int32_t* tris, int32_t* n_tris, int32_t* edges,
+                           int32_t* n_edges) {
+  if (n < 0 || (n > 0 && !pts) || !tris || !n_tris || !edges || !n_edges) return FB_E_ARG;
+  *n_tris = 0;
+  *n_edges = 0;
+  fbdel::Triangulator T;
+  std::vector<int> t, e;
+  if (!T.run(n, pts, t, e)) return FB_E_ARG;
+  std::copy(t.begin(), t.end(), tris);
+  std::copy(e.begin(), e.end(), edges);
+  *n_tris = (int32_t)(t.size() / 3);
+  *n_edges = (int32_t)(e.size() / 2);
   return FB_OK;
 }
 

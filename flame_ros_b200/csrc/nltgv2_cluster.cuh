@@ -5,14 +5,17 @@
 //     vertex (edges are sorted by (i,j), so each CTA's edges are one contiguous range too);
 //   * per-edge state (q, alpha, beta, dx, dy, addresses) and per-vertex state (x, w, z, threshold)
 //     live in REGISTERS of the owning thread for the whole solve;
-//   * the only data exchanged are the extragradient points (16 B / vertex, in shared memory, read
-//     by edge threads -- remotely over DSMEM for cut edges) and the K^T q contributions (16 B per
-//     vertex-edge incidence, pushed by the edge thread into the slot of the owning vertex, local
-//     or remote, in the vertex's CSR order so the accumulation order equals the streaming kernel's);
-//   * two hardware cluster barriers per iteration replace two kernel launches.
+//   * shared memory holds the extragradient points (16 B / vertex: the CTA's own vertices followed
+//     by HALO copies of the remote targets of its cut edges) and one 16 B slot per vertex-edge
+//     incidence that receives the edge's K^T q contribution, in the vertex's CSR order so the
+//     accumulation order equals the streaming kernel's (bit-identical results);
+//   * CTAs exchange only what crosses the cut, as asynchronous DSMEM stores that signal the
+//     receiver's mbarrier (st.async ... mbarrier::complete_tx::bytes): target contributions flow
+//     edge-owner -> vertex-owner in the dual half-step, refreshed halo points flow back after the
+//     primal half-step.  There is NO cluster-wide barrier inside the iteration loop: a CTA waits
+//     only for the bytes it actually consumes, plus two CTA-local bar.syncs per iteration.
 // HBM is touched once per solve (state in, state out) instead of once per iteration; the
 // extragradient tile is staged in/out of shared memory with TMA bulk copies (cp.async.bulk).
-// Arithmetic and summation order are identical to nltgv2.cuh, so both variants agree bit for bit.
 #pragma once
 
 #include <algorithm>
@@ -27,11 +30,15 @@
 #define FBC_SMEM_LIMIT (227 * 1024)
 
 struct ClusterPlan {
-  int C = 0;                 // cluster size the device plan was built for (0 = none)
-  int capV = 0, capI = 0;    // per-CTA capacities (max over streams and ranks) used for the layout
-  int4* eplan = nullptr;     // [S*maxE] {i_local, j_rank<<20|j_local, slot_i, j_rank<<20|slot_j}
+  int C = 0;                       // cluster size the device plan was built for (0 = none)
+  int capV = 0, capH = 0, capI = 0;  // per-CTA capacities (max over streams and ranks): layout
+  int4* eplan = nullptr;     // [S*maxE] {i_local, j_index, slot_i, rank<<20|slot_j}
+  int2* pplan = nullptr;     // [S*maxE] push list {local vertex, rank<<20|halo index}
+  int32_t* hplan = nullptr;  // [S*maxE] halo list: stream-local vertex id of every halo entry
   int32_t* vpart = nullptr;  // [S*(FBC_MAXC+1)] vertex range boundaries per rank
   int32_t* epart = nullptr;  // [S*(FBC_MAXC+1)] edge range boundaries per rank
+  int4* cinfo = nullptr;     // [S*FBC_MAXC] {halo count, incoming remote slots, push begin, push end}
+  int32_t* hpart = nullptr;  // [S*(FBC_MAXC+1)] halo list range per rank
   // host copies of every stream's topology so plans can be rebuilt when C changes
   struct Topo {
     int V = 0, E = 0;
@@ -39,9 +46,13 @@ struct ClusterPlan {
     std::vector<int32_t> row, inc;
     int needC = 1;      // smallest feasible cluster size for this graph (0 = does not fit)
     bool dirty = true;  // device plan out of date
-    int capV = 0, capI = 0;
+    int capV = 0, capH = 0, capI = 0;
+    int partC = 0;               // cluster size `part` was computed for (0 = stale)
+    struct FbcPartData { std::vector<int> vpart, epart; int capV = 0, capH = 0, capI = 0; } part;
   };
   std::vector<Topo> topo;
+  size_t smem_set = 0;  // dynamic shared memory size the kernel attribute is currently set to
+  bool nonportable_set = false;
 };
 
 // ---------------------------------------------------------------------------------- device side
@@ -53,18 +64,44 @@ __device__ __forceinline__ uint32_t fbc_mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ float4 fbc_ld_cluster(uint32_t addr) {
+__device__ __forceinline__ float4 fbc_lds(uint32_t addr) {
   float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "r"(addr)
                : "memory");
   return v;
 }
-__device__ __forceinline__ void fbc_st_cluster(uint32_t addr, float4 v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y),
-               "f"(v.z), "f"(v.w)
+__device__ __forceinline__ void fbc_sts(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
                : "memory");
+}
+// asynchronous 16 B store into a peer CTA's shared memory, completing 16 tx-bytes on its mbarrier
+__device__ __forceinline__ void fbc_st_async(uint32_t raddr, float4 v, uint32_t rmbar) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::
+          "r"(raddr),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rmbar)
+      : "memory");
+}
+__device__ __forceinline__ void fbc_mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fbc_mbar_expect(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void fbc_mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void fbc_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::
@@ -84,18 +121,22 @@ __device__ __forceinline__ uint32_t fbc_cluster_nctarank() {
 struct ClusterArgs {
   GraphView g;
   const int4* eplan;
+  const int2* pplan;
+  const int32_t* hplan;
   const int32_t* vpart;
   const int32_t* epart;
-  int capV, capI;
+  const int32_t* hpart;
+  const int4* cinfo;
+  int capV, capH, capI;
 };
 
 __global__ void __launch_bounds__(FBC_THREADS, 1)
 k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, float theta,
                  float xmin, float xmax) {
   extern __shared__ __align__(128) uint8_t fbc_smem[];
-  float4* s_bar = reinterpret_cast<float4*>(fbc_smem);              // [capV]
-  float4* s_slot = s_bar + a.capV;                                  // [capI]
-  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_slot + a.capI);  // TMA completion barrier
+  float4* s_bar = reinterpret_cast<float4*>(fbc_smem);  // [capV own | capH halo]
+  float4* s_slot = s_bar + a.capV + a.capH;             // [capI]
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_slot + a.capI);  // [0] TMA, [1] halo (A), [2] slots (B)
   const GraphView& g = a.g;
   const int tid = threadIdx.x;
   const uint32_t C = fbc_cluster_nctarank(), rank = fbc_cluster_ctarank();
@@ -103,50 +144,69 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
   if (g.nV[s] == 0) return;  // uniform over the cluster
   const int32_t* vp = a.vpart + (size_t)s * (FBC_MAXC + 1);
   const int32_t* ep = a.epart + (size_t)s * (FBC_MAXC + 1);
+  const int32_t* hp = a.hpart + (size_t)s * (FBC_MAXC + 1);
   const int v0 = vp[rank], v1 = vp[rank + 1], e0 = ep[rank], e1 = ep[rank + 1];
   const int Vc = v1 - v0;
+  const int4 ci = a.cinfo[(size_t)s * FBC_MAXC + rank];
+  const uint32_t haloBytes = 16u * (uint32_t)ci.x, slotBytes = 16u * (uint32_t)ci.y;
   const size_t vb = (size_t)s * g.maxV, eb = (size_t)s * g.maxE;
   const int32_t* row = g.row + (size_t)s * (g.maxV + 1);
   const int slot0 = row[v0];
 
-  // ---- stage this CTA's extragradient tile with one TMA bulk copy ---------------------------
-  const uint32_t mbar = fbc_smem_u32(s_mbar);
+  const uint32_t mb_tma = fbc_smem_u32(s_mbar), mb_halo = mb_tma + 8, mb_slot = mb_tma + 16;
+  const uint32_t bar_base = fbc_smem_u32(s_bar), slot_base = fbc_smem_u32(s_slot);
   const uint32_t bar_bytes = (uint32_t)Vc * 16u;
+
+  // ---- stage this CTA's extragradient tile with one TMA bulk copy; arm the exchange barriers ----
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    fbc_mbar_init(mb_tma, 1);
+    fbc_mbar_init(mb_halo, 1);
+    fbc_mbar_init(mb_slot, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (bar_bytes) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar),
-                   "r"(bar_bytes)
-                   : "memory");
+      fbc_mbar_expect(mb_tma, bar_bytes);
       asm volatile(
           "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-              "r"(fbc_smem_u32(s_bar)),
-          "l"(g.vbar + vb + v0), "r"(bar_bytes), "r"(mbar)
+              "r"(bar_base),
+          "l"(g.vbar + vb + v0), "r"(bar_bytes), "r"(mb_tma)
           : "memory");
     }
+    if (haloBytes && iters > 1) fbc_mbar_expect(mb_halo, haloBytes);  // halo phase 0
+    if (slotBytes) fbc_mbar_expect(mb_slot, slotBytes);               // slot phase 0
+  }
+  // halo copies of remote targets: first value straight from global memory
+  {
+    const int32_t* hl = a.hplan + eb + hp[rank];
+    for (int h = tid; h < ci.x; h += FBC_THREADS) s_bar[a.capV + h] = g.vbar[vb + hl[h]];
   }
 
   // ---- register-resident per-edge and per-vertex state (coalesced global loads) -------------
   float q1[FBC_EPT], q2[FBC_EPT], q3[FBC_EPT], ea[FBC_EPT], ebt[FBC_EPT], edx[FBC_EPT], edy[FBC_EPT];
-  uint32_t a_bi[FBC_EPT], a_bj[FBC_EPT], a_si[FBC_EPT], a_sj[FBC_EPT];
+  uint32_t a_bi[FBC_EPT], a_bj[FBC_EPT], a_si[FBC_EPT], a_sj[FBC_EPT], a_mb[FBC_EPT];
   bool ev[FBC_EPT];
 #pragma unroll
   for (int k = 0; k < FBC_EPT; ++k) {
     const int e = e0 + tid + k * FBC_THREADS;
     ev[k] = e < e1;
     q1[k] = q2[k] = q3[k] = ea[k] = ebt[k] = edx[k] = edy[k] = 0.f;
-    a_bi[k] = a_bj[k] = a_si[k] = a_sj[k] = 0u;
+    a_bi[k] = a_bj[k] = a_si[k] = a_sj[k] = a_mb[k] = 0u;
     if (ev[k]) {
       const int4 pl = a.eplan[eb + e];
       const float4 c = g.ec[eb + e];
       const float4 q = g.q4[eb + e];
       ea[k] = c.x; ebt[k] = c.y; edx[k] = c.z; edy[k] = c.w;
       q1[k] = q.x; q2[k] = q.y; q3[k] = q.z;
-      a_bi[k] = fbc_smem_u32(s_bar + pl.x);
-      a_bj[k] = fbc_mapa(fbc_smem_u32(s_bar + (pl.y & 0xfffff)), (uint32_t)pl.y >> 20);
-      a_si[k] = fbc_smem_u32(s_slot + pl.z);
-      a_sj[k] = fbc_mapa(fbc_smem_u32(s_slot + (pl.w & 0xfffff)), (uint32_t)pl.w >> 20);
+      a_bi[k] = bar_base + 16u * (uint32_t)pl.x;
+      a_bj[k] = bar_base + 16u * (uint32_t)pl.y;
+      a_si[k] = slot_base + 16u * (uint32_t)pl.z;
+      const uint32_t jr = (uint32_t)pl.w >> 20;
+      const uint32_t sj = slot_base + 16u * ((uint32_t)pl.w & 0xfffffu);
+      if (jr == rank) {
+        a_sj[k] = sj;  // a_mb == 0 marks "local"
+      } else {
+        a_sj[k] = fbc_mapa(sj, jr);
+        a_mb[k] = fbc_mapa(mb_slot, jr);
+      }
     }
   }
   float vx[FBC_VPT], vw1[FBC_VPT], vw2[FBC_VPT], vz[FBC_VPT], vth[FBC_VPT];
@@ -166,27 +226,19 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
       vs1[k] = row[v + 1] - slot0;
     }
   }
-  __syncthreads();  // mbarrier init visible to all threads of the CTA
-  if (bar_bytes) {
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(mbar)
-          : "memory");
-    }
-  }
-  fbc_cluster_sync();  // every CTA's tile is resident before any remote read
+  __syncthreads();  // mbarrier init + halo fill visible to all threads of the CTA
+  if (bar_bytes) fbc_mbar_wait(mb_tma, 0);
+  fbc_cluster_sync();  // every CTA's barriers are initialised before any remote store can target them
 
+  const int2* pl = a.pplan + eb;
   for (int it = 0; it < iters; ++it) {
-    // ---- dual half-step: edge threads, gather bar (local + DSMEM), push K^T q contributions ----
+    // ---- dual half-step ---------------------------------------------------------------------
+    if (it > 0 && haloBytes) fbc_mbar_wait(mb_halo, (uint32_t)(it - 1) & 1u);  // refreshed halo landed
 #pragma unroll
     for (int k = 0; k < FBC_EPT; ++k) {
       if (ev[k]) {
-        const float4 bi = fbc_ld_cluster(a_bi[k]);
-        const float4 bj = fbc_ld_cluster(a_bj[k]);
+        const float4 bi = fbc_lds(a_bi[k]);
+        const float4 bj = fbc_lds(a_bj[k]);
         float t = bi.x - bj.x;
         t = fmaf(-edx[k], bi.y, t);
         t = fmaf(-edy[k], bi.z, t);
@@ -197,19 +249,24 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
         q2[k] = fb_clamp1(fmaf(sigma, k2, q2[k]));
         q3[k] = fb_clamp1(fmaf(sigma, k3, q3[k]));
         const float a1 = ea[k] * q1[k];
-        fbc_st_cluster(a_si[k], make_float4(a1, fmaf(ebt[k], q2[k], -(edx[k] * a1)),
-                                            fmaf(ebt[k], q3[k], -(edy[k] * a1)), 0.f));
-        fbc_st_cluster(a_sj[k], make_float4(-a1, -(ebt[k] * q2[k]), -(ebt[k] * q3[k]), 0.f));
+        fbc_sts(a_si[k], make_float4(a1, fmaf(ebt[k], q2[k], -(edx[k] * a1)),
+                                     fmaf(ebt[k], q3[k], -(edy[k] * a1)), 0.f));
+        const float4 ct = make_float4(-a1, -(ebt[k] * q2[k]), -(ebt[k] * q3[k]), 0.f);
+        if (a_mb[k] == 0u) fbc_sts(a_sj[k], ct);
+        else fbc_st_async(a_sj[k], ct, a_mb[k]);
       }
     }
-    fbc_cluster_sync();
+    __syncthreads();  // local slot writes visible; every thread is past the halo wait, so the
+                      // next halo phase may be armed without a late waiter seeing the parity wrap
+    if (tid == 0 && it > 0 && haloBytes && it + 1 < iters) fbc_mbar_expect(mb_halo, haloBytes);
+    if (slotBytes) fbc_mbar_wait(mb_slot, (uint32_t)it & 1u);  // remote contributions have landed
     // ---- primal half-step: vertex threads, local slot gather in CSR order ---------------------
 #pragma unroll
     for (int k = 0; k < FBC_VPT; ++k) {
       if (vv[k]) {
         float gx = 0.f, g1 = 0.f, g2 = 0.f;
         for (int r = vs0[k]; r < vs1[k]; ++r) {
-          const float4 c = s_slot[r];
+          const float4 c = fbc_lds(slot_base + 16u * (uint32_t)r);
           gx += c.x;
           g1 += c.y;
           g2 += c.z;
@@ -222,12 +279,22 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
         float xn = (d > vth[k]) ? (xp - vth[k]) : ((d < -vth[k]) ? (xp + vth[k]) : vz[k]);
         xn = fminf(fmaxf(xn, xmin), xmax);
         vx[k] = xn; vw1[k] = w1n; vw2[k] = w2n;
-        s_bar[tid + k * FBC_THREADS] =
-            make_float4(fmaf(theta, xn - xo, xn), fmaf(theta, w1n - w1o, w1n),
-                        fmaf(theta, w2n - w2o, w2n), 0.f);
+        fbc_sts(bar_base + 16u * (uint32_t)(tid + k * FBC_THREADS),
+                make_float4(fmaf(theta, xn - xo, xn), fmaf(theta, w1n - w1o, w1n),
+                            fmaf(theta, w2n - w2o, w2n), 0.f));
       }
     }
-    fbc_cluster_sync();
+    __syncthreads();  // own points visible to the edge threads and to the push threads
+    if (tid == 0 && slotBytes && it + 1 < iters) fbc_mbar_expect(mb_slot, slotBytes);
+    // ---- refresh the halo copies held by the CTAs whose cut edges point at our vertices --------
+    if (it + 1 < iters) {
+      for (int p = ci.z + tid; p < ci.w; p += FBC_THREADS) {
+        const int2 e = pl[p];
+        const uint32_t pr = (uint32_t)e.y >> 20;
+        const float4 v = fbc_lds(bar_base + 16u * (uint32_t)e.x);
+        fbc_st_async(fbc_mapa(bar_base + 16u * ((uint32_t)e.y & 0xfffffu), pr), v, fbc_mapa(mb_halo, pr));
+      }
+    }
   }
 
   // ---- write back: registers -> global (coalesced), extragradient tile via TMA bulk store ----
@@ -243,27 +310,29 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
   if (tid == 0 && bar_bytes) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g.vbar + vb + v0),
-                 "r"(fbc_smem_u32(s_bar)), "r"(bar_bytes)
+                 "r"(bar_base), "r"(bar_bytes)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
+  fbc_cluster_sync();  // no CTA retires while a peer could still address its shared memory
 }
 
 // ---------------------------------------------------------------------------------- host side
-static inline size_t fbc_smem_bytes(int capV, int capI) {
-  return 16 * ((size_t)capV + (size_t)capI) + 64;
+static inline size_t fbc_smem_bytes(int capV, int capH, int capI) {
+  return 16 * ((size_t)capV + (size_t)capH + (size_t)capI) + 64;
 }
+
+typedef ClusterPlan::Topo::FbcPartData FbcPart;
 
 // Balanced contiguous partition into C vertex ranges; returns false when a range breaks the
 // per-thread register budget or the shared-memory capacity.
-static bool fbc_partition(const ClusterPlan::Topo& t, int C, std::vector<int>& vpart,
-                          std::vector<int>& epart, int& capV, int& capI) {
+static bool fbc_partition(const ClusterPlan::Topo& t, int C, FbcPart& P) {
   const int V = t.V, E = t.E;
-  vpart.assign(C + 1, V);
-  epart.assign(C + 1, E);
-  vpart[0] = 0;
-  epart[0] = 0;
+  P.vpart.assign(C + 1, V);
+  P.epart.assign(C + 1, E);
+  P.vpart[0] = 0;
+  P.epart[0] = 0;
   // first edge owned by each vertex (edges sorted by source)
   std::vector<int> first(V + 1, E);
   for (int e = E - 1; e >= 0; --e) first[t.eij[e].x] = e;
@@ -279,20 +348,30 @@ static bool fbc_partition(const ClusterPlan::Topo& t, int C, std::vector<int>& v
   for (int r = 1; r < C; ++r) {
     const double target = pre[V] * r / C;
     while (v < V && pre[v] < target) ++v;
-    vpart[r] = v;
+    P.vpart[r] = v;
   }
-  capV = capI = 0;
+  P.capV = P.capI = P.capH = 0;
+  std::vector<int> seen(V, -1);
   for (int r = 0; r < C; ++r) {
-    epart[r] = first[vpart[r]];
-    epart[r + 1] = first[vpart[r + 1]];
-    const int Vc = vpart[r + 1] - vpart[r];
-    const int Ec = epart[r + 1] - epart[r];
-    const int Ic = t.row[vpart[r + 1]] - t.row[vpart[r]];
+    P.epart[r] = first[P.vpart[r]];
+    P.epart[r + 1] = first[P.vpart[r + 1]];
+    const int Vc = P.vpart[r + 1] - P.vpart[r];
+    const int Ec = P.epart[r + 1] - P.epart[r];
+    const int Ic = t.row[P.vpart[r + 1]] - t.row[P.vpart[r]];
     if (Vc > FBC_VPT * FBC_THREADS || Ec > FBC_EPT * FBC_THREADS) return false;
-    capV = std::max(capV, Vc);
-    capI = std::max(capI, Ic);
+    int H = 0;
+    for (int e = P.epart[r]; e < P.epart[r + 1]; ++e) {
+      const int j = t.eij[e].y;
+      if (j >= P.vpart[r + 1] && seen[j] != r) {
+        seen[j] = r;
+        ++H;
+      }
+    }
+    P.capV = std::max(P.capV, Vc);
+    P.capI = std::max(P.capI, Ic);
+    P.capH = std::max(P.capH, H);
   }
-  return fbc_smem_bytes(capV, capI) <= FBC_SMEM_LIMIT;
+  return fbc_smem_bytes(P.capV, P.capH, P.capI) <= FBC_SMEM_LIMIT;
 }
 
 static int cluster_plan_build(fb_ctx* c, int s, int V, int E, const int2* eij, const int32_t* row,
@@ -300,9 +379,14 @@ static int cluster_plan_build(fb_ctx* c, int s, int V, int E, const int2* eij, c
   if (!c->plan) {
     c->plan = new ClusterPlan();
     c->plan->topo.resize(c->S);
-    if (dalloc(&c->plan->eplan, (size_t)c->S * c->maxE) != cudaSuccess ||
-        dalloc(&c->plan->vpart, (size_t)c->S * (FBC_MAXC + 1)) != cudaSuccess ||
-        dalloc(&c->plan->epart, (size_t)c->S * (FBC_MAXC + 1)) != cudaSuccess)
+    const size_t S = c->S;
+    if (dalloc(&c->plan->eplan, S * c->maxE) != cudaSuccess ||
+        dalloc(&c->plan->pplan, S * c->maxE) != cudaSuccess ||
+        dalloc(&c->plan->hplan, S * c->maxE) != cudaSuccess ||
+        dalloc(&c->plan->vpart, S * (FBC_MAXC + 1)) != cudaSuccess ||
+        dalloc(&c->plan->epart, S * (FBC_MAXC + 1)) != cudaSuccess ||
+        dalloc(&c->plan->hpart, S * (FBC_MAXC + 1)) != cudaSuccess ||
+        dalloc(&c->plan->cinfo, S * FBC_MAXC) != cudaSuccess)
       FB_FAIL(c, FB_E_NOMEM, "cluster plan allocation failed");
   }
   ClusterPlan::Topo& t = c->plan->topo[s];
@@ -313,10 +397,10 @@ static int cluster_plan_build(fb_ctx* c, int s, int V, int E, const int2* eij, c
   t.inc.assign(inc, inc + 2 * (size_t)E);
   t.dirty = true;
   t.needC = 0;
-  std::vector<int> vp, ep;
+  t.partC = 0;
+  FbcPart P;
   for (int C = 1; C <= FBC_MAXC; C *= 2) {
-    int capV, capI;
-    if (fbc_partition(t, C, vp, ep, capV, capI)) {
+    if (fbc_partition(t, C, P)) {
       t.needC = C;
       break;
     }
@@ -334,71 +418,132 @@ static bool cluster_plan_ready(fb_ctx* c) {
 static void cluster_plan_free(fb_ctx* c) {
   if (!c->plan) return;
   cudaFree(c->plan->eplan);
+  cudaFree(c->plan->pplan);
+  cudaFree(c->plan->hplan);
   cudaFree(c->plan->vpart);
   cudaFree(c->plan->epart);
+  cudaFree(c->plan->hpart);
+  cudaFree(c->plan->cinfo);
   delete c->plan;
   c->plan = nullptr;
 }
 
-// (Re)build the device plans of every dirty stream for cluster size C.
+// (Re)build the device plans of every dirty stream for cluster size C.  Because the shared-memory
+// layout (capV, capH) is baked into the j indices, a change of the context-wide capacities
+// invalidates every stream's plan.
 static int fbc_upload_plans(fb_ctx* c, int C) {
   ClusterPlan* P = c->plan;
   if (P->C != C)
     for (auto& t : P->topo) t.dirty = true;
   P->C = C;
-  std::vector<int> vp, ep;
-  std::vector<int4> eplan;
-  std::vector<int32_t> pad(FBC_MAXC + 1);
+  // pass 1: partitions + capacities
+  int capV = 1, capH = 0, capI = 1;
+  for (int s = 0; s < c->S; ++s) {
+    ClusterPlan::Topo& t = P->topo[s];
+    if (t.V == 0) continue;
+    if (t.partC != C) {  // partitions are cached per topology: recomputed only after fb_graph_set
+      if (!fbc_partition(t, C, t.part)) FB_FAIL(c, FB_E_STATE, "cluster plan: partition infeasible");
+      t.partC = C;
+    }
+    capV = std::max(capV, t.part.capV);
+    capH = std::max(capH, t.part.capH);
+    capI = std::max(capI, t.part.capI);
+  }
+  if (fbc_smem_bytes(capV, capH, capI) > FBC_SMEM_LIMIT)
+    FB_FAIL(c, FB_E_STATE, "cluster plan: shared-memory layout exceeds 227 KB");
+  if (capV != P->capV || capH != P->capH || capI != P->capI)
+    for (auto& t : P->topo) t.dirty = true;
+  P->capV = capV;
+  P->capH = capH;
+  P->capI = capI;
+  // pass 2: per-stream tables
+  std::vector<int4> eplan, cinfo(FBC_MAXC);
+  std::vector<int2> pplan;
+  std::vector<int32_t> hplan, pad(FBC_MAXC + 1), hpart(FBC_MAXC + 1);
+  cudaStream_t st = c->stream;
   for (int s = 0; s < c->S; ++s) {
     ClusterPlan::Topo& t = P->topo[s];
     if (!t.dirty) continue;
+    std::fill(cinfo.begin(), cinfo.end(), make_int4(0, 0, 0, 0));
     if (t.V == 0) {  // empty stream: its cluster exits on nV == 0, but keep the tables defined
       std::fill(pad.begin(), pad.end(), 0);
-      FB_CUDA(c, cudaMemcpyAsync(P->vpart + (size_t)s * (FBC_MAXC + 1), pad.data(), sizeof(int32_t) * (FBC_MAXC + 1), cudaMemcpyHostToDevice, c->stream));
-      FB_CUDA(c, cudaMemcpyAsync(P->epart + (size_t)s * (FBC_MAXC + 1), pad.data(), sizeof(int32_t) * (FBC_MAXC + 1), cudaMemcpyHostToDevice, c->stream));
-      FB_CUDA(c, cudaStreamSynchronize(c->stream));
-      t.capV = t.capI = 0;
+      FB_CUDA(c, cudaMemcpyAsync(P->vpart + (size_t)s * (FBC_MAXC + 1), pad.data(), sizeof(int32_t) * (FBC_MAXC + 1), cudaMemcpyHostToDevice, st));
+      FB_CUDA(c, cudaMemcpyAsync(P->epart + (size_t)s * (FBC_MAXC + 1), pad.data(), sizeof(int32_t) * (FBC_MAXC + 1), cudaMemcpyHostToDevice, st));
+      FB_CUDA(c, cudaMemcpyAsync(P->hpart + (size_t)s * (FBC_MAXC + 1), pad.data(), sizeof(int32_t) * (FBC_MAXC + 1), cudaMemcpyHostToDevice, st));
+      FB_CUDA(c, cudaMemcpyAsync(P->cinfo + (size_t)s * FBC_MAXC, cinfo.data(), sizeof(int4) * FBC_MAXC, cudaMemcpyHostToDevice, st));
+      FB_CUDA(c, cudaStreamSynchronize(st));
       t.dirty = false;
       continue;
     }
-    int capV = 0, capI = 0;
-    if (!fbc_partition(t, C, vp, ep, capV, capI))
-      FB_FAIL(c, FB_E_STATE, "cluster plan: partition infeasible");
-    t.capV = capV;
-    t.capI = capI;
-    // rank of every vertex
+    const std::vector<int>& vp = t.part.vpart;
+    const std::vector<int>& ep = t.part.epart;
     std::vector<int> rk(t.V);
     for (int r = 0; r < C; ++r)
       for (int v = vp[r]; v < vp[r + 1]; ++v) rk[v] = r;
-    eplan.assign(t.E, make_int4(0, 0, 0, 0));
+    // halo lists: per rank, the sorted unique remote targets of its owned edges
+    hplan.clear();
+    std::vector<int> hidx(t.V, -1);  // halo index of vertex j within the rank being processed
+    std::vector<std::vector<int2>> push(C);  // push[y] = {local vertex in y, rank<<20 | halo index}
+    for (int r = 0; r < C; ++r) {
+      hpart[r] = (int)hplan.size();
+      std::vector<int> hl;
+      for (int e = ep[r]; e < ep[r + 1]; ++e) {
+        const int j = t.eij[e].y;
+        if (j >= vp[r + 1]) hl.push_back(j);
+      }
+      std::sort(hl.begin(), hl.end());
+      hl.erase(std::unique(hl.begin(), hl.end()), hl.end());
+      for (size_t h = 0; h < hl.size(); ++h) {
+        hidx[hl[h]] = (int)h;
+        const int y = rk[hl[h]];
+        push[y].push_back(make_int2(hl[h] - vp[y], (r << 20) | (capV + (int)h)));
+        hplan.push_back(hl[h]);
+      }
+      cinfo[r].x = (int)hl.size();
+      // edge plans of rank r (needs hidx of this rank)
+      if (r == 0) eplan.assign(t.E, make_int4(0, 0, 0, 0));
+      for (int e = ep[r]; e < ep[r + 1]; ++e) {
+        const int i = t.eij[e].x, j = t.eij[e].y;
+        eplan[e].x = i - vp[r];
+        eplan[e].y = (j < vp[r + 1]) ? (j - vp[r]) : (capV + hidx[j]);
+      }
+    }
+    for (int r = C; r <= FBC_MAXC; ++r) hpart[r] = (int)hplan.size();
+    // slots: position of every incidence within its vertex's CTA
     for (int v = 0; v < t.V; ++v) {
       const int r = rk[v], base = t.row[vp[r]];
       for (int k = t.row[v]; k < t.row[v + 1]; ++k) {
         const int code = t.inc[k], e = code >> 1, local = k - base;
         if ((code & 1) == 0) {
-          eplan[e].x = v - vp[r];
           eplan[e].z = local;
         } else {
-          eplan[e].y = (r << 20) | (v - vp[r]);
           eplan[e].w = (r << 20) | local;
+          if (rk[t.eij[e].x] != r) cinfo[r].y++;  // incoming remote contribution
         }
       }
     }
-    cudaStream_t st = c->stream;
+    pplan.clear();
+    for (int r = 0; r < C; ++r) {
+      cinfo[r].z = (int)pplan.size();
+      pplan.insert(pplan.end(), push[r].begin(), push[r].end());
+      cinfo[r].w = (int)pplan.size();
+    }
+    if ((int)pplan.size() > c->maxE || (int)hplan.size() > c->maxE)
+      FB_FAIL(c, FB_E_NOMEM, "cluster plan: halo tables exceed capacity");
     if (t.E)
       FB_CUDA(c, cudaMemcpyAsync(P->eplan + (size_t)s * c->maxE, eplan.data(), sizeof(int4) * t.E, cudaMemcpyHostToDevice, st));
+    if (!pplan.empty())
+      FB_CUDA(c, cudaMemcpyAsync(P->pplan + (size_t)s * c->maxE, pplan.data(), sizeof(int2) * pplan.size(), cudaMemcpyHostToDevice, st));
+    if (!hplan.empty())
+      FB_CUDA(c, cudaMemcpyAsync(P->hplan + (size_t)s * c->maxE, hplan.data(), sizeof(int32_t) * hplan.size(), cudaMemcpyHostToDevice, st));
     for (int r = 0; r <= FBC_MAXC; ++r) pad[r] = vp[std::min(r, C)];
     FB_CUDA(c, cudaMemcpyAsync(P->vpart + (size_t)s * (FBC_MAXC + 1), pad.data(), sizeof(int32_t) * (FBC_MAXC + 1), cudaMemcpyHostToDevice, st));
     for (int r = 0; r <= FBC_MAXC; ++r) pad[r] = ep[std::min(r, C)];
     FB_CUDA(c, cudaMemcpyAsync(P->epart + (size_t)s * (FBC_MAXC + 1), pad.data(), sizeof(int32_t) * (FBC_MAXC + 1), cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(P->hpart + (size_t)s * (FBC_MAXC + 1), hpart.data(), sizeof(int32_t) * (FBC_MAXC + 1), cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(P->cinfo + (size_t)s * FBC_MAXC, cinfo.data(), sizeof(int4) * FBC_MAXC, cudaMemcpyHostToDevice, st));
     FB_CUDA(c, cudaStreamSynchronize(st));  // staging vectors are reused per stream
     t.dirty = false;
-  }
-  P->capV = P->capI = 1;
-  for (auto& t : P->topo) {
-    if (t.V == 0) continue;
-    P->capV = std::max(P->capV, t.capV);
-    P->capI = std::max(P->capI, t.capI);
   }
   return FB_OK;
 }
@@ -415,15 +560,26 @@ static int solve_cluster(fb_ctx* c, int iters, const fb_nltgv2_params* p) {
   if (!any) return FB_OK;
   int rc = fbc_upload_plans(c, C);
   if (rc) return rc;
-  const size_t smem = fbc_smem_bytes(P->capV, P->capI);
-  FB_CUDA(c, cudaFuncSetAttribute(k_nltgv2_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (C > 8) FB_CUDA(c, cudaFuncSetAttribute(k_nltgv2_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  const size_t smem = fbc_smem_bytes(P->capV, P->capH, P->capI);
+  if (smem != P->smem_set) {
+    FB_CUDA(c, cudaFuncSetAttribute(k_nltgv2_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    P->smem_set = smem;
+  }
+  if (C > 8 && !P->nonportable_set) {
+    FB_CUDA(c, cudaFuncSetAttribute(k_nltgv2_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    P->nonportable_set = true;
+  }
   ClusterArgs a;
   a.g = graph_view(c);
   a.eplan = P->eplan;
+  a.pplan = P->pplan;
+  a.hplan = P->hplan;
   a.vpart = P->vpart;
   a.epart = P->epart;
+  a.hpart = P->hpart;
+  a.cinfo = P->cinfo;
   a.capV = P->capV;
+  a.capH = P->capH;
   a.capI = P->capI;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(c->S * C));
@@ -438,6 +594,7 @@ static int solve_cluster(fb_ctx* c, int iters, const fb_nltgv2_params* p) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const float tl = p->step_x * p->data_factor;
+  ProfScope ps(c, FB_PROF_SOLVE);  // events hug the launch: host-side planning is not kernel time
   FB_CUDA(c, cudaLaunchKernelEx(&cfg, k_nltgv2_cluster, a, iters, p->step_q, p->step_x, tl, p->theta, p->x_min, p->x_max));
   c->launches++;
   return FB_OK;

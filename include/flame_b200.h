@@ -188,6 +188,38 @@ int fb_graph_bind_features(fb_ctx* ctx, int stream, const int32_t* vertex_featur
  * Vertices whose feature is dead keep their previous data term with weight 0. */
 int fb_graph_data_from_features(fb_ctx* ctx, int adaptive_weights);
 
+/* ------------------------------------------------------------------ one frame of every stream
+ * The per-frame hot path of flame::Flame::update (/root/reference/src/flame_nodelet.cc:634) for a
+ * batch, in one call: [new poseframe: load it, re-initialise the filters] -> load the new frame ->
+ * epipolar update -> data-term assembly -> `iters` NLTGV2-L1 iterations -> optional D2H of x.
+ * Images come from host memory (pitch == width) or, when the image pointer arrays are NULL, from
+ * the device pool. With x_out == NULL nothing is copied back and the call does not synchronise. */
+typedef struct {
+  int new_poseframe;
+  int ref_slot, cmp_slot;
+  const uint8_t* const* ref_images; /* [n_streams] host images, or NULL: use ref_pool_idx */
+  const uint8_t* const* cmp_images; /* [n_streams] host images, or NULL: use cmp_pool_idx */
+  const int32_t* ref_pool_idx;      /* [n_streams] */
+  const int32_t* cmp_pool_idx;      /* [n_streams] */
+  const float* ref_poses;           /* [n_streams*7], read when new_poseframe */
+  const float* cmp_poses;           /* [n_streams*7] */
+  float mu0, var0;                  /* prior of re-initialised features */
+  int adaptive_weights;
+  int iters, variant;
+  fb_nltgv2_params rparams;
+  float* x_out;                     /* host [n_streams*max_vertices] or NULL */
+} fb_step_desc;
+int fb_hotpath_step(fb_ctx* ctx, const fb_step_desc* d);
+
+/* ------------------------------------------------------------------ triangulation (host, no GPU needed)
+ * Stands in for the `triangulate` stage (/root/reference/src/utils.cc:154; the external core wraps
+ * Shewchuk's Triangle).  Exact-predicate incremental Delaunay of n pixel positions pts_xy[2n]
+ * (snapped to 1/64 px).  tris: capacity 3*2n ints, edges: capacity 2*3n ints (canonical: i<j,
+ * sorted by (i,j) -- directly usable by fb_graph_set).  Duplicate points are left unreferenced.
+ * Returns FB_OK, or FB_E_ARG when the points are degenerate (n < 3 or all collinear). */
+int fb_delaunay(int n, const float* pts_xy, int32_t* tris, int32_t* n_tris, int32_t* edges,
+                int32_t* n_edges);
+
 /* ------------------------------------------------------------------ mesh -> dense inverse depth
  * Stands in for the `interpolate` stage + flame::Flame::getInverseDepthMap /
  * getFilteredInverseDepthMap (/root/reference/src/flame_nodelet.cc:682-688). */
