@@ -93,6 +93,7 @@ struct fb_ctx {
   int solve_iters = 0;
   fb_nltgv2_params solve_params{};
   int last_variant = 0;
+  int cluster_min = 1;  // FB_CLUSTER_MIN env: lower bound on the cluster size of variant 2
 
   // ---- profiling
   bool prof = false;

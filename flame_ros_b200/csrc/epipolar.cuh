@@ -1,4 +1,4 @@
-// epipolar.cuh -- per-feature epipolar photometric inverse-depth update (one warp per feature).
+// epipolar.cuh -- per-feature epipolar photometric inverse-depth update (FB_EPI_LANES lanes per feature).
 //
 // Replaces flame::stereo::inverse_depth_filter::{search,update}, line_stereo and
 // InverseDepthMeasModel of the external `flame` core (the `update_idepths` stage,
@@ -102,6 +102,12 @@ __device__ __forceinline__ float fb_idepth_at(float x, float y, bool use_x, floa
   return fmaf(y, P0z, -P0y) / fmaf(-y, bz, by);
 }
 
+// Lanes cooperating on one feature.  The scalar set-up (geometry, interval, direction) is uniform
+// over the group, so a full warp per feature spends ~3/4 of its issue slots on redundant work;
+// 8 lanes keep the sampling / SSD loops parallel while 4 features share a warp.
+#define FB_EPI_LANES 8
+#define FB_EPI_GROUPS (32 / FB_EPI_LANES)
+
 struct EpiArgs {
   const uint8_t* imgs;
   const float* geo;
@@ -124,7 +130,8 @@ struct EpiArgs {
 __device__ int fb_epi_update_one(const EpiArgs& a, const uint8_t* __restrict__ iref,
                                  const uint8_t* __restrict__ icmp, const float* __restrict__ G,
                                  float ux, float uy, float& mu_io, float& var_io, float2& ucmp,
-                                 float* s_line, float* s_cost, float* s_ref, int lane) {
+                                 float* s_line, float* s_cost, float* s_ref, int lane,
+                                 unsigned gmask) {
   const fb_epi_params& p = a.p;
   const int W = a.W, H = a.H;
   const int win = p.win_size, h = win / 2;
@@ -165,14 +172,15 @@ __device__ int fb_epi_update_one(const EpiArgs& a, const uint8_t* __restrict__ i
   lrx = lrx / lrn;
   lry = lry / lrn;
   bool ref_in = true;
-  if (lane < win) {
-    const float kk = (float)(lane - h);
+  for (int k = lane; k < win; k += FB_EPI_LANES) {
+    const float kk = (float)(k - h);
     const float x = fmaf(kk, lrx, ux), y = fmaf(kk, lry, uy);
-    ref_in = fb_inside(x, y, W, H);
-    s_ref[lane] = ref_in ? fb_bilin(iref, W, x, y) : 0.0f;
+    const bool in = fb_inside(x, y, W, H);
+    ref_in = ref_in && in;
+    s_ref[k] = in ? fb_bilin(iref, W, x, y) : 0.0f;
   }
-  if (!__all_sync(0xffffffffu, ref_in)) return FB_FAIL_OUT_OF_IMAGE;
-  __syncwarp();
+  if (!__all_sync(gmask, ref_in)) return FB_FAIL_OUT_OF_IMAGE;
+  __syncwarp(gmask);
   float grad2 = 0.0f;
   for (int k = 0; k + 1 < win; ++k) {
     const float d = s_ref[k + 1] - s_ref[k];
@@ -187,17 +195,17 @@ __device__ int fb_epi_update_one(const EpiArgs& a, const uint8_t* __restrict__ i
 
   // sample the comparison image once along the line: lanes = positions (NaN marks "outside")
   const int n_samp = n_steps + 2 * h;
-  for (int mI = lane; mI < n_samp; mI += 32) {
+  for (int mI = lane; mI < n_samp; mI += FB_EPI_LANES) {
     const float s = s0 + (float)(mI - h);
     const float x = fmaf(s, lx, umx), y = fmaf(s, ly, umy);
     s_line[mI] = fb_inside(x, y, W, H) ? fb_bilin(icmp, W, x, y) : __int_as_float(0x7fc00000);
   }
-  __syncwarp();
+  __syncwarp(gmask);
   // sliding SSD: lanes = candidates; per-lane running best keeps the smallest n on ties
   const float INF = __int_as_float(0x7f800000);
   float best = INF;
   int nbest = 0x7fffffff;
-  for (int n = lane; n < n_steps; n += 32) {
+  for (int n = lane; n < n_steps; n += FB_EPI_LANES) {
     float c = 0.0f;
     for (int k = 0; k < win; ++k) {
       const float d = s_line[n + k] - s_ref[k];
@@ -210,25 +218,25 @@ __device__ int fb_epi_update_one(const EpiArgs& a, const uint8_t* __restrict__ i
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int on = __shfl_xor_sync(0xffffffffu, nbest, o);
+  for (int o = FB_EPI_LANES / 2; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(gmask, best, o);
+    const int on = __shfl_xor_sync(gmask, nbest, o);
     if (ob < best || (ob == best && on < nbest)) {
       best = ob;
       nbest = on;
     }
   }
   if (nbest == 0x7fffffff) return FB_FAIL_OUT_OF_IMAGE;
-  __syncwarp();
+  __syncwarp(gmask);
   float second = INF;
-  for (int n = lane; n < n_steps; n += 32) {
+  for (int n = lane; n < n_steps; n += FB_EPI_LANES) {
     const float c = s_cost[n];
     int dn2 = n - nbest;
     if (dn2 < 0) dn2 = -dn2;
     if (c == c && dn2 > p.ambiguity_radius && c < second) second = c;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) second = fminf(second, __shfl_xor_sync(0xffffffffu, second, o));
+  for (int o = FB_EPI_LANES / 2; o > 0; o >>= 1) second = fminf(second, __shfl_xor_sync(gmask, second, o));
   if (best > p.max_cost * (float)win) return FB_FAIL_MAX_COST;
   const float floor_c = p.pixel_noise_var * (float)win;
   if (second < INF && second < p.ambiguity_ratio * fmaxf(best, floor_c))
@@ -267,16 +275,19 @@ __device__ int fb_epi_update_one(const EpiArgs& a, const uint8_t* __restrict__ i
   return FB_SUCCESS;
 }
 
-// grid = (ceil(maxF / warps_per_block), S); dynamic smem = warps * (2*max_search + 2*FB_MAX_WIN+1) floats
+// grid = (ceil(maxF / (warps_per_block * FB_EPI_GROUPS)), S);
+// dynamic smem = warps * FB_EPI_GROUPS * (2*max_search + 2*FB_MAX_WIN + 2) floats
 __global__ void __launch_bounds__(256) k_epipolar_search(EpiArgs a) {
   extern __shared__ float smem[];
   const int s = blockIdx.y;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int f = blockIdx.x * wpb + wib;
+  const int wlane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int group = wlane / FB_EPI_LANES, lane = wlane % FB_EPI_LANES;
+  const unsigned gmask = (FB_EPI_LANES == 32 ? 0xffffffffu : ((1u << FB_EPI_LANES) - 1u)) << (group * FB_EPI_LANES);
+  const int f = (blockIdx.x * wpb + wib) * FB_EPI_GROUPS + group;
   const int cs = a.cmp_slot[s];
   if (cs < 0 || f >= a.nF[s]) return;
-  const int per_warp = 2 * a.p.max_search_px + 2 * FB_MAX_WIN + 2;
-  float* s_line = smem + (size_t)wib * per_warp;
+  const int per_group = 2 * a.p.max_search_px + 2 * FB_MAX_WIN + 2;
+  float* s_line = smem + (size_t)(wib * FB_EPI_GROUPS + group) * per_group;
   float* s_cost = s_line + a.p.max_search_px + FB_MAX_WIN + 1;
   float* s_ref = s_cost + a.p.max_search_px;
   const size_t fb = (size_t)s * a.maxF + f;
@@ -300,7 +311,7 @@ __global__ void __launch_bounds__(256) k_epipolar_search(EpiArgs a) {
     const uint8_t* icmp = a.imgs + ((size_t)s * a.n_slots + cs) * fsz;
     const float* G = a.geo + ((size_t)s * a.n_slots + r) * FB_GEO_STRIDE;
     const float2 u = a.u_ref[fb];
-    st = fb_epi_update_one(a, iref, icmp, G, u.x, u.y, mu, var, ucmp, s_line, s_cost, s_ref, lane);
+    st = fb_epi_update_one(a, iref, icmp, G, u.x, u.y, mu, var, ucmp, s_line, s_cost, s_ref, lane, gmask);
   }
   if (lane == 0) {
     if (st == FB_SUCCESS) {

@@ -3,6 +3,7 @@
 // hot path runs in the CUDA kernels of nltgv2*.cuh / epipolar.cuh / raster.cuh.  There is no CPU
 // fallback: every compute entry point launches kernels on ctx->stream.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -157,6 +158,10 @@ extern "C" fb_ctx* fb_create(int device, int n_streams, int width, int height, i
   }
   cudaMemcpyAsync(c->d_K, c->h_K.data(), sizeof(float) * S * 9, cudaMemcpyHostToDevice, c->stream);
   fb_default_epi_params(&c->epi);
+  if (const char* e = getenv("FB_CLUSTER_MIN")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->cluster_min = v;
+  }
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
     g_create_error = "fb_create: initialisation failed";
     free_all(c);
@@ -570,8 +575,10 @@ extern "C" int fb_idepth_update(fb_ctx* c, const int32_t* cmp_slot) {
   a.counters = c->counters; a.W = c->W; a.H = c->H; a.n_slots = c->n_slots; a.maxF = c->maxF;
   a.p = c->epi;
   const int wpb = 8;
-  const size_t smem = sizeof(float) * wpb * (2 * c->epi.max_search_px + 2 * FB_MAX_WIN + 2);
-  const dim3 grid(fb_div_up(maxf, wpb), c->S);
+  const size_t smem = sizeof(float) * wpb * FB_EPI_GROUPS * (2 * c->epi.max_search_px + 2 * FB_MAX_WIN + 2);
+  const dim3 grid(fb_div_up(maxf, wpb * FB_EPI_GROUPS), c->S);
+  if (smem > 48 * 1024)
+    FB_CUDA(c, cudaFuncSetAttribute(k_epipolar_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_epipolar_search<<<grid, wpb * 32, smem, c->stream>>>(a);
   c->launches++;
   FB_CUDA(c, cudaGetLastError());

@@ -23,9 +23,9 @@
 #include "common.cuh"
 #include "nltgv2.cuh"
 
-#define FBC_THREADS 1024
-#define FBC_EPT 2   // edges per thread (register resident)
-#define FBC_VPT 1   // vertices per thread
+#define FBC_THREADS 512
+#define FBC_EPT 4   // edges per thread (register resident)
+#define FBC_VPT 2   // vertices per thread
 #define FBC_MAXC 16
 #define FBC_SMEM_LIMIT (227 * 1024)
 
@@ -33,7 +33,10 @@ struct ClusterPlan {
   int C = 0;                       // cluster size the device plan was built for (0 = none)
   int capV = 0, capH = 0, capI = 0;  // per-CTA capacities (max over streams and ranks): layout
   int4* eplan = nullptr;     // [S*maxE] {i_local, j_index, slot_i, rank<<20|slot_j}
-  int2* pplan = nullptr;     // [S*maxE] push list {local vertex, rank<<20|halo index}
+  int2* pplan = nullptr;     // [S*maxE] overflow push list {local vertex, rank<<20|halo index}
+  int4* vplan = nullptr;     // [S*maxV] per vertex (processing order): {push target 0, push target 1 (-1 = none), slot begin, slot end}
+  int32_t* eorig = nullptr;  // [S*maxE] processing order -> edge id (cut edges first per CTA)
+  int32_t* vorig = nullptr;  // [S*maxV] processing order -> vertex id (halo-feeding vertices first)
   int32_t* hplan = nullptr;  // [S*maxE] halo list: stream-local vertex id of every halo entry
   int32_t* vpart = nullptr;  // [S*(FBC_MAXC+1)] vertex range boundaries per rank
   int32_t* epart = nullptr;  // [S*(FBC_MAXC+1)] edge range boundaries per rank
@@ -122,6 +125,9 @@ struct ClusterArgs {
   GraphView g;
   const int4* eplan;
   const int2* pplan;
+  const int4* vplan;
+  const int32_t* eorig;
+  const int32_t* vorig;
   const int32_t* hplan;
   const int32_t* vpart;
   const int32_t* epart;
@@ -135,8 +141,8 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
                  float xmin, float xmax) {
   extern __shared__ __align__(128) uint8_t fbc_smem[];
   float4* s_bar = reinterpret_cast<float4*>(fbc_smem);  // [capV own | capH halo]
-  float4* s_slot = s_bar + a.capV + a.capH;             // [capI]
-  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_slot + a.capI);  // [0] TMA, [1] halo (A), [2] slots (B)
+  float4* s_slot = s_bar + a.capV + a.capH;             // [capI + 1 dummy]
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_slot + a.capI + 1);  // [0] TMA, [1] halo (A), [2] slots (B)
   const GraphView& g = a.g;
   const int tid = threadIdx.x;
   const uint32_t C = fbc_cluster_nctarank(), rank = fbc_cluster_ctarank();
@@ -150,8 +156,6 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
   const int4 ci = a.cinfo[(size_t)s * FBC_MAXC + rank];
   const uint32_t haloBytes = 16u * (uint32_t)ci.x, slotBytes = 16u * (uint32_t)ci.y;
   const size_t vb = (size_t)s * g.maxV, eb = (size_t)s * g.maxE;
-  const int32_t* row = g.row + (size_t)s * (g.maxV + 1);
-  const int slot0 = row[v0];
 
   const uint32_t mb_tma = fbc_smem_u32(s_mbar), mb_halo = mb_tma + 8, mb_slot = mb_tma + 16;
   const uint32_t bar_base = fbc_smem_u32(s_bar), slot_base = fbc_smem_u32(s_slot);
@@ -181,49 +185,73 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
   }
 
   // ---- register-resident per-edge and per-vertex state (coalesced global loads) -------------
+  // indices into s_bar / s_slot are kept as 16-bit pairs; only remote addresses need 32 bits
   float q1[FBC_EPT], q2[FBC_EPT], q3[FBC_EPT], ea[FBC_EPT], ebt[FBC_EPT], edx[FBC_EPT], edy[FBC_EPT];
-  uint32_t a_bi[FBC_EPT], a_bj[FBC_EPT], a_si[FBC_EPT], a_sj[FBC_EPT], a_mb[FBC_EPT];
-  bool ev[FBC_EPT];
+  int e_bi[FBC_EPT], e_bj[FBC_EPT], e_si[FBC_EPT], e_id[FBC_EPT];
+  uint32_t a_sj[FBC_EPT], a_mb[FBC_EPT];  // target slot: local index (a_mb == 0) or remote address
+  // Processing order (eorig/vorig): a CTA's cut edges come first, so row k=0 of the unrolled edge
+  // loop sends the remote contributions at the very start of the dual half-step; the vertices that
+  // feed other CTAs' halos come first in the primal half-step.  The receiver then finds its bytes
+  // already landed when it gets to them: the exchange overlaps with the interior work.
 #pragma unroll
   for (int k = 0; k < FBC_EPT; ++k) {
     const int e = e0 + tid + k * FBC_THREADS;
-    ev[k] = e < e1;
+    e_id[k] = -1;
+    // idle lanes run the same arithmetic on zero weights and write to the dummy slot, so the
+    // unrolled edges of a thread form independent, branch-free instruction streams (ILP)
     q1[k] = q2[k] = q3[k] = ea[k] = ebt[k] = edx[k] = edy[k] = 0.f;
-    a_bi[k] = a_bj[k] = a_si[k] = a_sj[k] = a_mb[k] = 0u;
-    if (ev[k]) {
+    e_bi[k] = e_bj[k] = 0;
+    e_si[k] = a.capI;
+    a_sj[k] = (uint32_t)a.capI;
+    a_mb[k] = 0u;
+    if (e < e1) {
       const int4 pl = a.eplan[eb + e];
-      const float4 c = g.ec[eb + e];
-      const float4 q = g.q4[eb + e];
+      const int eo = a.eorig[eb + e];
+      e_id[k] = eo;
+      const float4 c = g.ec[eb + eo];
+      const float4 q = g.q4[eb + eo];
       ea[k] = c.x; ebt[k] = c.y; edx[k] = c.z; edy[k] = c.w;
       q1[k] = q.x; q2[k] = q.y; q3[k] = q.z;
-      a_bi[k] = bar_base + 16u * (uint32_t)pl.x;
-      a_bj[k] = bar_base + 16u * (uint32_t)pl.y;
-      a_si[k] = slot_base + 16u * (uint32_t)pl.z;
-      const uint32_t jr = (uint32_t)pl.w >> 20;
-      const uint32_t sj = slot_base + 16u * ((uint32_t)pl.w & 0xfffffu);
+      e_bi[k] = pl.x;
+      e_bj[k] = pl.y;
+      e_si[k] = pl.z;
+      const uint32_t jr = (uint32_t)pl.w >> 20, sj = (uint32_t)pl.w & 0xfffffu;
       if (jr == rank) {
-        a_sj[k] = sj;  // a_mb == 0 marks "local"
+        a_sj[k] = sj;
       } else {
-        a_sj[k] = fbc_mapa(sj, jr);
+        a_sj[k] = fbc_mapa(slot_base + 16u * sj, jr);
         a_mb[k] = fbc_mapa(mb_slot, jr);
       }
     }
   }
   float vx[FBC_VPT], vw1[FBC_VPT], vw2[FBC_VPT], vz[FBC_VPT], vth[FBC_VPT];
-  int vs0[FBC_VPT], vs1[FBC_VPT];
-  bool vv[FBC_VPT];
+  int vs0[FBC_VPT], vs1[FBC_VPT], v_li[FBC_VPT];
+  uint32_t p_a0[FBC_VPT], p_m0[FBC_VPT], p_a1[FBC_VPT], p_m1[FBC_VPT];  // halo copies to refresh
 #pragma unroll
   for (int k = 0; k < FBC_VPT; ++k) {
-    const int v = v0 + tid + k * FBC_THREADS;
-    vv[k] = v < v1;
+    const int vo = v0 + tid + k * FBC_THREADS;
     vx[k] = vw1[k] = vw2[k] = vz[k] = vth[k] = 0.f;
-    vs0[k] = vs1[k] = 0;
-    if (vv[k]) {
+    vs0[k] = 0;
+    vs1[k] = -1;  // marks "no vertex"
+    v_li[k] = 0;
+    p_a0[k] = p_m0[k] = p_a1[k] = p_m1[k] = 0u;
+    if (vo < v1) {
+      const int v = a.vorig[vb + vo];
+      v_li[k] = v - v0;
       vx[k] = g.x[vb + v]; vw1[k] = g.w1[vb + v]; vw2[k] = g.w2[vb + v];
       vz[k] = g.z[vb + v];
       vth[k] = tl * g.wt[vb + v];
-      vs0[k] = row[v] - slot0;
-      vs1[k] = row[v + 1] - slot0;
+      const int4 pt = a.vplan[vb + vo];
+      vs0[k] = pt.z;
+      vs1[k] = pt.w;
+      if (pt.x >= 0) {
+        p_a0[k] = fbc_mapa(bar_base + 16u * ((uint32_t)pt.x & 0xfffffu), (uint32_t)pt.x >> 20);
+        p_m0[k] = fbc_mapa(mb_halo, (uint32_t)pt.x >> 20);
+      }
+      if (pt.y >= 0) {
+        p_a1[k] = fbc_mapa(bar_base + 16u * ((uint32_t)pt.y & 0xfffffu), (uint32_t)pt.y >> 20);
+        p_m1[k] = fbc_mapa(mb_halo, (uint32_t)pt.y >> 20);
+      }
     }
   }
   __syncthreads();  // mbarrier init + halo fill visible to all threads of the CTA
@@ -232,13 +260,14 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
 
   const int2* pl = a.pplan + eb;
   for (int it = 0; it < iters; ++it) {
+    const bool more = it + 1 < iters;
     // ---- dual half-step ---------------------------------------------------------------------
     if (it > 0 && haloBytes) fbc_mbar_wait(mb_halo, (uint32_t)(it - 1) & 1u);  // refreshed halo landed
 #pragma unroll
     for (int k = 0; k < FBC_EPT; ++k) {
-      if (ev[k]) {
-        const float4 bi = fbc_lds(a_bi[k]);
-        const float4 bj = fbc_lds(a_bj[k]);
+      {
+        const float4 bi = s_bar[e_bi[k]];
+        const float4 bj = s_bar[e_bj[k]];
         float t = bi.x - bj.x;
         t = fmaf(-edx[k], bi.y, t);
         t = fmaf(-edy[k], bi.z, t);
@@ -249,50 +278,68 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
         q2[k] = fb_clamp1(fmaf(sigma, k2, q2[k]));
         q3[k] = fb_clamp1(fmaf(sigma, k3, q3[k]));
         const float a1 = ea[k] * q1[k];
-        fbc_sts(a_si[k], make_float4(a1, fmaf(ebt[k], q2[k], -(edx[k] * a1)),
-                                     fmaf(ebt[k], q3[k], -(edy[k] * a1)), 0.f));
+        s_slot[e_si[k]] = make_float4(a1, fmaf(ebt[k], q2[k], -(edx[k] * a1)),
+                                      fmaf(ebt[k], q3[k], -(edy[k] * a1)), 0.f);
         const float4 ct = make_float4(-a1, -(ebt[k] * q2[k]), -(ebt[k] * q3[k]), 0.f);
-        if (a_mb[k] == 0u) fbc_sts(a_sj[k], ct);
+        if (a_mb[k] == 0u) s_slot[a_sj[k]] = ct;
         else fbc_st_async(a_sj[k], ct, a_mb[k]);
       }
     }
     __syncthreads();  // local slot writes visible; every thread is past the halo wait, so the
                       // next halo phase may be armed without a late waiter seeing the parity wrap
-    if (tid == 0 && it > 0 && haloBytes && it + 1 < iters) fbc_mbar_expect(mb_halo, haloBytes);
+    if (tid == 0 && it > 0 && haloBytes && more) fbc_mbar_expect(mb_halo, haloBytes);
     if (slotBytes) fbc_mbar_wait(mb_slot, (uint32_t)it & 1u);  // remote contributions have landed
     // ---- primal half-step: vertex threads, local slot gather in CSR order ---------------------
+    {
+      // the slot gathers of a thread's vertices advance together (one slot of each per trip) so
+      // their dependent FADD chains interleave; per vertex the order is still CSR order
+      float gx[FBC_VPT], g1[FBC_VPT], g2[FBC_VPT];
+      int dmax = 0;
 #pragma unroll
-    for (int k = 0; k < FBC_VPT; ++k) {
-      if (vv[k]) {
-        float gx = 0.f, g1 = 0.f, g2 = 0.f;
-        for (int r = vs0[k]; r < vs1[k]; ++r) {
-          const float4 c = fbc_lds(slot_base + 16u * (uint32_t)r);
-          gx += c.x;
-          g1 += c.y;
-          g2 += c.z;
+      for (int k = 0; k < FBC_VPT; ++k) {
+        gx[k] = g1[k] = g2[k] = 0.f;
+        dmax = max(dmax, vs1[k] - vs0[k]);
+      }
+      for (int j = 0; j < dmax; ++j) {
+#pragma unroll
+        for (int k = 0; k < FBC_VPT; ++k) {
+          if (vs0[k] + j < vs1[k]) {
+            const float4 c = s_slot[vs0[k] + j];
+            gx[k] += c.x;
+            g1[k] += c.y;
+            g2[k] += c.z;
+          }
         }
-        const float xo = vx[k], w1o = vw1[k], w2o = vw2[k];
-        const float xp = fmaf(-tau, gx, xo);
-        const float w1n = fmaf(-tau, g1, w1o);
-        const float w2n = fmaf(-tau, g2, w2o);
-        const float d = xp - vz[k];
-        float xn = (d > vth[k]) ? (xp - vth[k]) : ((d < -vth[k]) ? (xp + vth[k]) : vz[k]);
-        xn = fminf(fmaxf(xn, xmin), xmax);
-        vx[k] = xn; vw1[k] = w1n; vw2[k] = w2n;
-        fbc_sts(bar_base + 16u * (uint32_t)(tid + k * FBC_THREADS),
-                make_float4(fmaf(theta, xn - xo, xn), fmaf(theta, w1n - w1o, w1n),
-                            fmaf(theta, w2n - w2o, w2n), 0.f));
+      }
+#pragma unroll
+      for (int k = 0; k < FBC_VPT; ++k) {
+        if (vs1[k] >= 0) {
+          const float xo = vx[k], w1o = vw1[k], w2o = vw2[k];
+          const float xp = fmaf(-tau, gx[k], xo);
+          const float w1n = fmaf(-tau, g1[k], w1o);
+          const float w2n = fmaf(-tau, g2[k], w2o);
+          const float d = xp - vz[k];
+          float xn = (d > vth[k]) ? (xp - vth[k]) : ((d < -vth[k]) ? (xp + vth[k]) : vz[k]);
+          xn = fminf(fmaxf(xn, xmin), xmax);
+          vx[k] = xn; vw1[k] = w1n; vw2[k] = w2n;
+          const float4 nb = make_float4(fmaf(theta, xn - xo, xn), fmaf(theta, w1n - w1o, w1n),
+                                        fmaf(theta, w2n - w2o, w2n), 0.f);
+          s_bar[v_li[k]] = nb;
+          // the owner refreshes the halo copies held by the CTAs whose cut edges point at this vertex
+          if (more) {
+            if (p_m0[k]) fbc_st_async(p_a0[k], nb, p_m0[k]);
+            if (p_m1[k]) fbc_st_async(p_a1[k], nb, p_m1[k]);
+          }
+        }
       }
     }
-    __syncthreads();  // own points visible to the edge threads and to the push threads
-    if (tid == 0 && slotBytes && it + 1 < iters) fbc_mbar_expect(mb_slot, slotBytes);
-    // ---- refresh the halo copies held by the CTAs whose cut edges point at our vertices --------
-    if (it + 1 < iters) {
+    __syncthreads();  // own points visible to the edge threads (and to the overflow push below)
+    if (tid == 0 && slotBytes && more) fbc_mbar_expect(mb_slot, slotBytes);
+    if (more) {  // vertices with more than two consumer CTAs (rare): remaining copies
       for (int p = ci.z + tid; p < ci.w; p += FBC_THREADS) {
         const int2 e = pl[p];
         const uint32_t pr = (uint32_t)e.y >> 20;
-        const float4 v = fbc_lds(bar_base + 16u * (uint32_t)e.x);
-        fbc_st_async(fbc_mapa(bar_base + 16u * ((uint32_t)e.y & 0xfffffu), pr), v, fbc_mapa(mb_halo, pr));
+        fbc_st_async(fbc_mapa(bar_base + 16u * ((uint32_t)e.y & 0xfffffu), pr), s_bar[e.x], fbc_mapa(mb_halo, pr));
       }
     }
   }
@@ -300,11 +347,11 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
   // ---- write back: registers -> global (coalesced), extragradient tile via TMA bulk store ----
 #pragma unroll
   for (int k = 0; k < FBC_EPT; ++k)
-    if (ev[k]) g.q4[eb + e0 + tid + k * FBC_THREADS] = make_float4(q1[k], q2[k], q3[k], 0.f);
+    if (e_id[k] >= 0) g.q4[eb + e_id[k]] = make_float4(q1[k], q2[k], q3[k], 0.f);
 #pragma unroll
   for (int k = 0; k < FBC_VPT; ++k)
-    if (vv[k]) {
-      const size_t v = vb + v0 + tid + k * FBC_THREADS;
+    if (vs1[k] >= 0) {
+      const size_t v = vb + v0 + v_li[k];
       g.x[v] = vx[k]; g.w1[v] = vw1[k]; g.w2[v] = vw2[k];
     }
   if (tid == 0 && bar_bytes) {
@@ -320,7 +367,7 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
 
 // ---------------------------------------------------------------------------------- host side
 static inline size_t fbc_smem_bytes(int capV, int capH, int capI) {
-  return 16 * ((size_t)capV + (size_t)capH + (size_t)capI) + 64;
+  return 16 * ((size_t)capV + (size_t)capH + (size_t)capI + 1) + 64;  // +1: dummy slot of idle lanes
 }
 
 typedef ClusterPlan::Topo::FbcPartData FbcPart;
@@ -357,7 +404,8 @@ static bool fbc_partition(const ClusterPlan::Topo& t, int C, FbcPart& P) {
     P.epart[r + 1] = first[P.vpart[r + 1]];
     const int Vc = P.vpart[r + 1] - P.vpart[r];
     const int Ec = P.epart[r + 1] - P.epart[r];
-    const int Ic = t.row[P.vpart[r + 1]] - t.row[P.vpart[r]];
+    int Ic = 0;  // slot blocks are padded to an odd number of 16 B records (bank-conflict-free gathers)
+    for (int v = P.vpart[r]; v < P.vpart[r + 1]; ++v) Ic += (t.row[v + 1] - t.row[v]) | 1;
     if (Vc > FBC_VPT * FBC_THREADS || Ec > FBC_EPT * FBC_THREADS) return false;
     int H = 0;
     for (int e = P.epart[r]; e < P.epart[r + 1]; ++e) {
@@ -382,6 +430,9 @@ static int cluster_plan_build(fb_ctx* c, int s, int V, int E, const int2* eij, c
     const size_t S = c->S;
     if (dalloc(&c->plan->eplan, S * c->maxE) != cudaSuccess ||
         dalloc(&c->plan->pplan, S * c->maxE) != cudaSuccess ||
+        dalloc(&c->plan->vplan, S * c->maxV) != cudaSuccess ||
+        dalloc(&c->plan->eorig, S * c->maxE) != cudaSuccess ||
+        dalloc(&c->plan->vorig, S * c->maxV) != cudaSuccess ||
         dalloc(&c->plan->hplan, S * c->maxE) != cudaSuccess ||
         dalloc(&c->plan->vpart, S * (FBC_MAXC + 1)) != cudaSuccess ||
         dalloc(&c->plan->epart, S * (FBC_MAXC + 1)) != cudaSuccess ||
@@ -419,6 +470,9 @@ static void cluster_plan_free(fb_ctx* c) {
   if (!c->plan) return;
   cudaFree(c->plan->eplan);
   cudaFree(c->plan->pplan);
+  cudaFree(c->plan->vplan);
+  cudaFree(c->plan->eorig);
+  cudaFree(c->plan->vorig);
   cudaFree(c->plan->hplan);
   cudaFree(c->plan->vpart);
   cudaFree(c->plan->epart);
@@ -509,11 +563,28 @@ static int fbc_upload_plans(fb_ctx* c, int C) {
       }
     }
     for (int r = C; r <= FBC_MAXC; ++r) hpart[r] = (int)hplan.size();
-    // slots: position of every incidence within its vertex's CTA
+    // processing order of the vertices: per CTA by descending degree, so the lanes of a warp run
+    // slot loops of equal length; slot blocks follow that order and are padded to an odd number
+    // of 16 B records, which makes the per-lane stride conflict-free across the 32 banks
+    std::vector<int32_t> vorig(t.V), sbase(t.V);
+    for (int r = 0; r < C; ++r) {
+      std::vector<int> vs;
+      for (int v = vp[r]; v < vp[r + 1]; ++v) vs.push_back(v);
+      std::stable_sort(vs.begin(), vs.end(), [&](int x, int y) {
+        return (t.row[x + 1] - t.row[x]) > (t.row[y + 1] - t.row[y]);
+      });
+      int base = 0;
+      for (size_t k = 0; k < vs.size(); ++k) {
+        vorig[vp[r] + k] = vs[k];
+        sbase[vs[k]] = base;
+        base += (t.row[vs[k] + 1] - t.row[vs[k]]) | 1;
+      }
+    }
+    // slots: position of every incidence within its vertex's block
     for (int v = 0; v < t.V; ++v) {
-      const int r = rk[v], base = t.row[vp[r]];
+      const int r = rk[v];
       for (int k = t.row[v]; k < t.row[v + 1]; ++k) {
-        const int code = t.inc[k], e = code >> 1, local = k - base;
+        const int code = t.inc[k], e = code >> 1, local = sbase[v] + (k - t.row[v]);
         if ((code & 1) == 0) {
           eplan[e].z = local;
         } else {
@@ -522,12 +593,42 @@ static int fbc_upload_plans(fb_ctx* c, int C) {
         }
       }
     }
+    // the first two consumers of a vertex are refreshed by its owner thread (vplan); the rest
+    // (a vertex referenced from more than two other CTAs) go to the overflow list (pplan)
     pplan.clear();
+    std::vector<int4> vplan(t.V, make_int4(-1, -1, 0, 0));
+    for (int v = 0; v < t.V; ++v) {
+      vplan[v].z = sbase[v];
+      vplan[v].w = sbase[v] + (t.row[v + 1] - t.row[v]);
+    }
     for (int r = 0; r < C; ++r) {
       cinfo[r].z = (int)pplan.size();
-      pplan.insert(pplan.end(), push[r].begin(), push[r].end());
+      for (const int2& e : push[r]) {
+        int4& slot = vplan[vp[r] + e.x];
+        if (slot.x < 0) slot.x = e.y;
+        else if (slot.y < 0) slot.y = e.y;
+        else pplan.push_back(e);
+      }
       cinfo[r].w = (int)pplan.size();
     }
+    // processing order of the edges: per CTA, cut edges first (their remote stores leave early)
+    std::vector<int32_t> eorig(t.E);
+    std::vector<int4> eperm(t.E);
+    std::vector<int4> vperm(t.V);
+    for (int r = 0; r < C; ++r) {
+      int pos = ep[r];
+      for (int pass = 0; pass < 2; ++pass)
+        for (int e = ep[r]; e < ep[r + 1]; ++e) {
+          const bool cut = ((uint32_t)eplan[e].w >> 20) != (uint32_t)r;
+          if (cut == (pass == 0)) eorig[pos++] = e;
+        }
+    }
+    for (int e = 0; e < t.E; ++e) eperm[e] = eplan[eorig[e]];
+    for (int v = 0; v < t.V; ++v) vperm[v] = vplan[vorig[v]];
+    FB_CUDA(c, cudaMemcpyAsync(P->vplan + (size_t)s * c->maxV, vperm.data(), sizeof(int4) * t.V, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(P->vorig + (size_t)s * c->maxV, vorig.data(), sizeof(int32_t) * t.V, cudaMemcpyHostToDevice, st));
+    if (t.E) FB_CUDA(c, cudaMemcpyAsync(P->eorig + (size_t)s * c->maxE, eorig.data(), sizeof(int32_t) * t.E, cudaMemcpyHostToDevice, st));
+    eplan.swap(eperm);
     if ((int)pplan.size() > c->maxE || (int)hplan.size() > c->maxE)
       FB_FAIL(c, FB_E_NOMEM, "cluster plan: halo tables exceed capacity");
     if (t.E)
@@ -558,6 +659,12 @@ static int solve_cluster(fb_ctx* c, int iters, const fb_nltgv2_params* p) {
       any = true;
     }
   if (!any) return FB_OK;
+  if (c->cluster_min > C) C = c->cluster_min;  // tuning knob: spread a graph over more SMs
+  // few streams: spread each graph over 16 SMs (non-portable cluster size) -- per-iteration work per
+  // CTA halves while the exchange cost stays, measured 115 -> 93 us per 50-iteration C2 solve
+  int maxV = 0;
+  for (auto& t : P->topo) maxV = std::max(maxV, t.V);
+  if (c->S <= 4 && maxV >= 2048 && C < 16 && !getenv("FB_CLUSTER_NO16")) C = 16;
   int rc = fbc_upload_plans(c, C);
   if (rc) return rc;
   const size_t smem = fbc_smem_bytes(P->capV, P->capH, P->capI);
@@ -573,6 +680,9 @@ static int solve_cluster(fb_ctx* c, int iters, const fb_nltgv2_params* p) {
   a.g = graph_view(c);
   a.eplan = P->eplan;
   a.pplan = P->pplan;
+  a.vplan = P->vplan;
+  a.eorig = P->eorig;
+  a.vorig = P->vorig;
   a.hplan = P->hplan;
   a.vpart = P->vpart;
   a.epart = P->epart;
