@@ -27,7 +27,10 @@ SYMBOLS = [
     "fb_features_set", "fb_features_get", "fb_features_reinit", "fb_idepth_update", "fb_idepth_counters",
     "fb_project_features", "fb_graph_bind_features", "fb_graph_data_from_features", "fb_mesh_set",
     "fb_interpolate", "fb_profile_enable", "fb_profile_reset", "fb_profile_get", "fb_launch_count",
-    "fb_last_solver_variant", "fb_delaunay", "fb_hotpath_step",
+    "fb_last_solver_variant", "fb_delaunay", "fb_hotpath_step", "fb_default_update_params",
+    "fb_set_update_params", "fb_update", "fb_get_mesh_sizes", "fb_get_mesh", "fb_get_idepthmap",
+    "fb_get_raw_idepths", "fb_get_stat", "fb_update_poseframe_poses", "fb_prune_poseframes",
+    "fb_frame_gradient", "fb_frame_pyr_down", "fb_detect", "fb_get_feature_pool",
 ]
 
 
@@ -57,6 +60,15 @@ class TriFilterParams(C.Structure):
                 ("oblique_idepth_diff_factor", C.c_float), ("oblique_idepth_diff_abs", C.c_float),
                 ("do_edge_length", C.c_int), ("edge_length_thresh", C.c_float),
                 ("do_idepth", C.c_int), ("min_triangle_idepth", C.c_float)]
+
+
+class UpdateParams(C.Structure):
+    """fb_update_params: the subset of flame::Params that drives flame::Flame::update
+    (/root/reference/src/flame_nodelet.cc:225-259)."""
+    _fields_ = [("detection_win_size", C.c_int), ("min_grad_mag", C.c_float), ("detection_border", C.c_int),
+                ("idepth_init", C.c_float), ("idepth_var_init", C.c_float), ("idepth_var_max_graph", C.c_float),
+                ("adaptive_data_weights", C.c_int), ("init_with_prediction", C.c_int), ("do_nltgv2", C.c_int),
+                ("iters", C.c_int), ("rparams", NLTGV2Params)]
 
 
 class StepDesc(C.Structure):
@@ -104,7 +116,8 @@ def load_library(build_if_missing=True):
     lib.fb_host_free.argtypes = [C.c_void_p]
     lib.fb_launch_count.restype = C.c_int64
     lib.fb_launch_count.argtypes = [C.c_void_p]
-    for name in ("fb_default_epi_params", "fb_default_nltgv2_params", "fb_default_tri_filter_params"):
+    for name in ("fb_default_epi_params", "fb_default_nltgv2_params", "fb_default_tri_filter_params",
+                 "fb_default_update_params"):
         getattr(lib, name).restype = None
     P = C.c_void_p
     I = C.c_int
@@ -122,6 +135,13 @@ def load_library(build_if_missing=True):
         "fb_mesh_set": [P, I, I, P], "fb_interpolate": [P, I, P, P, P],
         "fb_profile_enable": [P, I], "fb_profile_reset": [P], "fb_profile_get": [P, I, P, P, P],
         "fb_last_solver_variant": [P], "fb_version": [], "fb_delaunay": [I, P, P, P, P, P], "fb_hotpath_step": [P, P],
+        "fb_set_update_params": [P, P], "fb_update": [P, I, C.c_double, I, P, P, I, I],
+        "fb_get_mesh_sizes": [P, I, P, P, P], "fb_get_mesh": [P, I, P, P, P, P, P, P, P],
+        "fb_get_idepthmap": [P, I, P, P], "fb_get_raw_idepths": [P, I, P, P, P, P],
+        "fb_get_stat": [P, I, C.c_char_p, P], "fb_update_poseframe_poses": [P, I, I, P, P],
+        "fb_prune_poseframes": [P, I, I, P], "fb_frame_gradient": [P, I, I, P],
+        "fb_frame_pyr_down": [P, I, I, P], "fb_detect": [P, I, I, I, I, C.c_float, P, P, P, P],
+        "fb_get_feature_pool": [P, I, P, P, P, P, P, P],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -140,6 +160,12 @@ def default_nltgv2_params():
 def default_epi_params():
     p = EpiParams()
     load_library().fb_default_epi_params(C.byref(p))
+    return p
+
+
+def default_update_params():
+    p = UpdateParams()
+    load_library().fb_default_update_params(C.byref(p))
     return p
 
 
@@ -372,6 +398,91 @@ class Context:
         fp = C.byref(filter_params) if filter_params is not None else None
         self._ck(self._lib.fb_interpolate(self._h, stream, fp, _ptr(out), _ptr(valid)))
         return out, valid[:self._nT[stream]]
+
+    # ------------------------------------------------------------------ flame::Flame::update + getters
+    def set_update_params(self, p):
+        self._ck(self._lib.fb_set_update_params(self._h, C.byref(p)))
+
+    def update(self, stream, time, img_id, pose, gray, is_poseframe):
+        """flame::Flame::update: returns True when the mesh / depth outputs were refreshed."""
+        assert gray.dtype == np.uint8 and gray.shape == (self.H, self.W) and gray.strides[1] == 1
+        pose = _f32(pose)
+        rc = self._lib.fb_update(self._h, stream, float(time), int(img_id), _ptr(pose), _ptr(gray),
+                                 gray.strides[0], 1 if is_poseframe else 0)
+        if rc < 0:
+            self._ck(rc)
+        return rc == 1
+
+    def get_mesh(self, stream, filter_params=None):
+        V, T, E = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._ck(self._lib.fb_get_mesh_sizes(self._h, stream, C.byref(V), C.byref(T), C.byref(E)))
+        V, T, E = V.value, T.value, E.value
+        out = dict(vtx=np.zeros((V, 2), np.float32), idepth=np.zeros(V, np.float32),
+                   normals=np.zeros((V, 3), np.float32), tris=np.zeros((T, 3), np.int32),
+                   tri_valid=np.zeros(T, np.uint8), edges=np.zeros((E, 2), np.int32))
+        if V == 0:
+            return out
+        fp = C.byref(filter_params) if filter_params is not None else None
+        self._ck(self._lib.fb_get_mesh(self._h, stream, fp, _ptr(out["vtx"]), _ptr(out["idepth"]),
+                                       _ptr(out["normals"]), _ptr(out["tris"]), _ptr(out["tri_valid"]),
+                                       _ptr(out["edges"])))
+        return out
+
+    def get_idepthmap(self, stream, filter_params=None):
+        out = np.zeros((self.H, self.W), np.float32)
+        fp = C.byref(filter_params) if filter_params is not None else None
+        self._ck(self._lib.fb_get_idepthmap(self._h, stream, fp, _ptr(out)))
+        return out
+
+    def get_raw_idepths(self, stream):
+        n = C.c_int32(0)
+        xy = np.zeros((self.max_features, 2), np.float32)
+        mu = np.zeros(self.max_features, np.float32)
+        var = np.zeros(self.max_features, np.float32)
+        self._ck(self._lib.fb_get_raw_idepths(self._h, stream, C.byref(n), _ptr(xy), _ptr(mu), _ptr(var)))
+        return xy[:n.value].copy(), mu[:n.value].copy(), var[:n.value].copy()
+
+    def get_stat(self, stream, key):
+        v = C.c_double(0)
+        self._ck(self._lib.fb_get_stat(self._h, stream, key.encode(), C.byref(v)))
+        return v.value
+
+    def update_poseframe_poses(self, stream, img_ids, poses):
+        ids, poses = _i32(img_ids), _f32(poses)
+        self._ck(self._lib.fb_update_poseframe_poses(self._h, stream, ids.shape[0], _ptr(ids), _ptr(poses)))
+
+    def prune_poseframes(self, stream, img_ids_to_keep):
+        ids = _i32(img_ids_to_keep)
+        self._ck(self._lib.fb_prune_poseframes(self._h, stream, ids.shape[0], _ptr(ids)))
+
+    def frame_gradient(self, stream, slot):
+        out = np.zeros((self.H, self.W), np.float32)
+        self._ck(self._lib.fb_frame_gradient(self._h, stream, slot, _ptr(out)))
+        return out
+
+    def frame_pyr_down(self, stream, slot):
+        out = np.zeros((self.H // 2, self.W // 2), np.uint8)
+        self._ck(self._lib.fb_frame_pyr_down(self._h, stream, slot, _ptr(out)))
+        return out
+
+    def detect(self, stream, slot, win, border, min_grad_mag, occupied=None):
+        cells = (self.W // win) * (self.H // win)
+        xy = np.zeros((cells, 2), np.float32)
+        ok = np.zeros(cells, np.int32)
+        n = C.c_int32(0)
+        occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8).ravel()
+        self._ck(self._lib.fb_detect(self._h, stream, slot, win, border, min_grad_mag, _ptr(occ), _ptr(xy),
+                                     _ptr(ok), C.byref(n)))
+        return n.value, xy, ok
+
+    def get_feature_pool(self, stream):
+        N = self.max_features
+        out = dict(u_ref=np.zeros((N, 2), np.float32), ref_slot=np.zeros(N, np.int32), mu=np.zeros(N, np.float32),
+                   var=np.zeros(N, np.float32), dropouts=np.zeros(N, np.int32), alive=np.zeros(N, np.int32))
+        self._ck(self._lib.fb_get_feature_pool(self._h, stream, _ptr(out["u_ref"]), _ptr(out["ref_slot"]),
+                                               _ptr(out["mu"]), _ptr(out["var"]), _ptr(out["dropouts"]),
+                                               _ptr(out["alive"])))
+        return out
 
     def hotpath_step(self, desc):
         """desc: a StepDesc whose pointer fields the caller keeps alive."""

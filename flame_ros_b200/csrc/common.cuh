@@ -9,7 +9,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <chrono>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/flame_b200.h"
@@ -53,6 +55,7 @@ struct fb_ctx {
 
   // ---- persistent-cluster solver images (variant 2), rebuilt by fb_graph_set
   struct ClusterPlan* plan = nullptr;
+  struct UpdateState* upd = nullptr;  // fb_update pipeline state (flame_update.cuh)
 
   // ---- frames
   uint8_t* imgs = nullptr;  // [S][n_slots][H][W]
@@ -91,6 +94,7 @@ struct fb_ctx {
   // ---- CUDA-graph cache for the streaming solver
   cudaGraphExec_t solve_exec = nullptr;
   int solve_iters = 0;
+  int solve_only = -1;
   fb_nltgv2_params solve_params{};
   int last_variant = 0;
   int cluster_min = 1;  // FB_CLUSTER_MIN env: lower bound on the cluster size of variant 2

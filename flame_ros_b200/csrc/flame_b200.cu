@@ -15,8 +15,10 @@
 #include "nltgv2.cuh"
 #include "nltgv2_cluster.cuh"
 #include "raster.cuh"
+#include "frontend.cuh"
 
 static std::string g_create_error;
+static void update_free(fb_ctx* c);
 
 // ------------------------------------------------------------------------------------ helpers
 
@@ -77,6 +79,7 @@ static void free_all(fb_ctx* c) {
   cudaFree(c->counters); cudaFree(c->tri); cudaFree(c->nT); cudaFree(c->tri_valid);
   cudaFree(c->owner); cudaFree(c->idmap);
   cluster_plan_free(c);
+  update_free(c);
   if (c->solve_exec) cudaGraphExecDestroy(c->solve_exec);
   for (int k = 0; k < FB_PROF_NUM; ++k)
     for (cudaEvent_t e : c->sec[k].ev) cudaEventDestroy(e);
@@ -343,17 +346,18 @@ extern "C" int fb_graph_x_get_all(fb_ctx* c, float* x_all) {
   return FB_OK;
 }
 
-static int solve_streaming(fb_ctx* c, int iters, const fb_nltgv2_params* p) {
+static int solve_streaming(fb_ctx* c, int iters, const fb_nltgv2_params* p, int only = -1) {
   int maxv = 0, maxe = 0;
   for (int s = 0; s < c->S; ++s) { maxv = std::max(maxv, c->hV[s]); maxe = std::max(maxe, c->hE[s]); }
   if (maxv == 0) return FB_OK;
   // The launch sequence is captured once per (iters, params, extent) and replayed as one graph.
   static_assert(sizeof(fb_nltgv2_params) == 24, "params layout");
-  const bool reuse = c->solve_exec && c->solve_iters == iters &&
+  const bool reuse = c->solve_exec && c->solve_iters == iters && c->solve_only == only &&
                      memcmp(&c->solve_params, p, sizeof(*p)) == 0;
   if (!reuse) {
     if (c->solve_exec) { cudaGraphExecDestroy(c->solve_exec); c->solve_exec = nullptr; }
-    const GraphView g = graph_view(c);
+    GraphView g = graph_view(c);
+    g.only = only;
     // grid extents cover the context capacity so the captured graph survives topology changes
     const dim3 ge(fb_div_up(std::max(c->maxE, 1), 256), c->S), gv(fb_div_up(c->maxV, 256), c->S);
     const float tl = p->step_x * p->data_factor;
@@ -368,6 +372,7 @@ static int solve_streaming(fb_ctx* c, int iters, const fb_nltgv2_params* p) {
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { c->solve_exec = nullptr; FB_FAIL(c, FB_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
     c->solve_iters = iters;
+    c->solve_only = only;
     c->solve_params = *p;
   }
   ProfScope ps(c, FB_PROF_SOLVE);
@@ -387,6 +392,18 @@ extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, 
   c->last_variant = v;
   if (v == 2) return solve_cluster(c, iters, p);
   return solve_streaming(c, iters, p);
+}
+
+// One stream of a batch (fb_update drives streams independently).
+static int fb_nltgv2_solve_stream(fb_ctx* c, int s, int iters, const fb_nltgv2_params* p) {
+  if (iters <= 0) return FB_OK;
+  const int only = c->S > 1 ? s : -1;
+  if (cluster_plan_ready(c)) {
+    c->last_variant = 2;
+    return solve_cluster(c, iters, p, only);
+  }
+  c->last_variant = 1;
+  return solve_streaming(c, iters, p, only);
 }
 
 extern "C" int fb_last_solver_variant(const fb_ctx* c) { return c ? c->last_variant : 0; }
@@ -743,6 +760,268 @@ extern "C" int fb_interpolate(fb_ctx* c, int s, const fb_tri_filter_params* filt
   if (idepthmap) FB_CUDA(c, cudaMemcpyAsync(idepthmap, map, sizeof(float) * npx, cudaMemcpyDeviceToHost, c->stream));
   if (tri_valid && T) FB_CUDA(c, cudaMemcpyAsync(tri_valid, valid, T, cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------ update pipeline
+extern "C" void fb_default_update_params(fb_update_params* p) {
+  // detection win 16 / min_grad 5 / idepth_var_max 0.01: /root/reference/cfg/flame_nodelet.yaml:69-71,85
+  p->detection_win_size = 16;
+  p->min_grad_mag = 5.0f;
+  p->detection_border = 8;
+  p->idepth_init = 0.5f;
+  p->idepth_var_init = 0.25f;
+  p->idepth_var_max_graph = 0.01f;
+  p->adaptive_data_weights = 0;
+  p->init_with_prediction = 1;
+  p->do_nltgv2 = 1;
+  p->iters = 50;
+  fb_default_nltgv2_params(&p->rparams);
+}
+
+#include "flame_update.cuh"
+
+extern "C" int fb_set_update_params(fb_ctx* c, const fb_update_params* p) {
+  CHECK_CTX(c);
+  if (!p || p->detection_win_size < 4 || p->detection_win_size > 64 || p->iters < 0 || p->detection_border < 1)
+    FB_FAIL(c, FB_E_ARG, "fb_set_update_params: bad parameters (win in [4,64], border >= 1)");
+  int rc = update_alloc(c);
+  if (rc) return rc;
+  c->upd->up = *p;
+  return FB_OK;
+}
+
+extern "C" int fb_update(fb_ctx* c, int s, double time, int img_id, const float pose[7],
+                         const uint8_t* gray, int pitch, int is_poseframe) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (!pose || !gray) FB_FAIL(c, FB_E_ARG, "fb_update: null input");
+  if (c->n_slots < 3) FB_FAIL(c, FB_E_STATE, "fb_update: needs n_slots >= 3 (poseframe ring + current frame)");
+  return fb_update_impl(c, s, time, img_id, pose, gray, pitch, is_poseframe);
+}
+
+extern "C" int fb_get_mesh_sizes(fb_ctx* c, int s, int32_t* V, int32_t* T, int32_t* E) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  const bool have = c->upd && c->upd->st[s].have_graph;
+  if (V) *V = have ? c->hV[s] : 0;
+  if (T) *T = have ? c->hT[s] : 0;
+  if (E) *E = have ? c->hE[s] : 0;
+  return FB_OK;
+}
+
+extern "C" int fb_get_mesh(fb_ctx* c, int s, const fb_tri_filter_params* filter, float* vtx_xy,
+                           float* idepth, float* normals, int32_t* tris, uint8_t* tri_valid,
+                           int32_t* edges) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (!c->upd || !c->upd->st[s].have_graph) FB_FAIL(c, FB_E_STATE, "fb_get_mesh: no mesh yet");
+  UpdateStream& S = c->upd->st[s];
+  const int V = c->hV[s], T = c->hT[s];
+  const size_t vb = (size_t)s * c->maxV;
+  cudaStream_t st = c->stream;
+  std::vector<float> x(V), w1(V), w2(V);
+  std::vector<float2> pos(V);
+  FB_CUDA(c, cudaMemcpyAsync(x.data(), c->x + vb, sizeof(float) * V, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(c, cudaMemcpyAsync(w1.data(), c->w1 + vb, sizeof(float) * V, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(c, cudaMemcpyAsync(w2.data(), c->w2 + vb, sizeof(float) * V, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(c, cudaMemcpyAsync(pos.data(), c->vpos + vb, sizeof(float2) * V, cudaMemcpyDeviceToHost, st));
+  if (tri_valid && T) {
+    fb_tri_filter_params fp;
+    fb_default_tri_filter_params(&fp);
+    float cos_thresh = 0.f;
+    if (filter) {
+      fp = *filter;
+      cos_thresh = (float)cos((double)fp.oblique_normal_thresh);
+    }
+    uint8_t* valid = c->tri_valid + (size_t)s * c->maxT;
+    k_tri_validity<<<fb_div_up(T, 256), 256, 0, st>>>(c->W, c->d_K + 9 * s, c->vpos + vb, c->x + vb, T, c->tri + (size_t)s * c->maxT * 3, fp, cos_thresh, 1, valid);
+    c->launches++;
+    FB_CUDA(c, cudaMemcpyAsync(tri_valid, valid, T, cudaMemcpyDeviceToHost, st));
+  }
+  FB_CUDA(c, cudaStreamSynchronize(st));
+  const float* K = &c->h_K[9 * s];
+  for (int v = 0; v < V; ++v) {
+    if (vtx_xy) { vtx_xy[2 * v] = pos[v].x; vtx_xy[2 * v + 1] = pos[v].y; }
+    if (idepth) idepth[v] = x[v];
+    if (normals) {
+      // idepth(u,v) = w1 u + w2 v + c0 is the plane n.X = d seen through K: n/d = K^T (w1, w2, c0)
+      const float c0 = x[v] - w1[v] * pos[v].x - w2[v] * pos[v].y;
+      float nx = K[0] * w1[v], ny = K[4] * w2[v], nz = K[2] * w1[v] + K[5] * w2[v] + c0;
+      const float nn = sqrtf(nx * nx + ny * ny + nz * nz);
+      if (nn > 0.f) { nx /= nn; ny /= nn; nz /= nn; }
+      // point the normal toward the camera (negative z in the RDF optical frame)
+      if (nz > 0.f) { nx = -nx; ny = -ny; nz = -nz; }
+      normals[3 * v] = nx; normals[3 * v + 1] = ny; normals[3 * v + 2] = nz;
+    }
+  }
+  if (tris) std::copy(S.tris.begin(), S.tris.end(), tris);
+  if (edges) std::copy(S.edges.begin(), S.edges.end(), edges);
+  return FB_OK;
+}
+
+extern "C" int fb_get_idepthmap(fb_ctx* c, int s, const fb_tri_filter_params* filter, float* out) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (!out) FB_FAIL(c, FB_E_ARG, "fb_get_idepthmap: null output");
+  if (!c->upd || !c->upd->st[s].have_graph) {
+    const float qnan = nanf("");
+    std::fill(out, out + (size_t)c->W * c->H, qnan);
+    return FB_OK;
+  }
+  return fb_interpolate(c, s, filter, out, nullptr);
+}
+
+extern "C" int fb_get_raw_idepths(fb_ctx* c, int s, int32_t* N, float* xy, float* mu, float* var) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (!N) FB_FAIL(c, FB_E_ARG, "fb_get_raw_idepths: null count");
+  *N = 0;
+  if (!c->upd) return FB_OK;
+  UpdateState* U = c->upd;
+  const size_t fb = (size_t)s * c->maxF;
+  std::vector<float2> u(c->maxF);
+  std::vector<float> m(c->maxF), v(c->maxF);
+  std::vector<int32_t> valid(c->maxF);
+  cudaStream_t st = c->stream;
+  FB_CUDA(c, cudaMemcpyAsync(u.data(), U->f_ucur + fb, sizeof(float2) * c->maxF, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(c, cudaMemcpyAsync(m.data(), U->f_mucur + fb, sizeof(float) * c->maxF, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(c, cudaMemcpyAsync(v.data(), U->f_varcur + fb, sizeof(float) * c->maxF, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(c, cudaMemcpyAsync(valid.data(), U->f_valid + fb, sizeof(int32_t) * c->maxF, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(c, cudaStreamSynchronize(st));
+  int n = 0;
+  for (int f = 0; f < c->maxF; ++f)
+    if (valid[f]) {
+      if (xy) { xy[2 * n] = u[f].x; xy[2 * n + 1] = u[f].y; }
+      if (mu) mu[n] = m[f];
+      if (var) var[n] = v[f];
+      ++n;
+    }
+  *N = n;
+  return FB_OK;
+}
+
+extern "C" int fb_get_stat(fb_ctx* c, int s, const char* key, double* value) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (!key || !value || !c->upd) FB_FAIL(c, FB_E_ARG, "fb_get_stat: bad argument");
+  auto& m = c->upd->st[s].stats;
+  auto it = m.find(key);
+  if (it == m.end()) FB_FAIL(c, FB_E_ARG, std::string("fb_get_stat: unknown key ") + key);
+  *value = it->second;
+  return FB_OK;
+}
+
+extern "C" int fb_update_poseframe_poses(fb_ctx* c, int s, int n, const int32_t* ids, const float* poses) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (n < 0 || (n > 0 && (!ids || !poses))) FB_FAIL(c, FB_E_ARG, "fb_update_poseframe_poses: bad argument");
+  if (!c->upd) return FB_OK;
+  UpdateStream& S = c->upd->st[s];
+  for (int k = 0; k < n; ++k)
+    for (size_t slot = 0; slot < S.pf_img_id.size(); ++slot)
+      if (S.pf_img_id[slot] == ids[k])
+        memcpy(&c->h_pose[((size_t)s * c->n_slots + slot) * 7], poses + 7 * k, sizeof(float) * 7);
+  return FB_OK;
+}
+
+extern "C" int fb_prune_poseframes(fb_ctx* c, int s, int n, const int32_t* keep) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (n < 0 || (n > 0 && !keep)) FB_FAIL(c, FB_E_ARG, "fb_prune_poseframes: bad argument");
+  if (!c->upd) return FB_OK;
+  UpdateStream& S = c->upd->st[s];
+  const size_t fb = (size_t)s * c->maxF;
+  for (size_t slot = 0; slot < S.pf_img_id.size(); ++slot) {
+    if (S.pf_img_id[slot] < 0) continue;
+    bool kept = false;
+    for (int k = 0; k < n; ++k) kept = kept || keep[k] == S.pf_img_id[slot];
+    if (!kept) {
+      k_kill_ref_slot<<<fb_div_up(c->maxF, 256), 256, 0, c->stream>>>(c->maxF, (int)slot, c->f_alive + fb, c->f_ref + fb);
+      c->launches++;
+      S.pf_img_id[slot] = -1;
+    }
+  }
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_get_feature_pool(fb_ctx* c, int s, float* u_ref, int32_t* ref_slot, float* mu,
+                                   float* var, int32_t* dropouts, int32_t* alive) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  const size_t fb = (size_t)s * c->maxF;
+  const int N = c->maxF;
+  cudaStream_t st = c->stream;
+  if (u_ref) FB_CUDA(c, cudaMemcpyAsync(u_ref, c->f_uref + fb, sizeof(float2) * N, cudaMemcpyDeviceToHost, st));
+  if (ref_slot) FB_CUDA(c, cudaMemcpyAsync(ref_slot, c->f_ref + fb, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+  if (mu) FB_CUDA(c, cudaMemcpyAsync(mu, c->f_mu + fb, sizeof(float) * N, cudaMemcpyDeviceToHost, st));
+  if (var) FB_CUDA(c, cudaMemcpyAsync(var, c->f_var + fb, sizeof(float) * N, cudaMemcpyDeviceToHost, st));
+  if (dropouts) FB_CUDA(c, cudaMemcpyAsync(dropouts, c->f_drop + fb, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+  if (alive) FB_CUDA(c, cudaMemcpyAsync(alive, c->f_alive + fb, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(c, cudaStreamSynchronize(st));
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------ frame creation / detection
+extern "C" int fb_frame_gradient(fb_ctx* c, int s, int slot, float* mag) {
+  CHECK_CTX(c);
+  int rc = check_slot(c, s, slot);
+  if (rc) return rc;
+  if (!mag) FB_FAIL(c, FB_E_ARG, "fb_frame_gradient: null output");
+  const size_t npx = (size_t)c->W * c->H;
+  float* d = nullptr;
+  FB_CUDA(c, dalloc(&d, npx));
+  k_gradient_mag<<<fb_div_up((int)npx, 256), 256, 0, c->stream>>>(c->W, c->H, c->imgs + ((size_t)s * c->n_slots + slot) * npx, d);
+  c->launches++;
+  cudaError_t e = cudaMemcpyAsync(mag, d, sizeof(float) * npx, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  FB_CUDA(c, e);
+  return FB_OK;
+}
+
+extern "C" int fb_frame_pyr_down(fb_ctx* c, int s, int slot, uint8_t* out) {
+  CHECK_CTX(c);
+  int rc = check_slot(c, s, slot);
+  if (rc) return rc;
+  if (!out) FB_FAIL(c, FB_E_ARG, "fb_frame_pyr_down: null output");
+  const size_t npx = (size_t)c->W * c->H, n2 = (size_t)(c->W / 2) * (c->H / 2);
+  uint8_t* d = nullptr;
+  FB_CUDA(c, dalloc(&d, n2));
+  k_pyr_down<<<fb_div_up((int)n2, 256), 256, 0, c->stream>>>(c->W, c->H, c->imgs + ((size_t)s * c->n_slots + slot) * npx, d);
+  c->launches++;
+  cudaError_t e = cudaMemcpyAsync(out, d, n2, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  FB_CUDA(c, e);
+  return FB_OK;
+}
+
+extern "C" int fb_detect(fb_ctx* c, int s, int slot, int win, int border, float min_grad_mag,
+                         const uint8_t* occupied, float* det_xy, int32_t* det_ok, int32_t* n_det) {
+  CHECK_CTX(c);
+  int rc = check_slot(c, s, slot);
+  if (rc) return rc;
+  if (win < 4 || win > 64 || border < 0 || !det_xy || !det_ok) FB_FAIL(c, FB_E_ARG, "fb_detect: bad argument");
+  const int cells = (c->W / win) * (c->H / win);
+  const size_t npx = (size_t)c->W * c->H;
+  uint8_t* d_occ = nullptr; float2* d_xy = nullptr; int32_t *d_ok = nullptr, *d_rank = nullptr, *d_cnt = nullptr;
+  FB_CUDA(c, dalloc(&d_occ, cells)); FB_CUDA(c, dalloc(&d_xy, cells)); FB_CUDA(c, dalloc(&d_ok, cells));
+  FB_CUDA(c, dalloc(&d_rank, cells)); FB_CUDA(c, dalloc(&d_cnt, 1));
+  cudaStream_t st = c->stream;
+  cudaError_t e = occupied ? cudaMemcpyAsync(d_occ, occupied, cells, cudaMemcpyHostToDevice, st) : cudaMemsetAsync(d_occ, 0, cells, st);
+  k_detect_features<<<fb_div_up(cells * 32, 256), 256, 0, st>>>(c->W, c->H, win, border, min_grad_mag, c->imgs + ((size_t)s * c->n_slots + slot) * npx, d_occ, d_xy, d_ok);
+  k_scan_flags<<<1, 1024, 0, st>>>(cells, d_ok, d_rank, d_cnt);
+  c->launches += 2;
+  int32_t cnt = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(det_xy, d_xy, sizeof(float2) * cells, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(det_ok, d_ok, sizeof(int32_t) * cells, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, d_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_occ); cudaFree(d_xy); cudaFree(d_ok); cudaFree(d_rank); cudaFree(d_cnt);
+  FB_CUDA(c, e);
+  if (n_det) *n_det = cnt;
   return FB_OK;
 }
 

@@ -1,0 +1,423 @@
+// flame_update.cuh -- the per-frame orchestrator behind flame::Flame::update.
+//
+// Stands in for flame::Flame::update(time, img_id, T_world_cam, gray, is_poseframe)
+// (/root/reference/src/flame_nodelet.cc:634, src/flame_offline_tum.cc:578) and the stages whose
+// timing keys the wrapper exports (/root/reference/src/utils.cc:143-156):
+//   frame_creation -> update_idepths -> project_features -> sync_graph (+ triangulate) -> NLTGV2-L1
+//   iterations -> interpolate -> [poseframe: keyframe + detection].
+// Host C++ sequences the stages; every per-feature / per-vertex / per-pixel computation is a CUDA
+// kernel.  The only per-frame host work is the graph bookkeeping + Delaunay triangulation
+// (delaunay.h), fed by one small D2H of the projected feature table.
+//
+// State carried frame to frame on the device: the feature pool (fixed maxF slots, `alive` flags),
+// the poseframe ring (slots 0..n_slots-2; the last slot holds the current frame), the graph with
+// its primal/dual state, which k_remap_state re-threads through every topology change so (x, w, q)
+// never visit the host.
+#pragma once
+
+#include <unordered_map>
+
+#include "common.cuh"
+#include "delaunay.h"
+#include "epipolar.cuh"
+#include "frontend.cuh"
+#include "nltgv2.cuh"
+#include "raster.cuh"
+
+struct UpdateStream {
+  bool have_poseframe = false;
+  int pf_next = 0;                 // next ring slot to (over)write
+  std::vector<int> pf_img_id;      // img_id held by each ring slot, -1 = empty
+  int64_t frames = 0;
+  // graph bookkeeping (host): feature index backing every vertex, canonical edges
+  std::vector<int32_t> vert_feat;
+  std::vector<int32_t> edges;      // 2E
+  std::vector<int32_t> tris;       // 3T
+  bool have_graph = false;
+  // stats of the last update (names follow msg/FlameStats.msg)
+  std::unordered_map<std::string, double> stats;
+};
+
+struct UpdateState {
+  std::vector<UpdateStream> st;
+  // device scratch (per stream base s*maxF unless noted)
+  float2* f_ucur = nullptr;
+  float* f_mucur = nullptr;
+  float* f_varcur = nullptr;
+  int32_t* f_valid = nullptr;
+  uint8_t* occupied = nullptr;   // [maxCells]
+  float2* det_xy = nullptr;      // [maxCells]
+  int32_t* det_ok = nullptr;     // [maxCells]
+  int32_t* det_rank = nullptr;   // [maxCells]
+  int32_t* free_flag = nullptr;  // [maxF]
+  int32_t* free_rank = nullptr;  // [maxF]
+  int32_t* free_list = nullptr;  // [maxF]
+  int32_t* det_list = nullptr;   // [maxCells]
+  int32_t* counts = nullptr;     // [2] n_det, n_free
+  // old graph state stash for the remap
+  float* o_x = nullptr;
+  float* o_w1 = nullptr;
+  float* o_w2 = nullptr;
+  float4* o_vbar = nullptr;
+  float4* o_q4 = nullptr;
+  int32_t* map_v = nullptr;      // [maxV] new vertex -> old vertex or -1
+  int32_t* map_e = nullptr;      // [maxE] new edge -> old edge or -1
+  int maxCells = 0;
+  fb_update_params up;
+};
+
+// ------------------------------------------------------------------------------------ kernels
+// alive features that project outside the current frame leave the pool
+__global__ void __launch_bounds__(256)
+k_kill_invalid(int N, int32_t* __restrict__ alive, const int32_t* __restrict__ valid) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < N && alive[f] && !valid[f]) alive[f] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_kill_ref_slot(int N, int slot, int32_t* __restrict__ alive, const int32_t* __restrict__ ref_slot) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < N && alive[f] && ref_slot[f] == slot) alive[f] = 0;
+}
+
+// z = projected idepth of the backing feature, wt = 1 or 1/var (adaptive_data_weights)
+__global__ void __launch_bounds__(256)
+k_data_from_projection(int V, float* __restrict__ z, float* __restrict__ wt,
+                       const int32_t* __restrict__ vfeat, const float* __restrict__ mu_cur,
+                       const float* __restrict__ var_cur, int adaptive) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const int f = vfeat[v];
+  z[v] = mu_cur[f];
+  wt[v] = adaptive ? (1.0f / var_cur[f]) : 1.0f;
+}
+
+// Re-thread the solver state through a topology change: persisting vertices / edges keep
+// (x, w, xbar) / q; new vertices start at the prediction (dense idepthmap at the vertex, when valid
+// and init_with_prediction) or at their data term, with w = 0; new edges start at q = 0.
+__global__ void __launch_bounds__(256)
+k_remap_state(int V, int E, const int32_t* __restrict__ map_v, const int32_t* __restrict__ map_e,
+              const float* __restrict__ o_x, const float* __restrict__ o_w1,
+              const float* __restrict__ o_w2, const float4* __restrict__ o_vbar,
+              const float4* __restrict__ o_q4, const float* __restrict__ z,
+              const float2* __restrict__ vpos, const float* __restrict__ idmap, int W, int H,
+              int use_prediction, float* x, float* w1, float* w2, float4* vbar, float4* q4) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < V) {
+    const int o = map_v[t];
+    if (o >= 0) {
+      x[t] = o_x[o];
+      w1[t] = o_w1[o];
+      w2[t] = o_w2[o];
+      vbar[t] = o_vbar[o];
+    } else {
+      float x0 = z[t];
+      if (use_prediction && idmap) {
+        const int px = (int)rintf(vpos[t].x), py = (int)rintf(vpos[t].y);
+        if (px >= 0 && py >= 0 && px < W && py < H) {
+          const float p = idmap[py * W + px];
+          if (p == p && p > 0.0f) x0 = p;
+        }
+      }
+      x[t] = x0;
+      w1[t] = 0.0f;
+      w2[t] = 0.0f;
+      vbar[t] = make_float4(x0, 0.0f, 0.0f, 0.0f);
+    }
+  }
+  if (t < E) {
+    const int o = map_e[t];
+    q4[t] = (o >= 0) ? o_q4[o] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// free_list[rank] = slot for every free slot, det_list[rank] = cell for every detection
+__global__ void __launch_bounds__(256)
+k_scatter_ranked(int n, const int32_t* __restrict__ flag, const int32_t* __restrict__ rank,
+                 int32_t* __restrict__ list) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) list[rank[i]] = i;
+}
+
+__global__ void __launch_bounds__(256)
+k_free_flags(int N, const int32_t* __restrict__ alive, int32_t* __restrict__ free_flag) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < N) free_flag[f] = alive[f] ? 0 : 1;
+}
+
+// k-th detection (cell order) -> k-th free slot (ascending slot index)
+__global__ void __launch_bounds__(256)
+k_spawn_features(const int32_t* __restrict__ counts, const int32_t* __restrict__ det_list,
+                 const int32_t* __restrict__ free_list, const float2* __restrict__ det_xy,
+                 const float* __restrict__ idmap, int W, int H, int ref, float mu0, float var0,
+                 int use_prediction, float2* u_ref, int32_t* ref_slot, float* mu, float* var,
+                 int32_t* dropouts, int32_t* alive, int32_t* status) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(counts[0], counts[1]);
+  if (k >= n) return;
+  const int f = free_list[k];
+  const float2 p = det_xy[det_list[k]];
+  float m = mu0;
+  if (use_prediction && idmap) {
+    const float q = idmap[(int)p.y * W + (int)p.x];
+    if (q == q && q > 0.0f) m = q;
+  }
+  u_ref[f] = p;
+  ref_slot[f] = ref;
+  mu[f] = m;
+  var[f] = var0;
+  dropouts[f] = 0;
+  alive[f] = 1;
+  status[f] = FB_SKIPPED;
+}
+
+// ------------------------------------------------------------------------------------ host side
+static int update_alloc(fb_ctx* c) {
+  if (c->upd) return FB_OK;
+  UpdateState* U = new UpdateState();
+  c->upd = U;
+  U->st.resize(c->S);
+  for (auto& s : U->st) s.pf_img_id.assign(c->n_slots - 1, -1);
+  const size_t nf = (size_t)c->S * c->maxF;
+  U->maxCells = (c->W / 4) * (c->H / 4);  // detection win >= 4
+  bool ok = true;
+  auto A = [&](cudaError_t r) { ok = ok && r == cudaSuccess; };
+  A(dalloc(&U->f_ucur, nf)); A(dalloc(&U->f_mucur, nf)); A(dalloc(&U->f_varcur, nf)); A(dalloc(&U->f_valid, nf));
+  A(dalloc(&U->occupied, U->maxCells)); A(dalloc(&U->det_xy, U->maxCells)); A(dalloc(&U->det_ok, U->maxCells));
+  A(dalloc(&U->det_rank, U->maxCells)); A(dalloc(&U->det_list, U->maxCells));
+  A(dalloc(&U->free_flag, c->maxF)); A(dalloc(&U->free_rank, c->maxF)); A(dalloc(&U->free_list, c->maxF));
+  A(dalloc(&U->counts, 2));
+  A(dalloc(&U->o_x, c->maxV)); A(dalloc(&U->o_w1, c->maxV)); A(dalloc(&U->o_w2, c->maxV));
+  A(dalloc(&U->o_vbar, c->maxV)); A(dalloc(&U->o_q4, c->maxE));
+  A(dalloc(&U->map_v, c->maxV)); A(dalloc(&U->map_e, c->maxE));
+  if (!ok) FB_FAIL(c, FB_E_NOMEM, "fb_update: scratch allocation failed");
+  // the feature pool is a fixed set of maxF slots: mark them all dead
+  FB_CUDA(c, cudaMemsetAsync(c->f_alive, 0, sizeof(int32_t) * nf, c->stream));
+  FB_CUDA(c, cudaMemsetAsync(c->f_status, 0, sizeof(int32_t) * nf, c->stream));
+  for (int s = 0; s < c->S; ++s) c->hF[s] = c->maxF;
+  FB_CUDA(c, cudaMemcpyAsync(c->nF, c->hF.data(), sizeof(int32_t) * c->S, cudaMemcpyHostToDevice, c->stream));
+  fb_update_params& p = U->up;
+  fb_default_update_params(&p);
+  return FB_OK;
+}
+
+static void update_free(fb_ctx* c) {
+  UpdateState* U = c->upd;
+  if (!U) return;
+  cudaFree(U->f_ucur); cudaFree(U->f_mucur); cudaFree(U->f_varcur); cudaFree(U->f_valid);
+  cudaFree(U->occupied); cudaFree(U->det_xy); cudaFree(U->det_ok); cudaFree(U->det_rank);
+  cudaFree(U->det_list); cudaFree(U->free_flag); cudaFree(U->free_rank); cudaFree(U->free_list);
+  cudaFree(U->counts); cudaFree(U->o_x); cudaFree(U->o_w1); cudaFree(U->o_w2); cudaFree(U->o_vbar);
+  cudaFree(U->o_q4); cudaFree(U->map_v); cudaFree(U->map_e);
+  delete U;
+  c->upd = nullptr;
+}
+
+struct StageTimer {
+  std::unordered_map<std::string, double>& m;
+  const char* key;
+  std::chrono::steady_clock::time_point t0;
+  StageTimer(std::unordered_map<std::string, double>& mm, const char* k)
+      : m(mm), key(k), t0(std::chrono::steady_clock::now()) {}
+  ~StageTimer() {
+    m[key] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+
+// Detection on the frame in `img_slot` for cells without a live feature; spawns features that
+// reference poseframe slot `ref`.
+static int update_detect(fb_ctx* c, int s, int img_slot, int ref) {
+  UpdateState* U = c->upd;
+  const fb_update_params& p = U->up;
+  const int win = p.detection_win_size, cx = c->W / win, cy = c->H / win, cells = cx * cy;
+  if (cells > U->maxCells) FB_FAIL(c, FB_E_ARG, "fb_update: detection_win_size too small");
+  const size_t fb = (size_t)s * c->maxF, npx = (size_t)c->W * c->H;
+  cudaStream_t st = c->stream;
+  const uint8_t* img = c->imgs + ((size_t)s * c->n_slots + img_slot) * npx;
+  FB_CUDA(c, cudaMemsetAsync(U->occupied, 0, cells, st));
+  k_mark_occupied<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(c->W, c->H, win, c->maxF, U->f_ucur + fb, U->f_valid + fb, U->occupied);
+  k_detect_features<<<fb_div_up(cells * 32, 256), 256, 0, st>>>(c->W, c->H, win, p.detection_border, p.min_grad_mag, img, U->occupied, U->det_xy, U->det_ok);
+  k_scan_flags<<<1, 1024, 0, st>>>(cells, U->det_ok, U->det_rank, U->counts);
+  k_scatter_ranked<<<fb_div_up(cells, 256), 256, 0, st>>>(cells, U->det_ok, U->det_rank, U->det_list);
+  k_free_flags<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(c->maxF, c->f_alive + fb, U->free_flag);
+  k_scan_flags<<<1, 1024, 0, st>>>(c->maxF, U->free_flag, U->free_rank, U->counts + 1);
+  k_scatter_ranked<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(c->maxF, U->free_flag, U->free_rank, U->free_list);
+  const float* idmap = U->st[s].have_graph ? c->idmap + (size_t)s * npx : nullptr;
+  k_spawn_features<<<fb_div_up(std::min(cells, c->maxF), 256), 256, 0, st>>>(
+      U->counts, U->det_list, U->free_list, U->det_xy, idmap, c->W, c->H, ref, p.idepth_init, p.idepth_var_init,
+      p.init_with_prediction, c->f_uref + fb, c->f_ref + fb, c->f_mu + fb, c->f_var + fb, c->f_drop + fb,
+      c->f_alive + fb, c->f_status + fb);
+  c->launches += 8;
+  FB_CUDA(c, cudaGetLastError());
+  return FB_OK;
+}
+
+// Installs the current frame as a new poseframe in the ring and detects new features in it.
+static int update_new_poseframe(fb_ctx* c, int s, int img_id) {
+  UpdateState* U = c->upd;
+  UpdateStream& S = U->st[s];
+  const int cur = c->n_slots - 1, slot = S.pf_next;
+  const size_t fb = (size_t)s * c->maxF, npx = (size_t)c->W * c->H;
+  cudaStream_t st = c->stream;
+  if (S.pf_img_id[slot] >= 0) {  // ring wraps: features anchored in the evicted poseframe die
+    k_kill_ref_slot<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(c->maxF, slot, c->f_alive + fb, c->f_ref + fb);
+    c->launches++;
+  }
+  uint8_t* base = c->imgs + (size_t)s * c->n_slots * npx;
+  FB_CUDA(c, cudaMemcpyAsync(base + (size_t)slot * npx, base + (size_t)cur * npx, npx, cudaMemcpyDeviceToDevice, st));
+  memcpy(&c->h_pose[((size_t)s * c->n_slots + slot) * 7], &c->h_pose[((size_t)s * c->n_slots + cur) * 7], sizeof(float) * 7);
+  S.pf_img_id[slot] = img_id;
+  S.pf_next = (slot + 1) % (c->n_slots - 1);
+  S.have_poseframe = true;
+  return update_detect(c, s, cur, slot);
+}
+
+static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const float pose[7],
+                          const uint8_t* gray, int pitch, int is_poseframe) {
+  int rc = update_alloc(c);
+  if (rc) return rc;
+  UpdateState* U = c->upd;
+  UpdateStream& S = U->st[s];
+  const fb_update_params& p = U->up;
+  const int cur = c->n_slots - 1;
+  const size_t fb = (size_t)s * c->maxF, vb = (size_t)s * c->maxV, eb = (size_t)s * c->maxE;
+  const size_t npx = (size_t)c->W * c->H;
+  cudaStream_t st = c->stream;
+  S.stats.clear();
+  StageTimer t_all(S.stats, "update");
+  {
+    StageTimer t(S.stats, "frame_creation");
+    rc = fb_frame_set(c, s, cur, gray, pitch, pose);
+    if (rc) return rc;
+  }
+  S.frames++;
+  if (!S.have_poseframe) {  // very first frame: it becomes the first poseframe, nothing to estimate yet
+    StageTimer t(S.stats, "detection");
+    // no projections yet: every cell is free
+    FB_CUDA(c, cudaMemsetAsync(U->f_valid + fb, 0, sizeof(int32_t) * c->maxF, st));
+    rc = update_new_poseframe(c, s, img_id);
+    if (rc) return rc;
+    FB_CUDA(c, cudaStreamSynchronize(st));
+    return 0;
+  }
+
+  // ---- update_idepths + project_features (device) -------------------------------------------
+  std::vector<int32_t> cmp(c->S, -1);
+  cmp[s] = cur;
+  {
+    StageTimer t(S.stats, "update_idepths");
+    rc = fb_idepth_update(c, cmp.data());  // also refreshes the geometry table against `cur`
+    if (rc) return rc;
+    k_project_features<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(
+        c->d_geo, c->n_slots, s, c->maxF, c->W, c->H, c->f_uref + fb, c->f_ref + fb, c->f_mu + fb, c->f_var + fb,
+        c->f_alive + fb, U->f_ucur + fb, U->f_mucur + fb, U->f_varcur + fb, U->f_valid + fb);
+    k_kill_invalid<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(c->maxF, c->f_alive + fb, U->f_valid + fb);
+    c->launches += 2;
+  }
+  // ---- sync_graph: one small D2H, host bookkeeping + Delaunay --------------------------------
+  std::vector<float2> h_u(c->maxF);
+  std::vector<float> h_var(c->maxF);
+  std::vector<int32_t> h_valid(c->maxF);
+  {
+    StageTimer t(S.stats, "project_features");
+    FB_CUDA(c, cudaMemcpyAsync(h_u.data(), U->f_ucur + fb, sizeof(float2) * c->maxF, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(c, cudaMemcpyAsync(h_var.data(), U->f_varcur + fb, sizeof(float) * c->maxF, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(c, cudaMemcpyAsync(h_valid.data(), U->f_valid + fb, sizeof(int32_t) * c->maxF, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(c, cudaStreamSynchronize(st));
+  }
+  std::vector<int32_t> vfeat;
+  std::vector<float> pos;
+  for (int f = 0; f < c->maxF; ++f)
+    if (h_valid[f] && h_var[f] < p.idepth_var_max_graph) {  // valid implies alive
+      if ((int)vfeat.size() >= c->maxV) break;
+      vfeat.push_back(f);
+      pos.push_back(h_u[f].x);
+      pos.push_back(h_u[f].y);
+    }
+  int updated = 0;
+  const int V = (int)vfeat.size();
+  std::vector<int> tris, edges;
+  bool have_tri = false;
+  if (V >= 3) {
+    StageTimer t(S.stats, "triangulate");
+    fbdel::Triangulator T;
+    have_tri = T.run(V, pos.data(), tris, edges);
+    if ((int)edges.size() / 2 > c->maxE || (int)tris.size() / 3 > c->maxT) have_tri = false;
+  }
+  if (have_tri) {
+    const int E = (int)edges.size() / 2;
+    {
+      StageTimer t(S.stats, "sync_graph");
+      // maps new -> old for the state carry-over
+      std::vector<int32_t> map_v(V, -1), map_e(E, -1);
+      if (S.have_graph) {
+        std::vector<int32_t> f2v(c->maxF, -1);
+        for (size_t k = 0; k < S.vert_feat.size(); ++k) f2v[S.vert_feat[k]] = (int32_t)k;
+        std::unordered_map<uint64_t, int32_t> eold;
+        eold.reserve(S.edges.size());
+        for (size_t e = 0; e < S.edges.size() / 2; ++e)
+          eold[((uint64_t)S.vert_feat[S.edges[2 * e]] << 32) | (uint32_t)S.vert_feat[S.edges[2 * e + 1]]] = (int32_t)e;
+        for (int k = 0; k < V; ++k) map_v[k] = f2v[vfeat[k]];
+        for (int e = 0; e < E; ++e) {
+          auto it = eold.find(((uint64_t)vfeat[edges[2 * e]] << 32) | (uint32_t)vfeat[edges[2 * e + 1]]);
+          if (it != eold.end()) map_e[e] = it->second;
+        }
+        // stash the old state (device to device)
+        const int oV = (int)S.vert_feat.size(), oE = (int)S.edges.size() / 2;
+        FB_CUDA(c, cudaMemcpyAsync(U->o_x, c->x + vb, sizeof(float) * oV, cudaMemcpyDeviceToDevice, st));
+        FB_CUDA(c, cudaMemcpyAsync(U->o_w1, c->w1 + vb, sizeof(float) * oV, cudaMemcpyDeviceToDevice, st));
+        FB_CUDA(c, cudaMemcpyAsync(U->o_w2, c->w2 + vb, sizeof(float) * oV, cudaMemcpyDeviceToDevice, st));
+        FB_CUDA(c, cudaMemcpyAsync(U->o_vbar, c->vbar + vb, sizeof(float4) * oV, cudaMemcpyDeviceToDevice, st));
+        if (oE) FB_CUDA(c, cudaMemcpyAsync(U->o_q4, c->q4 + eb, sizeof(float4) * oE, cudaMemcpyDeviceToDevice, st));
+      }
+      // edge weights: alpha = 1/|delta| in pixels, beta = 1
+      std::vector<float> alpha(E), beta(E, 1.0f);
+      for (int e = 0; e < E; ++e) {
+        const float dx = pos[2 * edges[2 * e]] - pos[2 * edges[2 * e + 1]];
+        const float dy = pos[2 * edges[2 * e] + 1] - pos[2 * edges[2 * e + 1] + 1];
+        alpha[e] = 1.0f / sqrtf(dx * dx + dy * dy);
+      }
+      rc = fb_graph_set(c, s, V, E, pos.data(), edges.data(), alpha.data(), beta.data());
+      if (rc) return rc;
+      FB_CUDA(c, cudaMemcpyAsync(c->vfeat + vb, vfeat.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, st));
+      FB_CUDA(c, cudaMemcpyAsync(U->map_v, map_v.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, st));
+      if (E) FB_CUDA(c, cudaMemcpyAsync(U->map_e, map_e.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, st));
+      k_data_from_projection<<<fb_div_up(V, 256), 256, 0, st>>>(V, c->z + vb, c->wt + vb, c->vfeat + vb, U->f_mucur + fb, U->f_varcur + fb, p.adaptive_data_weights);
+      const float* idmap = S.have_graph ? c->idmap + (size_t)s * npx : nullptr;
+      k_remap_state<<<fb_div_up(std::max(V, E), 256), 256, 0, st>>>(
+          V, E, U->map_v, U->map_e, U->o_x, U->o_w1, U->o_w2, U->o_vbar, U->o_q4, c->z + vb, c->vpos + vb, idmap,
+          c->W, c->H, p.init_with_prediction, c->x + vb, c->w1 + vb, c->w2 + vb, c->vbar + vb, c->q4 + eb);
+      c->launches += 2;
+      FB_CUDA(c, cudaGetLastError());
+      FB_CUDA(c, cudaStreamSynchronize(st));  // the pageable staging vectors above go out of scope
+      S.vert_feat.assign(vfeat.begin(), vfeat.end());
+      S.edges.assign(edges.begin(), edges.end());
+      S.tris.assign(tris.begin(), tris.end());
+      S.have_graph = true;
+    }
+    if (p.do_nltgv2 && p.iters > 0) {
+      StageTimer t(S.stats, "nltgv2");
+      // solve only this stream's graph: other streams of the context keep their own cadence
+      rc = fb_nltgv2_solve_stream(c, s, p.iters, &p.rparams);
+      if (rc) return rc;
+    }
+    {
+      StageTimer t(S.stats, "interpolate");
+      rc = fb_mesh_set(c, s, (int)S.tris.size() / 3, S.tris.data());
+      if (rc) return rc;
+      rc = fb_interpolate(c, s, nullptr, nullptr, nullptr);  // unfiltered map stays on the device
+      if (rc) return rc;
+    }
+    updated = 1;
+  }
+  if (is_poseframe) {
+    StageTimer t(S.stats, "detection");
+    rc = update_new_poseframe(c, s, img_id);
+    if (rc) return rc;
+  }
+  FB_CUDA(c, cudaStreamSynchronize(st));
+  S.stats["num_vertices"] = V;
+  S.stats["num_edges"] = have_tri ? (double)edges.size() / 2 : 0.0;
+  S.stats["num_triangles"] = have_tri ? (double)tris.size() / 3 : 0.0;
+  return updated;
+}

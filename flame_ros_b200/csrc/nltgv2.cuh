@@ -31,6 +31,7 @@ struct GraphView {
   const int32_t* nV;
   const int32_t* nE;
   int maxV, maxE;
+  int only;  // >= 0: process this stream only (fb_update solves one stream of a batch)
 };
 
 static GraphView graph_view(fb_ctx* c) {
@@ -38,6 +39,7 @@ static GraphView graph_view(fb_ctx* c) {
   g.vbar = c->vbar; g.x = c->x; g.w1 = c->w1; g.w2 = c->w2; g.z = c->z; g.wt = c->wt;
   g.ec = c->ec; g.eij = c->eij; g.q4 = c->q4; g.row = c->row; g.inc = c->inc;
   g.nV = c->nV; g.nE = c->nE; g.maxV = c->maxV; g.maxE = c->maxE;
+  g.only = -1;
   return g;
 }
 
@@ -47,7 +49,7 @@ __device__ __forceinline__ float fb_clamp1(float t) { return fminf(fmaxf(t, -1.0
 __global__ void __launch_bounds__(256) k_dual_edges(GraphView g, float sigma) {
   const int s = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= g.nE[s]) return;
+  if (e >= g.nE[s] || (g.only >= 0 && s != g.only)) return;
   const size_t eb = (size_t)s * g.maxE + e;
   const size_t vb = (size_t)s * g.maxV;
   const int2 ij = g.eij[eb];
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(256)
 k_primal_vertices(GraphView g, float tau, float tl, float theta, float xmin, float xmax) {
   const int s = blockIdx.y;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= g.nV[s]) return;
+  if (v >= g.nV[s] || (g.only >= 0 && s != g.only)) return;
   const size_t vb = (size_t)s * g.maxV + v;
   const size_t eb = (size_t)s * g.maxE;
   const int32_t* row = g.row + (size_t)s * (g.maxV + 1);

@@ -147,7 +147,7 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
   const int tid = threadIdx.x;
   const uint32_t C = fbc_cluster_nctarank(), rank = fbc_cluster_ctarank();
   const int s = blockIdx.x / C;
-  if (g.nV[s] == 0) return;  // uniform over the cluster
+  if (g.nV[s] == 0 || (g.only >= 0 && s != g.only)) return;  // uniform over the cluster
   const int32_t* vp = a.vpart + (size_t)s * (FBC_MAXC + 1);
   const int32_t* ep = a.epart + (size_t)s * (FBC_MAXC + 1);
   const int32_t* hp = a.hpart + (size_t)s * (FBC_MAXC + 1);
@@ -649,7 +649,7 @@ static int fbc_upload_plans(fb_ctx* c, int C) {
   return FB_OK;
 }
 
-static int solve_cluster(fb_ctx* c, int iters, const fb_nltgv2_params* p) {
+static int solve_cluster(fb_ctx* c, int iters, const fb_nltgv2_params* p, int only = -1) {
   ClusterPlan* P = c->plan;
   int C = 1;
   bool any = false;
@@ -678,6 +678,7 @@ static int solve_cluster(fb_ctx* c, int iters, const fb_nltgv2_params* p) {
   }
   ClusterArgs a;
   a.g = graph_view(c);
+  a.g.only = only;
   a.eplan = P->eplan;
   a.pplan = P->pplan;
   a.vplan = P->vplan;

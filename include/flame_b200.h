@@ -211,6 +211,61 @@ typedef struct {
 } fb_step_desc;
 int fb_hotpath_step(fb_ctx* ctx, const fb_step_desc* d);
 
+/* ------------------------------------------------------------------ flame::Flame::update and getters
+ * fb_update is the whole per-frame pipeline of flame::Flame::update(time, img_id, T_world_cam, gray,
+ * is_poseframe) (/root/reference/src/flame_nodelet.cc:634; src/flame_offline_tum.cc:578): frame
+ * upload -> epipolar update of the feature pool -> projection into the new frame -> graph sync
+ * (vertex selection by idepth_var_max_graph, Delaunay, device-side carry-over of x/w/q) -> NLTGV2-L1
+ * iterations -> dense interpolation -> on poseframes: ring insertion + grid detection.
+ * Returns 1 when the mesh/depth outputs were updated, 0 when not yet (first frames), <0 on error:
+ * the reference's `bool update()` (/root/reference/src/flame_nodelet.cc:636-642). */
+typedef struct {
+  int detection_win_size;     /* features/detection/win_size, 16 (cfg/flame_nodelet.yaml:71) */
+  float min_grad_mag;         /* features/detection/min_grad_mag, 5.0 */
+  int detection_border;       /* px of image border without detections, 8 */
+  float idepth_init;          /* prior mean of a new feature when no prediction exists, 0.5 */
+  float idepth_var_init;      /* prior variance of a new feature, 0.25 */
+  float idepth_var_max_graph; /* regularization/nltgv2/idepth_var_max, 0.01 */
+  int adaptive_data_weights;  /* 0 */
+  int init_with_prediction;   /* 1 */
+  int do_nltgv2;              /* 1 */
+  int iters;                  /* NLTGV2 iterations per frame, 50 (BASELINE configs) */
+  fb_nltgv2_params rparams;
+} fb_update_params;
+void fb_default_update_params(fb_update_params* p);
+int fb_set_update_params(fb_ctx* ctx, const fb_update_params* p);
+int fb_update(fb_ctx* ctx, int stream, double time, int img_id, const float pose[7],
+              const uint8_t* gray, int pitch, int is_poseframe);
+/* getInverseDepthMesh (/root/reference/src/flame_nodelet.cc:669-676). fb_get_mesh_sizes first;
+ * arrays: vtx_xy[2V], idepth[V], normals[3V], tris[3T], tri_valid[T], edges[2E]; any may be NULL.
+ * filter == NULL: every triangle with positive idepths is valid. Synchronises. */
+int fb_get_mesh_sizes(fb_ctx* ctx, int stream, int32_t* V, int32_t* T, int32_t* E);
+int fb_get_mesh(fb_ctx* ctx, int stream, const fb_tri_filter_params* filter, float* vtx_xy,
+                float* idepth, float* normals, int32_t* tris, uint8_t* tri_valid, int32_t* edges);
+/* getInverseDepthMap / getFilteredInverseDepthMap (/root/reference/src/flame_nodelet.cc:682-688):
+ * filter == NULL -> unfiltered. out[H*W], NaN = no depth. Synchronises. */
+int fb_get_idepthmap(fb_ctx* ctx, int stream, const fb_tri_filter_params* filter, float* out);
+/* getRawIDepths (/root/reference/src/flame_nodelet.cc:721-723): live features projected into the
+ * current frame. Arrays sized max_features; *N receives the count. Synchronises. */
+int fb_get_raw_idepths(fb_ctx* ctx, int stream, int32_t* N, float* xy, float* mu, float* var);
+/* stats()/timings() of flame::utils::StatsTracker (/root/reference/src/flame_nodelet.cc:747-749):
+ * value of one key of the last update (ms for stage names, counts otherwise); FB_E_ARG if unknown. */
+int fb_get_stat(fb_ctx* ctx, int stream, const char* key, double* value);
+/* updatePoseFramePoses / prunePoseFrames (/root/reference/src/flame_nodelet.cc:474-475). */
+int fb_update_poseframe_poses(fb_ctx* ctx, int stream, int n, const int32_t* img_ids, const float* poses);
+int fb_prune_poseframes(fb_ctx* ctx, int stream, int n, const int32_t* img_ids_to_keep);
+/* Frame creation / detection building blocks, exposed for parity tests (host outputs; synchronise):
+ * gradient magnitude and half-resolution pyramid level of the frame held in `slot`; grid detection
+ * with an optional host occupancy mask [cells]. */
+int fb_frame_gradient(fb_ctx* ctx, int stream, int slot, float* mag);
+int fb_frame_pyr_down(fb_ctx* ctx, int stream, int slot, uint8_t* out);
+int fb_detect(fb_ctx* ctx, int stream, int slot, int win, int border, float min_grad_mag,
+              const uint8_t* occupied, float* det_xy, int32_t* det_ok, int32_t* n_det);
+/* Feature pool of the update pipeline (device -> host copy of every slot; arrays sized
+ * max_features): for parity tests against the oracle-side mirror. Synchronises. */
+int fb_get_feature_pool(fb_ctx* ctx, int stream, float* u_ref, int32_t* ref_slot, float* mu,
+                        float* var, int32_t* dropouts, int32_t* alive);
+
 /* ------------------------------------------------------------------ triangulation (host, no GPU needed)
  * Stands in for the `triangulate` stage (/root/reference/src/utils.cc:154; the external core wraps
  * Shewchuk's Triangle).  Exact-predicate incremental Delaunay of n pixel positions pts_xy[2n]

@@ -1,0 +1,132 @@
+"""GPU parity of the whole per-frame pipeline (fb_update = flame::Flame::update) against the
+oracle-side mirror, frame by frame on a synthetic stream: feature pool (integers exact, floats to
+TOL), mesh topology (exact), vertex inverse depths and the dense map (TOL = 1e-4, north_star)."""
+import numpy as np
+import pytest
+
+from flame_ros_b200 import synth
+from pipeline_mirror import MirrorFlame
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _stream(W, H, K, n, seed=0, step=0.01):
+    sc = synth.Scene(seed, tex_size=1024)
+    poses = synth.stream_poses(n, step=step)
+    return [sc.render(K, poses[k], W, H) for k in range(n)], poses
+
+
+def _oracle_up(oracle, up):
+    p = oracle.NLTGV2Params()
+    for n, _ in p._fields_:
+        setattr(p, n, getattr(up.rparams, n))
+    return p
+
+
+@pytest.mark.parametrize("W,H,win,iters,pf_every", [(320, 240, 16, 20, 3), (640, 480, 16, 50, 6)])
+def test_update_pipeline_matches_oracle_mirror(capi, oracle, W, H, win, iters, pf_every):
+    K = (synth.K_VGA * np.array([[W / 640.0], [H / 480.0], [1.0]], np.float32)).astype(np.float32)
+    n_frames = 14 if W == 320 else 10
+    frames, poses = _stream(W, H, K, n_frames, seed=1, step=0.02)
+    up = capi.default_update_params()
+    up.detection_win_size, up.iters = win, iters
+    up.idepth_var_max_graph = 0.05  # let the graph populate within a few frames
+    n_slots, maxF, maxV = 4, 2048, 2048
+    with capi.Context(1, W, H, n_slots, maxF, maxV, 3 * maxV) as ctx:
+        ctx.set_intrinsics(0, K)
+        ctx.set_update_params(up)
+        # the mirror solves with the oracle's parameter struct (same layout)
+        mup = type("UP", (), {})()
+        for n, _ in up._fields_:
+            setattr(mup, n, getattr(up, n))
+        mup.rparams = _oracle_up(oracle, up)
+        mir = MirrorFlame(oracle, capi, W, H, K, n_slots, maxF, maxV, mup)
+        n_updates = 0
+        for k in range(n_frames):
+            img = frames[k][0]
+            is_pf = (k % pf_every) == 0
+            got = ctx.update(0, k / 30.0, k, poses[k], img, is_pf)
+            ref = mir.update(k / 30.0, k, poses[k], img, is_pf)
+            assert got == ref, "frame %d: update() return differs" % k
+            pool = ctx.get_feature_pool(0)
+            assert np.array_equal(pool["alive"], mir.alive), "frame %d alive" % k
+            live = mir.alive == 1
+            assert np.array_equal(pool["ref_slot"][live], mir.ref_slot[live])
+            assert np.array_equal(pool["dropouts"][live], mir.dropouts[live])
+            assert np.array_equal(pool["u_ref"][live], mir.u_ref[live])
+            assert np.max(np.abs(pool["mu"][live] - mir.mu[live]), initial=0) < TOL
+            assert np.max(np.abs(pool["var"][live] - mir.var[live]), initial=0) < TOL
+            if got:
+                n_updates += 1
+                mesh = ctx.get_mesh(0)
+                assert np.array_equal(mesh["tris"], mir.tris) and np.array_equal(mesh["edges"], mir.edges)
+                assert np.max(np.abs(mesh["vtx"] - mir.pos)) < TOL
+                assert np.max(np.abs(mesh["idepth"] - mir.state["x"])) < TOL, "frame %d vertex idepth" % k
+                dm = ctx.get_idepthmap(0)
+                assert np.array_equal(np.isnan(dm), np.isnan(mir.idmap))
+                m = ~np.isnan(dm)
+                assert np.max(np.abs(dm[m] - mir.idmap[m]), initial=0) < TOL
+                assert ctx.get_stat(0, "num_vertices") == len(mir.vert_feat)
+        assert n_updates >= n_frames - 4
+        # the estimate is meaningful: dense map close to the rendered ground truth on covered pixels
+        truth = frames[n_frames - 1][1]
+        dm = ctx.get_idepthmap(0)
+        m = ~np.isnan(dm)
+        assert m.mean() > 0.3
+        assert np.median(np.abs(dm[m] - truth[m])) < 0.05
+        # filtered map is a subset of the unfiltered one; raw idepths are the live projected features
+        fm = ctx.get_idepthmap(0, capi.default_tri_filter_params())
+        assert np.all(np.isnan(dm)[np.isnan(fm) == False] == False)
+        xy, mu, var = ctx.get_raw_idepths(0)
+        assert len(mu) == int((mir.valid == 1).sum())
+        mesh = ctx.get_mesh(0, capi.default_tri_filter_params())
+        nrm = np.linalg.norm(mesh["normals"], axis=1)
+        assert np.allclose(nrm, 1.0, atol=1e-4) and np.all(mesh["normals"][:, 2] <= 0)
+
+
+def test_frontend_kernels_match_oracle(capi, oracle):
+    W, H = 320, 240
+    K = (synth.K_VGA * np.array([[0.5], [0.5], [1.0]], np.float32)).astype(np.float32)
+    frames, poses = _stream(W, H, K, 1, seed=3)
+    img = frames[0][0]
+    with capi.Context(1, W, H, 3, 16, 16, 16) as ctx:
+        ctx.frame_set(0, 0, img, poses[0])
+        mag = ctx.frame_gradient(0, 0)
+        half = ctx.frame_pyr_down(0, 0)
+        assert np.array_equal(mag, oracle.gradient_mag(img))
+        assert np.array_equal(half, oracle.pyr_down(img))
+        rng = np.random.default_rng(0)
+        for win, border in ((16, 8), (8, 4), (12, 1)):
+            cells = (W // win) * (H // win)
+            occ = (rng.uniform(size=cells) < 0.3).astype(np.uint8)
+            n, xy, ok = ctx.detect(0, 0, win, border, 5.0, occ)
+            rn, rxy, rok = oracle.detect_features(oracle.gradient_mag(img), win, border, 5.0, occ)
+            assert n == rn and np.array_equal(ok, rok) and np.array_equal(xy, rxy)
+            assert n > 0 and not np.any(ok[occ == 1])
+
+
+def test_ring_eviction_and_prune(capi, oracle):
+    """A 2-slot poseframe ring wraps after two poseframes: features anchored in the evicted frame die;
+    prunePoseFrames kills the features of dropped poseframes."""
+    W, H = 320, 240
+    K = (synth.K_VGA * np.array([[0.5], [0.5], [1.0]], np.float32)).astype(np.float32)
+    frames, poses = _stream(W, H, K, 8, seed=2, step=0.02)
+    up = capi.default_update_params()
+    up.iters = 5
+    with capi.Context(1, W, H, 3, 1024, 1024, 3072) as ctx:
+        ctx.set_intrinsics(0, K)
+        ctx.set_update_params(up)
+        for k in range(8):
+            ctx.update(0, k / 30.0, k, poses[k], frames[k][0], k % 2 == 0)
+            pool = ctx.get_feature_pool(0)
+            live = pool["alive"] == 1
+            assert set(np.unique(pool["ref_slot"][live])) <= {0, 1}
+        before = ctx.get_feature_pool(0)
+        keep_slot = 1 if (before["alive"] == 1).any() else 0
+        # poseframes were inserted at img_id 0,2,4,6 -> slots 0,1,0,1: slot 0 holds 4, slot 1 holds 6
+        ctx.prune_poseframes(0, [6])
+        after = ctx.get_feature_pool(0)
+        live = after["alive"] == 1
+        assert np.all(after["ref_slot"][live] == 1)
+        assert (before["alive"] == 1).sum() >= live.sum()
