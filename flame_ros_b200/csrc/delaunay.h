@@ -121,7 +121,7 @@ struct Triangulator {
   }
 
   std::vector<int> cavity, stack_, bnd_a, bnd_b, bnd_out, bnd_new;
-  std::vector<int> mark;
+  std::vector<int> mark, vslot;
 
   bool insert(int p) {
     int t0 = locate(p);
@@ -207,22 +207,19 @@ struct Triangulator {
           if (na == b && nbv == a) ta[3 * n + k] = t;
         }
     }
-    // link the fan triangles to each other: edge (b,p) of one matches edge (p,a') of the next
+    // link the fan triangles to each other: the boundary edges form a cycle around p, so triangle i's
+    // edge (b_i, p) is shared with the triangle whose boundary edge starts at b_i (its edge (p, a))
+    if (vslot.size() < px.size() + 1) vslot.assign(px.size() + 1, -1);
+    const int gidx = (int)px.size();  // slot of the ghost vertex
+    for (int i = 0; i < nb; ++i) vslot[bnd_a[i] == GHOST ? gidx : bnd_a[i]] = i;
     for (int i = 0; i < nb; ++i) {
-      const int t = bnd_new[i];
-      for (int k = 0; k < 3; ++k) {
-        if (ta[3 * t + k] >= 0) continue;
-        const int ea = tv[3 * t + k], eb = tv[3 * t + (k + 1) % 3];
-        for (int j = 0; j < nb; ++j) {
-          if (j == i) continue;
-          const int u = bnd_new[j];
-          for (int m = 0; m < 3; ++m)
-            if (tv[3 * u + m] == eb && tv[3 * u + (m + 1) % 3] == ea) {
-              ta[3 * t + k] = u;
-              ta[3 * u + m] = t;
-            }
-        }
-      }
+      const int a = bnd_a[i], b = bnd_b[i];
+      const int j = vslot[b == GHOST ? gidx : b];
+      const int bp = (a == GHOST) ? 0 : (b == GHOST ? 2 : 1);
+      const int aj = bnd_a[j], bj = bnd_b[j];
+      const int pa = (aj == GHOST) ? 1 : (bj == GHOST ? 0 : 2);
+      ta[3 * bnd_new[i] + bp] = bnd_new[j];
+      ta[3 * bnd_new[j] + pa] = bnd_new[i];
     }
     last = bnd_new[0];
     return true;
@@ -239,7 +236,7 @@ struct Triangulator {
       px[i] = (int64_t)llroundf(pts[2 * i] * 64.0f);
       py[i] = (int64_t)llroundf(pts[2 * i + 1] * 64.0f);
     }
-    tv.clear(); ta.clear(); dead.clear(); free_list.clear(); mark.clear();
+    tv.clear(); ta.clear(); dead.clear(); free_list.clear(); mark.clear(); vslot.clear();
     if (n < 3) return false;
     // insertion order: snake over a coarse grid for walk locality (deterministic)
     std::vector<int> order(n);

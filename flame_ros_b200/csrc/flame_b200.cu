@@ -398,7 +398,11 @@ extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, 
 static int fb_nltgv2_solve_stream(fb_ctx* c, int s, int iters, const fb_nltgv2_params* p) {
   if (iters <= 0) return FB_OK;
   const int only = c->S > 1 ? s : -1;
-  if (cluster_plan_ready(c)) {
+  // fb_update re-triangulates every frame; rebuilding the cluster plan on the host (~1 ms at 5k
+  // vertices) costs more than the persistent kernel saves, so a freshly changed topology is solved
+  // with the streaming kernels (graph replay, no per-topology host work)
+  const bool plan_fresh = c->plan && !c->plan->topo[s].dirty;
+  if (cluster_plan_ready(c) && plan_fresh) {
     c->last_variant = 2;
     return solve_cluster(c, iters, p, only);
   }

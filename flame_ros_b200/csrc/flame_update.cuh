@@ -353,14 +353,16 @@ static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const f
       if (S.have_graph) {
         std::vector<int32_t> f2v(c->maxF, -1);
         for (size_t k = 0; k < S.vert_feat.size(); ++k) f2v[S.vert_feat[k]] = (int32_t)k;
-        std::unordered_map<uint64_t, int32_t> eold;
-        eold.reserve(S.edges.size());
-        for (size_t e = 0; e < S.edges.size() / 2; ++e)
-          eold[((uint64_t)S.vert_feat[S.edges[2 * e]] << 32) | (uint32_t)S.vert_feat[S.edges[2 * e + 1]]] = (int32_t)e;
         for (int k = 0; k < V; ++k) map_v[k] = f2v[vfeat[k]];
+        // vertices are listed in ascending feature index in both graphs, so both canonical edge
+        // lists are sorted by (feature_i, feature_j): one linear merge matches the persisting edges
+        const size_t oEn = S.edges.size() / 2;
+        size_t o = 0;
         for (int e = 0; e < E; ++e) {
-          auto it = eold.find(((uint64_t)vfeat[edges[2 * e]] << 32) | (uint32_t)vfeat[edges[2 * e + 1]]);
-          if (it != eold.end()) map_e[e] = it->second;
+          const uint64_t key = ((uint64_t)vfeat[edges[2 * e]] << 32) | (uint32_t)vfeat[edges[2 * e + 1]];
+          while (o < oEn && (((uint64_t)S.vert_feat[S.edges[2 * o]] << 32) | (uint32_t)S.vert_feat[S.edges[2 * o + 1]]) < key) ++o;
+          if (o < oEn && (((uint64_t)S.vert_feat[S.edges[2 * o]] << 32) | (uint32_t)S.vert_feat[S.edges[2 * o + 1]]) == key)
+            map_e[e] = (int32_t)o;
         }
         // stash the old state (device to device)
         const int oV = (int)S.vert_feat.size(), oE = (int)S.edges.size() / 2;
