@@ -1,0 +1,5 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi -L
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 --no-single > gpurun_out/bench_r1_n2.json 2> gpurun_out/bench_r1_n2.err; tail -c 1500 gpurun_out/bench_r1_n2.json; tail -5 gpurun_out/bench_r1_n2.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 10 --warmup 2 > gpurun_out/bench_r1_n2_ref.json 2>> gpurun_out/bench_r1_n2.err; tail -c 600 gpurun_out/bench_r1_n2_ref.json
