@@ -38,7 +38,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("FB_NVCC_EXTRA", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
         ["-o", LIB_PATH, os.path.join(CSRC, "flame_b200.cu")]
     env = dict(os.environ)
     env.pop("CC", None)

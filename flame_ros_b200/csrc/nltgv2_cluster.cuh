@@ -23,9 +23,11 @@
 #include "common.cuh"
 #include "nltgv2.cuh"
 
+#ifndef FBC_THREADS
 #define FBC_THREADS 512
 #define FBC_EPT 4   // edges per thread (register resident)
 #define FBC_VPT 2   // vertices per thread
+#endif
 #define FBC_MAXC 16
 #define FBC_SMEM_LIMIT (227 * 1024)
 
@@ -278,11 +280,14 @@ k_nltgv2_cluster(ClusterArgs a, int iters, float sigma, float tau, float tl, flo
         q2[k] = fb_clamp1(fmaf(sigma, k2, q2[k]));
         q3[k] = fb_clamp1(fmaf(sigma, k3, q3[k]));
         const float a1 = ea[k] * q1[k];
-        s_slot[e_si[k]] = make_float4(a1, fmaf(ebt[k], q2[k], -(edx[k] * a1)),
+        const float4 cs = make_float4(a1, fmaf(ebt[k], q2[k], -(edx[k] * a1)),
                                       fmaf(ebt[k], q3[k], -(edy[k] * a1)), 0.f);
         const float4 ct = make_float4(-a1, -(ebt[k] * q2[k]), -(ebt[k] * q3[k]), 0.f);
-        if (a_mb[k] == 0u) s_slot[a_sj[k]] = ct;
-        else fbc_st_async(a_sj[k], ct, a_mb[k]);
+        if (e_id[k] >= 0) {  // predicated stores: idle lanes compute on zeros but write nothing
+          s_slot[e_si[k]] = cs;
+          if (a_mb[k] == 0u) s_slot[a_sj[k]] = ct;
+          else fbc_st_async(a_sj[k], ct, a_mb[k]);
+        }
       }
     }
     __syncthreads();  // local slot writes visible; every thread is past the halo wait, so the
