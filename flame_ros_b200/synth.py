@@ -4,6 +4,7 @@ No dataset (TUM / EuRoC) is on disk and there is no network, so every test and b
 generated here.  Nothing in this module touches the CPU oracle.
 """
 import math
+import os
 
 import numpy as np
 
@@ -199,3 +200,104 @@ def grid_features(W, H, win, border=8, seed=11):
     x = np.clip(x, border, W - 1 - border)
     y = np.clip(y, border, H - 1 - border)
     return np.stack([x, y], axis=1).astype(np.float32)
+
+
+# --------------------------------------------------------------------------- on-disk datasets (tests)
+
+def write_tum_dataset(root, frames, poses_rdf, K, input_frame="RDF_IN_FLU", with_depth=None, t0=1000.0, dt=1.0 / 30):
+    """Write a TUM-RGB-D-shaped dataset: rgb/*.png, optional depth/*.png (uint16, depth*5000),
+    `associations.txt` (t tx ty tz qx qy qz qw t_rgb rgb.png [t_d depth.png]) and a camera_info YAML.
+    poses_rdf are camera-in-world RDF poses; they are stored in `input_frame` so that the reader's
+    conversion (flame_ros_b200/offline.py:tum_pose_to_rdf) recovers them."""
+    import cv2
+    import yaml
+    from . import offline as off
+    os.makedirs(os.path.join(root, "rgb"), exist_ok=True)
+    if with_depth is not None:
+        os.makedirs(os.path.join(root, "depth"), exist_ok=True)
+    lines = []
+    for k, (img, p) in enumerate(zip(frames, poses_rdf)):
+        q, t = np.asarray(p[:4], np.float64), np.asarray(p[4:7], np.float64)
+        if input_frame == "RDF":
+            qs, ts = q, t
+        elif input_frame == "RDF_IN_FLU":
+            ci = off.q_inv(off.Q_FLU_TO_RDF)
+            qs, ts = off.q_mul(ci, q), off.q_rot(ci, t)
+        elif input_frame == "RDF_IN_FRD":
+            ci = off.q_inv(off.Q_FRD_TO_RDF)
+            qs, ts = off.q_mul(ci, q), off.q_rot(ci, t)
+        elif input_frame in ("FLU", "FRD"):
+            c = off.Q_FLU_TO_RDF if input_frame == "FLU" else off.Q_FRD_TO_RDF
+            ci = off.q_inv(c)
+            qs, ts = off.q_mul(off.q_mul(ci, q), c), off.q_rot(ci, t)
+        else:
+            raise ValueError(input_frame)
+        tm = t0 + k * dt
+        name = "rgb/%.6f.png" % tm
+        cv2.imwrite(os.path.join(root, name), np.stack([img] * 3, axis=-1))
+        line = "%.6f %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.6f %s" % (tm, ts[0], ts[1], ts[2], qs[0], qs[1], qs[2], qs[3], tm, name)
+        if with_depth is not None:
+            dname = "depth/%.6f.png" % tm
+            cv2.imwrite(os.path.join(root, dname), np.clip(with_depth[k] * 5000.0, 0, 65535).astype(np.uint16))
+            line += " %.6f %s" % (tm, dname)
+        lines.append(line)
+    open(os.path.join(root, "associations.txt"), "w").write("\n".join(lines) + "\n")
+    H, W = frames[0].shape
+    K = np.asarray(K, np.float64)
+    P = np.concatenate([K, np.zeros((3, 1))], axis=1)
+    calib = dict(image_height=int(H), image_width=int(W), camera_name="synthetic",
+                 camera_matrix=dict(rows=3, cols=3, data=[float(v) for v in K.ravel()]),
+                 distortion_model="plumb_bob", distortion_coefficients=dict(rows=1, cols=5, data=[0.0] * 5),
+                 rectification_matrix=dict(rows=3, cols=3, data=[1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0]),
+                 projection_matrix=dict(rows=3, cols=4, data=[float(v) for v in P.ravel()]))
+    yaml.safe_dump(calib, open(os.path.join(root, "calib.yaml"), "w"))
+    return os.path.join(root, "associations.txt"), os.path.join(root, "calib.yaml")
+
+
+def write_asl_dataset(root, frames, poses_rdf, K, world_frame="RFU", t0_ns=1403715273262142976, dt_ns=33333333,
+                      pose_rate_mult=4):
+    """Write an EuRoC/ASL-shaped dataset: cam0/{sensor.yaml,data.csv,data/*.png} and
+    state_groundtruth_estimate0/{sensor.yaml,data.csv} (pose rows t,tx,ty,tz,qw,qx,qy,qz at a higher
+    rate than the images, identity T_BS for the pose sensor, a non-trivial camera T_BS)."""
+    import cv2
+    import yaml
+    from . import offline as off
+    cam, gt = os.path.join(root, "cam0"), os.path.join(root, "state_groundtruth_estimate0")
+    os.makedirs(os.path.join(cam, "data"), exist_ok=True)
+    os.makedirs(gt, exist_ok=True)
+    c = {"RDF": None, "FLU": off.Q_FLU_TO_RDF, "FRD": off.Q_FRD_TO_RDF, "RFU": off.Q_RFU_TO_RDF}[world_frame]
+    # camera mounted rotated 90 deg about body z and offset: T_BS (camera in body)
+    q_cb = off.q_from_R([[0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    t_cb = np.array([0.05, -0.02, 0.01])
+    Tc = np.eye(4)
+    Tc[:3, :3] = quat_to_R(q_cb)
+    Tc[:3, 3] = t_cb
+    H, W = frames[0].shape
+    yaml.safe_dump(dict(sensor_type="camera", comment="synthetic cam0", T_BS=dict(rows=4, cols=4, data=[float(v) for v in Tc.ravel()]),
+                        rate_hz=30, resolution=[int(W), int(H)], camera_model="pinhole",
+                        intrinsics=[float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])],
+                        distortion_model="radial-tangential", distortion_coefficients=[0.0, 0.0, 0.0, 0.0]),
+                   open(os.path.join(cam, "sensor.yaml"), "w"))
+    yaml.safe_dump(dict(sensor_type="visual-inertial", comment="synthetic ground truth",
+                        T_BS=dict(rows=4, cols=4, data=[float(v) for v in np.eye(4).ravel()])),
+                   open(os.path.join(gt, "sensor.yaml"), "w"))
+    rows_img, rows_pose = ["#timestamp [ns],filename"], ["#timestamp,p_x,p_y,p_z,q_w,q_x,q_y,q_z"]
+    for k, (img, p) in enumerate(zip(frames, poses_rdf)):
+        ts = t0_ns + k * dt_ns
+        cv2.imwrite(os.path.join(cam, "data", "%d.png" % ts), img)
+        rows_img.append("%d,%d.png" % (ts, ts))
+        # camera-in-world (world_frame axes) from the RDF pose, then body-in-world
+        q, t = np.asarray(p[:4], np.float64), np.asarray(p[4:7], np.float64)
+        if c is not None:
+            ci = off.q_inv(c)
+            q, t = off.q_mul(ci, q), off.q_rot(ci, t)
+        q_bw = off.q_mul(q, off.q_inv(q_cb))
+        t_bw = t - off.q_rot(q_bw, t_cb)
+        # pose samples: the exact one 1 ms after the image stamp plus distractors between frames
+        rows_pose.append("%d,%.9f,%.9f,%.9f,%.9f,%.9f,%.9f,%.9f" % (ts + 1000000, t_bw[0], t_bw[1], t_bw[2], q_bw[3], q_bw[0], q_bw[1], q_bw[2]))
+        for j in range(1, pose_rate_mult):
+            tj = ts + j * dt_ns // pose_rate_mult
+            rows_pose.append("%d,%.9f,%.9f,%.9f,%.9f,%.9f,%.9f,%.9f" % (tj, t_bw[0] + 9.0, t_bw[1], t_bw[2], q_bw[3], q_bw[0], q_bw[1], q_bw[2]))
+    open(os.path.join(cam, "data.csv"), "w").write("\n".join(rows_img) + "\n")
+    open(os.path.join(gt, "data.csv"), "w").write("\n".join(rows_pose) + "\n")
+    return gt, cam

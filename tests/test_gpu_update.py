@@ -24,9 +24,11 @@ def _oracle_up(oracle, up):
     return p
 
 
-@pytest.mark.parametrize("W,H,win,iters,pf_every", [(320, 240, 16, 20, 3), (640, 480, 16, 50, 6)])
+@pytest.mark.parametrize("W,H,win,iters,pf_every", [(320, 240, 16, 20, 3), (640, 480, 16, 50, 6), (752, 480, 16, 50, 6)])
 def test_update_pipeline_matches_oracle_mirror(capi, oracle, W, H, win, iters, pf_every):
     K = (synth.K_VGA * np.array([[W / 640.0], [H / 480.0], [1.0]], np.float32)).astype(np.float32)
+    if W == 752:  # BASELINE configs[2]: EuRoC V1_01 cam0 shape (752x480, cam0 pinhole)
+        K = synth.K_EUROC
     n_frames = 14 if W == 320 else 10
     frames, poses = _stream(W, H, K, n_frames, seed=1, step=0.02)
     up = capi.default_update_params()
