@@ -125,7 +125,7 @@ class GpuRun:
         self.h_frames = capi.PinnedBuffer((self.S, WL.POOL_FRAMES, d0.H, d0.W), np.uint8)
         for s, d in enumerate(datas):
             np.copyto(self.h_frames.array[s], d.frames)
-        self.h_x = capi.PinnedBuffer((self.S, V), np.float32)
+        self.h_x = capi.PinnedBuffer((2, self.S, V), np.float32)   # double-buffered results
         self.maxV = V
         self.cmp = np.full(self.S, WL.CMP_SLOT, np.int32)
         ctx.sync()
@@ -152,28 +152,37 @@ class GpuRun:
             ref_ptr = (C.c_void_p * S)(*[self.h_frames.array[s, ref_idx].ctypes.data for s in range(S)])
             cmp_ptr = (C.c_void_p * S)(*[self.h_frames.array[s, cmp_idx].ctypes.data for s in range(S)])
             self._keep += [ref_poses, cmp_poses, ref_pool, cmp_pool, ref_ptr, cmp_ptr]
-            for e2e in (False, True):
+            for mode in ("resident", "e2e_sync", "e2e_pipe"):
                 d = capi.StepDesc()
                 d.new_poseframe, d.ref_slot, d.cmp_slot = int(newpf), ref_slot, WL.CMP_SLOT
-                if e2e:
+                if mode != "resident":
                     d.ref_images = C.cast(ref_ptr, C.POINTER(C.c_void_p))
                     d.cmp_images = C.cast(cmp_ptr, C.POINTER(C.c_void_p))
-                    d.x_out = self.h_x.array.ctypes.data_as(C.POINTER(C.c_float))
+                    d.x_out = self.h_x.array[k % 2].ctypes.data_as(C.POINTER(C.c_float))
+                if mode == "e2e_pipe":
+                    d.pipelined = 1
+                    d.cmp_slot = WL.CMP_SLOT + (k % 2)   # uploads alternate between two frame slots
                 d.ref_pool_idx = ref_pool.ctypes.data_as(C.POINTER(C.c_int32))
                 d.cmp_pool_idx = cmp_pool.ctypes.data_as(C.POINTER(C.c_int32))
                 d.ref_poses = ref_poses.ctypes.data_as(C.POINTER(C.c_float))
                 d.cmp_poses = cmp_poses.ctypes.data_as(C.POINTER(C.c_float))
                 d.mu0, d.var0, d.adaptive_weights = WL.MU0, WL.VAR0, 0
                 d.iters, d.variant, d.rparams = self.iters, self.variant, self.params
-                table[(k, e2e)] = d
+                table[(k, mode)] = d
         return table, period
 
-    def step(self, k, e2e):
-        """One frame of every stream: resident mode pulls frames from the device pool and does not
-        synchronise; e2e mode uploads the pinned host frames and reads the vertex idepths back."""
+    def step(self, k, mode):
+        """One frame of every stream.  resident: frames come from the device pool, no synchronisation.
+        e2e_sync: pinned host frames uploaded in-stream, vertex idepths read back, blocking.
+        e2e_pipe: the same through the pipelined API (uploads on a copy stream overlap the previous
+        frame's kernels; results land asynchronously in a pinned double buffer)."""
         if not hasattr(self, "_table"):
             self._table, self._period = self._descs()
-        self.ctx.hotpath_step(self._table[(k % self._period, e2e)])
+        self.ctx.hotpath_step(self._table[(k % self._period, mode)])
+
+    def consume(self, k):
+        """Touch the result of step k (the application's read of the vertex inverse depths)."""
+        return float(self.h_x.array[k % 2, 0, 0])
 
     def bytes_per_step(self):
         d = self.datas[0]
@@ -182,35 +191,53 @@ class GpuRun:
         return int(h2d), int(d2h)
 
 
-def run_gpu_leg(torch, run, steps, warmup, flush_buf, e2e, barrier):
+def run_gpu_leg(torch, run, steps, warmup, flush_buf, mode, barrier):
     """Returns (seconds over `steps` timed steps, launches in the timed region, solver ms, solver calls)."""
     ctx = run.ctx
     for k in range(warmup):
-        run.step(k, e2e)
+        run.step(k, mode)
     ctx.sync()
-    ctx.profile_enable(True)
+    ctx.profile_enable(mode != "e2e_pipe")   # per-launch event pairs would serialise the pipelined leg
     ctx.profile_reset()
     barrier()
     torch.cuda.synchronize()
     l0 = ctx.launch_count()
     total = 0.0
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for i in range(steps):
-        k = warmup + i
-        flush_buf.zero_()                      # evict L2 between timed steps (outside the timed bracket)
+    if mode == "e2e_pipe":
+        # K steps back to back; every step uploads its frames from pinned host memory and its vertex
+        # idepths are read on the host one step later (double-buffered), like a streaming consumer
+        t0 = time.perf_counter()
+        for i in range(steps):
+            k = warmup + i
+            run.step(k, mode)
+            if i > 0:
+                ctx.results_wait(1)
+                run.consume(k - 1)
+        ctx.results_wait(0)
+        run.consume(warmup + steps - 1)
         torch.cuda.synchronize()
-        if e2e:
-            t0 = time.perf_counter()
-            run.step(k, True)                  # ends with a synchronising D2H
-            total += time.perf_counter() - t0
-        else:
-            ev[i][0].record()
-            run.step(k, False)
-            ev[i][1].record()
-    torch.cuda.synchronize()
+        total = time.perf_counter() - t0
+    else:
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            k = warmup + i
+            flush_buf.zero_()                      # evict L2 between timed steps (outside the timed bracket)
+            if mode == "e2e_sync":
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                run.step(k, mode)                  # ends with a synchronising D2H
+                run.consume(k)
+                total += time.perf_counter() - t0
+            else:
+                # stream-ordered: flush, e0, the step's copies + kernels, e1.  No host sync between steps,
+                # so the host enqueues ahead while the flush runs and launch latency is not part of a step
+                ev[i][0].record()
+                run.step(k, mode)
+                ev[i][1].record()
+        torch.cuda.synchronize()
+        if mode == "resident":
+            total = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
     barrier()
-    if not e2e:
-        total = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
     launches = ctx.launch_count() - l0
     ms, calls, _ = ctx.profile_get(run.capi.PROF_SOLVE)
     ctx.profile_enable(False)
@@ -262,9 +289,10 @@ def gpu_main(args):
     if sampler:
         sampler.start()
     run = GpuRun(capi, datas, local_rank, stream_ptr, args.variant)
-    t_res, launches, solve_ms, solve_calls = run_gpu_leg(torch, run, args.steps, args.warmup, flush, False, barrier)
+    t_res, launches, solve_ms, solve_calls = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "resident", barrier)
     variant_used = run.ctx.last_solver_variant()
-    t_e2e, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, True, barrier)
+    t_sync, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "e2e_sync", barrier)
+    t_e2e, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "e2e_pipe", barrier)
     h2d, d2h = run.bytes_per_step()
     alg_bytes = sum(d.algorithmic_bytes_per_iter() for d in datas) * datas[0].iters
     iters = datas[0].iters
@@ -274,16 +302,18 @@ def gpu_main(args):
     single = None
     if not args.no_single and S > 1:
         run1 = GpuRun(capi, datas[:1], local_rank, stream_ptr, args.variant)
-        t1, _, ms1, c1 = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, False, barrier)
-        t1e, _, _, _ = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, True, barrier)
+        t1, _, ms1, c1 = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, "resident", barrier)
+        t1s, _, _, _ = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, "e2e_sync", barrier)
+        t1e, _, _, _ = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, "e2e_pipe", barrier)
         run1.close()
-        t1, t1e = max_over_ranks(t1), max_over_ranks(t1e)
+        t1, t1e, t1s = max_over_ranks(t1), max_over_ranks(t1e), max_over_ranks(t1s)
         single = {"streams_per_gpu": 1, "value": world * args.steps / t1, "e2e": world * args.steps / t1e,
+                  "e2e_sync": world * args.steps / t1s,
                   "ms_per_step": 1e3 * t1 / args.steps, "unit": UNIT,
                   "solver_us_per_frame": 1e3 * ms1 / max(c1, 1),
                   "roofline_frac": (datas[0].algorithmic_bytes_per_iter() * iters / (1e6 * ms1 / max(c1, 1))) / peak}
 
-    t_res, t_e2e = max_over_ranks(t_res), max_over_ranks(t_e2e)
+    t_res, t_e2e, t_sync = max_over_ranks(t_res), max_over_ranks(t_e2e), max_over_ranks(t_sync)
     launches_all = int(sum_over_ranks(launches))
     frames = world * S * args.steps
     solve_ms_per_launch = solve_ms / max(solve_calls, 1)
@@ -308,10 +338,17 @@ def gpu_main(args):
                        "streams_per_gpu": S, "vertices": datas[0].V, "edges": datas[0].E, "pd_iters": iters,
                        "solver_variant": {1: "streaming (2 kernels/iter, CUDA graph)", 2: "persistent cluster (DSMEM)"}.get(variant_used),
                        "l2": "flushed between timed steps (256 MiB memset outside the timed bracket)",
-                       "timing": "value: CUDA events per step on the launching stream; e2e: host clock per step incl. H2D/D2H"},
+                       "timing": "value: CUDA events around each step on the launching stream (sum over K steps), L2 flushed "
+                                 "by a 256 MiB memset enqueued between steps outside the event brackets; "
+                                 "e2e: host clock over the K steps run back to back through the pipelined C-ABI call "
+                                 "(pinned-host frames uploaded every step on a copy stream, vertex idepths read back "
+                                 "every step; inputs are streamed, never reused, so L2 is not flushed); "
+                                 "e2e_sync: blocking call per step with the L2 flush between steps"},
             "solver_iters_per_second": frames * iters / t_res,
             "e2e": {"value": frames / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * t_e2e / args.steps},
+                    "ms_per_step": 1e3 * t_e2e / args.steps, "mode": "pipelined"},
+            "e2e_sync": {"value": frames / t_sync, "unit": UNIT, "ms_per_step": 1e3 * t_sync / args.steps,
+                         "mode": "blocking call per step, L2 flushed between steps"},
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_nltgv2_cluster" if variant_used == 2 else "k_dual_edges+k_primal_vertices",

@@ -32,6 +32,11 @@ struct fb_ctx {
   int S = 0, W = 0, H = 0, n_slots = 0, maxF = 0, maxV = 0, maxE = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // pipelined fb_hotpath_step: uploads on a copy stream, per-slot ready/free events, result events
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> ev_ready, ev_free;
+  cudaEvent_t ev_result[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t n_pipelined = 0;
   std::string err;
 
   // ---- graph (per stream s: vertex base s*maxV, edge base s*maxE, incidence base s*2*maxE)

@@ -83,6 +83,10 @@ static void free_all(fb_ctx* c) {
   if (c->solve_exec) cudaGraphExecDestroy(c->solve_exec);
   for (int k = 0; k < FB_PROF_NUM; ++k)
     for (cudaEvent_t e : c->sec[k].ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_ready) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_free) cudaEventDestroy(e);
+  for (int k = 0; k < 4; ++k) if (c->ev_result[k]) cudaEventDestroy(c->ev_result[k]);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -663,6 +667,33 @@ extern "C" int fb_graph_data_from_features(fb_ctx* c, int adaptive) {
 }
 
 // ------------------------------------------------------------------------------------ batched frame
+static int pipeline_init(fb_ctx* c) {
+  if (c->copy_stream) return FB_OK;
+  FB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  c->ev_ready.resize(c->n_slots);
+  c->ev_free.resize(c->n_slots);
+  for (int k = 0; k < c->n_slots; ++k) {
+    FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_ready[k], cudaEventDisableTiming));
+    FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_free[k], cudaEventDisableTiming));
+  }
+  for (int k = 0; k < 4; ++k) FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_result[k], cudaEventDisableTiming));
+  return FB_OK;
+}
+
+// Host image -> slot on the copy stream, ordered after the last kernel that read the slot.
+static int pipeline_upload(fb_ctx* c, int slot, const uint8_t* const* images, const float* poses) {
+  const size_t fsz = (size_t)c->W * c->H;
+  FB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[slot], 0));
+  for (int s = 0; s < c->S; ++s) {
+    int rc = fb_frame_pose_set(c, s, slot, poses + 7 * s);
+    if (rc) return rc;
+    FB_CUDA(c, cudaMemcpyAsync(c->imgs + ((size_t)s * c->n_slots + slot) * fsz, images[s], fsz, cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  FB_CUDA(c, cudaEventRecord(c->ev_ready[slot], c->copy_stream));
+  FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_ready[slot], 0));
+  return FB_OK;
+}
+
 extern "C" int fb_hotpath_step(fb_ctx* c, const fb_step_desc* d) {
   CHECK_CTX(c);
   if (!d || !d->cmp_poses || (!d->cmp_images && !d->cmp_pool_idx))
@@ -670,18 +701,34 @@ extern "C" int fb_hotpath_step(fb_ctx* c, const fb_step_desc* d) {
   if (d->new_poseframe && (!d->ref_poses || (!d->ref_images && !d->ref_pool_idx)))
     FB_FAIL(c, FB_E_ARG, "fb_hotpath_step: poseframe inputs missing");
   int rc;
+  const bool pipe = d->pipelined && d->cmp_images;
+  if (pipe) {
+    rc = pipeline_init(c);
+    if (rc) return rc;
+    if (check_slot(c, 0, d->cmp_slot) || (d->new_poseframe && check_slot(c, 0, d->ref_slot))) return FB_E_ARG;
+  }
   std::vector<int32_t> slots(c->S);
   if (d->new_poseframe) {
-    for (int s = 0; s < c->S; ++s) {
-      rc = d->ref_images ? fb_frame_set(c, s, d->ref_slot, d->ref_images[s], c->W, d->ref_poses + 7 * s)
-                         : fb_frame_from_pool(c, s, d->ref_slot, d->ref_pool_idx[s], d->ref_poses + 7 * s);
+    if (pipe && d->ref_images) {
+      rc = pipeline_upload(c, d->ref_slot, d->ref_images, d->ref_poses);
       if (rc) return rc;
+    } else {
+      for (int s = 0; s < c->S; ++s) {
+        rc = d->ref_images ? fb_frame_set(c, s, d->ref_slot, d->ref_images[s], c->W, d->ref_poses + 7 * s)
+                           : fb_frame_from_pool(c, s, d->ref_slot, d->ref_pool_idx[s], d->ref_poses + 7 * s);
+        if (rc) return rc;
+      }
     }
   }
-  for (int s = 0; s < c->S; ++s) {
-    rc = d->cmp_images ? fb_frame_set(c, s, d->cmp_slot, d->cmp_images[s], c->W, d->cmp_poses + 7 * s)
-                       : fb_frame_from_pool(c, s, d->cmp_slot, d->cmp_pool_idx[s], d->cmp_poses + 7 * s);
+  if (pipe) {
+    rc = pipeline_upload(c, d->cmp_slot, d->cmp_images, d->cmp_poses);
     if (rc) return rc;
+  } else {
+    for (int s = 0; s < c->S; ++s) {
+      rc = d->cmp_images ? fb_frame_set(c, s, d->cmp_slot, d->cmp_images[s], c->W, d->cmp_poses + 7 * s)
+                         : fb_frame_from_pool(c, s, d->cmp_slot, d->cmp_pool_idx[s], d->cmp_poses + 7 * s);
+      if (rc) return rc;
+    }
   }
   if (d->new_poseframe) {
     std::fill(slots.begin(), slots.end(), d->ref_slot);
@@ -691,11 +738,34 @@ extern "C" int fb_hotpath_step(fb_ctx* c, const fb_step_desc* d) {
   std::fill(slots.begin(), slots.end(), d->cmp_slot);
   rc = fb_idepth_update(c, slots.data());
   if (rc) return rc;
+  if (pipe) {
+    // the frames read by this update may be overwritten once the epipolar kernel has run
+    FB_CUDA(c, cudaEventRecord(c->ev_free[d->cmp_slot], c->stream));
+    if (d->new_poseframe) {
+      // the OTHER poseframe slots are no longer referenced by any feature after the re-init
+      for (int k = 0; k < c->n_slots; ++k)
+        if (k != d->cmp_slot && k != d->ref_slot) FB_CUDA(c, cudaEventRecord(c->ev_free[k], c->stream));
+    }
+  }
   rc = fb_graph_data_from_features(c, d->adaptive_weights);
   if (rc) return rc;
   rc = fb_nltgv2_solve(c, d->iters, &d->rparams, d->variant);
   if (rc) return rc;
+  if (d->x_out && pipe) {
+    FB_CUDA(c, cudaMemcpyAsync(d->x_out, c->x, sizeof(float) * (size_t)c->S * c->maxV, cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(c, cudaEventRecord(c->ev_result[c->n_pipelined & 3], c->stream));
+    c->n_pipelined++;
+    return FB_OK;
+  }
   if (d->x_out) return fb_graph_x_get_all(c, d->x_out);
+  return FB_OK;
+}
+
+extern "C" int fb_results_wait(fb_ctx* c, int lag) {
+  CHECK_CTX(c);
+  if (lag < 0 || lag > 3) FB_FAIL(c, FB_E_ARG, "fb_results_wait: lag must be in [0,3]");
+  if (c->n_pipelined - 1 - lag < 0) return FB_OK;
+  FB_CUDA(c, cudaEventSynchronize(c->ev_result[(c->n_pipelined - 1 - lag) & 3]));
   return FB_OK;
 }
 

@@ -63,4 +63,4 @@ def schedule(step):
 
 
 CMP_SLOT = 2
-N_SLOTS = 3
+N_SLOTS = 4   # 2 alternating poseframe slots + 2 alternating current-frame slots (pipelined uploads)

@@ -208,8 +208,15 @@ typedef struct {
   int iters, variant;
   fb_nltgv2_params rparams;
   float* x_out;                     /* host [n_streams*max_vertices] or NULL */
+  int pipelined;                    /* 0: as documented above.  1: streaming mode -- host images are
+                                       uploaded on a separate copy stream (overlapping the previous
+                                       frame's kernels; the caller alternates cmp_slot between two
+                                       slots), x_out (pinned) is filled asynchronously and the call
+                                       never blocks; fb_results_wait() waits for a frame's x_out. */
 } fb_step_desc;
 int fb_hotpath_step(fb_ctx* ctx, const fb_step_desc* d);
+/* Waits until the x_out of the pipelined step issued `lag` calls ago (0 = the latest) has landed. */
+int fb_results_wait(fb_ctx* ctx, int lag);
 
 /* ------------------------------------------------------------------ flame::Flame::update and getters
  * fb_update is the whole per-frame pipeline of flame::Flame::update(time, img_id, T_world_cam, gray,
