@@ -109,11 +109,16 @@ class GpuRun:
         self.params = capi.default_nltgv2_params()
         self.iters = d0.iters
         ctx = self.ctx
-        ctx.pool_reserve(self.S * WL.POOL_FRAMES)
+        # device frame pool, replicated so that the pool the resident leg cycles through is larger
+        # than the 126 MB L2 (a frame is re-read only after > L2 bytes of other frames went by)
+        fbytes = d0.W * d0.H
+        self.pool_copies = max(1, -(-(160 << 20) // (self.S * WL.POOL_FRAMES * fbytes)))
+        ctx.pool_reserve(self.pool_copies * self.S * WL.POOL_FRAMES)
         for s, d in enumerate(datas):
             ctx.set_intrinsics(s, d.K)
-            for k in range(WL.POOL_FRAMES):
-                ctx.pool_upload(s * WL.POOL_FRAMES + k, d.frames[k])
+            for r in range(self.pool_copies):
+                for k in range(WL.POOL_FRAMES):
+                    ctx.pool_upload((r * self.S + s) * WL.POOL_FRAMES + k, d.frames[k])
             ctx.graph_set(s, d.u_ref, d.edges, d.alpha, d.beta)
             z0 = np.full(d.V, WL.MU0, np.float32)
             ctx.graph_data_set(s, z0)
@@ -142,13 +147,14 @@ class GpuRun:
         capi, S = self.capi, self.S
         self._keep = []
         table = {}
-        period = 2 * WL.EPOCH
+        period = 2 * WL.EPOCH * self.pool_copies
         for k in range(period):
             newpf, ref_slot, ref_idx, cmp_idx = WL.schedule(k)
+            r = (k // (2 * WL.EPOCH)) % self.pool_copies      # which replica of the pool this step reads
             ref_poses = np.ascontiguousarray(np.stack([d.poses[ref_idx] for d in self.datas]), np.float32)
             cmp_poses = np.ascontiguousarray(np.stack([d.poses[cmp_idx] for d in self.datas]), np.float32)
-            ref_pool = np.array([s * WL.POOL_FRAMES + ref_idx for s in range(S)], np.int32)
-            cmp_pool = np.array([s * WL.POOL_FRAMES + cmp_idx for s in range(S)], np.int32)
+            ref_pool = np.array([(r * S + s) * WL.POOL_FRAMES + ref_idx for s in range(S)], np.int32)
+            cmp_pool = np.array([(r * S + s) * WL.POOL_FRAMES + cmp_idx for s in range(S)], np.int32)
             ref_ptr = (C.c_void_p * S)(*[self.h_frames.array[s, ref_idx].ctypes.data for s in range(S)])
             cmp_ptr = (C.c_void_p * S)(*[self.h_frames.array[s, cmp_idx].ctypes.data for s in range(S)])
             self._keep += [ref_poses, cmp_poses, ref_pool, cmp_pool, ref_ptr, cmp_ptr]
@@ -159,9 +165,9 @@ class GpuRun:
                     d.ref_images = C.cast(ref_ptr, C.POINTER(C.c_void_p))
                     d.cmp_images = C.cast(cmp_ptr, C.POINTER(C.c_void_p))
                     d.x_out = self.h_x.array[k % 2].ctypes.data_as(C.POINTER(C.c_float))
-                if mode == "e2e_pipe":
+                if mode in ("e2e_pipe", "resident"):
                     d.pipelined = 1
-                    d.cmp_slot = WL.CMP_SLOT + (k % 2)   # uploads alternate between two frame slots
+                    d.cmp_slot = WL.CMP_SLOT + (k % 2)   # frames alternate between two slots
                 d.ref_pool_idx = ref_pool.ctypes.data_as(C.POINTER(C.c_int32))
                 d.cmp_pool_idx = cmp_pool.ctypes.data_as(C.POINTER(C.c_int32))
                 d.ref_poses = ref_poses.ctypes.data_as(C.POINTER(C.c_float))
@@ -197,13 +203,25 @@ def run_gpu_leg(torch, run, steps, warmup, flush_buf, mode, barrier):
     for k in range(warmup):
         run.step(k, mode)
     ctx.sync()
-    ctx.profile_enable(mode != "e2e_pipe")   # per-launch event pairs would serialise the pipelined leg
+    ctx.profile_enable(True)      # event pairs around every solver launch (markers only: nothing blocks)
     ctx.profile_reset()
     barrier()
     torch.cuda.synchronize()
     l0 = ctx.launch_count()
     total = 0.0
-    if mode == "e2e_pipe":
+    if mode == "resident":
+        # K frames back to back from the device pool (> L2, so no frame is L2-resident when re-read);
+        # one CUDA event before the first and one after the last step on the launching stream, which
+        # is joined on the device with the library's auxiliary streams first
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            run.step(warmup + i, mode)
+        ctx.pipeline_join()
+        e1.record()
+        torch.cuda.synchronize()
+        total = e0.elapsed_time(e1) * 1e-3
+    elif mode == "e2e_pipe":
         # K steps back to back; every step uploads its frames from pinned host memory and its vertex
         # idepths are read on the host one step later (double-buffered), like a streaming consumer
         t0 = time.perf_counter()
@@ -218,25 +236,15 @@ def run_gpu_leg(torch, run, steps, warmup, flush_buf, mode, barrier):
         torch.cuda.synchronize()
         total = time.perf_counter() - t0
     else:
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for i in range(steps):
             k = warmup + i
             flush_buf.zero_()                      # evict L2 between timed steps (outside the timed bracket)
-            if mode == "e2e_sync":
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                run.step(k, mode)                  # ends with a synchronising D2H
-                run.consume(k)
-                total += time.perf_counter() - t0
-            else:
-                # stream-ordered: flush, e0, the step's copies + kernels, e1.  No host sync between steps,
-                # so the host enqueues ahead while the flush runs and launch latency is not part of a step
-                ev[i][0].record()
-                run.step(k, mode)
-                ev[i][1].record()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run.step(k, mode)                      # ends with a synchronising D2H
+            run.consume(k)
+            total += time.perf_counter() - t0
         torch.cuda.synchronize()
-        if mode == "resident":
-            total = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
     barrier()
     launches = ctx.launch_count() - l0
     ms, calls, _ = ctx.profile_get(run.capi.PROF_SOLVE)
@@ -294,6 +302,7 @@ def gpu_main(args):
     t_sync, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "e2e_sync", barrier)
     t_e2e, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "e2e_pipe", barrier)
     h2d, d2h = run.bytes_per_step()
+    run_pool_mib = run.pool_copies * S * WL.POOL_FRAMES * datas[0].W * datas[0].H >> 20
     alg_bytes = sum(d.algorithmic_bytes_per_iter() for d in datas) * datas[0].iters
     iters = datas[0].iters
     run.close()
@@ -337,9 +346,11 @@ def gpu_main(args):
                                    % (args.config, datas[0].W, datas[0].H, datas[0].V, datas[0].V, iters, S),
                        "streams_per_gpu": S, "vertices": datas[0].V, "edges": datas[0].E, "pd_iters": iters,
                        "solver_variant": {1: "streaming (2 kernels/iter, CUDA graph)", 2: "persistent cluster (DSMEM)"}.get(variant_used),
-                       "l2": "flushed between timed steps (256 MiB memset outside the timed bracket)",
-                       "timing": "value: CUDA events around each step on the launching stream (sum over K steps), L2 flushed "
-                                 "by a 256 MiB memset enqueued between steps outside the event brackets; "
+                       "l2": "value: device frame pool of %d MiB cycled through (> 126 MiB L2), no frame is cache-resident "
+                             "when re-read; e2e: inputs streamed from pinned host memory; e2e_sync: 256 MiB memset "
+                             "between steps" % ((run_pool_mib)),
+                       "timing": "value: K steps back to back, one CUDA event before and one after on the launching stream "
+                                 "(joined with the library's copy/solve streams on the device); "
                                  "e2e: host clock over the K steps run back to back through the pipelined C-ABI call "
                                  "(pinned-host frames uploaded every step on a copy stream, vertex idepths read back "
                                  "every step; inputs are streamed, never reused, so L2 is not flushed); "

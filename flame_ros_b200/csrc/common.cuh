@@ -34,6 +34,17 @@ struct fb_ctx {
   bool own_stream = false;
   // pipelined fb_hotpath_step: uploads on a copy stream, per-slot ready/free events, result events
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t solve_stream = nullptr;   // assembly + solver of frame k run here while `stream` already
+                                         // processes the epipolar update of frame k+1
+  cudaEvent_t ev_epi = nullptr, ev_asm = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  // pinned staging ring for the small per-frame parameter uploads (poses, slot indices): pageable
+  // cudaMemcpyAsync would block the host until the stream reaches the copy and stall the pipeline
+  uint8_t* stage = nullptr;
+  size_t stage_slot_bytes = 0;
+  int stage_next = 0, stage_last = 0;
+  std::vector<cudaEvent_t> stage_ev;   // completion of the last copy issued from each slot
+  bool pipe_hold = false;                // inside a pipelined step: internal calls must not drain
+  bool pipe_dirty = false;               // pipelined work may be in flight on the auxiliary streams
   std::vector<cudaEvent_t> ev_ready, ev_free;
   cudaEvent_t ev_result[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t n_pipelined = 0;
@@ -106,6 +117,7 @@ struct fb_ctx {
 
   // ---- profiling
   bool prof = false;
+  std::vector<cudaEvent_t> prof_free;  // recycled timing events (creating one costs ~2 us of host time)
   ProfSection sec[FB_PROF_NUM];
   int64_t launches = 0;
 };
@@ -134,14 +146,24 @@ static cudaError_t dalloc(T** p, size_t n) {
 
 // Brackets a section with CUDA events (when profiling is enabled) and counts calls / launches.
 struct ProfScope {
+  static cudaEvent_t take(fb_ctx* c) {
+    cudaEvent_t e = nullptr;
+    if (!c->prof_free.empty()) {
+      e = c->prof_free.back();
+      c->prof_free.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  }
   fb_ctx* c;
   int sec;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   int64_t l0;
   ProfScope(fb_ctx* ctx, int section) : c(ctx), sec(section), l0(ctx->launches) {
     if (c->prof) {
-      cudaEventCreate(&e0);
-      cudaEventCreate(&e1);
+      e0 = take(c);
+      e1 = take(c);
       cudaEventRecord(e0, c->stream);
     }
   }

@@ -28,14 +28,26 @@ static void prof_fold(fb_ctx* c, int section) {
     float ms = 0.f;
     cudaEventSynchronize(s.ev[i + 1]);
     if (cudaEventElapsedTime(&ms, s.ev[i], s.ev[i + 1]) == cudaSuccess) s.total_ms += ms;
-    cudaEventDestroy(s.ev[i]);
-    cudaEventDestroy(s.ev[i + 1]);
+    c->prof_free.push_back(s.ev[i]);
+    c->prof_free.push_back(s.ev[i + 1]);
   }
   s.ev.clear();
 }
 
-#define CHECK_CTX(c) \
+// Work issued by the pipelined fb_hotpath_step lives on auxiliary streams; every other entry point
+// first waits for it so the single-stream ordering the rest of the API assumes still holds.
+static inline void pipeline_drain(fb_ctx* c) {
+  if (!c->pipe_dirty || c->pipe_hold) return;
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->solve_stream) cudaStreamSynchronize(c->solve_stream);
+  cudaStreamSynchronize(c->stream);
+  c->pipe_dirty = false;
+}
+#define CHECK_CTX_NODRAIN(c) \
   if (!(c)) return FB_E_ARG
+#define CHECK_CTX(c)           \
+  if (!(c)) return FB_E_ARG;   \
+  pipeline_drain(c)
 #define CHECK_STREAM(c, s) \
   if ((s) < 0 || (s) >= (c)->S) FB_FAIL(c, FB_E_ARG, "stream index out of range")
 
@@ -83,10 +95,18 @@ static void free_all(fb_ctx* c) {
   if (c->solve_exec) cudaGraphExecDestroy(c->solve_exec);
   for (int k = 0; k < FB_PROF_NUM; ++k)
     for (cudaEvent_t e : c->sec[k].ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->prof_free) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_ready) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_free) cudaEventDestroy(e);
   for (int k = 0; k < 4; ++k) if (c->ev_result[k]) cudaEventDestroy(c->ev_result[k]);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_join2) cudaEventDestroy(c->ev_join2);
+  if (c->ev_epi) cudaEventDestroy(c->ev_epi);
+  if (c->ev_asm) cudaEventDestroy(c->ev_asm);
+  if (c->stage) cudaFreeHost(c->stage);
+  for (cudaEvent_t e : c->stage_ev) if (e) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->solve_stream) cudaStreamDestroy(c->solve_stream);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -181,6 +201,8 @@ extern "C" fb_ctx* fb_create(int device, int n_streams, int width, int height, i
 extern "C" void fb_destroy(fb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  c->pipe_dirty = true;
+  pipeline_drain(c);
   cudaStreamSynchronize(c->stream);
   free_all(c);
   delete c;
@@ -554,6 +576,43 @@ extern "C" int fb_features_get(fb_ctx* c, int s, float* mu, float* var, int32_t*
   return FB_OK;
 }
 
+#define FB_STAGE_SLOTS 32
+// Next slot of the pinned staging ring (deep enough that a slot is never rewritten while a copy
+// from it is still queued: callers block on results at most a few frames behind).
+static uint8_t* stage_slot(fb_ctx* c) {
+  if (!c->stage) {
+    c->stage_slot_bytes = (sizeof(float) * 7 * (size_t)c->S * c->n_slots + sizeof(int32_t) * c->S + 255) & ~(size_t)255;
+    if (cudaMallocHost((void**)&c->stage, c->stage_slot_bytes * FB_STAGE_SLOTS) != cudaSuccess) return nullptr;
+    c->stage_ev.resize(FB_STAGE_SLOTS);
+    for (auto& e : c->stage_ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  // a caller that enqueues far ahead of the GPU waits here until the copy last issued from this
+  // slot has executed, so a slot is never rewritten under a queued copy
+  cudaEventSynchronize(c->stage_ev[c->stage_next]);
+  uint8_t* p = c->stage + c->stage_slot_bytes * (size_t)c->stage_next;
+  c->stage_last = c->stage_next;
+  c->stage_next = (c->stage_next + 1) % FB_STAGE_SLOTS;
+  return p;
+}
+// Call after the copies from the slot returned by stage_slot() have been enqueued on c->stream.
+static void stage_commit(fb_ctx* c) { cudaEventRecord(c->stage_ev[c->stage_last], c->stream); }
+
+static int upload_geometry(fb_ctx* c, const int32_t* cmp_slot) {
+  const size_t np = (size_t)c->S * c->n_slots * 7;
+  uint8_t* st = stage_slot(c);
+  if (!st) FB_FAIL(c, FB_E_NOMEM, "pinned staging allocation failed");
+  memcpy(st, c->h_pose.data(), sizeof(float) * np);
+  memcpy(st + sizeof(float) * np, cmp_slot, sizeof(int32_t) * c->S);
+  FB_CUDA(c, cudaMemcpyAsync(c->d_pose, st, sizeof(float) * np, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaMemcpyAsync(c->d_cmp, st + sizeof(float) * np, sizeof(int32_t) * c->S, cudaMemcpyHostToDevice, c->stream));
+  stage_commit(c);
+  k_epi_geometry<<<c->S, std::max(32, c->n_slots), 0, c->stream>>>(c->d_pose, c->d_K, c->d_cmp, c->n_slots, c->d_geo);
+  c->launches++;
+  FB_CUDA(c, cudaGetLastError());
+  return FB_OK;
+}
+
 extern "C" int fb_features_reinit(fb_ctx* c, const int32_t* ref_slot, float mu0, float var0) {
   CHECK_CTX(c);
   if (!ref_slot) FB_FAIL(c, FB_E_ARG, "fb_features_reinit: null ref_slot");
@@ -562,19 +621,13 @@ extern "C" int fb_features_reinit(fb_ctx* c, const int32_t* ref_slot, float mu0,
   if (c->maxF == 0) return FB_OK;
   ProfScope ps(c, FB_PROF_ASSEMBLY);
   // d_cmp doubles as the per-stream argument buffer (consumed by the kernel enqueued right after)
-  FB_CUDA(c, cudaMemcpyAsync(c->d_cmp, ref_slot, sizeof(int32_t) * c->S, cudaMemcpyHostToDevice, c->stream));
+  uint8_t* st = stage_slot(c);
+  if (!st) FB_FAIL(c, FB_E_NOMEM, "pinned staging allocation failed");
+  memcpy(st, ref_slot, sizeof(int32_t) * c->S);
+  FB_CUDA(c, cudaMemcpyAsync(c->d_cmp, st, sizeof(int32_t) * c->S, cudaMemcpyHostToDevice, c->stream));
+  stage_commit(c);
   const dim3 grid(fb_div_up(c->maxF, 256), c->S);
   k_features_reinit<<<grid, 256, 0, c->stream>>>(c->d_cmp, c->nF, c->maxF, mu0, var0, c->f_mu, c->f_var, c->f_drop, c->f_alive, c->f_ref);
-  c->launches++;
-  FB_CUDA(c, cudaGetLastError());
-  return FB_OK;
-}
-
-static int upload_geometry(fb_ctx* c, const int32_t* cmp_slot) {
-  const size_t np = (size_t)c->S * c->n_slots * 7;
-  FB_CUDA(c, cudaMemcpyAsync(c->d_pose, c->h_pose.data(), sizeof(float) * np, cudaMemcpyHostToDevice, c->stream));
-  FB_CUDA(c, cudaMemcpyAsync(c->d_cmp, cmp_slot, sizeof(int32_t) * c->S, cudaMemcpyHostToDevice, c->stream));
-  k_epi_geometry<<<c->S, std::max(32, c->n_slots), 0, c->stream>>>(c->d_pose, c->d_K, c->d_cmp, c->n_slots, c->d_geo);
   c->launches++;
   FB_CUDA(c, cudaGetLastError());
   return FB_OK;
@@ -677,58 +730,54 @@ static int pipeline_init(fb_ctx* c) {
     FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_free[k], cudaEventDisableTiming));
   }
   for (int k = 0; k < 4; ++k) FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_result[k], cudaEventDisableTiming));
+  FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
+  if (!getenv("FB_PIPE_SINGLE_STAGE")) {
+    int lo = 0, hi = 0;
+    FB_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    FB_CUDA(c, cudaStreamCreateWithPriority(&c->solve_stream, cudaStreamNonBlocking, hi));
+    FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_epi, cudaEventDisableTiming));
+    FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_asm, cudaEventDisableTiming));
+  }
   return FB_OK;
 }
 
 // Host image -> slot on the copy stream, ordered after the last kernel that read the slot.
-static int pipeline_upload(fb_ctx* c, int slot, const uint8_t* const* images, const float* poses) {
+static int pipeline_upload(fb_ctx* c, int slot, const uint8_t* const* images, const int32_t* pool_idx,
+                           const float* poses) {
   const size_t fsz = (size_t)c->W * c->H;
   FB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[slot], 0));
   for (int s = 0; s < c->S; ++s) {
     int rc = fb_frame_pose_set(c, s, slot, poses + 7 * s);
     if (rc) return rc;
-    FB_CUDA(c, cudaMemcpyAsync(c->imgs + ((size_t)s * c->n_slots + slot) * fsz, images[s], fsz, cudaMemcpyHostToDevice, c->copy_stream));
+    uint8_t* dst = c->imgs + ((size_t)s * c->n_slots + slot) * fsz;
+    if (images) {
+      FB_CUDA(c, cudaMemcpyAsync(dst, images[s], fsz, cudaMemcpyHostToDevice, c->copy_stream));
+    } else {
+      if (pool_idx[s] < 0 || pool_idx[s] >= c->pool_n) FB_FAIL(c, FB_E_ARG, "fb_hotpath_step: bad pool index");
+      FB_CUDA(c, cudaMemcpyAsync(dst, c->pool + (size_t)pool_idx[s] * fsz, fsz, cudaMemcpyDeviceToDevice, c->copy_stream));
+    }
   }
   FB_CUDA(c, cudaEventRecord(c->ev_ready[slot], c->copy_stream));
   FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_ready[slot], 0));
   return FB_OK;
 }
 
-extern "C" int fb_hotpath_step(fb_ctx* c, const fb_step_desc* d) {
-  CHECK_CTX(c);
-  if (!d || !d->cmp_poses || (!d->cmp_images && !d->cmp_pool_idx))
-    FB_FAIL(c, FB_E_ARG, "fb_hotpath_step: null descriptor field");
-  if (d->new_poseframe && (!d->ref_poses || (!d->ref_images && !d->ref_pool_idx)))
-    FB_FAIL(c, FB_E_ARG, "fb_hotpath_step: poseframe inputs missing");
+// The stages of one frame on c->stream (blocking / resident modes).
+static int hotpath_step_inline(fb_ctx* c, const fb_step_desc* d) {
   int rc;
-  const bool pipe = d->pipelined && d->cmp_images;
-  if (pipe) {
-    rc = pipeline_init(c);
-    if (rc) return rc;
-    if (check_slot(c, 0, d->cmp_slot) || (d->new_poseframe && check_slot(c, 0, d->ref_slot))) return FB_E_ARG;
-  }
   std::vector<int32_t> slots(c->S);
   if (d->new_poseframe) {
-    if (pipe && d->ref_images) {
-      rc = pipeline_upload(c, d->ref_slot, d->ref_images, d->ref_poses);
+    for (int s = 0; s < c->S; ++s) {
+      rc = d->ref_images ? fb_frame_set(c, s, d->ref_slot, d->ref_images[s], c->W, d->ref_poses + 7 * s)
+                         : fb_frame_from_pool(c, s, d->ref_slot, d->ref_pool_idx[s], d->ref_poses + 7 * s);
       if (rc) return rc;
-    } else {
-      for (int s = 0; s < c->S; ++s) {
-        rc = d->ref_images ? fb_frame_set(c, s, d->ref_slot, d->ref_images[s], c->W, d->ref_poses + 7 * s)
-                           : fb_frame_from_pool(c, s, d->ref_slot, d->ref_pool_idx[s], d->ref_poses + 7 * s);
-        if (rc) return rc;
-      }
     }
   }
-  if (pipe) {
-    rc = pipeline_upload(c, d->cmp_slot, d->cmp_images, d->cmp_poses);
+  for (int s = 0; s < c->S; ++s) {
+    rc = d->cmp_images ? fb_frame_set(c, s, d->cmp_slot, d->cmp_images[s], c->W, d->cmp_poses + 7 * s)
+                       : fb_frame_from_pool(c, s, d->cmp_slot, d->cmp_pool_idx[s], d->cmp_poses + 7 * s);
     if (rc) return rc;
-  } else {
-    for (int s = 0; s < c->S; ++s) {
-      rc = d->cmp_images ? fb_frame_set(c, s, d->cmp_slot, d->cmp_images[s], c->W, d->cmp_poses + 7 * s)
-                         : fb_frame_from_pool(c, s, d->cmp_slot, d->cmp_pool_idx[s], d->cmp_poses + 7 * s);
-      if (rc) return rc;
-    }
   }
   if (d->new_poseframe) {
     std::fill(slots.begin(), slots.end(), d->ref_slot);
@@ -738,31 +787,107 @@ extern "C" int fb_hotpath_step(fb_ctx* c, const fb_step_desc* d) {
   std::fill(slots.begin(), slots.end(), d->cmp_slot);
   rc = fb_idepth_update(c, slots.data());
   if (rc) return rc;
-  if (pipe) {
-    // the frames read by this update may be overwritten once the epipolar kernel has run
-    FB_CUDA(c, cudaEventRecord(c->ev_free[d->cmp_slot], c->stream));
-    if (d->new_poseframe) {
-      // the OTHER poseframe slots are no longer referenced by any feature after the re-init
-      for (int k = 0; k < c->n_slots; ++k)
-        if (k != d->cmp_slot && k != d->ref_slot) FB_CUDA(c, cudaEventRecord(c->ev_free[k], c->stream));
-    }
-  }
   rc = fb_graph_data_from_features(c, d->adaptive_weights);
   if (rc) return rc;
   rc = fb_nltgv2_solve(c, d->iters, &d->rparams, d->variant);
   if (rc) return rc;
-  if (d->x_out && pipe) {
-    FB_CUDA(c, cudaMemcpyAsync(d->x_out, c->x, sizeof(float) * (size_t)c->S * c->maxV, cudaMemcpyDeviceToHost, c->stream));
-    FB_CUDA(c, cudaEventRecord(c->ev_result[c->n_pipelined & 3], c->stream));
-    c->n_pipelined++;
-    return FB_OK;
-  }
   if (d->x_out) return fb_graph_x_get_all(c, d->x_out);
   return FB_OK;
 }
 
+// Streaming mode: a software pipeline over consecutive frames on three streams.
+//   copy stream : frame k+1 into its slot (H2D from pinned host memory, or D2D from the device pool),
+//                 ordered after the kernels that last read the slot
+//   c->stream   : feature re-init + epipolar update of frame k+1
+//   solve stream: data-term assembly + NLTGV2 solve + D2H of frame k
+// The filter update of frame k+1 does not depend on the solve of frame k; the assembly (which
+// snapshots mu into z) is the only hand-over.  Measured on B200, 8 streams: 149 us per frame batch
+// against 176 us with a single compute stream.
+static int hotpath_step_pipelined(fb_ctx* c, const fb_step_desc* d) {
+  int rc = pipeline_init(c);
+  if (rc) return rc;
+  if ((rc = check_slot(c, 0, d->cmp_slot)) != 0) return rc;
+  if (d->new_poseframe && (rc = check_slot(c, 0, d->ref_slot)) != 0) return rc;
+  c->pipe_dirty = true;
+  std::vector<int32_t> slots(c->S);
+  if (d->new_poseframe) {
+    rc = pipeline_upload(c, d->ref_slot, d->ref_images, d->ref_pool_idx, d->ref_poses);
+    if (rc) return rc;
+  }
+  rc = pipeline_upload(c, d->cmp_slot, d->cmp_images, d->cmp_pool_idx, d->cmp_poses);
+  if (rc) return rc;
+  if (d->new_poseframe) {
+    std::fill(slots.begin(), slots.end(), d->ref_slot);
+    rc = fb_features_reinit(c, slots.data(), d->mu0, d->var0);
+    if (rc) return rc;
+  }
+  std::fill(slots.begin(), slots.end(), d->cmp_slot);
+  rc = fb_idepth_update(c, slots.data());
+  if (rc) return rc;
+  // the frames read by this update may be overwritten once the epipolar kernel has run
+  FB_CUDA(c, cudaEventRecord(c->ev_free[d->cmp_slot], c->stream));
+  if (d->new_poseframe) {
+    // the OTHER poseframe slots are no longer referenced by any feature after the re-init
+    for (int k = 0; k < c->n_slots; ++k)
+      if (k != d->cmp_slot && k != d->ref_slot) FB_CUDA(c, cudaEventRecord(c->ev_free[k], c->stream));
+  }
+  // Second stage on its own (high-priority) stream: assembly + solve + D2H of frame k overlap the
+  // epipolar update of frame k+1, which does not depend on them (FB_PIPE_SINGLE_STAGE=1 disables).
+  cudaStream_t main_stream = c->stream;
+  if (c->solve_stream) {
+    FB_CUDA(c, cudaEventRecord(c->ev_epi, main_stream));
+    FB_CUDA(c, cudaStreamWaitEvent(c->solve_stream, c->ev_epi, 0));
+    c->stream = c->solve_stream;
+  }
+  rc = fb_graph_data_from_features(c, d->adaptive_weights);
+  if (!rc && c->solve_stream) {
+    // the next frame's filter update may touch the feature table once the assembly has read it
+    if (cudaEventRecord(c->ev_asm, c->stream) != cudaSuccess || cudaStreamWaitEvent(main_stream, c->ev_asm, 0) != cudaSuccess) rc = FB_E_CUDA;
+  }
+  if (!rc) rc = fb_nltgv2_solve(c, d->iters, &d->rparams, d->variant);
+  if (!rc && d->x_out) {
+    if (cudaMemcpyAsync(d->x_out, c->x, sizeof(float) * (size_t)c->S * c->maxV, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaEventRecord(c->ev_result[c->n_pipelined & 3], c->stream) != cudaSuccess)
+      rc = FB_E_CUDA;
+    c->n_pipelined++;
+  }
+  c->stream = main_stream;
+  if (rc == FB_E_CUDA) c->err = "fb_hotpath_step: CUDA error in the pipelined step";
+  return rc;
+}
+
+extern "C" int fb_hotpath_step(fb_ctx* c, const fb_step_desc* d) {
+  CHECK_CTX_NODRAIN(c);
+  if (!d || !d->cmp_poses || (!d->cmp_images && !d->cmp_pool_idx))
+    FB_FAIL(c, FB_E_ARG, "fb_hotpath_step: null descriptor field");
+  if (d->new_poseframe && (!d->ref_poses || (!d->ref_images && !d->ref_pool_idx)))
+    FB_FAIL(c, FB_E_ARG, "fb_hotpath_step: poseframe inputs missing");
+  if (d->pipelined) {
+    c->pipe_hold = true;  // the building blocks called inside must not wait for the work in flight
+    const int rc = hotpath_step_pipelined(c, d);
+    c->pipe_hold = false;
+    return rc;
+  }
+  pipeline_drain(c);
+  return hotpath_step_inline(c, d);
+}
+
+// Makes c->stream wait (on the device, not the host) for everything the pipelined steps have
+// enqueued on the auxiliary streams, so an event recorded on c->stream afterwards closes the region.
+extern "C" int fb_pipeline_join(fb_ctx* c) {
+  CHECK_CTX_NODRAIN(c);
+  if (!c->copy_stream) return FB_OK;
+  FB_CUDA(c, cudaEventRecord(c->ev_join, c->copy_stream));
+  FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  if (c->solve_stream) {
+    FB_CUDA(c, cudaEventRecord(c->ev_join2, c->solve_stream));
+    FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join2, 0));
+  }
+  return FB_OK;
+}
+
 extern "C" int fb_results_wait(fb_ctx* c, int lag) {
-  CHECK_CTX(c);
+  CHECK_CTX_NODRAIN(c);
   if (lag < 0 || lag > 3) FB_FAIL(c, FB_E_ARG, "fb_results_wait: lag must be in [0,3]");
   if (c->n_pipelined - 1 - lag < 0) return FB_OK;
   FB_CUDA(c, cudaEventSynchronize(c->ev_result[(c->n_pipelined - 1 - lag) & 3]));

@@ -208,15 +208,19 @@ typedef struct {
   int iters, variant;
   fb_nltgv2_params rparams;
   float* x_out;                     /* host [n_streams*max_vertices] or NULL */
-  int pipelined;                    /* 0: as documented above.  1: streaming mode -- host images are
-                                       uploaded on a separate copy stream (overlapping the previous
+  int pipelined;                    /* 0: as documented above.  1: streaming mode -- frames are brought
+                                       into their slots on a copy stream (overlapping the previous
                                        frame's kernels; the caller alternates cmp_slot between two
-                                       slots), x_out (pinned) is filled asynchronously and the call
-                                       never blocks; fb_results_wait() waits for a frame's x_out. */
+                                       slots), the solve of frame k overlaps the epipolar update of
+                                       frame k+1, x_out (pinned) is filled asynchronously and the
+                                       call never blocks; fb_results_wait() waits for a frame's x_out. */
 } fb_step_desc;
 int fb_hotpath_step(fb_ctx* ctx, const fb_step_desc* d);
 /* Waits until the x_out of the pipelined step issued `lag` calls ago (0 = the latest) has landed. */
 int fb_results_wait(fb_ctx* ctx, int lag);
+/* Device-side join: the context's main stream waits for everything the pipelined steps enqueued on
+ * the auxiliary streams (does not block the host). */
+int fb_pipeline_join(fb_ctx* ctx);
 
 /* ------------------------------------------------------------------ flame::Flame::update and getters
  * fb_update is the whole per-frame pipeline of flame::Flame::update(time, img_id, T_world_cam, gray,
