@@ -36,7 +36,7 @@ UNIT = "frames/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=8, help="independent streams per GPU (batched launch)")
@@ -63,37 +63,66 @@ def peaks():
 
 # --------------------------------------------------------------------------------------- clocks
 class ClockSampler(threading.Thread):
-    """Samples SM clock + throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples the SM clock and the throttle reasons every few ms while the timed legs run (NVML via
+    nvidia_ml_py; falls back to `nvidia-smi -lms` when NVML cannot be loaded)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.003):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+        self.index, self.period, self.stop_flag, self.proc = index, period_s, False, None
+        self.sm, self.sm_max, self.reasons = [], None, set()
+
+    def _run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        names = {getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                 getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                 getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                 getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap"}
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+            r = int(get_reasons(h))
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+            time.sleep(self.period)
+        N.nvmlShutdown()
+
+    def _run_smi(self):
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits", "-lms", "100"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            if self.stop_flag:
+                break
+            c = [v.strip() for v in line.split(",")]
+            if len(c) >= 6 and c[0].replace(".", "").isdigit():
+                self.sm.append(float(c[0]))
+                self.sm_max = float(c[1])
+                self.reasons |= {names[k] for k in range(4) if c[2 + k] == "Active"}
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.samples.append([c.strip() for c in line.split(",")])
+            self._run_nvml()
         except Exception:
-            pass
+            try:
+                self._run_smi()
+            except Exception:
+                pass
 
     def stop(self):
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for s in self.samples if len(s) >= 6 for k in range(4) if s[2 + k] == "Active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self.join(timeout=2.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -113,6 +142,7 @@ class GpuRun:
         # than the 126 MB L2 (a frame is re-read only after > L2 bytes of other frames went by)
         fbytes = d0.W * d0.H
         self.pool_copies = max(1, -(-(160 << 20) // (self.S * WL.POOL_FRAMES * fbytes)))
+        self.pool_copies = 3 * -(-self.pool_copies // 3)   # schedule period divisible by the 3 result buffers
         ctx.pool_reserve(self.pool_copies * self.S * WL.POOL_FRAMES)
         for s, d in enumerate(datas):
             ctx.set_intrinsics(s, d.K)
@@ -130,7 +160,7 @@ class GpuRun:
         self.h_frames = capi.PinnedBuffer((self.S, WL.POOL_FRAMES, d0.H, d0.W), np.uint8)
         for s, d in enumerate(datas):
             np.copyto(self.h_frames.array[s], d.frames)
-        self.h_x = capi.PinnedBuffer((2, self.S, V), np.float32)   # double-buffered results
+        self.h_x = capi.PinnedBuffer((3, self.S, V), np.float32)   # triple-buffered results
         self.maxV = V
         self.cmp = np.full(self.S, WL.CMP_SLOT, np.int32)
         ctx.sync()
@@ -164,7 +194,7 @@ class GpuRun:
                 if mode != "resident":
                     d.ref_images = C.cast(ref_ptr, C.POINTER(C.c_void_p))
                     d.cmp_images = C.cast(cmp_ptr, C.POINTER(C.c_void_p))
-                    d.x_out = self.h_x.array[k % 2].ctypes.data_as(C.POINTER(C.c_float))
+                    d.x_out = self.h_x.array[k % 3].ctypes.data_as(C.POINTER(C.c_float))
                 if mode in ("e2e_pipe", "resident"):
                     d.pipelined = 1
                     d.cmp_slot = WL.CMP_SLOT + (k % 2)   # frames alternate between two slots
@@ -188,7 +218,7 @@ class GpuRun:
 
     def consume(self, k):
         """Touch the result of step k (the application's read of the vertex inverse depths)."""
-        return float(self.h_x.array[k % 2, 0, 0])
+        return float(self.h_x.array[k % 3, 0, 0])
 
     def bytes_per_step(self):
         d = self.datas[0]
@@ -223,14 +253,17 @@ def run_gpu_leg(torch, run, steps, warmup, flush_buf, mode, barrier):
         total = e0.elapsed_time(e1) * 1e-3
     elif mode == "e2e_pipe":
         # K steps back to back; every step uploads its frames from pinned host memory and its vertex
-        # idepths are read on the host one step later (double-buffered), like a streaming consumer
+        # idepths are read on the host two steps later (triple-buffered), like a streaming consumer:
+        # the host stays two frames ahead of the GPU so the next upload is already in flight
         t0 = time.perf_counter()
         for i in range(steps):
             k = warmup + i
             run.step(k, mode)
-            if i > 0:
-                ctx.results_wait(1)
-                run.consume(k - 1)
+            if i > 1:
+                ctx.results_wait(2)
+                run.consume(k - 2)
+        ctx.results_wait(1)
+        run.consume(warmup + steps - 2)
         ctx.results_wait(0)
         run.consume(warmup + steps - 1)
         torch.cuda.synchronize()
@@ -293,10 +326,10 @@ def gpu_main(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     peak, peak_src = peaks()
 
+    run = GpuRun(capi, datas, local_rank, stream_ptr, args.variant)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
-    run = GpuRun(capi, datas, local_rank, stream_ptr, args.variant)
+        sampler.start()   # samples while the three timed legs below run (set-up is excluded)
     t_res, launches, solve_ms, solve_calls = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "resident", barrier)
     variant_used = run.ctx.last_solver_variant()
     t_sync, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "e2e_sync", barrier)
