@@ -113,6 +113,7 @@ struct fb_ctx {
   int solve_only = -1;
   fb_nltgv2_params solve_params{};
   int last_variant = 0;
+  int last_cluster = 0;  // cluster size of the last variant-2 launch
   int cluster_min = 1;  // FB_CLUSTER_MIN env: lower bound on the cluster size of variant 2
 
   // ---- profiling

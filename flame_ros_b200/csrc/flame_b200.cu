@@ -187,7 +187,7 @@ extern "C" fb_ctx* fb_create(int device, int n_streams, int width, int height, i
   fb_default_epi_params(&c->epi);
   if (const char* e = getenv("FB_CLUSTER_MIN")) {
     const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->cluster_min = v;
+    if (v >= 1 && v <= 16) c->cluster_min = v;
   }
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
     g_create_error = "fb_create: initialisation failed";
@@ -437,6 +437,7 @@ static int fb_nltgv2_solve_stream(fb_ctx* c, int s, int iters, const fb_nltgv2_p
 }
 
 extern "C" int fb_last_solver_variant(const fb_ctx* c) { return c ? c->last_variant : 0; }
+extern "C" int fb_last_cluster_size(const fb_ctx* c) { return c ? c->last_cluster : 0; }
 
 extern "C" int fb_costs(fb_ctx* c, int s, float data_factor, double* smooth, double* data) {
   CHECK_CTX(c);

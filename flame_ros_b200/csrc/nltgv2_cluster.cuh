@@ -57,6 +57,7 @@ struct ClusterPlan {
   };
   std::vector<Topo> topo;
   size_t smem_set = 0;  // dynamic shared memory size the kernel attribute is currently set to
+  int max_active[FBC_MAXC + 1] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};  // co-resident clusters per size
   bool nonportable_set = false;
 };
 
@@ -664,12 +665,61 @@ static int solve_cluster(fb_ctx* c, int iters, const fb_nltgv2_params* p, int on
       any = true;
     }
   if (!any) return FB_OK;
-  if (c->cluster_min > C) C = c->cluster_min;  // tuning knob: spread a graph over more SMs
-  // few streams: spread each graph over 16 SMs (non-portable cluster size) -- per-iteration work per
-  // CTA halves while the exchange cost stays, measured 115 -> 93 us per 50-iteration C2 solve
-  int maxV = 0;
-  for (auto& t : P->topo) maxV = std::max(maxV, t.V);
-  if (c->S <= 4 && maxV >= 2048 && C < 16 && !getenv("FB_CLUSTER_NO16")) C = 16;
+  // Cluster size: the largest C (<= 16, non-portable above 8) for which all active streams' clusters
+  // are co-resident, so few streams spread over more SMs (per-CTA work shrinks, the exchange cost
+  // stays: 115 us at C=8 vs 92 us at C=16 for one C2 graph) while many streams keep C small enough
+  // to run in one wave.  Graphs are never cut below ~256 vertices per CTA.
+  int n_act = 0, maxV = 0;
+  for (auto& t : P->topo) {
+    if (t.V > 0) ++n_act;
+    maxV = std::max(maxV, t.V);
+  }
+  if (only >= 0) n_act = 1;
+  if (c->cluster_min > 1) {
+    C = std::max(C, c->cluster_min);  // FB_CLUSTER_MIN: forced lower bound (tuning / tests)
+  } else {
+    const int cmax = std::min(FBC_MAXC, std::max(C, maxV / 256));
+    for (int cand = cmax; cand > C; --cand) {
+      if (P->max_active[cand] < 0) {
+        cudaLaunchConfig_t q{};
+        q.gridDim = dim3((unsigned)(cand * 64));
+        q.blockDim = dim3(FBC_THREADS);
+        q.dynamicSmemBytes = 96 * 1024;  // registers, not shared memory, limit residency (1 CTA / SM)
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = (unsigned)cand;
+        qa[0].val.clusterDim.y = 1;
+        qa[0].val.clusterDim.z = 1;
+        q.attrs = qa;
+        q.numAttrs = 1;
+        if (P->smem_set < 96 * 1024) {
+          cudaFuncSetAttribute(k_nltgv2_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+          P->smem_set = 96 * 1024;
+        }
+        if (cand > 8 && !P->nonportable_set) {
+          cudaFuncSetAttribute(k_nltgv2_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+          P->nonportable_set = true;
+        }
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, k_nltgv2_cluster, &q) != cudaSuccess) {
+          cudaGetLastError();
+          n = 0;
+        }
+        P->max_active[cand] = n;
+      }
+      if (P->max_active[cand] >= n_act) {
+        FbcPart probe;
+        bool fits = true;
+        for (auto& t : P->topo)
+          if (t.V > 0 && t.partC != cand && !fbc_partition(t, cand, probe)) fits = false;
+        if (fits) {
+          C = cand;
+          break;
+        }
+      }
+    }
+  }
+  c->last_cluster = C;
   int rc = fbc_upload_plans(c, C);
   if (rc) return rc;
   const size_t smem = fbc_smem_bytes(P->capV, P->capH, P->capI);

@@ -308,6 +308,8 @@ int fb_profile_get(fb_ctx* ctx, int section, float* total_ms, int64_t* calls, in
 int64_t fb_launch_count(const fb_ctx* ctx);
 /* Which solver variant the last fb_nltgv2_solve used (1 or 2). */
 int fb_last_solver_variant(const fb_ctx* ctx);
+/* CTAs per cluster (= SMs per stream) of the last variant-2 launch. */
+int fb_last_cluster_size(const fb_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -132,3 +132,35 @@ def test_ring_eviction_and_prune(capi, oracle):
         live = after["alive"] == 1
         assert np.all(after["ref_slot"][live] == 1)
         assert (before["alive"] == 1).sum() >= live.sum()
+
+
+def test_two_streams_in_one_context_are_independent(capi):
+    """fb_update drives each stream of a batch context on its own cadence (the solver is masked to the
+    stream being updated): interleaved updates of two different streams must equal two single-stream
+    contexts."""
+    W, H = 320, 240
+    K = (synth.K_VGA * np.array([[0.5], [0.5], [1.0]], np.float32)).astype(np.float32)
+    up = capi.default_update_params()
+    up.iters, up.idepth_var_max_graph = 15, 0.05
+    data = [_stream(W, H, K, 9, seed=s, step=0.02 + 0.005 * s) for s in range(2)]
+    solo = []
+    for s in range(2):
+        with capi.Context(1, W, H, 4, 1024, 1024, 3072) as ctx:
+            ctx.set_intrinsics(0, K)
+            ctx.set_update_params(up)
+            for k in range(9):
+                ctx.update(0, k / 30.0, k, data[s][1][k], data[s][0][k][0], k % 3 == 0)
+            solo.append((ctx.get_mesh(0), ctx.get_idepthmap(0), ctx.get_feature_pool(0)))
+    with capi.Context(2, W, H, 4, 1024, 1024, 3072) as ctx:
+        for s in range(2):
+            ctx.set_intrinsics(s, K)
+        ctx.set_update_params(up)
+        for k in range(9):
+            for s in (1, 0):  # interleaved, stream 1 first
+                ctx.update(s, k / 30.0, k, data[s][1][k], data[s][0][k][0], k % 3 == 0)
+        for s in range(2):
+            mesh, dm, pool = ctx.get_mesh(s), ctx.get_idepthmap(s), ctx.get_feature_pool(s)
+            assert np.array_equal(mesh["tris"], solo[s][0]["tris"])
+            assert np.array_equal(mesh["idepth"], solo[s][0]["idepth"])
+            assert np.array_equal(np.nan_to_num(dm, nan=-1), np.nan_to_num(solo[s][1], nan=-1))
+            assert np.array_equal(pool["alive"], solo[s][2]["alive"]) and np.array_equal(pool["mu"], solo[s][2]["mu"])
