@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=8, help="independent streams per GPU (batched launch)")
     ap.add_argument("--config", default="C2", choices=list(WL.CONFIGS))
-    ap.add_argument("--variant", type=int, default=0, help="solver variant: 0 auto, 1 streaming, 2 cluster")
+    ap.add_argument("--variant", type=int, default=0, help="solver variant: 0 auto, 1 streaming, 2 cluster, 3 grid-resident")
     ap.add_argument("--no-single", action="store_true", help="skip the extra single-stream measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -379,8 +379,9 @@ def gpu_main(args):
                                    "%d PD iters/frame; x %d independent streams per GPU, one batched launch"
                                    % (args.config, datas[0].W, datas[0].H, datas[0].V, datas[0].V, iters, S),
                        "streams_per_gpu": S, "vertices": datas[0].V, "edges": datas[0].E, "pd_iters": iters,
-                       "solver_variant": {1: "streaming (2 kernels/iter, CUDA graph)", 2: "persistent cluster (DSMEM)"}.get(variant_used),
-                       "sms_per_stream": cluster_size if variant_used == 2 else None,
+                       "solver_variant": {1: "streaming (2 kernels/iter, CUDA graph)", 2: "persistent cluster (DSMEM)",
+                                          3: "grid-resident (cooperative launch, tagged L2 mailboxes)"}.get(variant_used),
+                       "ctas_per_stream": cluster_size if variant_used in (2, 3) else None,
                        "l2": "value: device frame pool of %d MiB cycled through (> 126 MiB L2), no frame is cache-resident "
                              "when re-read; e2e: inputs streamed from pinned host memory; e2e_sync: 256 MiB memset "
                              "between steps" % ((run_pool_mib)),
@@ -397,11 +398,11 @@ def gpu_main(args):
                          "mode": "blocking call per step, L2 flushed between steps"},
             "gpu_launches": launches_all,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_nltgv2_cluster" if variant_used == 2 else "k_dual_edges+k_primal_vertices",
+            "roofline": {"bound": "hbm", "kernel": {2: "k_nltgv2_cluster", 3: "k_nltgv2_grid"}.get(variant_used, "k_dual_edges+k_primal_vertices"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_us": 1e3 * solve_ms_per_launch,
-                         "note": "algorithmic = (40E+64V) B/iter x iters x streams (SURVEY 8d); the cluster solver keeps the "
+                         "note": "algorithmic = (40E+64V) B/iter x iters x streams (SURVEY 8d); the persistent solvers keep the "
                                  "graph in shared memory/registers across iterations, so achieved may exceed the HBM peak "
                                  "while DRAM traffic (`traffic`) is ~1/iters of it"},
         }

@@ -71,6 +71,7 @@ struct fb_ctx {
 
   // ---- persistent-cluster solver images (variant 2), rebuilt by fb_graph_set
   struct ClusterPlan* plan = nullptr;
+  struct GridPlan* gplan = nullptr;   // grid-resident solver tables (variant 3)
   struct UpdateState* upd = nullptr;  // fb_update pipeline state (flame_update.cuh)
 
   // ---- frames

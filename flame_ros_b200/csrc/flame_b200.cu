@@ -14,6 +14,7 @@
 #include "epipolar.cuh"
 #include "nltgv2.cuh"
 #include "nltgv2_cluster.cuh"
+#include "nltgv2_grid.cuh"
 #include "raster.cuh"
 #include "frontend.cuh"
 
@@ -91,6 +92,7 @@ static void free_all(fb_ctx* c) {
   cudaFree(c->counters); cudaFree(c->tri); cudaFree(c->nT); cudaFree(c->tri_valid);
   cudaFree(c->owner); cudaFree(c->idmap);
   cluster_plan_free(c);
+  grid_plan_free(c);
   update_free(c);
   if (c->solve_exec) cudaGraphExecDestroy(c->solve_exec);
   for (int k = 0; k < FB_PROF_NUM; ++k)
@@ -211,6 +213,7 @@ extern "C" void fb_destroy(fb_ctx* c) {
 extern "C" int fb_sync(fb_ctx* c) {
   CHECK_CTX(c);
   FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (grid_watchdog_fired(c)) FB_FAIL(c, FB_E_STATE, "grid-resident solver: mailbox exchange timed out (watchdog)");
   return FB_OK;
 }
 
@@ -290,6 +293,8 @@ extern "C" int fb_graph_set(fb_ctx* c, int s, int V, int E, const float* pos,
   FB_CUDA(c, cudaMemcpyAsync(c->nE + s, &c->hE[s], sizeof(int32_t), cudaMemcpyHostToDevice, st));
   int rc = cluster_plan_build(c, s, V, E, eij.data(), row.data(), inc.data());
   if (rc != FB_OK) return rc;
+  rc = grid_plan_set(c, s, V, pos);
+  if (rc != FB_OK) return rc;
   // the staging vectors above are pageable: the runtime has copied them before returning
   FB_CUDA(c, cudaStreamSynchronize(st));
   return FB_OK;
@@ -358,6 +363,7 @@ extern "C" int fb_graph_state_get(fb_ctx* c, int s, float* x, float* w, float* q
   if (q) FB_CUDA(c, cudaMemcpyAsync(q4.data(), c->q4 + eb, sizeof(float4) * E, cudaMemcpyDeviceToHost, st));
   if (xbar) FB_CUDA(c, cudaMemcpyAsync(vb4.data(), c->vbar + vb, sizeof(float4) * V, cudaMemcpyDeviceToHost, st));
   FB_CUDA(c, cudaStreamSynchronize(st));
+  if (grid_watchdog_fired(c)) FB_FAIL(c, FB_E_STATE, "grid-resident solver: mailbox exchange timed out (watchdog)");
   if (w) for (int v = 0; v < V; ++v) { w[2 * v] = w1[v]; w[2 * v + 1] = w2[v]; }
   if (q) for (int e = 0; e < E; ++e) { q[3 * e] = q4[e].x; q[3 * e + 1] = q4[e].y; q[3 * e + 2] = q4[e].z; }
   if (xbar) for (int v = 0; v < V; ++v) { xbar[3 * v] = vb4[v].x; xbar[3 * v + 1] = vb4[v].y; xbar[3 * v + 2] = vb4[v].z; }
@@ -409,9 +415,22 @@ static int solve_streaming(fb_ctx* c, int iters, const fb_nltgv2_params* p, int 
 
 extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, int variant) {
   CHECK_CTX(c);
-  if (!p || iters < 0 || variant < 0 || variant > 2) FB_FAIL(c, FB_E_ARG, "fb_nltgv2_solve: bad argument");
+  if (!p || iters < 0 || variant < 0 || variant > 3) FB_FAIL(c, FB_E_ARG, "fb_nltgv2_solve: bad argument");
   if (iters == 0) return FB_OK;
   int v = variant;
+  if (v == 0 || v == 3) {
+    int nper = 0;
+    size_t smem = 0;
+    if (iters <= FBG_MAX_ITERS) {
+      int rc = grid_prepare(c, -1, &nper, &smem);
+      if (rc) return rc;
+    }
+    if (nper > 0) {
+      c->last_variant = 3;
+      return solve_grid(c, iters, p, nper, smem);
+    }
+    if (v == 3) FB_FAIL(c, FB_E_STATE, "fb_nltgv2_solve: the batch does not fit the grid-resident solver");
+  }
   if (v == 0) v = cluster_plan_ready(c) ? 2 : 1;
   if (v == 2 && !cluster_plan_ready(c))
     FB_FAIL(c, FB_E_STATE, "fb_nltgv2_solve: a graph of this context does not fit the cluster-resident solver");
@@ -434,6 +453,18 @@ static int fb_nltgv2_solve_stream(fb_ctx* c, int s, int iters, const fb_nltgv2_p
   }
   c->last_variant = 1;
   return solve_streaming(c, iters, p, only);
+}
+
+// Context-free, host-only: builds the variant-3 partition tables of one graph for `parts` CTAs and
+// checks the invariants k_nltgv2_grid relies on (see fbg_verify).  Returns 0 when they hold.
+extern "C" int fb_grid_plan_verify(int V, int E, const float* pos, const int32_t* ij, int parts, int32_t* stats) {
+  if (V < 0 || E < 0 || parts < 1 || parts > FBG_MAXP || (V > 0 && !pos) || (E > 0 && !ij)) return FB_E_ARG;
+  for (int e = 0; e < E; ++e)
+    if (ij[2 * e] < 0 || ij[2 * e] >= ij[2 * e + 1] || ij[2 * e + 1] >= V) return FB_E_ARG;
+  std::string why;
+  const int rc = fbg_verify(V, E, pos, ij, parts, stats, why);
+  if (rc) g_create_error = "fb_grid_plan_verify: " + why;
+  return rc;
 }
 
 extern "C" int fb_last_solver_variant(const fb_ctx* c) { return c ? c->last_variant : 0; }

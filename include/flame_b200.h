@@ -134,7 +134,12 @@ int fb_graph_state_get(fb_ctx* ctx, int stream, float* x, float* w, float* q, fl
 int fb_graph_x_get_all(fb_ctx* ctx, float* x_all);
 /* `iters` Chambolle-Pock iterations on every stream's graph (one batched launch sequence).
  * variant: 0 = auto, 1 = streaming (two kernels per iteration, any size),
- *          2 = persistent thread-block-cluster kernel (graph resident in shared memory). */
+ *          2 = persistent thread-block-cluster kernel (graph resident in shared memory, one
+ *              cluster of <= 16 CTAs per stream, DSMEM exchange),
+ *          3 = grid-resident kernel (graphs resident in registers/shared memory of every
+ *              co-resident CTA of the device, cut edges held by both sides, one tagged 128-bit
+ *              mailbox exchange through L2 per iteration; cooperative launch).
+ * auto picks 3 when the batch fits, else 2, else 1.  All variants give bit-identical results. */
 int fb_nltgv2_solve(fb_ctx* ctx, int iters, const fb_nltgv2_params* p, int variant);
 /* nltgv2_total_{smoothness,data}_cost (/root/reference/src/utils.cc:131-136); synchronises. */
 int fb_costs(fb_ctx* ctx, int stream, float data_factor, double* smoothness, double* data);
@@ -306,9 +311,17 @@ int fb_profile_reset(fb_ctx* ctx);
 int fb_profile_get(fb_ctx* ctx, int section, float* total_ms, int64_t* calls, int64_t* launches);
 /* Total kernels launched by this context since creation. */
 int64_t fb_launch_count(const fb_ctx* ctx);
-/* Which solver variant the last fb_nltgv2_solve used (1 or 2). */
+/* Host-only self-check of the variant-3 partitioner (no device, no context): cuts the graph into
+ * `parts` CTAs' worth of tables and verifies the invariants the kernel relies on (every vertex owned
+ * once, every incidence slot written exactly once in CSR order, halo vertices published by their
+ * owners, every edge written back exactly once).  0 = OK, 1 = does not fit this part count, other
+ * > 0 = violated invariant (fb_last_error(NULL) says which), < 0 = bad argument.
+ * stats[8] (optional) = {max own vertices, max edges, max halo, duplicated edges, max slots,
+ * shared-memory bytes, boundary vertices, parts}. */
+int fb_grid_plan_verify(int V, int E, const float* pos, const int32_t* ij, int parts, int32_t* stats);
+/* Which solver variant the last fb_nltgv2_solve used (1, 2 or 3). */
 int fb_last_solver_variant(const fb_ctx* ctx);
-/* CTAs per cluster (= SMs per stream) of the last variant-2 launch. */
+/* CTAs per stream of the last variant-2 (cluster size) or variant-3 (parts per stream) launch. */
 int fb_last_cluster_size(const fb_ctx* ctx);
 
 #ifdef __cplusplus

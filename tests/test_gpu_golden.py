@@ -12,7 +12,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-4
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_golden_nltgv2_small(capi, variant):
     gd = np.load(os.path.join(GOLD, "nltgv2_small.npz"))
     with capi.Context(1, 96, 72, 2, 16, 256, 1024) as ctx:
@@ -31,7 +31,7 @@ def test_golden_nltgv2_small(capi, variant):
         assert np.allclose([s, d], gd["costs_it50"], rtol=1e-6)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_golden_nltgv2_c2(capi, variant):
     gd = np.load(os.path.join(GOLD, "nltgv2_c2.npz"))
     pos, edges, z = gd["pos"], gd["edges"].astype(np.int32), gd["z"]

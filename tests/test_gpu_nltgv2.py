@@ -18,7 +18,7 @@ def linf(a, b):
     return max(float(np.max(np.abs(a[k] - b[k]))) for k in STATE_KEYS if len(a[k]))
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("iters", [1, 10, 50])
 def test_small_graph_parity(capi, oracle, variant, iters):
     g = small_graph()
@@ -32,7 +32,7 @@ def test_small_graph_parity(capi, oracle, variant, iters):
     assert np.array_equal(ref["x"], got["x"]), "expected bit-exact x (same expression order)"
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_c2_graph_parity_50_iters(capi, oracle, variant):
     g = synth.s_graph("C2")
     ref = run_oracle(oracle, g, 50)
@@ -47,14 +47,47 @@ def test_c2_graph_parity_50_iters(capi, oracle, variant):
     assert abs(s_gpu - s_ref) <= 1e-6 * abs(s_ref) and abs(d_gpu - d_ref) <= 1e-6 * abs(d_ref)
 
 
-def test_c4_graph_parity_100_iters_streaming(capi, oracle):
+@pytest.mark.parametrize("variant", [1, 3])
+def test_c4_graph_parity_100_iters(capi, oracle, variant):
+    """C4 (20k vertices) does not fit one cluster: streaming kernels or the grid-resident solver."""
     g = synth.s_graph("C4")
     ref = run_oracle(oracle, g, 100, nthreads=4)
     with capi.Context(1, 1280, 720, 2, 16, 20000, 60000) as ctx:
         gpu_load_graph(ctx, 0, g)
-        ctx.nltgv2_solve(100, variant=1)
+        ctx.nltgv2_solve(100, variant=variant)
+        assert ctx.last_solver_variant() == variant
         got = ctx.graph_state_get(0)
     assert linf(ref, got) < TOL
+    assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS), "expected bit-exact state"
+
+
+@pytest.mark.parametrize("budget", ["7", "40", "75"])
+def test_grid_solver_is_partition_invariant(capi, oracle, budget, monkeypatch):
+    """Variant 3: the result does not depend on how many CTAs share a graph (cut edges are computed
+    on both sides of a cut with bit-identical results)."""
+    monkeypatch.setenv("FB_GRID_CTAS", budget)
+    g = small_graph(40, 30, 320, 240, seed=5)
+    ref = run_oracle(oracle, g, 30)
+    with capi.Context(1, 320, 240, 2, 16, 1200, 3600) as ctx:
+        gpu_load_graph(ctx, 0, g)
+        ctx.nltgv2_solve(30, variant=3)
+        assert ctx.last_solver_variant() == 3
+        got = ctx.graph_state_get(0)
+    assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
+
+
+def test_grid_solver_repeated_launches_and_topology_change(capi, oracle):
+    """Mailbox tags are unique per launch: many back-to-back solves and a re-upload of a different
+    graph into the same context never see a stale point."""
+    ga, gb = small_graph(24, 18, 192, 144, seed=11), small_graph(20, 20, 192, 144, seed=12)
+    with capi.Context(1, 192, 144, 2, 16, 600, 1800) as ctx:
+        for g in (ga, gb, ga):
+            ref = run_oracle(oracle, g, 12)
+            gpu_load_graph(ctx, 0, g)
+            for _ in range(6):
+                ctx.nltgv2_solve(2, variant=3)
+            got = ctx.graph_state_get(0)
+            assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
 
 
 def test_split_solve_equals_single_solve(capi):
@@ -85,7 +118,7 @@ def test_warm_start_roundtrip(capi, oracle):
     assert linf(ref, got) < TOL
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_batched_streams_block_diagonal(capi, oracle, variant):
     """Different graphs in different streams of one context: one launch, independent results."""
     graphs = [small_graph(10 + 2 * s, 8 + s, 96, 72, seed=20 + s) for s in range(3)]
