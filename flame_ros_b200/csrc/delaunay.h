@@ -14,6 +14,7 @@
 // the first occurrence and reported through `dup_of`.
 #pragma once
 
+#include <math.h>
 #include <stdint.h>
 
 #include <algorithm>
@@ -38,18 +39,27 @@ struct Triangulator {
   }
   int64_t orientv(int a, int b, int c) const { return orient(px[a], py[a], px[b], py[b], px[c], py[c]); }
 
-  // > 0 iff p lies strictly inside the circumcircle of ccw triangle (a,b,c)
+  // > 0 iff p lies strictly inside the circumcircle of ccw triangle (a,b,c).  Lattice coordinates
+  // are < 2^24, so differences and the 2x2 minors are exact in double; only the final three-term
+  // sum rounds.  A static error bound decides the sign; inside the bound the determinant is
+  // re-evaluated exactly in 128-bit integers (co-circular grid detections land there).
   int incircle_sign(int a, int b, int c, int p) const {
     const int64_t adx = px[a] - px[p], ady = py[a] - py[p];
     const int64_t bdx = px[b] - px[p], bdy = py[b] - py[p];
     const int64_t cdx = px[c] - px[p], cdy = py[c] - py[p];
-    const i128 al = (i128)(adx * adx + ady * ady);
-    const i128 bl = (i128)(bdx * bdx + bdy * bdy);
-    const i128 cl = (i128)(cdx * cdx + cdy * cdy);
-    const i128 det = al * (i128)(bdx * cdy - bdy * cdx) + bl * (i128)(cdx * ady - cdy * adx) +
-                     cl * (i128)(adx * bdy - ady * bdx);
+    const int64_t al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
+    const int64_t ma = bdx * cdy - bdy * cdx, mb = cdx * ady - cdy * adx, mc = adx * bdy - ady * bdx;
+    if (exact_double) {
+      const double ta_ = (double)al * (double)ma, tb_ = (double)bl * (double)mb, tc_ = (double)cl * (double)mc;
+      const double det = ta_ + tb_ + tc_;
+      const double bound = 8.9e-16 * (fabs(ta_) + fabs(tb_) + fabs(tc_));  // 8 ulp of the magnitude sum
+      if (det > bound) return 1;
+      if (det < -bound) return -1;
+    }
+    const i128 det = (i128)al * (i128)ma + (i128)bl * (i128)mb + (i128)cl * (i128)mc;
     return det > 0 ? 1 : (det < 0 ? -1 : 0);
   }
+  bool exact_double = false;  // set by run(): all |coordinates| < 2^24 => al, ma, .. exact in double
 
   // Does the (possibly ghost) triangle t conflict with point p (p inside its circumdisk)?
   bool conflicts(int t, int p) const {
@@ -238,6 +248,7 @@ struct Triangulator {
     }
     tv.clear(); ta.clear(); dead.clear(); free_list.clear(); mark.clear(); vslot.clear();
     if (n < 3) return false;
+    tv.reserve(3 * (2 * (size_t)n + 16)); ta.reserve(3 * (2 * (size_t)n + 16)); dead.reserve(2 * (size_t)n + 16);
     // insertion order: snake over a coarse grid for walk locality (deterministic)
     std::vector<int> order(n);
     for (int i = 0; i < n; ++i) order[i] = i;
@@ -246,6 +257,7 @@ struct Triangulator {
       xmin = std::min(xmin, px[i]); xmax = std::max(xmax, px[i]);
       ymin = std::min(ymin, py[i]); ymax = std::max(ymax, py[i]);
     }
+    exact_double = (xmax - xmin) < (1 << 24) && (ymax - ymin) < (1 << 24);
     int g = 1;
     while (g * g * 4 < n) ++g;
     const int64_t cw = std::max<int64_t>(1, (xmax - xmin) / g + 1), ch = std::max<int64_t>(1, (ymax - ymin) / g + 1);
@@ -316,27 +328,43 @@ struct Triangulator {
         }
       }
     }
+    // triangles, and every edge once: from the lower-numbered of its two triangles (hull edges from
+    // their only real triangle); then a counting sort by the smaller endpoint and a short insertion
+    // sort inside each bucket (degree ~6) give the canonical (i<j, sorted by (i,j)) list in O(E)
+    std::vector<int> ea, eb, cnt(n + 1, 0);
+    ea.reserve(3 * (size_t)n);
+    eb.reserve(3 * (size_t)n);
     for (int u = 0; u < (int)dead.size(); ++u) {
       if (dead[u] || tv[3 * u + 2] == GHOST) continue;
       tris.push_back(tv[3 * u]);
       tris.push_back(tv[3 * u + 1]);
       tris.push_back(tv[3 * u + 2]);
-    }
-    // canonical edge list
-    std::vector<uint64_t> ek;
-    ek.reserve(tris.size());
-    for (size_t k = 0; k < tris.size(); k += 3)
       for (int m = 0; m < 3; ++m) {
-        int a = tris[k + m], b = tris[k + (m + 1) % 3];
+        const int nb = ta[3 * u + m];
+        if (nb >= 0 && tv[3 * nb + 2] != GHOST && nb < u) continue;
+        int a = tv[3 * u + m], b = tv[3 * u + (m == 2 ? 0 : m + 1)];
         if (a > b) std::swap(a, b);
-        ek.push_back(((uint64_t)a << 32) | (uint32_t)b);
+        ea.push_back(a);
+        eb.push_back(b);
+        cnt[a + 1]++;
       }
-    std::sort(ek.begin(), ek.end());
-    ek.erase(std::unique(ek.begin(), ek.end()), ek.end());
-    edges.reserve(2 * ek.size());
-    for (uint64_t e : ek) {
-      edges.push_back((int)(e >> 32));
-      edges.push_back((int)(e & 0xffffffffu));
+    }
+    for (int i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
+    edges.assign(2 * ea.size(), 0);
+    {
+      std::vector<int> fill(cnt.begin(), cnt.begin() + n);
+      for (size_t k = 0; k < ea.size(); ++k) {
+        const int a = ea[k], b = eb[k];
+        int pos = fill[a]++;
+        while (pos > cnt[a] && edges[2 * (pos - 1) + 1] > b) {  // insertion sort within the bucket
+          edges[2 * pos + 1] = edges[2 * (pos - 1) + 1];
+          --pos;
+        }
+        edges[2 * pos] = a;
+        edges[2 * pos + 1] = b;
+      }
+      for (int a = 0; a < n; ++a)
+        for (int k = cnt[a]; k < cnt[a + 1]; ++k) edges[2 * k] = a;
     }
     return true;
   }
