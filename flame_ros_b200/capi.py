@@ -27,7 +27,7 @@ SYMBOLS = [
     "fb_features_set", "fb_features_get", "fb_features_reinit", "fb_idepth_update", "fb_idepth_counters",
     "fb_project_features", "fb_graph_bind_features", "fb_graph_data_from_features", "fb_mesh_set",
     "fb_interpolate", "fb_profile_enable", "fb_profile_reset", "fb_profile_get", "fb_launch_count",
-    "fb_last_solver_variant", "fb_last_cluster_size", "fb_grid_plan_verify", "fb_delaunay", "fb_hotpath_step", "fb_results_wait", "fb_pipeline_join", "fb_default_update_params",
+    "fb_last_solver_variant", "fb_last_cluster_size", "fb_last_solver_transport", "fb_grid_plan_verify", "fb_delaunay", "fb_hotpath_step", "fb_results_wait", "fb_pipeline_join", "fb_default_update_params",
     "fb_set_update_params", "fb_update", "fb_get_mesh_sizes", "fb_get_mesh", "fb_get_idepthmap",
     "fb_get_raw_idepths", "fb_get_stat", "fb_update_poseframe_poses", "fb_prune_poseframes",
     "fb_frame_gradient", "fb_frame_pyr_down", "fb_detect", "fb_get_feature_pool",
@@ -134,7 +134,7 @@ def load_library(build_if_missing=True):
         "fb_graph_bind_features": [P, I, P], "fb_graph_data_from_features": [P, I],
         "fb_mesh_set": [P, I, I, P], "fb_interpolate": [P, I, P, P, P],
         "fb_profile_enable": [P, I], "fb_profile_reset": [P], "fb_profile_get": [P, I, P, P, P],
-        "fb_last_solver_variant": [P], "fb_last_cluster_size": [P], "fb_grid_plan_verify": [I, I, P, P, I, P], "fb_version": [], "fb_delaunay": [I, P, P, P, P, P], "fb_hotpath_step": [P, P], "fb_results_wait": [P, I], "fb_pipeline_join": [P],
+        "fb_last_solver_variant": [P], "fb_last_cluster_size": [P], "fb_last_solver_transport": [P], "fb_grid_plan_verify": [I, I, P, P, I, I, P], "fb_version": [], "fb_delaunay": [I, P, P, P, P, P], "fb_hotpath_step": [P, P], "fb_results_wait": [P, I], "fb_pipeline_join": [P],
         "fb_set_update_params": [P, P], "fb_update": [P, I, C.c_double, I, P, P, I, I],
         "fb_get_mesh_sizes": [P, I, P, P, P], "fb_get_mesh": [P, I, P, P, P, P, P, P, P],
         "fb_get_idepthmap": [P, I, P, P], "fb_get_raw_idepths": [P, I, P, P, P, P],
@@ -202,14 +202,14 @@ def delaunay(pts):
     return tris[:nt.value].copy(), edges[:ne.value].copy()
 
 
-def grid_plan_verify(pos, edges, parts):
+def grid_plan_verify(pos, edges, parts, cluster=False):
     """Host-only self-check of the grid-resident solver's partition tables (no GPU needed).
     Returns (rc, stats dict); rc 0 = invariants hold, 1 = does not fit `parts` CTAs."""
     lib = load_library()
     pos = _f32(pos)
     edges = np.ascontiguousarray(edges, np.int32).reshape(-1, 2)
     stats = np.zeros(8, np.int32)
-    rc = lib.fb_grid_plan_verify(pos.shape[0], edges.shape[0], _ptr(pos), _ptr(edges), int(parts), _ptr(stats))
+    rc = lib.fb_grid_plan_verify(pos.shape[0], edges.shape[0], _ptr(pos), _ptr(edges), int(parts), int(bool(cluster)), _ptr(stats))
     if rc < 0:
         raise FlameError("fb_grid_plan_verify: bad argument")
     if rc > 1:
@@ -326,6 +326,10 @@ class Context:
 
     def last_solver_variant(self):
         return self._lib.fb_last_solver_variant(self._h)
+
+    def last_solver_transport(self):
+        """Variant 3: 1 = cluster (DSMEM), 2 = L2 mailboxes."""
+        return self._lib.fb_last_solver_transport(self._h)
 
     def last_cluster_size(self):
         return self._lib.fb_last_cluster_size(self._h)

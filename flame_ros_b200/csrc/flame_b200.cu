@@ -421,8 +421,8 @@ extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, 
   if (v == 0 || v == 3) {
     int nper = 0;
     size_t smem = 0;
-    if (iters <= FBG_MAX_ITERS) {
-      int rc = grid_prepare(c, -1, &nper, &smem);
+    {
+      int rc = grid_prepare(c, iters, -1, &nper, &smem);
       if (rc) return rc;
     }
     if (nper > 0) {
@@ -457,18 +457,21 @@ static int fb_nltgv2_solve_stream(fb_ctx* c, int s, int iters, const fb_nltgv2_p
 
 // Context-free, host-only: builds the variant-3 partition tables of one graph for `parts` CTAs and
 // checks the invariants k_nltgv2_grid relies on (see fbg_verify).  Returns 0 when they hold.
-extern "C" int fb_grid_plan_verify(int V, int E, const float* pos, const int32_t* ij, int parts, int32_t* stats) {
-  if (V < 0 || E < 0 || parts < 1 || parts > FBG_MAXP || (V > 0 && !pos) || (E > 0 && !ij)) return FB_E_ARG;
+extern "C" int fb_grid_plan_verify(int V, int E, const float* pos, const int32_t* ij, int parts, int cluster,
+                                   int32_t* stats) {
+  if (V < 0 || E < 0 || parts < 1 || parts > (cluster ? FBG_MAXC : FBG_MAXP) || (V > 0 && !pos) || (E > 0 && !ij)) return FB_E_ARG;
   for (int e = 0; e < E; ++e)
     if (ij[2 * e] < 0 || ij[2 * e] >= ij[2 * e + 1] || ij[2 * e + 1] >= V) return FB_E_ARG;
   std::string why;
-  const int rc = fbg_verify(V, E, pos, ij, parts, stats, why);
+  const int rc = fbg_verify(V, E, pos, ij, parts, cluster ? FBG_THREADS_CL : FBG_THREADS_L2,
+                            cluster ? FBG_SMEM_LIMIT_CL : FBG_SMEM_LIMIT_L2, stats, why);
   if (rc) g_create_error = "fb_grid_plan_verify: " + why;
   return rc;
 }
 
 extern "C" int fb_last_solver_variant(const fb_ctx* c) { return c ? c->last_variant : 0; }
 extern "C" int fb_last_cluster_size(const fb_ctx* c) { return c ? c->last_cluster : 0; }
+extern "C" int fb_last_solver_transport(const fb_ctx* c) { return c ? c->last_transport : 0; }
 
 extern "C" int fb_costs(fb_ctx* c, int s, float data_factor, double* smooth, double* data) {
   CHECK_CTX(c);

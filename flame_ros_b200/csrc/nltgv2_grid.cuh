@@ -1,24 +1,30 @@
-// nltgv2_grid.cuh -- grid-resident NLTGV2-L1 solver (variant 3).
+// nltgv2_grid.cuh -- resident NLTGV2-L1 solver with ONE halo exchange per iteration (variant 3).
 //
-// The whole batch of graphs stays on chip for ALL iterations of a solve, spread over as many CTAs as
-// the device keeps co-resident (cooperative launch, up to two CTAs per SM, no cluster-size or GPC
-// limit), so graphs of any practical size run persistently (C4: 20k vertices over 148+ CTAs):
+// The batch of graphs stays on chip for ALL iterations of a solve:
 //   * each stream's vertices are cut into `nper` compact parts by recursive coordinate bisection
 //     of the pixel positions (balanced by degree); a part is owned by one CTA;
 //   * a CTA holds EVERY edge incident to its vertices -- cut edges are held (and computed) by both
 //     sides.  Both copies see bit-identical inputs and run the same instruction sequence, so they
 //     stay bit-identical; only the copy in the source vertex's CTA is written back.  All K^T q
 //     contributions a vertex needs are therefore produced inside its own CTA: the only thing that
-//     crosses CTAs is the extragradient point of boundary vertices, ONCE per iteration;
-//   * that exchange is a tagged 128-bit mailbox in L2: the owner publishes (xb, w1b, w2b, tag)
-//     with one st.relaxed.gpu.b128, readers poll the same 16 bytes with ld.relaxed.gpu.b128 until
-//     the tag of the iteration shows up.  Data and flag travel in one single-copy-atomic access:
-//     no fence, no flag round trip, no cluster barrier, no grid barrier.  Mailboxes are double
-//     buffered by iteration parity (a writer can be at most one iteration ahead of a reader);
+//     crosses CTAs is the extragradient point of boundary vertices, ONCE per iteration
+//     (variant 2 exchanges twice: contributions one way, refreshed halo points back);
 //   * per-edge state (q, alpha, beta, dx, dy) and per-vertex state (x, w, z, threshold) live in
-//     registers for the whole solve; shared memory holds the extragradient points (own + halo) and
-//     one 16 B slot per vertex-edge incidence in the vertex's CSR order, so the summation order
-//     (ascending edge id) and hence every bit of the result equals the streaming kernels'.
+//     registers for the whole solve; shared memory holds the extragradient points (own + halo,
+//     double-banked by iteration parity) and one 16 B slot per vertex-edge incidence in the
+//     vertex's CSR order, so the summation order (ascending edge id) and hence every bit of the
+//     result equals the streaming kernels'.
+// Two transports for the halo, same kernel body (template parameter):
+//   CLUSTER  one thread-block cluster (<= 16 CTAs x 512 threads) per stream: the owner thread pushes
+//            the new point straight into the consumers' shared memory with
+//            st.async...mbarrier::complete_tx::bytes; a CTA waits on its own mbarrier (one per
+//            parity) for exactly the bytes it consumes.  ~215 cycles per hand-over.
+//   L2       any number of co-resident CTAs (cooperative launch, 2 x 256 threads per SM) for
+//            graphs that need more than 16 CTAs (C4: 20k vertices): the owner publishes
+//            (xb, w1b, w2b, tag) with one st.relaxed.gpu.b128, readers poll the same 16 bytes with
+//            ld.relaxed.gpu.b128 until the tag of the iteration shows up.  Data and flag travel in
+//            one single-copy-atomic access: no fence, no flag round trip, no grid barrier.
+//            Measured floor ~1700 cycles per lockstep iteration (profiles/r1_mailbox_latency.md).
 // HBM is touched once per solve (state in, state out).
 #pragma once
 
@@ -29,40 +35,55 @@
 #include "nltgv2.cuh"
 #include "nltgv2_cluster.cuh"
 
-#define FBG_THREADS 256
-#define FBG_EPT 4            // edges per thread (register resident)
-#define FBG_VPT 2            // vertices per thread
-#define FBG_MAXP 512         // parts per stream (table stride)
-#define FBG_MAX_ITERS 16383  // tag space per launch
-#define FBG_SMEM_LIMIT (100 * 1024)
+#define FBG_EPT 4              // edges per thread (register resident)
+#define FBG_VPT 2              // vertices per thread
+#define FBG_THREADS_L2 256     // L2 transport: two CTAs per SM
+#define FBG_THREADS_CL 512     // cluster transport: one CTA per SM
+#define FBG_MAXP 512           // parts per stream (table stride)
+#define FBG_MAXC 16            // largest cluster
+#define FBG_MAX_ITERS 16383    // tag space per launch (L2 transport)
+#define FBG_SMEM_LIMIT_L2 (100 * 1024)
+#define FBG_SMEM_LIMIT_CL (200 * 1024)
 #define FBG_SPIN_LIMIT (1u << 21)  // mailbox polls before a reader gives up (watchdog, ~0.3 s)
 
 struct GridPlan {
-  int nper = 0;              // parts per stream the device tables are built for
   int2* eplan = nullptr;     // [S*2*maxE] {bi | bj<<16, si | sj<<16}: s_bar / s_slot entry indices
   int32_t* eid = nullptr;    // [S*2*maxE] edge id, bit 31 set on the copy that is NOT written back
-  int4* vplan = nullptr;     // [S*maxV] {vertex id, slot begin, slot end, 1 = boundary (published)}
+  int4* vplan = nullptr;     // [S*maxV] {vertex id, slot begin, slot end, push begin | push end << 16}
   int32_t* hplan = nullptr;  // [S*2*maxE] halo lists: stream-local vertex ids
-  int4* cinfo = nullptr;     // [S*FBG_MAXP*2] {vBeg, nOwn, eBeg, nEdge}, {hBeg, nHalo, nSlot, 0}
-  float4* pub = nullptr;     // [2][S*maxV] tagged mailboxes (parity-major)
+  int2* pplan = nullptr;     // [S*2*maxE] push lists: {consumer part, entry index in its s_bar}
+  int4* cinfo = nullptr;     // [S*FBG_MAXP*3] {vBeg, nOwn, eBeg, nEdge}, {hBeg, nHalo, nSlot, 0}, {pBeg, nPush, 0, 0}
+  float4* pub = nullptr;     // [2][S*maxV] tagged mailboxes (parity-major), L2 transport
   int* err = nullptr;        // mapped host flag: set by the watchdog
   uint32_t seq = 0;          // launch counter -> tag base
-  int max_blocks = -1;       // co-resident CTAs of k_nltgv2_grid on this device
-  size_t smem_set = 0;
-  int budget_env = 0;        // FB_GRID_CTAS: total CTA budget override
-  int sms = 0;
-  int capBar = 0;            // layout of the last prepared launch
+  int max_blocks = -1;       // co-resident CTAs of the L2-transport kernel on this device
+  int max_clusters[FBG_MAXC + 1];  // co-resident clusters per cluster size (-1 = not queried)
+  size_t smem_set[2] = {0, 0};
+  bool nonportable_set = false;
+  int budget_env = 0;        // FB_GRID_CTAS: CTA budget of the L2 transport
+  int cluster_env = 0;       // FB_GRID_CLUSTER: forced cluster size
+  int mode_env = 0;          // FB_GRID_MODE: 1 = cluster only, 2 = L2 only
+  // layout of the last prepared launch
+  int nper = 0, capBar = 0, capSlot = 0, capPush = 0;
+  bool cluster = false;
+  // decision cache: valid while no topology changed (version) and the same streams are solved
+  uint64_t version = 1, dec_version = 0;
+  int dec_only = -2, dec_nper = 0;
+  bool dec_cluster = false;
+  size_t dec_smem = 0;
   struct Topo {
     std::vector<float2> pos;
     bool dirty = true;
-    int planned = 0;   // nper the cached tables below were built for (0 = none)
+    int planned = 0;          // nper the cached tables below were built for (0 = none)
+    int planned_threads = 0;  // capacity class they were checked against
     bool feasible = false;
-    int capBar = 0, capSlot = 0;
-    std::vector<int2> eplan;
+    int capBar = 0, capSlot = 0, capPush = 0;
+    std::vector<int2> eplan, pplan;
     std::vector<int32_t> eid, hplan;
     std::vector<int4> vplan, cinfo;
   };
   std::vector<Topo> topo;
+  GridPlan() { std::fill(max_clusters, max_clusters + FBG_MAXC + 1, -1); }
 };
 
 // ---------------------------------------------------------------------------------- device side
@@ -107,144 +128,209 @@ struct GridArgs {
   const int32_t* eid;
   const int4* vplan;
   const int32_t* hplan;
+  const int2* pplan;
   const int4* cinfo;
   float4* pub;
   int* err;
   int nper;
-  int capBar;      // s_slot starts capBar records after s_bar
+  int capBar;      // records per s_bar bank
+  int capSlot;     // slot records (+1 dummy)
   size_t pstride;  // S*maxV: distance between the two mailbox banks
 };
 
-__global__ void __launch_bounds__(FBG_THREADS, 2)
+struct FbgEdges {  // register-resident edge rows of one thread
+  float q1[FBG_EPT], q2[FBG_EPT], q3[FBG_EPT], a[FBG_EPT], b[FBG_EPT], dx[FBG_EPT], dy[FBG_EPT];
+  uint32_t bar[FBG_EPT], slot[FBG_EPT];  // packed 16-bit entry indices: (bi, bj) and (si, sj)
+  int id[FBG_EPT];
+};
+struct FbgVerts {  // register-resident vertex rows of one thread
+  float x[FBG_VPT], w1[FBG_VPT], w2[FBG_VPT], z[FBG_VPT], th[FBG_VPT];
+  int s0[FBG_VPT], s1[FBG_VPT], id[FBG_VPT];  // id: vertex id, bit 30 = boundary; -1 = none
+  uint32_t push[FBG_VPT];                     // push list range begin | end << 16 (cluster transport)
+};
+
+// Dual half-step over the first R edge rows of this thread (R is warp-uniform: rows whose 32 lanes
+// are all idle are not executed at all; inside an active row idle lanes compute on zero weights and
+// store nothing, so the R rows form independent branch-free instruction streams).
+template <int R>
+__device__ __forceinline__ void fbg_dual(FbgEdges& E, uint32_t bar_rd, uint32_t slot_base, float sigma) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const float4 bi = fbc_lds(bar_rd + ((E.bar[k] & 0xffffu) << 4));
+    const float4 bj = fbc_lds(bar_rd + ((E.bar[k] >> 16) << 4));
+    float t = bi.x - bj.x;
+    t = fmaf(-E.dx[k], bi.y, t);
+    t = fmaf(-E.dy[k], bi.z, t);
+    const float k1 = E.a[k] * t;
+    const float k2 = E.b[k] * (bi.y - bj.y);
+    const float k3 = E.b[k] * (bi.z - bj.z);
+    E.q1[k] = fb_clamp1(fmaf(sigma, k1, E.q1[k]));
+    E.q2[k] = fb_clamp1(fmaf(sigma, k2, E.q2[k]));
+    E.q3[k] = fb_clamp1(fmaf(sigma, k3, E.q3[k]));
+    const float a1 = E.a[k] * E.q1[k];
+    const float4 cs = make_float4(a1, fmaf(E.b[k], E.q2[k], -(E.dx[k] * a1)),
+                                  fmaf(E.b[k], E.q3[k], -(E.dy[k] * a1)), 0.f);
+    const float4 ct = make_float4(-a1, -(E.b[k] * E.q2[k]), -(E.b[k] * E.q3[k]), 0.f);
+    if (E.id[k] != -1) {  // the endpoint owned by another CTA maps to the dummy slot
+      fbc_sts(slot_base + ((E.slot[k] & 0xffffu) << 4), cs);
+      fbc_sts(slot_base + ((E.slot[k] >> 16) << 4), ct);
+    }
+  }
+}
+
+template <int THREADS, int MINB, bool CLUSTER>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float theta, float xmin,
               float xmax, uint32_t tag0) {
   extern __shared__ __align__(16) uint8_t fbg_smem[];
-  float4* s_bar = reinterpret_cast<float4*>(fbg_smem);  // [nOwn own | nHalo halo]
-  float4* s_slot = s_bar + a.capBar;                    // [nSlot + 1 dummy]
+  float4* s_bar = reinterpret_cast<float4*>(fbg_smem);  // 2 banks x [nOwn own | nHalo halo]
+  float4* s_slot = s_bar + 2 * a.capBar;                // [nSlot + 1 dummy]
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_slot + a.capSlot + 1);  // [2] one per parity
+  uint2* s_push = reinterpret_cast<uint2*>(s_mbar + 2);  // {remote s_bar address (bank 0), remote mbarrier 0}
   const GraphView& g = a.g;
   const int tid = threadIdx.x;
   const int s = (g.only >= 0) ? g.only : (int)blockIdx.x / a.nper;
-  const int r = (int)blockIdx.x % a.nper;
-  if (g.nV[s] == 0) return;
-  const int4 c0 = a.cinfo[((size_t)s * FBG_MAXP + r) * 2], c1 = a.cinfo[((size_t)s * FBG_MAXP + r) * 2 + 1];
-  const int nOwn = c0.y, nEdge = c0.w, nHalo = c1.y;
-  if (nOwn == 0) return;  // an empty part owns nothing and feeds nobody
+  const int r = CLUSTER ? (int)fbc_cluster_ctarank() : (int)blockIdx.x % a.nper;
+  if (g.nV[s] == 0) return;  // uniform over the stream's CTAs
+  const int4* ci = a.cinfo + ((size_t)s * FBG_MAXP + r) * 3;
+  const int4 c0 = ci[0], c1 = ci[1], c2 = ci[2];
+  const int nOwn = c0.y, nEdge = c0.w, nHalo = c1.y, nPush = c2.y;
+  if (nOwn == 0) {  // an empty part owns nothing and feeds nobody
+    if (CLUSTER) {
+      fbc_cluster_sync();
+      fbc_cluster_sync();
+    }
+    return;
+  }
   const size_t vb = (size_t)s * g.maxV, eb = (size_t)s * g.maxE;
   const int2* epl = a.eplan + 2 * eb + c0.z;
   const int32_t* eidl = a.eid + 2 * eb + c0.z;
   const int4* vpl = a.vplan + vb + c0.x;
   const int32_t* hl = a.hplan + 2 * eb + c1.x;
-  const size_t pstride = a.pstride;  // second mailbox bank (odd iterations)
   float4* pub0 = a.pub + vb;
+  const uint32_t bar_base = fbc_smem_u32(s_bar), slot_base = fbc_smem_u32(s_slot);
+  const uint32_t bank_bytes = 16u * (uint32_t)a.capBar;
+  const uint32_t mb0 = fbc_smem_u32(s_mbar);
+  const uint32_t haloBytes = 16u * (uint32_t)nHalo;
 
   // ---- register-resident per-edge and per-vertex state ----------------------------------------
-  float q1[FBG_EPT], q2[FBG_EPT], q3[FBG_EPT], ea[FBG_EPT], ebt[FBG_EPT], edx[FBG_EPT], edy[FBG_EPT];
-  uint32_t e_b[FBG_EPT], e_s[FBG_EPT];  // packed 16-bit entry indices: (bi, bj) and (si, sj)
-  int e_id[FBG_EPT];
+  FbgEdges E;
 #pragma unroll
   for (int k = 0; k < FBG_EPT; ++k) {
-    const int idx = tid + k * FBG_THREADS;
-    e_id[k] = -1;
-    // idle lanes run the same arithmetic on zero weights and store nothing (branch-free ILP)
-    q1[k] = q2[k] = q3[k] = ea[k] = ebt[k] = edx[k] = edy[k] = 0.f;
-    e_b[k] = 0u;
-    e_s[k] = (uint32_t)c1.z | ((uint32_t)c1.z << 16);
+    const int idx = tid + k * THREADS;
+    E.id[k] = -1;
+    E.q1[k] = E.q2[k] = E.q3[k] = E.a[k] = E.b[k] = E.dx[k] = E.dy[k] = 0.f;
+    E.bar[k] = 0u;
+    E.slot[k] = (uint32_t)c1.z | ((uint32_t)c1.z << 16);
     if (idx < nEdge) {
       const int2 pl = epl[idx];
       const int id = eidl[idx];
-      e_id[k] = id;
+      E.id[k] = id;
       const float4 c = g.ec[eb + (id & 0x7fffffff)];
       const float4 q = g.q4[eb + (id & 0x7fffffff)];
-      ea[k] = c.x; ebt[k] = c.y; edx[k] = c.z; edy[k] = c.w;
-      q1[k] = q.x; q2[k] = q.y; q3[k] = q.z;
-      e_b[k] = (uint32_t)pl.x;
-      e_s[k] = (uint32_t)pl.y;
+      E.a[k] = c.x; E.b[k] = c.y; E.dx[k] = c.z; E.dy[k] = c.w;
+      E.q1[k] = q.x; E.q2[k] = q.y; E.q3[k] = q.z;
+      E.bar[k] = (uint32_t)pl.x;
+      E.slot[k] = (uint32_t)pl.y;
     }
   }
-  float vx[FBG_VPT], vw1[FBG_VPT], vw2[FBG_VPT], vz[FBG_VPT], vth[FBG_VPT];
-  int vs0[FBG_VPT], vs1[FBG_VPT], v_id[FBG_VPT];  // v_id: vertex id, bit 30 = boundary; -1 = none
+  FbgVerts Vt;
 #pragma unroll
   for (int k = 0; k < FBG_VPT; ++k) {
-    const int idx = tid + k * FBG_THREADS;
-    vx[k] = vw1[k] = vw2[k] = vz[k] = vth[k] = 0.f;
-    vs0[k] = 0;
-    vs1[k] = 0;
-    v_id[k] = -1;
+    const int idx = tid + k * THREADS;
+    Vt.x[k] = Vt.w1[k] = Vt.w2[k] = Vt.z[k] = Vt.th[k] = 0.f;
+    Vt.s0[k] = Vt.s1[k] = 0;
+    Vt.id[k] = -1;
+    Vt.push[k] = 0u;
     if (idx < nOwn) {
       const int4 pt = vpl[idx];
       const int v = pt.x;
-      v_id[k] = v | (pt.w ? 0x40000000 : 0);
-      vx[k] = g.x[vb + v]; vw1[k] = g.w1[vb + v]; vw2[k] = g.w2[vb + v];
-      vz[k] = g.z[vb + v];
-      vth[k] = tl * g.wt[vb + v];
-      vs0[k] = pt.y;
-      vs1[k] = pt.z;
-      s_bar[idx] = g.vbar[vb + v];
+      Vt.push[k] = (uint32_t)pt.w;
+      Vt.id[k] = v | (((uint32_t)pt.w >> 16) != ((uint32_t)pt.w & 0xffffu) ? 0x40000000 : 0);
+      Vt.x[k] = g.x[vb + v]; Vt.w1[k] = g.w1[vb + v]; Vt.w2[k] = g.w2[vb + v];
+      Vt.z[k] = g.z[vb + v];
+      Vt.th[k] = tl * g.wt[vb + v];
+      Vt.s0[k] = pt.y;
+      Vt.s1[k] = pt.z;
+      s_bar[idx] = g.vbar[vb + v];  // bank 0: the points iteration 0 reads
     }
   }
-  // halo: vertex ids of the first two entries per thread stay in registers; the first value comes
-  // straight from global memory (written by earlier kernels of the stream)
+  // halo: the first value comes straight from global memory (written by earlier kernels of the
+  // stream); L2 transport keeps the vertex ids of a thread's first two entries in registers
   int hv0 = -1, hv1 = -1;
-  for (int h = tid; h < nHalo; h += FBG_THREADS) {
+  for (int h = tid; h < nHalo; h += THREADS) {
     const int hv = hl[h];
     if (h == tid) hv0 = hv;
-    else if (h == tid + FBG_THREADS) hv1 = hv;
+    else if (h == tid + THREADS) hv1 = hv;
     s_bar[nOwn + h] = g.vbar[vb + hv];
   }
+  if (CLUSTER) {
+    if (tid == 0) {
+      fbc_mbar_init(mb0, 1);
+      fbc_mbar_init(mb0 + 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      // points of iteration it-1 land in bank it&1 and complete mbarrier it&1
+      if (nHalo && iters > 1) fbc_mbar_expect(mb0 + 8, haloBytes);
+      if (nHalo && iters > 2) fbc_mbar_expect(mb0, haloBytes);
+    }
+    const int2* ppl = a.pplan + 2 * eb + c2.x;
+    for (int i = tid; i < nPush; i += THREADS) {
+      const int2 e = ppl[i];
+      s_push[i] = make_uint2(fbc_mapa(bar_base + 16u * (uint32_t)e.y, (uint32_t)e.x), fbc_mapa(mb0, (uint32_t)e.x));
+    }
+    __syncthreads();
+    fbc_cluster_sync();  // every CTA's barriers are initialised before any remote store can target them
+  }
   bool dead = false;
+  // rows of this warp that hold at least one edge / vertex (warp-uniform)
+  const int wbase = tid & ~31;
+  const int rowsE = max(0, min(FBG_EPT, (nEdge - wbase + THREADS - 1) / THREADS));
+  const int rowsV = max(0, min(FBG_VPT, (nOwn - wbase + THREADS - 1) / THREADS));
 
   for (int it = 0; it < iters; ++it) {
     const bool more = it + 1 < iters;
-    // ---- halo refresh: poll the tagged mailboxes of iteration it-1 ---------------------------
-    if (it > 0 && hv0 >= 0) {
-      const uint32_t tag = tag0 + (uint32_t)(it - 1);
-      const float4* pb = pub0 + (size_t)((it - 1) & 1) * pstride;
-      s_bar[nOwn + tid] = fbg_poll(pb + hv0, tag, a.err, dead);
-      if (hv1 >= 0) {
-        s_bar[nOwn + tid + FBG_THREADS] = fbg_poll(pb + hv1, tag, a.err, dead);
-        for (int h = tid + 2 * FBG_THREADS; h < nHalo; h += FBG_THREADS)
-          s_bar[nOwn + h] = fbg_poll(pb + hl[h], tag, a.err, dead);
+    const uint32_t rd_off = (it & 1) ? bank_bytes : 0u, wr_off = bank_bytes - rd_off;
+    // ---- halo of iteration it-1 -----------------------------------------------------------------
+    if (it > 0) {
+      if (CLUSTER) {
+        if (nHalo) fbc_mbar_wait(mb0 + 8u * (uint32_t)(it & 1), (uint32_t)(((it + 1) >> 1) - 1) & 1u);
+      } else if (hv0 >= 0) {
+        const uint32_t tag = tag0 + (uint32_t)(it - 1);
+        const float4* pb = pub0 + (size_t)((it - 1) & 1) * a.pstride;
+        float4* hb = s_bar + ((it & 1) ? a.capBar : 0) + nOwn;
+        hb[tid] = fbg_poll(pb + hv0, tag, a.err, dead);
+        if (hv1 >= 0) {
+          hb[tid + THREADS] = fbg_poll(pb + hv1, tag, a.err, dead);
+          for (int h = tid + 2 * THREADS; h < nHalo; h += THREADS) hb[h] = fbg_poll(pb + hl[h], tag, a.err, dead);
+        }
       }
     }
     __syncthreads();  // own points (primal of it-1) and halo points visible to the edge threads
+    // every thread is past the wait: the barrier of this parity is re-armed for iteration it+2
+    if (CLUSTER && tid == 0 && nHalo && it > 0 && it + 2 < iters) fbc_mbar_expect(mb0 + 8u * (uint32_t)(it & 1), haloBytes);
     // ---- dual half-step: every edge incident to this CTA's vertices ---------------------------
-#pragma unroll
-    for (int k = 0; k < FBG_EPT; ++k) {
-      const float4 bi = s_bar[e_b[k] & 0xffffu];
-      const float4 bj = s_bar[e_b[k] >> 16];
-      float t = bi.x - bj.x;
-      t = fmaf(-edx[k], bi.y, t);
-      t = fmaf(-edy[k], bi.z, t);
-      const float k1 = ea[k] * t;
-      const float k2 = ebt[k] * (bi.y - bj.y);
-      const float k3 = ebt[k] * (bi.z - bj.z);
-      q1[k] = fb_clamp1(fmaf(sigma, k1, q1[k]));
-      q2[k] = fb_clamp1(fmaf(sigma, k2, q2[k]));
-      q3[k] = fb_clamp1(fmaf(sigma, k3, q3[k]));
-      const float a1 = ea[k] * q1[k];
-      const float4 cs = make_float4(a1, fmaf(ebt[k], q2[k], -(edx[k] * a1)),
-                                    fmaf(ebt[k], q3[k], -(edy[k] * a1)), 0.f);
-      const float4 ct = make_float4(-a1, -(ebt[k] * q2[k]), -(ebt[k] * q3[k]), 0.f);
-      if (e_id[k] != -1) {  // the endpoint owned by another CTA maps to the dummy slot
-        s_slot[e_s[k] & 0xffffu] = cs;
-        s_slot[e_s[k] >> 16] = ct;
-      }
+    switch (rowsE) {
+      case 1: fbg_dual<1>(E, bar_base + rd_off, slot_base, sigma); break;
+      case 2: fbg_dual<2>(E, bar_base + rd_off, slot_base, sigma); break;
+      case 3: fbg_dual<3>(E, bar_base + rd_off, slot_base, sigma); break;
+      case 4: fbg_dual<4>(E, bar_base + rd_off, slot_base, sigma); break;
+      default: break;
     }
     __syncthreads();  // slots complete
-    // ---- primal half-step: slot gather in CSR order, prox, box, extragradient, publish --------
-    {
+    // ---- primal half-step: slot gather in CSR order, prox, box, extragradient, hand-over -------
+    if (rowsV > 0) {
       float gx[FBG_VPT], g1[FBG_VPT], g2[FBG_VPT];
       int dmax = 0;
 #pragma unroll
       for (int k = 0; k < FBG_VPT; ++k) {
         gx[k] = g1[k] = g2[k] = 0.f;
-        dmax = max(dmax, vs1[k] - vs0[k]);
+        dmax = max(dmax, Vt.s1[k] - Vt.s0[k]);
       }
       for (int j = 0; j < dmax; ++j) {
 #pragma unroll
         for (int k = 0; k < FBG_VPT; ++k) {
-          if (vs0[k] + j < vs1[k]) {
-            const float4 c = s_slot[vs0[k] + j];
+          if (Vt.s0[k] + j < Vt.s1[k]) {
+            const float4 c = s_slot[Vt.s0[k] + j];
             gx[k] += c.x;
             g1[k] += c.y;
             g2[k] += c.z;
@@ -253,24 +339,33 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
       }
 #pragma unroll
       for (int k = 0; k < FBG_VPT; ++k) {
-        if (v_id[k] >= 0) {
-          const float xo = vx[k], w1o = vw1[k], w2o = vw2[k];
+        if (Vt.id[k] >= 0) {
+          const float xo = Vt.x[k], w1o = Vt.w1[k], w2o = Vt.w2[k];
           const float xp = fmaf(-tau, gx[k], xo);
           const float w1n = fmaf(-tau, g1[k], w1o);
           const float w2n = fmaf(-tau, g2[k], w2o);
-          const float d = xp - vz[k];
-          float xn = (d > vth[k]) ? (xp - vth[k]) : ((d < -vth[k]) ? (xp + vth[k]) : vz[k]);
+          const float d = xp - Vt.z[k];
+          float xn = (d > Vt.th[k]) ? (xp - Vt.th[k]) : ((d < -Vt.th[k]) ? (xp + Vt.th[k]) : Vt.z[k]);
           xn = fminf(fmaxf(xn, xmin), xmax);
-          vx[k] = xn; vw1[k] = w1n; vw2[k] = w2n;
+          Vt.x[k] = xn; Vt.w1[k] = w1n; Vt.w2[k] = w2n;
           const float4 nb = make_float4(fmaf(theta, xn - xo, xn), fmaf(theta, w1n - w1o, w1n),
                                         fmaf(theta, w2n - w2o, w2n), 0.f);
           if (more) {
-            if (v_id[k] & 0x40000000)
-              fbg_st_mailbox(pub0 + (size_t)(it & 1) * pstride + (v_id[k] & 0x3fffffff), nb.x, nb.y, nb.z,
-                             tag0 + (uint32_t)it);
-            s_bar[tid + k * FBG_THREADS] = nb;
+            if (Vt.id[k] & 0x40000000) {  // boundary vertex: hand the point to the CTAs across the cut
+              if (CLUSTER) {
+                const uint32_t moff = 8u * (uint32_t)((it + 1) & 1);
+                for (uint32_t p = Vt.push[k] & 0xffffu; p < (Vt.push[k] >> 16); ++p) {
+                  const uint2 e = s_push[p];
+                  fbc_st_async(e.x + wr_off, nb, e.y + moff);
+                }
+              } else {
+                fbg_st_mailbox(pub0 + (size_t)(it & 1) * a.pstride + (Vt.id[k] & 0x3fffffff), nb.x, nb.y, nb.z,
+                               tag0 + (uint32_t)it);
+              }
+            }
+            fbc_sts(bar_base + wr_off + 16u * (uint32_t)(tid + k * THREADS), nb);
           } else {
-            g.vbar[vb + (v_id[k] & 0x3fffffff)] = nb;
+            g.vbar[vb + (Vt.id[k] & 0x3fffffff)] = nb;
           }
         }
       }
@@ -280,18 +375,19 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   // ---- write back: registers -> global -----------------------------------------------------------
 #pragma unroll
   for (int k = 0; k < FBG_EPT; ++k)
-    if (e_id[k] >= 0) g.q4[eb + e_id[k]] = make_float4(q1[k], q2[k], q3[k], 0.f);
+    if (E.id[k] >= 0) g.q4[eb + E.id[k]] = make_float4(E.q1[k], E.q2[k], E.q3[k], 0.f);
 #pragma unroll
   for (int k = 0; k < FBG_VPT; ++k)
-    if (v_id[k] >= 0) {
-      const size_t v = vb + (v_id[k] & 0x3fffffff);
-      g.x[v] = vx[k]; g.w1[v] = vw1[k]; g.w2[v] = vw2[k];
+    if (Vt.id[k] >= 0) {
+      const size_t v = vb + (Vt.id[k] & 0x3fffffff);
+      g.x[v] = Vt.x[k]; g.w1[v] = Vt.w1[k]; g.w2[v] = Vt.w2[k];
     }
+  if (CLUSTER) fbc_cluster_sync();  // no CTA retires while a peer could still address its shared memory
 }
 
 // ---------------------------------------------------------------------------------- host side
-static inline size_t fbg_smem_bytes(int capBar, int capSlot) {
-  return 16 * ((size_t)capBar + (size_t)capSlot + 1);
+static inline size_t fbg_smem_bytes(int capBar, int capSlot, int capPush) {
+  return 16 * (2 * (size_t)capBar + (size_t)capSlot + 1) + 16 + 8 * (size_t)capPush;
 }
 
 // Recursive coordinate bisection: ids[lo,hi) -> parts [p0, p0+np), split along the longer extent
@@ -324,15 +420,17 @@ static void fbg_rcb(const float2* pos, const int* wgt, int* ids, int lo, int hi,
   fbg_rcb(pos, wgt, ids, m, hi, p0 + nl, np - nl, part);
 }
 
-// Build the host tables of one stream for `nper` parts.  Returns false when a part exceeds the
-// per-CTA register or shared-memory capacity (the caller then tries more parts or another variant).
-static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper) {
+// Build the host tables of one stream for `nper` parts and a CTA of `threads` threads.  Returns
+// false when a part exceeds the per-CTA register or shared-memory capacity (the caller then tries
+// more parts, the other transport or another variant).
+static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, int threads, size_t smem_limit) {
   const int V = t.V, E = t.E;
   g.planned = nper;
+  g.planned_threads = threads;
   g.feasible = false;
-  g.capBar = g.capSlot = 0;
-  g.cinfo.assign((size_t)2 * nper, make_int4(0, 0, 0, 0));
-  g.eplan.clear(); g.eid.clear(); g.hplan.clear();
+  g.capBar = g.capSlot = g.capPush = 0;
+  g.cinfo.assign((size_t)3 * nper, make_int4(0, 0, 0, 0));
+  g.eplan.clear(); g.eid.clear(); g.hplan.clear(); g.pplan.clear();
   g.vplan.assign(V, make_int4(0, 0, 0, 0));
   if (V == 0) {
     g.feasible = true;
@@ -356,7 +454,7 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper) {
       if (code & 1) pdst[code >> 1] = k - t.row[v];
       else psrc[code >> 1] = k - t.row[v];
     }
-  // processing order per part: boundary vertices first (published early), then descending degree
+  // processing order per part: boundary vertices first (handed over early), then descending degree
   // (lanes of a warp run slot loops of equal length); slot blocks are padded to an odd number of
   // 16 B records so a warp's gathers spread over all banks
   std::vector<int> cnt(nper + 1, 0);
@@ -380,14 +478,14 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper) {
       lidx[v] = k - cnt[r];
       sbase[v] = base;
       base += deg[v] | 1;
-      g.vplan[k] = make_int4(v, sbase[v], sbase[v] + deg[v], bnd[v]);
+      g.vplan[k] = make_int4(v, sbase[v], sbase[v] + deg[v], 0);
     }
     nslot[r] = base;
     const int nOwn = cnt[r + 1] - cnt[r];
-    if (nOwn > FBG_VPT * FBG_THREADS || base + 1 > 0xffff) return false;
-    g.cinfo[2 * r].x = cnt[r];
-    g.cinfo[2 * r].y = nOwn;
-    g.cinfo[2 * r + 1].z = base;
+    if (nOwn > FBG_VPT * threads || base + 1 > 0xffff) return false;
+    g.cinfo[3 * r].x = cnt[r];
+    g.cinfo[3 * r].y = nOwn;
+    g.cinfo[3 * r + 1].z = base;
     g.capSlot = std::max(g.capSlot, base);
   }
   // edge lists per part: interior edges first, then cut edges (held by both sides)
@@ -411,9 +509,10 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper) {
       if (rj != ri) elist[efill[rj]++] = e | (int)0x80000000;
     }
   std::vector<int> hidx(V, -1), hstamp(V, -1);
+  std::vector<std::vector<int4>> push(nper);  // per owner part: {owner-local vertex, consumer part, consumer entry}
   for (int r = 0; r < nper; ++r) {
     const int nOwn = cnt[r + 1] - cnt[r], nE = ecnt[r + 1] - ecnt[r];
-    if (nE > FBG_EPT * FBG_THREADS) return false;
+    if (nE > FBG_EPT * threads) return false;
     const int hbeg = (int)g.hplan.size();
     int nh = 0;
     for (int k = ecnt[r]; k < ecnt[r + 1]; ++k) {
@@ -431,6 +530,7 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper) {
             hstamp[v] = r;
             hidx[v] = nh++;
             g.hplan.push_back(v);
+            push[part[v]].push_back(make_int4(lidx[v], r, nOwn + hidx[v], 0));
           }
           b[side] = nOwn + hidx[v];
           sl[side] = nslot[r];  // dummy slot
@@ -440,13 +540,32 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper) {
       g.eplan[k] = make_int2(b[0] | (b[1] << 16), sl[0] | (sl[1] << 16));
       g.eid[k] = code;
     }
-    g.cinfo[2 * r].z = ecnt[r];
-    g.cinfo[2 * r].w = nE;
-    g.cinfo[2 * r + 1].x = hbeg;
-    g.cinfo[2 * r + 1].y = nh;
+    g.cinfo[3 * r].z = ecnt[r];
+    g.cinfo[3 * r].w = nE;
+    g.cinfo[3 * r + 1].x = hbeg;
+    g.cinfo[3 * r + 1].y = nh;
     g.capBar = std::max(g.capBar, nOwn + nh);
   }
-  if (fbg_smem_bytes(g.capBar, g.capSlot) > FBG_SMEM_LIMIT) return false;
+  // push lists (cluster transport): per owner part, grouped by vertex in processing order
+  for (int r = 0; r < nper; ++r) {
+    std::vector<int4>& pl = push[r];
+    std::stable_sort(pl.begin(), pl.end(), [](const int4& x, const int4& y) { return x.x < y.x; });
+    if (pl.size() > 0xffff) return false;
+    const int pbeg = (int)g.pplan.size();
+    size_t k = 0;
+    for (int li = 0; li < cnt[r + 1] - cnt[r]; ++li) {
+      const size_t b = k;
+      while (k < pl.size() && pl[k].x == li) {
+        g.pplan.push_back(make_int2(pl[k].y, pl[k].z));
+        ++k;
+      }
+      g.vplan[cnt[r] + li].w = (int)(b | (k << 16));
+    }
+    g.cinfo[3 * r + 2].x = pbeg;
+    g.cinfo[3 * r + 2].y = (int)pl.size();
+    g.capPush = std::max(g.capPush, (int)pl.size());
+  }
+  if (fbg_smem_bytes(g.capBar, g.capSlot, g.capPush) > smem_limit) return false;
   g.feasible = true;
   return true;
 }
@@ -459,12 +578,15 @@ static int grid_plan_init(fb_ctx* c) {
   const size_t S = c->S;
   if (dalloc(&P->eplan, S * 2 * c->maxE) != cudaSuccess || dalloc(&P->eid, S * 2 * c->maxE) != cudaSuccess ||
       dalloc(&P->vplan, S * c->maxV) != cudaSuccess || dalloc(&P->hplan, S * 2 * c->maxE) != cudaSuccess ||
-      dalloc(&P->cinfo, S * FBG_MAXP * 2) != cudaSuccess || dalloc(&P->pub, 2 * S * c->maxV) != cudaSuccess ||
+      dalloc(&P->pplan, S * 2 * c->maxE) != cudaSuccess ||
+      dalloc(&P->cinfo, S * FBG_MAXP * 3) != cudaSuccess || dalloc(&P->pub, 2 * S * c->maxV) != cudaSuccess ||
       cudaHostAlloc((void**)&P->err, sizeof(int), cudaHostAllocMapped) != cudaSuccess)
     FB_FAIL(c, FB_E_NOMEM, "grid plan allocation failed");
   *P->err = 0;
   FB_CUDA(c, cudaMemsetAsync(P->pub, 0, sizeof(float4) * 2 * S * c->maxV, c->stream));
   if (const char* e = getenv("FB_GRID_CTAS")) P->budget_env = atoi(e);
+  if (const char* e = getenv("FB_GRID_CLUSTER")) P->cluster_env = std::max(0, std::min(FBG_MAXC, atoi(e)));
+  if (const char* e = getenv("FB_GRID_MODE")) P->mode_env = (e[0] == 'c') ? 1 : (e[0] == 'l' ? 2 : 0);
   return FB_OK;
 }
 
@@ -478,14 +600,15 @@ static int grid_plan_set(fb_ctx* c, int s, int V, const float* pos) {
   for (int v = 0; v < V; ++v) g.pos[v] = make_float2(pos[2 * v], pos[2 * v + 1]);
   g.dirty = true;
   g.planned = 0;
+  c->gplan->version++;
   return FB_OK;
 }
 
 static void grid_plan_free(fb_ctx* c) {
   GridPlan* P = c->gplan;
   if (!P) return;
-  cudaFree(P->eplan); cudaFree(P->eid); cudaFree(P->vplan); cudaFree(P->hplan); cudaFree(P->cinfo);
-  cudaFree(P->pub);
+  cudaFree(P->eplan); cudaFree(P->eid); cudaFree(P->vplan); cudaFree(P->hplan); cudaFree(P->pplan);
+  cudaFree(P->cinfo); cudaFree(P->pub);
   if (P->err) cudaFreeHost(P->err);
   delete P;
   c->gplan = nullptr;
@@ -494,68 +617,147 @@ static void grid_plan_free(fb_ctx* c) {
 // True when the watchdog of an earlier variant-3 launch fired (checked after stream syncs).
 static bool grid_watchdog_fired(const fb_ctx* c) { return c->gplan && c->gplan->err && *c->gplan->err != 0; }
 
-// Pick the parts per stream, (re)build and upload the tables.  Returns FB_OK with *nper_out = 0
-// when the batch does not fit the grid-resident solver (the caller falls back to another variant).
-static int grid_prepare(fb_ctx* c, int only, int* nper_out, size_t* smem_out) {
+static inline bool fbg_active(const fb_ctx* c, int s, int only) { return (only < 0 || s == only) && c->hV[s] > 0; }
+
+// (Re)build every active stream's tables for (nper, threads); true when all of them fit.
+static bool fbg_plan_all(fb_ctx* c, int only, int nper, int threads, size_t smem_limit) {
+  GridPlan* P = c->gplan;
+  for (int s = 0; s < c->S; ++s) {
+    if (!fbg_active(c, s, only)) continue;
+    GridPlan::Topo& g = P->topo[s];
+    if (g.planned != nper || g.planned_threads != threads) {
+      fbg_build(g, c->plan->topo[s], nper, threads, smem_limit);
+      g.dirty = true;
+    }
+    if (!g.feasible) return false;
+  }
+  return true;
+}
+
+static int fbg_max_clusters(GridPlan* P, int C, size_t smem) {
+  if (P->max_clusters[C] >= 0) return P->max_clusters[C];
+  auto kern = k_nltgv2_grid<FBG_THREADS_CL, 1, true>;
+  if (P->smem_set[1] < FBG_SMEM_LIMIT_CL) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FBG_SMEM_LIMIT_CL);
+    P->smem_set[1] = FBG_SMEM_LIMIT_CL;
+  }
+  if (C > 8 && !P->nonportable_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    P->nonportable_set = true;
+  }
+  cudaLaunchConfig_t q{};
+  q.gridDim = dim3((unsigned)(C * 64));
+  q.blockDim = dim3(FBG_THREADS_CL);
+  q.dynamicSmemBytes = std::max<size_t>(smem, 64 * 1024);  // registers (1 CTA / SM), not smem, bound residency
+  cudaLaunchAttribute qa[1];
+  qa[0].id = cudaLaunchAttributeClusterDimension;
+  qa[0].val.clusterDim.x = (unsigned)C;
+  qa[0].val.clusterDim.y = 1;
+  qa[0].val.clusterDim.z = 1;
+  q.attrs = qa;
+  q.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  P->max_clusters[C] = n;
+  return n;
+}
+
+// Pick the transport and the parts per stream, (re)build and upload the tables.  Returns FB_OK with
+// *nper_out = 0 when the batch does not fit (the caller falls back to another variant).
+static int grid_prepare(fb_ctx* c, int iters, int only, int* nper_out, size_t* smem_out) {
   *nper_out = 0;
   if (!c->gplan || !c->plan) return FB_OK;
   GridPlan* P = c->gplan;
+  if (P->dec_version == P->version && P->dec_only == only && (P->dec_cluster || iters <= FBG_MAX_ITERS)) {
+    P->nper = P->dec_nper;  // nothing changed since the last launch: tables are on the device
+    P->cluster = P->dec_cluster;
+    *nper_out = P->dec_nper;
+    *smem_out = P->dec_smem;
+    return FB_OK;
+  }
   int n_act = 0, maxV = 0, maxE = 0;
   for (int s = 0; s < c->S; ++s) {
-    if (only >= 0 && s != only) continue;
-    if (c->hV[s] > 0) ++n_act;
+    if (!fbg_active(c, s, only)) continue;
+    ++n_act;
     maxV = std::max(maxV, c->hV[s]);
     maxE = std::max(maxE, c->hE[s]);
   }
   if (n_act == 0) return FB_OK;
-  if (P->max_blocks < 0) {
-    // co-residency bound of the cooperative launch, at the shared-memory ceiling the plans may use
-    cudaFuncSetAttribute(k_nltgv2_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, FBG_SMEM_LIMIT);
-    P->smem_set = FBG_SMEM_LIMIT;
-    int per_sm = 0, sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nltgv2_grid, FBG_THREADS, FBG_SMEM_LIMIT) != cudaSuccess) {
-      cudaGetLastError();
-      per_sm = 0;
+  int nper = 0;
+  bool cluster = false;
+  // ---- cluster transport: the largest cluster size (<= 16) for which all active streams'
+  // clusters are co-resident (one wave), never below ~128 vertices per CTA
+  if (P->mode_env != 2) {
+    const int need = std::max(1, std::max(fb_div_up(maxV, FBG_VPT * FBG_THREADS_CL), fb_div_up(maxE + maxE / 8, FBG_EPT * FBG_THREADS_CL)));
+    int cmax = std::min(FBG_MAXC, std::max(need, maxV / 128));
+    if (P->cluster_env > 0) cmax = std::max(need, P->cluster_env);
+    for (int cand = std::min(cmax, FBG_MAXC); cand >= need && cand >= 1 && !cluster; --cand) {
+      // co-residency first (cheap, cached per size), then the tables
+      if (P->cluster_env == 0 && fbg_max_clusters(P, cand, 0) < n_act) continue;
+      if (!fbg_plan_all(c, only, cand, FBG_THREADS_CL, FBG_SMEM_LIMIT_CL)) continue;
+      nper = cand;
+      cluster = true;
     }
-    P->max_blocks = per_sm * sms;
-    P->sms = sms;
+    // more streams than co-resident clusters of any size: the smallest feasible cluster, in waves
+    // (streams are independent, so clusters need not run at the same time)
+    for (int cand = need; cand <= FBG_MAXC && !cluster; ++cand) {
+      if (!fbg_plan_all(c, only, cand, FBG_THREADS_CL, FBG_SMEM_LIMIT_CL)) continue;
+      nper = cand;
+      cluster = true;
+    }
   }
-  int budget = P->max_blocks;
-  if (P->budget_env > 0) budget = std::min(budget, P->budget_env);
-  const int n_div = only >= 0 ? 1 : c->S;  // CTAs of empty streams are launched too (they exit at once)
-  if (budget < n_div) return FB_OK;
-  // parts per stream: all co-resident CTAs shared by the active streams, but never below ~96
-  // vertices per part (the exchange then dominates) and at least what the capacities need
-  int nper = std::min(budget / n_div, FBG_MAXP);
-  nper = std::max(1, std::min(nper, std::max(1, maxV / (P->budget_env > 0 ? 16 : 96))));
-  const int need = std::max(fb_div_up(maxV, FBG_VPT * FBG_THREADS), fb_div_up(maxE + maxE / 4, FBG_EPT * FBG_THREADS));
-  nper = std::max(nper, need);
-  bool ok = false;
-  for (; nper * n_div <= budget && nper <= FBG_MAXP; nper += std::max(1, nper / 8)) {
-    ok = true;
-    for (int s = 0; s < c->S && ok; ++s) {
-      if ((only >= 0 && s != only) || c->hV[s] == 0) continue;
-      GridPlan::Topo& g = P->topo[s];
-      if (g.planned != nper) {
-        fbg_build(g, c->plan->topo[s], nper);
-        g.dirty = true;
+  // ---- L2 transport: all co-resident CTAs shared by the streams of the launch
+  if (!cluster && P->mode_env != 1 && iters <= FBG_MAX_ITERS) {
+    auto kern = k_nltgv2_grid<FBG_THREADS_L2, 2, false>;
+    if (P->max_blocks < 0) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FBG_SMEM_LIMIT_L2);
+      P->smem_set[0] = FBG_SMEM_LIMIT_L2;
+      int per_sm = 0, sms = 0;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FBG_THREADS_L2, FBG_SMEM_LIMIT_L2) != cudaSuccess) {
+        cudaGetLastError();
+        per_sm = 0;
       }
-      ok = g.feasible;
+      P->max_blocks = per_sm * sms;
     }
-    if (ok) break;
+    int budget = P->max_blocks;
+    if (P->budget_env > 0) budget = std::min(budget, P->budget_env);
+    const int n_div = only >= 0 ? 1 : c->S;  // CTAs of empty streams are launched too (they exit at once)
+    nper = 0;
+    if (budget >= n_div) {
+      // never below ~96 vertices per part (the exchange then dominates), at least what the capacities need
+      nper = std::min(budget / n_div, FBG_MAXP);
+      nper = std::max(1, std::min(nper, std::max(1, maxV / (P->budget_env > 0 ? 16 : 96))));
+      const int need = std::max(fb_div_up(maxV, FBG_VPT * FBG_THREADS_L2), fb_div_up(maxE + maxE / 4, FBG_EPT * FBG_THREADS_L2));
+      nper = std::max(nper, need);
+      bool ok = false;
+      for (; nper * n_div <= budget && nper <= FBG_MAXP; nper += std::max(1, nper / 8))
+        if ((ok = fbg_plan_all(c, only, nper, FBG_THREADS_L2, FBG_SMEM_LIMIT_L2))) break;
+      if (!ok) nper = 0;
+    }
   }
-  if (!ok) return FB_OK;
-  int capBar = 1, capSlot = 1;
+  if (nper == 0) {  // does not fit: remember that too (the caller falls back to another variant)
+    P->dec_version = P->version;
+    P->dec_only = only;
+    P->dec_nper = 0;
+    P->dec_cluster = true;
+    P->dec_smem = 0;
+    return FB_OK;
+  }
+  int capBar = 1, capSlot = 1, capPush = 0;
   cudaStream_t st = c->stream;
   for (int s = 0; s < c->S; ++s) {
-    if ((only >= 0 && s != only) || c->hV[s] == 0) continue;
+    if (!fbg_active(c, s, only)) continue;
     GridPlan::Topo& g = P->topo[s];
     capBar = std::max(capBar, g.capBar);
     capSlot = std::max(capSlot, g.capSlot);
+    capPush = std::max(capPush, g.capPush);
     if (!g.dirty) continue;
     const size_t vb = (size_t)s * c->maxV, eb2 = (size_t)s * 2 * c->maxE;
-    if (g.eplan.size() > 2 * (size_t)c->maxE || g.hplan.size() > 2 * (size_t)c->maxE)
+    if (g.eplan.size() > 2 * (size_t)c->maxE || g.hplan.size() > 2 * (size_t)c->maxE || g.pplan.size() > 2 * (size_t)c->maxE)
       FB_FAIL(c, FB_E_NOMEM, "grid plan: tables exceed capacity");
     FB_CUDA(c, cudaMemcpyAsync(P->vplan + vb, g.vplan.data(), sizeof(int4) * g.vplan.size(), cudaMemcpyHostToDevice, st));
     if (!g.eplan.empty()) {
@@ -564,20 +766,29 @@ static int grid_prepare(fb_ctx* c, int only, int* nper_out, size_t* smem_out) {
     }
     if (!g.hplan.empty())
       FB_CUDA(c, cudaMemcpyAsync(P->hplan + eb2, g.hplan.data(), sizeof(int32_t) * g.hplan.size(), cudaMemcpyHostToDevice, st));
-    FB_CUDA(c, cudaMemcpyAsync(P->cinfo + (size_t)s * FBG_MAXP * 2, g.cinfo.data(), sizeof(int4) * g.cinfo.size(), cudaMemcpyHostToDevice, st));
+    if (!g.pplan.empty())
+      FB_CUDA(c, cudaMemcpyAsync(P->pplan + eb2, g.pplan.data(), sizeof(int2) * g.pplan.size(), cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(P->cinfo + (size_t)s * FBG_MAXP * 3, g.cinfo.data(), sizeof(int4) * g.cinfo.size(), cudaMemcpyHostToDevice, st));
     g.dirty = false;  // host tables stay alive in the Topo: no staging lifetime issue
   }
   P->nper = nper;
+  P->cluster = cluster;
   P->capBar = capBar;
+  P->capSlot = capSlot;
+  P->capPush = capPush;
   *nper_out = nper;
-  *smem_out = fbg_smem_bytes(capBar, capSlot);
+  *smem_out = fbg_smem_bytes(capBar, capSlot, capPush);
+  P->dec_version = P->version;
+  P->dec_only = only;
+  P->dec_nper = nper;
+  P->dec_cluster = cluster;
+  P->dec_smem = *smem_out;
   return FB_OK;
 }
 
 static int solve_grid(fb_ctx* c, int iters, const fb_nltgv2_params* p, int nper, size_t smem, int only = -1) {
   GridPlan* P = c->gplan;
-  if (iters > FBG_MAX_ITERS) FB_FAIL(c, FB_E_ARG, "fb_nltgv2_solve: variant 3 supports at most 16383 iterations per call");
-  // tags are unique per launch; when the 32-bit tag space is used up the mailboxes are cleared
+  // L2 transport: tags are unique per launch; when the 32-bit tag space is used up the mailboxes are cleared
   if (P->seq >= 0xffffffffu / (FBG_MAX_ITERS + 1) - 1) {
     FB_CUDA(c, cudaMemsetAsync(P->pub, 0, sizeof(float4) * 2 * (size_t)c->S * c->maxV, c->stream));
     P->seq = 0;
@@ -587,27 +798,49 @@ static int solve_grid(fb_ctx* c, int iters, const fb_nltgv2_params* p, int nper,
   GridArgs a;
   a.g = graph_view(c);
   a.g.only = only;
-  a.eplan = P->eplan; a.eid = P->eid; a.vplan = P->vplan; a.hplan = P->hplan; a.cinfo = P->cinfo;
+  a.eplan = P->eplan; a.eid = P->eid; a.vplan = P->vplan; a.hplan = P->hplan; a.pplan = P->pplan;
+  a.cinfo = P->cinfo;
   a.pub = P->pub;
   a.err = P->err;
   a.nper = nper;
   a.capBar = P->capBar;
+  a.capSlot = P->capSlot;
   a.pstride = (size_t)c->S * c->maxV;
   c->last_cluster = nper;
+  c->last_transport = P->cluster ? 1 : 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)((only >= 0 ? 1 : c->S) * nper));
-  cfg.blockDim = dim3(FBG_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = c->stream;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the mailbox readers spin
-  attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const float tl = p->step_x * p->data_factor;
-  ProfScope ps(c, FB_PROF_SOLVE);
-  FB_CUDA(c, cudaLaunchKernelEx(&cfg, k_nltgv2_grid, a, iters, p->step_q, p->step_x, tl, p->theta, p->x_min,
-                                p->x_max, tag0));
+  if (P->cluster) {
+    auto kern = k_nltgv2_grid<FBG_THREADS_CL, 1, true>;
+    if (P->smem_set[1] < smem) {
+      FB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FBG_SMEM_LIMIT_CL));
+      P->smem_set[1] = FBG_SMEM_LIMIT_CL;
+    }
+    if (nper > 8 && !P->nonportable_set) {
+      FB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      P->nonportable_set = true;
+    }
+    cfg.blockDim = dim3(FBG_THREADS_CL);
+    attr[0].id = cudaLaunchAttributeClusterDimension;  // streams are independent: clusters may run in waves
+    attr[0].val.clusterDim.x = (unsigned)nper;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    ProfScope ps(c, FB_PROF_SOLVE);
+    FB_CUDA(c, cudaLaunchKernelEx(&cfg, kern, a, iters, p->step_q, p->step_x, tl, p->theta, p->x_min, p->x_max, tag0));
+  } else {
+    auto kern = k_nltgv2_grid<FBG_THREADS_L2, 2, false>;
+    cfg.blockDim = dim3(FBG_THREADS_L2);
+    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the mailbox readers spin
+    attr[0].val.cooperative = 1;
+    ProfScope ps(c, FB_PROF_SOLVE);
+    FB_CUDA(c, cudaLaunchKernelEx(&cfg, kern, a, iters, p->step_q, p->step_x, tl, p->theta, p->x_min, p->x_max, tag0));
+  }
   c->launches++;
   return FB_OK;
 }
@@ -617,7 +850,8 @@ static int solve_grid(fb_ctx* c, int iters, const fb_nltgv2_params* p, int nper,
 // CPU test-suite to validate the partitioner against the invariants the kernel relies on.
 // stats[8] = {max own vertices, max edges per part, max halo, duplicated (cut) edges, max slots,
 //             shared memory bytes, boundary vertices, parts}.
-static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int nper, int32_t* stats, std::string& why) {
+static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int nper, int threads, size_t smem_limit,
+                      int32_t* stats, std::string& why) {
   ClusterPlan::Topo t;
   t.V = V;
   t.E = E;
@@ -640,14 +874,14 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
   GridPlan::Topo g;
   g.pos.resize(V);
   for (int v = 0; v < V; ++v) g.pos[v] = make_float2(pos[2 * v], pos[2 * v + 1]);
-  if (!fbg_build(g, t, nper)) {
+  if (!fbg_build(g, t, nper, threads, smem_limit)) {
     why = "partition infeasible for this part count";
     return 1;
   }
   std::vector<int> owner(V, -1), lidx(V, -1), written(E, 0);
   int maxOwn = 0, maxEdge = 0, maxHalo = 0, dup = 0, maxSlot = 0, nb = 0;
   for (int r = 0; r < nper; ++r) {
-    const int4 c0 = g.cinfo[2 * r], c1 = g.cinfo[2 * r + 1];
+    const int4 c0 = g.cinfo[3 * r], c1 = g.cinfo[3 * r + 1];
     for (int k = 0; k < c0.y; ++k) {
       const int4 pv = g.vplan[c0.x + k];
       if (pv.x < 0 || pv.x >= V || owner[pv.x] != -1) { why = "vertex owned twice or out of range"; return 2; }
@@ -655,7 +889,7 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
       lidx[pv.x] = k;
       if (pv.z - pv.y != t.row[pv.x + 1] - t.row[pv.x]) { why = "slot block size != degree"; return 3; }
       if (pv.z > c1.z) { why = "slot block beyond the part's slot count"; return 3; }
-      nb += pv.w ? 1 : 0;
+      nb += ((uint32_t)pv.w >> 16) != ((uint32_t)pv.w & 0xffffu) ? 1 : 0;
     }
     maxOwn = std::max(maxOwn, c0.y);
     maxEdge = std::max(maxEdge, c0.w);
@@ -665,7 +899,7 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
   for (int v = 0; v < V; ++v)
     if (owner[v] < 0) { why = "vertex without owner"; return 2; }
   for (int r = 0; r < nper; ++r) {
-    const int4 c0 = g.cinfo[2 * r], c1 = g.cinfo[2 * r + 1];
+    const int4 c0 = g.cinfo[3 * r], c1 = g.cinfo[3 * r + 1];
     std::vector<int> hit(c1.z + 1, 0);
     for (int k = 0; k < c0.w; ++k) {
       const int code = g.eid[c0.z + k], e = code & 0x7fffffff;
@@ -691,8 +925,15 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
           const int h = b[side] - c0.y;
           if (h < 0 || h >= c1.y || g.hplan[c1.x + h] != v) { why = "halo index mismatch"; return 7; }
           if (sl[side] != c1.z) { why = "remote endpoint must map to the dummy slot"; return 8; }
-          const int4 pv = g.vplan[g.cinfo[2 * owner[v]].x + lidx[v]];
-          if (!pv.w) { why = "halo vertex not published by its owner"; return 9; }
+          // the owner's push list must name exactly this halo entry
+          const int4 pv = g.vplan[g.cinfo[3 * owner[v]].x + lidx[v]];
+          const int pbeg = g.cinfo[3 * owner[v] + 2].x;
+          bool found = false;
+          for (uint32_t q = (uint32_t)pv.w & 0xffffu; q < ((uint32_t)pv.w >> 16); ++q) {
+            const int2 pe = g.pplan[pbeg + q];
+            if (pe.x == r && pe.y == b[side]) found = true;
+          }
+          if (!found) { why = "halo vertex not pushed/published by its owner"; return 9; }
         }
       }
       if (!any_own) { why = "edge without an own endpoint"; return 10; }
@@ -709,9 +950,14 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
   }
   for (int e = 0; e < E; ++e)
     if (written[e] != 1) { why = "edge not written back exactly once"; return 13; }
+  {  // every push entry corresponds to one halo entry
+    size_t np = 0, nh = 0;
+    for (int r = 0; r < nper; ++r) { np += g.cinfo[3 * r + 2].y; nh += g.cinfo[3 * r + 1].y; }
+    if (np != nh || np != g.pplan.size()) { why = "push lists and halo lists differ in size"; return 14; }
+  }
   if (stats) {
     stats[0] = maxOwn; stats[1] = maxEdge; stats[2] = maxHalo; stats[3] = dup; stats[4] = maxSlot;
-    stats[5] = (int32_t)fbg_smem_bytes(g.capBar, g.capSlot); stats[6] = nb; stats[7] = nper;
+    stats[5] = (int32_t)fbg_smem_bytes(g.capBar, g.capSlot, g.capPush); stats[6] = nb; stats[7] = nper;
   }
   return 0;
 }

@@ -136,9 +136,10 @@ int fb_graph_x_get_all(fb_ctx* ctx, float* x_all);
  * variant: 0 = auto, 1 = streaming (two kernels per iteration, any size),
  *          2 = persistent thread-block-cluster kernel (graph resident in shared memory, one
  *              cluster of <= 16 CTAs per stream, DSMEM exchange),
- *          3 = grid-resident kernel (graphs resident in registers/shared memory of every
- *              co-resident CTA of the device, cut edges held by both sides, one tagged 128-bit
- *              mailbox exchange through L2 per iteration; cooperative launch).
+ *          3 = resident kernel with ONE halo exchange per iteration (cut edges held by both
+ *              sides): a cluster of <= 16 CTAs per stream with DSMEM st.async hand-over when the
+ *              graphs fit, else every co-resident CTA of the device with tagged 128-bit
+ *              mailboxes in L2 (cooperative launch).
  * auto picks 3 when the batch fits, else 2, else 1.  All variants give bit-identical results. */
 int fb_nltgv2_solve(fb_ctx* ctx, int iters, const fb_nltgv2_params* p, int variant);
 /* nltgv2_total_{smoothness,data}_cost (/root/reference/src/utils.cc:131-136); synchronises. */
@@ -312,17 +313,22 @@ int fb_profile_get(fb_ctx* ctx, int section, float* total_ms, int64_t* calls, in
 /* Total kernels launched by this context since creation. */
 int64_t fb_launch_count(const fb_ctx* ctx);
 /* Host-only self-check of the variant-3 partitioner (no device, no context): cuts the graph into
- * `parts` CTAs' worth of tables and verifies the invariants the kernel relies on (every vertex owned
+ * `parts` CTAs' worth of tables (cluster != 0: capacities of the cluster transport, parts <= 16;
+ * else of the L2 transport) and verifies the invariants the kernel relies on (every vertex owned
  * once, every incidence slot written exactly once in CSR order, halo vertices published by their
- * owners, every edge written back exactly once).  0 = OK, 1 = does not fit this part count, other
+ * and pushed by their owners, every edge written back exactly once).  0 = OK, 1 = does not fit this part count, other
  * > 0 = violated invariant (fb_last_error(NULL) says which), < 0 = bad argument.
  * stats[8] (optional) = {max own vertices, max edges, max halo, duplicated edges, max slots,
  * shared-memory bytes, boundary vertices, parts}. */
-int fb_grid_plan_verify(int V, int E, const float* pos, const int32_t* ij, int parts, int32_t* stats);
+int fb_grid_plan_verify(int V, int E, const float* pos, const int32_t* ij, int parts, int cluster,
+                        int32_t* stats);
 /* Which solver variant the last fb_nltgv2_solve used (1, 2 or 3). */
 int fb_last_solver_variant(const fb_ctx* ctx);
 /* CTAs per stream of the last variant-2 (cluster size) or variant-3 (parts per stream) launch. */
 int fb_last_cluster_size(const fb_ctx* ctx);
+/* Halo transport of the last variant-3 launch: 1 = thread-block cluster (DSMEM st.async +
+ * mbarrier), 2 = tagged 128-bit mailboxes in L2 (cooperative launch); 0 = none yet. */
+int fb_last_solver_transport(const fb_ctx* ctx);
 
 #ifdef __cplusplus
 }

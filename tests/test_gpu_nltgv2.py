@@ -61,24 +61,61 @@ def test_c4_graph_parity_100_iters(capi, oracle, variant):
     assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS), "expected bit-exact state"
 
 
-@pytest.mark.parametrize("budget", ["7", "40", "75"])
-def test_grid_solver_is_partition_invariant(capi, oracle, budget, monkeypatch):
-    """Variant 3: the result does not depend on how many CTAs share a graph (cut edges are computed
-    on both sides of a cut with bit-identical results)."""
-    monkeypatch.setenv("FB_GRID_CTAS", budget)
+@pytest.mark.parametrize("mode,knob,val,transport", [("l2", "FB_GRID_CTAS", "7", 2), ("l2", "FB_GRID_CTAS", "40", 2),
+                                                     ("l2", "FB_GRID_CTAS", "75", 2), ("cluster", "FB_GRID_CLUSTER", "2", 1),
+                                                     ("cluster", "FB_GRID_CLUSTER", "5", 1), ("cluster", "FB_GRID_CLUSTER", "8", 1),
+                                                     ("cluster", "FB_GRID_CLUSTER", "16", 1)])
+def test_grid_solver_is_partition_and_transport_invariant(capi, oracle, mode, knob, val, transport, monkeypatch):
+    """Variant 3: the result depends neither on how many CTAs share a graph (cut edges are computed
+    on both sides of a cut with bit-identical results) nor on the halo transport."""
+    monkeypatch.setenv("FB_GRID_MODE", mode)
+    monkeypatch.setenv(knob, val)
     g = small_graph(40, 30, 320, 240, seed=5)
-    ref = run_oracle(oracle, g, 30)
+    ref = run_oracle(oracle, g, 31)
     with capi.Context(1, 320, 240, 2, 16, 1200, 3600) as ctx:
         gpu_load_graph(ctx, 0, g)
-        ctx.nltgv2_solve(30, variant=3)
-        assert ctx.last_solver_variant() == 3
+        ctx.nltgv2_solve(31, variant=3)
+        assert ctx.last_solver_variant() == 3 and ctx.last_solver_transport() == transport
+        if mode == "cluster":
+            assert ctx.last_cluster_size() == int(val)
         got = ctx.graph_state_get(0)
     assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
 
 
-def test_grid_solver_repeated_launches_and_topology_change(capi, oracle):
+@pytest.mark.parametrize("mode", ["l2", "cluster"])
+@pytest.mark.parametrize("iters", [1, 2, 3, 4, 5])
+def test_grid_solver_short_solves(capi, oracle, mode, iters, monkeypatch):
+    """The two-parity barrier / mailbox schedule at its edges: 1..5 iterations."""
+    monkeypatch.setenv("FB_GRID_MODE", mode)
+    monkeypatch.setenv("FB_GRID_CLUSTER" if mode == "cluster" else "FB_GRID_CTAS", "6")
+    g = small_graph(24, 18, 192, 144, seed=11)
+    ref = run_oracle(oracle, g, iters)
+    with capi.Context(1, 192, 144, 2, 16, 600, 1800) as ctx:
+        gpu_load_graph(ctx, 0, g)
+        ctx.nltgv2_solve(iters, variant=3)
+        got = ctx.graph_state_get(0)
+    assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
+
+
+@pytest.mark.parametrize("mode", ["l2", "cluster"])
+def test_c2_grid_solver_both_transports(capi, oracle, mode, monkeypatch):
+    monkeypatch.setenv("FB_GRID_MODE", mode)
+    g = synth.s_graph("C2")
+    ref = run_oracle(oracle, g, 50)
+    with capi.Context(1, 640, 480, 2, 16, 5000, 15000) as ctx:
+        gpu_load_graph(ctx, 0, g)
+        ctx.nltgv2_solve(50, variant=3)
+        assert ctx.last_solver_transport() == (1 if mode == "cluster" else 2)
+        got = ctx.graph_state_get(0)
+    assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
+
+
+@pytest.mark.parametrize("mode", ["l2", "cluster"])
+def test_grid_solver_repeated_launches_and_topology_change(capi, oracle, mode, monkeypatch):
     """Mailbox tags are unique per launch: many back-to-back solves and a re-upload of a different
     graph into the same context never see a stale point."""
+    monkeypatch.setenv("FB_GRID_MODE", mode)
+    monkeypatch.setenv("FB_GRID_CLUSTER" if mode == "cluster" else "FB_GRID_CTAS", "5")
     ga, gb = small_graph(24, 18, 192, 144, seed=11), small_graph(20, 20, 192, 144, seed=12)
     with capi.Context(1, 192, 144, 2, 16, 600, 1800) as ctx:
         for g in (ga, gb, ga):

@@ -20,12 +20,24 @@ def test_small_graph_tables(capi, parts):
         assert st["dup_edges"] > 0 and st["max_halo"] > 0
 
 
-@pytest.mark.parametrize("cfg,parts", [("C2", 18), ("C2", 37), ("C2", 52), ("C4", 148), ("C4", 296)])
-def test_benchmark_graph_tables(capi, cfg, parts):
+@pytest.mark.parametrize("parts", [1, 2, 5, 16])
+def test_small_graph_tables_cluster_transport(capi, parts):
+    g = small_graph(20, 15, 160, 120, seed=9)
+    rc, st = capi.grid_plan_verify(g["pos"], g["edges"], parts, cluster=True)
+    assert rc == 0 and st["parts"] == parts
+
+
+@pytest.mark.parametrize("cfg,parts,cluster", [("C2", 18, False), ("C2", 37, False), ("C2", 52, False),
+                                               ("C4", 148, False), ("C4", 296, False),
+                                               ("C2", 8, True), ("C2", 10, True), ("C2", 16, True)])
+def test_benchmark_graph_tables(capi, cfg, parts, cluster):
     g = synth.s_graph(cfg)
     V, E = len(g["pos"]), len(g["edges"])
-    rc, st = capi.grid_plan_verify(g["pos"], g["edges"], parts)
+    rc, st = capi.grid_plan_verify(g["pos"], g["edges"], parts, cluster)
     assert rc == 0
+    if cluster:
+        assert st["max_edges"] <= 2048 and st["max_own"] <= 1024 and st["smem_bytes"] <= 200 * 1024
+        return
     # compact parts: the cut stays a small fraction of the edges, the load is balanced
     assert st["dup_edges"] < 0.35 * E
     assert st["max_own"] <= 1.35 * V / parts + 8
@@ -35,6 +47,9 @@ def test_benchmark_graph_tables(capi, cfg, parts):
 def test_too_few_parts_is_reported_not_mangled(capi):
     g = synth.s_graph("C2")
     rc, _ = capi.grid_plan_verify(g["pos"], g["edges"], 4)   # 1250 vertices per part > 512
+    assert rc == 1
+    g4 = synth.s_graph("C4")
+    rc, _ = capi.grid_plan_verify(g4["pos"], g4["edges"], 16, cluster=True)   # 20k vertices need > 16 CTAs
     assert rc == 1
 
 
