@@ -214,7 +214,7 @@ def grid_plan_verify(pos, edges, parts, cluster=False):
         raise FlameError("fb_grid_plan_verify: bad argument")
     if rc > 1:
         raise FlameError(lib.fb_last_error(None).decode())
-    keys = ("max_own", "max_edges", "max_halo", "dup_edges", "max_slots", "smem_bytes", "boundary", "parts")
+    keys = ("max_own", "max_generic", "max_halo", "cut_edges", "max_slots", "smem_bytes", "boundary", "overflow_edges")
     return rc, dict(zip(keys, stats.tolist()))
 
 

@@ -9,11 +9,19 @@
 //     contributions a vertex needs are therefore produced inside its own CTA: the only thing that
 //     crosses CTAs is the extragradient point of boundary vertices, ONCE per iteration
 //     (variant 2 exchanges twice: contributions one way, refreshed halo points back);
-//   * per-edge state (q, alpha, beta, dx, dy) and per-vertex state (x, w, z, threshold) live in
-//     registers for the whole solve; shared memory holds the extragradient points (own + halo,
-//     double-banked by iteration parity) and one 16 B slot per vertex-edge incidence in the
-//     vertex's CSR order, so the summation order (ascending edge id) and hence every bit of the
-//     result equals the streaming kernels'.
+//   * a thread owns ONE vertex and that vertex's out-edges (edges (v,w), v < w: up to FBG_FAST of
+//     them in register rows).  Its vertex state (x, w, z, threshold, extragradient point) and its
+//     edges' state (q, alpha, beta, dx, dy) live in registers for the whole solve, so the dual
+//     update of an out-edge reads only the TARGET's point from shared memory and writes only the
+//     target's K^T q contribution to a slot; the source's contribution is re-derived from q in
+//     registers.  Per vertex and iteration that is ~160 B of shared-memory traffic instead of
+//     ~300 B for an edge-parallel layout -- shared-memory bandwidth bounds this kernel, not HBM;
+//   * a vertex sums its contributions in CSR order (ascending edge id): edges are sorted by (i,j)
+//     with i < j, so that order is [in-edges, from slots] [out-edges, from registers]
+//     [out-edges beyond the register rows, from slots] -- every bit of the result equals the
+//     streaming kernels';
+//   * edges whose source is not a thread's own vertex (cut edges seen from the target's CTA,
+//     out-edges beyond FBG_FAST) are "generic": one per thread, both points through shared memory.
 // Two transports for the halo, same kernel body (template parameter):
 //   CLUSTER  one thread-block cluster (<= 16 CTAs x 512 threads) per stream: the owner thread pushes
 //            the new point straight into the consumers' shared memory with
@@ -35,8 +43,7 @@
 #include "nltgv2.cuh"
 #include "nltgv2_cluster.cuh"
 
-#define FBG_EPT 4              // edges per thread (register resident)
-#define FBG_VPT 2              // vertices per thread
+#define FBG_FAST 4             // register rows: out-edges of the thread's own vertex
 #define FBG_THREADS_L2 256     // L2 transport: two CTAs per SM
 #define FBG_THREADS_CL 512     // cluster transport: one CTA per SM
 #define FBG_MAXP 512           // parts per stream (table stride)
@@ -47,12 +54,14 @@
 #define FBG_SPIN_LIMIT (1u << 21)  // mailbox polls before a reader gives up (watchdog, ~0.3 s)
 
 struct GridPlan {
-  int2* eplan = nullptr;     // [S*2*maxE] {bi | bj<<16, si | sj<<16}: s_bar / s_slot entry indices
-  int32_t* eid = nullptr;    // [S*2*maxE] edge id, bit 31 set on the copy that is NOT written back
-  int4* vplan = nullptr;     // [S*maxV] {vertex id, slot begin, slot end, push begin | push end << 16}
+  uint32_t* fplan = nullptr; // [S*FBG_FAST*maxV] fast rows: bj | sj<<16 (row-major: row k, vertex slot)
+  int32_t* feid = nullptr;   // [S*FBG_FAST*maxV] fast rows: edge id, -1 = idle
+  int2* gplan = nullptr;     // [S*2*maxE] generic edges {bi | bj<<16, si | sj<<16}: s_bar / s_slot entry indices
+  int32_t* geid = nullptr;   // [S*2*maxE] generic edges: edge id, bit 31 set on a copy that is NOT written back
+  int4* vplan = nullptr;     // [S*maxV] {vertex id, slot begin | n_target<<16 | n_overflow<<24, push begin | end<<16, 0}
   int32_t* hplan = nullptr;  // [S*2*maxE] halo lists: stream-local vertex ids
   int2* pplan = nullptr;     // [S*2*maxE] push lists: {consumer part, entry index in its s_bar}
-  int4* cinfo = nullptr;     // [S*FBG_MAXP*3] {vBeg, nOwn, eBeg, nEdge}, {hBeg, nHalo, nSlot, 0}, {pBeg, nPush, 0, 0}
+  int4* cinfo = nullptr;     // [S*FBG_MAXP*3] {vBeg, nOwn, gBeg, nGen}, {hBeg, nHalo, nSlot, 0}, {pBeg, nPush, 0, 0}
   float4* pub = nullptr;     // [2][S*maxV] tagged mailboxes (parity-major), L2 transport
   int* err = nullptr;        // mapped host flag: set by the watchdog
   uint32_t seq = 0;          // launch counter -> tag base
@@ -78,8 +87,10 @@ struct GridPlan {
     int planned_threads = 0;  // capacity class they were checked against
     bool feasible = false;
     int capBar = 0, capSlot = 0, capPush = 0;
-    std::vector<int2> eplan, pplan;
-    std::vector<int32_t> eid, hplan;
+    std::vector<uint32_t> fplan;   // [FBG_FAST][V]
+    std::vector<int32_t> feid;     // [FBG_FAST][V]
+    std::vector<int2> gplan, pplan;
+    std::vector<int32_t> geid, hplan;
     std::vector<int4> vplan, cinfo;
   };
   std::vector<Topo> topo;
@@ -124,8 +135,10 @@ __device__ __forceinline__ float4 fbg_poll(const float4* p, uint32_t tag, int* e
 
 struct GridArgs {
   GraphView g;
-  const int2* eplan;
-  const int32_t* eid;
+  const uint32_t* fplan;
+  const int32_t* feid;
+  const int2* gplan;
+  const int32_t* geid;
   const int4* vplan;
   const int32_t* hplan;
   const int2* pplan;
@@ -138,43 +151,37 @@ struct GridArgs {
   size_t pstride;  // S*maxV: distance between the two mailbox banks
 };
 
-struct FbgEdges {  // register-resident edge rows of one thread
-  float q1[FBG_EPT], q2[FBG_EPT], q3[FBG_EPT], a[FBG_EPT], b[FBG_EPT], dx[FBG_EPT], dy[FBG_EPT];
-  uint32_t bar[FBG_EPT], slot[FBG_EPT];  // packed 16-bit entry indices: (bi, bj) and (si, sj)
-  int id[FBG_EPT];
+struct FbgFast {  // register-resident out-edges of the thread's own vertex (source = own vertex)
+  float q1[FBG_FAST], q2[FBG_FAST], q3[FBG_FAST], a[FBG_FAST], b[FBG_FAST], dx[FBG_FAST], dy[FBG_FAST];
+  uint32_t idx[FBG_FAST];  // target's s_bar entry | target's slot << 16 (dummy slot when the target is remote)
 };
-struct FbgVerts {  // register-resident vertex rows of one thread
-  float x[FBG_VPT], w1[FBG_VPT], w2[FBG_VPT], z[FBG_VPT], th[FBG_VPT];
-  int s0[FBG_VPT], s1[FBG_VPT], id[FBG_VPT];  // id: vertex id, bit 30 = boundary; -1 = none
-  uint32_t push[FBG_VPT];                     // push list range begin | end << 16 (cluster transport)
+struct FbgGen {  // register-resident generic edge (both endpoints through shared memory)
+  float q1, q2, q3, a, b, dx, dy;
+  uint32_t bar, slot;  // (bi, bj) and (si, sj), 16 bits each
 };
 
-// Dual half-step over the first R edge rows of this thread (R is warp-uniform: rows whose 32 lanes
-// are all idle are not executed at all; inside an active row idle lanes compute on zero weights and
-// store nothing, so the R rows form independent branch-free instruction streams).
+// Dual half-step of the first R out-edges of the thread's vertex.  The source's extragradient point
+// is in registers; only the target's is read from shared memory, only the target's contribution is
+// written to a slot (the source's is re-derived from q in the primal half-step).  Stores are
+// unconditional: idle rows and remote targets write to the dummy slot, so the R rows are
+// independent branch-free instruction streams.
 template <int R>
-__device__ __forceinline__ void fbg_dual(FbgEdges& E, uint32_t bar_rd, uint32_t slot_base, float sigma) {
+__device__ __forceinline__ void fbg_dual_fast(FbgFast& F, float xb, float w1b, float w2b, uint32_t bar_rd,
+                                              uint32_t slot_base, float sigma) {
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    const float4 bi = fbc_lds(bar_rd + ((E.bar[k] & 0xffffu) << 4));
-    const float4 bj = fbc_lds(bar_rd + ((E.bar[k] >> 16) << 4));
-    float t = bi.x - bj.x;
-    t = fmaf(-E.dx[k], bi.y, t);
-    t = fmaf(-E.dy[k], bi.z, t);
-    const float k1 = E.a[k] * t;
-    const float k2 = E.b[k] * (bi.y - bj.y);
-    const float k3 = E.b[k] * (bi.z - bj.z);
-    E.q1[k] = fb_clamp1(fmaf(sigma, k1, E.q1[k]));
-    E.q2[k] = fb_clamp1(fmaf(sigma, k2, E.q2[k]));
-    E.q3[k] = fb_clamp1(fmaf(sigma, k3, E.q3[k]));
-    const float a1 = E.a[k] * E.q1[k];
-    const float4 cs = make_float4(a1, fmaf(E.b[k], E.q2[k], -(E.dx[k] * a1)),
-                                  fmaf(E.b[k], E.q3[k], -(E.dy[k] * a1)), 0.f);
-    const float4 ct = make_float4(-a1, -(E.b[k] * E.q2[k]), -(E.b[k] * E.q3[k]), 0.f);
-    if (E.id[k] != -1) {  // the endpoint owned by another CTA maps to the dummy slot
-      fbc_sts(slot_base + ((E.slot[k] & 0xffffu) << 4), cs);
-      fbc_sts(slot_base + ((E.slot[k] >> 16) << 4), ct);
-    }
+    const float4 bj = fbc_lds(bar_rd + ((F.idx[k] & 0xffffu) << 4));
+    float t = xb - bj.x;
+    t = fmaf(-F.dx[k], w1b, t);
+    t = fmaf(-F.dy[k], w2b, t);
+    const float k1 = F.a[k] * t;
+    const float k2 = F.b[k] * (w1b - bj.y);
+    const float k3 = F.b[k] * (w2b - bj.z);
+    F.q1[k] = fb_clamp1(fmaf(sigma, k1, F.q1[k]));
+    F.q2[k] = fb_clamp1(fmaf(sigma, k2, F.q2[k]));
+    F.q3[k] = fb_clamp1(fmaf(sigma, k3, F.q3[k]));
+    const float a1 = F.a[k] * F.q1[k];
+    fbc_sts(slot_base + ((F.idx[k] >> 16) << 4), make_float4(-a1, -(F.b[k] * F.q2[k]), -(F.b[k] * F.q3[k]), 0.f));
   }
 }
 
@@ -194,7 +201,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   if (g.nV[s] == 0) return;  // uniform over the stream's CTAs
   const int4* ci = a.cinfo + ((size_t)s * FBG_MAXP + r) * 3;
   const int4 c0 = ci[0], c1 = ci[1], c2 = ci[2];
-  const int nOwn = c0.y, nEdge = c0.w, nHalo = c1.y, nPush = c2.y;
+  const int nOwn = c0.y, nGen = c0.w, nHalo = c1.y, nPush = c2.y;
   if (nOwn == 0) {  // an empty part owns nothing and feeds nobody
     if (CLUSTER) {
       fbc_cluster_sync();
@@ -203,57 +210,66 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     return;
   }
   const size_t vb = (size_t)s * g.maxV, eb = (size_t)s * g.maxE;
-  const int2* epl = a.eplan + 2 * eb + c0.z;
-  const int32_t* eidl = a.eid + 2 * eb + c0.z;
-  const int4* vpl = a.vplan + vb + c0.x;
   const int32_t* hl = a.hplan + 2 * eb + c1.x;
   float4* pub0 = a.pub + vb;
   const uint32_t bar_base = fbc_smem_u32(s_bar), slot_base = fbc_smem_u32(s_slot);
   const uint32_t bank_bytes = 16u * (uint32_t)a.capBar;
   const uint32_t mb0 = fbc_smem_u32(s_mbar);
   const uint32_t haloBytes = 16u * (uint32_t)nHalo;
+  const uint32_t dummy = (uint32_t)c1.z;
 
-  // ---- register-resident per-edge and per-vertex state ----------------------------------------
-  FbgEdges E;
+  // ---- register-resident state: the thread's vertex, its out-edges, one generic edge ------------
+  float vx = 0.f, vw1 = 0.f, vw2 = 0.f, vz = 0.f, vth = 0.f, xb = 0.f, w1b = 0.f, w2b = 0.f;
+  int v_id = -1;             // vertex id, bit 30 = boundary; -1 = none
+  uint32_t v_sl = 0u;        // slot begin | n_target << 16 | n_overflow << 24
+  uint32_t v_push = 0u;      // push list range begin | end << 16 (cluster transport)
+  uint32_t fvalid = 0u;      // bit k: fast row k holds an edge
+  FbgFast F;
 #pragma unroll
-  for (int k = 0; k < FBG_EPT; ++k) {
-    const int idx = tid + k * THREADS;
-    E.id[k] = -1;
-    E.q1[k] = E.q2[k] = E.q3[k] = E.a[k] = E.b[k] = E.dx[k] = E.dy[k] = 0.f;
-    E.bar[k] = 0u;
-    E.slot[k] = (uint32_t)c1.z | ((uint32_t)c1.z << 16);
-    if (idx < nEdge) {
-      const int2 pl = epl[idx];
-      const int id = eidl[idx];
-      E.id[k] = id;
-      const float4 c = g.ec[eb + (id & 0x7fffffff)];
-      const float4 q = g.q4[eb + (id & 0x7fffffff)];
-      E.a[k] = c.x; E.b[k] = c.y; E.dx[k] = c.z; E.dy[k] = c.w;
-      E.q1[k] = q.x; E.q2[k] = q.y; E.q3[k] = q.z;
-      E.bar[k] = (uint32_t)pl.x;
-      E.slot[k] = (uint32_t)pl.y;
+  for (int k = 0; k < FBG_FAST; ++k) {
+    F.q1[k] = F.q2[k] = F.q3[k] = F.a[k] = F.b[k] = F.dx[k] = F.dy[k] = 0.f;
+    F.idx[k] = dummy << 16;
+  }
+  if (tid < nOwn) {
+    const int4 pt = a.vplan[vb + c0.x + tid];
+    const int v = pt.x;
+    v_sl = (uint32_t)pt.y;
+    v_push = (uint32_t)pt.z;
+    v_id = v | (((uint32_t)pt.z >> 16) != ((uint32_t)pt.z & 0xffffu) ? 0x40000000 : 0);
+    vx = g.x[vb + v]; vw1 = g.w1[vb + v]; vw2 = g.w2[vb + v];
+    vz = g.z[vb + v];
+    vth = tl * g.wt[vb + v];
+    const float4 b0 = g.vbar[vb + v];
+    xb = b0.x; w1b = b0.y; w2b = b0.z;
+    s_bar[tid] = b0;  // bank 0: the points iteration 0 reads
+#pragma unroll
+    for (int k = 0; k < FBG_FAST; ++k) {
+      const size_t fi = ((size_t)s * FBG_FAST + k) * g.maxV + c0.x + tid;
+      const int id = a.feid[fi];
+      if (id >= 0) {
+        fvalid |= 1u << k;
+        F.idx[k] = a.fplan[fi];
+        const float4 c = g.ec[eb + id];
+        const float4 q = g.q4[eb + id];
+        F.a[k] = c.x; F.b[k] = c.y; F.dx[k] = c.z; F.dy[k] = c.w;
+        F.q1[k] = q.x; F.q2[k] = q.y; F.q3[k] = q.z;
+      }
     }
   }
-  FbgVerts Vt;
-#pragma unroll
-  for (int k = 0; k < FBG_VPT; ++k) {
-    const int idx = tid + k * THREADS;
-    Vt.x[k] = Vt.w1[k] = Vt.w2[k] = Vt.z[k] = Vt.th[k] = 0.f;
-    Vt.s0[k] = Vt.s1[k] = 0;
-    Vt.id[k] = -1;
-    Vt.push[k] = 0u;
-    if (idx < nOwn) {
-      const int4 pt = vpl[idx];
-      const int v = pt.x;
-      Vt.push[k] = (uint32_t)pt.w;
-      Vt.id[k] = v | (((uint32_t)pt.w >> 16) != ((uint32_t)pt.w & 0xffffu) ? 0x40000000 : 0);
-      Vt.x[k] = g.x[vb + v]; Vt.w1[k] = g.w1[vb + v]; Vt.w2[k] = g.w2[vb + v];
-      Vt.z[k] = g.z[vb + v];
-      Vt.th[k] = tl * g.wt[vb + v];
-      Vt.s0[k] = pt.y;
-      Vt.s1[k] = pt.z;
-      s_bar[idx] = g.vbar[vb + v];  // bank 0: the points iteration 0 reads
-    }
+  FbgGen G;
+  G.q1 = G.q2 = G.q3 = G.a = G.b = G.dx = G.dy = 0.f;
+  G.bar = 0u;
+  G.slot = dummy | (dummy << 16);
+  int g_id = -1;
+  if (tid < nGen) {
+    const int2 pl = a.gplan[2 * eb + c0.z + tid];
+    g_id = a.geid[2 * eb + c0.z + tid];
+    const float4 c = g.ec[eb + (g_id & 0x7fffffff)];
+    const float4 q = g.q4[eb + (g_id & 0x7fffffff)];
+    G.a = c.x; G.b = c.y; G.dx = c.z; G.dy = c.w;
+    G.q1 = q.x; G.q2 = q.y; G.q3 = q.z;
+    G.bar = (uint32_t)pl.x;
+    G.slot = (uint32_t)pl.y;
   }
   // halo: the first value comes straight from global memory (written by earlier kernels of the
   // stream); L2 transport keeps the vertex ids of a thread's first two entries in registers
@@ -282,10 +298,10 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     fbc_cluster_sync();  // every CTA's barriers are initialised before any remote store can target them
   }
   bool dead = false;
-  // rows of this warp that hold at least one edge / vertex (warp-uniform)
-  const int wbase = tid & ~31;
-  const int rowsE = max(0, min(FBG_EPT, (nEdge - wbase + THREADS - 1) / THREADS));
-  const int rowsV = max(0, min(FBG_VPT, (nOwn - wbase + THREADS - 1) / THREADS));
+  // warp-uniform work extents: fast rows any lane of the warp uses, generic row, vertex row
+  const int rowsF = __reduce_max_sync(0xffffffffu, __popc(fvalid));
+  const bool warpG = (tid & ~31) < nGen, warpV = (tid & ~31) < nOwn;
+  const int s0 = (int)(v_sl & 0xffffu), nT = (int)((v_sl >> 16) & 0xffu), nO = (int)(v_sl >> 24);
 
   for (int it = 0; it < iters; ++it) {
     const bool more = it + 1 < iters;
@@ -308,80 +324,102 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     __syncthreads();  // own points (primal of it-1) and halo points visible to the edge threads
     // every thread is past the wait: the barrier of this parity is re-armed for iteration it+2
     if (CLUSTER && tid == 0 && nHalo && it > 0 && it + 2 < iters) fbc_mbar_expect(mb0 + 8u * (uint32_t)(it & 1), haloBytes);
-    // ---- dual half-step: every edge incident to this CTA's vertices ---------------------------
-    switch (rowsE) {
-      case 1: fbg_dual<1>(E, bar_base + rd_off, slot_base, sigma); break;
-      case 2: fbg_dual<2>(E, bar_base + rd_off, slot_base, sigma); break;
-      case 3: fbg_dual<3>(E, bar_base + rd_off, slot_base, sigma); break;
-      case 4: fbg_dual<4>(E, bar_base + rd_off, slot_base, sigma); break;
-      default: break;
+    // ---- dual half-step ---------------------------------------------------------------------------
+    switch (rowsF) {
+      case 0: break;
+      case 1: fbg_dual_fast<1>(F, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma); break;
+      case 2: fbg_dual_fast<2>(F, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma); break;
+      case 3: fbg_dual_fast<3>(F, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma); break;
+      default: fbg_dual_fast<FBG_FAST>(F, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma); break;
+    }
+    if (warpG) {  // generic edges: the source is remote (cut edge seen from the target's CTA) or overflowed
+      const float4 bi = fbc_lds(bar_base + rd_off + ((G.bar & 0xffffu) << 4));
+      const float4 bj = fbc_lds(bar_base + rd_off + ((G.bar >> 16) << 4));
+      float t = bi.x - bj.x;
+      t = fmaf(-G.dx, bi.y, t);
+      t = fmaf(-G.dy, bi.z, t);
+      const float k1 = G.a * t;
+      const float k2 = G.b * (bi.y - bj.y);
+      const float k3 = G.b * (bi.z - bj.z);
+      G.q1 = fb_clamp1(fmaf(sigma, k1, G.q1));
+      G.q2 = fb_clamp1(fmaf(sigma, k2, G.q2));
+      G.q3 = fb_clamp1(fmaf(sigma, k3, G.q3));
+      const float a1 = G.a * G.q1;
+      fbc_sts(slot_base + ((G.slot & 0xffffu) << 4),
+              make_float4(a1, fmaf(G.b, G.q2, -(G.dx * a1)), fmaf(G.b, G.q3, -(G.dy * a1)), 0.f));
+      fbc_sts(slot_base + ((G.slot >> 16) << 4), make_float4(-a1, -(G.b * G.q2), -(G.b * G.q3), 0.f));
     }
     __syncthreads();  // slots complete
-    // ---- primal half-step: slot gather in CSR order, prox, box, extragradient, hand-over -------
-    if (rowsV > 0) {
-      float gx[FBG_VPT], g1[FBG_VPT], g2[FBG_VPT];
-      int dmax = 0;
-#pragma unroll
-      for (int k = 0; k < FBG_VPT; ++k) {
-        gx[k] = g1[k] = g2[k] = 0.f;
-        dmax = max(dmax, Vt.s1[k] - Vt.s0[k]);
+    // ---- primal half-step: CSR order = target-role slots, own out-edges, overflow slots -----------
+    if (warpV) {
+      float gx = 0.f, g1 = 0.f, g2 = 0.f;
+      for (int j = 0; j < nT; ++j) {
+        const float4 c = s_slot[s0 + j];
+        gx += c.x;
+        g1 += c.y;
+        g2 += c.z;
       }
-      for (int j = 0; j < dmax; ++j) {
 #pragma unroll
-        for (int k = 0; k < FBG_VPT; ++k) {
-          if (Vt.s0[k] + j < Vt.s1[k]) {
-            const float4 c = s_slot[Vt.s0[k] + j];
-            gx[k] += c.x;
-            g1[k] += c.y;
-            g2[k] += c.z;
-          }
+      for (int k = 0; k < FBG_FAST; ++k) {
+        if (fvalid & (1u << k)) {  // the source's contribution, same expression the slot would have held
+          const float a1 = F.a[k] * F.q1[k];
+          gx += a1;
+          g1 += fmaf(F.b[k], F.q2[k], -(F.dx[k] * a1));
+          g2 += fmaf(F.b[k], F.q3[k], -(F.dy[k] * a1));
         }
       }
-#pragma unroll
-      for (int k = 0; k < FBG_VPT; ++k) {
-        if (Vt.id[k] >= 0) {
-          const float xo = Vt.x[k], w1o = Vt.w1[k], w2o = Vt.w2[k];
-          const float xp = fmaf(-tau, gx[k], xo);
-          const float w1n = fmaf(-tau, g1[k], w1o);
-          const float w2n = fmaf(-tau, g2[k], w2o);
-          const float d = xp - Vt.z[k];
-          float xn = (d > Vt.th[k]) ? (xp - Vt.th[k]) : ((d < -Vt.th[k]) ? (xp + Vt.th[k]) : Vt.z[k]);
-          xn = fminf(fmaxf(xn, xmin), xmax);
-          Vt.x[k] = xn; Vt.w1[k] = w1n; Vt.w2[k] = w2n;
-          const float4 nb = make_float4(fmaf(theta, xn - xo, xn), fmaf(theta, w1n - w1o, w1n),
-                                        fmaf(theta, w2n - w2o, w2n), 0.f);
-          if (more) {
-            if (Vt.id[k] & 0x40000000) {  // boundary vertex: hand the point to the CTAs across the cut
-              if (CLUSTER) {
-                const uint32_t moff = 8u * (uint32_t)((it + 1) & 1);
-                for (uint32_t p = Vt.push[k] & 0xffffu; p < (Vt.push[k] >> 16); ++p) {
-                  const uint2 e = s_push[p];
-                  fbc_st_async(e.x + wr_off, nb, e.y + moff);
-                }
-              } else {
-                fbg_st_mailbox(pub0 + (size_t)(it & 1) * a.pstride + (Vt.id[k] & 0x3fffffff), nb.x, nb.y, nb.z,
-                               tag0 + (uint32_t)it);
+      for (int j = 0; j < nO; ++j) {
+        const float4 c = s_slot[s0 + nT + j];
+        gx += c.x;
+        g1 += c.y;
+        g2 += c.z;
+      }
+      if (v_id >= 0) {
+        const float xo = vx, w1o = vw1, w2o = vw2;
+        const float xp = fmaf(-tau, gx, xo);
+        const float w1n = fmaf(-tau, g1, w1o);
+        const float w2n = fmaf(-tau, g2, w2o);
+        const float d = xp - vz;
+        float xn = (d > vth) ? (xp - vth) : ((d < -vth) ? (xp + vth) : vz);
+        xn = fminf(fmaxf(xn, xmin), xmax);
+        vx = xn; vw1 = w1n; vw2 = w2n;
+        xb = fmaf(theta, xn - xo, xn);
+        w1b = fmaf(theta, w1n - w1o, w1n);
+        w2b = fmaf(theta, w2n - w2o, w2n);
+        const float4 nb = make_float4(xb, w1b, w2b, 0.f);
+        if (more) {
+          if (v_id & 0x40000000) {  // boundary vertex: hand the point to the CTAs across the cut
+            if (CLUSTER) {
+              const uint32_t moff = 8u * (uint32_t)((it + 1) & 1);
+              for (uint32_t p = v_push & 0xffffu; p < (v_push >> 16); ++p) {
+                const uint2 e = s_push[p];
+                fbc_st_async(e.x + wr_off, nb, e.y + moff);
               }
+            } else {
+              fbg_st_mailbox(pub0 + (size_t)(it & 1) * a.pstride + (v_id & 0x3fffffff), nb.x, nb.y, nb.z,
+                             tag0 + (uint32_t)it);
             }
-            fbc_sts(bar_base + wr_off + 16u * (uint32_t)(tid + k * THREADS), nb);
-          } else {
-            g.vbar[vb + (Vt.id[k] & 0x3fffffff)] = nb;
           }
+          fbc_sts(bar_base + wr_off + 16u * (uint32_t)tid, nb);
+        } else {
+          g.vbar[vb + (v_id & 0x3fffffff)] = nb;
         }
       }
     }
   }
 
   // ---- write back: registers -> global -----------------------------------------------------------
+  if (v_id >= 0) {
+    const size_t v = vb + (v_id & 0x3fffffff);
+    g.x[v] = vx; g.w1[v] = vw1; g.w2[v] = vw2;
 #pragma unroll
-  for (int k = 0; k < FBG_EPT; ++k)
-    if (E.id[k] >= 0) g.q4[eb + E.id[k]] = make_float4(E.q1[k], E.q2[k], E.q3[k], 0.f);
-#pragma unroll
-  for (int k = 0; k < FBG_VPT; ++k)
-    if (Vt.id[k] >= 0) {
-      const size_t v = vb + (Vt.id[k] & 0x3fffffff);
-      g.x[v] = Vt.x[k]; g.w1[v] = Vt.w1[k]; g.w2[v] = Vt.w2[k];
-    }
+    for (int k = 0; k < FBG_FAST; ++k)
+      if (fvalid & (1u << k)) {
+        const int id = a.feid[((size_t)s * FBG_FAST + k) * g.maxV + c0.x + tid];
+        g.q4[eb + id] = make_float4(F.q1[k], F.q2[k], F.q3[k], 0.f);
+      }
+  }
+  if (g_id >= 0) g.q4[eb + g_id] = make_float4(G.q1, G.q2, G.q3, 0.f);
   if (CLUSTER) fbc_cluster_sync();  // no CTA retires while a peer could still address its shared memory
 }
 
@@ -420,9 +458,9 @@ static void fbg_rcb(const float2* pos, const int* wgt, int* ids, int lo, int hi,
   fbg_rcb(pos, wgt, ids, m, hi, p0 + nl, np - nl, part);
 }
 
-// Build the host tables of one stream for `nper` parts and a CTA of `threads` threads.  Returns
-// false when a part exceeds the per-CTA register or shared-memory capacity (the caller then tries
-// more parts, the other transport or another variant).
+// Build the host tables of one stream for `nper` parts and a CTA of `threads` threads (one vertex
+// and one generic edge per thread).  Returns false when a part exceeds the per-CTA capacity (the
+// caller then tries more parts, the other transport or another variant).
 static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, int threads, size_t smem_limit) {
   const int V = t.V, E = t.E;
   g.planned = nper;
@@ -430,33 +468,42 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
   g.feasible = false;
   g.capBar = g.capSlot = g.capPush = 0;
   g.cinfo.assign((size_t)3 * nper, make_int4(0, 0, 0, 0));
-  g.eplan.clear(); g.eid.clear(); g.hplan.clear(); g.pplan.clear();
+  g.gplan.clear(); g.geid.clear(); g.hplan.clear(); g.pplan.clear();
   g.vplan.assign(V, make_int4(0, 0, 0, 0));
+  g.fplan.assign((size_t)FBG_FAST * V, 0u);
+  g.feid.assign((size_t)FBG_FAST * V, -1);
   if (V == 0) {
     g.feasible = true;
     return true;
   }
-  std::vector<int> deg(V), wgt(V), ids(V), part(V, 0);
+  // CSR rows hold the target-role incidences (edges (u,v), u < v) before the source-role ones
+  // (edges (v,w)): edges are sorted by (i,j) with i < j.  The kernel's summation order relies on it.
+  std::vector<int> nin(V, 0), deg(V), wgt(V), ids(V), part(V, 0);
   for (int v = 0; v < V; ++v) {
     deg[v] = t.row[v + 1] - t.row[v];
+    bool src_seen = false;
+    for (int k = t.row[v]; k < t.row[v + 1]; ++k) {
+      if (t.inc[k] & 1) {
+        if (src_seen) return false;
+        nin[v]++;
+      } else {
+        src_seen = true;
+      }
+    }
     wgt[v] = 2 + deg[v];
   }
   std::iota(ids.begin(), ids.end(), 0);
   fbg_rcb(g.pos.data(), wgt.data(), ids.data(), 0, V, 0, nper, part.data());
-  // boundary vertices; CSR position of every edge at its two endpoints
   std::vector<uint8_t> bnd(V, 0);
-  std::vector<int> psrc(E), pdst(E);
+  std::vector<int> pdst(E);  // position of edge e among the target-role incidences of its target
   for (int e = 0; e < E; ++e)
     if (part[t.eij[e].x] != part[t.eij[e].y]) bnd[t.eij[e].x] = bnd[t.eij[e].y] = 1;
   for (int v = 0; v < V; ++v)
-    for (int k = t.row[v]; k < t.row[v + 1]; ++k) {
-      const int code = t.inc[k];
-      if (code & 1) pdst[code >> 1] = k - t.row[v];
-      else psrc[code >> 1] = k - t.row[v];
-    }
-  // processing order per part: boundary vertices first (handed over early), then descending degree
-  // (lanes of a warp run slot loops of equal length); slot blocks are padded to an odd number of
-  // 16 B records so a warp's gathers spread over all banks
+    for (int k = t.row[v]; k < t.row[v] + nin[v]; ++k) pdst[t.inc[k] >> 1] = k - t.row[v];
+  // thread order per part: boundary vertices first (handed over early), then by descending in-degree
+  // (lanes of a warp run slot loops of equal length and, the degree being ~6, use equally many fast
+  // rows); slot blocks hold the target-role incidences followed by the out-edges beyond the
+  // FBG_FAST register rows, padded to an odd number of 16 B records (conflict-free gathers)
   std::vector<int> cnt(nper + 1, 0);
   for (int v = 0; v < V; ++v) cnt[part[v] + 1]++;
   for (int r = 0; r < nper; ++r) cnt[r + 1] += cnt[r];
@@ -469,84 +516,95 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
   for (int r = 0; r < nper; ++r) {
     std::sort(order.begin() + cnt[r], order.begin() + cnt[r + 1], [&](int u, int v) {
       if (bnd[u] != bnd[v]) return bnd[u] > bnd[v];
-      if (deg[u] != deg[v]) return deg[u] > deg[v];
+      if (nin[u] != nin[v]) return nin[u] > nin[v];
       return u < v;
     });
     int base = 0;
     for (int k = cnt[r]; k < cnt[r + 1]; ++k) {
       const int v = order[k];
+      const int nout = deg[v] - nin[v], novf = std::max(0, nout - FBG_FAST);
+      if (nin[v] > 255 || novf > 255) return false;
       lidx[v] = k - cnt[r];
       sbase[v] = base;
-      base += deg[v] | 1;
-      g.vplan[k] = make_int4(v, sbase[v], sbase[v] + deg[v], 0);
+      g.vplan[k] = make_int4(v, base | (nin[v] << 16) | (novf << 24), 0, 0);
+      base += (nin[v] + novf) | 1;
     }
     nslot[r] = base;
     const int nOwn = cnt[r + 1] - cnt[r];
-    if (nOwn > FBG_VPT * threads || base + 1 > 0xffff) return false;
+    if (nOwn > threads || base + 1 > 0xffff) return false;
     g.cinfo[3 * r].x = cnt[r];
     g.cinfo[3 * r].y = nOwn;
     g.cinfo[3 * r + 1].z = base;
     g.capSlot = std::max(g.capSlot, base);
   }
-  // edge lists per part: interior edges first, then cut edges (held by both sides)
-  std::vector<int> ecnt(nper + 1, 0);
-  for (int e = 0; e < E; ++e) {
-    const int ri = part[t.eij[e].x], rj = part[t.eij[e].y];
-    ecnt[ri + 1]++;
-    if (rj != ri) ecnt[rj + 1]++;
-  }
-  for (int r = 0; r < nper; ++r) ecnt[r + 1] += ecnt[r];
-  const int total = ecnt[nper];
-  g.eplan.assign(total, make_int2(0, 0));
-  g.eid.assign(total, 0);
-  std::vector<int> efill(ecnt.begin(), ecnt.begin() + nper);
-  std::vector<int> elist(total);
-  for (int pass = 0; pass < 2; ++pass)
-    for (int e = 0; e < E; ++e) {
-      const int ri = part[t.eij[e].x], rj = part[t.eij[e].y];
-      if ((ri != rj) != (pass == 1)) continue;
-      elist[efill[ri]++] = e;
-      if (rj != ri) elist[efill[rj]++] = e | (int)0x80000000;
-    }
-  std::vector<int> hidx(V, -1), hstamp(V, -1);
+  // halo entries and push lists: every remote endpoint of an edge touching the part
+  std::vector<int> hidx(V, -1), hstamp(V, -1), nh(nper, 0), hbeg(nper, 0);
+  std::vector<std::vector<int>> halo(nper);
   std::vector<std::vector<int4>> push(nper);  // per owner part: {owner-local vertex, consumer part, consumer entry}
-  for (int r = 0; r < nper; ++r) {
-    const int nOwn = cnt[r + 1] - cnt[r], nE = ecnt[r + 1] - ecnt[r];
-    if (nE > FBG_EPT * threads) return false;
-    const int hbeg = (int)g.hplan.size();
-    int nh = 0;
-    for (int k = ecnt[r]; k < ecnt[r + 1]; ++k) {
-      const int code = elist[k], e = code & 0x7fffffff;
-      const int i = t.eij[e].x, j = t.eij[e].y;
-      int b[2], sl[2];
-      const int end[2] = {i, j};
-      for (int side = 0; side < 2; ++side) {
-        const int v = end[side];
-        if (part[v] == r) {
-          b[side] = lidx[v];
-          sl[side] = sbase[v] + (side == 0 ? psrc[e] : pdst[e]);
-        } else {
-          if (hstamp[v] != r) {
-            hstamp[v] = r;
-            hidx[v] = nh++;
-            g.hplan.push_back(v);
-            push[part[v]].push_back(make_int4(lidx[v], r, nOwn + hidx[v], 0));
-          }
-          b[side] = nOwn + hidx[v];
-          sl[side] = nslot[r];  // dummy slot
-        }
-      }
-      if (nOwn + nh > 0xffff) return false;
-      g.eplan[k] = make_int2(b[0] | (b[1] << 16), sl[0] | (sl[1] << 16));
-      g.eid[k] = code;
-    }
-    g.cinfo[3 * r].z = ecnt[r];
-    g.cinfo[3 * r].w = nE;
-    g.cinfo[3 * r + 1].x = hbeg;
-    g.cinfo[3 * r + 1].y = nh;
-    g.capBar = std::max(g.capBar, nOwn + nh);
+  std::vector<std::vector<int>> gen(nper);    // generic edges per part: edge id | bit31 (no write-back)
+  // pass over the edges in ascending id: out-edges of a vertex arrive in ascending target order
+  std::vector<int> nfast(V, 0), novf_seen(V, 0);
+  // halo index lookup must be per part: first collect (part, vertex) pairs
+  for (int e = 0; e < E; ++e) {
+    const int i = t.eij[e].x, j = t.eij[e].y, ri = part[i], rj = part[j];
+    if (ri == rj) continue;
+    halo[ri].push_back(j);
+    halo[rj].push_back(i);
   }
-  // push lists (cluster transport): per owner part, grouped by vertex in processing order
+  std::vector<std::vector<std::pair<int, int>>> hmap(nper);  // sorted (vertex, halo index)
+  for (int r = 0; r < nper; ++r) {
+    std::vector<int>& h = halo[r];
+    std::sort(h.begin(), h.end());
+    h.erase(std::unique(h.begin(), h.end()), h.end());
+    const int nOwn = cnt[r + 1] - cnt[r];
+    if (nOwn + (int)h.size() > 0xffff) return false;
+    hbeg[r] = (int)g.hplan.size();
+    for (size_t k = 0; k < h.size(); ++k) {
+      g.hplan.push_back(h[k]);
+      push[part[h[k]]].push_back(make_int4(lidx[h[k]], r, nOwn + (int)k, 0));
+    }
+    nh[r] = (int)h.size();
+    g.cinfo[3 * r + 1].x = hbeg[r];
+    g.cinfo[3 * r + 1].y = nh[r];
+    g.capBar = std::max(g.capBar, nOwn + nh[r]);
+  }
+  auto entry = [&](int r, int v) -> int {  // s_bar entry of vertex v as seen from part r
+    if (part[v] == r) return lidx[v];
+    const std::vector<int>& h = halo[r];
+    return (cnt[r + 1] - cnt[r]) + (int)(std::lower_bound(h.begin(), h.end(), v) - h.begin());
+  };
+  std::vector<int2> gtmp_plan;
+  std::vector<std::vector<int2>> gpl(nper);
+  std::vector<std::vector<int>> gid(nper);
+  for (int e = 0; e < E; ++e) {
+    const int i = t.eij[e].x, j = t.eij[e].y, ri = part[i], rj = part[j];
+    // the copy in the source's part: a register row of i's thread, or (beyond FBG_FAST) a generic edge
+    const int sj_i = (rj == ri) ? sbase[j] + pdst[e] : nslot[ri];
+    const int bj_i = entry(ri, j);
+    if (nfast[i] < FBG_FAST) {
+      const size_t fi = (size_t)nfast[i] * V + cnt[ri] + lidx[i];
+      g.fplan[fi] = (uint32_t)bj_i | ((uint32_t)sj_i << 16);
+      g.feid[fi] = e;
+      nfast[i]++;
+    } else {
+      const int si = sbase[i] + nin[i] + novf_seen[i]++;
+      gpl[ri].push_back(make_int2(lidx[i] | (bj_i << 16), si | (sj_i << 16)));
+      gid[ri].push_back(e);
+    }
+    // cut edge: the copy in the target's part reads the source from the halo, feeds only the target
+    if (rj != ri) {
+      gpl[rj].push_back(make_int2(entry(rj, i) | (lidx[j] << 16), nslot[rj] | ((sbase[j] + pdst[e]) << 16)));
+      gid[rj].push_back(e | (int)0x80000000);
+    }
+  }
+  for (int r = 0; r < nper; ++r) {
+    if ((int)gpl[r].size() > threads) return false;
+    g.cinfo[3 * r].z = (int)g.gplan.size();
+    g.cinfo[3 * r].w = (int)gpl[r].size();
+    g.gplan.insert(g.gplan.end(), gpl[r].begin(), gpl[r].end());
+    g.geid.insert(g.geid.end(), gid[r].begin(), gid[r].end());
+  }
+  // push lists (cluster transport): per owner part, grouped by vertex in thread order
   for (int r = 0; r < nper; ++r) {
     std::vector<int4>& pl = push[r];
     std::stable_sort(pl.begin(), pl.end(), [](const int4& x, const int4& y) { return x.x < y.x; });
@@ -559,7 +617,7 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
         g.pplan.push_back(make_int2(pl[k].y, pl[k].z));
         ++k;
       }
-      g.vplan[cnt[r] + li].w = (int)(b | (k << 16));
+      g.vplan[cnt[r] + li].z = (int)(b | (k << 16));
     }
     g.cinfo[3 * r + 2].x = pbeg;
     g.cinfo[3 * r + 2].y = (int)pl.size();
@@ -576,7 +634,8 @@ static int grid_plan_init(fb_ctx* c) {
   c->gplan = P;
   P->topo.resize(c->S);
   const size_t S = c->S;
-  if (dalloc(&P->eplan, S * 2 * c->maxE) != cudaSuccess || dalloc(&P->eid, S * 2 * c->maxE) != cudaSuccess ||
+  if (dalloc(&P->fplan, S * FBG_FAST * c->maxV) != cudaSuccess || dalloc(&P->feid, S * FBG_FAST * c->maxV) != cudaSuccess ||
+      dalloc(&P->gplan, S * 2 * c->maxE) != cudaSuccess || dalloc(&P->geid, S * 2 * c->maxE) != cudaSuccess ||
       dalloc(&P->vplan, S * c->maxV) != cudaSuccess || dalloc(&P->hplan, S * 2 * c->maxE) != cudaSuccess ||
       dalloc(&P->pplan, S * 2 * c->maxE) != cudaSuccess ||
       dalloc(&P->cinfo, S * FBG_MAXP * 3) != cudaSuccess || dalloc(&P->pub, 2 * S * c->maxV) != cudaSuccess ||
@@ -607,7 +666,8 @@ static int grid_plan_set(fb_ctx* c, int s, int V, const float* pos) {
 static void grid_plan_free(fb_ctx* c) {
   GridPlan* P = c->gplan;
   if (!P) return;
-  cudaFree(P->eplan); cudaFree(P->eid); cudaFree(P->vplan); cudaFree(P->hplan); cudaFree(P->pplan);
+  cudaFree(P->fplan); cudaFree(P->feid); cudaFree(P->gplan); cudaFree(P->geid); cudaFree(P->vplan);
+  cudaFree(P->hplan); cudaFree(P->pplan);
   cudaFree(P->cinfo); cudaFree(P->pub);
   if (P->err) cudaFreeHost(P->err);
   delete P;
@@ -691,7 +751,7 @@ static int grid_prepare(fb_ctx* c, int iters, int only, int* nper_out, size_t* s
   // ---- cluster transport: the largest cluster size (<= 16) for which all active streams'
   // clusters are co-resident (one wave), never below ~128 vertices per CTA
   if (P->mode_env != 2) {
-    const int need = std::max(1, std::max(fb_div_up(maxV, FBG_VPT * FBG_THREADS_CL), fb_div_up(maxE + maxE / 8, FBG_EPT * FBG_THREADS_CL)));
+    const int need = std::max(1, fb_div_up(maxV + maxV / 16, FBG_THREADS_CL));
     int cmax = std::min(FBG_MAXC, std::max(need, maxV / 128));
     if (P->cluster_env > 0) cmax = std::max(need, P->cluster_env);
     for (int cand = std::min(cmax, FBG_MAXC); cand >= need && cand >= 1 && !cluster; --cand) {
@@ -731,7 +791,7 @@ static int grid_prepare(fb_ctx* c, int iters, int only, int* nper_out, size_t* s
       // never below ~96 vertices per part (the exchange then dominates), at least what the capacities need
       nper = std::min(budget / n_div, FBG_MAXP);
       nper = std::max(1, std::min(nper, std::max(1, maxV / (P->budget_env > 0 ? 16 : 96))));
-      const int need = std::max(fb_div_up(maxV, FBG_VPT * FBG_THREADS_L2), fb_div_up(maxE + maxE / 4, FBG_EPT * FBG_THREADS_L2));
+      const int need = fb_div_up(maxV + maxV / 16, FBG_THREADS_L2);
       nper = std::max(nper, need);
       bool ok = false;
       for (; nper * n_div <= budget && nper <= FBG_MAXP; nper += std::max(1, nper / 8))
@@ -757,12 +817,18 @@ static int grid_prepare(fb_ctx* c, int iters, int only, int* nper_out, size_t* s
     capPush = std::max(capPush, g.capPush);
     if (!g.dirty) continue;
     const size_t vb = (size_t)s * c->maxV, eb2 = (size_t)s * 2 * c->maxE;
-    if (g.eplan.size() > 2 * (size_t)c->maxE || g.hplan.size() > 2 * (size_t)c->maxE || g.pplan.size() > 2 * (size_t)c->maxE)
+    if (g.gplan.size() > 2 * (size_t)c->maxE || g.hplan.size() > 2 * (size_t)c->maxE || g.pplan.size() > 2 * (size_t)c->maxE)
       FB_FAIL(c, FB_E_NOMEM, "grid plan: tables exceed capacity");
-    FB_CUDA(c, cudaMemcpyAsync(P->vplan + vb, g.vplan.data(), sizeof(int4) * g.vplan.size(), cudaMemcpyHostToDevice, st));
-    if (!g.eplan.empty()) {
-      FB_CUDA(c, cudaMemcpyAsync(P->eplan + eb2, g.eplan.data(), sizeof(int2) * g.eplan.size(), cudaMemcpyHostToDevice, st));
-      FB_CUDA(c, cudaMemcpyAsync(P->eid + eb2, g.eid.data(), sizeof(int32_t) * g.eid.size(), cudaMemcpyHostToDevice, st));
+    const size_t Vs = g.vplan.size();
+    FB_CUDA(c, cudaMemcpyAsync(P->vplan + vb, g.vplan.data(), sizeof(int4) * Vs, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < FBG_FAST; ++k) {  // row-major on the device with the context's vertex capacity as stride
+      const size_t dv = ((size_t)s * FBG_FAST + k) * c->maxV;
+      FB_CUDA(c, cudaMemcpyAsync(P->fplan + dv, g.fplan.data() + k * Vs, sizeof(uint32_t) * Vs, cudaMemcpyHostToDevice, st));
+      FB_CUDA(c, cudaMemcpyAsync(P->feid + dv, g.feid.data() + k * Vs, sizeof(int32_t) * Vs, cudaMemcpyHostToDevice, st));
+    }
+    if (!g.gplan.empty()) {
+      FB_CUDA(c, cudaMemcpyAsync(P->gplan + eb2, g.gplan.data(), sizeof(int2) * g.gplan.size(), cudaMemcpyHostToDevice, st));
+      FB_CUDA(c, cudaMemcpyAsync(P->geid + eb2, g.geid.data(), sizeof(int32_t) * g.geid.size(), cudaMemcpyHostToDevice, st));
     }
     if (!g.hplan.empty())
       FB_CUDA(c, cudaMemcpyAsync(P->hplan + eb2, g.hplan.data(), sizeof(int32_t) * g.hplan.size(), cudaMemcpyHostToDevice, st));
@@ -798,7 +864,8 @@ static int solve_grid(fb_ctx* c, int iters, const fb_nltgv2_params* p, int nper,
   GridArgs a;
   a.g = graph_view(c);
   a.g.only = only;
-  a.eplan = P->eplan; a.eid = P->eid; a.vplan = P->vplan; a.hplan = P->hplan; a.pplan = P->pplan;
+  a.fplan = P->fplan; a.feid = P->feid; a.gplan = P->gplan; a.geid = P->geid;
+  a.vplan = P->vplan; a.hplan = P->hplan; a.pplan = P->pplan;
   a.cinfo = P->cinfo;
   a.pub = P->pub;
   a.err = P->err;
@@ -848,8 +915,8 @@ static int solve_grid(fb_ctx* c, int iters, const fb_nltgv2_params* p, int nper,
 // ---------------------------------------------------------------------------------- plan verifier
 // Host-only structural check of the variant-3 tables for one graph (no device needed): used by the
 // CPU test-suite to validate the partitioner against the invariants the kernel relies on.
-// stats[8] = {max own vertices, max edges per part, max halo, duplicated (cut) edges, max slots,
-//             shared memory bytes, boundary vertices, parts}.
+// stats[8] = {max own vertices, max generic edges per part, max halo, cut edges (held twice),
+//             max slots, shared memory bytes, boundary vertices, edges beyond the register rows}.
 static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int nper, int threads, size_t smem_limit,
                       int32_t* stats, std::string& why) {
   ClusterPlan::Topo t;
@@ -879,73 +946,134 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
     return 1;
   }
   std::vector<int> owner(V, -1), lidx(V, -1), written(E, 0);
-  int maxOwn = 0, maxEdge = 0, maxHalo = 0, dup = 0, maxSlot = 0, nb = 0;
+  int maxOwn = 0, maxGen = 0, maxHalo = 0, dup = 0, maxSlot = 0, nb = 0, novf = 0;
   for (int r = 0; r < nper; ++r) {
     const int4 c0 = g.cinfo[3 * r], c1 = g.cinfo[3 * r + 1];
+    if (c0.y > threads || c0.w > threads) { why = "part exceeds the CTA's thread count"; return 2; }
     for (int k = 0; k < c0.y; ++k) {
       const int4 pv = g.vplan[c0.x + k];
       if (pv.x < 0 || pv.x >= V || owner[pv.x] != -1) { why = "vertex owned twice or out of range"; return 2; }
       owner[pv.x] = r;
       lidx[pv.x] = k;
-      if (pv.z - pv.y != t.row[pv.x + 1] - t.row[pv.x]) { why = "slot block size != degree"; return 3; }
-      if (pv.z > c1.z) { why = "slot block beyond the part's slot count"; return 3; }
-      nb += ((uint32_t)pv.w >> 16) != ((uint32_t)pv.w & 0xffffu) ? 1 : 0;
+      const int s0 = pv.y & 0xffff, nt = (pv.y >> 16) & 0xff, no = (int)((uint32_t)pv.y >> 24);
+      int nin = 0;
+      for (int q = t.row[pv.x]; q < t.row[pv.x + 1]; ++q) nin += t.inc[q] & 1;
+      const int nout = t.row[pv.x + 1] - t.row[pv.x] - nin;
+      if (nt != nin || no != std::max(0, nout - FBG_FAST)) { why = "slot block does not match the in-degree / overflow"; return 3; }
+      if (s0 + nt + no > c1.z) { why = "slot block beyond the part's slot count"; return 3; }
+      nb += ((uint32_t)pv.z >> 16) != ((uint32_t)pv.z & 0xffffu) ? 1 : 0;
+      novf += no;
     }
     maxOwn = std::max(maxOwn, c0.y);
-    maxEdge = std::max(maxEdge, c0.w);
+    maxGen = std::max(maxGen, c0.w);
     maxHalo = std::max(maxHalo, c1.y);
     maxSlot = std::max(maxSlot, c1.z);
   }
   for (int v = 0; v < V; ++v)
     if (owner[v] < 0) { why = "vertex without owner"; return 2; }
+  // what an (entry, slot) pair must be for endpoint v of edge e seen from part r
+  auto check_end = [&](int r, int e, int v, bool is_target, int ovf_pos, int b, int sl, bool slot_used, int& code) -> bool {
+    const int4 c0 = g.cinfo[3 * r], c1 = g.cinfo[3 * r + 1];
+    if (owner[v] == r) {
+      if (b != lidx[v]) { code = 5; return false; }
+      if (!slot_used) return true;
+      const int4 pv = g.vplan[c0.x + lidx[v]];
+      const int s0 = pv.y & 0xffff, nt = (pv.y >> 16) & 0xff;
+      int want;
+      if (is_target) {  // position among the target-role incidences (CSR order)
+        int posn = -1;
+        for (int q = t.row[v]; q < t.row[v + 1]; ++q)
+          if (t.inc[q] == ((e << 1) | 1)) posn = q - t.row[v];
+        want = s0 + posn;
+        if (posn < 0 || posn >= nt) { code = 6; return false; }
+      } else {
+        want = s0 + nt + ovf_pos;
+      }
+      if (sl != want) { code = 6; return false; }
+    } else {
+      const int h = b - c0.y;
+      if (h < 0 || h >= c1.y || g.hplan[c1.x + h] != v) { code = 7; return false; }
+      if (slot_used && sl != c1.z) { code = 8; return false; }
+      // the owner's push list must name exactly this halo entry
+      const int4 pv = g.vplan[g.cinfo[3 * owner[v]].x + lidx[v]];
+      const int pbeg = g.cinfo[3 * owner[v] + 2].x;
+      bool found = false;
+      for (uint32_t q = (uint32_t)pv.z & 0xffffu; q < ((uint32_t)pv.z >> 16); ++q) {
+        const int2 pe = g.pplan[pbeg + q];
+        if (pe.x == r && pe.y == b) found = true;
+      }
+      if (!found) { code = 9; return false; }
+    }
+    return true;
+  };
+  static const char* msg[] = {"", "", "", "", "", "own endpoint index mismatch", "slot != block base + CSR position",
+                              "halo index mismatch", "remote endpoint must map to the dummy slot",
+                              "halo vertex not pushed/published by its owner"};
+  std::vector<std::vector<int>> hit(nper);
+  for (int r = 0; r < nper; ++r) hit[r].assign(g.cinfo[3 * r + 1].z + 1, 0);
+  // register rows: out-edges of each vertex in ascending edge id
+  for (int r = 0; r < nper; ++r) {
+    const int4 c0 = g.cinfo[3 * r];
+    for (int k = 0; k < c0.y; ++k) {
+      const int v = g.vplan[c0.x + k].x;
+      int nin = 0;
+      for (int q = t.row[v]; q < t.row[v + 1]; ++q) nin += t.inc[q] & 1;
+      const int nout = t.row[v + 1] - t.row[v] - nin;
+      for (int f = 0; f < FBG_FAST; ++f) {
+        const size_t fi = (size_t)f * V + c0.x + k;
+        const int e = g.feid[fi];
+        if (f >= nout) {
+          if (e != -1) { why = "register row beyond the out-degree must be idle"; return 15; }
+          continue;
+        }
+        const int want_e = t.inc[t.row[v] + nin + f] >> 1;  // f-th source-role incidence
+        if (e != want_e) { why = "register rows must hold the out-edges in ascending edge id"; return 15; }
+        const int j = t.eij[e].y;
+        const int b = (int)(g.fplan[fi] & 0xffffu), sl = (int)(g.fplan[fi] >> 16);
+        int code = 0;
+        if (!check_end(r, e, j, true, 0, b, sl, true, code)) { why = msg[code]; return code; }
+        if (owner[j] == r) hit[r][sl]++;
+        written[e]++;
+      }
+    }
+  }
+  // generic edges
+  std::vector<int> ovf_seen(V, 0);
   for (int r = 0; r < nper; ++r) {
     const int4 c0 = g.cinfo[3 * r], c1 = g.cinfo[3 * r + 1];
-    std::vector<int> hit(c1.z + 1, 0);
     for (int k = 0; k < c0.w; ++k) {
-      const int code = g.eid[c0.z + k], e = code & 0x7fffffff;
+      const int code_e = g.geid[c0.z + k], e = code_e & 0x7fffffff;
       if (e >= E) { why = "edge id out of range"; return 4; }
-      const int2 pl = g.eplan[c0.z + k];
-      const int end[2] = {t.eij[e].x, t.eij[e].y};
-      const int b[2] = {pl.x & 0xffff, (int)((uint32_t)pl.x >> 16)};
-      const int sl[2] = {pl.y & 0xffff, (int)((uint32_t)pl.y >> 16)};
-      bool any_own = false;
-      for (int side = 0; side < 2; ++side) {
-        const int v = end[side];
-        if (owner[v] == r) {
-          any_own = true;
-          if (b[side] != lidx[v]) { why = "own endpoint index mismatch"; return 5; }
-          // slot = block base + CSR position of this incidence
-          const int4 pv = g.vplan[c0.x + lidx[v]];
-          int posn = -1;
-          for (int q = t.row[v]; q < t.row[v + 1]; ++q)
-            if (t.inc[q] == ((e << 1) | side)) posn = q - t.row[v];
-          if (posn < 0 || sl[side] != pv.y + posn) { why = "slot != base + CSR position"; return 6; }
-          hit[sl[side]]++;
-        } else {
-          const int h = b[side] - c0.y;
-          if (h < 0 || h >= c1.y || g.hplan[c1.x + h] != v) { why = "halo index mismatch"; return 7; }
-          if (sl[side] != c1.z) { why = "remote endpoint must map to the dummy slot"; return 8; }
-          // the owner's push list must name exactly this halo entry
-          const int4 pv = g.vplan[g.cinfo[3 * owner[v]].x + lidx[v]];
-          const int pbeg = g.cinfo[3 * owner[v] + 2].x;
-          bool found = false;
-          for (uint32_t q = (uint32_t)pv.w & 0xffffu; q < ((uint32_t)pv.w >> 16); ++q) {
-            const int2 pe = g.pplan[pbeg + q];
-            if (pe.x == r && pe.y == b[side]) found = true;
-          }
-          if (!found) { why = "halo vertex not pushed/published by its owner"; return 9; }
-        }
+      const int2 pl = g.gplan[c0.z + k];
+      const int i = t.eij[e].x, j = t.eij[e].y;
+      const int bi = pl.x & 0xffff, bj = (int)((uint32_t)pl.x >> 16), si = pl.y & 0xffff, sj = (int)((uint32_t)pl.y >> 16);
+      const bool wb = code_e >= 0;
+      int code = 0;
+      if (wb) {  // overflowed out-edge of an own vertex
+        if (owner[i] != r) { why = "write-back copy must live with the source vertex"; return 11; }
+        if (!check_end(r, e, i, false, ovf_seen[i], bi, si, true, code)) { why = msg[code]; return code; }
+        ovf_seen[i]++;
+        hit[r][si]++;
+        if (!check_end(r, e, j, true, 0, bj, sj, true, code)) { why = msg[code]; return code; }
+        if (owner[j] == r) hit[r][sj]++;
+        written[e]++;
+      } else {  // cut edge seen from the target's part
+        if (owner[j] != r || owner[i] == r) { why = "non-write-back copy must be a cut edge in the target's part"; return 11; }
+        if (!check_end(r, e, i, false, 0, bi, si, true, code)) { why = msg[code]; return code; }
+        if (!check_end(r, e, j, true, 0, bj, sj, true, code)) { why = msg[code]; return code; }
+        hit[r][sj]++;
+        ++dup;
       }
-      if (!any_own) { why = "edge without an own endpoint"; return 10; }
-      const bool wb = code >= 0;
-      if (wb != (owner[end[0]] == r)) { why = "write-back copy must live with the source vertex"; return 11; }
-      if (wb) written[e]++;
-      else ++dup;
+      (void)c1;
     }
+  }
+  for (int r = 0; r < nper; ++r) {
+    const int4 c0 = g.cinfo[3 * r];
     for (int k = 0; k < c0.y; ++k) {
       const int4 pv = g.vplan[c0.x + k];
-      for (int q = pv.y; q < pv.z; ++q)
-        if (hit[q] != 1) { why = "slot not written exactly once"; return 12; }
+      const int s0 = pv.y & 0xffff, n = ((pv.y >> 16) & 0xff) + (int)((uint32_t)pv.y >> 24);
+      for (int q = s0; q < s0 + n; ++q)
+        if (hit[r][q] != 1) { why = "slot not written exactly once"; return 12; }
     }
   }
   for (int e = 0; e < E; ++e)
@@ -956,8 +1084,8 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
     if (np != nh || np != g.pplan.size()) { why = "push lists and halo lists differ in size"; return 14; }
   }
   if (stats) {
-    stats[0] = maxOwn; stats[1] = maxEdge; stats[2] = maxHalo; stats[3] = dup; stats[4] = maxSlot;
-    stats[5] = (int32_t)fbg_smem_bytes(g.capBar, g.capSlot, g.capPush); stats[6] = nb; stats[7] = nper;
+    stats[0] = maxOwn; stats[1] = maxGen; stats[2] = maxHalo; stats[3] = dup; stats[4] = maxSlot;
+    stats[5] = (int32_t)fbg_smem_bytes(g.capBar, g.capSlot, g.capPush); stats[6] = nb; stats[7] = novf;
   }
   return 0;
 }

@@ -315,11 +315,12 @@ int64_t fb_launch_count(const fb_ctx* ctx);
 /* Host-only self-check of the variant-3 partitioner (no device, no context): cuts the graph into
  * `parts` CTAs' worth of tables (cluster != 0: capacities of the cluster transport, parts <= 16;
  * else of the L2 transport) and verifies the invariants the kernel relies on (every vertex owned
- * once, every incidence slot written exactly once in CSR order, halo vertices published by their
+ * once, register rows holding each vertex's out-edges in ascending edge id, every slot written
+ * exactly once in CSR order, halo vertices published by their
  * and pushed by their owners, every edge written back exactly once).  0 = OK, 1 = does not fit this part count, other
  * > 0 = violated invariant (fb_last_error(NULL) says which), < 0 = bad argument.
- * stats[8] (optional) = {max own vertices, max edges, max halo, duplicated edges, max slots,
- * shared-memory bytes, boundary vertices, parts}. */
+ * stats[8] (optional) = {max own vertices, max generic edges per part, max halo, cut edges (held by
+ * both sides), max slots, shared-memory bytes, boundary vertices, out-edges beyond the register rows}. */
 int fb_grid_plan_verify(int V, int E, const float* pos, const int32_t* ij, int parts, int cluster,
                         int32_t* stats);
 /* Which solver variant the last fb_nltgv2_solve used (1, 2 or 3). */

@@ -62,7 +62,7 @@ def test_c4_graph_parity_100_iters(capi, oracle, variant):
 
 
 @pytest.mark.parametrize("mode,knob,val,transport", [("l2", "FB_GRID_CTAS", "7", 2), ("l2", "FB_GRID_CTAS", "40", 2),
-                                                     ("l2", "FB_GRID_CTAS", "75", 2), ("cluster", "FB_GRID_CLUSTER", "2", 1),
+                                                     ("l2", "FB_GRID_CTAS", "75", 2), ("cluster", "FB_GRID_CLUSTER", "3", 1),
                                                      ("cluster", "FB_GRID_CLUSTER", "5", 1), ("cluster", "FB_GRID_CLUSTER", "8", 1),
                                                      ("cluster", "FB_GRID_CLUSTER", "16", 1)])
 def test_grid_solver_is_partition_and_transport_invariant(capi, oracle, mode, knob, val, transport, monkeypatch):

@@ -13,44 +13,62 @@ def test_small_graph_tables(capi, parts):
     g = small_graph()
     rc, st = capi.grid_plan_verify(g["pos"], g["edges"], parts)
     assert rc == 0
-    assert st["parts"] == parts
     if parts == 1:
-        assert st["dup_edges"] == 0 and st["max_halo"] == 0 and st["boundary"] == 0
+        assert st["cut_edges"] == 0 and st["max_halo"] == 0 and st["boundary"] == 0
     else:
-        assert st["dup_edges"] > 0 and st["max_halo"] > 0
+        assert st["cut_edges"] > 0 and st["max_halo"] > 0
 
 
 @pytest.mark.parametrize("parts", [1, 2, 5, 16])
 def test_small_graph_tables_cluster_transport(capi, parts):
     g = small_graph(20, 15, 160, 120, seed=9)
     rc, st = capi.grid_plan_verify(g["pos"], g["edges"], parts, cluster=True)
-    assert rc == 0 and st["parts"] == parts
+    assert rc == 0
 
 
-@pytest.mark.parametrize("cfg,parts,cluster", [("C2", 18, False), ("C2", 37, False), ("C2", 52, False),
+@pytest.mark.parametrize("cfg,parts,cluster", [("C2", 24, False), ("C2", 37, False), ("C2", 52, False),
                                                ("C4", 148, False), ("C4", 296, False),
-                                               ("C2", 8, True), ("C2", 10, True), ("C2", 16, True)])
+                                               ("C2", 10, True), ("C2", 12, True), ("C2", 16, True)])
 def test_benchmark_graph_tables(capi, cfg, parts, cluster):
     g = synth.s_graph(cfg)
     V, E = len(g["pos"]), len(g["edges"])
     rc, st = capi.grid_plan_verify(g["pos"], g["edges"], parts, cluster)
     assert rc == 0
     if cluster:
-        assert st["max_edges"] <= 2048 and st["max_own"] <= 1024 and st["smem_bytes"] <= 200 * 1024
+        assert st["max_generic"] <= 512 and st["max_own"] <= 512 and st["smem_bytes"] <= 200 * 1024
         return
     # compact parts: the cut stays a small fraction of the edges, the load is balanced
-    assert st["dup_edges"] < 0.35 * E
+    assert st["cut_edges"] < 0.35 * E
     assert st["max_own"] <= 1.35 * V / parts + 8
-    assert st["max_edges"] <= 1024 and st["max_own"] <= 512 and st["smem_bytes"] <= 100 * 1024
+    assert st["max_generic"] <= 256 and st["max_own"] <= 256 and st["smem_bytes"] <= 100 * 1024
+    assert st["overflow_edges"] < 0.05 * E   # raster-ordered vertices: out-degree ~3
 
 
 def test_too_few_parts_is_reported_not_mangled(capi):
     g = synth.s_graph("C2")
-    rc, _ = capi.grid_plan_verify(g["pos"], g["edges"], 4)   # 1250 vertices per part > 512
+    rc, _ = capi.grid_plan_verify(g["pos"], g["edges"], 4)   # 1250 vertices per part > 256
     assert rc == 1
     g4 = synth.s_graph("C4")
     rc, _ = capi.grid_plan_verify(g4["pos"], g4["edges"], 16, cluster=True)   # 20k vertices need > 16 CTAs
     assert rc == 1
+
+
+def test_shuffled_vertex_ids_use_overflow_slots(capi):
+    """Vertex ids in random order: out-degrees spread over 0..deg, edges beyond the FBG_FAST register
+    rows of a vertex go to generic edges with their own slots -- the invariants must still hold."""
+    g = small_graph(30, 24, 240, 192, seed=4)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(len(g["pos"]))
+    pos = g["pos"][perm]
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    e = inv[g["edges"]]
+    e = np.sort(e, axis=1)
+    e = e[np.lexsort((e[:, 1], e[:, 0]))].astype(np.int32)
+    for parts, cluster in ((2, True), (4, True), (9, False)):
+        rc, st = capi.grid_plan_verify(pos, e, parts, cluster)
+        assert rc == 0
+        assert st["overflow_edges"] > 0
 
 
 def test_degenerate_graphs(capi):
