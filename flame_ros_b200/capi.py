@@ -208,13 +208,14 @@ def grid_plan_verify(pos, edges, parts, cluster=False):
     lib = load_library()
     pos = _f32(pos)
     edges = np.ascontiguousarray(edges, np.int32).reshape(-1, 2)
-    stats = np.zeros(8, np.int32)
+    stats = np.zeros(12, np.int32)
     rc = lib.fb_grid_plan_verify(pos.shape[0], edges.shape[0], _ptr(pos), _ptr(edges), int(parts), int(bool(cluster)), _ptr(stats))
     if rc < 0:
         raise FlameError("fb_grid_plan_verify: bad argument")
     if rc > 1:
         raise FlameError(lib.fb_last_error(None).decode())
-    keys = ("max_own", "max_generic", "max_halo", "cut_edges", "max_slots", "smem_bytes", "boundary", "overflow_edges")
+    keys = ("max_own", "max_generic", "max_halo", "cut_edges", "max_slots", "smem_bytes", "boundary", "overflow_edges",
+            "wavefronts_ideal", "wavefronts_load", "wavefronts_store", "reserved")
     return rc, dict(zip(keys, stats.tolist()))
 
 

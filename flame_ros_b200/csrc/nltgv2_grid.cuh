@@ -160,28 +160,66 @@ struct FbgGen {  // register-resident generic edge (both endpoints through share
   uint32_t bar, slot;  // (bi, bj) and (si, sj), 16 bits each
 };
 
-// Dual half-step of the first R out-edges of the thread's vertex.  The source's extragradient point
-// is in registers; only the target's is read from shared memory, only the target's contribution is
-// written to a slot (the source's is re-derived from q in the primal half-step).  Stores are
-// unconditional: idle rows and remote targets write to the dummy slot, so the R rows are
-// independent branch-free instruction streams.
-template <int R>
-__device__ __forceinline__ void fbg_dual_fast(FbgFast& F, float xb, float w1b, float w2b, uint32_t bar_rd,
-                                              uint32_t slot_base, float sigma) {
+// Dual half-step of one thread: the first R out-edges of its vertex (register rows) and, when GEN,
+// its generic edge.  For an out-edge the source's extragradient point is in registers; only the
+// target's is read from shared memory, only the target's contribution is written to a slot (the
+// source's is re-derived from q in the primal half-step).  All loads are issued before the first
+// dependent instruction and the stores are unconditional (idle rows and remote targets write to the
+// dummy slot), so the rows are independent branch-free instruction streams that overlap.
+template <int R, bool GEN>
+__device__ __forceinline__ void fbg_dual(FbgFast& F, FbgGen& G, float xb, float w1b, float w2b, uint32_t bar_rd,
+                                         uint32_t slot_base, float sigma) {
+  float4 bj[R > 0 ? R : 1], gi, gj;
+#pragma unroll
+  for (int k = 0; k < R; ++k) bj[k] = fbc_lds(bar_rd + ((F.idx[k] & 0xffffu) << 4));
+  if (GEN) {
+    gi = fbc_lds(bar_rd + ((G.bar & 0xffffu) << 4));
+    gj = fbc_lds(bar_rd + ((G.bar >> 16) << 4));
+  }
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    const float4 bj = fbc_lds(bar_rd + ((F.idx[k] & 0xffffu) << 4));
-    float t = xb - bj.x;
+    float t = xb - bj[k].x;
     t = fmaf(-F.dx[k], w1b, t);
     t = fmaf(-F.dy[k], w2b, t);
     const float k1 = F.a[k] * t;
-    const float k2 = F.b[k] * (w1b - bj.y);
-    const float k3 = F.b[k] * (w2b - bj.z);
+    const float k2 = F.b[k] * (w1b - bj[k].y);
+    const float k3 = F.b[k] * (w2b - bj[k].z);
     F.q1[k] = fb_clamp1(fmaf(sigma, k1, F.q1[k]));
     F.q2[k] = fb_clamp1(fmaf(sigma, k2, F.q2[k]));
     F.q3[k] = fb_clamp1(fmaf(sigma, k3, F.q3[k]));
+  }
+  if (GEN) {  // the source is remote (cut edge seen from the target's CTA) or beyond the register rows
+    float t = gi.x - gj.x;
+    t = fmaf(-G.dx, gi.y, t);
+    t = fmaf(-G.dy, gi.z, t);
+    const float k1 = G.a * t;
+    const float k2 = G.b * (gi.y - gj.y);
+    const float k3 = G.b * (gi.z - gj.z);
+    G.q1 = fb_clamp1(fmaf(sigma, k1, G.q1));
+    G.q2 = fb_clamp1(fmaf(sigma, k2, G.q2));
+    G.q3 = fb_clamp1(fmaf(sigma, k3, G.q3));
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
     const float a1 = F.a[k] * F.q1[k];
     fbc_sts(slot_base + ((F.idx[k] >> 16) << 4), make_float4(-a1, -(F.b[k] * F.q2[k]), -(F.b[k] * F.q3[k]), 0.f));
+  }
+  if (GEN) {
+    const float a1 = G.a * G.q1;
+    fbc_sts(slot_base + ((G.slot & 0xffffu) << 4),
+            make_float4(a1, fmaf(G.b, G.q2, -(G.dx * a1)), fmaf(G.b, G.q3, -(G.dy * a1)), 0.f));
+    fbc_sts(slot_base + ((G.slot >> 16) << 4), make_float4(-a1, -(G.b * G.q2), -(G.b * G.q3), 0.f));
+  }
+}
+template <bool GEN>
+__device__ __forceinline__ void fbg_dual_rows(int rows, FbgFast& F, FbgGen& G, float xb, float w1b, float w2b,
+                                              uint32_t bar_rd, uint32_t slot_base, float sigma) {
+  switch (rows) {  // warp-uniform
+    case 0: fbg_dual<0, GEN>(F, G, xb, w1b, w2b, bar_rd, slot_base, sigma); break;
+    case 1: fbg_dual<1, GEN>(F, G, xb, w1b, w2b, bar_rd, slot_base, sigma); break;
+    case 2: fbg_dual<2, GEN>(F, G, xb, w1b, w2b, bar_rd, slot_base, sigma); break;
+    case 3: fbg_dual<3, GEN>(F, G, xb, w1b, w2b, bar_rd, slot_base, sigma); break;
+    default: fbg_dual<FBG_FAST, GEN>(F, G, xb, w1b, w2b, bar_rd, slot_base, sigma); break;
   }
 }
 
@@ -325,30 +363,8 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     // every thread is past the wait: the barrier of this parity is re-armed for iteration it+2
     if (CLUSTER && tid == 0 && nHalo && it > 0 && it + 2 < iters) fbc_mbar_expect(mb0 + 8u * (uint32_t)(it & 1), haloBytes);
     // ---- dual half-step ---------------------------------------------------------------------------
-    switch (rowsF) {
-      case 0: break;
-      case 1: fbg_dual_fast<1>(F, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma); break;
-      case 2: fbg_dual_fast<2>(F, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma); break;
-      case 3: fbg_dual_fast<3>(F, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma); break;
-      default: fbg_dual_fast<FBG_FAST>(F, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma); break;
-    }
-    if (warpG) {  // generic edges: the source is remote (cut edge seen from the target's CTA) or overflowed
-      const float4 bi = fbc_lds(bar_base + rd_off + ((G.bar & 0xffffu) << 4));
-      const float4 bj = fbc_lds(bar_base + rd_off + ((G.bar >> 16) << 4));
-      float t = bi.x - bj.x;
-      t = fmaf(-G.dx, bi.y, t);
-      t = fmaf(-G.dy, bi.z, t);
-      const float k1 = G.a * t;
-      const float k2 = G.b * (bi.y - bj.y);
-      const float k3 = G.b * (bi.z - bj.z);
-      G.q1 = fb_clamp1(fmaf(sigma, k1, G.q1));
-      G.q2 = fb_clamp1(fmaf(sigma, k2, G.q2));
-      G.q3 = fb_clamp1(fmaf(sigma, k3, G.q3));
-      const float a1 = G.a * G.q1;
-      fbc_sts(slot_base + ((G.slot & 0xffffu) << 4),
-              make_float4(a1, fmaf(G.b, G.q2, -(G.dx * a1)), fmaf(G.b, G.q3, -(G.dy * a1)), 0.f));
-      fbc_sts(slot_base + ((G.slot >> 16) << 4), make_float4(-a1, -(G.b * G.q2), -(G.b * G.q3), 0.f));
-    }
+    if (warpG) fbg_dual_rows<true>(rowsF, F, G, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma);
+    else fbg_dual_rows<false>(rowsF, F, G, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma);
     __syncthreads();  // slots complete
     // ---- primal half-step: CSR order = target-role slots, own out-edges, overflow slots -----------
     if (warpV) {
@@ -500,10 +516,11 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
     if (part[t.eij[e].x] != part[t.eij[e].y]) bnd[t.eij[e].x] = bnd[t.eij[e].y] = 1;
   for (int v = 0; v < V; ++v)
     for (int k = t.row[v]; k < t.row[v] + nin[v]; ++k) pdst[t.inc[k] >> 1] = k - t.row[v];
-  // thread order per part: boundary vertices first (handed over early), then by descending in-degree
-  // (lanes of a warp run slot loops of equal length and, the degree being ~6, use equally many fast
-  // rows); slot blocks hold the target-role incidences followed by the out-edges beyond the
-  // FBG_FAST register rows, padded to an odd number of 16 B records (conflict-free gathers)
+  // thread order per part: raster order over strips about one vertex spacing high, so the lanes of
+  // a quarter-warp hold neighbouring vertices and the k-th out-edges of those lanes point at
+  // neighbouring entries / slot blocks (few shared-memory bank conflicts on the target side);
+  // slot blocks hold the target-role incidences followed by the out-edges beyond the FBG_FAST
+  // register rows, padded to an odd number of 16 B records (conflict-free gathers)
   std::vector<int> cnt(nper + 1, 0);
   for (int v = 0; v < V; ++v) cnt[part[v] + 1]++;
   for (int r = 0; r < nper; ++r) cnt[r + 1] += cnt[r];
@@ -512,13 +529,25 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
     std::vector<int> fill(cnt.begin(), cnt.begin() + nper);
     for (int v = 0; v < V; ++v) order[fill[part[v]]++] = v;
   }
-  std::vector<int> lidx(V), sbase(V), nslot(nper, 0);
+  std::vector<int> lidx(V), sbase(V), nslot(nper, 0), strip(V, 0);
   for (int r = 0; r < nper; ++r) {
-    std::sort(order.begin() + cnt[r], order.begin() + cnt[r + 1], [&](int u, int v) {
-      if (bnd[u] != bnd[v]) return bnd[u] > bnd[v];
-      if (nin[u] != nin[v]) return nin[u] > nin[v];
-      return u < v;
-    });
+    {
+      float x0 = 1e30f, x1 = -1e30f, y0 = 1e30f, y1 = -1e30f;
+      for (int k = cnt[r]; k < cnt[r + 1]; ++k) {
+        const float2 p = g.pos[order[k]];
+        x0 = std::min(x0, p.x); x1 = std::max(x1, p.x);
+        y0 = std::min(y0, p.y); y1 = std::max(y1, p.y);
+      }
+      const int n = cnt[r + 1] - cnt[r];
+      const float area = std::max(1e-6f, (x1 - x0) * (y1 - y0));
+      const float hstrip = std::max(1e-3f, sqrtf(area / std::max(1, n)));
+      for (int k = cnt[r]; k < cnt[r + 1]; ++k) strip[order[k]] = (int)((g.pos[order[k]].y - y0) / hstrip);
+      std::sort(order.begin() + cnt[r], order.begin() + cnt[r + 1], [&](int u, int v) {
+        if (strip[u] != strip[v]) return strip[u] < strip[v];
+        if (g.pos[u].x != g.pos[v].x) return g.pos[u].x < g.pos[v].x;
+        return u < v;
+      });
+    }
     int base = 0;
     for (int k = cnt[r]; k < cnt[r + 1]; ++k) {
       const int v = order[k];
@@ -538,10 +567,9 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
     g.capSlot = std::max(g.capSlot, base);
   }
   // halo entries and push lists: every remote endpoint of an edge touching the part
-  std::vector<int> hidx(V, -1), hstamp(V, -1), nh(nper, 0), hbeg(nper, 0);
+  std::vector<int> nh(nper, 0), hbeg(nper, 0);
   std::vector<std::vector<int>> halo(nper);
   std::vector<std::vector<int4>> push(nper);  // per owner part: {owner-local vertex, consumer part, consumer entry}
-  std::vector<std::vector<int>> gen(nper);    // generic edges per part: edge id | bit31 (no write-back)
   // pass over the edges in ascending id: out-edges of a vertex arrive in ascending target order
   std::vector<int> nfast(V, 0), novf_seen(V, 0);
   // halo index lookup must be per part: first collect (part, vertex) pairs
@@ -573,7 +601,6 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
     const std::vector<int>& h = halo[r];
     return (cnt[r + 1] - cnt[r]) + (int)(std::lower_bound(h.begin(), h.end(), v) - h.begin());
   };
-  std::vector<int2> gtmp_plan;
   std::vector<std::vector<int2>> gpl(nper);
   std::vector<std::vector<int>> gid(nper);
   for (int e = 0; e < E; ++e) {
@@ -751,7 +778,7 @@ static int grid_prepare(fb_ctx* c, int iters, int only, int* nper_out, size_t* s
   // ---- cluster transport: the largest cluster size (<= 16) for which all active streams'
   // clusters are co-resident (one wave), never below ~128 vertices per CTA
   if (P->mode_env != 2) {
-    const int need = std::max(1, fb_div_up(maxV + maxV / 16, FBG_THREADS_CL));
+    const int need = std::max(1, fb_div_up(maxV, FBG_THREADS_CL));
     int cmax = std::min(FBG_MAXC, std::max(need, maxV / 128));
     if (P->cluster_env > 0) cmax = std::max(need, P->cluster_env);
     for (int cand = std::min(cmax, FBG_MAXC); cand >= need && cand >= 1 && !cluster; --cand) {
@@ -791,7 +818,7 @@ static int grid_prepare(fb_ctx* c, int iters, int only, int* nper_out, size_t* s
       // never below ~96 vertices per part (the exchange then dominates), at least what the capacities need
       nper = std::min(budget / n_div, FBG_MAXP);
       nper = std::max(1, std::min(nper, std::max(1, maxV / (P->budget_env > 0 ? 16 : 96))));
-      const int need = fb_div_up(maxV + maxV / 16, FBG_THREADS_L2);
+      const int need = fb_div_up(maxV, FBG_THREADS_L2);
       nper = std::max(nper, need);
       bool ok = false;
       for (; nper * n_div <= budget && nper <= FBG_MAXP; nper += std::max(1, nper / 8))
@@ -1083,7 +1110,36 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
     for (int r = 0; r < nper; ++r) { np += g.cinfo[3 * r + 2].y; nh += g.cinfo[3 * r + 1].y; }
     if (np != nh || np != g.pplan.size()) { why = "push lists and halo lists differ in size"; return 14; }
   }
+  // shared-memory wavefronts of the register rows' target-side accesses (LDS.128 of the target's
+  // point, STS.128 of its contribution): a quarter-warp (8 lanes x 16 B) is one wavefront when its
+  // lanes touch 8 different 16-byte bank groups (equal addresses broadcast / merge)
+  long long wf_ideal = 0, wf_ld = 0, wf_st = 0;
+  for (int r = 0; r < nper; ++r) {
+    const int4 c0 = g.cinfo[3 * r];
+    for (int f = 0; f < FBG_FAST; ++f)
+      for (int q0 = 0; q0 < c0.y; q0 += 8) {
+        int cl[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int seen_l[8], seen_s[8], nl = 0, ns = 0;
+        bool any = false;
+        for (int k = q0; k < std::min(q0 + 8, c0.y); ++k) {
+          const size_t fi = (size_t)f * V + c0.x + k;
+          if (g.feid[fi] < 0) continue;
+          any = true;
+          const int b = (int)(g.fplan[fi] & 0xffffu), sl = (int)(g.fplan[fi] >> 16);
+          bool dup_l = false, dup_s = false;
+          for (int m = 0; m < nl; ++m) dup_l |= seen_l[m] == b;
+          for (int m = 0; m < ns; ++m) dup_s |= seen_s[m] == sl;
+          if (!dup_l) { seen_l[nl++] = b; cl[b & 7]++; }
+          if (!dup_s) { seen_s[ns++] = sl; cs[sl & 7]++; }
+        }
+        if (!any) continue;
+        wf_ideal++;
+        wf_ld += *std::max_element(cl, cl + 8);
+        wf_st += *std::max_element(cs, cs + 8);
+      }
+  }
   if (stats) {
+    stats[8] = (int32_t)wf_ideal; stats[9] = (int32_t)wf_ld; stats[10] = (int32_t)wf_st; stats[11] = 0;
     stats[0] = maxOwn; stats[1] = maxGen; stats[2] = maxHalo; stats[3] = dup; stats[4] = maxSlot;
     stats[5] = (int32_t)fbg_smem_bytes(g.capBar, g.capSlot, g.capPush); stats[6] = nb; stats[7] = novf;
   }

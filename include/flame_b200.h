@@ -319,8 +319,9 @@ int64_t fb_launch_count(const fb_ctx* ctx);
  * exactly once in CSR order, halo vertices published by their
  * and pushed by their owners, every edge written back exactly once).  0 = OK, 1 = does not fit this part count, other
  * > 0 = violated invariant (fb_last_error(NULL) says which), < 0 = bad argument.
- * stats[8] (optional) = {max own vertices, max generic edges per part, max halo, cut edges (held by
- * both sides), max slots, shared-memory bytes, boundary vertices, out-edges beyond the register rows}. */
+ * stats[12] (optional) = {max own vertices, max generic edges per part, max halo, cut edges (held by
+ * both sides), max slots, shared-memory bytes, boundary vertices, out-edges beyond the register rows, ideal / estimated
+ * load / estimated store shared-memory wavefronts of the register rows' target-side accesses, 0}. */
 int fb_grid_plan_verify(int V, int E, const float* pos, const int32_t* ij, int parts, int cluster,
                         int32_t* stats);
 /* Which solver variant the last fb_nltgv2_solve used (1, 2 or 3). */

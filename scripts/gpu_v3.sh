@@ -12,18 +12,12 @@ except Exception as e:
 "
 }
 B="--steps 100 --no-single --no-cpu-baseline"
-timeout 200 python bench.py --streams 1 --variant 2 $B 2>/tmp/err.txt | line "S=1 v2"; tail -2 /tmp/err.txt
 timeout 200 python bench.py --streams 1 --variant 3 $B 2>/tmp/err.txt | line "S=1 v3 auto"; tail -2 /tmp/err.txt
-FB_GRID_CLUSTER=10 timeout 200 python bench.py --streams 1 --variant 3 $B 2>/tmp/err.txt | line "S=1 v3 cluster=10"; tail -2 /tmp/err.txt
 FB_GRID_MODE=l2 timeout 200 python bench.py --streams 1 --variant 3 $B 2>/tmp/err.txt | line "S=1 v3 L2"; tail -2 /tmp/err.txt
-timeout 200 python bench.py --streams 8 --variant 2 $B 2>/tmp/err.txt | line "S=8 v2"; tail -2 /tmp/err.txt
 timeout 200 python bench.py --streams 8 --variant 3 $B 2>/tmp/err.txt | line "S=8 v3 auto"; tail -2 /tmp/err.txt
-for C in 12 14 16; do
-FB_GRID_CLUSTER=$C timeout 200 python bench.py --streams 8 --variant 3 $B 2>/tmp/err.txt | line "S=8 v3 cluster=$C"; tail -2 /tmp/err.txt
-done
 FB_GRID_MODE=l2 timeout 200 python bench.py --streams 8 --variant 3 $B 2>/tmp/err.txt | line "S=8 v3 L2"; tail -2 /tmp/err.txt
-timeout 200 python bench.py --streams 15 --variant 3 $B 2>/tmp/err.txt | line "S=15 v3 auto"; tail -2 /tmp/err.txt
-timeout 200 python bench.py --streams 32 --variant 3 $B 2>/tmp/err.txt | line "S=32 v3 auto (waves)"; tail -2 /tmp/err.txt
+timeout 200 python bench.py --streams 11 --variant 3 $B 2>/tmp/err.txt | line "S=11 v3 auto"; tail -2 /tmp/err.txt
+timeout 200 python bench.py --streams 14 --variant 3 $B 2>/tmp/err.txt | line "S=14 v3 auto"; tail -2 /tmp/err.txt
 timeout 300 python bench.py --config C4 --streams 1 --variant 3 --steps 40 --warmup 5 --no-single --no-cpu-baseline 2>/tmp/err.txt | line "C4 v3"; tail -2 /tmp/err.txt
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_nltgv2_grid -s 3 -c 1 -o gpurun_out/prof_grid_r1_v3 python bench.py --steps 6 --warmup 3 --variant 3 --no-single --no-cpu-baseline > gpurun_out/ncu_grid.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_nltgv2_grid -s 3 -c 1 -o gpurun_out/prof_grid_r1_v4 python bench.py --steps 6 --warmup 3 --variant 3 --no-single --no-cpu-baseline > gpurun_out/ncu_grid.log 2>&1
 tail -2 gpurun_out/ncu_grid.log
