@@ -58,7 +58,7 @@ struct GridPlan {
   int32_t* feid = nullptr;   // [S*FBG_FAST*maxV] fast rows: edge id, -1 = idle
   int2* gplan = nullptr;     // [S*2*maxE] generic edges {bi | bj<<16, si | sj<<16}: s_bar / s_slot entry indices
   int32_t* geid = nullptr;   // [S*2*maxE] generic edges: edge id, bit 31 set on a copy that is NOT written back
-  int4* vplan = nullptr;     // [S*maxV] {vertex id, slot begin | n_target<<16 | n_overflow<<24, push begin | end<<16, 0}
+  int4* vplan = nullptr;     // [S*maxV] {vertex id, n_target | n_overflow<<8, push begin | end<<16, 0}
   int32_t* hplan = nullptr;  // [S*2*maxE] halo lists: stream-local vertex ids
   int2* pplan = nullptr;     // [S*2*maxE] push lists: {consumer part, entry index in its s_bar}
   int4* cinfo = nullptr;     // [S*FBG_MAXP*3] {vBeg, nOwn, gBeg, nGen}, {hBeg, nHalo, nSlot, 0}, {pBeg, nPush, 0, 0}
@@ -259,7 +259,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   // ---- register-resident state: the thread's vertex, its out-edges, one generic edge ------------
   float vx = 0.f, vw1 = 0.f, vw2 = 0.f, vz = 0.f, vth = 0.f, xb = 0.f, w1b = 0.f, w2b = 0.f;
   int v_id = -1;             // vertex id, bit 30 = boundary; -1 = none
-  uint32_t v_sl = 0u;        // slot begin | n_target << 16 | n_overflow << 24
+  uint32_t v_sl = 0u;        // n_target | n_overflow << 8 (slot rows of this vertex, slot-major layout)
   uint32_t v_push = 0u;      // push list range begin | end << 16 (cluster transport)
   uint32_t fvalid = 0u;      // bit k: fast row k holds an edge
   FbgFast F;
@@ -339,7 +339,12 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   // warp-uniform work extents: fast rows any lane of the warp uses, generic row, vertex row
   const int rowsF = __reduce_max_sync(0xffffffffu, __popc(fvalid));
   const bool warpG = (tid & ~31) < nGen, warpV = (tid & ~31) < nOwn;
-  const int s0 = (int)(v_sl & 0xffffu), nT = (int)((v_sl >> 16) & 0xffu), nO = (int)(v_sl >> 24);
+  // slots are slot-major: record (row p, thread t) at p * nOwn + t, so a warp's gather of row p is
+  // one conflict-free contiguous read; rows [0, nT) hold the in-edges' contributions, rows
+  // [nT, nT + nO) those of out-edges beyond the register rows
+  const int nT = (int)(v_sl & 0xffu), nO = (int)((v_sl >> 8) & 0xffu);
+  const int rowsT = __reduce_max_sync(0xffffffffu, nT);
+  const int rowsO = __reduce_max_sync(0xffffffffu, nO) ? __reduce_max_sync(0xffffffffu, nT + nO) : 0;
 
   for (int it = 0; it < iters; ++it) {
     const bool more = it + 1 < iters;
@@ -369,11 +374,14 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     // ---- primal half-step: CSR order = target-role slots, own out-edges, overflow slots -----------
     if (warpV) {
       float gx = 0.f, g1 = 0.f, g2 = 0.f;
-      for (int j = 0; j < nT; ++j) {
-        const float4 c = s_slot[s0 + j];
-        gx += c.x;
-        g1 += c.y;
-        g2 += c.z;
+#pragma unroll 4
+      for (int j = 0; j < rowsT; ++j) {  // warp-uniform trip count, per-lane predicate
+        if (j < nT) {
+          const float4 c = s_slot[j * nOwn + tid];
+          gx += c.x;
+          g1 += c.y;
+          g2 += c.z;
+        }
       }
 #pragma unroll
       for (int k = 0; k < FBG_FAST; ++k) {
@@ -384,11 +392,13 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
           g2 += fmaf(F.b[k], F.q3[k], -(F.dy[k] * a1));
         }
       }
-      for (int j = 0; j < nO; ++j) {
-        const float4 c = s_slot[s0 + nT + j];
-        gx += c.x;
-        g1 += c.y;
-        g2 += c.z;
+      for (int jj = 0; jj < rowsO; ++jj) {  // rare: out-edges beyond the register rows
+        if (jj >= nT && jj < nT + nO) {
+          const float4 c = s_slot[jj * nOwn + tid];
+          gx += c.x;
+          g1 += c.y;
+          g2 += c.z;
+        }
       }
       if (v_id >= 0) {
         const float xo = vx, w1o = vw1, w2o = vw2;
@@ -519,8 +529,8 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
   // thread order per part: raster order over strips about one vertex spacing high, so the lanes of
   // a quarter-warp hold neighbouring vertices and the k-th out-edges of those lanes point at
   // neighbouring entries / slot blocks (few shared-memory bank conflicts on the target side);
-  // slot blocks hold the target-role incidences followed by the out-edges beyond the FBG_FAST
-  // register rows, padded to an odd number of 16 B records (conflict-free gathers)
+  // slots are slot-major (row p of thread t at p * nOwn + t): rows [0, in-degree) take the in-edges'
+  // contributions in CSR order, the following rows those of out-edges beyond the FBG_FAST register rows
   std::vector<int> cnt(nper + 1, 0);
   for (int v = 0; v < V; ++v) cnt[part[v] + 1]++;
   for (int r = 0; r < nper; ++r) cnt[r + 1] += cnt[r];
@@ -529,7 +539,7 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
     std::vector<int> fill(cnt.begin(), cnt.begin() + nper);
     for (int v = 0; v < V; ++v) order[fill[part[v]]++] = v;
   }
-  std::vector<int> lidx(V), sbase(V), nslot(nper, 0), strip(V, 0);
+  std::vector<int> lidx(V), nslot(nper, 0), strip(V, 0), nown(nper, 0);
   for (int r = 0; r < nper; ++r) {
     {
       float x0 = 1e30f, x1 = -1e30f, y0 = 1e30f, y1 = -1e30f;
@@ -548,19 +558,20 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
         return u < v;
       });
     }
-    int base = 0;
+    const int nOwn = cnt[r + 1] - cnt[r];
+    int rows = 0;  // slot rows of the part: max over its vertices of in-degree + overflow
     for (int k = cnt[r]; k < cnt[r + 1]; ++k) {
       const int v = order[k];
       const int nout = deg[v] - nin[v], novf = std::max(0, nout - FBG_FAST);
       if (nin[v] > 255 || novf > 255) return false;
       lidx[v] = k - cnt[r];
-      sbase[v] = base;
-      g.vplan[k] = make_int4(v, base | (nin[v] << 16) | (novf << 24), 0, 0);
-      base += (nin[v] + novf) | 1;
+      g.vplan[k] = make_int4(v, nin[v] | (novf << 8), 0, 0);
+      rows = std::max(rows, nin[v] + novf);
     }
+    const int base = rows * nOwn;  // slot-major: record (row p, thread t) at p * nOwn + t; dummy at the end
     nslot[r] = base;
-    const int nOwn = cnt[r + 1] - cnt[r];
     if (nOwn > threads || base + 1 > 0xffff) return false;
+    nown[r] = nOwn;
     g.cinfo[3 * r].x = cnt[r];
     g.cinfo[3 * r].y = nOwn;
     g.cinfo[3 * r + 1].z = base;
@@ -606,7 +617,7 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
   for (int e = 0; e < E; ++e) {
     const int i = t.eij[e].x, j = t.eij[e].y, ri = part[i], rj = part[j];
     // the copy in the source's part: a register row of i's thread, or (beyond FBG_FAST) a generic edge
-    const int sj_i = (rj == ri) ? sbase[j] + pdst[e] : nslot[ri];
+    const int sj_i = (rj == ri) ? pdst[e] * nown[ri] + lidx[j] : nslot[ri];
     const int bj_i = entry(ri, j);
     if (nfast[i] < FBG_FAST) {
       const size_t fi = (size_t)nfast[i] * V + cnt[ri] + lidx[i];
@@ -614,13 +625,13 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
       g.feid[fi] = e;
       nfast[i]++;
     } else {
-      const int si = sbase[i] + nin[i] + novf_seen[i]++;
+      const int si = (nin[i] + novf_seen[i]++) * nown[ri] + lidx[i];
       gpl[ri].push_back(make_int2(lidx[i] | (bj_i << 16), si | (sj_i << 16)));
       gid[ri].push_back(e);
     }
     // cut edge: the copy in the target's part reads the source from the halo, feeds only the target
     if (rj != ri) {
-      gpl[rj].push_back(make_int2(entry(rj, i) | (lidx[j] << 16), nslot[rj] | ((sbase[j] + pdst[e]) << 16)));
+      gpl[rj].push_back(make_int2(entry(rj, i) | (lidx[j] << 16), nslot[rj] | ((pdst[e] * nown[rj] + lidx[j]) << 16)));
       gid[rj].push_back(e | (int)0x80000000);
     }
   }
@@ -982,12 +993,12 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
       if (pv.x < 0 || pv.x >= V || owner[pv.x] != -1) { why = "vertex owned twice or out of range"; return 2; }
       owner[pv.x] = r;
       lidx[pv.x] = k;
-      const int s0 = pv.y & 0xffff, nt = (pv.y >> 16) & 0xff, no = (int)((uint32_t)pv.y >> 24);
+      const int nt = pv.y & 0xff, no = (pv.y >> 8) & 0xff;
       int nin = 0;
       for (int q = t.row[pv.x]; q < t.row[pv.x + 1]; ++q) nin += t.inc[q] & 1;
       const int nout = t.row[pv.x + 1] - t.row[pv.x] - nin;
       if (nt != nin || no != std::max(0, nout - FBG_FAST)) { why = "slot block does not match the in-degree / overflow"; return 3; }
-      if (s0 + nt + no > c1.z) { why = "slot block beyond the part's slot count"; return 3; }
+      if ((nt + no) * c0.y > c1.z) { why = "slot rows beyond the part's slot count"; return 3; }
       nb += ((uint32_t)pv.z >> 16) != ((uint32_t)pv.z & 0xffffu) ? 1 : 0;
       novf += no;
     }
@@ -1005,16 +1016,16 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
       if (b != lidx[v]) { code = 5; return false; }
       if (!slot_used) return true;
       const int4 pv = g.vplan[c0.x + lidx[v]];
-      const int s0 = pv.y & 0xffff, nt = (pv.y >> 16) & 0xff;
+      const int nt = pv.y & 0xff;
       int want;
       if (is_target) {  // position among the target-role incidences (CSR order)
         int posn = -1;
         for (int q = t.row[v]; q < t.row[v + 1]; ++q)
           if (t.inc[q] == ((e << 1) | 1)) posn = q - t.row[v];
-        want = s0 + posn;
+        want = posn * c0.y + lidx[v];
         if (posn < 0 || posn >= nt) { code = 6; return false; }
       } else {
-        want = s0 + nt + ovf_pos;
+        want = (nt + ovf_pos) * c0.y + lidx[v];
       }
       if (sl != want) { code = 6; return false; }
     } else {
@@ -1033,7 +1044,7 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
     }
     return true;
   };
-  static const char* msg[] = {"", "", "", "", "", "own endpoint index mismatch", "slot != block base + CSR position",
+  static const char* msg[] = {"", "", "", "", "", "own endpoint index mismatch", "slot != CSR position * nOwn + thread",
                               "halo index mismatch", "remote endpoint must map to the dummy slot",
                               "halo vertex not pushed/published by its owner"};
   std::vector<std::vector<int>> hit(nper);
@@ -1098,9 +1109,9 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
     const int4 c0 = g.cinfo[3 * r];
     for (int k = 0; k < c0.y; ++k) {
       const int4 pv = g.vplan[c0.x + k];
-      const int s0 = pv.y & 0xffff, n = ((pv.y >> 16) & 0xff) + (int)((uint32_t)pv.y >> 24);
-      for (int q = s0; q < s0 + n; ++q)
-        if (hit[r][q] != 1) { why = "slot not written exactly once"; return 12; }
+      const int n = (pv.y & 0xff) + ((pv.y >> 8) & 0xff);
+      for (int q = 0; q < n; ++q)
+        if (hit[r][q * c0.y + k] != 1) { why = "slot not written exactly once"; return 12; }
     }
   }
   for (int e = 0; e < E; ++e)

@@ -19,5 +19,5 @@ FB_GRID_MODE=l2 timeout 200 python bench.py --streams 8 --variant 3 $B 2>/tmp/er
 timeout 200 python bench.py --streams 11 --variant 3 $B 2>/tmp/err.txt | line "S=11 v3 auto"; tail -2 /tmp/err.txt
 timeout 200 python bench.py --streams 14 --variant 3 $B 2>/tmp/err.txt | line "S=14 v3 auto"; tail -2 /tmp/err.txt
 timeout 300 python bench.py --config C4 --streams 1 --variant 3 --steps 40 --warmup 5 --no-single --no-cpu-baseline 2>/tmp/err.txt | line "C4 v3"; tail -2 /tmp/err.txt
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_nltgv2_grid -s 3 -c 1 -o gpurun_out/prof_grid_r1_v4 python bench.py --steps 6 --warmup 3 --variant 3 --no-single --no-cpu-baseline > gpurun_out/ncu_grid.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_nltgv2_grid -s 3 -c 1 -o gpurun_out/prof_grid_r1_v5 python bench.py --steps 6 --warmup 3 --variant 3 --no-single --no-cpu-baseline > gpurun_out/ncu_grid.log 2>&1
 tail -2 gpurun_out/ncu_grid.log
