@@ -38,6 +38,7 @@
 
 #include <algorithm>
 #include <numeric>
+#include <set>
 
 #include "common.cuh"
 #include "nltgv2.cuh"
@@ -58,10 +59,10 @@ struct GridPlan {
   int32_t* feid = nullptr;   // [S*FBG_FAST*maxV] fast rows: edge id, -1 = idle
   int2* gplan = nullptr;     // [S*2*maxE] generic edges {bi | bj<<16, si | sj<<16}: s_bar / s_slot entry indices
   int32_t* geid = nullptr;   // [S*2*maxE] generic edges: edge id, bit 31 set on a copy that is NOT written back
-  int4* vplan = nullptr;     // [S*maxV] {vertex id, n_target | n_overflow<<8, push begin | end<<16, 0}
+  int4* vplan = nullptr;     // [S*maxV] {vertex id, n_target | n_overflow<<8 | entry<<16, push begin | end<<16, 0}
   int32_t* hplan = nullptr;  // [S*2*maxE] halo lists: stream-local vertex ids
   int2* pplan = nullptr;     // [S*2*maxE] push lists: {consumer part, entry index in its s_bar}
-  int4* cinfo = nullptr;     // [S*FBG_MAXP*3] {vBeg, nOwn, gBeg, nGen}, {hBeg, nHalo, nSlot, 0}, {pBeg, nPush, 0, 0}
+  int4* cinfo = nullptr;     // [S*FBG_MAXP*3] {vBeg, nOwn, gBeg, nGen}, {hBeg, nHalo, nSlot, in-edge rows | stride<<8}, {pBeg, nPush, 0, 0}
   float4* pub = nullptr;     // [2][S*maxV] tagged mailboxes (parity-major), L2 transport
   int* err = nullptr;        // mapped host flag: set by the watchdog
   uint32_t seq = 0;          // launch counter -> tag base
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float theta, float xmin,
               float xmax, uint32_t tag0) {
   extern __shared__ __align__(16) uint8_t fbg_smem[];
-  float4* s_bar = reinterpret_cast<float4*>(fbg_smem);  // 2 banks x [nOwn own | nHalo halo]
+  float4* s_bar = reinterpret_cast<float4*>(fbg_smem);  // 2 banks x [nEnt own entries | nHalo halo]
   float4* s_slot = s_bar + 2 * a.capBar;                // [nSlot + 1 dummy]
   uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_slot + a.capSlot + 1);  // [2] one per parity
   uint2* s_push = reinterpret_cast<uint2*>(s_mbar + 2);  // {remote s_bar address (bank 0), remote mbarrier 0}
@@ -255,11 +256,12 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   const uint32_t mb0 = fbc_smem_u32(s_mbar);
   const uint32_t haloBytes = 16u * (uint32_t)nHalo;
   const uint32_t dummy = (uint32_t)c1.z;
+  const int rowsIn = c1.w & 0xff, stride = c1.w >> 8, nEnt = stride - 1;  // slot rows of in-edges, row stride, own entries
 
   // ---- register-resident state: the thread's vertex, its out-edges, one generic edge ------------
   float vx = 0.f, vw1 = 0.f, vw2 = 0.f, vz = 0.f, vth = 0.f, xb = 0.f, w1b = 0.f, w2b = 0.f;
   int v_id = -1;             // vertex id, bit 30 = boundary; -1 = none
-  uint32_t v_sl = 0u;        // n_target | n_overflow << 8 (slot rows of this vertex, slot-major layout)
+  uint32_t v_sl = 0u;        // n_target | n_overflow << 8 | entry << 16 (slot rows and s_bar entry of this vertex)
   uint32_t v_push = 0u;      // push list range begin | end << 16 (cluster transport)
   uint32_t fvalid = 0u;      // bit k: fast row k holds an edge
   FbgFast F;
@@ -279,7 +281,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     vth = tl * g.wt[vb + v];
     const float4 b0 = g.vbar[vb + v];
     xb = b0.x; w1b = b0.y; w2b = b0.z;
-    s_bar[tid] = b0;  // bank 0: the points iteration 0 reads
+    s_bar[v_sl >> 16] = b0;  // bank 0: the points iteration 0 reads
 #pragma unroll
     for (int k = 0; k < FBG_FAST; ++k) {
       const size_t fi = ((size_t)s * FBG_FAST + k) * g.maxV + c0.x + tid;
@@ -316,7 +318,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     const int hv = hl[h];
     if (h == tid) hv0 = hv;
     else if (h == tid + THREADS) hv1 = hv;
-    s_bar[nOwn + h] = g.vbar[vb + hv];
+    s_bar[nEnt + h] = g.vbar[vb + hv];
   }
   if (CLUSTER) {
     if (tid == 0) {
@@ -339,12 +341,12 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   // warp-uniform work extents: fast rows any lane of the warp uses, generic row, vertex row
   const int rowsF = __reduce_max_sync(0xffffffffu, __popc(fvalid));
   const bool warpG = (tid & ~31) < nGen, warpV = (tid & ~31) < nOwn;
-  // slots are slot-major: record (row p, thread t) at p * nOwn + t, so a warp's gather of row p is
-  // one conflict-free contiguous read; rows [0, nT) hold the in-edges' contributions, rows
-  // [nT, nT + nO) those of out-edges beyond the register rows
-  const int nT = (int)(v_sl & 0xffu), nO = (int)((v_sl >> 8) & 0xffu);
-  const int rowsT = __reduce_max_sync(0xffffffffu, nT);
-  const int rowsO = __reduce_max_sync(0xffffffffu, nO) ? __reduce_max_sync(0xffffffffu, nT + nO) : 0;
+  // slots are slot-major: record (row p, entry n) at p * stride + n.  Entries are a permutation of the
+  // thread index inside each aligned group of 8 and the stride is odd, so a warp's gather of one
+  // row is conflict-free; rows [0, nT) hold the in-edges' contributions, rows [rowsIn, rowsIn + nO)
+  // those of out-edges beyond the register rows (rare)
+  const int nT = (int)(v_sl & 0xffu), nO = (int)((v_sl >> 8) & 0xffu), ent = (int)(v_sl >> 16);
+  const int rowsT = __reduce_max_sync(0xffffffffu, nT), rowsO = __reduce_max_sync(0xffffffffu, nO);
 
   for (int it = 0; it < iters; ++it) {
     const bool more = it + 1 < iters;
@@ -356,7 +358,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
       } else if (hv0 >= 0) {
         const uint32_t tag = tag0 + (uint32_t)(it - 1);
         const float4* pb = pub0 + (size_t)((it - 1) & 1) * a.pstride;
-        float4* hb = s_bar + ((it & 1) ? a.capBar : 0) + nOwn;
+        float4* hb = s_bar + ((it & 1) ? a.capBar : 0) + nEnt;
         hb[tid] = fbg_poll(pb + hv0, tag, a.err, dead);
         if (hv1 >= 0) {
           hb[tid + THREADS] = fbg_poll(pb + hv1, tag, a.err, dead);
@@ -377,7 +379,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
 #pragma unroll 4
       for (int j = 0; j < rowsT; ++j) {  // warp-uniform trip count, per-lane predicate
         if (j < nT) {
-          const float4 c = s_slot[j * nOwn + tid];
+          const float4 c = s_slot[j * stride + ent];
           gx += c.x;
           g1 += c.y;
           g2 += c.z;
@@ -392,9 +394,10 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
           g2 += fmaf(F.b[k], F.q3[k], -(F.dy[k] * a1));
         }
       }
-      for (int jj = 0; jj < rowsO; ++jj) {  // rare: out-edges beyond the register rows
-        if (jj >= nT && jj < nT + nO) {
-          const float4 c = s_slot[jj * nOwn + tid];
+#pragma unroll 1
+      for (int o = 0; o < rowsO; ++o) {  // rare: out-edges beyond the register rows
+        if (o < nO) {
+          const float4 c = s_slot[(rowsIn + o) * stride + ent];
           gx += c.x;
           g1 += c.y;
           g2 += c.z;
@@ -417,6 +420,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
           if (v_id & 0x40000000) {  // boundary vertex: hand the point to the CTAs across the cut
             if (CLUSTER) {
               const uint32_t moff = 8u * (uint32_t)((it + 1) & 1);
+#pragma unroll 1
               for (uint32_t p = v_push & 0xffffu; p < (v_push >> 16); ++p) {
                 const uint2 e = s_push[p];
                 fbc_st_async(e.x + wr_off, nb, e.y + moff);
@@ -426,7 +430,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
                              tag0 + (uint32_t)it);
             }
           }
-          fbc_sts(bar_base + wr_off + 16u * (uint32_t)tid, nb);
+          fbc_sts(bar_base + wr_off + 16u * (uint32_t)ent, nb);
         } else {
           g.vbar[vb + (v_id & 0x3fffffff)] = nb;
         }
@@ -484,6 +488,28 @@ static void fbg_rcb(const float2* pos, const int* wgt, int* ids, int lo, int hi,
   fbg_rcb(pos, wgt, ids, m, hi, p0 + nl, np - nl, part);
 }
 
+// Shared-memory wavefronts one quarter-warp (8 lanes x 16 B) needs for a set of records: the largest
+// number of DIFFERENT records falling into one 16-byte bank group (equal records merge).
+static inline int fbg_group_cost(const int* rec, int n) {
+  int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, worst = 0;
+  for (int a = 0; a < n; ++a) {
+    bool dup = false;
+    for (int b = 0; b < a; ++b) dup |= rec[b] == rec[a];
+    if (!dup) worst = std::max(worst, ++cnt[rec[a] & 7]);
+  }
+  return worst;
+}
+// Smooth surrogate of the above for the local search: pairs of different records in one bank group.
+static inline int fbg_group_pairs(const int* rec, int n) {
+  int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pairs = 0;
+  for (int a = 0; a < n; ++a) {
+    bool dup = false;
+    for (int b = 0; b < a; ++b) dup |= rec[b] == rec[a];
+    if (!dup) pairs += cnt[rec[a] & 7]++;
+  }
+  return pairs;
+}
+
 // Build the host tables of one stream for `nper` parts and a CTA of `threads` threads (one vertex
 // and one generic edge per thread).  Returns false when a part exceeds the per-CTA capacity (the
 // caller then tries more parts, the other transport or another variant).
@@ -520,17 +546,13 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
   }
   std::iota(ids.begin(), ids.end(), 0);
   fbg_rcb(g.pos.data(), wgt.data(), ids.data(), 0, V, 0, nper, part.data());
-  std::vector<uint8_t> bnd(V, 0);
   std::vector<int> pdst(E);  // position of edge e among the target-role incidences of its target
-  for (int e = 0; e < E; ++e)
-    if (part[t.eij[e].x] != part[t.eij[e].y]) bnd[t.eij[e].x] = bnd[t.eij[e].y] = 1;
   for (int v = 0; v < V; ++v)
     for (int k = t.row[v]; k < t.row[v] + nin[v]; ++k) pdst[t.inc[k] >> 1] = k - t.row[v];
-  // thread order per part: raster order over strips about one vertex spacing high, so the lanes of
-  // a quarter-warp hold neighbouring vertices and the k-th out-edges of those lanes point at
-  // neighbouring entries / slot blocks (few shared-memory bank conflicts on the target side);
-  // slots are slot-major (row p of thread t at p * nOwn + t): rows [0, in-degree) take the in-edges'
-  // contributions in CSR order, the following rows those of out-edges beyond the FBG_FAST register rows
+  // thread order per part: by in-degree, then out-degree -- the lanes of a warp then run equally many
+  // slot rows and register rows.  Shared-memory records are addressed through an ENTRY index that
+  // is a permutation of the thread index inside each aligned group of 8 (chosen below), slots are
+  // slot-major with an odd row stride: record (row p, entry n) at p * stride + n.
   std::vector<int> cnt(nper + 1, 0);
   for (int v = 0; v < V; ++v) cnt[part[v] + 1]++;
   for (int r = 0; r < nper; ++r) cnt[r + 1] += cnt[r];
@@ -539,99 +561,146 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
     std::vector<int> fill(cnt.begin(), cnt.begin() + nper);
     for (int v = 0; v < V; ++v) order[fill[part[v]]++] = v;
   }
-  std::vector<int> lidx(V), nslot(nper, 0), strip(V, 0), nown(nper, 0);
+  std::vector<int> lidx(V), ent(V), nent(nper), stride(nper), rows_in(nper, 0), nslot(nper, 0);
   for (int r = 0; r < nper; ++r) {
-    {
-      float x0 = 1e30f, x1 = -1e30f, y0 = 1e30f, y1 = -1e30f;
-      for (int k = cnt[r]; k < cnt[r + 1]; ++k) {
-        const float2 p = g.pos[order[k]];
-        x0 = std::min(x0, p.x); x1 = std::max(x1, p.x);
-        y0 = std::min(y0, p.y); y1 = std::max(y1, p.y);
-      }
-      const int n = cnt[r + 1] - cnt[r];
-      const float area = std::max(1e-6f, (x1 - x0) * (y1 - y0));
-      const float hstrip = std::max(1e-3f, sqrtf(area / std::max(1, n)));
-      for (int k = cnt[r]; k < cnt[r + 1]; ++k) strip[order[k]] = (int)((g.pos[order[k]].y - y0) / hstrip);
-      std::sort(order.begin() + cnt[r], order.begin() + cnt[r + 1], [&](int u, int v) {
-        if (strip[u] != strip[v]) return strip[u] < strip[v];
-        if (g.pos[u].x != g.pos[v].x) return g.pos[u].x < g.pos[v].x;
-        return u < v;
-      });
-    }
+    std::sort(order.begin() + cnt[r], order.begin() + cnt[r + 1], [&](int u, int v) {
+      if (nin[u] != nin[v]) return nin[u] > nin[v];
+      if (deg[u] != deg[v]) return deg[u] > deg[v];
+      return u < v;
+    });
     const int nOwn = cnt[r + 1] - cnt[r];
-    int rows = 0;  // slot rows of the part: max over its vertices of in-degree + overflow
+    int rows_ov = 0;
     for (int k = cnt[r]; k < cnt[r + 1]; ++k) {
       const int v = order[k];
-      const int nout = deg[v] - nin[v], novf = std::max(0, nout - FBG_FAST);
+      const int novf = std::max(0, deg[v] - nin[v] - FBG_FAST);
       if (nin[v] > 255 || novf > 255) return false;
-      lidx[v] = k - cnt[r];
-      g.vplan[k] = make_int4(v, nin[v] | (novf << 8), 0, 0);
-      rows = std::max(rows, nin[v] + novf);
+      lidx[v] = ent[v] = k - cnt[r];
+      rows_in[r] = std::max(rows_in[r], nin[v]);
+      rows_ov = std::max(rows_ov, novf);
     }
-    const int base = rows * nOwn;  // slot-major: record (row p, thread t) at p * nOwn + t; dummy at the end
-    nslot[r] = base;
-    if (nOwn > threads || base + 1 > 0xffff) return false;
-    nown[r] = nOwn;
+    nent[r] = (nOwn + 7) & ~7;
+    stride[r] = nent[r] + 1;  // odd: the rows of one entry fall into different bank groups
+    nslot[r] = (rows_in[r] + rows_ov) * stride[r];  // the dummy record follows the last row
+    if (nOwn > threads || nslot[r] + 1 > 0xffff) return false;
     g.cinfo[3 * r].x = cnt[r];
     g.cinfo[3 * r].y = nOwn;
-    g.cinfo[3 * r + 1].z = base;
-    g.capSlot = std::max(g.capSlot, base);
+    g.cinfo[3 * r + 1].z = nslot[r];
+    g.cinfo[3 * r + 1].w = rows_in[r] | (stride[r] << 8);
+    g.capSlot = std::max(g.capSlot, nslot[r]);
   }
-  // halo entries and push lists: every remote endpoint of an edge touching the part
-  std::vector<int> nh(nper, 0), hbeg(nper, 0);
+  // halo entries (sorted vertex ids) follow the own entries; push lists name them for the owners
   std::vector<std::vector<int>> halo(nper);
-  std::vector<std::vector<int4>> push(nper);  // per owner part: {owner-local vertex, consumer part, consumer entry}
-  // pass over the edges in ascending id: out-edges of a vertex arrive in ascending target order
-  std::vector<int> nfast(V, 0), novf_seen(V, 0);
-  // halo index lookup must be per part: first collect (part, vertex) pairs
+  std::vector<std::vector<int4>> push(nper);  // per owner part: {owner-local thread, consumer part, consumer entry}
   for (int e = 0; e < E; ++e) {
     const int i = t.eij[e].x, j = t.eij[e].y, ri = part[i], rj = part[j];
     if (ri == rj) continue;
     halo[ri].push_back(j);
     halo[rj].push_back(i);
   }
-  std::vector<std::vector<std::pair<int, int>>> hmap(nper);  // sorted (vertex, halo index)
   for (int r = 0; r < nper; ++r) {
     std::vector<int>& h = halo[r];
     std::sort(h.begin(), h.end());
     h.erase(std::unique(h.begin(), h.end()), h.end());
-    const int nOwn = cnt[r + 1] - cnt[r];
-    if (nOwn + (int)h.size() > 0xffff) return false;
-    hbeg[r] = (int)g.hplan.size();
+    if (nent[r] + (int)h.size() > 0xffff) return false;
+    g.cinfo[3 * r + 1].x = (int)g.hplan.size();
+    g.cinfo[3 * r + 1].y = (int)h.size();
     for (size_t k = 0; k < h.size(); ++k) {
       g.hplan.push_back(h[k]);
-      push[part[h[k]]].push_back(make_int4(lidx[h[k]], r, nOwn + (int)k, 0));
+      push[part[h[k]]].push_back(make_int4(lidx[h[k]], r, nent[r] + (int)k, 0));
     }
-    nh[r] = (int)h.size();
-    g.cinfo[3 * r + 1].x = hbeg[r];
-    g.cinfo[3 * r + 1].y = nh[r];
-    g.capBar = std::max(g.capBar, nOwn + nh[r]);
+    g.capBar = std::max(g.capBar, nent[r] + (int)h.size());
+  }
+  // register rows: the first FBG_FAST out-edges of every vertex in ascending edge id
+  std::vector<int> fe((size_t)FBG_FAST * V, -1), nfast(V, 0);
+  for (int e = 0; e < E; ++e) {
+    const int i = t.eij[e].x;
+    if (nfast[i] < FBG_FAST) fe[(size_t)nfast[i]++ * V + cnt[part[i]] + lidx[i]] = e;
+  }
+  // ---- entry permutation: inside every aligned group of 8 threads, swap entries while that lowers
+  // the bank conflicts of the register rows' target-side accesses (LDS of the target's point: bank
+  // group = entry & 7; STS of its contribution: bank group = (row + entry) & 7 with the odd stride).
+  // Own stores and slot gathers stay conflict-free because each group of 8 keeps 8 distinct entries.
+  for (int r = 0; r < nper; ++r) {
+    const int nOwn = cnt[r + 1] - cnt[r];
+    if (nOwn <= 8) continue;
+    const int ngrp = (nOwn + 7) / 8;
+    // groups = (quarter-warp, row); members = (target vertex, slot row) with the target in this part
+    std::vector<std::vector<int>> memb((size_t)ngrp * FBG_FAST);  // packed: target local thread | row << 16
+    std::vector<std::vector<int>> of_vertex(nOwn);             // groups a local vertex is a target in
+    for (int k = 0; k < FBG_FAST; ++k)
+      for (int tl = 0; tl < nOwn; ++tl) {
+        const int e = fe[(size_t)k * V + cnt[r] + tl];
+        if (e < 0) continue;
+        const int j = t.eij[e].y;
+        if (part[j] != r) continue;  // halo targets keep their fixed entries: left out of the search
+        const int gi = (tl / 8) * FBG_FAST + k;
+        memb[gi].push_back(lidx[j] | (pdst[e] << 16));
+        of_vertex[lidx[j]].push_back(gi);
+      }
+    std::vector<int> e_of(nOwn);  // local thread -> entry
+    for (int tl = 0; tl < nOwn; ++tl) e_of[tl] = tl;
+    auto cost = [&](int gi) {
+      int ld[8], st[8];
+      const std::vector<int>& m = memb[gi];
+      const int n = std::min((int)m.size(), 8);
+      for (int a = 0; a < n; ++a) {
+        const int en = e_of[m[a] & 0xffff], row = m[a] >> 16;
+        ld[a] = en;
+        st[a] = row * stride[r] + en;
+      }
+      return fbg_group_pairs(ld, n) + fbg_group_pairs(st, n);
+    };
+    for (int sweep = 0; sweep < 12; ++sweep) {
+      bool improved = false;
+      for (int q = 0; q < ngrp; ++q) {
+        const int lo = q * 8, hi = std::min(nOwn, lo + 8);
+        for (int u = lo; u < hi; ++u)
+          for (int v = u + 1; v < hi; ++v) {
+            if (of_vertex[u].empty() && of_vertex[v].empty()) continue;
+            int before = 0, after = 0;
+            for (int gi : of_vertex[u]) before += cost(gi);
+            for (int gi : of_vertex[v]) before += cost(gi);
+            std::swap(e_of[u], e_of[v]);
+            for (int gi : of_vertex[u]) after += cost(gi);
+            for (int gi : of_vertex[v]) after += cost(gi);
+            if (after < before) improved = true;
+            else std::swap(e_of[u], e_of[v]);
+          }
+      }
+      if (!improved) break;
+    }
+    for (int tl = 0; tl < nOwn; ++tl) ent[order[cnt[r] + tl]] = e_of[tl];
   }
   auto entry = [&](int r, int v) -> int {  // s_bar entry of vertex v as seen from part r
-    if (part[v] == r) return lidx[v];
+    if (part[v] == r) return ent[v];
     const std::vector<int>& h = halo[r];
-    return (cnt[r + 1] - cnt[r]) + (int)(std::lower_bound(h.begin(), h.end(), v) - h.begin());
+    return nent[r] + (int)(std::lower_bound(h.begin(), h.end(), v) - h.begin());
   };
+  for (int v = 0; v < V; ++v) {
+    const int novf = std::max(0, deg[v] - nin[v] - FBG_FAST);
+    g.vplan[cnt[part[v]] + lidx[v]] = make_int4(v, nin[v] | (novf << 8) | (ent[v] << 16), 0, 0);
+  }
+  // ---- edge tables
   std::vector<std::vector<int2>> gpl(nper);
   std::vector<std::vector<int>> gid(nper);
+  std::vector<int> nf2(V, 0), novf_seen(V, 0);
   for (int e = 0; e < E; ++e) {
     const int i = t.eij[e].x, j = t.eij[e].y, ri = part[i], rj = part[j];
     // the copy in the source's part: a register row of i's thread, or (beyond FBG_FAST) a generic edge
-    const int sj_i = (rj == ri) ? pdst[e] * nown[ri] + lidx[j] : nslot[ri];
+    const int sj_i = (rj == ri) ? pdst[e] * stride[ri] + ent[j] : nslot[ri];
     const int bj_i = entry(ri, j);
-    if (nfast[i] < FBG_FAST) {
-      const size_t fi = (size_t)nfast[i] * V + cnt[ri] + lidx[i];
+    if (nf2[i] < FBG_FAST) {
+      const size_t fi = (size_t)nf2[i]++ * V + cnt[ri] + lidx[i];
       g.fplan[fi] = (uint32_t)bj_i | ((uint32_t)sj_i << 16);
       g.feid[fi] = e;
-      nfast[i]++;
     } else {
-      const int si = (nin[i] + novf_seen[i]++) * nown[ri] + lidx[i];
-      gpl[ri].push_back(make_int2(lidx[i] | (bj_i << 16), si | (sj_i << 16)));
+      const int si = (rows_in[ri] + novf_seen[i]++) * stride[ri] + ent[i];
+      gpl[ri].push_back(make_int2(ent[i] | (bj_i << 16), si | (sj_i << 16)));
       gid[ri].push_back(e);
     }
     // cut edge: the copy in the target's part reads the source from the halo, feeds only the target
     if (rj != ri) {
-      gpl[rj].push_back(make_int2(entry(rj, i) | (lidx[j] << 16), nslot[rj] | ((pdst[e] * nown[rj] + lidx[j]) << 16)));
+      gpl[rj].push_back(make_int2(entry(rj, i) | (ent[j] << 16), nslot[rj] | ((pdst[e] * stride[rj] + ent[j]) << 16)));
       gid[rj].push_back(e | (int)0x80000000);
     }
   }
@@ -983,7 +1052,8 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
     why = "partition infeasible for this part count";
     return 1;
   }
-  std::vector<int> owner(V, -1), lidx(V, -1), written(E, 0);
+  std::vector<int> owner(V, -1), lidx(V, -1), written(E, 0), ent_of(V, -1);
+  std::vector<std::set<int>> ent_used(nper);
   int maxOwn = 0, maxGen = 0, maxHalo = 0, dup = 0, maxSlot = 0, nb = 0, novf = 0;
   for (int r = 0; r < nper; ++r) {
     const int4 c0 = g.cinfo[3 * r], c1 = g.cinfo[3 * r + 1];
@@ -993,12 +1063,18 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
       if (pv.x < 0 || pv.x >= V || owner[pv.x] != -1) { why = "vertex owned twice or out of range"; return 2; }
       owner[pv.x] = r;
       lidx[pv.x] = k;
-      const int nt = pv.y & 0xff, no = (pv.y >> 8) & 0xff;
+      const int nt = pv.y & 0xff, no = (pv.y >> 8) & 0xff, en = (int)((uint32_t)pv.y >> 16);
+      const int rows_in = c1.w & 0xff, stride = c1.w >> 8;
+      if (en >= stride - 1 || en / 8 != k / 8) { why = "entry must be a permutation inside the thread's group of 8"; return 16; }
+      if (ent_used[r].count(en)) { why = "entry used twice"; return 16; }
+      ent_used[r].insert(en);
+      ent_of[pv.x] = en;
+      if (nt > rows_in) { why = "in-degree beyond the part's in-edge rows"; return 3; }
       int nin = 0;
       for (int q = t.row[pv.x]; q < t.row[pv.x + 1]; ++q) nin += t.inc[q] & 1;
       const int nout = t.row[pv.x + 1] - t.row[pv.x] - nin;
       if (nt != nin || no != std::max(0, nout - FBG_FAST)) { why = "slot block does not match the in-degree / overflow"; return 3; }
-      if ((nt + no) * c0.y > c1.z) { why = "slot rows beyond the part's slot count"; return 3; }
+      if ((rows_in + no) * stride > c1.z) { why = "slot rows beyond the part's slot count"; return 3; }
       nb += ((uint32_t)pv.z >> 16) != ((uint32_t)pv.z & 0xffffu) ? 1 : 0;
       novf += no;
     }
@@ -1012,24 +1088,23 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
   // what an (entry, slot) pair must be for endpoint v of edge e seen from part r
   auto check_end = [&](int r, int e, int v, bool is_target, int ovf_pos, int b, int sl, bool slot_used, int& code) -> bool {
     const int4 c0 = g.cinfo[3 * r], c1 = g.cinfo[3 * r + 1];
+    const int rows_in = c1.w & 0xff, stride = c1.w >> 8;
     if (owner[v] == r) {
-      if (b != lidx[v]) { code = 5; return false; }
+      if (b != ent_of[v]) { code = 5; return false; }
       if (!slot_used) return true;
-      const int4 pv = g.vplan[c0.x + lidx[v]];
-      const int nt = pv.y & 0xff;
       int want;
       if (is_target) {  // position among the target-role incidences (CSR order)
         int posn = -1;
         for (int q = t.row[v]; q < t.row[v + 1]; ++q)
           if (t.inc[q] == ((e << 1) | 1)) posn = q - t.row[v];
-        want = posn * c0.y + lidx[v];
-        if (posn < 0 || posn >= nt) { code = 6; return false; }
+        want = posn * stride + ent_of[v];
+        if (posn < 0 || posn >= rows_in) { code = 6; return false; }
       } else {
-        want = (nt + ovf_pos) * c0.y + lidx[v];
+        want = (rows_in + ovf_pos) * stride + ent_of[v];
       }
       if (sl != want) { code = 6; return false; }
     } else {
-      const int h = b - c0.y;
+      const int h = b - (stride - 1);
       if (h < 0 || h >= c1.y || g.hplan[c1.x + h] != v) { code = 7; return false; }
       if (slot_used && sl != c1.z) { code = 8; return false; }
       // the owner's push list must name exactly this halo entry
@@ -1044,7 +1119,7 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
     }
     return true;
   };
-  static const char* msg[] = {"", "", "", "", "", "own endpoint index mismatch", "slot != CSR position * nOwn + thread",
+  static const char* msg[] = {"", "", "", "", "", "own endpoint index mismatch", "slot != row * stride + entry",
                               "halo index mismatch", "remote endpoint must map to the dummy slot",
                               "halo vertex not pushed/published by its owner"};
   std::vector<std::vector<int>> hit(nper);
@@ -1109,9 +1184,12 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
     const int4 c0 = g.cinfo[3 * r];
     for (int k = 0; k < c0.y; ++k) {
       const int4 pv = g.vplan[c0.x + k];
-      const int n = (pv.y & 0xff) + ((pv.y >> 8) & 0xff);
-      for (int q = 0; q < n; ++q)
-        if (hit[r][q * c0.y + k] != 1) { why = "slot not written exactly once"; return 12; }
+      const int4 c1 = g.cinfo[3 * r + 1];
+      const int rows_in = c1.w & 0xff, stride = c1.w >> 8, en = (int)((uint32_t)pv.y >> 16);
+      for (int q = 0; q < (pv.y & 0xff); ++q)
+        if (hit[r][q * stride + en] != 1) { why = "slot not written exactly once"; return 12; }
+      for (int q = 0; q < ((pv.y >> 8) & 0xff); ++q)
+        if (hit[r][(rows_in + q) * stride + en] != 1) { why = "overflow slot not written exactly once"; return 12; }
     }
   }
   for (int e = 0; e < E; ++e)

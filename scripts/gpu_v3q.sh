@@ -1,0 +1,17 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_nltgv2.py tests/test_gpu_golden.py -q -x 2>&1 | tail -3
+line() {
+python -c "
+import json,sys
+try:
+    d=json.loads(sys.stdin.read())
+    print('$1 variant=%s ctas=%s value %.0f (%.3f ms) e2e %.0f e2e_sync %.0f solver_us %.1f frac %.2f'%(d['config']['solver_variant'][:12],d['config']['ctas_per_stream'],d['value'],d['ms_per_step'],d['e2e']['value'],d['e2e_sync']['value'],d['roofline']['launch_us'],d['roofline']['frac']))
+except Exception as e:
+    print('$1 FAILED', e)
+"
+}
+B="--steps 100 --no-single --no-cpu-baseline"
+timeout 200 python bench.py --streams 1 --variant 3 $B 2>/tmp/err.txt | line "S=1 v3 auto"; tail -2 /tmp/err.txt
+timeout 200 python bench.py --streams 8 --variant 3 $B 2>/tmp/err.txt | line "S=8 v3 auto"; tail -2 /tmp/err.txt
+timeout 300 python bench.py --config C4 --streams 1 --variant 3 --steps 40 --warmup 5 --no-single --no-cpu-baseline 2>/tmp/err.txt | line "C4 v3"; tail -2 /tmp/err.txt
+bash scripts/gpu_trace.sh
