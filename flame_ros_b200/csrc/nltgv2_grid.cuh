@@ -547,10 +547,13 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
   std::iota(ids.begin(), ids.end(), 0);
   fbg_rcb(g.pos.data(), wgt.data(), ids.data(), 0, V, 0, nper, part.data());
   std::vector<int> pdst(E);  // position of edge e among the target-role incidences of its target
+  std::vector<uint8_t> bnd(V, 0);
+  for (int e = 0; e < E; ++e)
+    if (part[t.eij[e].x] != part[t.eij[e].y]) bnd[t.eij[e].x] = bnd[t.eij[e].y] = 1;
   for (int v = 0; v < V; ++v)
     for (int k = t.row[v]; k < t.row[v] + nin[v]; ++k) pdst[t.inc[k] >> 1] = k - t.row[v];
-  // thread order per part: by in-degree, then out-degree -- the lanes of a warp then run equally many
-  // slot rows and register rows.  Shared-memory records are addressed through an ENTRY index that
+  // thread order per part: boundary vertices first, then by in-degree and out-degree -- the lanes of a
+  // warp then run equally many slot rows and register rows.  Shared-memory records are addressed through an ENTRY index that
   // is a permutation of the thread index inside each aligned group of 8 (chosen below), slots are
   // slot-major with an odd row stride: record (row p, entry n) at p * stride + n.
   std::vector<int> cnt(nper + 1, 0);
@@ -564,6 +567,7 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
   std::vector<int> lidx(V), ent(V), nent(nper), stride(nper), rows_in(nper, 0), nslot(nper, 0);
   for (int r = 0; r < nper; ++r) {
     std::sort(order.begin() + cnt[r], order.begin() + cnt[r + 1], [&](int u, int v) {
+      if (bnd[u] != bnd[v]) return bnd[u] > bnd[v];  // boundary vertices first: few warps run the hand-over
       if (nin[u] != nin[v]) return nin[u] > nin[v];
       if (deg[u] != deg[v]) return deg[u] > deg[v];
       return u < v;
