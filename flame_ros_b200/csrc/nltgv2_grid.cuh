@@ -62,7 +62,7 @@ struct GridPlan {
   int4* vplan = nullptr;     // [S*maxV] {vertex id, n_target | n_overflow<<8 | entry<<16, push begin | end<<16, 0}
   int32_t* hplan = nullptr;  // [S*2*maxE] halo lists: stream-local vertex ids
   int2* pplan = nullptr;     // [S*2*maxE] push lists: {consumer part, entry index in its s_bar}
-  int4* cinfo = nullptr;     // [S*FBG_MAXP*3] {vBeg, nOwn, gBeg, nGen}, {hBeg, nHalo, nSlot, in-edge rows | stride<<8}, {pBeg, nPush, 0, 0}
+  int4* cinfo = nullptr;     // [S*FBG_MAXP*3] {vBeg, nOwn, gBeg, nGen}, {hBeg, nHalo, nSlot, in-edge rows | stride<<8}, {pBeg, nPush, halo-reading threads, 0}
   float4* pub = nullptr;     // [2][S*maxV] tagged mailboxes (parity-major), L2 transport
   int* err = nullptr;        // mapped host flag: set by the watchdog
   uint32_t seq = 0;          // launch counter -> tag base
@@ -240,7 +240,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   if (g.nV[s] == 0) return;  // uniform over the stream's CTAs
   const int4* ci = a.cinfo + ((size_t)s * FBG_MAXP + r) * 3;
   const int4 c0 = ci[0], c1 = ci[1], c2 = ci[2];
-  const int nOwn = c0.y, nGen = c0.w, nHalo = c1.y, nPush = c2.y;
+  const int nOwn = c0.y, nGen = c0.w, nHalo = c1.y, nPush = c2.y, nHaloThr = c2.z;
   if (nOwn == 0) {  // an empty part owns nothing and feeds nobody
     if (CLUSTER) {
       fbc_cluster_sync();
@@ -341,6 +341,9 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   // warp-uniform work extents: fast rows any lane of the warp uses, generic row, vertex row
   const int rowsF = __reduce_max_sync(0xffffffffu, __popc(fvalid));
   const bool warpG = (tid & ~31) < nGen, warpV = (tid & ~31) < nOwn;
+  // only the first warps (boundary vertices, generic edges) ever read a halo entry: the others start
+  // the dual half-step without waiting for the hand-over
+  const bool warpH = (tid & ~31) < nHaloThr;
   // slots are slot-major: record (row p, entry n) at p * stride + n.  Entries are a permutation of the
   // thread index inside each aligned group of 8 and the stride is odd, so a warp's gather of one
   // row is conflict-free; rows [0, nT) hold the in-edges' contributions, rows [rowsIn, rowsIn + nO)
@@ -352,23 +355,24 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     const bool more = it + 1 < iters;
     const uint32_t rd_off = (it & 1) ? bank_bytes : 0u, wr_off = bank_bytes - rd_off;
     // ---- halo of iteration it-1 -----------------------------------------------------------------
-    if (it > 0) {
-      if (CLUSTER) {
-        if (nHalo) fbc_mbar_wait(mb0 + 8u * (uint32_t)(it & 1), (uint32_t)(((it + 1) >> 1) - 1) & 1u);
-      } else if (hv0 >= 0) {
-        const uint32_t tag = tag0 + (uint32_t)(it - 1);
-        const float4* pb = pub0 + (size_t)((it - 1) & 1) * a.pstride;
-        float4* hb = s_bar + ((it & 1) ? a.capBar : 0) + nEnt;
-        hb[tid] = fbg_poll(pb + hv0, tag, a.err, dead);
-        if (hv1 >= 0) {
-          hb[tid + THREADS] = fbg_poll(pb + hv1, tag, a.err, dead);
-          for (int h = tid + 2 * THREADS; h < nHalo; h += THREADS) hb[h] = fbg_poll(pb + hl[h], tag, a.err, dead);
-        }
+    if (!CLUSTER && it > 0 && hv0 >= 0) {
+      const uint32_t tag = tag0 + (uint32_t)(it - 1);
+      const float4* pb = pub0 + (size_t)((it - 1) & 1) * a.pstride;
+      float4* hb = s_bar + ((it & 1) ? a.capBar : 0) + nEnt;
+      hb[tid] = fbg_poll(pb + hv0, tag, a.err, dead);
+      if (hv1 >= 0) {
+        hb[tid + THREADS] = fbg_poll(pb + hv1, tag, a.err, dead);
+        for (int h = tid + 2 * THREADS; h < nHalo; h += THREADS) hb[h] = fbg_poll(pb + hl[h], tag, a.err, dead);
       }
     }
-    __syncthreads();  // own points (primal of it-1) and halo points visible to the edge threads
-    // every thread is past the wait: the barrier of this parity is re-armed for iteration it+2
-    if (CLUSTER && tid == 0 && nHalo && it > 0 && it + 2 < iters) fbc_mbar_expect(mb0 + 8u * (uint32_t)(it & 1), haloBytes);
+    __syncthreads();  // own points (primal of it-1) and polled halo points visible to the edge threads
+    if (CLUSTER && it > 0 && nHalo && warpH) {
+      // pushed halo points: only the warps that read them wait; the barrier of this parity is re-armed
+      // for iteration it+2 by thread 0 once it has seen the phase complete (waits are by parity, so a
+      // slower warp still finds this phase completed)
+      fbc_mbar_wait(mb0 + 8u * (uint32_t)(it & 1), (uint32_t)(((it + 1) >> 1) - 1) & 1u);
+      if (tid == 0 && it + 2 < iters) fbc_mbar_expect(mb0 + 8u * (uint32_t)(it & 1), haloBytes);
+    }
     // ---- dual half-step ---------------------------------------------------------------------------
     if (warpG) fbg_dual_rows<true>(rowsF, F, G, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma);
     else fbg_dual_rows<false>(rowsF, F, G, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma);
@@ -707,6 +711,17 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
       gpl[rj].push_back(make_int2(entry(rj, i) | (ent[j] << 16), nslot[rj] | ((pdst[e] * stride[rj] + ent[j]) << 16)));
       gid[rj].push_back(e | (int)0x80000000);
     }
+  }
+  // threads that read a halo entry: boundary vertices with a remote out-neighbour in a register row,
+  // and every generic edge (cut edges seen from the target side; overflow edges ride along)
+  for (int r = 0; r < nper; ++r) {
+    int last = (int)gpl[r].size();
+    for (int tl = 0; tl < cnt[r + 1] - cnt[r]; ++tl)
+      for (int k = 0; k < FBG_FAST; ++k) {
+        const size_t fi = (size_t)k * V + cnt[r] + tl;
+        if (g.feid[fi] >= 0 && (int)(g.fplan[fi] & 0xffffu) >= nent[r]) last = std::max(last, tl + 1);
+      }
+    g.cinfo[3 * r + 2].z = last;
   }
   for (int r = 0; r < nper; ++r) {
     if ((int)gpl[r].size() > threads) return false;
@@ -1150,6 +1165,7 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
         int code = 0;
         if (!check_end(r, e, j, true, 0, b, sl, true, code)) { why = msg[code]; return code; }
         if (owner[j] == r) hit[r][sl]++;
+        else if (k >= g.cinfo[3 * r + 2].z) { why = "halo read by a thread beyond the halo-reading bound"; return 17; }
         written[e]++;
       }
     }
