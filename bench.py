@@ -333,6 +333,7 @@ def gpu_main(args):
     t_res, launches, solve_ms, solve_calls = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "resident", barrier)
     variant_used = run.ctx.last_solver_variant()
     cluster_size = run.ctx.last_cluster_size()
+    transport = run.ctx.last_solver_transport()
     t_sync, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "e2e_sync", barrier)
     t_e2e, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "e2e_pipe", barrier)
     h2d, d2h = run.bytes_per_step()
@@ -380,7 +381,8 @@ def gpu_main(args):
                                    % (args.config, datas[0].W, datas[0].H, datas[0].V, datas[0].V, iters, S),
                        "streams_per_gpu": S, "vertices": datas[0].V, "edges": datas[0].E, "pd_iters": iters,
                        "solver_variant": {1: "streaming (2 kernels/iter, CUDA graph)", 2: "persistent cluster (DSMEM)",
-                                          3: "grid-resident (cooperative launch, tagged L2 mailboxes)"}.get(variant_used),
+                                          3: "resident, one exchange per iteration (%s)" % {1: "cluster of CTAs, DSMEM st.async hand-over",
+                                                                                               2: "cooperative grid, tagged 128-bit L2 mailboxes"}.get(transport, "?")}.get(variant_used),
                        "ctas_per_stream": cluster_size if variant_used in (2, 3) else None,
                        "l2": "value: device frame pool of %d MiB cycled through (> 126 MiB L2), no frame is cache-resident "
                              "when re-read; e2e: inputs streamed from pinned host memory; e2e_sync: 256 MiB memset "

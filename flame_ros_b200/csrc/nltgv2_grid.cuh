@@ -46,7 +46,8 @@
 
 #define FBG_FAST 4             // register rows: out-edges of the thread's own vertex
 #define FBG_THREADS_L2 256     // L2 transport: two CTAs per SM
-#define FBG_THREADS_CL 512     // cluster transport: one CTA per SM
+#define FBG_THREADS_CL 512     // cluster transport: largest CTA (one per SM); see FBG_CL for the others
+#define FBG_NCL 3
 #define FBG_MAXP 512           // parts per stream (table stride)
 #define FBG_MAXC 16            // largest cluster
 #define FBG_MAX_ITERS 16383    // tag space per launch (L2 transport)
@@ -67,9 +68,10 @@ struct GridPlan {
   int* err = nullptr;        // mapped host flag: set by the watchdog
   uint32_t seq = 0;          // launch counter -> tag base
   int max_blocks = -1;       // co-resident CTAs of the L2-transport kernel on this device
-  int max_clusters[FBG_MAXC + 1];  // co-resident clusters per cluster size (-1 = not queried)
-  size_t smem_set[2] = {0, 0};
-  bool nonportable_set = false;
+  int max_clusters[FBG_NCL][FBG_MAXC + 1];  // co-resident clusters per CTA shape and cluster size (-1 = not queried)
+  size_t smem_set[1 + FBG_NCL] = {0, 0, 0, 0};  // [0] L2 kernel, [1 + k] cluster kernel of shape k
+  int cl_cfg = 0;            // CTA shape (index into FBG_CL) of the last prepared cluster launch
+  int threads_env = 0;       // FB_GRID_THREADS: forced CTA size of the cluster transport
   int budget_env = 0;        // FB_GRID_CTAS: CTA budget of the L2 transport
   int cluster_env = 0;       // FB_GRID_CLUSTER: forced cluster size
   int mode_env = 0;          // FB_GRID_MODE: 1 = cluster only, 2 = L2 only
@@ -80,6 +82,7 @@ struct GridPlan {
   uint64_t version = 1, dec_version = 0;
   int dec_only = -2, dec_nper = 0;
   bool dec_cluster = false;
+  int dec_cfg = 0;
   size_t dec_smem = 0;
   struct Topo {
     std::vector<float2> pos;
@@ -95,7 +98,7 @@ struct GridPlan {
     std::vector<int4> vplan, cinfo;
   };
   std::vector<Topo> topo;
-  GridPlan() { std::fill(max_clusters, max_clusters + FBG_MAXC + 1, -1); }
+  GridPlan() { std::fill(&max_clusters[0][0], &max_clusters[0][0] + FBG_NCL * (FBG_MAXC + 1), -1); }
 };
 
 // ---------------------------------------------------------------------------------- device side
@@ -457,6 +460,18 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   if (CLUSTER) fbc_cluster_sync();  // no CTA retires while a peer could still address its shared memory
 }
 
+// CTA shapes of the cluster transport: 512 threads x 1 CTA per SM (126 registers), or smaller CTAs of
+// which two share an SM (<= 96 / 80 registers), so that two streams' phases overlap on one SM.
+struct FbgClCfg { int threads, per_sm; size_t smem_limit; };
+static const FbgClCfg FBG_CL[FBG_NCL] = {{512, 1, FBG_SMEM_LIMIT_CL}, {384, 2, FBG_SMEM_LIMIT_L2}, {320, 2, FBG_SMEM_LIMIT_L2}};
+static const void* fbg_cl_kernel(int k) {
+  switch (k) {
+    case 1: return (const void*)k_nltgv2_grid<384, 2, true>;
+    case 2: return (const void*)k_nltgv2_grid<320, 2, true>;
+    default: return (const void*)k_nltgv2_grid<512, 1, true>;
+  }
+}
+
 // ---------------------------------------------------------------------------------- host side
 static inline size_t fbg_smem_bytes(int capBar, int capSlot, int capPush) {
   return 16 * (2 * (size_t)capBar + (size_t)capSlot + 1) + 16 + 8 * (size_t)capPush;
@@ -771,6 +786,7 @@ static int grid_plan_init(fb_ctx* c) {
   FB_CUDA(c, cudaMemsetAsync(P->pub, 0, sizeof(float4) * 2 * S * c->maxV, c->stream));
   if (const char* e = getenv("FB_GRID_CTAS")) P->budget_env = atoi(e);
   if (const char* e = getenv("FB_GRID_CLUSTER")) P->cluster_env = std::max(0, std::min(FBG_MAXC, atoi(e)));
+  if (const char* e = getenv("FB_GRID_THREADS")) P->threads_env = atoi(e);
   if (const char* e = getenv("FB_GRID_MODE")) P->mode_env = (e[0] == 'c') ? 1 : (e[0] == 'l' ? 2 : 0);
   return FB_OK;
 }
@@ -820,21 +836,18 @@ static bool fbg_plan_all(fb_ctx* c, int only, int nper, int threads, size_t smem
   return true;
 }
 
-static int fbg_max_clusters(GridPlan* P, int C, size_t smem) {
-  if (P->max_clusters[C] >= 0) return P->max_clusters[C];
-  auto kern = k_nltgv2_grid<FBG_THREADS_CL, 1, true>;
-  if (P->smem_set[1] < FBG_SMEM_LIMIT_CL) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FBG_SMEM_LIMIT_CL);
-    P->smem_set[1] = FBG_SMEM_LIMIT_CL;
+static int fbg_max_clusters(GridPlan* P, int k, int C) {
+  if (P->max_clusters[k][C] >= 0) return P->max_clusters[k][C];
+  const void* kern = fbg_cl_kernel(k);
+  if (P->smem_set[1 + k] < FBG_CL[k].smem_limit) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBG_CL[k].smem_limit);
+    P->smem_set[1 + k] = FBG_CL[k].smem_limit;
   }
-  if (C > 8 && !P->nonportable_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    P->nonportable_set = true;
-  }
+  if (C > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t q{};
   q.gridDim = dim3((unsigned)(C * 64));
-  q.blockDim = dim3(FBG_THREADS_CL);
-  q.dynamicSmemBytes = std::max<size_t>(smem, 64 * 1024);  // registers (1 CTA / SM), not smem, bound residency
+  q.blockDim = dim3((unsigned)FBG_CL[k].threads);
+  q.dynamicSmemBytes = 64 * 1024;  // registers, not shared memory, bound residency
   cudaLaunchAttribute qa[1];
   qa[0].id = cudaLaunchAttributeClusterDimension;
   qa[0].val.clusterDim.x = (unsigned)C;
@@ -847,7 +860,7 @@ static int fbg_max_clusters(GridPlan* P, int C, size_t smem) {
     cudaGetLastError();
     n = 0;
   }
-  P->max_clusters[C] = n;
+  P->max_clusters[k][C] = n;
   return n;
 }
 
@@ -860,6 +873,7 @@ static int grid_prepare(fb_ctx* c, int iters, int only, int* nper_out, size_t* s
   if (P->dec_version == P->version && P->dec_only == only && (P->dec_cluster || iters <= FBG_MAX_ITERS)) {
     P->nper = P->dec_nper;  // nothing changed since the last launch: tables are on the device
     P->cluster = P->dec_cluster;
+    P->cl_cfg = P->dec_cfg;
     *nper_out = P->dec_nper;
     *smem_out = P->dec_smem;
     return FB_OK;
@@ -877,22 +891,43 @@ static int grid_prepare(fb_ctx* c, int iters, int only, int* nper_out, size_t* s
   // ---- cluster transport: the largest cluster size (<= 16) for which all active streams'
   // clusters are co-resident (one wave), never below ~128 vertices per CTA
   if (P->mode_env != 2) {
-    const int need = std::max(1, fb_div_up(maxV, FBG_THREADS_CL));
-    int cmax = std::min(FBG_MAXC, std::max(need, maxV / 128));
-    if (P->cluster_env > 0) cmax = std::max(need, P->cluster_env);
-    for (int cand = std::min(cmax, FBG_MAXC); cand >= need && cand >= 1 && !cluster; --cand) {
-      // co-residency first (cheap, cached per size), then the tables
-      if (P->cluster_env == 0 && fbg_max_clusters(P, cand, 0) < n_act) continue;
-      if (!fbg_plan_all(c, only, cand, FBG_THREADS_CL, FBG_SMEM_LIMIT_CL)) continue;
-      nper = cand;
-      cluster = true;
+    // CTA shape: FB_GRID_THREADS forces one; otherwise one 512-thread CTA per SM while all streams'
+    // clusters are co-resident (measured, C2: 8 streams 74 us against 94 us with two 320-thread CTAs
+    // per SM), and the two-per-SM shapes for larger batches (12 streams: 98 us against 135 us in two
+    // waves of 512-thread clusters)
+    int order[FBG_NCL], norder = 0;
+    for (int k = 0; k < FBG_NCL; ++k)
+      if (P->threads_env == FBG_CL[k].threads) order[norder++] = k;
+    if (norder == 0) {
+      order[norder++] = 0;
+      order[norder++] = 2;
+      order[norder++] = 1;
     }
-    // more streams than co-resident clusters of any size: the smallest feasible cluster, in waves
-    // (streams are independent, so clusters need not run at the same time)
-    for (int cand = need; cand <= FBG_MAXC && !cluster; ++cand) {
-      if (!fbg_plan_all(c, only, cand, FBG_THREADS_CL, FBG_SMEM_LIMIT_CL)) continue;
-      nper = cand;
-      cluster = true;
+    for (int oi = 0; oi < norder && !cluster; ++oi) {
+      const int k = order[oi], thr = FBG_CL[k].threads;
+      const int need = std::max(1, fb_div_up(maxV, thr));
+      if (need > FBG_MAXC) continue;
+      int cmax = std::min(FBG_MAXC, std::max(need, maxV / 128));
+      if (P->cluster_env > 0) cmax = std::max(need, std::min(FBG_MAXC, P->cluster_env));
+      for (int cand = cmax; cand >= need && cand >= 1 && !cluster; --cand) {
+        // co-residency first (cheap, cached per shape and size), then the tables
+        if (P->cluster_env == 0 && fbg_max_clusters(P, k, cand) < n_act) continue;
+        if (!fbg_plan_all(c, only, cand, thr, FBG_CL[k].smem_limit)) continue;
+        nper = cand;
+        cluster = true;
+        P->cl_cfg = k;
+      }
+    }
+    // more streams than co-resident clusters of any size: the smallest feasible cluster of the largest
+    // CTA shape, in waves (streams are independent, so clusters need not run at the same time)
+    for (int oi = 0; oi < norder && !cluster; ++oi) {
+      const int k = order[oi], thr = FBG_CL[k].threads;
+      for (int cand = std::max(1, fb_div_up(maxV, thr)); cand <= FBG_MAXC && !cluster; ++cand) {
+        if (!fbg_plan_all(c, only, cand, thr, FBG_CL[k].smem_limit)) continue;
+        nper = cand;
+        cluster = true;
+        P->cl_cfg = k;
+      }
     }
   }
   // ---- L2 transport: all co-resident CTAs shared by the streams of the launch
@@ -974,6 +1009,7 @@ static int grid_prepare(fb_ctx* c, int iters, int only, int* nper_out, size_t* s
   P->dec_only = only;
   P->dec_nper = nper;
   P->dec_cluster = cluster;
+  P->dec_cfg = P->cl_cfg;
   P->dec_smem = *smem_out;
   return FB_OK;
 }
@@ -1010,22 +1046,25 @@ static int solve_grid(fb_ctx* c, int iters, const fb_nltgv2_params* p, int nper,
   cfg.numAttrs = 1;
   const float tl = p->step_x * p->data_factor;
   if (P->cluster) {
-    auto kern = k_nltgv2_grid<FBG_THREADS_CL, 1, true>;
-    if (P->smem_set[1] < smem) {
-      FB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FBG_SMEM_LIMIT_CL));
-      P->smem_set[1] = FBG_SMEM_LIMIT_CL;
+    const int k = P->cl_cfg;
+    const void* kern = fbg_cl_kernel(k);
+    if (P->smem_set[1 + k] < smem) {
+      FB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBG_CL[k].smem_limit));
+      P->smem_set[1 + k] = FBG_CL[k].smem_limit;
     }
-    if (nper > 8 && !P->nonportable_set) {
-      FB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      P->nonportable_set = true;
-    }
-    cfg.blockDim = dim3(FBG_THREADS_CL);
+    if (nper > 8) FB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cfg.blockDim = dim3((unsigned)FBG_CL[k].threads);
     attr[0].id = cudaLaunchAttributeClusterDimension;  // streams are independent: clusters may run in waves
     attr[0].val.clusterDim.x = (unsigned)nper;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    float sq = p->step_q, sx = p->step_x, th = p->theta, x0 = p->x_min, x1 = p->x_max, tlv = tl;
+    uint32_t tg = tag0;
+    int itv = iters;
+    void* args[] = {&a, &itv, &sq, &sx, &tlv, &th, &x0, &x1, &tg};
     ProfScope ps(c, FB_PROF_SOLVE);
-    FB_CUDA(c, cudaLaunchKernelEx(&cfg, kern, a, iters, p->step_q, p->step_x, tl, p->theta, p->x_min, p->x_max, tag0));
+    FB_CUDA(c, cudaLaunchKernelExC(&cfg, kern, args));
+    c->last_threads = FBG_CL[k].threads;
   } else {
     auto kern = k_nltgv2_grid<FBG_THREADS_L2, 2, false>;
     cfg.blockDim = dim3(FBG_THREADS_L2);
@@ -1033,6 +1072,7 @@ static int solve_grid(fb_ctx* c, int iters, const fb_nltgv2_params* p, int nper,
     attr[0].val.cooperative = 1;
     ProfScope ps(c, FB_PROF_SOLVE);
     FB_CUDA(c, cudaLaunchKernelEx(&cfg, kern, a, iters, p->step_q, p->step_x, tl, p->theta, p->x_min, p->x_max, tag0));
+    c->last_threads = FBG_THREADS_L2;
   }
   c->launches++;
   return FB_OK;

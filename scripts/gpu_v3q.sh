@@ -11,8 +11,12 @@ except Exception as e:
 "
 }
 B="--steps 100 --no-single --no-cpu-baseline"
-timeout 200 python bench.py --streams 1 --variant 3 $B 2>/tmp/err.txt | line "S=1 v3 auto"; tail -2 /tmp/err.txt
+for T in 512 384 320; do
+for S in 1 8 12; do
+FB_GRID_THREADS=$T timeout 200 python bench.py --streams $S --variant 3 $B 2>/tmp/err.txt | line "S=$S v3 threads=$T"; tail -2 /tmp/err.txt
+done
+done
 timeout 200 python bench.py --streams 8 --variant 3 $B 2>/tmp/err.txt | line "S=8 v3 auto"; tail -2 /tmp/err.txt
 timeout 300 python bench.py --config C4 --streams 1 --variant 3 --steps 40 --warmup 5 --no-single --no-cpu-baseline 2>/tmp/err.txt | line "C4 v3"; tail -2 /tmp/err.txt
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_nltgv2_grid -s 3 -c 1 -o gpurun_out/prof_grid_r1_v8 python bench.py --steps 6 --warmup 3 --variant 3 --no-single --no-cpu-baseline > gpurun_out/ncu_grid.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_nltgv2_grid -s 3 -c 1 -o gpurun_out/prof_grid_r1_v9 python bench.py --steps 6 --warmup 3 --variant 3 --no-single --no-cpu-baseline > gpurun_out/ncu_grid.log 2>&1
 tail -2 gpurun_out/ncu_grid.log

@@ -70,6 +70,7 @@ def test_grid_solver_is_partition_and_transport_invariant(capi, oracle, mode, kn
     on both sides of a cut with bit-identical results) nor on the halo transport."""
     monkeypatch.setenv("FB_GRID_MODE", mode)
     monkeypatch.setenv(knob, val)
+    monkeypatch.setenv("FB_GRID_THREADS", "512")
     g = small_graph(40, 30, 320, 240, seed=5)
     ref = run_oracle(oracle, g, 31)
     with capi.Context(1, 320, 240, 2, 16, 1200, 3600) as ctx:
@@ -95,6 +96,23 @@ def test_grid_solver_short_solves(capi, oracle, mode, iters, monkeypatch):
         ctx.nltgv2_solve(iters, variant=3)
         got = ctx.graph_state_get(0)
     assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
+
+
+@pytest.mark.parametrize("threads", ["512", "384", "320"])
+def test_c2_grid_solver_cluster_cta_shapes(capi, oracle, threads, monkeypatch):
+    """Cluster transport with one 512-thread CTA per SM or two smaller CTAs per SM: same bits."""
+    monkeypatch.setenv("FB_GRID_MODE", "cluster")
+    monkeypatch.setenv("FB_GRID_THREADS", threads)
+    g = synth.s_graph("C2")
+    ref = run_oracle(oracle, g, 50)
+    with capi.Context(2, 640, 480, 2, 16, 5000, 15000) as ctx:
+        for s in range(2):
+            gpu_load_graph(ctx, s, g)
+        ctx.nltgv2_solve(50, variant=3)
+        assert ctx.last_solver_transport() == 1
+        for s in range(2):
+            got = ctx.graph_state_get(s)
+            assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
 
 
 @pytest.mark.parametrize("mode", ["l2", "cluster"])
