@@ -119,6 +119,13 @@ __device__ __forceinline__ void fbg_st_mailbox(float4* p, float a, float b, floa
                "l"(lo), "l"(hi)
                : "memory");
 }
+// Predicated 16 B shared-memory store (no branch): rows without a local target store nothing.
+__device__ __forceinline__ void fbg_sts_if(uint32_t addr, float4 v, uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(addr),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(pred)
+      : "memory");
+}
 // Poll one mailbox until it carries `tag`; returns the point.  A reader that never sees its tag
 // (a bug, or a grid that is not co-resident) raises the context's error flag instead of hanging.
 __device__ __forceinline__ float4 fbg_poll(const float4* p, uint32_t tag, int* err, bool& dead) {
@@ -158,6 +165,7 @@ struct GridArgs {
 struct FbgFast {  // register-resident out-edges of the thread's own vertex (source = own vertex)
   float q1[FBG_FAST], q2[FBG_FAST], q3[FBG_FAST], a[FBG_FAST], b[FBG_FAST], dx[FBG_FAST], dy[FBG_FAST];
   uint32_t idx[FBG_FAST];  // target's s_bar entry | target's slot << 16 (dummy slot when the target is remote)
+  uint32_t store;          // bit k: row k has a local target slot; bits 8 / 9: the generic edge's source / target slot
 };
 struct FbgGen {  // register-resident generic edge (both endpoints through shared memory)
   float q1, q2, q3, a, b, dx, dy;
@@ -168,8 +176,8 @@ struct FbgGen {  // register-resident generic edge (both endpoints through share
 // its generic edge.  For an out-edge the source's extragradient point is in registers; only the
 // target's is read from shared memory, only the target's contribution is written to a slot (the
 // source's is re-derived from q in the primal half-step).  All loads are issued before the first
-// dependent instruction and the stores are unconditional (idle rows and remote targets write to the
-// dummy slot), so the rows are independent branch-free instruction streams that overlap.
+// dependent instruction and the stores are predicated, not branched around (idle rows and remote
+// targets store nothing), so the rows are independent branch-free instruction streams that overlap.
 template <int R, bool GEN>
 __device__ __forceinline__ void fbg_dual(FbgFast& F, FbgGen& G, float xb, float w1b, float w2b, uint32_t bar_rd,
                                          uint32_t slot_base, float sigma) {
@@ -206,13 +214,14 @@ __device__ __forceinline__ void fbg_dual(FbgFast& F, FbgGen& G, float xb, float 
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     const float a1 = F.a[k] * F.q1[k];
-    fbc_sts(slot_base + ((F.idx[k] >> 16) << 4), make_float4(-a1, -(F.b[k] * F.q2[k]), -(F.b[k] * F.q3[k]), 0.f));
+    fbg_sts_if(slot_base + ((F.idx[k] >> 16) << 4), make_float4(-a1, -(F.b[k] * F.q2[k]), -(F.b[k] * F.q3[k]), 0.f),
+               F.store & (1u << k));
   }
   if (GEN) {
     const float a1 = G.a * G.q1;
-    fbc_sts(slot_base + ((G.slot & 0xffffu) << 4),
-            make_float4(a1, fmaf(G.b, G.q2, -(G.dx * a1)), fmaf(G.b, G.q3, -(G.dy * a1)), 0.f));
-    fbc_sts(slot_base + ((G.slot >> 16) << 4), make_float4(-a1, -(G.b * G.q2), -(G.b * G.q3), 0.f));
+    fbg_sts_if(slot_base + ((G.slot & 0xffffu) << 4),
+               make_float4(a1, fmaf(G.b, G.q2, -(G.dx * a1)), fmaf(G.b, G.q3, -(G.dy * a1)), 0.f), F.store & 0x100u);
+    fbg_sts_if(slot_base + ((G.slot >> 16) << 4), make_float4(-a1, -(G.b * G.q2), -(G.b * G.q3), 0.f), F.store & 0x200u);
   }
 }
 template <bool GEN>
@@ -273,6 +282,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     F.q1[k] = F.q2[k] = F.q3[k] = F.a[k] = F.b[k] = F.dx[k] = F.dy[k] = 0.f;
     F.idx[k] = dummy << 16;
   }
+  F.store = 0u;
   if (tid < nOwn) {
     const int4 pt = a.vplan[vb + c0.x + tid];
     const int v = pt.x;
@@ -292,6 +302,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
       if (id >= 0) {
         fvalid |= 1u << k;
         F.idx[k] = a.fplan[fi];
+        if ((F.idx[k] >> 16) != dummy) F.store |= 1u << k;
         const float4 c = g.ec[eb + id];
         const float4 q = g.q4[eb + id];
         F.a[k] = c.x; F.b[k] = c.y; F.dx[k] = c.z; F.dy[k] = c.w;
@@ -313,6 +324,8 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     G.q1 = q.x; G.q2 = q.y; G.q3 = q.z;
     G.bar = (uint32_t)pl.x;
     G.slot = (uint32_t)pl.y;
+    if ((G.slot & 0xffffu) != dummy) F.store |= 0x100u;
+    if ((G.slot >> 16) != dummy) F.store |= 0x200u;
   }
   // halo: the first value comes straight from global memory (written by earlier kernels of the
   // stream); L2 transport keeps the vertex ids of a thread's first two entries in registers
