@@ -326,6 +326,20 @@ def gpu_main(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     peak, peak_src = peaks()
 
+    # host->device link rate of this box (pinned memory, 64 MiB, best of 5): the e2e leg uploads every
+    # frame, so frames/s x bytes/frame cannot exceed it -- reported next to e2e as its own roofline
+    hbuf = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    dbuf = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    link_gbs = 0.0
+    for _ in range(5):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        dbuf.copy_(hbuf, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        link_gbs = max(link_gbs, (64 << 20) / (ev0.elapsed_time(ev1) * 1e-3) / 1e9)
+    del hbuf, dbuf
+
     run = GpuRun(capi, datas, local_rank, stream_ptr, args.variant)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -395,7 +409,9 @@ def gpu_main(args):
                                  "e2e_sync: blocking call per step with the L2 flush between steps"},
             "solver_iters_per_second": frames * iters / t_res,
             "e2e": {"value": frames / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * t_e2e / args.steps, "mode": "pipelined"},
+                    "ms_per_step": 1e3 * t_e2e / args.steps, "mode": "pipelined",
+                    "h2d_link_gbs": link_gbs,
+                    "h2d_link_frac": (h2d * args.steps / t_e2e / 1e9) / link_gbs if link_gbs > 0 else None},
             "e2e_sync": {"value": frames / t_sync, "unit": UNIT, "ms_per_step": 1e3 * t_sync / args.steps,
                          "mode": "blocking call per step, L2 flushed between steps"},
             "gpu_launches": launches_all,

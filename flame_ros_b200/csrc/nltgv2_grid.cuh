@@ -63,7 +63,7 @@ struct GridPlan {
   int4* vplan = nullptr;     // [S*maxV] {vertex id, n_target | n_overflow<<8 | entry<<16, push begin | end<<16, 0}
   int32_t* hplan = nullptr;  // [S*2*maxE] halo lists: stream-local vertex ids
   int2* pplan = nullptr;     // [S*2*maxE] push lists: {consumer part, entry index in its s_bar}
-  int4* cinfo = nullptr;     // [S*FBG_MAXP*3] {vBeg, nOwn, gBeg, nGen}, {hBeg, nHalo, nSlot, in-edge rows | stride<<8}, {pBeg, nPush, halo-reading threads, 0}
+  int4* cinfo = nullptr;     // [S*FBG_MAXP*3] {vBeg, nOwn, gBeg, nGen}, {hBeg, nHalo, nSlot, in-edge rows | stride<<8}, {pBeg, nPush, first halo-reading thread, 0}
   float4* pub = nullptr;     // [2][S*maxV] tagged mailboxes (parity-major), L2 transport
   int* err = nullptr;        // mapped host flag: set by the watchdog
   uint32_t seq = 0;          // launch counter -> tag base
@@ -252,7 +252,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   if (g.nV[s] == 0) return;  // uniform over the stream's CTAs
   const int4* ci = a.cinfo + ((size_t)s * FBG_MAXP + r) * 3;
   const int4 c0 = ci[0], c1 = ci[1], c2 = ci[2];
-  const int nOwn = c0.y, nGen = c0.w, nHalo = c1.y, nPush = c2.y, nHaloThr = c2.z;
+  const int nOwn = c0.y, nGen = c0.w, nHalo = c1.y, nPush = c2.y, haloLo = c2.z;
   if (nOwn == 0) {  // an empty part owns nothing and feeds nobody
     if (CLUSTER) {
       fbc_cluster_sync();
@@ -315,9 +315,10 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   G.bar = 0u;
   G.slot = dummy | (dummy << 16);
   int g_id = -1;
-  if (tid < nGen) {
-    const int2 pl = a.gplan[2 * eb + c0.z + tid];
-    g_id = a.geid[2 * eb + c0.z + tid];
+  const int gi = THREADS - 1 - tid;  // generic edges sit at the back of the CTA (see warpH below)
+  if (gi < nGen) {
+    const int2 pl = a.gplan[2 * eb + c0.z + gi];
+    g_id = a.geid[2 * eb + c0.z + gi];
     const float4 c = g.ec[eb + (g_id & 0x7fffffff)];
     const float4 q = g.q4[eb + (g_id & 0x7fffffff)];
     G.a = c.x; G.b = c.y; G.dx = c.z; G.dy = c.w;
@@ -356,10 +357,11 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   bool dead = false;
   // warp-uniform work extents: fast rows any lane of the warp uses, generic row, vertex row
   const int rowsF = __reduce_max_sync(0xffffffffu, __popc(fvalid));
-  const bool warpG = (tid & ~31) < nGen, warpV = (tid & ~31) < nOwn;
-  // only the first warps (boundary vertices, generic edges) ever read a halo entry: the others start
-  // the dual half-step without waiting for the hand-over
-  const bool warpH = (tid & ~31) < nHaloThr;
+  const bool warpG = (THREADS - 1 - (tid | 31)) < nGen, warpV = (tid & ~31) < nOwn;
+  // only the LAST warps (boundary vertices, generic edges) ever read a halo entry: the others start the
+  // dual half-step without waiting for the hand-over.  The warps on the exchange's critical path are
+  // the high-numbered ones on purpose: the SMSP arbiter issues the highest warp id first.
+  const bool warpH = (tid | 31) >= haloLo;
   // slots are slot-major: record (row p, entry n) at p * stride + n.  Entries are a permutation of the
   // thread index inside each aligned group of 8 and the stride is odd, so a warp's gather of one
   // row is conflict-free; rows [0, nT) hold the in-edges' contributions, rows [rowsIn, rowsIn + nO)
@@ -384,10 +386,10 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     __syncthreads();  // own points (primal of it-1) and polled halo points visible to the edge threads
     if (CLUSTER && it > 0 && nHalo && warpH) {
       // pushed halo points: only the warps that read them wait; the barrier of this parity is re-armed
-      // for iteration it+2 by thread 0 once it has seen the phase complete (waits are by parity, so a
+      // for iteration it+2 by one of the waiting threads once it has seen the phase complete (waits are by parity, so a
       // slower warp still finds this phase completed)
       fbc_mbar_wait(mb0 + 8u * (uint32_t)(it & 1), (uint32_t)(((it + 1) >> 1) - 1) & 1u);
-      if (tid == 0 && it + 2 < iters) fbc_mbar_expect(mb0 + 8u * (uint32_t)(it & 1), haloBytes);
+      if (tid == haloLo && it + 2 < iters) fbc_mbar_expect(mb0 + 8u * (uint32_t)(it & 1), haloBytes);
     }
     // ---- dual half-step ---------------------------------------------------------------------------
     if (warpG) fbg_dual_rows<true>(rowsF, F, G, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma);
@@ -584,7 +586,8 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
     if (part[t.eij[e].x] != part[t.eij[e].y]) bnd[t.eij[e].x] = bnd[t.eij[e].y] = 1;
   for (int v = 0; v < V; ++v)
     for (int k = t.row[v]; k < t.row[v] + nin[v]; ++k) pdst[t.inc[k] >> 1] = k - t.row[v];
-  // thread order per part: boundary vertices first, then by in-degree and out-degree -- the lanes of a
+  // thread order per part: interior vertices, then boundary vertices (the high-numbered warps are
+  // issued first by the SMSP arbiter and carry the exchange), each by in-degree and out-degree -- the lanes of a
   // warp then run equally many slot rows and register rows.  Shared-memory records are addressed through an ENTRY index that
   // is a permutation of the thread index inside each aligned group of 8 (chosen below), slots are
   // slot-major with an odd row stride: record (row p, entry n) at p * stride + n.
@@ -599,7 +602,7 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
   std::vector<int> lidx(V), ent(V), nent(nper), stride(nper), rows_in(nper, 0), nslot(nper, 0);
   for (int r = 0; r < nper; ++r) {
     std::sort(order.begin() + cnt[r], order.begin() + cnt[r + 1], [&](int u, int v) {
-      if (bnd[u] != bnd[v]) return bnd[u] > bnd[v];  // boundary vertices first: few warps run the hand-over
+      if (bnd[u] != bnd[v]) return bnd[u] < bnd[v];  // boundary vertices last: few warps run the hand-over
       if (nin[u] != nin[v]) return nin[u] > nin[v];
       if (deg[u] != deg[v]) return deg[u] > deg[v];
       return u < v;
@@ -740,16 +743,17 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
       gid[rj].push_back(e | (int)0x80000000);
     }
   }
-  // threads that read a halo entry: boundary vertices with a remote out-neighbour in a register row,
-  // and every generic edge (cut edges seen from the target side; overflow edges ride along)
+  // first thread that reads a halo entry: boundary vertices with a remote out-neighbour in a register
+  // row sit at the end of the own threads, generic edges (cut edges seen from the target side;
+  // overflow edges ride along) occupy the last threads of the CTA
   for (int r = 0; r < nper; ++r) {
-    int last = (int)gpl[r].size();
-    for (int tl = 0; tl < cnt[r + 1] - cnt[r]; ++tl)
+    int first = threads - (int)gpl[r].size();
+    for (int tl = 0; tl < cnt[r + 1] - cnt[r] && tl < first; ++tl)
       for (int k = 0; k < FBG_FAST; ++k) {
         const size_t fi = (size_t)k * V + cnt[r] + tl;
-        if (g.feid[fi] >= 0 && (int)(g.fplan[fi] & 0xffffu) >= nent[r]) last = std::max(last, tl + 1);
+        if (g.feid[fi] >= 0 && (int)(g.fplan[fi] & 0xffffu) >= nent[r]) first = std::min(first, tl);
       }
-    g.cinfo[3 * r + 2].z = last;
+    g.cinfo[3 * r + 2].z = std::max(0, std::min(first, threads - 1));
   }
   for (int r = 0; r < nper; ++r) {
     if ((int)gpl[r].size() > threads) return false;
@@ -1218,7 +1222,7 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
         int code = 0;
         if (!check_end(r, e, j, true, 0, b, sl, true, code)) { why = msg[code]; return code; }
         if (owner[j] == r) hit[r][sl]++;
-        else if (k >= g.cinfo[3 * r + 2].z) { why = "halo read by a thread beyond the halo-reading bound"; return 17; }
+        else if (k < g.cinfo[3 * r + 2].z) { why = "halo read by a thread below the halo-reading bound"; return 17; }
         written[e]++;
       }
     }
@@ -1235,6 +1239,7 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
       const int bi = pl.x & 0xffff, bj = (int)((uint32_t)pl.x >> 16), si = pl.y & 0xffff, sj = (int)((uint32_t)pl.y >> 16);
       const bool wb = code_e >= 0;
       int code = 0;
+      if (threads - 1 - k < g.cinfo[3 * r + 2].z) { why = "generic edge on a thread below the halo-reading bound"; return 17; }
       if (wb) {  // overflowed out-edge of an own vertex
         if (owner[i] != r) { why = "write-back copy must live with the source vertex"; return 11; }
         if (!check_end(r, e, i, false, ovf_seen[i], bi, si, true, code)) { why = msg[code]; return code; }
