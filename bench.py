@@ -295,6 +295,9 @@ def gpu_main(args):
         raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -426,7 +429,7 @@ def gpu_main(args):
         }
         if single:
             out["single_stream"] = single
-    if rank == 0 and world >= 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # the CPU baseline is an N=1 figure
         out["cpu_baseline"] = cpu_baseline(args, datas, sample_steps=3)
     if world > 1:
         dist.barrier()
