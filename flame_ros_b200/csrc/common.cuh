@@ -115,6 +115,7 @@ struct fb_ctx {
   fb_nltgv2_params solve_params{};
   int last_variant = 0;
   int last_cluster = 0;  // cluster size of the last variant-2 launch / parts per stream of variant 3
+  bool grid_disabled = false;  // variant 3 launch refused once by the device: auto stops trying it
   int last_threads = 0;    // variant 3: threads per CTA of the last launch
   int last_transport = 0;  // variant 3: 1 = cluster (DSMEM st.async), 2 = L2 mailboxes
   int cluster_min = 1;  // FB_CLUSTER_MIN env: lower bound on the cluster size of variant 2

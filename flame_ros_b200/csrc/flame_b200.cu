@@ -418,7 +418,7 @@ extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, 
   if (!p || iters < 0 || variant < 0 || variant > 3) FB_FAIL(c, FB_E_ARG, "fb_nltgv2_solve: bad argument");
   if (iters == 0) return FB_OK;
   int v = variant;
-  if (v == 0 || v == 3) {
+  if ((v == 0 && !c->grid_disabled) || v == 3) {
     int nper = 0;
     size_t smem = 0;
     {
@@ -427,9 +427,15 @@ extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, 
     }
     if (nper > 0) {
       c->last_variant = 3;
-      return solve_grid(c, iters, p, nper, smem);
+      const int rc = solve_grid(c, iters, p, nper, smem);
+      if (rc == FB_OK || v == 3) return rc;
+      // auto: a launch configuration this device / driver refuses (cluster size, cooperative launch)
+      // is an error of the launch call itself -- nothing ran; remember it and use the other variants
+      cudaGetLastError();
+      c->grid_disabled = true;
+    } else if (v == 3) {
+      FB_FAIL(c, FB_E_STATE, "fb_nltgv2_solve: the batch does not fit the grid-resident solver");
     }
-    if (v == 3) FB_FAIL(c, FB_E_STATE, "fb_nltgv2_solve: the batch does not fit the grid-resident solver");
   }
   if (v == 0) v = cluster_plan_ready(c) ? 2 : 1;
   if (v == 2 && !cluster_plan_ready(c))
