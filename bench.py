@@ -136,7 +136,7 @@ class GpuRun:
         E = max(d.E for d in datas)
         self.ctx = capi.Context(self.S, d0.W, d0.H, WL.N_SLOTS, V, V, E, device=device, cuda_stream=cuda_stream)
         self.params = capi.default_nltgv2_params()
-        self.iters = d0.iters
+        self.iters = int(os.environ.get("FB_BENCH_PD_ITERS", d0.iters))   # diagnosis only: host-bound floor of the legs
         ctx = self.ctx
         # device frame pool, replicated so that the pool the resident leg cycles through is larger
         # than the 126 MB L2 (a frame is re-read only after > L2 bytes of other frames went by)

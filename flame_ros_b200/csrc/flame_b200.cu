@@ -795,8 +795,8 @@ static int pipeline_upload(fb_ctx* c, int slot, const uint8_t* const* images, co
   }
   // Device-pool frames of a step usually sit at a constant stride (entries of one replica): then they
   // go as ONE pitched device-to-device copy instead of S launches (measured, 8 streams: 93 -> 89 us
-  // per step).  Host frames keep one linear copy each: a pitched H2D copy of the same 8 frames was
-  // slower on this box (122 -> 135 us per step).
+  // per step).  Host frames keep one linear copy each: a pitched H2D copy and a cudaMemcpyBatchAsync
+  // of the same 8 frames were both slower on this box (122 -> 135 / 134 us per step).
   uint8_t* dst0 = c->imgs + (size_t)slot * fsz;
   const size_t dpitch = (size_t)c->n_slots * fsz;
   ptrdiff_t stride = 0;
