@@ -689,7 +689,7 @@ static bool fbg_build(GridPlan::Topo& g, const ClusterPlan::Topo& t, int nper, i
       }
       return fbg_group_pairs(ld, n) + fbg_group_pairs(st, n);
     };
-    for (int sweep = 0; sweep < 12; ++sweep) {
+    for (int sweep = 0; sweep < 2; ++sweep) {
       bool improved = false;
       for (int q = 0; q < ngrp; ++q) {
         const int lo = q * 8, hi = std::min(nOwn, lo + 8);
