@@ -160,6 +160,7 @@ struct GridArgs {
   int capBar;      // records per s_bar bank
   int capSlot;     // slot records (+1 dummy)
   size_t pstride;  // S*maxV: distance between the two mailbox banks
+  long long* trace;  // FBG_TRACE builds: [CTA][iteration][6] clock64 stamps of thread 0 (else unused)
 };
 
 struct FbgFast {  // register-resident out-edges of the thread's own vertex (source = own vertex)
@@ -369,8 +370,16 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
   const int nT = (int)(v_sl & 0xffu), nO = (int)((v_sl >> 8) & 0xffu), ent = (int)(v_sl >> 16);
   const int rowsT = __reduce_max_sync(0xffffffffu, nT), rowsO = __reduce_max_sync(0xffffffffu, nO);
 
+// Phase trace (scripts/grid_trace.py; build with FB_NVCC_EXTRA=-DFBG_TRACE): thread 0 of every CTA
+// stamps clock64 at the phase boundaries of the first 64 iterations.  Compiled out otherwise.
+#ifdef FBG_TRACE
+#define FBG_STAMP(k) if (a.trace && tid == 0 && it < 64) a.trace[((size_t)blockIdx.x * 64 + it) * 6 + (k)] = clock64();
+#else
+#define FBG_STAMP(k)
+#endif
   for (int it = 0; it < iters; ++it) {
     const bool more = it + 1 < iters;
+    FBG_STAMP(0)
     const uint32_t rd_off = (it & 1) ? bank_bytes : 0u, wr_off = bank_bytes - rd_off;
     // ---- halo of iteration it-1 -----------------------------------------------------------------
     if (!CLUSTER && it > 0 && hv0 >= 0) {
@@ -383,7 +392,9 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
         for (int h = tid + 2 * THREADS; h < nHalo; h += THREADS) hb[h] = fbg_poll(pb + hl[h], tag, a.err, dead);
       }
     }
+    FBG_STAMP(1)
     __syncthreads();  // own points (primal of it-1) and polled halo points visible to the edge threads
+    FBG_STAMP(2)
     if (CLUSTER && it > 0 && nHalo && warpH) {
       // pushed halo points: only the warps that read them wait; the barrier of this parity is re-armed
       // for iteration it+2 by one of the waiting threads once it has seen the phase complete (waits are by parity, so a
@@ -394,7 +405,9 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     // ---- dual half-step ---------------------------------------------------------------------------
     if (warpG) fbg_dual_rows<true>(rowsF, F, G, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma);
     else fbg_dual_rows<false>(rowsF, F, G, xb, w1b, w2b, bar_base + rd_off, slot_base, sigma);
+    FBG_STAMP(3)
     __syncthreads();  // slots complete
+    FBG_STAMP(4)
     // ---- primal half-step: CSR order = target-role slots, own out-edges, overflow slots -----------
     if (warpV) {
       float gx = 0.f, g1 = 0.f, g2 = 0.f;
@@ -458,6 +471,7 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
         }
       }
     }
+    FBG_STAMP(5)
   }
 
   // ---- write back: registers -> global -----------------------------------------------------------
@@ -1052,6 +1066,16 @@ static int solve_grid(fb_ctx* c, int iters, const fb_nltgv2_params* p, int nper,
   a.capBar = P->capBar;
   a.capSlot = P->capSlot;
   a.pstride = (size_t)c->S * c->maxV;
+  a.trace = nullptr;
+#ifdef FBG_TRACE
+  static long long* d_trace = nullptr;
+  const size_t trace_n = (size_t)((only >= 0 ? 1 : c->S) * nper) * 64 * 6;
+  if (getenv("FB_GRID_TRACE")) {
+    if (!d_trace) cudaMalloc((void**)&d_trace, sizeof(long long) * 1024 * 64 * 6);
+    cudaMemsetAsync(d_trace, 0, sizeof(long long) * trace_n, c->stream);
+    a.trace = d_trace;
+  }
+#endif
   c->last_cluster = nper;
   c->last_transport = P->cluster ? 1 : 2;
   cudaLaunchConfig_t cfg{};
@@ -1091,6 +1115,17 @@ static int solve_grid(fb_ctx* c, int iters, const fb_nltgv2_params* p, int nper,
     FB_CUDA(c, cudaLaunchKernelEx(&cfg, kern, a, iters, p->step_q, p->step_x, tl, p->theta, p->x_min, p->x_max, tag0));
     c->last_threads = FBG_THREADS_L2;
   }
+#ifdef FBG_TRACE
+  if (a.trace) {  // debugging aid: dump the stamps of this launch (synchronises)
+    std::vector<long long> h(trace_n);
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(h.data(), d_trace, sizeof(long long) * trace_n, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(getenv("FB_GRID_TRACE"), "wb")) {
+      fwrite(h.data(), sizeof(long long), trace_n, f);
+      fclose(f);
+    }
+  }
+#endif
   c->launches++;
   return FB_OK;
 }
