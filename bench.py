@@ -296,8 +296,9 @@ def gpu_main(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (this image's default) and at WARN; INFO/TRACE asked for by the user is left alone
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
