@@ -130,8 +130,19 @@ struct Triangulator {
     return -1;
   }
 
+  // scratch of insert(): plain arrays with explicit counts (push_back bookkeeping was ~25 % of an
+  // insertion); `mark` holds the stamp of the insertion that last put a triangle into a cavity
   std::vector<int> cavity, stack_, bnd_a, bnd_b, bnd_out, bnd_new;
   std::vector<int> mark, vslot;
+  int stamp = 0;
+
+  void grow_scratch(size_t need) {
+    if (cavity.size() < need) {
+      const size_t cap = std::max<size_t>(2 * need, 64);
+      cavity.resize(cap); stack_.resize(cap);
+      bnd_a.resize(3 * cap); bnd_b.resize(3 * cap); bnd_out.resize(3 * cap); bnd_new.resize(3 * cap);
+    }
+  }
 
   bool insert(int p) {
     int t0 = locate(p);
@@ -160,63 +171,60 @@ struct Triangulator {
       }
       if (!found) return false;  // duplicate of an existing vertex
     }
-    if (mark.size() < dead.size()) mark.resize(dead.size(), 0);
-    cavity.clear();
-    stack_.clear();
-    stack_.push_back(t0);
-    mark[t0] = 1;
-    while (!stack_.empty()) {
-      const int t = stack_.back();
-      stack_.pop_back();
-      cavity.push_back(t);
+    if (mark.size() < dead.size() + 16) mark.resize(2 * dead.size() + 64, 0);
+    ++stamp;
+    grow_scratch(16);
+    int ncav = 0, nstack = 0;
+    stack_[nstack++] = t0;
+    mark[t0] = stamp;
+    while (nstack > 0) {
+      const int t = stack_[--nstack];
+      if ((size_t)ncav + 4 > cavity.size()) grow_scratch(cavity.size() + 4);
+      cavity[ncav++] = t;
       for (int k = 0; k < 3; ++k) {
         const int n = ta[3 * t + k];
-        if (n >= 0 && !mark[n] && conflicts(n, p)) {
-          mark[n] = 1;
-          stack_.push_back(n);
+        if (n >= 0 && mark[n] != stamp && conflicts(n, p)) {
+          mark[n] = stamp;
+          stack_[nstack++] = n;
         }
       }
     }
     // boundary edges (a,b) of the cavity with the triangle outside
-    bnd_a.clear(); bnd_b.clear(); bnd_out.clear();
-    for (int t : cavity)
+    int nb = 0;
+    for (int c = 0; c < ncav; ++c) {
+      const int t = cavity[c];
       for (int k = 0; k < 3; ++k) {
         const int n = ta[3 * t + k];
-        if (n < 0 || !mark[n]) {
-          bnd_a.push_back(tv[3 * t + k]);
-          bnd_b.push_back(tv[3 * t + (k + 1) % 3]);
-          bnd_out.push_back(n);
+        if (n < 0 || mark[n] != stamp) {
+          bnd_a[nb] = tv[3 * t + k];
+          bnd_b[nb] = tv[3 * t + (k == 2 ? 0 : k + 1)];
+          bnd_out[nb] = n;
+          ++nb;
         }
       }
-    for (int t : cavity) {
-      mark[t] = 0;
-      dead[t] = 1;
-      free_list.push_back(t);
+    }
+    for (int c = 0; c < ncav; ++c) {
+      dead[cavity[c]] = 1;
+      free_list.push_back(cavity[c]);
     }
     // fan of new triangles (a, b, p); ghost boundary edges keep GHOST in slot 2
-    const int nb = (int)bnd_a.size();
-    bnd_new.assign(nb, -1);
     for (int i = 0; i < nb; ++i) {
       const int a = bnd_a[i], b = bnd_b[i];
-      int t;
-      if (a == GHOST) t = new_tri(b, p, GHOST);        // edge (inf, b): new ghost (b, p, inf)
-      else if (b == GHOST) t = new_tri(p, a, GHOST);   // edge (a, inf): new ghost (p, a, inf)
-      else t = new_tri(a, b, p);
+      int t, slot;
+      if (a == GHOST) { t = new_tri(b, p, GHOST); slot = 2; }       // edge (inf, b): new ghost (b, p, inf), edge (inf,b) is slot 2
+      else if (b == GHOST) { t = new_tri(p, a, GHOST); slot = 1; }  // edge (a, inf): new ghost (p, a, inf), edge (a,inf) is slot 1
+      else { t = new_tri(a, b, p); slot = 0; }                      // (a,b,p): edge (a,b) is slot 0
       bnd_new[i] = t;
-      if (mark.size() < dead.size()) mark.resize(dead.size(), 0);
       // link across the boundary edge
       const int n = bnd_out[i];
-      int slot;
-      if (a == GHOST) slot = 2;        // (b,p,inf): edge (inf,b) is slot 2
-      else if (b == GHOST) slot = 1;   // (p,a,inf): edge (a,inf) is slot 1
-      else slot = 0;                   // (a,b,p): edge (a,b) is slot 0
       ta[3 * t + slot] = n;
-      if (n >= 0)
-        for (int k = 0; k < 3; ++k) {
-          const int na = tv[3 * n + k], nbv = tv[3 * n + (k + 1) % 3];
-          if (na == b && nbv == a) ta[3 * n + k] = t;
-        }
+      if (n >= 0) {
+        const int* nv = &tv[3 * n];
+        const int k = (nv[0] == b && nv[1] == a) ? 0 : ((nv[1] == b && nv[2] == a) ? 1 : 2);
+        ta[3 * n + k] = t;
+      }
     }
+    if (mark.size() < dead.size() + 16) mark.resize(2 * dead.size() + 64, 0);
     // link the fan triangles to each other: the boundary edges form a cycle around p, so triangle i's
     // edge (b_i, p) is shared with the triangle whose boundary edge starts at b_i (its edge (p, a))
     if (vslot.size() < px.size() + 1) vslot.assign(px.size() + 1, -1);
@@ -247,28 +255,58 @@ struct Triangulator {
       py[i] = (int64_t)llroundf(pts[2 * i + 1] * 64.0f);
     }
     tv.clear(); ta.clear(); dead.clear(); free_list.clear(); mark.clear(); vslot.clear();
+    stamp = 0;
     if (n < 3) return false;
     tv.reserve(3 * (2 * (size_t)n + 16)); ta.reserve(3 * (2 * (size_t)n + 16)); dead.reserve(2 * (size_t)n + 16);
-    // insertion order: snake over a coarse grid for walk locality (deterministic)
+    // Insertion order: biased randomised rounds (BRIO).  A fixed pseudo-random permutation is cut into
+    // rounds of doubling size; inside a round the points are visited along a snake over a grid with
+    // about two points per cell.  Points of a late round fall into the interior of an already
+    // well-shaped triangulation (cavities of ~4 triangles, short walks from the previous point); a
+    // plain raster sweep instead inserts every point on the current hull (cavities of 6+ triangles
+    // full of ghosts, 4x more triangles created than survive).  Deterministic: no clock, no rand().
     std::vector<int> order(n);
     for (int i = 0; i < n; ++i) order[i] = i;
+    {
+      uint64_t st = 0x9e3779b97f4a7c15ull;
+      for (int i = n - 1; i > 0; --i) {
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        const int j = (int)((st >> 33) % (uint64_t)(i + 1));
+        std::swap(order[i], order[j]);
+      }
+    }
     int64_t xmin = px[0], xmax = px[0], ymin = py[0], ymax = py[0];
     for (int i = 1; i < n; ++i) {
       xmin = std::min(xmin, px[i]); xmax = std::max(xmax, px[i]);
       ymin = std::min(ymin, py[i]); ymax = std::max(ymax, py[i]);
     }
     exact_double = (xmax - xmin) < (1 << 24) && (ymax - ymin) < (1 << 24);
-    int g = 1;
-    while (g * g * 4 < n) ++g;
-    const int64_t cw = std::max<int64_t>(1, (xmax - xmin) / g + 1), ch = std::max<int64_t>(1, (ymax - ymin) / g + 1);
-    std::vector<int64_t> key(n);
-    for (int i = 0; i < n; ++i) {
-      const int64_t cy = (py[i] - ymin) / ch;
-      int64_t cx = (px[i] - xmin) / cw;
-      if (cy & 1) cx = g - cx;
-      key[i] = ((cy * (g + 2) + cx) << 32) | (uint32_t)i;
+    {
+      std::vector<uint64_t> key(n);
+      int hi = n;
+      std::vector<int> starts;  // round boundaries, last round first
+      while (hi > 0) {
+        const int lo = hi > 64 ? hi / 2 : 0;
+        starts.push_back(lo);
+        hi = lo;
+      }
+      hi = n;
+      for (size_t r = 0; r < starts.size(); ++r) {
+        const int lo = starts[r], cntr = hi - lo;
+        int g = 1;
+        while (g * g * 2 < cntr) ++g;
+        const int64_t cw = std::max<int64_t>(1, (xmax - xmin) / g + 1), ch = std::max<int64_t>(1, (ymax - ymin) / g + 1);
+        for (int k = lo; k < hi; ++k) {
+          const int i = order[k];
+          const int64_t cy = (py[i] - ymin) / ch;
+          int64_t cx = (px[i] - xmin) / cw;
+          if (cy & 1) cx = g - cx;
+          key[k] = ((uint64_t)(cy * (g + 2) + cx) << 32) | (uint32_t)i;
+        }
+        std::sort(key.begin() + lo, key.begin() + hi);
+        for (int k = lo; k < hi; ++k) order[k] = (int)(key[k] & 0xffffffffu);
+        hi = lo;
+      }
     }
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
     // seed triangle: first point, the next distinct point, the next non-collinear point
     int i0 = order[0], i1 = -1, i2 = -1;
     size_t k1 = 1;
