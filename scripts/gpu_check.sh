@@ -1,5 +1,8 @@
+# Quick health check of the committed state: GPU tests, smoke(), fb_update stage timings, default bench.
+mkdir -p gpurun_out
 timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -2
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python scripts/profile_update.py 16; python scripts/profile_update.py 8
 timeout 500 python bench.py > gpurun_out/bench_check.json 2> gpurun_out/bench_check.err; tail -2 gpurun_out/bench_check.err
 python -c "
 import json; d=json.load(open('gpurun_out/bench_check.json'))
