@@ -26,9 +26,11 @@ typedef __int128 i128;
 
 struct Triangulator {
   static const int GHOST = -1;
-  std::vector<int64_t> px, py;  // lattice coordinates
-  std::vector<int> tv;          // 3 vertices per triangle (ccw); ghost triangles hold GHOST at slot 2
-  std::vector<int> ta;          // ta[3t+k] = triangle across the edge (v[k], v[k+1])
+  std::vector<int32_t> px, py;  // lattice coordinates (|v| < 2^30: differences and orientation products fit 64 bits)
+  // one 32-byte record per triangle: tt[8t + k] = vertex k (ccw; ghost triangles hold GHOST at slot 2),
+  // tt[8t + 4 + k] = triangle across the edge (v[k], v[k+1]); vertices and neighbours of a triangle
+  // share half a cache line
+  std::vector<int> tt;
   std::vector<char> dead;
   std::vector<int> free_list;
   std::vector<int> dup_of;      // -1, or index of the earlier identical point
@@ -63,7 +65,7 @@ struct Triangulator {
 
   // Does the (possibly ghost) triangle t conflict with point p (p inside its circumdisk)?
   bool conflicts(int t, int p) const {
-    const int a = tv[3 * t], b = tv[3 * t + 1], c = tv[3 * t + 2];
+    const int a = tt[8 * t], b = tt[8 * t + 1], c = tt[8 * t + 2];
     if (c != GHOST) return incircle_sign(a, b, c, p) > 0;
     // ghost (a,b,inf): the "disk" is the open half-plane to the left of a->b (outside the hull, which
     // lies to the right of the reversed hull edge) plus the open segment ab
@@ -84,11 +86,10 @@ struct Triangulator {
     } else {
       t = (int)dead.size();
       dead.push_back(0);
-      tv.resize(tv.size() + 3);
-      ta.resize(ta.size() + 3);
+      tt.resize(tt.size() + 8);
     }
-    tv[3 * t] = a; tv[3 * t + 1] = b; tv[3 * t + 2] = c;
-    ta[3 * t] = ta[3 * t + 1] = ta[3 * t + 2] = -1;
+    tt[8 * t] = a; tt[8 * t + 1] = b; tt[8 * t + 2] = c;
+    tt[8 * t + 4] = tt[8 * t + 4 + 1] = tt[8 * t + 4 + 2] = -1;
     return t;
   }
 
@@ -100,24 +101,24 @@ struct Triangulator {
         if (!dead[t]) break;
     }
     for (int guard = 0; guard < 4 * (int)dead.size() + 64; ++guard) {
-      if (tv[3 * t + 2] == GHOST) {
+      if (tt[8 * t + 2] == GHOST) {
         if (conflicts(t, p)) return t;
         // slide along the hull: move to the neighbouring ghost whose edge faces p
-        const int a = tv[3 * t], b = tv[3 * t + 1];
+        const int a = tt[8 * t], b = tt[8 * t + 1];
         const int64_t dx = px[b] - px[a], dy = py[b] - py[a];
         const int64_t t0 = (px[p] - px[a]) * dx + (py[p] - py[a]) * dy;
         if (orientv(a, b, p) < 0) {
-          t = ta[3 * t];  // p is on the hull's side: step into the real triangle
+          t = tt[8 * t + 4];  // p is on the hull's side: step into the real triangle
         } else {
-          t = (t0 <= 0) ? ta[3 * t + 2] : ta[3 * t + 1];  // collinear, beyond a or beyond b
+          t = (t0 <= 0) ? tt[8 * t + 4 + 2] : tt[8 * t + 4 + 1];  // collinear, beyond a or beyond b
         }
         continue;
       }
       bool moved = false;
       for (int k = 0; k < 3; ++k) {
-        const int a = tv[3 * t + k], b = tv[3 * t + (k + 1) % 3];
+        const int a = tt[8 * t + k], b = tt[8 * t + (k + 1) % 3];
         if (orientv(a, b, p) < 0) {
-          t = ta[3 * t + k];
+          t = tt[8 * t + 4 + k];
           moved = true;
           break;
         }
@@ -148,7 +149,7 @@ struct Triangulator {
     int t0 = locate(p);
     if (t0 < 0) return false;
     for (int k = 0; k < 3; ++k) {
-      const int v = tv[3 * t0 + k];
+      const int v = tt[8 * t0 + k];
       if (v != GHOST && px[v] == px[p] && py[v] == py[p]) return false;  // duplicate vertex
     }
     if (!conflicts(t0, p)) {
@@ -156,7 +157,7 @@ struct Triangulator {
       // look for any neighbour that conflicts (happens for points on shared edges / cocircular)
       bool found = false;
       for (int k = 0; k < 3 && !found; ++k) {
-        const int n = ta[3 * t0 + k];
+        const int n = tt[8 * t0 + 4 + k];
         if (n >= 0 && conflicts(n, p)) {
           t0 = n;
           found = true;
@@ -182,7 +183,7 @@ struct Triangulator {
       if ((size_t)ncav + 4 > cavity.size()) grow_scratch(cavity.size() + 4);
       cavity[ncav++] = t;
       for (int k = 0; k < 3; ++k) {
-        const int n = ta[3 * t + k];
+        const int n = tt[8 * t + 4 + k];
         if (n >= 0 && mark[n] != stamp && conflicts(n, p)) {
           mark[n] = stamp;
           stack_[nstack++] = n;
@@ -194,10 +195,10 @@ struct Triangulator {
     for (int c = 0; c < ncav; ++c) {
       const int t = cavity[c];
       for (int k = 0; k < 3; ++k) {
-        const int n = ta[3 * t + k];
+        const int n = tt[8 * t + 4 + k];
         if (n < 0 || mark[n] != stamp) {
-          bnd_a[nb] = tv[3 * t + k];
-          bnd_b[nb] = tv[3 * t + (k == 2 ? 0 : k + 1)];
+          bnd_a[nb] = tt[8 * t + k];
+          bnd_b[nb] = tt[8 * t + (k == 2 ? 0 : k + 1)];
           bnd_out[nb] = n;
           ++nb;
         }
@@ -217,11 +218,11 @@ struct Triangulator {
       bnd_new[i] = t;
       // link across the boundary edge
       const int n = bnd_out[i];
-      ta[3 * t + slot] = n;
+      tt[8 * t + 4 + slot] = n;
       if (n >= 0) {
-        const int* nv = &tv[3 * n];
+        const int* nv = &tt[8 * n];
         const int k = (nv[0] == b && nv[1] == a) ? 0 : ((nv[1] == b && nv[2] == a) ? 1 : 2);
-        ta[3 * n + k] = t;
+        tt[8 * n + 4 + k] = t;
       }
     }
     if (mark.size() < dead.size() + 16) mark.resize(2 * dead.size() + 64, 0);
@@ -236,8 +237,8 @@ struct Triangulator {
       const int bp = (a == GHOST) ? 0 : (b == GHOST ? 2 : 1);
       const int aj = bnd_a[j], bj = bnd_b[j];
       const int pa = (aj == GHOST) ? 1 : (bj == GHOST ? 0 : 2);
-      ta[3 * bnd_new[i] + bp] = bnd_new[j];
-      ta[3 * bnd_new[j] + pa] = bnd_new[i];
+      tt[8 * bnd_new[i] + 4 + bp] = bnd_new[j];
+      tt[8 * bnd_new[j] + 4 + pa] = bnd_new[i];
     }
     last = bnd_new[0];
     return true;
@@ -251,13 +252,15 @@ struct Triangulator {
     py.resize(n);
     dup_of.assign(n, -1);
     for (int i = 0; i < n; ++i) {
-      px[i] = (int64_t)llroundf(pts[2 * i] * 64.0f);
-      py[i] = (int64_t)llroundf(pts[2 * i + 1] * 64.0f);
+      const long long lx = llroundf(pts[2 * i] * 64.0f), ly = llroundf(pts[2 * i + 1] * 64.0f);
+      if (lx <= -(1ll << 30) || lx >= (1ll << 30) || ly <= -(1ll << 30) || ly >= (1ll << 30)) return false;  // not pixel coordinates
+      px[i] = (int32_t)lx;
+      py[i] = (int32_t)ly;
     }
-    tv.clear(); ta.clear(); dead.clear(); free_list.clear(); mark.clear(); vslot.clear();
+    tt.clear(); dead.clear(); free_list.clear(); mark.clear(); vslot.clear();
     stamp = 0;
     if (n < 3) return false;
-    tv.reserve(3 * (2 * (size_t)n + 16)); ta.reserve(3 * (2 * (size_t)n + 16)); dead.reserve(2 * (size_t)n + 16);
+    tt.reserve(8 * (2 * (size_t)n + 16)); dead.reserve(2 * (size_t)n + 16);
     // Insertion order: biased randomised rounds (BRIO).  A fixed pseudo-random permutation is cut into
     // rounds of doubling size; inside a round the points are visited along a snake over a grid with
     // about two points per cell.  Points of a late round fall into the interior of an already
@@ -276,8 +279,8 @@ struct Triangulator {
     }
     int64_t xmin = px[0], xmax = px[0], ymin = py[0], ymax = py[0];
     for (int i = 1; i < n; ++i) {
-      xmin = std::min(xmin, px[i]); xmax = std::max(xmax, px[i]);
-      ymin = std::min(ymin, py[i]); ymax = std::max(ymax, py[i]);
+      xmin = std::min<int64_t>(xmin, px[i]); xmax = std::max<int64_t>(xmax, px[i]);
+      ymin = std::min<int64_t>(ymin, py[i]); ymax = std::max<int64_t>(ymax, py[i]);
     }
     exact_double = (xmax - xmin) < (1 << 24) && (ymax - ymin) < (1 << 24);
     {
@@ -326,13 +329,13 @@ struct Triangulator {
     if (orientv(i0, i1, i2) < 0) std::swap(i1, i2);
     const int t = new_tri(i0, i1, i2);
     const int g0 = new_tri(i1, i0, GHOST), g1 = new_tri(i2, i1, GHOST), g2 = new_tri(i0, i2, GHOST);
-    ta[3 * t] = g0; ta[3 * t + 1] = g1; ta[3 * t + 2] = g2;
-    ta[3 * g0] = t; ta[3 * g1] = t; ta[3 * g2] = t;
+    tt[8 * t + 4] = g0; tt[8 * t + 4 + 1] = g1; tt[8 * t + 4 + 2] = g2;
+    tt[8 * g0 + 4] = t; tt[8 * g1 + 4] = t; tt[8 * g2 + 4] = t;
     // ghost (a,b,inf): slot 1 = edge (b,inf) -> ghost starting at ... , slot 2 = edge (inf,a)
     // g0=(i1,i0): (b=i0,inf) continues to the ghost whose a == i0: g2=(i0,i2); (inf,a=i1): ghost whose b == i1: g1
-    ta[3 * g0 + 1] = g2; ta[3 * g0 + 2] = g1;
-    ta[3 * g1 + 1] = g0; ta[3 * g1 + 2] = g2;
-    ta[3 * g2 + 1] = g1; ta[3 * g2 + 2] = g0;
+    tt[8 * g0 + 4 + 1] = g2; tt[8 * g0 + 4 + 2] = g1;
+    tt[8 * g1 + 4 + 1] = g0; tt[8 * g1 + 4 + 2] = g2;
+    tt[8 * g2 + 4 + 1] = g1; tt[8 * g2 + 4 + 2] = g0;
     last = t;
     std::vector<char> done(n, 0);
     done[i0] = done[i1] = done[i2] = 1;
@@ -373,14 +376,14 @@ struct Triangulator {
     ea.reserve(3 * (size_t)n);
     eb.reserve(3 * (size_t)n);
     for (int u = 0; u < (int)dead.size(); ++u) {
-      if (dead[u] || tv[3 * u + 2] == GHOST) continue;
-      tris.push_back(tv[3 * u]);
-      tris.push_back(tv[3 * u + 1]);
-      tris.push_back(tv[3 * u + 2]);
+      if (dead[u] || tt[8 * u + 2] == GHOST) continue;
+      tris.push_back(tt[8 * u]);
+      tris.push_back(tt[8 * u + 1]);
+      tris.push_back(tt[8 * u + 2]);
       for (int m = 0; m < 3; ++m) {
-        const int nb = ta[3 * u + m];
-        if (nb >= 0 && tv[3 * nb + 2] != GHOST && nb < u) continue;
-        int a = tv[3 * u + m], b = tv[3 * u + (m == 2 ? 0 : m + 1)];
+        const int nb = tt[8 * u + 4 + m];
+        if (nb >= 0 && tt[8 * nb + 2] != GHOST && nb < u) continue;
+        int a = tt[8 * u + m], b = tt[8 * u + (m == 2 ? 0 : m + 1)];
         if (a > b) std::swap(a, b);
         ea.push_back(a);
         eb.push_back(b);
