@@ -453,7 +453,7 @@ static int fb_nltgv2_solve_stream(fb_ctx* c, int s, int iters, const fb_nltgv2_p
   // vertices) costs more than the persistent kernel saves, so a freshly changed topology is solved
   // with the streaming kernels (graph replay, no per-topology host work)
   const bool plan_fresh = c->plan && !c->plan->topo[s].dirty;
-  if (cluster_plan_ready(c) && plan_fresh) {
+  if (plan_fresh && cluster_plan_ready(c)) {
     c->last_variant = 2;
     return solve_cluster(c, iters, p, only);
   }

@@ -40,6 +40,7 @@ struct UpdateStream {
 
 struct UpdateState {
   std::vector<UpdateStream> st;
+  std::vector<fbdel::Triangulator> tri;  // one per stream: scratch capacity survives from frame to frame
   // device scratch (per stream base s*maxF unless noted)
   float2* f_ucur = nullptr;
   float* f_mucur = nullptr;
@@ -340,8 +341,8 @@ static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const f
   bool have_tri = false;
   if (V >= 3) {
     StageTimer t(S.stats, "triangulate");
-    fbdel::Triangulator T;
-    have_tri = T.run(V, pos.data(), tris, edges);
+    if ((int)U->tri.size() < c->S) U->tri.resize(c->S);
+    have_tri = U->tri[s].run(V, pos.data(), tris, edges);
     if ((int)edges.size() / 2 > c->maxE || (int)tris.size() / 3 > c->maxT) have_tri = false;
   }
   if (have_tri) {

@@ -49,7 +49,7 @@ struct ClusterPlan {
     int V = 0, E = 0;
     std::vector<int2> eij;
     std::vector<int32_t> row, inc;
-    int needC = 1;      // smallest feasible cluster size for this graph (0 = does not fit)
+    int needC = 1;      // smallest feasible cluster size for this graph (0 = does not fit, -1 = not computed yet)
     bool dirty = true;  // device plan out of date
     int capV = 0, capH = 0, capI = 0;
     int partC = 0;               // cluster size `part` was computed for (0 = stale)
@@ -453,8 +453,14 @@ static int cluster_plan_build(fb_ctx* c, int s, int V, int E, const int2* eij, c
   t.row.assign(row, row + V + 1);
   t.inc.assign(inc, inc + 2 * (size_t)E);
   t.dirty = true;
-  t.needC = 0;
+  t.needC = -1;  // computed on first use: fb_update re-sets the graph every frame and never asks
   t.partC = 0;
+  return FB_OK;
+}
+
+static void fbc_need(ClusterPlan::Topo& t) {
+  if (t.needC >= 0) return;
+  t.needC = 0;
   FbcPart P;
   for (int C = 1; C <= FBC_MAXC; C *= 2) {
     if (fbc_partition(t, C, P)) {
@@ -462,13 +468,15 @@ static int cluster_plan_build(fb_ctx* c, int s, int V, int E, const int2* eij, c
       break;
     }
   }
-  return FB_OK;
 }
 
 static bool cluster_plan_ready(fb_ctx* c) {
   if (!c->plan) return false;
   for (int s = 0; s < c->S; ++s)
-    if (c->plan->topo[s].V > 0 && c->plan->topo[s].needC == 0) return false;
+    if (c->plan->topo[s].V > 0) {
+      fbc_need(c->plan->topo[s]);
+      if (c->plan->topo[s].needC == 0) return false;
+    }
   return true;
 }
 
@@ -661,6 +669,7 @@ static int solve_cluster(fb_ctx* c, int iters, const fb_nltgv2_params* p, int on
   bool any = false;
   for (auto& t : P->topo)
     if (t.V > 0) {
+      fbc_need(t);
       C = std::max(C, t.needC);
       any = true;
     }
