@@ -107,3 +107,26 @@ def test_degenerate_inputs_are_rejected(capi):
         capi.delaunay(np.zeros((2, 2), np.float32))
     with pytest.raises(capi.FlameError):
         capi.delaunay(np.stack([np.arange(6.0), 2 * np.arange(6.0)], axis=1).astype(np.float32))
+
+
+def test_deterministic_and_independent_of_earlier_calls(capi):
+    """The insertion order is a fixed pseudo-random permutation (no clock, no global state): the same
+    points give the same triangles in the same order, whatever was triangulated before."""
+    rng = np.random.default_rng(3)
+    pts = snap(rng.uniform([0, 0], [639, 479], (2000, 2)))
+    t1, e1 = capi.delaunay(pts)
+    capi.delaunay(snap(rng.uniform([0, 0], [100, 100], (50, 2))))
+    t2, e2 = capi.delaunay(pts)
+    assert np.array_equal(t1, t2) and np.array_equal(e1, e2)
+
+
+def test_c4_sized_grid_matches_qhull(capi):
+    pts = snap(synth.jittered_grid(1280, 720, 200, 100, 2.5, seed=3))
+    tris, edges = capi.delaunay(pts)
+    assert edge_set(tris) == edge_set(Delaunay(pts.astype(np.float64)).simplices)
+
+
+def test_coordinates_outside_the_lattice_range_are_rejected(capi):
+    pts = np.array([[0, 0], [1e8, 0], [0, 1e8], [5, 5]], np.float32)
+    with pytest.raises(capi.FlameError):
+        capi.delaunay(pts)
