@@ -85,3 +85,33 @@ def test_degenerate_graphs(capi):
     for parts in (1, 2, 3):
         rc, _ = capi.grid_plan_verify(pos, edges, parts)
         assert rc == 0
+
+
+def test_random_graphs_and_part_counts(capi):
+    """Property test over seeded random point sets (uniform, clustered, nearly collinear strips) and part
+    counts: whenever the partitioner accepts a configuration, every invariant of the kernel holds."""
+    rng = np.random.default_rng(42)
+    accepted = 0
+    for trial in range(40):
+        n = int(rng.integers(4, 900))
+        kind = trial % 3
+        if kind == 0:
+            pts = rng.uniform([0, 0], [639, 479], (n, 2))
+        elif kind == 1:   # clusters: very uneven density, high-degree hubs
+            centres = rng.uniform([50, 50], [590, 430], (5, 2))
+            pts = centres[rng.integers(0, 5, n)] + rng.normal(0, 12.0, (n, 2))
+        else:             # a thin strip: long skinny parts, many cut edges per vertex
+            pts = np.stack([rng.uniform(0, 639, n), rng.uniform(200, 206, n)], axis=1)
+        pts = np.unique((np.round(pts * 64) / 64).astype(np.float32), axis=0)
+        if len(pts) < 3:
+            continue
+        try:
+            _, edges = capi.delaunay(pts)
+        except capi.FlameError:
+            continue
+        for cluster in (False, True):
+            parts = int(rng.integers(1, 17 if cluster else 60))
+            rc, st = capi.grid_plan_verify(pts, edges, parts, cluster)
+            assert rc in (0, 1)          # 1 = does not fit this part count; anything else raises
+            accepted += rc == 0
+    assert accepted >= 40
