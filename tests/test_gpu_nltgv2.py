@@ -249,3 +249,27 @@ def test_bad_arguments_are_rejected(capi):
             ctx.graph_set(0, pos, np.array([[1, 2], [0, 1]], np.int32), np.ones(2), np.ones(2))
         with pytest.raises(capi.FlameError):  # capacity
             ctx.graph_set(0, np.zeros((9, 2), np.float32), np.zeros((0, 2), np.int32), np.zeros(0), np.zeros(0))
+
+
+@pytest.mark.parametrize("mode", ["l2", "cluster"])
+def test_grid_solver_irregular_graph(capi, oracle, mode, monkeypatch):
+    """Clustered points with shuffled vertex ids: hubs with many in-edges (more slot rows than the
+    unrolled gather), out-degrees beyond the register rows (overflow slots), long thin parts."""
+    monkeypatch.setenv("FB_GRID_MODE", mode)
+    monkeypatch.setenv("FB_GRID_CLUSTER" if mode == "cluster" else "FB_GRID_CTAS", "7")
+    rng = np.random.default_rng(7)
+    centres = rng.uniform([40, 40], [280, 200], (6, 2))
+    pts = centres[rng.integers(0, 6, 700)] + rng.normal(0, 9.0, (700, 2))
+    pts = np.unique((np.round(np.clip(pts, 1, [318, 238]) * 64) / 64).astype(np.float32), axis=0)
+    pts = pts[rng.permutation(len(pts))]
+    _, edges = capi.delaunay(pts)
+    alpha, beta = synth.edge_weights(pts, edges)
+    z, _ = synth.plane_data(pts, 320, 240, seed=8, noise=0.02)
+    g = dict(pos=pts, edges=edges, alpha=alpha, beta=beta, z=z, wt=np.ones(len(z), np.float32))
+    ref = run_oracle(oracle, g, 23)
+    with capi.Context(1, 320, 240, 2, 16, 800, 2400) as ctx:
+        gpu_load_graph(ctx, 0, g)
+        ctx.nltgv2_solve(23, variant=3)
+        assert ctx.last_solver_variant() == 3
+        got = ctx.graph_state_get(0)
+    assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
