@@ -1198,7 +1198,7 @@ static int fbg_verify(int V, int E, const float* pos, const int32_t* ij, int npe
     if (owner[v] < 0) { why = "vertex without owner"; return 2; }
   // what an (entry, slot) pair must be for endpoint v of edge e seen from part r
   auto check_end = [&](int r, int e, int v, bool is_target, int ovf_pos, int b, int sl, bool slot_used, int& code) -> bool {
-    const int4 c0 = g.cinfo[3 * r], c1 = g.cinfo[3 * r + 1];
+    const int4 c1 = g.cinfo[3 * r + 1];
     const int rows_in = c1.w & 0xff, stride = c1.w >> 8;
     if (owner[v] == r) {
       if (b != ent_of[v]) { code = 5; return false; }
