@@ -950,6 +950,7 @@ extern "C" int fb_results_wait(fb_ctx* c, int lag) {
   if (lag < 0 || lag > 3) FB_FAIL(c, FB_E_ARG, "fb_results_wait: lag must be in [0,3]");
   if (c->n_pipelined - 1 - lag < 0) return FB_OK;
   FB_CUDA(c, cudaEventSynchronize(c->ev_result[(c->n_pipelined - 1 - lag) & 3]));
+  if (grid_watchdog_fired(c)) FB_FAIL(c, FB_E_STATE, "grid-resident solver: mailbox exchange timed out (watchdog)");
   return FB_OK;
 }
 
