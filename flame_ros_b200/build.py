@@ -22,7 +22,8 @@ def _nvcc():
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+    # every file the translation unit includes: .h too (delaunay.h, delaunay_star.h are plain headers)
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
 
 
 def is_stale():

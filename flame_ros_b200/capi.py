@@ -30,7 +30,7 @@ SYMBOLS = [
     "fb_last_solver_variant", "fb_last_cluster_size", "fb_last_solver_transport", "fb_grid_plan_verify", "fb_delaunay", "fb_hotpath_step", "fb_results_wait", "fb_pipeline_join", "fb_default_update_params",
     "fb_set_update_params", "fb_update", "fb_get_mesh_sizes", "fb_get_mesh", "fb_get_idepthmap",
     "fb_get_raw_idepths", "fb_get_stat", "fb_update_poseframe_poses", "fb_prune_poseframes",
-    "fb_frame_gradient", "fb_frame_pyr_down", "fb_detect", "fb_get_feature_pool",
+    "fb_frame_gradient", "fb_frame_pyr_down", "fb_detect", "fb_get_feature_pool", "fb_delaunay_device",
 ]
 
 
@@ -68,7 +68,7 @@ class UpdateParams(C.Structure):
     _fields_ = [("detection_win_size", C.c_int), ("min_grad_mag", C.c_float), ("detection_border", C.c_int),
                 ("idepth_init", C.c_float), ("idepth_var_init", C.c_float), ("idepth_var_max_graph", C.c_float),
                 ("adaptive_data_weights", C.c_int), ("init_with_prediction", C.c_int), ("do_nltgv2", C.c_int),
-                ("iters", C.c_int), ("rparams", NLTGV2Params)]
+                ("iters", C.c_int), ("rparams", NLTGV2Params), ("triangulator", C.c_int)]
 
 
 class StepDesc(C.Structure):
@@ -142,6 +142,7 @@ def load_library(build_if_missing=True):
         "fb_prune_poseframes": [P, I, I, P], "fb_frame_gradient": [P, I, I, P],
         "fb_frame_pyr_down": [P, I, I, P], "fb_detect": [P, I, I, I, I, C.c_float, P, P, P, P],
         "fb_get_feature_pool": [P, I, P, P, P, P, P, P],
+        "fb_delaunay_device": [P, I, I, P, P, P, P, P],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -451,6 +452,19 @@ class Context:
                                        _ptr(out["normals"]), _ptr(out["tris"]), _ptr(out["tri_valid"]),
                                        _ptr(out["edges"])))
         return out
+
+    def delaunay_device(self, stream, pts):
+        """fb_delaunay_device: the update pipeline's device triangulation of an arbitrary point set.
+        Returns (tris [T,3], edges [E,2]) like delaunay()."""
+        pts = _f32(pts)
+        n = pts.shape[0]
+        tris = np.zeros((max(2 * n, 1), 3), np.int32)
+        edges = np.zeros((max(3 * n, 1), 2), np.int32)
+        nt, ne = C.c_int32(0), C.c_int32(0)
+        rc = self._lib.fb_delaunay_device(self._h, stream, n, _ptr(pts), _ptr(tris), C.byref(nt), _ptr(edges), C.byref(ne))
+        if rc != 0:
+            raise FlameError("fb_delaunay_device: rc %d (%s)" % (rc, self._lib.fb_last_error(self._h).decode()))
+        return tris[:nt.value].copy(), edges[:ne.value].copy()
 
     def get_idepthmap(self, stream, filter_params=None):
         out = np.zeros((self.H, self.W), np.float32)

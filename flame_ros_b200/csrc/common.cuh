@@ -108,11 +108,17 @@ struct fb_ctx {
   int32_t* owner = nullptr;      // [S][H*W] owning triangle per pixel
   float* idmap = nullptr;        // [S][H*W]
 
-  // ---- CUDA-graph cache for the streaming solver
-  cudaGraphExec_t solve_exec = nullptr;
-  int solve_iters = 0;
-  int solve_only = -1;
-  fb_nltgv2_params solve_params{};
+  // ---- CUDA-graph cache for the streaming solver: one executable per value of `only` (index
+  // only + 1; fb_update on a batch context solves one stream at a time, round robin)
+  std::vector<cudaGraphExec_t> solve_exec;
+  std::vector<int> solve_iters;
+  std::vector<fb_nltgv2_params> solve_params;
+  // ---- plan-free resident solver (variant 4, nltgv2_coop.cuh)
+  float4* coop_contrib = nullptr;  // [S*2*maxE] K^T q per edge end
+  int* coop_err = nullptr;         // mapped host flag
+  int coop_cluster = -1;           // cluster size: -1 not probed, 0 unavailable
+  int coop_ept = 0, coop_vpt = 0;  // edges / vertices per thread of the instantiation in use
+  float* idmap_scratch = nullptr;  // [H*W] filtered maps of getter calls (never the prediction source)
   int last_variant = 0;
   int last_cluster = 0;  // cluster size of the last variant-2 launch / parts per stream of variant 3
   bool grid_disabled = false;  // variant 3 launch refused once by the device: auto stops trying it

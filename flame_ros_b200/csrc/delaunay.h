@@ -244,6 +244,44 @@ struct Triangulator {
     return true;
   }
 
+  // Canonical form for co-circular point sets (integer-pixel detections form exact rectangles): the
+  // points on one empty circle span a convex polygon that every Delaunay triangulation fills somehow;
+  // flipping a tied diagonal (a,b) to (c,d) whenever min(c,d) < min(a,b) terminates (the sum of the
+  // diagonals' smaller endpoints falls) in the fan from the polygon's smallest vertex index.  The
+  // per-vertex stars of delaunay_star.h produce the same fan, so both triangulators agree exactly.
+  void canonicalize() {
+    std::vector<int> work;
+    for (int t = 0; t < (int)dead.size(); ++t)
+      if (!dead[t] && tt[8 * t + 2] != GHOST) work.push_back(t);
+    while (!work.empty()) {
+      const int t = work.back();
+      work.pop_back();
+      if (dead[t] || tt[8 * t + 2] == GHOST) continue;
+      for (int k = 0; k < 3; ++k) {
+        const int n = tt[8 * t + 4 + k];
+        if (n < 0 || tt[8 * n + 2] == GHOST) continue;
+        const int a = tt[8 * t + k], b = tt[8 * t + (k + 1) % 3], c = tt[8 * t + (k + 2) % 3];
+        int kn = 0;  // edge (b,a) in n
+        while (kn < 3 && !(tt[8 * n + kn] == b && tt[8 * n + (kn + 1) % 3] == a)) ++kn;
+        if (kn == 3) continue;
+        const int d = tt[8 * n + (kn + 2) % 3];
+        if (std::min(c, d) >= std::min(a, b) || incircle_sign(a, b, c, d) != 0) continue;
+        // t = (a,b,c), n = (b,a,d)  ->  t = (a,d,c), n = (d,b,c)
+        const int X = tt[8 * t + 4 + (k + 1) % 3], Y = tt[8 * t + 4 + (k + 2) % 3];
+        const int Z = tt[8 * n + 4 + (kn + 1) % 3], U = tt[8 * n + 4 + (kn + 2) % 3];
+        tt[8 * t] = a; tt[8 * t + 1] = d; tt[8 * t + 2] = c;
+        tt[8 * t + 4] = Z; tt[8 * t + 5] = n; tt[8 * t + 6] = Y;
+        tt[8 * n] = d; tt[8 * n + 1] = b; tt[8 * n + 2] = c;
+        tt[8 * n + 4] = U; tt[8 * n + 5] = X; tt[8 * n + 6] = t;
+        if (Z >= 0) for (int m = 0; m < 3; ++m) if (tt[8 * Z + 4 + m] == n) { tt[8 * Z + 4 + m] = t; break; }
+        if (X >= 0) for (int m = 0; m < 3; ++m) if (tt[8 * X + 4 + m] == t) { tt[8 * X + 4 + m] = n; break; }
+        work.push_back(t);
+        work.push_back(n);
+        break;
+      }
+    }
+  }
+
   // pts: n points (x,y) in pixels.  Returns false when all points are collinear / fewer than 3.
   bool run(int n, const float* pts, std::vector<int>& tris, std::vector<int>& edges) {
     tris.clear();
@@ -310,6 +348,23 @@ struct Triangulator {
         hi = lo;
       }
     }
+    // identical lattice points: the smallest index keeps the vertex (canonical, like delaunay_star.h),
+    // the others are left unreferenced.  Open-addressing table keyed by the coordinates.
+    {
+      size_t cap = 16;
+      while (cap < 2 * (size_t)n) cap <<= 1;
+      std::vector<int> tab(cap, -1);
+      bool any = false;
+      for (int i = 0; i < n; ++i) {
+        size_t h = ((uint64_t)(uint32_t)px[i] * 0x9e3779b97f4a7c15ull ^ (uint64_t)(uint32_t)py[i] * 0xc2b2ae3d27d4eb4full) >> 20;
+        for (h &= cap - 1;; h = (h + 1) & (cap - 1)) {
+          const int j = tab[h];
+          if (j < 0) { tab[h] = i; break; }
+          if (px[j] == px[i] && py[j] == py[i]) { dup_of[i] = j; any = true; break; }  // j < i
+        }
+      }
+      if (any) order.erase(std::remove_if(order.begin(), order.end(), [&](int i) { return dup_of[i] >= 0; }), order.end());
+    }
     // seed triangle: first point, the next distinct point, the next non-collinear point
     int i0 = order[0], i1 = -1, i2 = -1;
     size_t k1 = 1;
@@ -344,6 +399,7 @@ struct Triangulator {
       done[idx] = 1;
       if (!insert(idx)) dup_of[idx] = -2;  // resolved below
     }
+    canonicalize();
     // duplicates: map to the first vertex with identical lattice coordinates
     {
       bool any = false;
@@ -377,9 +433,13 @@ struct Triangulator {
     eb.reserve(3 * (size_t)n);
     for (int u = 0; u < (int)dead.size(); ++u) {
       if (dead[u] || tt[8 * u + 2] == GHOST) continue;
-      tris.push_back(tt[8 * u]);
-      tris.push_back(tt[8 * u + 1]);
-      tris.push_back(tt[8 * u + 2]);
+      {  // smallest vertex first (orientation kept); sorted into the canonical order below
+        const int v0 = tt[8 * u], v1 = tt[8 * u + 1], v2 = tt[8 * u + 2];
+        const int r = (v0 < v1 && v0 < v2) ? 0 : ((v1 < v2) ? 1 : 2);
+        tris.push_back(tt[8 * u + r]);
+        tris.push_back(tt[8 * u + (r + 1) % 3]);
+        tris.push_back(tt[8 * u + (r + 2) % 3]);
+      }
       for (int m = 0; m < 3; ++m) {
         const int nb = tt[8 * u + 4 + m];
         if (nb >= 0 && tt[8 * nb + 2] != GHOST && nb < u) continue;
@@ -406,6 +466,28 @@ struct Triangulator {
       }
       for (int a = 0; a < n; ++a)
         for (int k = cnt[a]; k < cnt[a + 1]; ++k) edges[2 * k] = a;
+    }
+    // canonical triangle order: (v0 = smallest vertex, v1, v2) counter-clockwise, sorted by (v0, v1)
+    // -- a counting sort by v0 and an insertion sort inside each bucket (a vertex starts ~2 triangles)
+    {
+      const size_t T = tris.size() / 3;
+      std::vector<int> tc(n + 1, 0), out(tris.size());
+      for (size_t t = 0; t < T; ++t) tc[tris[3 * t] + 1]++;
+      for (int i = 0; i < n; ++i) tc[i + 1] += tc[i];
+      std::vector<int> fill(tc.begin(), tc.begin() + n);
+      for (size_t t = 0; t < T; ++t) {
+        const int v0 = tris[3 * t], v1 = tris[3 * t + 1], v2 = tris[3 * t + 2];
+        int pos = fill[v0]++;
+        while (pos > tc[v0] && out[3 * (pos - 1) + 1] > v1) {
+          out[3 * pos + 1] = out[3 * (pos - 1) + 1];
+          out[3 * pos + 2] = out[3 * (pos - 1) + 2];
+          --pos;
+        }
+        out[3 * pos] = v0; out[3 * pos + 1] = v1; out[3 * pos + 2] = v2;
+      }
+      for (int a = 0; a < n; ++a)
+        for (int k = tc[a]; k < tc[a + 1]; ++k) out[3 * k] = a;
+      tris.swap(out);
     }
     return true;
   }

@@ -1,0 +1,446 @@
+// delaunay_gpu.cuh -- the `sync_graph` + `triangulate` stages of flame::Flame::update on the device
+// (timing keys /root/reference/src/utils.cc:151-154; gates regularization/nltgv2/idepth_var_max and
+// friends, /root/reference/src/flame_nodelet.cc:249-263).
+//
+// Why on the device: on the C2 stream every frame adds ~30 and removes ~25 of ~6k vertices and changes
+// ~2 % of the edges (scripts/topology_churn.py), so a topology can never be kept from one frame to the
+// next; the host triangulator cost 2.7 ms per frame plus two stream synchronisations and the upload
+// of the rebuilt graph.  Here the whole chain runs as six small launches with no host involvement:
+//   k_ds_stash    previous graph state (x, w, xbar, q, edge lists) aside for the carry-over
+//   k_ds_prepare  vertex selection (projected live features below the variance gate, in ascending
+//                 feature index), lattice coordinates, bounding box, cell grid, counting sort by
+//                 cell, duplicate marking -- one CTA, everything in shared memory
+//   k_ds_stars    one warp per vertex: its Delaunay star (delaunay_star.h), exact predicates
+//   k_ds_scan     prefix sums of out-degree / started triangles / degree -> edge, triangle and CSR
+//                 offsets, the device-side counts (nV, nE, nT), symmetry check
+//   k_ds_emit     canonical edges (i<j, sorted by (i,j)) with alpha = 1/|delta|, beta = 1, delta;
+//                 canonical triangles (smallest vertex first, sorted)
+//   k_ds_csr      CSR incidence in ascending edge id, data term, and the carry-over of (x, w, q)
+//                 from the previous graph by feature identity (new vertices start at the dense
+//                 prediction or their data term, new edges at q = 0)
+// The mesh is bit-identical to the host triangulator's canonical output (tests/test_delaunay_gpu.py).
+#pragma once
+
+#include "common.cuh"
+#include "delaunay_star.h"
+#include "nltgv2.cuh"
+
+#define DSG_MAXCELLS 4096
+#define DSG_THREADS 1024
+
+// meta record of one stream (device ints)
+enum { DSG_GX = 0, DSG_GY, DSG_SHIFT, DSG_BX0, DSG_BY0, DSG_BX1, DSG_BY1, DSG_NV, DSG_NE, DSG_NT, DSG_ERR,
+       DSG_SUMDEG, DSG_OLD_NV, DSG_OLD_NE, DSG_HAVE, DSG_META };
+
+struct DelGpu {
+  DsPt* vxy = nullptr;          // [S*maxV] lattice coordinates by vertex
+  DsPt* sxy = nullptr;          // [S*maxV] cell-sorted
+  int32_t* sid = nullptr;       // [S*maxV]
+  int32_t* cell_start = nullptr;  // [S*(DSG_MAXCELLS+1)]
+  int32_t* star = nullptr;      // [S*maxV*DS_MAXD]
+  int32_t* deg = nullptr;       // [S*maxV] degree | closed << 8
+  int32_t* od = nullptr;        // [S*maxV] out-degree
+  int32_t* tc = nullptr;        // [S*maxV] triangles started
+  int32_t* eoff = nullptr;      // [S*(maxV+1)]
+  int32_t* toff = nullptr;      // [S*(maxV+1)]
+  int32_t* meta = nullptr;      // [S*DSG_META]
+  int32_t* f2v = nullptr;       // [2][S*maxF] feature -> vertex of the current / previous graph (by parity)
+  // previous graph, for the carry-over
+  float* o_x = nullptr; float* o_w1 = nullptr; float* o_w2 = nullptr;
+  float4* o_vbar = nullptr; float4* o_q4 = nullptr;
+  int2* o_eij = nullptr; int32_t* o_eoff = nullptr;
+};
+
+// ------------------------------------------------------------------------------------ block scan
+// Exclusive scan of one int per thread over the block; returns the exclusive prefix, *total the sum.
+__device__ __forceinline__ int dsg_block_scan(int v, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < nw ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  *total = s_warp[nw - 1];
+  return (wid ? s_warp[wid - 1] : 0) + incl - v;
+}
+
+// ------------------------------------------------------------------------------------ k_ds_stash
+struct DsgGraph {
+  float* x; float* w1; float* w2; float4* vbar; float4* q4; int2* eij;
+};
+__global__ void __launch_bounds__(256)
+k_ds_stash(DsgGraph g, DelGpu d, int s, int maxV, int maxE) {
+  int32_t* meta = d.meta + (size_t)s * DSG_META;
+  const int V = meta[DSG_NV], E = meta[DSG_NE];
+  const size_t vb = (size_t)s * maxV, eb = (size_t)s * maxE, ob = (size_t)s * (maxV + 1);
+  const int n = blockDim.x * gridDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int v = t0; v < V; v += n) {
+    d.o_x[vb + v] = g.x[vb + v];
+    d.o_w1[vb + v] = g.w1[vb + v];
+    d.o_w2[vb + v] = g.w2[vb + v];
+    d.o_vbar[vb + v] = g.vbar[vb + v];
+  }
+  for (int v = t0; v <= V; v += n) d.o_eoff[ob + v] = d.eoff[ob + v];
+  for (int e = t0; e < E; e += n) {
+    d.o_q4[eb + e] = g.q4[eb + e];
+    d.o_eij[eb + e] = g.eij[eb + e];
+  }
+  if (t0 == 0) {
+    meta[DSG_OLD_NV] = meta[DSG_HAVE] ? V : 0;
+    meta[DSG_OLD_NE] = meta[DSG_HAVE] ? E : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------ k_ds_prepare
+struct DsgSelect {
+  const float2* u_cur;      // [maxF] projected position in the current frame
+  const float* var_cur;     // [maxF]
+  const int32_t* valid;     // [maxF]
+  float var_max;
+  int maxF, maxV, W, H;
+};
+// One CTA.  vfeat / vpos / f2v_new are the stream's slices.
+__global__ void __launch_bounds__(DSG_THREADS)
+k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t* f2v_new, int32_t* nV_out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_cnt[DSG_MAXCELLS];
+  __shared__ int s_box[4];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  int32_t* meta = d.meta + (size_t)s * DSG_META;
+  const size_t vb = (size_t)s * q.maxV;
+  DsPt* vxy = d.vxy + vb;
+  DsPt* sxy = d.sxy + vb;
+  int32_t* sid = d.sid + vb;
+  int32_t* cell_start = d.cell_start + (size_t)s * (DSG_MAXCELLS + 1);
+  if (tid == 0) {
+    s_box[0] = s_box[1] = 0x7fffffff;
+    s_box[2] = s_box[3] = -0x7fffffff;
+    s_bad = 0;
+  }
+  __syncthreads();
+  // ---- selection in ascending feature index
+  int carry = 0;
+  for (int base = 0; base < q.maxF; base += DSG_THREADS) {
+    const int f = base + tid;
+    const int flag = (f < q.maxF && q.valid[f] && q.var_cur[f] < q.var_max) ? 1 : 0;
+    int tot;
+    const int rank = carry + dsg_block_scan(flag, s_warp, &tot);
+    int v = -1;
+    if (flag && rank < q.maxV) {
+      v = rank;
+      const float2 u = q.u_cur[f];
+      int bad = 0;
+      DsPt l;
+      l.x = ds_lattice(u.x, &bad);
+      l.y = ds_lattice(u.y, &bad);
+      if (bad) s_bad = 1;
+      vfeat[v] = f;
+      vpos[v] = u;
+      vxy[v] = l;
+      atomicMin(&s_box[0], l.x); atomicMin(&s_box[1], l.y);
+      atomicMax(&s_box[2], l.x); atomicMax(&s_box[3], l.y);
+    }
+    if (f < q.maxF) f2v_new[f] = v;
+    carry += tot;
+    __syncthreads();
+  }
+  const int V = carry < q.maxV ? carry : q.maxV;
+  // ---- cell grid: ~2 mean spacings per cell, at most DS_MAXROWS rows and DSG_MAXCELLS cells
+  int shift = 9, gx = 1, gy = 1;
+  if (V > 0) {
+    const float spacing = sqrtf((float)q.W * (float)q.H / (float)V);
+    while ((float)(1 << (shift - 6)) < 2.0f * spacing && shift < 20) ++shift;
+    const int mx = s_box[2] > 0 ? s_box[2] : 0, my = s_box[3] > 0 ? s_box[3] : 0;
+    for (;; ++shift) {
+      gx = (mx >> shift) + 1;
+      gy = (my >> shift) + 1;
+      if (gy <= DS_MAXROWS && gx * gy <= DSG_MAXCELLS) break;
+    }
+  }
+  const int cells = gx * gy;
+  for (int c = tid; c < cells; c += DSG_THREADS) s_cnt[c] = 0;
+  __syncthreads();
+  DsIn in;
+  in.gx = gx; in.gy = gy; in.shift = shift;
+  // slot inside the cell (any order is fine: the stars do not depend on it); parked in `od`, which
+  // k_ds_stars overwrites later
+  int32_t* slot = d.od + vb;
+  for (int v = tid; v < V; v += DSG_THREADS) {
+    const DsPt l = vxy[v];
+    const int c = ds_celly(in, l.y) * gx + ds_cellx(in, l.x);
+    slot[v] = atomicAdd(&s_cnt[c], 1);
+  }
+  __syncthreads();
+  // ---- exclusive scan of the cell counts (in place)
+  carry = 0;
+  for (int base = 0; base < cells; base += DSG_THREADS) {
+    const int c = base + tid;
+    const int n = c < cells ? s_cnt[c] : 0;
+    int tot;
+    const int ex = carry + dsg_block_scan(n, s_warp, &tot);
+    if (c < cells) {
+      s_cnt[c] = ex;
+      cell_start[c] = ex;
+    }
+    carry += tot;
+    __syncthreads();
+  }
+  if (tid == 0) cell_start[cells] = carry;
+  // ---- scatter (slot -> sorted position)
+  for (int v = tid; v < V; v += DSG_THREADS) {
+    const DsPt l = vxy[v];
+    const int c = ds_celly(in, l.y) * gx + ds_cellx(in, l.x);
+    const int k = s_cnt[c] + slot[v];
+    sxy[k] = l;
+    sid[k] = v;
+  }
+  __syncthreads();
+  // ---- duplicates: a point with an identical point of smaller index is left out (sid = ~id)
+  for (int v = tid; v < V; v += DSG_THREADS) {
+    const DsPt l = vxy[v];
+    const int c = ds_celly(in, l.y) * gx + ds_cellx(in, l.x);
+    const int beg = s_cnt[c], end = (c + 1 < cells) ? s_cnt[c + 1] : V;
+    bool dup = false;
+    int me = -1;
+    for (int k = beg; k < end; ++k) {
+      const int raw = sid[k], id = raw < 0 ? ~raw : raw;
+      if (id == v) me = k;
+      else if (id < v && sxy[k].x == l.x && sxy[k].y == l.y) dup = true;
+    }
+    if (dup && me >= 0) sid[me] = ~v;
+  }
+  if (tid == 0) {
+    meta[DSG_GX] = gx; meta[DSG_GY] = gy; meta[DSG_SHIFT] = shift;
+    meta[DSG_BX0] = s_box[0]; meta[DSG_BY0] = s_box[1]; meta[DSG_BX1] = s_box[2]; meta[DSG_BY1] = s_box[3];
+    meta[DSG_NV] = V;
+    meta[DSG_ERR] = s_bad ? 0x100 : 0;
+    *nV_out = V;
+  }
+}
+
+// ------------------------------------------------------------------------------------ k_ds_stars
+#define DSG_WARPS 8
+__global__ void __launch_bounds__(DSG_WARPS * 32)
+k_ds_stars(DelGpu d, int s, int maxV) {
+  __shared__ int s_row[DSG_WARPS][2 * DS_MAXROWS];
+  __shared__ int s_list[DSG_WARPS][2 * DS_MAXD];
+  int32_t* meta = d.meta + (size_t)s * DSG_META;
+  const int V = meta[DSG_NV];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * DSG_WARPS + w;
+  if (p >= V) return;
+  const size_t vb = (size_t)s * maxV;
+  DsIn in;
+  in.n = V;
+  in.vxy = d.vxy + vb;
+  in.gx = meta[DSG_GX]; in.gy = meta[DSG_GY]; in.shift = meta[DSG_SHIFT];
+  in.cell_start = d.cell_start + (size_t)s * (DSG_MAXCELLS + 1);
+  in.sxy = d.sxy + vb;
+  in.sid = d.sid + vb;
+  in.bx0 = meta[DSG_BX0]; in.by0 = meta[DSG_BY0]; in.bx1 = meta[DSG_BX1]; in.by1 = meta[DSG_BY1];
+  int32_t* star = d.star + (vb + p) * DS_MAXD;
+  int deg = 0, closed = 0, od = 0, tc = 0;
+  // a duplicate point has no star: find its own entry flag through its cell
+  bool dup = false;
+  {
+    const DsPt l = in.vxy[p];
+    const int c = ds_celly(in, l.y) * in.gx + ds_cellx(in, l.x);
+    for (int k = in.cell_start[c] + lane; k < in.cell_start[c + 1]; k += 32)
+      if (in.sid[k] == ~p) dup = true;
+    dup = __any_sync(0xffffffffu, dup);
+  }
+  if (!dup) {
+    const int rc = ds_star<DsW32>(in, p, s_row[w], s_row[w] + DS_MAXROWS, s_list[w], s_list[w] + DS_MAXD, star, &deg, &closed);
+    if (rc) {
+      if (lane == 0) atomicOr(&meta[DSG_ERR], 1 << rc);
+      deg = 0;
+    }
+    __syncwarp();
+    if (lane == 0) ds_counts(p, star, deg, closed, &od, &tc);
+  }
+  if (lane == 0) {
+    d.deg[vb + p] = deg | (closed << 8);
+    d.od[vb + p] = od;
+    d.tc[vb + p] = tc;
+  }
+}
+
+// ------------------------------------------------------------------------------------ k_ds_scan
+// One CTA: offsets of edges / triangles / CSR rows, counts, consistency.
+__global__ void __launch_bounds__(DSG_THREADS)
+k_ds_scan(DelGpu d, int s, int maxV, int maxE, int maxT, int32_t* row, int32_t* nE_out, int32_t* nT_out) {
+  __shared__ int s_warp[32];
+  int32_t* meta = d.meta + (size_t)s * DSG_META;
+  const int V = meta[DSG_NV];
+  const size_t vb = (size_t)s * maxV, ob = (size_t)s * (maxV + 1);
+  int ce = 0, ct = 0, cr = 0;
+  for (int base = 0; base < V; base += DSG_THREADS) {
+    const int v = base + threadIdx.x;
+    const int o = v < V ? d.od[vb + v] : 0, t = v < V ? d.tc[vb + v] : 0, g = v < V ? (d.deg[vb + v] & 0xff) : 0;
+    int te, tt, tr;
+    const int ee = ce + dsg_block_scan(o, s_warp, &te);
+    __syncthreads();
+    const int et = ct + dsg_block_scan(t, s_warp, &tt);
+    __syncthreads();
+    const int er = cr + dsg_block_scan(g, s_warp, &tr);
+    __syncthreads();
+    if (v < V) {
+      d.eoff[ob + v] = ee;
+      d.toff[ob + v] = et;
+      row[v] = er;
+    }
+    ce += te; ct += tt; cr += tr;
+  }
+  if (threadIdx.x == 0) {
+    d.eoff[ob + V] = ce;
+    d.toff[ob + V] = ct;
+    row[V] = cr;
+    int err = meta[DSG_ERR];
+    if (cr != 2 * ce) err |= 0x200;              // asymmetric stars
+    if (ce > maxE || ct > maxT) err |= 0x400;    // capacity
+    const bool ok = err == 0 && ct > 0;
+    meta[DSG_ERR] = err;
+    meta[DSG_NE] = ok ? ce : 0;
+    meta[DSG_NT] = ok ? ct : 0;
+    meta[DSG_SUMDEG] = cr;
+    meta[DSG_HAVE] = ok ? 1 : 0;
+    *nE_out = ok ? ce : 0;
+    *nT_out = ok ? ct : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------ k_ds_emit
+__global__ void __launch_bounds__(128)
+k_ds_emit(DelGpu d, int s, int maxV, int maxE, int maxT, const float2* __restrict__ vpos, int2* __restrict__ eij,
+          float4* __restrict__ ec, int32_t* __restrict__ tri) {
+  const int32_t* meta = d.meta + (size_t)s * DSG_META;
+  const int V = meta[DSG_NV];
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V || meta[DSG_NT] == 0) return;
+  const size_t vb = (size_t)s * maxV, ob = (size_t)s * (maxV + 1);
+  const int dg = d.deg[vb + v], deg = dg & 0xff, closed = dg >> 8;
+  if (deg == 0) return;
+  int st[DS_MAXD], outs[DS_MAXD], tr[3 * DS_MAXD], ntri = 0;
+  const int32_t* star = d.star + (vb + v) * DS_MAXD;
+  for (int k = 0; k < deg; ++k) st[k] = star[k];
+  const int no = ds_emit(v, st, deg, closed, outs, tr, &ntri);
+  const int e0 = d.eoff[ob + v], t0 = d.toff[ob + v];
+  const float2 pv = vpos[v];
+  for (int k = 0; k < no; ++k) {
+    const int w = outs[k];
+    const float2 pw = vpos[w];
+    // dx = pos_i - pos_j in fp32, alpha = 1/|delta|, beta = 1 (same expressions as the host path)
+    const float dx = pv.x - pw.x, dy = pv.y - pw.y;
+    eij[e0 + k] = make_int2(v, w);
+    ec[e0 + k] = make_float4(1.0f / sqrtf(dx * dx + dy * dy), 1.0f, dx, dy);
+  }
+  for (int k = 0; k < 3 * ntri; ++k) tri[3 * t0 + k] = tr[k];
+}
+
+// ------------------------------------------------------------------------------------ k_ds_csr
+struct DsgCarry {
+  const float* mu_cur;      // [maxF] projected idepth of every feature
+  const float* var_cur;     // [maxF]
+  const int32_t* f2v_old;   // [maxF] feature -> vertex of the previous graph
+  const float* idmap;       // previous dense map (prediction) or NULL
+  int W, H, adaptive, use_prediction;
+};
+// One thread per vertex: CSR incidence (ascending edge id = in-edges by source, then out-edges),
+// data term, state carry-over for the vertex and its out-edges.
+__global__ void __launch_bounds__(128)
+k_ds_csr(DelGpu d, DsgCarry q, int s, int maxV, int maxE, const int32_t* __restrict__ vfeat,
+         const float2* __restrict__ vpos, const int2* __restrict__ eij, const int32_t* __restrict__ row,
+         int32_t* __restrict__ inc, float* z, float* wt, float* x, float* w1, float* w2, float4* vbar, float4* q4) {
+  int32_t* meta = d.meta + (size_t)s * DSG_META;
+  const int V = meta[DSG_NV];
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const size_t vb = (size_t)s * maxV, eb = (size_t)s * maxE, ob = (size_t)s * (maxV + 1);
+  // ---- data term + vertex state
+  const int f = vfeat[v];
+  const float zz = q.mu_cur[f];
+  z[v] = zz;
+  wt[v] = q.adaptive ? (1.0f / q.var_cur[f]) : 1.0f;
+  const int oV = meta[DSG_OLD_NV], oE = meta[DSG_OLD_NE];
+  const int ov = oV > 0 ? q.f2v_old[f] : -1;
+  if (ov >= 0 && ov < oV) {
+    x[v] = d.o_x[vb + ov];
+    w1[v] = d.o_w1[vb + ov];
+    w2[v] = d.o_w2[vb + ov];
+    vbar[v] = d.o_vbar[vb + ov];
+  } else {
+    float x0 = zz;
+    if (q.use_prediction && q.idmap) {
+      const int px = (int)rintf(vpos[v].x), py = (int)rintf(vpos[v].y);
+      if (px >= 0 && py >= 0 && px < q.W && py < q.H) {
+        const float p = q.idmap[py * q.W + px];
+        if (p == p && p > 0.0f) x0 = p;
+      }
+    }
+    x[v] = x0;
+    w1[v] = 0.0f;
+    w2[v] = 0.0f;
+    vbar[v] = make_float4(x0, 0.0f, 0.0f, 0.0f);
+  }
+  if (meta[DSG_NT] == 0) return;
+  const int dg = d.deg[vb + v], deg = dg & 0xff;
+  const int e0 = d.eoff[ob + v], e1 = d.eoff[ob + v + 1];
+  // ---- out-edges: carry q over from the previous graph (both endpoints persisted, edge existed)
+  for (int e = e0; e < e1; ++e) {
+    float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ov >= 0 && ov < oV) {
+      const int ow = q.f2v_old[vfeat[eij[e].y]];
+      if (ow >= 0 && ow < oV) {
+        const int b = d.o_eoff[ob + ov], en = d.o_eoff[ob + ov + 1];
+        for (int k = b; k < en && k < oE; ++k)
+          if (d.o_eij[eb + k].y == ow) {
+            qq = d.o_q4[eb + k];
+            break;
+          }
+      }
+    }
+    q4[e] = qq;
+  }
+  // ---- CSR: in-edges (neighbours u < v, ascending u), then out-edges (ascending target)
+  int ins[DS_MAXD], ni = 0;
+  const int32_t* star = d.star + (vb + v) * DS_MAXD;
+  for (int k = 0; k < deg; ++k) {
+    const int u = star[k];
+    if (u >= v) continue;
+    int pos = ni++;
+    while (pos > 0 && ins[pos - 1] > u) { ins[pos] = ins[pos - 1]; --pos; }
+    ins[pos] = u;
+  }
+  int r = row[v];
+  for (int k = 0; k < ni; ++k) {
+    const int u = ins[k];
+    const int b = d.eoff[ob + u], en = d.eoff[ob + u + 1];
+    int e = -1;
+    for (int m = b; m < en; ++m)
+      if (eij[m].y == v) {
+        e = m;
+        break;
+      }
+    if (e < 0) {
+      atomicOr(&meta[DSG_ERR], 0x800);  // u does not list v
+      e = 0;
+    }
+    inc[r++] = (e << 1) | 1;
+  }
+  for (int e = e0; e < e1; ++e) inc[r++] = e << 1;
+}

@@ -1,0 +1,456 @@
+// delaunay_star.h -- per-vertex Delaunay stars: the core of the GPU `triangulate` stage.
+//
+// Stands in for the `triangulate` stage of flame::Flame::update (timing key
+// /root/reference/src/utils.cc:154; the external flame core wraps Shewchuk's Triangle).  The host
+// triangulator (delaunay.h) inserts points one by one into a shared structure -- inherently serial,
+// 2.7 ms per frame at 5.9k vertices and every frame changes ~2 % of the edges, so nothing can be
+// cached.  Here every vertex computes ITS OWN star (its Delaunay neighbours in counter-clockwise
+// order) independently, one warp per vertex:
+//   1. nearest neighbour n0 (always a Delaunay neighbour: its diametral circle is empty);
+//   2. counter-clockwise sweep: given the Delaunay edge (p, cur), the next neighbour is the point c
+//      strictly left of p->cur whose circle (p, cur, c) contains no other left point (a max under
+//      the in-circle order: one pass over the candidates, lanes in parallel, shuffle reduction);
+//   3. an open star (p on the convex hull) is completed by the mirrored clockwise sweep from n0.
+// Candidates come from a uniform cell grid.  A pass over a block of cells is conclusive only when
+// the block covers (circle or half-plane) INTERSECTED with the bounding box of all points; else the
+// block grows to that region and the pass is repeated.  Hull edges and hull slivers therefore cost
+// a strip of boundary cells, not the whole point set.
+// Exactness: lattice coordinates (1/64 px), orientation in 64-bit integers, in-circle by a double
+// filter with a 128-bit integer fallback -- the same predicates as delaunay.h, so both produce THE
+// Delaunay triangulation.  Co-circular point sets (integer-pixel detections form exact rectangles)
+// are triangulated canonically by both: the polygon of points on one empty circle becomes a fan
+// from its smallest vertex index.  Seen from p with the edge (p, cur) and the tied set T on the
+// sweep side: p smallest -> the member of T angularly closest to cur; cur smallest -> the farthest;
+// otherwise the smallest index itself (which then is in T).
+//
+// The same source is compiled for the device (32 lanes) and, in tests/cpp/star_sim.cc, for the host
+// with a 1-lane "warp" so the logic is checked against the host triangulator without a GPU.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define DS_FN __host__ __device__ __forceinline__
+#define DS_MEM __host__ __device__ __forceinline__ static
+#else
+#define DS_FN static inline
+#define DS_MEM static inline
+#endif
+
+#define DS_MAXD 32      // largest star (error above)
+#define DS_MAXROWS 64   // grid rows (cells along y) at most
+#define DS_COORD_LIM (1 << 20)
+
+typedef __int128 ds_i128;
+
+struct DsPt {
+  int32_t x, y;
+};
+
+struct DsIn {
+  int n;                      // vertices (including duplicates)
+  const DsPt* vxy;            // [n] lattice coordinates by vertex id
+  int gx, gy, shift;          // cell grid: cell = clamp(coord >> shift)
+  const int32_t* cell_start;  // [gx*gy + 1] into the cell-sorted arrays
+  const DsPt* sxy;            // [n] cell-sorted coordinates
+  const int32_t* sid;         // [n] vertex id of the sorted entry, ~id for a duplicate point
+  int bx0, by0, bx1, by1;     // bounding box of all points (lattice)
+};
+
+enum { DS_OK = 0, DS_E_DEGREE = 1, DS_E_TIE = 2, DS_E_LOOP = 3 };
+
+// ------------------------------------------------------------------------------------ predicates
+DS_FN int64_t ds_orient(DsPt a, DsPt b, DsPt c) {
+  return (int64_t)(b.x - a.x) * (int64_t)(c.y - a.y) - (int64_t)(b.y - a.y) * (int64_t)(c.x - a.x);
+}
+
+// > 0 iff p lies strictly inside the circumcircle of the counter-clockwise triangle (a, b, c);
+// 0 iff on it.  |coordinates| < 2^20: differences < 2^21, squared lengths and 2x2 minors < 2^43 are
+// exact in double; the three-term sum is decided by a static error bound, else exactly in 128 bits.
+DS_FN int ds_incircle(DsPt a, DsPt b, DsPt c, DsPt p) {
+  const int64_t adx = a.x - p.x, ady = a.y - p.y, bdx = b.x - p.x, bdy = b.y - p.y;
+  const int64_t cdx = c.x - p.x, cdy = c.y - p.y;
+  const int64_t al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
+  const int64_t ma = bdx * cdy - bdy * cdx, mb = cdx * ady - cdy * adx, mc = adx * bdy - ady * bdx;
+  const double ta = (double)al * (double)ma, tb = (double)bl * (double)mb, tc = (double)cl * (double)mc;
+  const double det = ta + tb + tc;
+  const double bound = 8.9e-16 * (fabs(ta) + fabs(tb) + fabs(tc));
+  if (det > bound) return 1;
+  if (det < -bound) return -1;
+  const ds_i128 d = (ds_i128)al * (ds_i128)ma + (ds_i128)bl * (ds_i128)mb + (ds_i128)cl * (ds_i128)mc;
+  return d > 0 ? 1 : (d < 0 ? -1 : 0);
+}
+
+// dir = +1: counter-clockwise sweep (candidates strictly left of p->cur), -1: clockwise (right).
+DS_FN bool ds_side(DsPt p, DsPt cur, DsPt c, int dir) {
+  const int64_t o = ds_orient(p, cur, c);
+  return dir > 0 ? o > 0 : o < 0;
+}
+// > 0: c strictly inside the circle (p, cur, b); 0: on it.  b and c are on the sweep side.
+DS_FN int ds_inside(DsPt p, DsPt cur, DsPt b, DsPt c, int dir) {
+  return dir > 0 ? ds_incircle(p, cur, b, c) : ds_incircle(p, b, cur, c);
+}
+
+// ------------------------------------------------------------------------------------ lanes
+struct DsSeq {  // host simulation: one lane
+  static const int LANES = 1;
+  DS_MEM int lane() { return 0; }
+  DS_MEM int shfl_xor(int v, int) { return v; }
+  DS_MEM long long shfl_xor(long long v, int) { return v; }
+  DS_MEM int bcast(int v, int) { return v; }
+  DS_MEM bool any(bool p) { return p; }
+  DS_MEM void sync() {}
+};
+#ifdef __CUDACC__
+struct DsW32 {
+  static const int LANES = 32;
+  __device__ __forceinline__ static int lane() { return threadIdx.x & 31; }
+  __device__ __forceinline__ static int shfl_xor(int v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+  __device__ __forceinline__ static long long shfl_xor(long long v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+  __device__ __forceinline__ static int bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ __forceinline__ static bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+  __device__ __forceinline__ static void sync() { __syncwarp(); }
+};
+#endif
+
+// ------------------------------------------------------------------------------------ cell blocks
+struct DsBlock {
+  int x0, y0, x1, y1;  // inclusive cell rectangle
+  int nrows;           // rows of the row table (1 when the rectangle spans the full grid width)
+};
+
+DS_FN int ds_cellx(const DsIn& in, int64_t x) {
+  const int64_t c = x >> in.shift;
+  return c < 0 ? 0 : (c >= in.gx ? in.gx - 1 : (int)c);
+}
+DS_FN int ds_celly(const DsIn& in, int64_t y) {
+  const int64_t c = y >> in.shift;
+  return c < 0 ? 0 : (c >= in.gy ? in.gy - 1 : (int)c);
+}
+
+// Row table of a block: contiguous ranges of the cell-sorted arrays (cells are sorted row-major).
+template <class W>
+DS_FN void ds_block_rows(const DsIn& in, DsBlock& b, int* rowbeg, int* rowcnt) {
+  W::sync();
+  if (b.x0 == 0 && b.x1 == in.gx - 1) {
+    b.nrows = 1;
+    if (W::lane() == 0) {
+      rowbeg[0] = in.cell_start[b.y0 * in.gx];
+      rowcnt[0] = in.cell_start[(b.y1 + 1) * in.gx] - rowbeg[0];
+    }
+  } else {
+    b.nrows = b.y1 - b.y0 + 1;
+    for (int r = W::lane(); r < b.nrows; r += W::LANES) {
+      const int beg = in.cell_start[(b.y0 + r) * in.gx + b.x0];
+      rowbeg[r] = beg;
+      rowcnt[r] = in.cell_start[(b.y0 + r) * in.gx + b.x1 + 1] - beg;
+    }
+  }
+  W::sync();
+}
+
+// Grow the block to contain the lattice rectangle [rx0,rx1]x[ry0,ry1]; true when it changed.
+DS_FN bool ds_block_cover(const DsIn& in, DsBlock& b, int64_t rx0, int64_t ry0, int64_t rx1, int64_t ry1) {
+  const int nx0 = ds_cellx(in, rx0), nx1 = ds_cellx(in, rx1), ny0 = ds_celly(in, ry0), ny1 = ds_celly(in, ry1);
+  bool ch = false;
+  if (nx0 < b.x0) { b.x0 = nx0; ch = true; }
+  if (ny0 < b.y0) { b.y0 = ny0; ch = true; }
+  if (nx1 > b.x1) { b.x1 = nx1; ch = true; }
+  if (ny1 > b.y1) { b.y1 = ny1; ch = true; }
+  return ch;
+}
+DS_FN bool ds_block_all(const DsIn& in, const DsBlock& b) {
+  return b.x0 == 0 && b.y0 == 0 && b.x1 == in.gx - 1 && b.y1 == in.gy - 1;
+}
+
+// Bounding box of (closed disc through p, a, b) clipped to the bounding box of all points.
+// (p, a, b) counter-clockwise.  Conservative: rounded outward.
+DS_FN void ds_circle_region(const DsIn& in, DsPt p, DsPt a, DsPt b, int64_t* r) {
+  const double ax = (double)(a.x - p.x), ay = (double)(a.y - p.y), bx = (double)(b.x - p.x), by = (double)(b.y - p.y);
+  const double d = 2.0 * (ax * by - ay * bx);  // > 0, exact
+  const double a2 = ax * ax + ay * ay, b2 = bx * bx + by * by;
+  const double ux = (by * a2 - ay * b2) / d, uy = (ax * b2 - bx * a2) / d;
+  const double rad = sqrt(ux * ux + uy * uy);
+  const double m = 2.0 + rad * 1e-9 + (fabs(ux) + fabs(uy)) * 1e-9;
+  double x0 = (double)p.x + ux - rad - m, x1 = (double)p.x + ux + rad + m;
+  double y0 = (double)p.y + uy - rad - m, y1 = (double)p.y + uy + rad + m;
+  x0 = fmax(x0, (double)in.bx0); y0 = fmax(y0, (double)in.by0);
+  x1 = fmin(x1, (double)in.bx1); y1 = fmin(y1, (double)in.by1);
+  r[0] = (int64_t)floor(x0); r[1] = (int64_t)floor(y0); r[2] = (int64_t)ceil(x1); r[3] = (int64_t)ceil(y1);
+}
+
+// Bounding box of (half-plane on the sweep side of p->cur) clipped to the bounding box of all
+// points; false when the intersection is empty.
+DS_FN bool ds_halfplane_region(const DsIn& in, DsPt p, DsPt cur, int dir, int64_t* r) {
+  const DsPt c[4] = {{in.bx0, in.by0}, {in.bx1, in.by0}, {in.bx1, in.by1}, {in.bx0, in.by1}};
+  int64_t o[4];
+  for (int k = 0; k < 4; ++k) o[k] = ds_orient(p, cur, c[k]) * dir;
+  double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+  bool any = false;
+  for (int k = 0; k < 4; ++k) {
+    if (o[k] > 0) {
+      any = true;
+      x0 = fmin(x0, (double)c[k].x); x1 = fmax(x1, (double)c[k].x);
+      y0 = fmin(y0, (double)c[k].y); y1 = fmax(y1, (double)c[k].y);
+    }
+    const int k2 = (k + 1) & 3;
+    if ((o[k] > 0) != (o[k2] > 0)) {
+      const double t = (double)o[k] / ((double)o[k] - (double)o[k2]);
+      const double ix = (double)c[k].x + t * (double)(c[k2].x - c[k].x);
+      const double iy = (double)c[k].y + t * (double)(c[k2].y - c[k].y);
+      any = true;
+      x0 = fmin(x0, ix - 2.0); x1 = fmax(x1, ix + 2.0);
+      y0 = fmin(y0, iy - 2.0); y1 = fmax(y1, iy + 2.0);
+    }
+  }
+  if (!any) return false;
+  x0 = fmax(x0, (double)in.bx0); y0 = fmax(y0, (double)in.by0);
+  x1 = fmin(x1, (double)in.bx1); y1 = fmin(y1, (double)in.by1);
+  r[0] = (int64_t)floor(x0); r[1] = (int64_t)floor(y0); r[2] = (int64_t)ceil(x1); r[3] = (int64_t)ceil(y1);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------ sweep step
+// Next neighbour of p after cur in direction dir; -1 when there is none (hull end).  All lanes
+// return the same value; *nxy receives its coordinates.  *err is set on an invariant violation.
+template <class W>
+DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, DsBlock& blk, int* rowbeg,
+                  int* rowcnt, DsPt* nxy, int* err) {
+  for (int guard = 0; guard < 4 * DS_MAXROWS; ++guard) {
+    int bid = -1;
+    DsPt bxy = {0, 0};
+    for (int r = 0; r < blk.nrows; ++r) {
+      const int beg = rowbeg[r], end = beg + rowcnt[r];
+      for (int k = beg + W::lane(); k < end; k += W::LANES) {
+        const int id = in.sid[k];
+        if (id < 0 || id == p || id == curid) continue;
+        const DsPt c = in.sxy[k];
+        if (!ds_side(pp, cur, c, dir)) continue;
+        if (bid < 0 || ds_inside(pp, cur, bxy, c, dir) > 0) {
+          bid = id;
+          bxy = c;
+        }
+      }
+    }
+    for (int o = W::LANES >> 1; o > 0; o >>= 1) {
+      const int oid = W::shfl_xor(bid, o);
+      DsPt oxy;
+      oxy.x = W::shfl_xor(bxy.x, o);
+      oxy.y = W::shfl_xor(bxy.y, o);
+      if (oid >= 0 && (bid < 0 || ds_inside(pp, cur, bxy, oxy, dir) > 0)) {
+        bid = oid;
+        bxy = oxy;
+      }
+    }
+    bid = W::bcast(bid, 0);  // tied lanes may disagree: lane 0 decides
+    bxy.x = W::bcast(bxy.x, 0);
+    bxy.y = W::bcast(bxy.y, 0);
+    int64_t reg[4];
+    if (bid < 0) {
+      if (ds_block_all(in, blk) || !ds_halfplane_region(in, pp, cur, dir, reg)) return -1;
+      if (!ds_block_cover(in, blk, reg[0], reg[1], reg[2], reg[3])) return -1;
+      ds_block_rows<W>(in, blk, rowbeg, rowcnt);
+      continue;
+    }
+    if (!ds_block_all(in, blk)) {
+      if (dir > 0) ds_circle_region(in, pp, cur, bxy, reg);
+      else ds_circle_region(in, pp, bxy, cur, reg);
+      if (ds_block_cover(in, blk, reg[0], reg[1], reg[2], reg[3])) {
+        ds_block_rows<W>(in, blk, rowbeg, rowcnt);
+        continue;
+      }
+    }
+    // the circle (p, cur, best) is empty; other points ON it make a co-circular polygon
+    bool tie = false;
+    for (int r = 0; r < blk.nrows; ++r) {
+      const int beg = rowbeg[r], end = beg + rowcnt[r];
+      for (int k = beg + W::lane(); k < end; k += W::LANES) {
+        const int id = in.sid[k];
+        if (id < 0 || id == p || id == curid || id == bid) continue;
+        const DsPt c = in.sxy[k];
+        if (ds_side(pp, cur, c, dir) && ds_inside(pp, cur, bxy, c, dir) == 0) tie = true;
+      }
+    }
+    if (W::any(tie)) {
+      // canonical fan from the smallest index (all lanes run the same sequential pass)
+      int minid = p < curid ? p : curid;
+      int cl = bid, fa = bid, mt = -1;
+      DsPt clxy = bxy, faxy = bxy, mtxy = bxy;
+      if (bid < minid) { minid = bid; mt = bid; }
+      for (int r = 0; r < blk.nrows; ++r) {
+        const int beg = rowbeg[r], end = beg + rowcnt[r];
+        for (int k = beg; k < end; ++k) {
+          const int id = in.sid[k];
+          if (id < 0 || id == p || id == curid || id == bid) continue;
+          const DsPt c = in.sxy[k];
+          if (!ds_side(pp, cur, c, dir) || ds_inside(pp, cur, bxy, c, dir) != 0) continue;
+          if (id < minid) { minid = id; mt = id; mtxy = c; }
+          if (ds_orient(pp, c, clxy) * dir > 0) { cl = id; clxy = c; }   // c comes before the closest so far
+          if (ds_orient(pp, faxy, c) * dir > 0) { fa = id; faxy = c; }   // c comes after the farthest so far
+        }
+      }
+      if (minid == p) { bid = cl; bxy = clxy; }
+      else if (minid == curid) { bid = fa; bxy = faxy; }
+      else if (mt >= 0) { bid = mt; bxy = mtxy; }
+      else { *err = DS_E_TIE; return -1; }
+    }
+    *nxy = bxy;
+    return bid;
+  }
+  *err = DS_E_LOOP;
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------ star of p
+// ccw / cw: per-warp scratch [DS_MAXD] each; rowbeg / rowcnt: per-warp scratch [DS_MAXROWS].
+// Result (lane 0 writes): star[0..deg) counter-clockwise; *closed = 1 for an interior vertex.
+template <class W>
+DS_FN int ds_star(const DsIn& in, int p, int* rowbeg, int* rowcnt, int* ccw, int* cw, int* star, int* deg_out,
+                  int* closed_out) {
+  const DsPt pp = in.vxy[p];
+  const int cxp = ds_cellx(in, pp.x), cyp = ds_celly(in, pp.y);
+  DsBlock blk;
+  blk.x0 = cxp > 0 ? cxp - 1 : 0; blk.x1 = cxp < in.gx - 1 ? cxp + 1 : in.gx - 1;
+  blk.y0 = cyp > 0 ? cyp - 1 : 0; blk.y1 = cyp < in.gy - 1 ? cyp + 1 : in.gy - 1;
+  ds_block_rows<W>(in, blk, rowbeg, rowcnt);
+  *deg_out = 0;
+  *closed_out = 0;
+  // ---- nearest neighbour
+  int n0 = -1;
+  DsPt n0xy = {0, 0};
+  for (int guard = 0; guard < 4 * DS_MAXROWS; ++guard) {
+    long long bd = 0x7fffffffffffffffll;
+    int bid = -1;
+    DsPt bxy = {0, 0};
+    for (int r = 0; r < blk.nrows; ++r) {
+      const int beg = rowbeg[r], end = beg + rowcnt[r];
+      for (int k = beg + W::lane(); k < end; k += W::LANES) {
+        const int id = in.sid[k];
+        if (id < 0 || id == p) continue;
+        const DsPt c = in.sxy[k];
+        const long long dx = c.x - pp.x, dy = c.y - pp.y, d2 = dx * dx + dy * dy;
+        if (d2 < bd || (d2 == bd && id < bid)) { bd = d2; bid = id; bxy = c; }
+      }
+    }
+    for (int o = W::LANES >> 1; o > 0; o >>= 1) {
+      const long long od = W::shfl_xor(bd, o);
+      const int oid = W::shfl_xor(bid, o), ox = W::shfl_xor(bxy.x, o), oy = W::shfl_xor(bxy.y, o);
+      if (oid >= 0 && (od < bd || (od == bd && oid < bid))) { bd = od; bid = oid; bxy.x = ox; bxy.y = oy; }
+    }
+    if (bid < 0) {
+      if (ds_block_all(in, blk)) return DS_OK;  // the only point
+      const int hx = blk.x1 - blk.x0 + 1, hy = blk.y1 - blk.y0 + 1;
+      blk.x0 = blk.x0 - hx < 0 ? 0 : blk.x0 - hx; blk.x1 = blk.x1 + hx > in.gx - 1 ? in.gx - 1 : blk.x1 + hx;
+      blk.y0 = blk.y0 - hy < 0 ? 0 : blk.y0 - hy; blk.y1 = blk.y1 + hy > in.gy - 1 ? in.gy - 1 : blk.y1 + hy;
+      ds_block_rows<W>(in, blk, rowbeg, rowcnt);
+      continue;
+    }
+    const int64_t rr = (int64_t)ceil(sqrt((double)bd)) + 2;
+    int64_t x0 = pp.x - rr, x1 = pp.x + rr, y0 = pp.y - rr, y1 = pp.y + rr;
+    if (x0 < in.bx0) x0 = in.bx0;
+    if (y0 < in.by0) y0 = in.by0;
+    if (x1 > in.bx1) x1 = in.bx1;
+    if (y1 > in.by1) y1 = in.by1;
+    if (!ds_block_all(in, blk) && ds_block_cover(in, blk, x0, y0, x1, y1)) {
+      ds_block_rows<W>(in, blk, rowbeg, rowcnt);
+      continue;
+    }
+    n0 = bid;
+    n0xy = bxy;
+    break;
+  }
+  if (n0 < 0) return DS_E_LOOP;
+  // ---- counter-clockwise sweep from n0
+  int err = DS_OK, nccw = 1, ncw = 0, closed = 0;
+  if (W::lane() == 0) ccw[0] = n0;
+  int curid = n0;
+  DsPt cur = n0xy;
+  for (;;) {
+    DsPt nxy;
+    const int nx = ds_next<W>(in, p, pp, curid, cur, +1, blk, rowbeg, rowcnt, &nxy, &err);
+    if (err) return err;
+    if (nx < 0) break;
+    if (nx == n0) { closed = 1; break; }
+    if (nccw >= DS_MAXD) return DS_E_DEGREE;
+    if (W::lane() == 0) ccw[nccw] = nx;
+    ++nccw;
+    curid = nx;
+    cur = nxy;
+  }
+  if (!closed) {  // hull vertex: clockwise sweep from n0
+    curid = n0;
+    cur = n0xy;
+    for (;;) {
+      DsPt nxy;
+      const int nx = ds_next<W>(in, p, pp, curid, cur, -1, blk, rowbeg, rowcnt, &nxy, &err);
+      if (err) return err;
+      if (nx < 0) break;
+      if (nccw + ncw >= DS_MAXD) return DS_E_DEGREE;
+      if (W::lane() == 0) cw[ncw] = nx;
+      ++ncw;
+      curid = nx;
+      cur = nxy;
+    }
+  }
+  W::sync();
+  if (W::lane() == 0) {
+    for (int k = 0; k < ncw; ++k) star[k] = cw[ncw - 1 - k];
+    for (int k = 0; k < nccw; ++k) star[ncw + k] = ccw[k];
+  }
+  W::sync();
+  *deg_out = nccw + ncw;
+  *closed_out = closed;
+  return DS_OK;
+}
+
+// ------------------------------------------------------------------------------------ stars -> mesh
+// Canonical mesh from the stars (shared by the device kernels and the host simulation):
+//   edges (i, j), i < j, sorted by (i, j): vertex v contributes its neighbours larger than v;
+//   triangles (v, a, b) counter-clockwise with v the smallest index, sorted by (v, a): vertex v
+//   contributes every consecutive star pair (a, b) with a > v and b > v.
+DS_FN void ds_counts(int v, const int* star, int deg, int closed, int* od, int* tc) {
+  int o = 0, t = 0;
+  for (int k = 0; k < deg; ++k) o += star[k] > v ? 1 : 0;
+  const int pairs = closed ? deg : deg - 1;
+  for (int k = 0; k < pairs; ++k) {
+    const int a = star[k], b = star[k + 1 == deg ? 0 : k + 1];
+    t += (a > v && b > v) ? 1 : 0;
+  }
+  *od = o;
+  *tc = t;
+}
+// outs[0..od): ascending; tris[0..3*tc): (v, a, b) ascending a.  Returns od; *tc_out = tc.
+DS_FN int ds_emit(int v, const int* star, int deg, int closed, int* outs, int* tris, int* tc_out) {
+  int o = 0, t = 0;
+  for (int k = 0; k < deg; ++k) {
+    const int w = star[k];
+    if (w <= v) continue;
+    int pos = o++;
+    while (pos > 0 && outs[pos - 1] > w) { outs[pos] = outs[pos - 1]; --pos; }
+    outs[pos] = w;
+  }
+  const int pairs = closed ? deg : deg - 1;
+  for (int k = 0; k < pairs; ++k) {
+    const int a = star[k], b = star[k + 1 == deg ? 0 : k + 1];
+    if (!(a > v && b > v)) continue;
+    int pos = t++;
+    while (pos > 0 && tris[3 * (pos - 1) + 1] > a) {
+      tris[3 * pos + 1] = tris[3 * (pos - 1) + 1];
+      tris[3 * pos + 2] = tris[3 * (pos - 1) + 2];
+      --pos;
+    }
+    tris[3 * pos + 1] = a;
+    tris[3 * pos + 2] = b;
+  }
+  for (int k = 0; k < t; ++k) tris[3 * k] = v;
+  *tc_out = t;
+  return o;
+}
+
+// Lattice coordinate of a pixel position (same rounding as delaunay.h: llroundf(v * 64)).
+DS_FN int32_t ds_lattice(float v, int* bad) {
+  const long long l = llroundf(v * 64.0f);
+  if (l <= -(long long)DS_COORD_LIM || l >= (long long)DS_COORD_LIM) { *bad = 1; return 0; }
+  return (int32_t)l;
+}

@@ -15,11 +15,13 @@
 #include "nltgv2.cuh"
 #include "nltgv2_cluster.cuh"
 #include "nltgv2_grid.cuh"
+#include "nltgv2_coop.cuh"
 #include "raster.cuh"
 #include "frontend.cuh"
 
 static std::string g_create_error;
 static void update_free(fb_ctx* c);
+static void update_mark_host_graph(fb_ctx* c, int s);
 
 // ------------------------------------------------------------------------------------ helpers
 
@@ -94,7 +96,9 @@ static void free_all(fb_ctx* c) {
   cluster_plan_free(c);
   grid_plan_free(c);
   update_free(c);
-  if (c->solve_exec) cudaGraphExecDestroy(c->solve_exec);
+  for (cudaGraphExec_t e : c->solve_exec) if (e) cudaGraphExecDestroy(e);
+  cudaFree(c->coop_contrib); cudaFree(c->idmap_scratch);
+  if (c->coop_err) cudaFreeHost(c->coop_err);
   for (int k = 0; k < FB_PROF_NUM; ++k)
     for (cudaEvent_t e : c->sec[k].ev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->prof_free) cudaEventDestroy(e);
@@ -289,6 +293,7 @@ extern "C" int fb_graph_set(fb_ctx* c, int s, int V, int E, const float* pos,
   }
   c->hV[s] = V;
   c->hE[s] = E;
+  update_mark_host_graph(c, s);
   FB_CUDA(c, cudaMemcpyAsync(c->nV + s, &c->hV[s], sizeof(int32_t), cudaMemcpyHostToDevice, st));
   FB_CUDA(c, cudaMemcpyAsync(c->nE + s, &c->hE[s], sizeof(int32_t), cudaMemcpyHostToDevice, st));
   int rc = cluster_plan_build(c, s, V, E, eij.data(), row.data(), inc.data());
@@ -379,18 +384,22 @@ extern "C" int fb_graph_x_get_all(fb_ctx* c, float* x_all) {
 }
 
 static int solve_streaming(fb_ctx* c, int iters, const fb_nltgv2_params* p, int only = -1) {
-  int maxv = 0, maxe = 0;
-  for (int s = 0; s < c->S; ++s) { maxv = std::max(maxv, c->hV[s]); maxe = std::max(maxe, c->hE[s]); }
-  if (maxv == 0) return FB_OK;
-  // The launch sequence is captured once per (iters, params, extent) and replayed as one graph.
+  // The launch sequence is captured once per (only, iters, params) and replayed as one graph; grid
+  // extents cover the context capacity and counts are read on the device, so a captured graph
+  // survives topology changes.
   static_assert(sizeof(fb_nltgv2_params) == 24, "params layout");
-  const bool reuse = c->solve_exec && c->solve_iters == iters && c->solve_only == only &&
-                     memcmp(&c->solve_params, p, sizeof(*p)) == 0;
+  if (c->solve_exec.empty()) {
+    c->solve_exec.assign(c->S + 1, nullptr);
+    c->solve_iters.assign(c->S + 1, 0);
+    c->solve_params.assign(c->S + 1, fb_nltgv2_params{});
+  }
+  const int slot = only + 1;
+  const bool reuse = c->solve_exec[slot] && c->solve_iters[slot] == iters &&
+                     memcmp(&c->solve_params[slot], p, sizeof(*p)) == 0;
   if (!reuse) {
-    if (c->solve_exec) { cudaGraphExecDestroy(c->solve_exec); c->solve_exec = nullptr; }
+    if (c->solve_exec[slot]) { cudaGraphExecDestroy(c->solve_exec[slot]); c->solve_exec[slot] = nullptr; }
     GraphView g = graph_view(c);
     g.only = only;
-    // grid extents cover the context capacity so the captured graph survives topology changes
     const dim3 ge(fb_div_up(std::max(c->maxE, 1), 256), c->S), gv(fb_div_up(c->maxV, 256), c->S);
     const float tl = p->step_x * p->data_factor;
     cudaGraph_t graph = nullptr;
@@ -400,24 +409,111 @@ static int solve_streaming(fb_ctx* c, int iters, const fb_nltgv2_params* p, int 
       k_primal_vertices<<<gv, 256, 0, c->stream>>>(g, p->step_x, tl, p->theta, p->x_min, p->x_max);
     }
     FB_CUDA(c, cudaStreamEndCapture(c->stream, &graph));
-    cudaError_t e = cudaGraphInstantiate(&c->solve_exec, graph, 0);
+    cudaError_t e = cudaGraphInstantiate(&c->solve_exec[slot], graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { c->solve_exec = nullptr; FB_FAIL(c, FB_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
-    c->solve_iters = iters;
-    c->solve_only = only;
-    c->solve_params = *p;
+    if (e != cudaSuccess) { c->solve_exec[slot] = nullptr; FB_FAIL(c, FB_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    c->solve_iters[slot] = iters;
+    c->solve_params[slot] = *p;
   }
   ProfScope ps(c, FB_PROF_SOLVE);
-  FB_CUDA(c, cudaGraphLaunch(c->solve_exec, c->stream));
+  FB_CUDA(c, cudaGraphLaunch(c->solve_exec[slot], c->stream));
   c->launches += 2 * (int64_t)iters;
   return FB_OK;
 }
 
+// ---- variant 4: plan-free resident solver (nltgv2_coop.cuh) ---------------------------------------
+static const void* coop_kernel(int ept) {
+  return ept <= 3 ? (const void*)k_nltgv2_coop<3, 1> : (const void*)k_nltgv2_coop<6, 2>;
+}
+// Cluster size and instantiation for this context's capacities; coop_cluster = 0 when unavailable.
+static void coop_probe(fb_ctx* c) {
+  if (c->coop_cluster >= 0) return;
+  c->coop_cluster = 0;
+  const int sizes[2] = {16, 8};
+  for (int k = 0; k < 2 && !c->coop_cluster; ++k) {
+    const int C = sizes[k], NT = C * FBK_THREADS;
+    int ept = 0, vpt = 0;
+    if (c->maxE <= 3 * NT && c->maxV <= NT) { ept = 3; vpt = 1; }
+    else if (c->maxE <= 6 * NT && c->maxV <= 2 * NT) { ept = 6; vpt = 2; }
+    else continue;
+    const void* kern = coop_kernel(ept);
+    if (C > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3((unsigned)C);
+    q.blockDim = dim3(FBK_THREADS);
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = (unsigned)C; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa;
+    q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (n >= 1) { c->coop_cluster = C; c->coop_ept = ept; c->coop_vpt = vpt; }
+  }
+  if (const char* e = getenv("FB_COOP_DISABLE")) if (atoi(e)) c->coop_cluster = 0;
+}
+static bool fb_coop_failed(const fb_ctx* c) { return c->coop_err && *c->coop_err != 0; }
+
+static int solve_coop(fb_ctx* c, int iters, const fb_nltgv2_params* p, int only = -1) {
+  coop_probe(c);
+  if (!c->coop_cluster) FB_FAIL(c, FB_E_STATE, "fb_nltgv2_solve: the plan-free resident solver does not fit this context");
+  if (!c->coop_contrib) {
+    FB_CUDA(c, dalloc(&c->coop_contrib, (size_t)c->S * 2 * c->maxE));
+    FB_CUDA(c, cudaHostAlloc((void**)&c->coop_err, sizeof(int), cudaHostAllocMapped));
+    *c->coop_err = 0;
+  }
+  GraphView g = graph_view(c);
+  g.only = only;
+  const int C = c->coop_cluster;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((only >= 0 ? 1 : c->S) * C));
+  cfg.blockDim = dim3(FBK_THREADS);
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  float sq = p->step_q, sx = p->step_x, tl = p->step_x * p->data_factor, th = p->theta, x0 = p->x_min, x1 = p->x_max;
+  int itv = iters;
+  float4* cb = c->coop_contrib;
+  int* er = c->coop_err;
+  void* args[] = {&g, &cb, &er, &itv, &sq, &sx, &tl, &th, &x0, &x1};
+  ProfScope ps(c, FB_PROF_SOLVE);
+  FB_CUDA(c, cudaLaunchKernelExC(&cfg, coop_kernel(c->coop_ept), args));
+  c->launches++;
+  c->last_cluster = C;
+  return FB_OK;
+}
+
+// True when a stream's current graph was built on the device (fb_update, delaunay_gpu.cuh): the
+// per-topology tables of variants 2 / 3 then do not exist for it.
+static bool any_device_graph(const fb_ctx* c);
+
 extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, int variant) {
   CHECK_CTX(c);
-  if (!p || iters < 0 || variant < 0 || variant > 3) FB_FAIL(c, FB_E_ARG, "fb_nltgv2_solve: bad argument");
+  if (!p || iters < 0 || variant < 0 || variant > 4) FB_FAIL(c, FB_E_ARG, "fb_nltgv2_solve: bad argument");
   if (iters == 0) return FB_OK;
   int v = variant;
+  const bool devg = any_device_graph(c);
+  if (devg && (v == 2 || v == 3)) FB_FAIL(c, FB_E_STATE, "fb_nltgv2_solve: variants 2 / 3 need a host-set topology (fb_graph_set)");
+  if (v == 4 || (v == 0 && devg)) {
+    coop_probe(c);
+    if (c->coop_cluster) {
+      c->last_variant = 4;
+      const int rc = solve_coop(c, iters, p);
+      if (rc == FB_OK || v == 4) return rc;
+      cudaGetLastError();
+      c->coop_cluster = 0;
+    } else if (v == 4) {
+      FB_FAIL(c, FB_E_STATE, "fb_nltgv2_solve: the plan-free resident solver does not fit this context");
+    }
+    c->last_variant = 1;
+    return solve_streaming(c, iters, p);
+  }
   if ((v == 0 && !c->grid_disabled) || v == 3) {
     int nper = 0;
     size_t smem = 0;
@@ -445,17 +541,18 @@ extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, 
   return solve_streaming(c, iters, p);
 }
 
-// One stream of a batch (fb_update drives streams independently).
+// One stream of a batch (fb_update drives streams independently).  fb_update re-triangulates every
+// frame (~2 % of the edges change), so per-topology tables are never reusable: the plan-free resident
+// kernel (variant 4) takes the solve, the streaming kernels (graph replay) when it does not fit.
 static int fb_nltgv2_solve_stream(fb_ctx* c, int s, int iters, const fb_nltgv2_params* p) {
   if (iters <= 0) return FB_OK;
   const int only = c->S > 1 ? s : -1;
-  // fb_update re-triangulates every frame; rebuilding the cluster plan on the host (~1 ms at 5k
-  // vertices) costs more than the persistent kernel saves, so a freshly changed topology is solved
-  // with the streaming kernels (graph replay, no per-topology host work)
-  const bool plan_fresh = c->plan && !c->plan->topo[s].dirty;
-  if (plan_fresh && cluster_plan_ready(c)) {
-    c->last_variant = 2;
-    return solve_cluster(c, iters, p, only);
+  coop_probe(c);
+  if (c->coop_cluster) {
+    c->last_variant = 4;
+    if (solve_coop(c, iters, p, only) == FB_OK) return FB_OK;
+    cudaGetLastError();  // launch refused: nothing ran
+    c->coop_cluster = 0;
   }
   c->last_variant = 1;
   return solve_streaming(c, iters, p, only);
@@ -685,7 +782,9 @@ extern "C" int fb_idepth_update(fb_ctx* c, const int32_t* cmp_slot) {
   ProfScope ps(c, FB_PROF_IDEPTH);
   int rc = upload_geometry(c, cmp_slot);
   if (rc) return rc;
-  FB_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(int32_t) * c->S * FB_NUM_COUNTERS, c->stream));
+  for (int s = 0; s < c->S; ++s)  // only the streams updated by this call: the others keep theirs
+    if (cmp_slot[s] >= 0)
+      FB_CUDA(c, cudaMemsetAsync(c->counters + (size_t)s * FB_NUM_COUNTERS, 0, sizeof(int32_t) * FB_NUM_COUNTERS, c->stream));
   if (maxf == 0) return FB_OK;
   EpiArgs a;
   a.imgs = c->imgs; a.geo = c->d_geo; a.cmp_slot = c->d_cmp; a.u_ref = c->f_uref;
@@ -994,7 +1093,14 @@ extern "C" int fb_interpolate(fb_ctx* c, int s, const fb_tri_filter_params* filt
   const size_t npx = (size_t)c->W * c->H;
   const size_t vb = (size_t)s * c->maxV;
   int32_t* owner = c->owner + (size_t)s * npx;
+  // The unfiltered map is persistent state: the next fb_update reads it as the prediction for new
+  // vertices / features.  A filtered request (getFilteredInverseDepthMap) must not replace it, so it
+  // is rendered into a scratch map.
   float* map = c->idmap + (size_t)s * npx;
+  if (filter) {
+    if (!c->idmap_scratch) FB_CUDA(c, dalloc(&c->idmap_scratch, npx));
+    map = c->idmap_scratch;
+  }
   uint8_t* valid = c->tri_valid + (size_t)s * c->maxT;
   const int32_t* tri = c->tri + (size_t)s * c->maxT * 3;
   {
@@ -1036,14 +1142,26 @@ extern "C" void fb_default_update_params(fb_update_params* p) {
   p->do_nltgv2 = 1;
   p->iters = 50;
   fb_default_nltgv2_params(&p->rparams);
+  p->triangulator = 0;
 }
 
 #include "flame_update.cuh"
 
+static void update_mark_host_graph(fb_ctx* c, int s) {
+  if (c->upd) c->upd->st[s].dev_graph = false;
+}
+static bool any_device_graph(const fb_ctx* c) {
+  if (!c->upd) return false;
+  for (int s = 0; s < c->S; ++s)
+    if (c->upd->st[s].dev_graph && c->hV[s] > 0) return true;
+  return false;
+}
+
 extern "C" int fb_set_update_params(fb_ctx* c, const fb_update_params* p) {
   CHECK_CTX(c);
-  if (!p || p->detection_win_size < 4 || p->detection_win_size > 64 || p->iters < 0 || p->detection_border < 1)
-    FB_FAIL(c, FB_E_ARG, "fb_set_update_params: bad parameters (win in [4,64], border >= 1)");
+  if (!p || p->detection_win_size < 4 || p->detection_win_size > 64 || p->iters < 0 || p->detection_border < 1 ||
+      p->triangulator < 0 || p->triangulator > 1)
+    FB_FAIL(c, FB_E_ARG, "fb_set_update_params: bad parameters (win in [4,64], border >= 1, triangulator 0|1)");
   int rc = update_alloc(c);
   if (rc) return rc;
   c->upd->up = *p;
@@ -1085,6 +1203,9 @@ extern "C" int fb_get_mesh(fb_ctx* c, int s, const fb_tri_filter_params* filter,
   FB_CUDA(c, cudaMemcpyAsync(w1.data(), c->w1 + vb, sizeof(float) * V, cudaMemcpyDeviceToHost, st));
   FB_CUDA(c, cudaMemcpyAsync(w2.data(), c->w2 + vb, sizeof(float) * V, cudaMemcpyDeviceToHost, st));
   FB_CUDA(c, cudaMemcpyAsync(pos.data(), c->vpos + vb, sizeof(float2) * V, cudaMemcpyDeviceToHost, st));
+  // the mesh lives on the device (built there by fb_update, or uploaded by fb_graph_set / fb_mesh_set)
+  if (tris && T) FB_CUDA(c, cudaMemcpyAsync(tris, c->tri + (size_t)s * c->maxT * 3, sizeof(int32_t) * 3 * T, cudaMemcpyDeviceToHost, st));
+  if (edges && c->hE[s]) FB_CUDA(c, cudaMemcpyAsync(edges, c->eij + (size_t)s * c->maxE, sizeof(int32_t) * 2 * c->hE[s], cudaMemcpyDeviceToHost, st));
   if (tri_valid && T) {
     fb_tri_filter_params fp;
     fb_default_tri_filter_params(&fp);
@@ -1114,8 +1235,7 @@ extern "C" int fb_get_mesh(fb_ctx* c, int s, const fb_tri_filter_params* filter,
       normals[3 * v] = nx; normals[3 * v + 1] = ny; normals[3 * v + 2] = nz;
     }
   }
-  if (tris) std::copy(S.tris.begin(), S.tris.end(), tris);
-  if (edges) std::copy(S.edges.begin(), S.edges.end(), edges);
+  (void)S;
   return FB_OK;
 }
 
@@ -1126,6 +1246,12 @@ extern "C" int fb_get_idepthmap(fb_ctx* c, int s, const fb_tri_filter_params* fi
   if (!c->upd || !c->upd->st[s].have_graph) {
     const float qnan = nanf("");
     std::fill(out, out + (size_t)c->W * c->H, qnan);
+    return FB_OK;
+  }
+  if (!filter) {  // rendered by the last fb_update; no need to rasterise again
+    const size_t npx = (size_t)c->W * c->H;
+    FB_CUDA(c, cudaMemcpyAsync(out, c->idmap + (size_t)s * npx, sizeof(float) * npx, cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
     return FB_OK;
   }
   return fb_interpolate(c, s, filter, out, nullptr);
@@ -1220,6 +1346,59 @@ extern "C" int fb_get_feature_pool(fb_ctx* c, int s, float* u_ref, int32_t* ref_
   if (alive) FB_CUDA(c, cudaMemcpyAsync(alive, c->f_alive + fb, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
   FB_CUDA(c, cudaStreamSynchronize(st));
   return FB_OK;
+}
+
+// Device triangulation of an arbitrary point set through the update pipeline's kernels
+// (k_ds_prepare .. k_ds_emit): the points stand in for the projected features of `stream`.
+extern "C" int fb_delaunay_device(fb_ctx* c, int s, int n, const float* pts, int32_t* tris, int32_t* n_tris,
+                                  int32_t* edges, int32_t* n_edges) {
+  CHECK_CTX(c);
+  CHECK_STREAM(c, s);
+  if (n < 0 || (n > 0 && !pts) || !tris || !n_tris || !edges || !n_edges) FB_FAIL(c, FB_E_ARG, "fb_delaunay_device: bad argument");
+  if (n > c->maxF || n > c->maxV) FB_FAIL(c, FB_E_NOMEM, "fb_delaunay_device: n exceeds max_features / max_vertices");
+  int rc = update_alloc(c);
+  if (rc) return rc;
+  UpdateState* U = c->upd;
+  DelGpu& D = U->del;
+  const size_t fb = (size_t)s * c->maxF, vb = (size_t)s * c->maxV, eb = (size_t)s * c->maxE;
+  cudaStream_t st = c->stream;
+  *n_tris = *n_edges = 0;
+  std::vector<int32_t> valid(c->maxF, 0);
+  std::fill(valid.begin(), valid.begin() + n, 1);
+  FB_CUDA(c, cudaMemcpyAsync(U->f_valid + fb, valid.data(), sizeof(int32_t) * c->maxF, cudaMemcpyHostToDevice, st));
+  if (n) FB_CUDA(c, cudaMemcpyAsync(U->f_ucur + fb, pts, sizeof(float2) * n, cudaMemcpyHostToDevice, st));
+  FB_CUDA(c, cudaMemsetAsync(U->f_varcur + fb, 0, sizeof(float) * c->maxF, st));
+  DsgSelect q{U->f_ucur + fb, U->f_varcur + fb, U->f_valid + fb, 1.0f, c->maxF, c->maxV, c->W, c->H};
+  k_ds_prepare<<<1, DSG_THREADS, 0, st>>>(q, D, s, c->vfeat + vb, c->vpos + vb, D.f2v + fb, c->nV + s);
+  k_ds_stars<<<fb_div_up(c->maxV, DSG_WARPS), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
+  k_ds_scan<<<1, DSG_THREADS, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->row + (size_t)s * (c->maxV + 1), c->nE + s, c->nT + s);
+  k_ds_emit<<<fb_div_up(c->maxV, 128), 128, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->vpos + vb, c->eij + eb, c->ec + eb,
+                                                    c->tri + (size_t)s * c->maxT * 3);
+  c->launches += 4;
+  FB_CUDA(c, cudaGetLastError());
+  int32_t meta[DSG_META];
+  FB_CUDA(c, cudaMemcpyAsync(meta, D.meta + (size_t)s * DSG_META, sizeof(meta), cudaMemcpyDeviceToHost, st));
+  FB_CUDA(c, cudaStreamSynchronize(st));
+  // this entry point leaves no usable graph behind
+  c->hV[s] = c->hE[s] = c->hT[s] = 0;
+  int32_t zero[DSG_META] = {0};
+  FB_CUDA(c, cudaMemcpyAsync(D.meta + (size_t)s * DSG_META, zero, sizeof(zero), cudaMemcpyHostToDevice, st));
+  FB_CUDA(c, cudaMemsetAsync(c->nV + s, 0, sizeof(int32_t), st));
+  FB_CUDA(c, cudaMemsetAsync(c->nE + s, 0, sizeof(int32_t), st));
+  FB_CUDA(c, cudaMemsetAsync(c->nT + s, 0, sizeof(int32_t), st));
+  if (meta[DSG_ERR]) {
+    char msg[96];
+    snprintf(msg, sizeof(msg), "fb_delaunay_device: failed (flags 0x%x)", meta[DSG_ERR]);
+    FB_CUDA(c, cudaStreamSynchronize(st));
+    FB_FAIL(c, FB_E_STATE, msg);
+  }
+  const int T = meta[DSG_NT], E = meta[DSG_NE];
+  if (T) FB_CUDA(c, cudaMemcpyAsync(tris, c->tri + (size_t)s * c->maxT * 3, sizeof(int32_t) * 3 * T, cudaMemcpyDeviceToHost, st));
+  if (E) FB_CUDA(c, cudaMemcpyAsync(edges, c->eij + eb, sizeof(int32_t) * 2 * E, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(c, cudaStreamSynchronize(st));
+  *n_tris = T;
+  *n_edges = E;
+  return T > 0 ? FB_OK : FB_E_ARG;  // degenerate input: same contract as fb_delaunay
 }
 
 // ------------------------------------------------------------------------------------ frame creation / detection

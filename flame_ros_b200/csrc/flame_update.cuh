@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "delaunay.h"
+#include "delaunay_gpu.cuh"
 #include "epipolar.cuh"
 #include "frontend.cuh"
 #include "nltgv2.cuh"
@@ -34,6 +35,8 @@ struct UpdateStream {
   std::vector<int32_t> edges;      // 2E
   std::vector<int32_t> tris;       // 3T
   bool have_graph = false;
+  bool dev_graph = false;          // the current graph was built on the device (delaunay_gpu.cuh)
+  int64_t builds = 0;              // device graph builds so far (parity of the f2v tables)
   // stats of the last update (names follow msg/FlameStats.msg)
   std::unordered_map<std::string, double> stats;
 };
@@ -65,14 +68,24 @@ struct UpdateState {
   int32_t* map_e = nullptr;      // [maxE] new edge -> old edge or -1
   int maxCells = 0;
   fb_update_params up;
+  std::vector<int32_t> cmp_scratch;
+  DelGpu del;                    // device-side sync_graph + triangulate (delaunay_gpu.cuh)
+  int32_t* misc = nullptr;       // [S*4] device: covered pixels, live projected features, 0, 0
+  int32_t* h_read = nullptr;     // pinned [S*(DSG_META+4)]: per-frame readback of meta + misc
 };
 
 // ------------------------------------------------------------------------------------ kernels
 // alive features that project outside the current frame leave the pool
 __global__ void __launch_bounds__(256)
-k_kill_invalid(int N, int32_t* __restrict__ alive, const int32_t* __restrict__ valid) {
+k_kill_invalid(int N, int32_t* __restrict__ alive, const int32_t* __restrict__ valid,
+               int32_t* __restrict__ n_valid = nullptr) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f < N && alive[f] && !valid[f]) alive[f] = 0;
+  const bool v = f < N && valid[f];
+  if (f < N && alive[f] && !v) alive[f] = 0;
+  if (n_valid) {  // `num_feats` stat (/root/reference/src/utils.cc:117)
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, __popc(m));
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -152,10 +165,13 @@ k_spawn_features(const int32_t* __restrict__ counts, const int32_t* __restrict__
                  const int32_t* __restrict__ free_list, const float2* __restrict__ det_xy,
                  const float* __restrict__ idmap, int W, int H, int ref, float mu0, float var0,
                  int use_prediction, float2* u_ref, int32_t* ref_slot, float* mu, float* var,
-                 int32_t* dropouts, int32_t* alive, int32_t* status) {
+                 int32_t* dropouts, int32_t* alive, int32_t* status, int have_host = 1,
+                 const int32_t* __restrict__ have_dev = nullptr) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = min(counts[0], counts[1]);
   if (k >= n) return;
+  // a dense prediction exists when an earlier frame produced one (host flag) or this frame did
+  if (!(have_host || (have_dev && *have_dev > 0))) idmap = nullptr;
   const int f = free_list[k];
   const float2 p = det_xy[det_list[k]];
   float m = mu0;
@@ -179,7 +195,7 @@ static int update_alloc(fb_ctx* c) {
   c->upd = U;
   U->st.resize(c->S);
   for (auto& s : U->st) s.pf_img_id.assign(c->n_slots - 1, -1);
-  const size_t nf = (size_t)c->S * c->maxF;
+  const size_t S = c->S, nf = S * c->maxF, nv = S * c->maxV, ne = S * c->maxE;
   U->maxCells = (c->W / 4) * (c->H / 4);  // detection win >= 4
   bool ok = true;
   auto A = [&](cudaError_t r) { ok = ok && r == cudaSuccess; };
@@ -191,7 +207,21 @@ static int update_alloc(fb_ctx* c) {
   A(dalloc(&U->o_x, c->maxV)); A(dalloc(&U->o_w1, c->maxV)); A(dalloc(&U->o_w2, c->maxV));
   A(dalloc(&U->o_vbar, c->maxV)); A(dalloc(&U->o_q4, c->maxE));
   A(dalloc(&U->map_v, c->maxV)); A(dalloc(&U->map_e, c->maxE));
+  DelGpu& D = U->del;
+  A(dalloc(&D.vxy, nv)); A(dalloc(&D.sxy, nv)); A(dalloc(&D.sid, nv));
+  A(dalloc(&D.cell_start, S * (DSG_MAXCELLS + 1))); A(dalloc(&D.star, nv * DS_MAXD));
+  A(dalloc(&D.deg, nv)); A(dalloc(&D.od, nv)); A(dalloc(&D.tc, nv));
+  A(dalloc(&D.eoff, S * (c->maxV + 1))); A(dalloc(&D.toff, S * (c->maxV + 1)));
+  A(dalloc(&D.meta, S * DSG_META)); A(dalloc(&D.f2v, 2 * nf));
+  A(dalloc(&D.o_x, nv)); A(dalloc(&D.o_w1, nv)); A(dalloc(&D.o_w2, nv)); A(dalloc(&D.o_vbar, nv));
+  A(dalloc(&D.o_q4, ne)); A(dalloc(&D.o_eij, ne)); A(dalloc(&D.o_eoff, S * (c->maxV + 1)));
+  A(dalloc(&U->misc, S * 4));
+  A(cudaMallocHost((void**)&U->h_read, sizeof(int32_t) * S * (DSG_META + 4)));
   if (!ok) FB_FAIL(c, FB_E_NOMEM, "fb_update: scratch allocation failed");
+  FB_CUDA(c, cudaMemsetAsync(D.meta, 0, sizeof(int32_t) * S * DSG_META, c->stream));
+  FB_CUDA(c, cudaMemsetAsync(D.eoff, 0, sizeof(int32_t) * S * (c->maxV + 1), c->stream));
+  FB_CUDA(c, cudaMemsetAsync(D.f2v, 0xff, sizeof(int32_t) * 2 * nf, c->stream));
+  FB_CUDA(c, cudaMemsetAsync(U->misc, 0, sizeof(int32_t) * S * 4, c->stream));
   // the feature pool is a fixed set of maxF slots: mark them all dead
   FB_CUDA(c, cudaMemsetAsync(c->f_alive, 0, sizeof(int32_t) * nf, c->stream));
   FB_CUDA(c, cudaMemsetAsync(c->f_status, 0, sizeof(int32_t) * nf, c->stream));
@@ -210,6 +240,13 @@ static void update_free(fb_ctx* c) {
   cudaFree(U->det_list); cudaFree(U->free_flag); cudaFree(U->free_rank); cudaFree(U->free_list);
   cudaFree(U->counts); cudaFree(U->o_x); cudaFree(U->o_w1); cudaFree(U->o_w2); cudaFree(U->o_vbar);
   cudaFree(U->o_q4); cudaFree(U->map_v); cudaFree(U->map_e);
+  DelGpu& D = U->del;
+  cudaFree(D.vxy); cudaFree(D.sxy); cudaFree(D.sid); cudaFree(D.cell_start); cudaFree(D.star);
+  cudaFree(D.deg); cudaFree(D.od); cudaFree(D.tc); cudaFree(D.eoff); cudaFree(D.toff); cudaFree(D.meta);
+  cudaFree(D.f2v); cudaFree(D.o_x); cudaFree(D.o_w1); cudaFree(D.o_w2); cudaFree(D.o_vbar);
+  cudaFree(D.o_q4); cudaFree(D.o_eij); cudaFree(D.o_eoff);
+  cudaFree(U->misc);
+  if (U->h_read) cudaFreeHost(U->h_read);
   delete U;
   c->upd = nullptr;
 }
@@ -243,11 +280,14 @@ static int update_detect(fb_ctx* c, int s, int img_slot, int ref) {
   k_free_flags<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(c->maxF, c->f_alive + fb, U->free_flag);
   k_scan_flags<<<1, 1024, 0, st>>>(c->maxF, U->free_flag, U->free_rank, U->counts + 1);
   k_scatter_ranked<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(c->maxF, U->free_flag, U->free_rank, U->free_list);
-  const float* idmap = U->st[s].have_graph ? c->idmap + (size_t)s * npx : nullptr;
+  // the dense prediction: present when an earlier frame produced a map (host flag), or -- device
+  // path, where this frame's outcome is not known on the host yet -- when this frame did
+  UpdateStream& S = U->st[s];
+  const int32_t* have_dev = S.dev_graph ? U->del.meta + (size_t)s * DSG_META + DSG_NT : nullptr;
   k_spawn_features<<<fb_div_up(std::min(cells, c->maxF), 256), 256, 0, st>>>(
-      U->counts, U->det_list, U->free_list, U->det_xy, idmap, c->W, c->H, ref, p.idepth_init, p.idepth_var_init,
-      p.init_with_prediction, c->f_uref + fb, c->f_ref + fb, c->f_mu + fb, c->f_var + fb, c->f_drop + fb,
-      c->f_alive + fb, c->f_status + fb);
+      U->counts, U->det_list, U->free_list, U->det_xy, c->idmap + (size_t)s * npx, c->W, c->H, ref, p.idepth_init,
+      p.idepth_var_init, p.init_with_prediction, c->f_uref + fb, c->f_ref + fb, c->f_mu + fb, c->f_var + fb,
+      c->f_drop + fb, c->f_alive + fb, c->f_status + fb, S.have_graph ? 1 : 0, have_dev);
   c->launches += 8;
   FB_CUDA(c, cudaGetLastError());
   return FB_OK;
@@ -273,6 +313,165 @@ static int update_new_poseframe(fb_ctx* c, int s, int img_id) {
   return update_detect(c, s, cur, slot);
 }
 
+// Unfiltered dense map of the stream's current mesh into c->idmap (kept on the device: it is the
+// prediction source of the next frames).  Tdev != NULL: the triangle count lives on the device.
+static int update_interpolate(fb_ctx* c, int s, const int32_t* Tdev, int32_t* covered) {
+  const int T = Tdev ? c->maxT : c->hT[s];
+  const size_t npx = (size_t)c->W * c->H, vb = (size_t)s * c->maxV;
+  int32_t* owner = c->owner + (size_t)s * npx;
+  uint8_t* valid = c->tri_valid + (size_t)s * c->maxT;
+  const int32_t* tri = c->tri + (size_t)s * c->maxT * 3;
+  cudaStream_t st = c->stream;
+  ProfScope ps(c, FB_PROF_INTERP);
+  FB_CUDA(c, cudaMemsetAsync(owner, 0x7f, sizeof(int32_t) * npx, st));
+  if (covered) FB_CUDA(c, cudaMemsetAsync(covered, 0, sizeof(int32_t), st));
+  if (T) {
+    fb_tri_filter_params fp;
+    fb_default_tri_filter_params(&fp);
+    k_tri_validity<<<fb_div_up(T, 256), 256, 0, st>>>(c->W, c->d_K + 9 * s, c->vpos + vb, c->x + vb, T, tri, fp, 0.f, 0, valid, Tdev);
+    k_raster_claim<<<fb_div_up(T * 32, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, T, tri, valid, owner, Tdev);
+    c->launches += 2;
+  }
+  k_raster_shade<<<fb_div_up((int)npx, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, c->x + vb, tri, owner, c->idmap + (size_t)s * npx, Tdev, covered);
+  c->launches++;
+  FB_CUDA(c, cudaGetLastError());
+  return FB_OK;
+}
+
+// sync_graph + triangulate on the device (delaunay_gpu.cuh): six launches, no host involvement.
+static int update_graph_device(fb_ctx* c, int s) {
+  UpdateState* U = c->upd;
+  UpdateStream& S = U->st[s];
+  const fb_update_params& p = U->up;
+  DelGpu& D = U->del;
+  const size_t fb = (size_t)s * c->maxF, vb = (size_t)s * c->maxV, eb = (size_t)s * c->maxE;
+  const size_t npx = (size_t)c->W * c->H, nf = (size_t)c->S * c->maxF;
+  cudaStream_t st = c->stream;
+  const int par = (int)(S.builds & 1);
+  DsgGraph gg{c->x, c->w1, c->w2, c->vbar, c->q4, c->eij};
+  k_ds_stash<<<64, 256, 0, st>>>(gg, D, s, c->maxV, c->maxE);
+  DsgSelect q{U->f_ucur + fb, U->f_varcur + fb, U->f_valid + fb, p.idepth_var_max_graph, c->maxF, c->maxV, c->W, c->H};
+  k_ds_prepare<<<1, DSG_THREADS, 0, st>>>(q, D, s, c->vfeat + vb, c->vpos + vb, D.f2v + par * nf + fb, c->nV + s);
+  k_ds_stars<<<fb_div_up(c->maxV, DSG_WARPS), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
+  k_ds_scan<<<1, DSG_THREADS, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->row + (size_t)s * (c->maxV + 1), c->nE + s, c->nT + s);
+  k_ds_emit<<<fb_div_up(c->maxV, 128), 128, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->vpos + vb, c->eij + eb, c->ec + eb,
+                                                    c->tri + (size_t)s * c->maxT * 3);
+  DsgCarry cq{U->f_mucur + fb, U->f_varcur + fb, D.f2v + (1 - par) * nf + fb,
+              S.have_graph ? c->idmap + (size_t)s * npx : nullptr, c->W, c->H, p.adaptive_data_weights, p.init_with_prediction};
+  k_ds_csr<<<fb_div_up(c->maxV, 128), 128, 0, st>>>(D, cq, s, c->maxV, c->maxE, c->vfeat + vb, c->vpos + vb, c->eij + eb,
+                                                   c->row + (size_t)s * (c->maxV + 1), c->inc + 2 * eb, c->z + vb, c->wt + vb,
+                                                   c->x + vb, c->w1 + vb, c->w2 + vb, c->vbar + vb, c->q4 + eb);
+  c->launches += 6;
+  FB_CUDA(c, cudaGetLastError());
+  S.builds++;
+  S.dev_graph = true;
+  // per-topology tables of the resident solvers (variants 2 / 3) do not describe this graph
+  if (c->plan && s < (int)c->plan->topo.size()) { c->plan->topo[s].V = 0; c->plan->topo[s].dirty = true; }
+  if (c->gplan) { c->gplan->topo[s].dirty = true; c->gplan->topo[s].planned = 0; c->gplan->version++; }
+  return FB_OK;
+}
+
+// sync_graph + triangulate on the host (delaunay.h) -- the reference path the device one is tested
+// against; selected with fb_update_params::triangulator = 1.  Returns 1 when a graph was built.
+static int update_graph_host(fb_ctx* c, int s) {
+  UpdateState* U = c->upd;
+  UpdateStream& S = U->st[s];
+  const fb_update_params& p = U->up;
+  const size_t fb = (size_t)s * c->maxF, vb = (size_t)s * c->maxV, eb = (size_t)s * c->maxE;
+  const size_t npx = (size_t)c->W * c->H;
+  cudaStream_t st = c->stream;
+  int rc;
+  std::vector<float2> h_u(c->maxF);
+  std::vector<float> h_var(c->maxF);
+  std::vector<int32_t> h_valid(c->maxF);
+  {
+    StageTimer t(S.stats, "project_features");
+    FB_CUDA(c, cudaMemcpyAsync(h_u.data(), U->f_ucur + fb, sizeof(float2) * c->maxF, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(c, cudaMemcpyAsync(h_var.data(), U->f_varcur + fb, sizeof(float) * c->maxF, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(c, cudaMemcpyAsync(h_valid.data(), U->f_valid + fb, sizeof(int32_t) * c->maxF, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(c, cudaStreamSynchronize(st));
+  }
+  std::vector<int32_t> vfeat;
+  std::vector<float> pos;
+  int n_valid = 0;
+  for (int f = 0; f < c->maxF; ++f) {
+    n_valid += h_valid[f] ? 1 : 0;
+    if (h_valid[f] && h_var[f] < p.idepth_var_max_graph && (int)vfeat.size() < c->maxV) {  // valid implies alive
+      vfeat.push_back(f);
+      pos.push_back(h_u[f].x);
+      pos.push_back(h_u[f].y);
+    }
+  }
+  S.stats["num_feats"] = n_valid;
+  const int V = (int)vfeat.size();
+  S.stats["num_vtx"] = V;
+  std::vector<int> tris, edges;
+  bool have_tri = false;
+  if (V >= 3) {
+    StageTimer t(S.stats, "triangulate");
+    if ((int)U->tri.size() < c->S) U->tri.resize(c->S);
+    have_tri = U->tri[s].run(V, pos.data(), tris, edges);
+    if ((int)edges.size() / 2 > c->maxE || (int)tris.size() / 3 > c->maxT) have_tri = false;
+    if (tris.empty()) have_tri = false;
+  }
+  if (!have_tri) return 0;
+  const int E = (int)edges.size() / 2;
+  StageTimer t(S.stats, "sync_graph");
+  // maps new -> old for the state carry-over
+  std::vector<int32_t> map_v(V, -1), map_e(E, -1);
+  if (S.have_graph) {
+    std::vector<int32_t> f2v(c->maxF, -1);
+    for (size_t k = 0; k < S.vert_feat.size(); ++k) f2v[S.vert_feat[k]] = (int32_t)k;
+    for (int k = 0; k < V; ++k) map_v[k] = f2v[vfeat[k]];
+    // vertices are listed in ascending feature index in both graphs, so both canonical edge
+    // lists are sorted by (feature_i, feature_j): one linear merge matches the persisting edges
+    const size_t oEn = S.edges.size() / 2;
+    size_t o = 0;
+    for (int e = 0; e < E; ++e) {
+      const uint64_t key = ((uint64_t)vfeat[edges[2 * e]] << 32) | (uint32_t)vfeat[edges[2 * e + 1]];
+      while (o < oEn && (((uint64_t)S.vert_feat[S.edges[2 * o]] << 32) | (uint32_t)S.vert_feat[S.edges[2 * o + 1]]) < key) ++o;
+      if (o < oEn && (((uint64_t)S.vert_feat[S.edges[2 * o]] << 32) | (uint32_t)S.vert_feat[S.edges[2 * o + 1]]) == key)
+        map_e[e] = (int32_t)o;
+    }
+    // stash the old state (device to device)
+    const int oV = (int)S.vert_feat.size(), oE = (int)S.edges.size() / 2;
+    FB_CUDA(c, cudaMemcpyAsync(U->o_x, c->x + vb, sizeof(float) * oV, cudaMemcpyDeviceToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(U->o_w1, c->w1 + vb, sizeof(float) * oV, cudaMemcpyDeviceToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(U->o_w2, c->w2 + vb, sizeof(float) * oV, cudaMemcpyDeviceToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(U->o_vbar, c->vbar + vb, sizeof(float4) * oV, cudaMemcpyDeviceToDevice, st));
+    if (oE) FB_CUDA(c, cudaMemcpyAsync(U->o_q4, c->q4 + eb, sizeof(float4) * oE, cudaMemcpyDeviceToDevice, st));
+  }
+  // edge weights: alpha = 1/|delta| in pixels, beta = 1
+  std::vector<float> alpha(E), beta(E, 1.0f);
+  for (int e = 0; e < E; ++e) {
+    const float dx = pos[2 * edges[2 * e]] - pos[2 * edges[2 * e + 1]];
+    const float dy = pos[2 * edges[2 * e] + 1] - pos[2 * edges[2 * e + 1] + 1];
+    alpha[e] = 1.0f / sqrtf(dx * dx + dy * dy);
+  }
+  rc = fb_graph_set(c, s, V, E, pos.data(), edges.data(), alpha.data(), beta.data());
+  if (rc) return rc;
+  FB_CUDA(c, cudaMemcpyAsync(c->vfeat + vb, vfeat.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, st));
+  FB_CUDA(c, cudaMemcpyAsync(U->map_v, map_v.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, st));
+  if (E) FB_CUDA(c, cudaMemcpyAsync(U->map_e, map_e.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, st));
+  k_data_from_projection<<<fb_div_up(V, 256), 256, 0, st>>>(V, c->z + vb, c->wt + vb, c->vfeat + vb, U->f_mucur + fb, U->f_varcur + fb, p.adaptive_data_weights);
+  const float* idmap = S.have_graph ? c->idmap + (size_t)s * npx : nullptr;
+  k_remap_state<<<fb_div_up(std::max(V, E), 256), 256, 0, st>>>(
+      V, E, U->map_v, U->map_e, U->o_x, U->o_w1, U->o_w2, U->o_vbar, U->o_q4, c->z + vb, c->vpos + vb, idmap,
+      c->W, c->H, p.init_with_prediction, c->x + vb, c->w1 + vb, c->w2 + vb, c->vbar + vb, c->q4 + eb);
+  c->launches += 2;
+  FB_CUDA(c, cudaGetLastError());
+  FB_CUDA(c, cudaStreamSynchronize(st));  // the pageable staging vectors above go out of scope
+  S.vert_feat.assign(vfeat.begin(), vfeat.end());
+  S.edges.assign(edges.begin(), edges.end());
+  S.tris.assign(tris.begin(), tris.end());
+  S.dev_graph = false;
+  rc = fb_mesh_set(c, s, (int)S.tris.size() / 3, S.tris.data());
+  if (rc) return rc;
+  S.stats["num_edges"] = E;
+  S.stats["num_tris"] = (double)S.tris.size() / 3;
+  return 1;
+}
+
 static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const float pose[7],
                           const uint8_t* gray, int pitch, int is_poseframe) {
   int rc = update_alloc(c);
@@ -281,9 +480,10 @@ static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const f
   UpdateStream& S = U->st[s];
   const fb_update_params& p = U->up;
   const int cur = c->n_slots - 1;
-  const size_t fb = (size_t)s * c->maxF, vb = (size_t)s * c->maxV, eb = (size_t)s * c->maxE;
+  const size_t fb = (size_t)s * c->maxF;
   const size_t npx = (size_t)c->W * c->H;
   cudaStream_t st = c->stream;
+  const bool dev = p.triangulator == 0;
   S.stats.clear();
   StageTimer t_all(S.stats, "update");
   {
@@ -303,124 +503,98 @@ static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const f
   }
 
   // ---- update_idepths + project_features (device) -------------------------------------------
-  std::vector<int32_t> cmp(c->S, -1);
-  cmp[s] = cur;
+  int32_t* misc = U->misc + 4 * s;
   {
     StageTimer t(S.stats, "update_idepths");
+    std::vector<int32_t>& cmp = U->cmp_scratch;
+    cmp.assign(c->S, -1);
+    cmp[s] = cur;
     rc = fb_idepth_update(c, cmp.data());  // also refreshes the geometry table against `cur`
     if (rc) return rc;
+    FB_CUDA(c, cudaMemsetAsync(misc, 0, sizeof(int32_t) * 4, st));
     k_project_features<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(
         c->d_geo, c->n_slots, s, c->maxF, c->W, c->H, c->f_uref + fb, c->f_ref + fb, c->f_mu + fb, c->f_var + fb,
         c->f_alive + fb, U->f_ucur + fb, U->f_mucur + fb, U->f_varcur + fb, U->f_valid + fb);
-    k_kill_invalid<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(c->maxF, c->f_alive + fb, U->f_valid + fb);
+    k_kill_invalid<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(c->maxF, c->f_alive + fb, U->f_valid + fb, misc + 1);
     c->launches += 2;
   }
-  // ---- sync_graph: one small D2H, host bookkeeping + Delaunay --------------------------------
-  std::vector<float2> h_u(c->maxF);
-  std::vector<float> h_var(c->maxF);
-  std::vector<int32_t> h_valid(c->maxF);
-  {
-    StageTimer t(S.stats, "project_features");
-    FB_CUDA(c, cudaMemcpyAsync(h_u.data(), U->f_ucur + fb, sizeof(float2) * c->maxF, cudaMemcpyDeviceToHost, st));
-    FB_CUDA(c, cudaMemcpyAsync(h_var.data(), U->f_varcur + fb, sizeof(float) * c->maxF, cudaMemcpyDeviceToHost, st));
-    FB_CUDA(c, cudaMemcpyAsync(h_valid.data(), U->f_valid + fb, sizeof(int32_t) * c->maxF, cudaMemcpyDeviceToHost, st));
-    FB_CUDA(c, cudaStreamSynchronize(st));
-  }
-  std::vector<int32_t> vfeat;
-  std::vector<float> pos;
-  for (int f = 0; f < c->maxF; ++f)
-    if (h_valid[f] && h_var[f] < p.idepth_var_max_graph) {  // valid implies alive
-      if ((int)vfeat.size() >= c->maxV) break;
-      vfeat.push_back(f);
-      pos.push_back(h_u[f].x);
-      pos.push_back(h_u[f].y);
-    }
   int updated = 0;
-  const int V = (int)vfeat.size();
-  std::vector<int> tris, edges;
-  bool have_tri = false;
-  if (V >= 3) {
-    StageTimer t(S.stats, "triangulate");
-    if ((int)U->tri.size() < c->S) U->tri.resize(c->S);
-    have_tri = U->tri[s].run(V, pos.data(), tris, edges);
-    if ((int)edges.size() / 2 > c->maxE || (int)tris.size() / 3 > c->maxT) have_tri = false;
-  }
-  if (have_tri) {
-    const int E = (int)edges.size() / 2;
+  if (dev) {
+    // ---- device path: the whole frame is enqueued; ONE synchronisation at the end --------------
     {
       StageTimer t(S.stats, "sync_graph");
-      // maps new -> old for the state carry-over
-      std::vector<int32_t> map_v(V, -1), map_e(E, -1);
-      if (S.have_graph) {
-        std::vector<int32_t> f2v(c->maxF, -1);
-        for (size_t k = 0; k < S.vert_feat.size(); ++k) f2v[S.vert_feat[k]] = (int32_t)k;
-        for (int k = 0; k < V; ++k) map_v[k] = f2v[vfeat[k]];
-        // vertices are listed in ascending feature index in both graphs, so both canonical edge
-        // lists are sorted by (feature_i, feature_j): one linear merge matches the persisting edges
-        const size_t oEn = S.edges.size() / 2;
-        size_t o = 0;
-        for (int e = 0; e < E; ++e) {
-          const uint64_t key = ((uint64_t)vfeat[edges[2 * e]] << 32) | (uint32_t)vfeat[edges[2 * e + 1]];
-          while (o < oEn && (((uint64_t)S.vert_feat[S.edges[2 * o]] << 32) | (uint32_t)S.vert_feat[S.edges[2 * o + 1]]) < key) ++o;
-          if (o < oEn && (((uint64_t)S.vert_feat[S.edges[2 * o]] << 32) | (uint32_t)S.vert_feat[S.edges[2 * o + 1]]) == key)
-            map_e[e] = (int32_t)o;
-        }
-        // stash the old state (device to device)
-        const int oV = (int)S.vert_feat.size(), oE = (int)S.edges.size() / 2;
-        FB_CUDA(c, cudaMemcpyAsync(U->o_x, c->x + vb, sizeof(float) * oV, cudaMemcpyDeviceToDevice, st));
-        FB_CUDA(c, cudaMemcpyAsync(U->o_w1, c->w1 + vb, sizeof(float) * oV, cudaMemcpyDeviceToDevice, st));
-        FB_CUDA(c, cudaMemcpyAsync(U->o_w2, c->w2 + vb, sizeof(float) * oV, cudaMemcpyDeviceToDevice, st));
-        FB_CUDA(c, cudaMemcpyAsync(U->o_vbar, c->vbar + vb, sizeof(float4) * oV, cudaMemcpyDeviceToDevice, st));
-        if (oE) FB_CUDA(c, cudaMemcpyAsync(U->o_q4, c->q4 + eb, sizeof(float4) * oE, cudaMemcpyDeviceToDevice, st));
-      }
-      // edge weights: alpha = 1/|delta| in pixels, beta = 1
-      std::vector<float> alpha(E), beta(E, 1.0f);
-      for (int e = 0; e < E; ++e) {
-        const float dx = pos[2 * edges[2 * e]] - pos[2 * edges[2 * e + 1]];
-        const float dy = pos[2 * edges[2 * e] + 1] - pos[2 * edges[2 * e + 1] + 1];
-        alpha[e] = 1.0f / sqrtf(dx * dx + dy * dy);
-      }
-      rc = fb_graph_set(c, s, V, E, pos.data(), edges.data(), alpha.data(), beta.data());
+      rc = update_graph_device(c, s);
       if (rc) return rc;
-      FB_CUDA(c, cudaMemcpyAsync(c->vfeat + vb, vfeat.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, st));
-      FB_CUDA(c, cudaMemcpyAsync(U->map_v, map_v.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, st));
-      if (E) FB_CUDA(c, cudaMemcpyAsync(U->map_e, map_e.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, st));
-      k_data_from_projection<<<fb_div_up(V, 256), 256, 0, st>>>(V, c->z + vb, c->wt + vb, c->vfeat + vb, U->f_mucur + fb, U->f_varcur + fb, p.adaptive_data_weights);
-      const float* idmap = S.have_graph ? c->idmap + (size_t)s * npx : nullptr;
-      k_remap_state<<<fb_div_up(std::max(V, E), 256), 256, 0, st>>>(
-          V, E, U->map_v, U->map_e, U->o_x, U->o_w1, U->o_w2, U->o_vbar, U->o_q4, c->z + vb, c->vpos + vb, idmap,
-          c->W, c->H, p.init_with_prediction, c->x + vb, c->w1 + vb, c->w2 + vb, c->vbar + vb, c->q4 + eb);
-      c->launches += 2;
-      FB_CUDA(c, cudaGetLastError());
-      FB_CUDA(c, cudaStreamSynchronize(st));  // the pageable staging vectors above go out of scope
-      S.vert_feat.assign(vfeat.begin(), vfeat.end());
-      S.edges.assign(edges.begin(), edges.end());
-      S.tris.assign(tris.begin(), tris.end());
-      S.have_graph = true;
     }
     if (p.do_nltgv2 && p.iters > 0) {
       StageTimer t(S.stats, "nltgv2");
-      // solve only this stream's graph: other streams of the context keep their own cadence
       rc = fb_nltgv2_solve_stream(c, s, p.iters, &p.rparams);
       if (rc) return rc;
     }
     {
       StageTimer t(S.stats, "interpolate");
-      rc = fb_mesh_set(c, s, (int)S.tris.size() / 3, S.tris.data());
-      if (rc) return rc;
-      rc = fb_interpolate(c, s, nullptr, nullptr, nullptr);  // unfiltered map stays on the device
+      rc = update_interpolate(c, s, c->nT + s, misc);
       if (rc) return rc;
     }
-    updated = 1;
+    if (is_poseframe) {
+      StageTimer t(S.stats, "detection");
+      rc = update_new_poseframe(c, s, img_id);
+      if (rc) return rc;
+    }
+    int32_t* h = U->h_read + (size_t)s * (DSG_META + 4);
+    FB_CUDA(c, cudaMemcpyAsync(h, U->del.meta + (size_t)s * DSG_META, sizeof(int32_t) * DSG_META, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(c, cudaMemcpyAsync(h + DSG_META, misc, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(c, cudaStreamSynchronize(st));
+    if (fb_coop_failed(c)) FB_FAIL(c, FB_E_STATE, "fb_update: resident solver rejected the graph size");
+    const int err = h[DSG_ERR];
+    c->hV[s] = h[DSG_NV];
+    c->hE[s] = h[DSG_NE];
+    c->hT[s] = h[DSG_NT];
+    if (err) {
+      char msg[96];
+      snprintf(msg, sizeof(msg), "fb_update: device triangulation failed (flags 0x%x); set triangulator = 1", err);
+      FB_FAIL(c, FB_E_STATE, msg);
+    }
+    updated = h[DSG_NT] > 0 ? 1 : 0;
+    if (updated) S.have_graph = true;
+    S.stats["num_feats"] = h[DSG_META + 1];
+    S.stats["num_vtx"] = h[DSG_NV];
+    S.stats["num_edges"] = h[DSG_NE];
+    S.stats["num_tris"] = h[DSG_NT];
+    S.stats["coverage"] = (double)h[DSG_META] / (double)npx;
+  } else {
+    // ---- host path: D2H of the projected features, host Delaunay, upload --------------------
+    rc = update_graph_host(c, s);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      S.have_graph = true;
+      if (p.do_nltgv2 && p.iters > 0) {
+        StageTimer t(S.stats, "nltgv2");
+        // solve only this stream's graph: other streams of the context keep their own cadence
+        rc = fb_nltgv2_solve_stream(c, s, p.iters, &p.rparams);
+        if (rc) return rc;
+      }
+      {
+        StageTimer t(S.stats, "interpolate");
+        rc = update_interpolate(c, s, nullptr, misc);
+        if (rc) return rc;
+      }
+      updated = 1;
+    }
+    if (is_poseframe) {
+      StageTimer t(S.stats, "detection");
+      rc = update_new_poseframe(c, s, img_id);
+      if (rc) return rc;
+    }
+    int32_t* h = U->h_read + (size_t)s * (DSG_META + 4);
+    FB_CUDA(c, cudaMemcpyAsync(h + DSG_META, misc, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(c, cudaStreamSynchronize(st));
+    if (updated) S.stats["coverage"] = (double)h[DSG_META] / (double)npx;
+    if (!S.stats.count("num_edges")) { S.stats["num_edges"] = 0.0; S.stats["num_tris"] = 0.0; }
   }
-  if (is_poseframe) {
-    StageTimer t(S.stats, "detection");
-    rc = update_new_poseframe(c, s, img_id);
-    if (rc) return rc;
-  }
-  FB_CUDA(c, cudaStreamSynchronize(st));
-  S.stats["num_vertices"] = V;
-  S.stats["num_edges"] = have_tri ? (double)edges.size() / 2 : 0.0;
-  S.stats["num_triangles"] = have_tri ? (double)tris.size() / 3 : 0.0;
+  // aliases of round 1 (kept for callers of fb_get_stat)
+  S.stats["num_vertices"] = S.stats["num_vtx"];
+  S.stats["num_triangles"] = S.stats["num_tris"];
+  if (is_poseframe) S.stats["keyframe"] = S.stats.count("detection") ? S.stats["detection"] : 0.0;
   return updated;
 }

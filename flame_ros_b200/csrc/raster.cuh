@@ -20,8 +20,9 @@ __global__ void __launch_bounds__(256)
 k_tri_validity(int W, const float* __restrict__ K, const float2* __restrict__ vtx,
                const float* __restrict__ idepth, int T, const int32_t* __restrict__ tri,
                fb_tri_filter_params fp, float cos_thresh, int use_filter,
-               uint8_t* __restrict__ valid) {
+               uint8_t* __restrict__ valid, const int32_t* __restrict__ Tdev = nullptr) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (Tdev) T = *Tdev;  // device-built meshes: the count never visits the host
   if (t >= T) return;
   const int a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
   const float d[3] = {idepth[a], idepth[b], idepth[c]};
@@ -86,9 +87,10 @@ k_tri_validity(int W, const float* __restrict__ K, const float2* __restrict__ vt
 __global__ void __launch_bounds__(256)
 k_raster_claim(int W, int H, const float2* __restrict__ vtx, int T,
                const int32_t* __restrict__ tri, const uint8_t* __restrict__ valid,
-               int32_t* __restrict__ owner) {
+               int32_t* __restrict__ owner, const int32_t* __restrict__ Tdev = nullptr) {
   const int lane = threadIdx.x & 31;
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (Tdev) T = *Tdev;
   if (t >= T || !valid[t]) return;
   const float2 A = vtx[tri[3 * t]], B = vtx[tri[3 * t + 1]], C = vtx[tri[3 * t + 2]];
   const float area = fb_edge_fn(A.x, A.y, B.x, B.y, C.x, C.y);
@@ -113,8 +115,10 @@ k_raster_claim(int W, int H, const float2* __restrict__ vtx, int T,
 __global__ void __launch_bounds__(256)
 k_raster_shade(int W, int H, const float2* __restrict__ vtx, const float* __restrict__ idepth,
                const int32_t* __restrict__ tri, const int32_t* __restrict__ owner,
-               float* __restrict__ map) {
+               float* __restrict__ map, const int32_t* __restrict__ Tdev = nullptr,
+               int32_t* __restrict__ covered = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (Tdev && *Tdev == 0) return;  // no mesh this frame: the previous map stays
   if (i >= W * H) return;
   const int t = owner[i];
   float out = __int_as_float(0x7fc00000);
@@ -129,4 +133,8 @@ k_raster_shade(int W, int H, const float2* __restrict__ vtx, const float* __rest
     out = fmaf(w0, idepth[a], fmaf(w1, idepth[b], w2 * idepth[c]));
   }
   map[i] = out;
+  if (covered) {  // `coverage` stat (/root/reference/src/utils.cc:122): pixels with a depth
+    const unsigned m = __ballot_sync(__activemask(), out == out);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(covered, __popc(m));
+  }
 }

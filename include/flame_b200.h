@@ -140,7 +140,11 @@ int fb_graph_x_get_all(fb_ctx* ctx, float* x_all);
  *              sides): a cluster of <= 16 CTAs per stream with DSMEM st.async hand-over when the
  *              graphs fit, else every co-resident CTA of the device with tagged 128-bit
  *              mailboxes in L2 (cooperative launch).
- * auto picks 3 when the batch fits, else 2, else 1.  All variants give bit-identical results. */
+ *          4 = plan-free resident kernel: one cluster per stream, state in registers, exchange
+ *              through L2 behind the cluster barrier; needs no per-topology tables, so it serves
+ *              graphs that change every frame (fb_update).
+ * auto picks 3 when the batch fits, else 2, else 1 (4, else 1, for graphs built on the device by
+ * fb_update).  All variants give bit-identical results. */
 int fb_nltgv2_solve(fb_ctx* ctx, int iters, const fb_nltgv2_params* p, int variant);
 /* nltgv2_total_{smoothness,data}_cost (/root/reference/src/utils.cc:131-136); synchronises. */
 int fb_costs(fb_ctx* ctx, int stream, float data_factor, double* smoothness, double* data);
@@ -248,6 +252,9 @@ typedef struct {
   int do_nltgv2;              /* 1 */
   int iters;                  /* NLTGV2 iterations per frame, 50 (BASELINE configs) */
   fb_nltgv2_params rparams;
+  int triangulator;           /* sync_graph + triangulate: 0 = on the device (per-vertex Delaunay stars,
+                                 default, no host round trip), 1 = host (incremental Bowyer-Watson).
+                                 Both give the same canonical mesh. */
 } fb_update_params;
 void fb_default_update_params(fb_update_params* p);
 int fb_set_update_params(fb_ctx* ctx, const fb_update_params* p);
@@ -291,6 +298,13 @@ int fb_get_feature_pool(fb_ctx* ctx, int stream, float* u_ref, int32_t* ref_slot
  * Returns FB_OK, or FB_E_ARG when the points are degenerate (n < 3 or all collinear). */
 int fb_delaunay(int n, const float* pts_xy, int32_t* tris, int32_t* n_tris, int32_t* edges,
                 int32_t* n_edges);
+
+/* The same triangulation computed on the device by the kernels fb_update uses (one warp per vertex
+ * computes that vertex's Delaunay star with exact predicates; csrc/delaunay_star.h).  Same output
+ * contract and bit-identical output as fb_delaunay; n <= max_features and max_vertices of the
+ * context.  FB_E_STATE when a star exceeds 32 neighbours.  Leaves stream `stream` without a graph. */
+int fb_delaunay_device(fb_ctx* ctx, int stream, int n, const float* pts_xy, int32_t* tris, int32_t* n_tris,
+                       int32_t* edges, int32_t* n_edges);
 
 /* ------------------------------------------------------------------ mesh -> dense inverse depth
  * Stands in for the `interpolate` stage + flame::Flame::getInverseDepthMap /

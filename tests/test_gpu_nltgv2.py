@@ -18,7 +18,7 @@ def linf(a, b):
     return max(float(np.max(np.abs(a[k] - b[k]))) for k in STATE_KEYS if len(a[k]))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("iters", [1, 10, 50])
 def test_small_graph_parity(capi, oracle, variant, iters):
     g = small_graph()
@@ -32,14 +32,16 @@ def test_small_graph_parity(capi, oracle, variant, iters):
     assert np.array_equal(ref["x"], got["x"]), "expected bit-exact x (same expression order)"
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_c2_graph_parity_50_iters(capi, oracle, variant):
     g = synth.s_graph("C2")
     ref = run_oracle(oracle, g, 50)
     with capi.Context(1, 640, 480, 2, 16, 5000, 15000) as ctx:
         gpu_load_graph(ctx, 0, g)
         ctx.nltgv2_solve(50, variant=variant)
+        assert ctx.last_solver_variant() == variant
         got = ctx.graph_state_get(0)
+        assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS), "expected bit-exact state"
         s_gpu, d_gpu = ctx.costs(0, 0.15)
     assert linf(ref, got) < TOL
     s_ref, d_ref = oracle.nltgv2_costs(g["pos"], g["edges"], g["alpha"], g["beta"], g["z"], g["wt"],
@@ -173,7 +175,7 @@ def test_warm_start_roundtrip(capi, oracle):
     assert linf(ref, got) < TOL
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_batched_streams_block_diagonal(capi, oracle, variant):
     """Different graphs in different streams of one context: one launch, independent results."""
     graphs = [small_graph(10 + 2 * s, 8 + s, 96, 72, seed=20 + s) for s in range(3)]
@@ -271,5 +273,19 @@ def test_grid_solver_irregular_graph(capi, oracle, mode, monkeypatch):
         gpu_load_graph(ctx, 0, g)
         ctx.nltgv2_solve(23, variant=3)
         assert ctx.last_solver_variant() == 3
+        got = ctx.graph_state_get(0)
+    assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
+
+
+def test_plan_free_solver_two_instantiations_and_warm_restart(capi, oracle):
+    """Variant 4 (plan-free resident kernel): the (6 edges, 2 vertices) per thread instantiation is
+    chosen by the context's capacities; consecutive launches continue from each other's state."""
+    g = synth.s_graph("C2")
+    ref = run_oracle(oracle, g, 30)
+    with capi.Context(1, 640, 480, 2, 16, 12000, 40000) as ctx:  # capacities beyond 8192 / 24576
+        gpu_load_graph(ctx, 0, g)
+        ctx.nltgv2_solve(10, variant=4)
+        ctx.nltgv2_solve(20, variant=4)
+        assert ctx.last_solver_variant() == 4
         got = ctx.graph_state_get(0)
     assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
