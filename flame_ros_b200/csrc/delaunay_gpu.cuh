@@ -234,15 +234,14 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
 }
 
 // ------------------------------------------------------------------------------------ k_ds_stars
-#define DSG_WARPS 8
-__global__ void __launch_bounds__(DSG_WARPS * 32)
+#define DSG_GROUPS 16  // vertices per CTA: 16 groups of 8 lanes
+__global__ void __launch_bounds__(DSG_GROUPS * 8)
 k_ds_stars(DelGpu d, int s, int maxV) {
-  __shared__ int s_row[DSG_WARPS][2 * DS_MAXROWS];
-  __shared__ int s_list[DSG_WARPS][2 * DS_MAXD];
+  __shared__ DsScratch s_scr[DSG_GROUPS];
   int32_t* meta = d.meta + (size_t)s * DSG_META;
   const int V = meta[DSG_NV];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * DSG_WARPS + w;
+  const int g = threadIdx.x >> 3, lane = threadIdx.x & 7;
+  const int p = blockIdx.x * DSG_GROUPS + g;
   if (p >= V) return;
   const size_t vb = (size_t)s * maxV;
   DsIn in;
@@ -260,17 +259,17 @@ k_ds_stars(DelGpu d, int s, int maxV) {
   {
     const DsPt l = in.vxy[p];
     const int c = ds_celly(in, l.y) * in.gx + ds_cellx(in, l.x);
-    for (int k = in.cell_start[c] + lane; k < in.cell_start[c + 1]; k += 32)
+    for (int k = in.cell_start[c] + lane; k < in.cell_start[c + 1]; k += 8)
       if (in.sid[k] == ~p) dup = true;
-    dup = __any_sync(0xffffffffu, dup);
+    dup = DsW8::any(dup);
   }
   if (!dup) {
-    const int rc = ds_star<DsW32>(in, p, s_row[w], s_row[w] + DS_MAXROWS, s_list[w], s_list[w] + DS_MAXD, star, &deg, &closed);
+    const int rc = ds_star<DsW8>(in, p, &s_scr[g], star, &deg, &closed);
     if (rc) {
       if (lane == 0) atomicOr(&meta[DSG_ERR], 1 << rc);
       deg = 0;
     }
-    __syncwarp();
+    DsW8::sync();
     if (lane == 0) ds_counts(p, star, deg, closed, &od, &tc);
   }
   if (lane == 0) {

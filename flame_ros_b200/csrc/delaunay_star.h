@@ -69,15 +69,21 @@ DS_FN int64_t ds_orient(DsPt a, DsPt b, DsPt c) {
 // 0 iff on it.  |coordinates| < 2^20: differences < 2^21, squared lengths and 2x2 minors < 2^43 are
 // exact in double; the three-term sum is decided by a static error bound, else exactly in 128 bits.
 DS_FN int ds_incircle(DsPt a, DsPt b, DsPt c, DsPt p) {
-  const int64_t adx = a.x - p.x, ady = a.y - p.y, bdx = b.x - p.x, bdy = b.y - p.y;
-  const int64_t cdx = c.x - p.x, cdy = c.y - p.y;
+  const int32_t iadx = a.x - p.x, iady = a.y - p.y, ibdx = b.x - p.x, ibdy = b.y - p.y;
+  const int32_t icdx = c.x - p.x, icdy = c.y - p.y;
+  {
+    const double adx = iadx, ady = iady, bdx = ibdx, bdy = ibdy, cdx = icdx, cdy = icdy;
+    const double al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;  // exact
+    const double ma = bdx * cdy - bdy * cdx, mb = cdx * ady - cdy * adx, mc = adx * bdy - ady * bdx;  // exact
+    const double ta = al * ma, tb = bl * mb, tc = cl * mc;
+    const double det = ta + tb + tc;
+    const double bound = 8.9e-16 * (fabs(ta) + fabs(tb) + fabs(tc));
+    if (det > bound) return 1;
+    if (det < -bound) return -1;
+  }
+  const int64_t adx = iadx, ady = iady, bdx = ibdx, bdy = ibdy, cdx = icdx, cdy = icdy;
   const int64_t al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
   const int64_t ma = bdx * cdy - bdy * cdx, mb = cdx * ady - cdy * adx, mc = adx * bdy - ady * bdx;
-  const double ta = (double)al * (double)ma, tb = (double)bl * (double)mb, tc = (double)cl * (double)mc;
-  const double det = ta + tb + tc;
-  const double bound = 8.9e-16 * (fabs(ta) + fabs(tb) + fabs(tc));
-  if (det > bound) return 1;
-  if (det < -bound) return -1;
   const ds_i128 d = (ds_i128)al * (ds_i128)ma + (ds_i128)bl * (ds_i128)mb + (ds_i128)cl * (ds_i128)mc;
   return d > 0 ? 1 : (d < 0 ? -1 : 0);
 }
@@ -103,22 +109,53 @@ struct DsSeq {  // host simulation: one lane
   DS_MEM void sync() {}
 };
 #ifdef __CUDACC__
-struct DsW32 {
-  static const int LANES = 32;
-  __device__ __forceinline__ static int lane() { return threadIdx.x & 31; }
-  __device__ __forceinline__ static int shfl_xor(int v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
-  __device__ __forceinline__ static long long shfl_xor(long long v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
-  __device__ __forceinline__ static int bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-  __device__ __forceinline__ static bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
-  __device__ __forceinline__ static void sync() { __syncwarp(); }
+// Eight lanes per vertex, four vertices per warp: a star's candidate set is ~40 points, so 32 lanes
+// would idle through most passes and replicate the scalar set-up four times as often.
+struct DsW8 {
+  static const int LANES = 8;
+  __device__ __forceinline__ static unsigned mask() { return 0xffu << (threadIdx.x & 24); }
+  __device__ __forceinline__ static int lane() { return threadIdx.x & 7; }
+  __device__ __forceinline__ static int shfl_xor(int v, int o) { return __shfl_xor_sync(mask(), v, o, 8); }
+  __device__ __forceinline__ static long long shfl_xor(long long v, int o) { return __shfl_xor_sync(mask(), v, o, 8); }
+  __device__ __forceinline__ static int bcast(int v, int src) { return __shfl_sync(mask(), v, src, 8); }
+  __device__ __forceinline__ static bool any(bool p) { return __any_sync(mask(), p) != 0; }
+  __device__ __forceinline__ static void sync() { __syncwarp(mask()); }
 };
 #endif
 
 // ------------------------------------------------------------------------------------ cell blocks
+#define DS_CACHE 128  // candidates of a block held in the group's scratch (larger blocks are re-read)
 struct DsBlock {
   int x0, y0, x1, y1;  // inclusive cell rectangle
   int nrows;           // rows of the row table (1 when the rectangle spans the full grid width)
+  int ncache;          // candidates in the scratch cache, -1 = too many (iterate the rows)
 };
+// Scratch of one lane group (shared memory on the device).
+struct DsScratch {
+  int rowbeg[DS_MAXROWS], rowcnt[DS_MAXROWS];
+  int ccw[DS_MAXD], cw[DS_MAXD];
+  int cid[DS_CACHE];
+  DsPt cxy[DS_CACHE];
+};
+// for (every candidate of the block: id ID, coordinates PT) BODY -- lanes stride (SEQ = 0) or every
+// lane visits all (SEQ = 1).  `continue` inside BODY skips to the next candidate.
+#define DS_FOR_CAND(W, in, S, blk, SEQ, ID, PT, ...)                                              \
+  if ((blk).ncache >= 0) {                                                                        \
+    for (int k_ = (SEQ) ? 0 : W::lane(); k_ < (blk).ncache; k_ += (SEQ) ? 1 : W::LANES) {         \
+      const int ID = (S)->cid[k_];                                                                \
+      const DsPt PT = (S)->cxy[k_];                                                               \
+      __VA_ARGS__                                                                                 \
+    }                                                                                             \
+  } else {                                                                                        \
+    for (int r_ = 0; r_ < (blk).nrows; ++r_) {                                                    \
+      const int beg_ = (S)->rowbeg[r_], end_ = beg_ + (S)->rowcnt[r_];                            \
+      for (int k_ = beg_ + ((SEQ) ? 0 : W::lane()); k_ < end_; k_ += (SEQ) ? 1 : W::LANES) {      \
+        const int ID = (in).sid[k_];                                                              \
+        const DsPt PT = (in).sxy[k_];                                                             \
+        __VA_ARGS__                                                                               \
+      }                                                                                           \
+    }                                                                                             \
+  }
 
 DS_FN int ds_cellx(const DsIn& in, int64_t x) {
   const int64_t c = x >> in.shift;
@@ -129,25 +166,42 @@ DS_FN int ds_celly(const DsIn& in, int64_t y) {
   return c < 0 ? 0 : (c >= in.gy ? in.gy - 1 : (int)c);
 }
 
-// Row table of a block: contiguous ranges of the cell-sorted arrays (cells are sorted row-major).
+// Row table of a block: contiguous ranges of the cell-sorted arrays (cells are sorted row-major);
+// small blocks are copied into the scratch cache.
 template <class W>
-DS_FN void ds_block_rows(const DsIn& in, DsBlock& b, int* rowbeg, int* rowcnt) {
+DS_FN void ds_block_rows(const DsIn& in, DsBlock& b, DsScratch* S) {
   W::sync();
   if (b.x0 == 0 && b.x1 == in.gx - 1) {
     b.nrows = 1;
     if (W::lane() == 0) {
-      rowbeg[0] = in.cell_start[b.y0 * in.gx];
-      rowcnt[0] = in.cell_start[(b.y1 + 1) * in.gx] - rowbeg[0];
+      S->rowbeg[0] = in.cell_start[b.y0 * in.gx];
+      S->rowcnt[0] = in.cell_start[(b.y1 + 1) * in.gx] - S->rowbeg[0];
     }
   } else {
     b.nrows = b.y1 - b.y0 + 1;
     for (int r = W::lane(); r < b.nrows; r += W::LANES) {
       const int beg = in.cell_start[(b.y0 + r) * in.gx + b.x0];
-      rowbeg[r] = beg;
-      rowcnt[r] = in.cell_start[(b.y0 + r) * in.gx + b.x1 + 1] - beg;
+      S->rowbeg[r] = beg;
+      S->rowcnt[r] = in.cell_start[(b.y0 + r) * in.gx + b.x1 + 1] - beg;
     }
   }
   W::sync();
+  int total = 0;
+  for (int r = 0; r < b.nrows; ++r) total += S->rowcnt[r];
+  b.ncache = -1;
+  if (total <= DS_CACHE) {
+    int base = 0;
+    for (int r = 0; r < b.nrows; ++r) {
+      const int beg = S->rowbeg[r], cnt = S->rowcnt[r];
+      for (int k = W::lane(); k < cnt; k += W::LANES) {
+        S->cid[base + k] = in.sid[beg + k];
+        S->cxy[base + k] = in.sxy[beg + k];
+      }
+      base += cnt;
+    }
+    b.ncache = total;
+    W::sync();
+  }
 }
 
 // Grow the block to contain the lattice rectangle [rx0,rx1]x[ry0,ry1]; true when it changed.
@@ -215,30 +269,25 @@ DS_FN bool ds_halfplane_region(const DsIn& in, DsPt p, DsPt cur, int dir, int64_
 // Next neighbour of p after cur in direction dir; -1 when there is none (hull end).  All lanes
 // return the same value; *nxy receives its coordinates.  *err is set on an invariant violation.
 template <class W>
-DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, DsBlock& blk, int* rowbeg,
-                  int* rowcnt, DsPt* nxy, int* err) {
+DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, DsBlock& blk, DsScratch* S,
+                  DsPt* nxy, int* err) {
   for (int guard = 0; guard < 4 * DS_MAXROWS; ++guard) {
     int bid = -1;
     DsPt bxy = {0, 0};
-    for (int r = 0; r < blk.nrows; ++r) {
-      const int beg = rowbeg[r], end = beg + rowcnt[r];
-      for (int k = beg + W::lane(); k < end; k += W::LANES) {
-        const int id = in.sid[k];
-        if (id < 0 || id == p || id == curid) continue;
-        const DsPt c = in.sxy[k];
-        if (!ds_side(pp, cur, c, dir)) continue;
-        if (bid < 0 || ds_inside(pp, cur, bxy, c, dir) > 0) {
-          bid = id;
-          bxy = c;
-        }
+    DS_FOR_CAND(W, in, S, blk, 0, id, c, {
+      if (id < 0 || id == p || id == curid) continue;
+      if (!ds_side(pp, cur, c, dir)) continue;
+      if (bid < 0 || ds_inside(pp, cur, bxy, c, dir) > 0) {
+        bid = id;
+        bxy = c;
       }
-    }
+    })
     for (int o = W::LANES >> 1; o > 0; o >>= 1) {
       const int oid = W::shfl_xor(bid, o);
       DsPt oxy;
       oxy.x = W::shfl_xor(bxy.x, o);
       oxy.y = W::shfl_xor(bxy.y, o);
-      if (oid >= 0 && (bid < 0 || ds_inside(pp, cur, bxy, oxy, dir) > 0)) {
+      if (oid >= 0 && oid != bid && (bid < 0 || ds_inside(pp, cur, bxy, oxy, dir) > 0)) {
         bid = oid;
         bxy = oxy;
       }
@@ -250,46 +299,36 @@ DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, 
     if (bid < 0) {
       if (ds_block_all(in, blk) || !ds_halfplane_region(in, pp, cur, dir, reg)) return -1;
       if (!ds_block_cover(in, blk, reg[0], reg[1], reg[2], reg[3])) return -1;
-      ds_block_rows<W>(in, blk, rowbeg, rowcnt);
+      ds_block_rows<W>(in, blk, S);
       continue;
     }
     if (!ds_block_all(in, blk)) {
       if (dir > 0) ds_circle_region(in, pp, cur, bxy, reg);
       else ds_circle_region(in, pp, bxy, cur, reg);
       if (ds_block_cover(in, blk, reg[0], reg[1], reg[2], reg[3])) {
-        ds_block_rows<W>(in, blk, rowbeg, rowcnt);
+        ds_block_rows<W>(in, blk, S);
         continue;
       }
     }
     // the circle (p, cur, best) is empty; other points ON it make a co-circular polygon
     bool tie = false;
-    for (int r = 0; r < blk.nrows; ++r) {
-      const int beg = rowbeg[r], end = beg + rowcnt[r];
-      for (int k = beg + W::lane(); k < end; k += W::LANES) {
-        const int id = in.sid[k];
-        if (id < 0 || id == p || id == curid || id == bid) continue;
-        const DsPt c = in.sxy[k];
-        if (ds_side(pp, cur, c, dir) && ds_inside(pp, cur, bxy, c, dir) == 0) tie = true;
-      }
-    }
+    DS_FOR_CAND(W, in, S, blk, 0, id, c, {
+      if (id < 0 || id == p || id == curid || id == bid) continue;
+      if (ds_side(pp, cur, c, dir) && ds_inside(pp, cur, bxy, c, dir) == 0) tie = true;
+    })
     if (W::any(tie)) {
       // canonical fan from the smallest index (all lanes run the same sequential pass)
       int minid = p < curid ? p : curid;
       int cl = bid, fa = bid, mt = -1;
       DsPt clxy = bxy, faxy = bxy, mtxy = bxy;
       if (bid < minid) { minid = bid; mt = bid; }
-      for (int r = 0; r < blk.nrows; ++r) {
-        const int beg = rowbeg[r], end = beg + rowcnt[r];
-        for (int k = beg; k < end; ++k) {
-          const int id = in.sid[k];
-          if (id < 0 || id == p || id == curid || id == bid) continue;
-          const DsPt c = in.sxy[k];
-          if (!ds_side(pp, cur, c, dir) || ds_inside(pp, cur, bxy, c, dir) != 0) continue;
-          if (id < minid) { minid = id; mt = id; mtxy = c; }
-          if (ds_orient(pp, c, clxy) * dir > 0) { cl = id; clxy = c; }   // c comes before the closest so far
-          if (ds_orient(pp, faxy, c) * dir > 0) { fa = id; faxy = c; }   // c comes after the farthest so far
-        }
-      }
+      DS_FOR_CAND(W, in, S, blk, 1, id, c, {
+        if (id < 0 || id == p || id == curid || id == bid) continue;
+        if (!ds_side(pp, cur, c, dir) || ds_inside(pp, cur, bxy, c, dir) != 0) continue;
+        if (id < minid) { minid = id; mt = id; mtxy = c; }
+        if (ds_orient(pp, c, clxy) * dir > 0) { cl = id; clxy = c; }   // c comes before the closest so far
+        if (ds_orient(pp, faxy, c) * dir > 0) { fa = id; faxy = c; }   // c comes after the farthest so far
+      })
       if (minid == p) { bid = cl; bxy = clxy; }
       else if (minid == curid) { bid = fa; bxy = faxy; }
       else if (mt >= 0) { bid = mt; bxy = mtxy; }
@@ -303,17 +342,16 @@ DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, 
 }
 
 // ------------------------------------------------------------------------------------ star of p
-// ccw / cw: per-warp scratch [DS_MAXD] each; rowbeg / rowcnt: per-warp scratch [DS_MAXROWS].
-// Result (lane 0 writes): star[0..deg) counter-clockwise; *closed = 1 for an interior vertex.
+// S: the lane group's scratch.  Result (lane 0 writes): star[0..deg) counter-clockwise; *closed = 1
+// for an interior vertex.
 template <class W>
-DS_FN int ds_star(const DsIn& in, int p, int* rowbeg, int* rowcnt, int* ccw, int* cw, int* star, int* deg_out,
-                  int* closed_out) {
+DS_FN int ds_star(const DsIn& in, int p, DsScratch* S, int* star, int* deg_out, int* closed_out) {
   const DsPt pp = in.vxy[p];
   const int cxp = ds_cellx(in, pp.x), cyp = ds_celly(in, pp.y);
   DsBlock blk;
   blk.x0 = cxp > 0 ? cxp - 1 : 0; blk.x1 = cxp < in.gx - 1 ? cxp + 1 : in.gx - 1;
   blk.y0 = cyp > 0 ? cyp - 1 : 0; blk.y1 = cyp < in.gy - 1 ? cyp + 1 : in.gy - 1;
-  ds_block_rows<W>(in, blk, rowbeg, rowcnt);
+  ds_block_rows<W>(in, blk, S);
   *deg_out = 0;
   *closed_out = 0;
   // ---- nearest neighbour
@@ -323,16 +361,11 @@ DS_FN int ds_star(const DsIn& in, int p, int* rowbeg, int* rowcnt, int* ccw, int
     long long bd = 0x7fffffffffffffffll;
     int bid = -1;
     DsPt bxy = {0, 0};
-    for (int r = 0; r < blk.nrows; ++r) {
-      const int beg = rowbeg[r], end = beg + rowcnt[r];
-      for (int k = beg + W::lane(); k < end; k += W::LANES) {
-        const int id = in.sid[k];
-        if (id < 0 || id == p) continue;
-        const DsPt c = in.sxy[k];
-        const long long dx = c.x - pp.x, dy = c.y - pp.y, d2 = dx * dx + dy * dy;
-        if (d2 < bd || (d2 == bd && id < bid)) { bd = d2; bid = id; bxy = c; }
-      }
-    }
+    DS_FOR_CAND(W, in, S, blk, 0, id, c, {
+      if (id < 0 || id == p) continue;
+      const long long dx = c.x - pp.x, dy = c.y - pp.y, d2 = dx * dx + dy * dy;
+      if (d2 < bd || (d2 == bd && id < bid)) { bd = d2; bid = id; bxy = c; }
+    })
     for (int o = W::LANES >> 1; o > 0; o >>= 1) {
       const long long od = W::shfl_xor(bd, o);
       const int oid = W::shfl_xor(bid, o), ox = W::shfl_xor(bxy.x, o), oy = W::shfl_xor(bxy.y, o);
@@ -343,7 +376,7 @@ DS_FN int ds_star(const DsIn& in, int p, int* rowbeg, int* rowcnt, int* ccw, int
       const int hx = blk.x1 - blk.x0 + 1, hy = blk.y1 - blk.y0 + 1;
       blk.x0 = blk.x0 - hx < 0 ? 0 : blk.x0 - hx; blk.x1 = blk.x1 + hx > in.gx - 1 ? in.gx - 1 : blk.x1 + hx;
       blk.y0 = blk.y0 - hy < 0 ? 0 : blk.y0 - hy; blk.y1 = blk.y1 + hy > in.gy - 1 ? in.gy - 1 : blk.y1 + hy;
-      ds_block_rows<W>(in, blk, rowbeg, rowcnt);
+      ds_block_rows<W>(in, blk, S);
       continue;
     }
     const int64_t rr = (int64_t)ceil(sqrt((double)bd)) + 2;
@@ -353,7 +386,7 @@ DS_FN int ds_star(const DsIn& in, int p, int* rowbeg, int* rowcnt, int* ccw, int
     if (x1 > in.bx1) x1 = in.bx1;
     if (y1 > in.by1) y1 = in.by1;
     if (!ds_block_all(in, blk) && ds_block_cover(in, blk, x0, y0, x1, y1)) {
-      ds_block_rows<W>(in, blk, rowbeg, rowcnt);
+      ds_block_rows<W>(in, blk, S);
       continue;
     }
     n0 = bid;
@@ -363,17 +396,17 @@ DS_FN int ds_star(const DsIn& in, int p, int* rowbeg, int* rowcnt, int* ccw, int
   if (n0 < 0) return DS_E_LOOP;
   // ---- counter-clockwise sweep from n0
   int err = DS_OK, nccw = 1, ncw = 0, closed = 0;
-  if (W::lane() == 0) ccw[0] = n0;
+  if (W::lane() == 0) S->ccw[0] = n0;
   int curid = n0;
   DsPt cur = n0xy;
   for (;;) {
     DsPt nxy;
-    const int nx = ds_next<W>(in, p, pp, curid, cur, +1, blk, rowbeg, rowcnt, &nxy, &err);
+    const int nx = ds_next<W>(in, p, pp, curid, cur, +1, blk, S, &nxy, &err);
     if (err) return err;
     if (nx < 0) break;
     if (nx == n0) { closed = 1; break; }
     if (nccw >= DS_MAXD) return DS_E_DEGREE;
-    if (W::lane() == 0) ccw[nccw] = nx;
+    if (W::lane() == 0) S->ccw[nccw] = nx;
     ++nccw;
     curid = nx;
     cur = nxy;
@@ -383,11 +416,11 @@ DS_FN int ds_star(const DsIn& in, int p, int* rowbeg, int* rowcnt, int* ccw, int
     cur = n0xy;
     for (;;) {
       DsPt nxy;
-      const int nx = ds_next<W>(in, p, pp, curid, cur, -1, blk, rowbeg, rowcnt, &nxy, &err);
+      const int nx = ds_next<W>(in, p, pp, curid, cur, -1, blk, S, &nxy, &err);
       if (err) return err;
       if (nx < 0) break;
       if (nccw + ncw >= DS_MAXD) return DS_E_DEGREE;
-      if (W::lane() == 0) cw[ncw] = nx;
+      if (W::lane() == 0) S->cw[ncw] = nx;
       ++ncw;
       curid = nx;
       cur = nxy;
@@ -395,8 +428,8 @@ DS_FN int ds_star(const DsIn& in, int p, int* rowbeg, int* rowcnt, int* ccw, int
   }
   W::sync();
   if (W::lane() == 0) {
-    for (int k = 0; k < ncw; ++k) star[k] = cw[ncw - 1 - k];
-    for (int k = 0; k < nccw; ++k) star[ncw + k] = ccw[k];
+    for (int k = 0; k < ncw; ++k) star[k] = S->cw[ncw - 1 - k];
+    for (int k = 0; k < nccw; ++k) star[ncw + k] = S->ccw[k];
   }
   W::sync();
   *deg_out = nccw + ncw;

@@ -210,6 +210,53 @@ void fo_rasterize_idepth(int W, int H, int V, const float* vtx, const float* ide
                          int T, const int32_t* tri, const uint8_t* valid /*NULL = all*/,
                          float* idepthmap /*[H][W]*/);
 
+/* ------------------------------------- triangulation (flame_pipeline.c)    */
+/*
+ * Delaunay triangulation of n pixel positions (snapped to a 1/64 px lattice, exact predicates):
+ * the `triangulate` stage (/root/reference/src/utils.cc:154).  Canonical output: co-circular point
+ * sets fan out from their smallest index, identical points keep the smallest index, triangles
+ * (v0 smallest, counter-clockwise in stored coordinates) sorted by (v0, v1), edges (i<j) sorted.
+ * tris capacity 3*2n, edges capacity 2*3n.  Returns 0, -1 when degenerate.
+ */
+int fo_delaunay(int n, const float* pts, int32_t* tris, int32_t* n_tris, int32_t* edges,
+                int32_t* n_edges);
+
+/* ------------------------------------- whole per-frame pipeline            */
+/* flame::Flame::update (/root/reference/src/flame_nodelet.cc:634) restated on the CPU. */
+typedef struct {
+  int detection_win_size;     /* features/detection/win_size, 16 */
+  float min_grad_mag;         /* features/detection/min_grad_mag, 5.0 */
+  int detection_border;       /* OUR CHOICE: 8 px */
+  float idepth_init;          /* OUR CHOICE: prior mean of a new feature, 0.5 */
+  float idepth_var_init;      /* OUR CHOICE: prior variance, 0.25 */
+  float idepth_var_max_graph; /* regularization/nltgv2/idepth_var_max, 0.01 */
+  int adaptive_data_weights;
+  int init_with_prediction;
+  int do_nltgv2;
+  int iters;                  /* OUR CHOICE: iterations per frame, 50 */
+  fo_nltgv2_params rparams;
+} fo_update_params;
+void fo_default_update_params(fo_update_params* p);
+
+enum { FO_STAGE_UPDATE = 0, FO_STAGE_FRAME, FO_STAGE_IDEPTH, FO_STAGE_PROJECT, FO_STAGE_SYNC,
+       FO_STAGE_TRIANGULATE, FO_STAGE_SOLVE, FO_STAGE_INTERP, FO_STAGE_DETECT, FO_STAGE_NUM };
+
+typedef struct fo_pipeline fo_pipeline;
+fo_pipeline* fo_pipeline_create(int W, int H, const float* K /*[9]*/, int n_slots, int max_features,
+                                int max_vertices, const fo_update_params* up, const fo_epi_params* ep,
+                                int nthreads);
+void fo_pipeline_destroy(fo_pipeline* P);
+/* One frame; returns 1 when the mesh / dense map were updated. */
+int fo_pipeline_update(fo_pipeline* P, int img_id, const float* pose /*[7]*/, const uint8_t* gray,
+                       int is_poseframe);
+void fo_pipeline_sizes(const fo_pipeline* P, int32_t* V, int32_t* T, int32_t* E);
+void fo_pipeline_mesh(const fo_pipeline* P, float* vtx, float* idepth, int32_t* tris, int32_t* edges,
+                      int32_t* vert_feat);
+void fo_pipeline_idepthmap(const fo_pipeline* P, const fo_tri_filter_params* filter, float* out);
+void fo_pipeline_features(const fo_pipeline* P, float* u_ref, int32_t* ref_slot, float* mu, float* var,
+                          int32_t* dropouts, int32_t* alive, int32_t* valid);
+void fo_pipeline_stage_ms(const fo_pipeline* P, double* ms /*[FO_STAGE_NUM]*/);
+
 #ifdef __cplusplus
 }
 #endif

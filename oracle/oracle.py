@@ -84,8 +84,8 @@ def load(native=False):
         return _LIB
     name = "libflame_oracle_native.so" if native else "libflame_oracle.so"
     path = os.path.join(_HERE, "_build", name)
-    src = os.path.join(_HERE, "flame_oracle.c")
-    if native or not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("flame_oracle.c", "flame_pipeline.c", "flame_oracle.h")]
+    if native or not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(f) for f in srcs):
         build(native=native)
     lib = C.CDLL(path)
     for fn in ("fo_nltgv2_solve", "fo_nltgv2_costs", "fo_idepth_update", "fo_epi_geometry",
@@ -93,6 +93,12 @@ def load(native=False):
                "fo_rasterize_idepth"):
         getattr(lib, fn).restype = None
     lib.fo_detect_features.restype = C.c_int
+    for fn in ("fo_default_update_params", "fo_pipeline_destroy", "fo_pipeline_sizes", "fo_pipeline_mesh",
+               "fo_pipeline_idepthmap", "fo_pipeline_features", "fo_pipeline_stage_ms"):
+        getattr(lib, fn).restype = None
+    lib.fo_delaunay.restype = C.c_int
+    lib.fo_pipeline_create.restype = C.c_void_p
+    lib.fo_pipeline_update.restype = C.c_int
     if native:
         _LIB_NATIVE = lib
     else:
@@ -252,3 +258,111 @@ def rasterize_idepth(W, H, vtx, idepth, tri, valid=None):
     lib.fo_rasterize_idepth(C.c_int(W), C.c_int(H), C.c_int(idepth.shape[0]), _fp(vtx), _fp(idepth),
                             C.c_int(T), _ip(tri), _bp(v) if v is not None else None, _fp(out))
     return out
+
+
+class UpdateParams(C.Structure):
+    _fields_ = [("detection_win_size", C.c_int), ("min_grad_mag", C.c_float), ("detection_border", C.c_int),
+                ("idepth_init", C.c_float), ("idepth_var_init", C.c_float), ("idepth_var_max_graph", C.c_float),
+                ("adaptive_data_weights", C.c_int), ("init_with_prediction", C.c_int), ("do_nltgv2", C.c_int),
+                ("iters", C.c_int), ("rparams", NLTGV2Params)]
+
+    @classmethod
+    def default(cls):
+        p = cls()
+        load().fo_default_update_params(C.byref(p))
+        return p
+
+    @classmethod
+    def like(cls, other):
+        """Copy the fields this struct shares with another parameter struct (the product's fb_update_params)."""
+        p = cls.default()
+        for n, _ in cls._fields_:
+            if n == "rparams":
+                for m, _ in NLTGV2Params._fields_:
+                    setattr(p.rparams, m, getattr(other.rparams, m))
+            elif hasattr(other, n):
+                setattr(p, n, getattr(other, n))
+        return p
+
+
+STAGES = ["update", "frame_creation", "update_idepths", "project_features", "sync_graph", "triangulate", "nltgv2",
+          "interpolate", "detection"]
+
+
+def delaunay(pts):
+    """The oracle's own triangulator (sorted sweep + Lawson flips, exact predicates).  Returns
+    (tris [T,3], edges [E,2]) in the canonical order, or raises ValueError when degenerate."""
+    lib = load()
+    pts = _f32(pts)
+    n = pts.shape[0]
+    tris = np.zeros((max(2 * n, 1), 3), np.int32)
+    edges = np.zeros((max(3 * n, 1), 2), np.int32)
+    nt, ne = C.c_int32(0), C.c_int32(0)
+    rc = lib.fo_delaunay(C.c_int(n), _fp(pts), _ip(tris), C.byref(nt), _ip(edges), C.byref(ne))
+    if rc != 0:
+        raise ValueError("fo_delaunay: degenerate input")
+    return tris[:nt.value].copy(), edges[:ne.value].copy()
+
+
+class Pipeline:
+    """fo_pipeline_*: the whole flame::Flame::update pipeline on the CPU."""
+
+    def __init__(self, W, H, K, n_slots, max_features, max_vertices, up=None, ep=None, nthreads=1, native=False):
+        self._lib = load(native)
+        self._lib.fo_pipeline_create.restype = C.c_void_p
+        self._lib.fo_pipeline_update.restype = C.c_int
+        self.W, self.H, self.maxF, self.maxV = W, H, max_features, max_vertices
+        self.up = up or UpdateParams.default()
+        self.ep = ep or EpiParams.default()
+        Kf = _f32(K).ravel()
+        self._h = C.c_void_p(self._lib.fo_pipeline_create(C.c_int(W), C.c_int(H), _fp(Kf), C.c_int(n_slots),
+                                                          C.c_int(max_features), C.c_int(max_vertices),
+                                                          C.byref(self.up), C.byref(self.ep), C.c_int(nthreads)))
+        if not self._h:
+            raise ValueError("fo_pipeline_create failed")
+
+    def close(self):
+        if self._h:
+            self._lib.fo_pipeline_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def update(self, img_id, pose, gray, is_poseframe):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        assert gray.shape == (self.H, self.W)
+        return bool(self._lib.fo_pipeline_update(self._h, C.c_int(img_id), _fp(_f32(pose)), _bp(gray),
+                                                 C.c_int(1 if is_poseframe else 0)))
+
+    def mesh(self):
+        V, T, E = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._lib.fo_pipeline_sizes(self._h, C.byref(V), C.byref(T), C.byref(E))
+        out = dict(vtx=np.zeros((V.value, 2), np.float32), idepth=np.zeros(V.value, np.float32),
+                   tris=np.zeros((T.value, 3), np.int32), edges=np.zeros((E.value, 2), np.int32),
+                   vert_feat=np.zeros(V.value, np.int32))
+        self._lib.fo_pipeline_mesh(self._h, _fp(out["vtx"]), _fp(out["idepth"]), _ip(out["tris"]), _ip(out["edges"]),
+                                   _ip(out["vert_feat"]))
+        return out
+
+    def idepthmap(self, filter_params=None):
+        out = np.zeros((self.H, self.W), np.float32)
+        self._lib.fo_pipeline_idepthmap(self._h, C.byref(filter_params) if filter_params is not None else None, _fp(out))
+        return out
+
+    def features(self):
+        F = self.maxF
+        out = dict(u_ref=np.zeros((F, 2), np.float32), ref_slot=np.zeros(F, np.int32), mu=np.zeros(F, np.float32),
+                   var=np.zeros(F, np.float32), dropouts=np.zeros(F, np.int32), alive=np.zeros(F, np.int32),
+                   valid=np.zeros(F, np.int32))
+        self._lib.fo_pipeline_features(self._h, _fp(out["u_ref"]), _ip(out["ref_slot"]), _fp(out["mu"]), _fp(out["var"]),
+                                       _ip(out["dropouts"]), _ip(out["alive"]), _ip(out["valid"]))
+        return out
+
+    def stage_ms(self):
+        ms = (C.c_double * len(STAGES))()
+        self._lib.fo_pipeline_stage_ms(self._h, ms)
+        return dict(zip(STAGES, list(ms)))

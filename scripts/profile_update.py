@@ -9,12 +9,14 @@ sys.path.insert(0, ".")
 from flame_ros_b200 import capi, synth
 
 W, H, win = 640, 480, int(sys.argv[1]) if len(sys.argv) > 1 else 8
-n = 40
+tri = int(sys.argv[2]) if len(sys.argv) > 2 else 0   # 0 = device sync_graph + triangulate, 1 = host
+n = 60
 sc = synth.Scene(0, tex_size=1024)
 poses = synth.stream_poses(n, step=0.01)
 frames = [sc.render(synth.K_VGA, poses[k], W, H)[0] for k in range(n)]
 up = capi.default_update_params()
 up.detection_win_size = win
+up.triangulator = tri
 with capi.Context(1, W, H, 8, 8192, 8192, 24576) as ctx:
     ctx.set_intrinsics(0, synth.K_VGA)
     ctx.set_update_params(up)
@@ -34,4 +36,5 @@ with capi.Context(1, W, H, 8, 8192, 8192, 24576) as ctx:
     out = {k: float(np.median(v[10:])) for k, v in acc.items() if len(v) > 10}
     out["wall_ms_median"] = 1e3 * float(np.median(wall[10:]))
     out["fps"] = 1.0 / float(np.median(wall[10:]))
+    out["win"], out["triangulator"], out["solver_variant"] = win, tri, ctx.last_solver_variant()
     print(json.dumps(out))

@@ -65,10 +65,10 @@ extern "C" int star_sim_delaunay(int n, const float* pts, int cell_px, int32_t* 
   for (int k = 0; k < n; ++k)
     if (sid[k] < 0) dup[~sid[k]] = 1;
   std::vector<int> star((size_t)n * DS_MAXD), deg(n, 0), closed(n, 0), od(n, 0), tc(n, 0);
-  int rowbeg[DS_MAXROWS], rowcnt[DS_MAXROWS], ccw[DS_MAXD], cw[DS_MAXD];
+  DsScratch scratch;
   for (int p = 0; p < n; ++p) {
     if (dup[p]) continue;
-    const int rc = ds_star<DsSeq>(in, p, rowbeg, rowcnt, ccw, cw, &star[(size_t)p * DS_MAXD], &deg[p], &closed[p]);
+    const int rc = ds_star<DsSeq>(in, p, &scratch, &star[(size_t)p * DS_MAXD], &deg[p], &closed[p]);
     if (rc) return rc;
     ds_counts(p, &star[(size_t)p * DS_MAXD], deg[p], closed[p], &od[p], &tc[p]);
     if (max_deg) *max_deg = std::max(*max_deg, deg[p]);
