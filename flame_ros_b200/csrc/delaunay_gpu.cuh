@@ -36,6 +36,7 @@ struct DelGpu {
   DsPt* vxy = nullptr;          // [S*maxV] lattice coordinates by vertex
   DsPt* sxy = nullptr;          // [S*maxV] cell-sorted
   int32_t* sid = nullptr;       // [S*maxV]
+  int32_t* vorder = nullptr;    // [S*maxV] processing order of k_ds_stars: vertices of border cells first
   int32_t* cell_start = nullptr;  // [S*(DSG_MAXCELLS+1)]
   int32_t* star = nullptr;      // [S*maxV*DS_MAXD]
   int32_t* deg = nullptr;       // [S*maxV] degree | closed << 8
@@ -224,6 +225,32 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
     }
     if (dup && me >= 0) sid[me] = ~v;
   }
+  // ---- processing order of the star kernel: the vertices of the grid's border cells first.  Hull
+  // vertices and their neighbours scan long strips of border cells (10x the median work); started
+  // first they overlap with the bulk instead of forming the kernel's tail.
+  {
+    int32_t* vorder = d.vorder + vb;
+    int nb = 0;  // border vertices so far
+    for (int pass = 0; pass < 2; ++pass) {
+      carry = pass ? nb : 0;
+      for (int base = 0; base < V; base += DSG_THREADS) {
+        const int v = base + tid;
+        int flag = 0;
+        if (v < V) {
+          const DsPt l = vxy[v];
+          const int cx = ds_cellx(in, l.x), cy = ds_celly(in, l.y);
+          const int border = (cx == 0 || cy == 0 || cx == gx - 1 || cy == gy - 1) ? 1 : 0;
+          flag = pass ? 1 - border : border;
+        }
+        int tot;
+        const int rank = carry + dsg_block_scan(flag, s_warp, &tot);
+        if (flag) vorder[rank] = v;
+        carry += tot;
+        __syncthreads();
+      }
+      if (!pass) nb = carry;
+    }
+  }
   if (tid == 0) {
     meta[DSG_GX] = gx; meta[DSG_GY] = gy; meta[DSG_SHIFT] = shift;
     meta[DSG_BX0] = s_box[0]; meta[DSG_BY0] = s_box[1]; meta[DSG_BX1] = s_box[2]; meta[DSG_BY1] = s_box[3];
@@ -234,16 +261,16 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
 }
 
 // ------------------------------------------------------------------------------------ k_ds_stars
-#define DSG_GROUPS 16  // vertices per CTA: 16 groups of 8 lanes
-__global__ void __launch_bounds__(DSG_GROUPS * 8)
+#define DSG_WARPS 4  // vertices per CTA: one warp each (the candidate cache takes ~7 KB per warp)
+__global__ void __launch_bounds__(DSG_WARPS * 32)
 k_ds_stars(DelGpu d, int s, int maxV) {
-  __shared__ DsScratch s_scr[DSG_GROUPS];
+  __shared__ DsScratch s_scr[DSG_WARPS];
   int32_t* meta = d.meta + (size_t)s * DSG_META;
   const int V = meta[DSG_NV];
-  const int g = threadIdx.x >> 3, lane = threadIdx.x & 7;
-  const int p = blockIdx.x * DSG_GROUPS + g;
-  if (p >= V) return;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x * DSG_WARPS + g >= V) return;
   const size_t vb = (size_t)s * maxV;
+  const int p = d.vorder[vb + blockIdx.x * DSG_WARPS + g];
   DsIn in;
   in.n = V;
   in.vxy = d.vxy + vb;
@@ -259,17 +286,17 @@ k_ds_stars(DelGpu d, int s, int maxV) {
   {
     const DsPt l = in.vxy[p];
     const int c = ds_celly(in, l.y) * in.gx + ds_cellx(in, l.x);
-    for (int k = in.cell_start[c] + lane; k < in.cell_start[c + 1]; k += 8)
+    for (int k = in.cell_start[c] + lane; k < in.cell_start[c + 1]; k += 32)
       if (in.sid[k] == ~p) dup = true;
-    dup = DsW8::any(dup);
+    dup = DsW32::any(dup);
   }
   if (!dup) {
-    const int rc = ds_star<DsW8>(in, p, &s_scr[g], star, &deg, &closed);
+    const int rc = ds_star<DsW32>(in, p, &s_scr[g], star, &deg, &closed);
     if (rc) {
       if (lane == 0) atomicOr(&meta[DSG_ERR], 1 << rc);
       deg = 0;
     }
-    DsW8::sync();
+    DsW32::sync();
     if (lane == 0) ds_counts(p, star, deg, closed, &od, &tc);
   }
   if (lane == 0) {

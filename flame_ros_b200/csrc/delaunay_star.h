@@ -109,22 +109,30 @@ struct DsSeq {  // host simulation: one lane
   DS_MEM void sync() {}
 };
 #ifdef __CUDACC__
-// Eight lanes per vertex, four vertices per warp: a star's candidate set is ~40 points, so 32 lanes
-// would idle through most passes and replicate the scalar set-up four times as often.
-struct DsW8 {
-  static const int LANES = 8;
-  __device__ __forceinline__ static unsigned mask() { return 0xffu << (threadIdx.x & 24); }
-  __device__ __forceinline__ static int lane() { return threadIdx.x & 7; }
-  __device__ __forceinline__ static int shfl_xor(int v, int o) { return __shfl_xor_sync(mask(), v, o, 8); }
-  __device__ __forceinline__ static long long shfl_xor(long long v, int o) { return __shfl_xor_sync(mask(), v, o, 8); }
-  __device__ __forceinline__ static int bcast(int v, int src) { return __shfl_sync(mask(), v, src, 8); }
-  __device__ __forceinline__ static bool any(bool p) { return __any_sync(mask(), p) != 0; }
-  __device__ __forceinline__ static void sync() { __syncwarp(mask()); }
+// One warp per vertex.  (Eight lanes per vertex, four vertices per warp, was measured and is 2x
+// slower: the four sweeps diverge at every data-dependent branch and serialise.)
+struct DsW32 {
+  static const int LANES = 32;
+  __device__ __forceinline__ static int lane() { return threadIdx.x & 31; }
+  __device__ __forceinline__ static int shfl_xor(int v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+  __device__ __forceinline__ static long long shfl_xor(long long v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+  __device__ __forceinline__ static int bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ __forceinline__ static bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+  __device__ __forceinline__ static void sync() { __syncwarp(); }
 };
 #endif
 
 // ------------------------------------------------------------------------------------ cell blocks
-#define DS_CACHE 128  // candidates of a block held in the group's scratch (larger blocks are re-read)
+#define DS_CACHE 512  // candidates of a block held in the group's scratch (larger blocks are re-read)
+#ifdef DS_STATS
+extern long long ds_stat_visits, ds_stat_passes, ds_stat_iters32;
+extern int ds_dbg_p;
+#define DS_STAT_PASS(blk, S) { if (ds_dbg_p >= 0) printf("  pass block [%d..%d]x[%d..%d] rows %d cache %d\n", (blk).x0, (blk).x1, (blk).y0, (blk).y1, (blk).nrows, (blk).ncache); ++ds_stat_passes; int t_ = 0; if ((blk).ncache >= 0) t_ = ((blk).ncache + 31) / 32; else for (int r_ = 0; r_ < (blk).nrows; ++r_) t_ += ((S)->rowcnt[r_] + 31) / 32; ds_stat_iters32 += t_; }
+#define DS_STAT_VISIT ++ds_stat_visits;
+#else
+#define DS_STAT_PASS(blk, S)
+#define DS_STAT_VISIT
+#endif
 struct DsBlock {
   int x0, y0, x1, y1;  // inclusive cell rectangle
   int nrows;           // rows of the row table (1 when the rectangle spans the full grid width)
@@ -139,11 +147,13 @@ struct DsScratch {
 };
 // for (every candidate of the block: id ID, coordinates PT) BODY -- lanes stride (SEQ = 0) or every
 // lane visits all (SEQ = 1).  `continue` inside BODY skips to the next candidate.
-#define DS_FOR_CAND(W, in, S, blk, SEQ, ID, PT, ...)                                              \
+#define DS_FOR_CAND(W, in, S, blk, SEQ, ID, PT, ...)  \
+  DS_STAT_PASS(blk, S)                                                                                                                        \
   if ((blk).ncache >= 0) {                                                                        \
     for (int k_ = (SEQ) ? 0 : W::lane(); k_ < (blk).ncache; k_ += (SEQ) ? 1 : W::LANES) {         \
       const int ID = (S)->cid[k_];                                                                \
       const DsPt PT = (S)->cxy[k_];                                                               \
+      DS_STAT_VISIT                                                                               \
       __VA_ARGS__                                                                                 \
     }                                                                                             \
   } else {                                                                                        \
@@ -152,6 +162,7 @@ struct DsScratch {
       for (int k_ = beg_ + ((SEQ) ? 0 : W::lane()); k_ < end_; k_ += (SEQ) ? 1 : W::LANES) {      \
         const int ID = (in).sid[k_];                                                              \
         const DsPt PT = (in).sxy[k_];                                                             \
+        DS_STAT_VISIT                                                                             \
         __VA_ARGS__                                                                               \
       }                                                                                           \
     }                                                                                             \
@@ -204,33 +215,56 @@ DS_FN void ds_block_rows(const DsIn& in, DsBlock& b, DsScratch* S) {
   }
 }
 
-// Grow the block to contain the lattice rectangle [rx0,rx1]x[ry0,ry1]; true when it changed.
+// Grow the block toward the lattice rectangle [rx0,rx1]x[ry0,ry1], each side by at most the block's
+// current extent (the rectangle usually comes from a provisional circle -- the best candidate of a
+// block that is still too small -- and shrinks drastically once nearer candidates are seen, so
+// jumping to it would scan a large part of the image for nothing).  True when the block changed,
+// false when it already covers the rectangle.
 DS_FN bool ds_block_cover(const DsIn& in, DsBlock& b, int64_t rx0, int64_t ry0, int64_t rx1, int64_t ry1) {
   const int nx0 = ds_cellx(in, rx0), nx1 = ds_cellx(in, rx1), ny0 = ds_celly(in, ry0), ny1 = ds_celly(in, ry1);
+  const int sx = b.x1 - b.x0 + 1, sy = b.y1 - b.y0 + 1;
   bool ch = false;
-  if (nx0 < b.x0) { b.x0 = nx0; ch = true; }
-  if (ny0 < b.y0) { b.y0 = ny0; ch = true; }
-  if (nx1 > b.x1) { b.x1 = nx1; ch = true; }
-  if (ny1 > b.y1) { b.y1 = ny1; ch = true; }
+  if (nx0 < b.x0) { b.x0 = nx0 > b.x0 - sx ? nx0 : b.x0 - sx; ch = true; }
+  if (ny0 < b.y0) { b.y0 = ny0 > b.y0 - sy ? ny0 : b.y0 - sy; ch = true; }
+  if (nx1 > b.x1) { b.x1 = nx1 < b.x1 + sx ? nx1 : b.x1 + sx; ch = true; }
+  if (ny1 > b.y1) { b.y1 = ny1 < b.y1 + sy ? ny1 : b.y1 + sy; ch = true; }
+  if (b.x0 < 0) b.x0 = 0;
+  if (b.y0 < 0) b.y0 = 0;
+  if (b.x1 > in.gx - 1) b.x1 = in.gx - 1;
+  if (b.y1 > in.gy - 1) b.y1 = in.gy - 1;
   return ch;
 }
 DS_FN bool ds_block_all(const DsIn& in, const DsBlock& b) {
   return b.x0 == 0 && b.y0 == 0 && b.x1 == in.gx - 1 && b.y1 == in.gy - 1;
 }
 
-// Bounding box of (closed disc through p, a, b) clipped to the bounding box of all points.
-// (p, a, b) counter-clockwise.  Conservative: rounded outward.
-DS_FN void ds_circle_region(const DsIn& in, DsPt p, DsPt a, DsPt b, int64_t* r) {
+// Bounding box of the part of the closed disc through (p, cur, best) that lies on the sweep side of
+// the chord p->cur, clipped to the bounding box of all points: the circular segment spanned by the
+// chord's endpoints and those of the circle's four axis-extreme points that are on the sweep side.
+// (Only sweep-side points can contradict `best`; for a sliver near the hull the segment is a thin
+// cap while the whole disc would cover half the image.)  Conservative: rounded outward.
+DS_FN void ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir, int64_t* r) {
+  // (p, a, b) counter-clockwise
+  const DsPt a = dir > 0 ? cur : best, b = dir > 0 ? best : cur;
   const double ax = (double)(a.x - p.x), ay = (double)(a.y - p.y), bx = (double)(b.x - p.x), by = (double)(b.y - p.y);
   const double d = 2.0 * (ax * by - ay * bx);  // > 0, exact
   const double a2 = ax * ax + ay * ay, b2 = bx * bx + by * by;
-  const double ux = (by * a2 - ay * b2) / d, uy = (ax * b2 - bx * a2) / d;
+  const double ux = (by * a2 - ay * b2) / d, uy = (ax * b2 - bx * a2) / d;  // centre - p
   const double rad = sqrt(ux * ux + uy * uy);
   const double m = 2.0 + rad * 1e-9 + (fabs(ux) + fabs(uy)) * 1e-9;
-  double x0 = (double)p.x + ux - rad - m, x1 = (double)p.x + ux + rad + m;
-  double y0 = (double)p.y + uy - rad - m, y1 = (double)p.y + uy + rad + m;
-  x0 = fmax(x0, (double)in.bx0); y0 = fmax(y0, (double)in.by0);
-  x1 = fmin(x1, (double)in.bx1); y1 = fmin(y1, (double)in.by1);
+  const double cx = (double)(cur.x - p.x), cy = (double)(cur.y - p.y);   // chord
+  const double tol = 1e-6 * (fabs(cx) + fabs(cy)) * (rad + 1.0) + 4.0;
+  double x0 = fmin(0.0, cx), x1 = fmax(0.0, cx), y0 = fmin(0.0, cy), y1 = fmax(0.0, cy);
+  const double ex[4] = {ux - rad, ux + rad, ux, ux}, ey[4] = {uy, uy, uy - rad, uy + rad};
+  for (int k = 0; k < 4; ++k) {
+    const double side = (cx * ey[k] - cy * ex[k]) * (double)dir;
+    if (side > -tol) {
+      x0 = fmin(x0, ex[k]); x1 = fmax(x1, ex[k]);
+      y0 = fmin(y0, ey[k]); y1 = fmax(y1, ey[k]);
+    }
+  }
+  x0 = fmax((double)p.x + x0 - m, (double)in.bx0); y0 = fmax((double)p.y + y0 - m, (double)in.by0);
+  x1 = fmin((double)p.x + x1 + m, (double)in.bx1); y1 = fmin((double)p.y + y1 + m, (double)in.by1);
   r[0] = (int64_t)floor(x0); r[1] = (int64_t)floor(y0); r[2] = (int64_t)ceil(x1); r[3] = (int64_t)ceil(y1);
 }
 
@@ -271,30 +305,59 @@ DS_FN bool ds_halfplane_region(const DsIn& in, DsPt p, DsPt cur, int dir, int64_
 template <class W>
 DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, DsBlock& blk, DsScratch* S,
                   DsPt* nxy, int* err) {
+  if (blk.ncache < 0) {
+    // the previous step needed a block too large for the cache (a sliver near the hull): this step
+    // starts from the 3x3 block again instead of dragging the large one along
+    const int cxp = ds_cellx(in, pp.x), cyp = ds_celly(in, pp.y);
+    blk.x0 = cxp > 0 ? cxp - 1 : 0; blk.x1 = cxp < in.gx - 1 ? cxp + 1 : in.gx - 1;
+    blk.y0 = cyp > 0 ? cyp - 1 : 0; blk.y1 = cyp < in.gy - 1 ? cyp + 1 : in.gy - 1;
+    ds_block_rows<W>(in, blk, S);
+  }
   for (int guard = 0; guard < 4 * DS_MAXROWS; ++guard) {
+    // One pass finds the best candidate AND whether other candidates lie on its circle: on the sweep
+    // side the discs through the chord (p, cur) are nested, so a candidate on the FINAL circle is
+    // either compared with a best that already has that circle (in-circle == 0: tie recorded) or
+    // becomes best itself and meets the others later.  A strictly better candidate shrinks the
+    // circle and clears the flag.
     int bid = -1;
+    bool tie = false;
     DsPt bxy = {0, 0};
     DS_FOR_CAND(W, in, S, blk, 0, id, c, {
       if (id < 0 || id == p || id == curid) continue;
       if (!ds_side(pp, cur, c, dir)) continue;
-      if (bid < 0 || ds_inside(pp, cur, bxy, c, dir) > 0) {
+      if (bid < 0) {
         bid = id;
         bxy = c;
+        continue;
+      }
+      const int r = ds_inside(pp, cur, bxy, c, dir);
+      if (r > 0) {
+        bid = id;
+        bxy = c;
+        tie = false;
+      } else if (r == 0) {
+        tie = true;
       }
     })
     for (int o = W::LANES >> 1; o > 0; o >>= 1) {
       const int oid = W::shfl_xor(bid, o);
+      const int otie = W::shfl_xor(tie ? 1 : 0, o);
       DsPt oxy;
       oxy.x = W::shfl_xor(bxy.x, o);
       oxy.y = W::shfl_xor(bxy.y, o);
-      if (oid >= 0 && oid != bid && (bid < 0 || ds_inside(pp, cur, bxy, oxy, dir) > 0)) {
-        bid = oid;
-        bxy = oxy;
+      if (oid < 0 || oid == bid) continue;
+      if (bid < 0) {
+        bid = oid; bxy = oxy; tie = otie != 0;
+        continue;
       }
+      const int r = ds_inside(pp, cur, bxy, oxy, dir);
+      if (r > 0) { bid = oid; bxy = oxy; tie = otie != 0; }
+      else if (r == 0) tie = true;
     }
-    bid = W::bcast(bid, 0);  // tied lanes may disagree: lane 0 decides
+    bid = W::bcast(bid, 0);  // tied lanes may disagree on the representative: lane 0 decides
     bxy.x = W::bcast(bxy.x, 0);
     bxy.y = W::bcast(bxy.y, 0);
+    tie = W::bcast(tie ? 1 : 0, 0) != 0;
     int64_t reg[4];
     if (bid < 0) {
       if (ds_block_all(in, blk) || !ds_halfplane_region(in, pp, cur, dir, reg)) return -1;
@@ -303,20 +366,14 @@ DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, 
       continue;
     }
     if (!ds_block_all(in, blk)) {
-      if (dir > 0) ds_circle_region(in, pp, cur, bxy, reg);
-      else ds_circle_region(in, pp, bxy, cur, reg);
+      ds_circle_region(in, pp, cur, bxy, dir, reg);
       if (ds_block_cover(in, blk, reg[0], reg[1], reg[2], reg[3])) {
         ds_block_rows<W>(in, blk, S);
         continue;
       }
     }
     // the circle (p, cur, best) is empty; other points ON it make a co-circular polygon
-    bool tie = false;
-    DS_FOR_CAND(W, in, S, blk, 0, id, c, {
-      if (id < 0 || id == p || id == curid || id == bid) continue;
-      if (ds_side(pp, cur, c, dir) && ds_inside(pp, cur, bxy, c, dir) == 0) tie = true;
-    })
-    if (W::any(tie)) {
+    if (tie) {
       // canonical fan from the smallest index (all lanes run the same sequential pass)
       int minid = p < curid ? p : curid;
       int cl = bid, fa = bid, mt = -1;

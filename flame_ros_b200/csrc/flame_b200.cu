@@ -1370,7 +1370,7 @@ extern "C" int fb_delaunay_device(fb_ctx* c, int s, int n, const float* pts, int
   FB_CUDA(c, cudaMemsetAsync(U->f_varcur + fb, 0, sizeof(float) * c->maxF, st));
   DsgSelect q{U->f_ucur + fb, U->f_varcur + fb, U->f_valid + fb, 1.0f, c->maxF, c->maxV, c->W, c->H};
   k_ds_prepare<<<1, DSG_THREADS, 0, st>>>(q, D, s, c->vfeat + vb, c->vpos + vb, D.f2v + fb, c->nV + s);
-  k_ds_stars<<<fb_div_up(c->maxV, DSG_GROUPS), DSG_GROUPS * 8, 0, st>>>(D, s, c->maxV);
+  k_ds_stars<<<fb_div_up(c->maxV, DSG_WARPS), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
   k_ds_scan<<<1, DSG_THREADS, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->row + (size_t)s * (c->maxV + 1), c->nE + s, c->nT + s);
   k_ds_emit<<<fb_div_up(c->maxV, 128), 128, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->vpos + vb, c->eij + eb, c->ec + eb,
                                                     c->tri + (size_t)s * c->maxT * 3);

@@ -208,7 +208,7 @@ static int update_alloc(fb_ctx* c) {
   A(dalloc(&U->o_vbar, c->maxV)); A(dalloc(&U->o_q4, c->maxE));
   A(dalloc(&U->map_v, c->maxV)); A(dalloc(&U->map_e, c->maxE));
   DelGpu& D = U->del;
-  A(dalloc(&D.vxy, nv)); A(dalloc(&D.sxy, nv)); A(dalloc(&D.sid, nv));
+  A(dalloc(&D.vxy, nv)); A(dalloc(&D.sxy, nv)); A(dalloc(&D.sid, nv)); A(dalloc(&D.vorder, nv));
   A(dalloc(&D.cell_start, S * (DSG_MAXCELLS + 1))); A(dalloc(&D.star, nv * DS_MAXD));
   A(dalloc(&D.deg, nv)); A(dalloc(&D.od, nv)); A(dalloc(&D.tc, nv));
   A(dalloc(&D.eoff, S * (c->maxV + 1))); A(dalloc(&D.toff, S * (c->maxV + 1)));
@@ -241,7 +241,7 @@ static void update_free(fb_ctx* c) {
   cudaFree(U->counts); cudaFree(U->o_x); cudaFree(U->o_w1); cudaFree(U->o_w2); cudaFree(U->o_vbar);
   cudaFree(U->o_q4); cudaFree(U->map_v); cudaFree(U->map_e);
   DelGpu& D = U->del;
-  cudaFree(D.vxy); cudaFree(D.sxy); cudaFree(D.sid); cudaFree(D.cell_start); cudaFree(D.star);
+  cudaFree(D.vxy); cudaFree(D.sxy); cudaFree(D.sid); cudaFree(D.vorder); cudaFree(D.cell_start); cudaFree(D.star);
   cudaFree(D.deg); cudaFree(D.od); cudaFree(D.tc); cudaFree(D.eoff); cudaFree(D.toff); cudaFree(D.meta);
   cudaFree(D.f2v); cudaFree(D.o_x); cudaFree(D.o_w1); cudaFree(D.o_w2); cudaFree(D.o_vbar);
   cudaFree(D.o_q4); cudaFree(D.o_eij); cudaFree(D.o_eoff);
@@ -352,7 +352,7 @@ static int update_graph_device(fb_ctx* c, int s) {
   k_ds_stash<<<64, 256, 0, st>>>(gg, D, s, c->maxV, c->maxE);
   DsgSelect q{U->f_ucur + fb, U->f_varcur + fb, U->f_valid + fb, p.idepth_var_max_graph, c->maxF, c->maxV, c->W, c->H};
   k_ds_prepare<<<1, DSG_THREADS, 0, st>>>(q, D, s, c->vfeat + vb, c->vpos + vb, D.f2v + par * nf + fb, c->nV + s);
-  k_ds_stars<<<fb_div_up(c->maxV, DSG_GROUPS), DSG_GROUPS * 8, 0, st>>>(D, s, c->maxV);
+  k_ds_stars<<<fb_div_up(c->maxV, DSG_WARPS), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
   k_ds_scan<<<1, DSG_THREADS, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->row + (size_t)s * (c->maxV + 1), c->nE + s, c->nT + s);
   k_ds_emit<<<fb_div_up(c->maxV, 128), 128, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->vpos + vb, c->eij + eb, c->ec + eb,
                                                     c->tri + (size_t)s * c->maxT * 3);

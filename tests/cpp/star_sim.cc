@@ -3,8 +3,14 @@
 // delaunay_gpu.cuh.  Test infrastructure: lets the CPU test-suite check the per-vertex star
 // algorithm against the host triangulator (fb_delaunay) and Qhull without a GPU.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
+#ifdef DS_STATS
+long long ds_stat_visits = 0, ds_stat_passes = 0, ds_stat_iters32 = 0;
+int ds_dbg_p = -1;
+#endif
 #include "../../flame_ros_b200/csrc/delaunay_star.h"
 
 extern "C" int star_sim_delaunay(int n, const float* pts, int cell_px, int32_t* tris, int32_t* n_tris,
@@ -68,7 +74,16 @@ extern "C" int star_sim_delaunay(int n, const float* pts, int cell_px, int32_t* 
   DsScratch scratch;
   for (int p = 0; p < n; ++p) {
     if (dup[p]) continue;
+#ifdef DS_STATS
+    const long long v0 = ds_stat_visits, p0 = ds_stat_passes, i0 = ds_stat_iters32;
+    ds_dbg_p = (getenv("DS_DBG_P") && atoi(getenv("DS_DBG_P")) == p) ? p : -1;
+    if (ds_dbg_p >= 0) printf("vertex %d at (%d,%d) cell (%d,%d) grid %dx%d shift %d bbox %d %d %d %d\n", p, vxy[p].x, vxy[p].y, ds_cellx(in, vxy[p].x), ds_celly(in, vxy[p].y), in.gx, in.gy, in.shift, in.bx0, in.by0, in.bx1, in.by1);
+#endif
     const int rc = ds_star<DsSeq>(in, p, &scratch, &star[(size_t)p * DS_MAXD], &deg[p], &closed[p]);
+#ifdef DS_STATS
+    if (getenv("DS_STATS_DUMP"))
+      printf("%d %lld %lld %lld %d %d\n", p, ds_stat_visits - v0, ds_stat_passes - p0, ds_stat_iters32 - i0, deg[p], closed[p]);
+#endif
     if (rc) return rc;
     ds_counts(p, &star[(size_t)p * DS_MAXD], deg[p], closed[p], &od[p], &tc[p]);
     if (max_deg) *max_deg = std::max(*max_deg, deg[p]);
