@@ -73,6 +73,7 @@ struct fb_ctx {
   struct ClusterPlan* plan = nullptr;
   struct GridPlan* gplan = nullptr;   // grid-resident solver tables (variant 3)
   struct UpdateState* upd = nullptr;  // fb_update pipeline state (flame_update.cuh)
+  struct TilePlan* tplan = nullptr;   // device-planned tile-resident solver (variant 5, nltgv2_tile.cuh)
 
   // ---- frames
   uint8_t* imgs = nullptr;  // [S][n_slots][H][W]

@@ -16,12 +16,16 @@
 #include "nltgv2_cluster.cuh"
 #include "nltgv2_grid.cuh"
 #include "nltgv2_coop.cuh"
+#include "nltgv2_tile.cuh"
 #include "raster.cuh"
 #include "frontend.cuh"
 
 static std::string g_create_error;
 static void update_free(fb_ctx* c);
 static void update_mark_host_graph(fb_ctx* c, int s);
+static void tile_plan_free(fb_ctx* c);
+static void tile_plan_mark(fb_ctx* c, int s);
+static bool fb_tile_failed(const fb_ctx* c);
 
 // ------------------------------------------------------------------------------------ helpers
 
@@ -95,6 +99,7 @@ static void free_all(fb_ctx* c) {
   cudaFree(c->owner); cudaFree(c->idmap);
   cluster_plan_free(c);
   grid_plan_free(c);
+  tile_plan_free(c);
   update_free(c);
   for (cudaGraphExec_t e : c->solve_exec) if (e) cudaGraphExecDestroy(e);
   cudaFree(c->coop_contrib); cudaFree(c->idmap_scratch);
@@ -218,6 +223,7 @@ extern "C" int fb_sync(fb_ctx* c) {
   CHECK_CTX(c);
   FB_CUDA(c, cudaStreamSynchronize(c->stream));
   if (grid_watchdog_fired(c)) FB_FAIL(c, FB_E_STATE, "grid-resident solver: mailbox exchange timed out (watchdog)");
+  if (fb_tile_failed(c)) FB_FAIL(c, FB_E_STATE, "tile-resident solver: a tile exceeded its capacity (nothing was solved)");
   return FB_OK;
 }
 
@@ -294,6 +300,7 @@ extern "C" int fb_graph_set(fb_ctx* c, int s, int V, int E, const float* pos,
   c->hV[s] = V;
   c->hE[s] = E;
   update_mark_host_graph(c, s);
+  tile_plan_mark(c, s);
   FB_CUDA(c, cudaMemcpyAsync(c->nV + s, &c->hV[s], sizeof(int32_t), cudaMemcpyHostToDevice, st));
   FB_CUDA(c, cudaMemcpyAsync(c->nE + s, &c->hE[s], sizeof(int32_t), cudaMemcpyHostToDevice, st));
   int rc = cluster_plan_build(c, s, V, E, eij.data(), row.data(), inc.data());
@@ -369,6 +376,7 @@ extern "C" int fb_graph_state_get(fb_ctx* c, int s, float* x, float* w, float* q
   if (xbar) FB_CUDA(c, cudaMemcpyAsync(vb4.data(), c->vbar + vb, sizeof(float4) * V, cudaMemcpyDeviceToHost, st));
   FB_CUDA(c, cudaStreamSynchronize(st));
   if (grid_watchdog_fired(c)) FB_FAIL(c, FB_E_STATE, "grid-resident solver: mailbox exchange timed out (watchdog)");
+  if (fb_tile_failed(c)) FB_FAIL(c, FB_E_STATE, "tile-resident solver: a tile exceeded its capacity (nothing was solved)");
   if (w) for (int v = 0; v < V; ++v) { w[2 * v] = w1[v]; w[2 * v + 1] = w2[v]; }
   if (q) for (int e = 0; e < E; ++e) { q[3 * e] = q4[e].x; q[3 * e + 1] = q4[e].y; q[3 * e + 2] = q4[e].z; }
   if (xbar) for (int v = 0; v < V; ++v) { xbar[3 * v] = vb4[v].x; xbar[3 * v + 1] = vb4[v].y; xbar[3 * v + 2] = vb4[v].z; }
@@ -418,6 +426,93 @@ static int solve_streaming(fb_ctx* c, int iters, const fb_nltgv2_params* p, int 
   ProfScope ps(c, FB_PROF_SOLVE);
   FB_CUDA(c, cudaGraphLaunch(c->solve_exec[slot], c->stream));
   c->launches += 2 * (int64_t)iters;
+  return FB_OK;
+}
+
+// ---- variant 5: tile-resident solver planned on the device (nltgv2_tile.cuh) ----------------------
+static void tile_plan_free(fb_ctx* c) {
+  TilePlan* T = c->tplan;
+  if (!T) return;
+  cudaFree(T->vtile); cudaFree(T->vloc); cudaFree(T->tlist); cudaFree(T->toff); cudaFree(T->lrow); cudaFree(T->derr);
+  if (T->err) cudaFreeHost(T->err);
+  delete T;
+  c->tplan = nullptr;
+}
+static void tile_plan_mark(fb_ctx* c, int s) {
+  if (c->tplan && s < (int)c->tplan->dirty.size()) c->tplan->dirty[s] = 1;
+}
+static bool fb_tile_failed(const fb_ctx* c) { return c->tplan && c->tplan->err && *c->tplan->err != 0; }
+// Allocates the plan and probes the launch configuration (cluster of 16, ~148 KB shared memory).
+static bool tile_available(fb_ctx* c) {
+  if (c->tplan && c->tplan->available >= 0) return c->tplan->available == 1;
+  if (!c->tplan) c->tplan = new TilePlan();
+  TilePlan* T = c->tplan;
+  T->available = 0;
+  if (const char* e = getenv("FB_TILE_DISABLE")) if (atoi(e)) return false;
+  // tiles hold V/16 vertices give or take the granularity of the split: keep 35 % head room
+  if ((long long)c->maxV * 100 > (long long)FBT_C * FBT_VCAP * 65) return false;
+  const size_t S = c->S, nv = S * c->maxV;
+  if (dalloc(&T->vtile, nv) != cudaSuccess || dalloc(&T->vloc, nv) != cudaSuccess || dalloc(&T->tlist, nv) != cudaSuccess ||
+      dalloc(&T->toff, S * (FBT_C + 1)) != cudaSuccess || dalloc(&T->lrow, nv) != cudaSuccess ||
+      dalloc(&T->derr, 1) != cudaSuccess || cudaMemset(T->derr, 0, sizeof(int)) != cudaSuccess ||
+      cudaHostAlloc((void**)&T->err, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  *T->err = 0;
+  T->dirty.assign(c->S, 1);
+  T->smem = fbt_smem_bytes();
+  const void* kern = (const void*)k_nltgv2_tile;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T->smem) != cudaSuccess ||
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaLaunchConfig_t q{};
+  q.gridDim = dim3(FBT_C);
+  q.blockDim = dim3(FBT_THREADS);
+  q.dynamicSmemBytes = T->smem;
+  cudaLaunchAttribute qa[1];
+  qa[0].id = cudaLaunchAttributeClusterDimension;
+  qa[0].val.clusterDim.x = FBT_C; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+  q.attrs = qa;
+  q.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  T->available = n >= 1 ? 1 : 0;
+  return T->available == 1;
+}
+
+static int solve_tile(fb_ctx* c, int iters, const fb_nltgv2_params* p, int only = -1) {
+  if (!tile_available(c)) FB_FAIL(c, FB_E_STATE, "fb_nltgv2_solve: the tile-resident solver is not available for this context");
+  TilePlan* T = c->tplan;
+  for (int s = 0; s < c->S; ++s) {
+    if ((only >= 0 && s != only) || !T->dirty[s]) continue;
+    k_tile_assign<<<1, 1024, 0, c->stream>>>(s, c->maxV, c->nV, c->vpos, T->vtile, T->vloc, T->tlist, T->toff);
+    c->launches++;
+    T->dirty[s] = 0;
+  }
+  TileArgs a;
+  a.g = graph_view(c);
+  a.g.only = only;
+  a.vtile = T->vtile; a.vloc = T->vloc; a.tlist = T->tlist; a.toff = T->toff; a.lrow = T->lrow; a.err = T->err; a.derr = T->derr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((only >= 0 ? 1 : c->S) * FBT_C));
+  cfg.blockDim = dim3(FBT_THREADS);
+  cfg.dynamicSmemBytes = T->smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = FBT_C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  float sq = p->step_q, sx = p->step_x, tl = p->step_x * p->data_factor, th = p->theta, x0 = p->x_min, x1 = p->x_max;
+  int itv = iters;
+  void* args[] = {&a, &itv, &sq, &sx, &tl, &th, &x0, &x1};
+  ProfScope ps(c, FB_PROF_SOLVE);
+  FB_CUDA(c, cudaLaunchKernelExC(&cfg, (const void*)k_nltgv2_tile, args));
+  c->launches++;
+  c->last_cluster = FBT_C;
   return FB_OK;
 }
 
@@ -495,11 +590,22 @@ static bool any_device_graph(const fb_ctx* c);
 
 extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, int variant) {
   CHECK_CTX(c);
-  if (!p || iters < 0 || variant < 0 || variant > 4) FB_FAIL(c, FB_E_ARG, "fb_nltgv2_solve: bad argument");
+  if (!p || iters < 0 || variant < 0 || variant > 5) FB_FAIL(c, FB_E_ARG, "fb_nltgv2_solve: bad argument");
   if (iters == 0) return FB_OK;
   int v = variant;
   const bool devg = any_device_graph(c);
   if (devg && (v == 2 || v == 3)) FB_FAIL(c, FB_E_STATE, "fb_nltgv2_solve: variants 2 / 3 need a host-set topology (fb_graph_set)");
+  if (v == 5 || (v == 0 && devg)) {
+    if (tile_available(c)) {
+      c->last_variant = 5;
+      const int rc = solve_tile(c, iters, p);
+      if (rc == FB_OK || v == 5) return rc;
+      cudaGetLastError();
+      c->tplan->available = 0;
+    } else if (v == 5) {
+      FB_FAIL(c, FB_E_STATE, "fb_nltgv2_solve: the tile-resident solver is not available for this context");
+    }
+  }
   if (v == 4 || (v == 0 && devg)) {
     coop_probe(c);
     if (c->coop_cluster) {
@@ -547,6 +653,12 @@ extern "C" int fb_nltgv2_solve(fb_ctx* c, int iters, const fb_nltgv2_params* p, 
 static int fb_nltgv2_solve_stream(fb_ctx* c, int s, int iters, const fb_nltgv2_params* p) {
   if (iters <= 0) return FB_OK;
   const int only = c->S > 1 ? s : -1;
+  if (tile_available(c)) {
+    c->last_variant = 5;
+    if (solve_tile(c, iters, p, only) == FB_OK) return FB_OK;
+    cudaGetLastError();  // launch refused: nothing ran
+    c->tplan->available = 0;
+  }
   coop_probe(c);
   if (c->coop_cluster) {
     c->last_variant = 4;

@@ -368,6 +368,7 @@ static int update_graph_device(fb_ctx* c, int s) {
   // per-topology tables of the resident solvers (variants 2 / 3) do not describe this graph
   if (c->plan && s < (int)c->plan->topo.size()) { c->plan->topo[s].V = 0; c->plan->topo[s].dirty = true; }
   if (c->gplan) { c->gplan->topo[s].dirty = true; c->gplan->topo[s].planned = 0; c->gplan->version++; }
+  tile_plan_mark(c, s);  // positions moved: the tiles of variant 5 are re-cut (one small kernel)
   return FB_OK;
 }
 
@@ -545,7 +546,7 @@ static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const f
     FB_CUDA(c, cudaMemcpyAsync(h, U->del.meta + (size_t)s * DSG_META, sizeof(int32_t) * DSG_META, cudaMemcpyDeviceToHost, st));
     FB_CUDA(c, cudaMemcpyAsync(h + DSG_META, misc, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA(c, cudaStreamSynchronize(st));
-    if (fb_coop_failed(c)) FB_FAIL(c, FB_E_STATE, "fb_update: resident solver rejected the graph size");
+    if (fb_coop_failed(c) || fb_tile_failed(c)) FB_FAIL(c, FB_E_STATE, "fb_update: resident solver rejected the graph size");
     const int err = h[DSG_ERR];
     c->hV[s] = h[DSG_NV];
     c->hE[s] = h[DSG_NE];

@@ -1,0 +1,355 @@
+// nltgv2_tile.cuh -- tile-resident NLTGV2-L1 solver planned ON THE DEVICE (variant 5).
+//
+// flame::Flame::update re-triangulates every frame and ~2 % of the edges change, so the per-topology
+// tables of variants 2 / 3 (built on the host in ~1 ms) can never be reused; variant 4 needs no tables
+// but moves ~1.9 MB per iteration through the L2 port of ONE GPC (a cluster lives in one GPC) and is
+// bound by it: 270 us per 50 iterations at 5.6k vertices (profiles/r2_update_launch_table_v1.md).
+// This variant gets the locality of variants 2 / 3 from a plan that costs one small kernel:
+//   k_tile_assign  (one CTA)  a balanced 4 x 4 k-d split of the vertex positions (4 vertical strips
+//                  of equal count, each cut into 4 parts of equal count): tile and in-tile index of
+//                  every vertex.  Tiles are compact, so ~90 % of the edges stay inside a tile.
+//   k_nltgv2_tile  one cluster of 16 CTAs per stream, CTA = tile.  The prologue derives everything
+//                  else in parallel from the CSR arrays already on the device (own edges = the
+//                  contiguous out-edge ranges of the own vertices, slot of every incidence = CSR
+//                  position), then all iterations run with the state in registers and the exchange in
+//                  shared memory: an edge thread reads the two extragradient points (the target's
+//                  through DSMEM when it lives in another tile) and stores the two K^T q contributions
+//                  into the CSR slots of its endpoints (the target's through DSMEM); a vertex thread
+//                  sums its slots in CSR order.  Two cluster barriers per iteration, no global memory
+//                  traffic inside the loop.
+// Arithmetic and summation order are those of nltgv2.cuh: results are bit-identical.
+#pragma once
+
+#include "common.cuh"
+#include "delaunay_gpu.cuh"
+#include "nltgv2.cuh"
+#include "nltgv2_cluster.cuh"
+
+#define FBT_THREADS 512
+#define FBT_VPT 2
+#define FBT_EPT 5
+#define FBT_VCAP (FBT_THREADS * FBT_VPT)   // vertices per tile
+#define FBT_ECAP (FBT_THREADS * FBT_EPT)   // out-edges per tile
+#define FBT_SLOTCAP 7168                   // incidences per tile
+#define FBT_C 16                           // tiles = cluster size
+#define FBT_TX 4
+#define FBT_TY 4
+#define FBT_BINS 64
+
+struct TilePlan {
+  int32_t* vtile = nullptr;  // [S*maxV] tile of every vertex
+  int32_t* vloc = nullptr;   // [S*maxV] index inside its tile
+  int32_t* tlist = nullptr;  // [S*maxV] vertex ids in tile order
+  int32_t* toff = nullptr;   // [S*(FBT_C+1)]
+  int32_t* lrow = nullptr;   // [S*maxV] slot base of every vertex inside its tile (written by the solver's prologue)
+  int* err = nullptr;        // mapped host flag: capacity exceeded
+  int* derr = nullptr;       // the same flag in device memory (read by every CTA after the prologue)
+  std::vector<char> dirty;   // per stream: positions / topology changed since the last k_tile_assign
+  int available = -1;        // -1 not probed, 0 no (cluster of 16 refused), 1 yes
+  size_t smem = 0;
+};
+
+static inline size_t fbt_smem_bytes() {
+  return sizeof(float4) * (FBT_VCAP + FBT_SLOTCAP) + sizeof(int) * (2 * (FBT_VCAP + 1) + 2 * FBT_VCAP) + 64;
+}
+
+// ------------------------------------------------------------------------------------ k_tile_assign
+__global__ void __launch_bounds__(1024)
+k_tile_assign(int s, int maxV, const int32_t* __restrict__ nV, const float2* __restrict__ vpos, int32_t* vtile,
+              int32_t* vloc, int32_t* tlist, int32_t* toff) {
+  __shared__ int s_box[4];
+  __shared__ int s_col[FBT_BINS], s_row[FBT_TX][FBT_BINS];
+  __shared__ int s_c2s[FBT_BINS];               // bin column -> strip
+  __shared__ int s_r2p[FBT_TX][FBT_BINS];       // (strip, bin row) -> part
+  __shared__ int s_cnt[FBT_C], s_off[FBT_C + 1];
+  const int tid = threadIdx.x;
+  const int V = nV[s];
+  const size_t vb = (size_t)s * maxV;
+  vpos += vb; vtile += vb; vloc += vb; tlist += vb; toff += (size_t)s * (FBT_C + 1);
+  if (tid == 0) { s_box[0] = s_box[1] = 0x7fffffff; s_box[2] = s_box[3] = -0x7fffffff; }
+  for (int k = tid; k < FBT_BINS; k += blockDim.x) s_col[k] = 0;
+  for (int k = tid; k < FBT_TX * FBT_BINS; k += blockDim.x) (&s_row[0][0])[k] = 0;
+  if (tid < FBT_C) s_cnt[tid] = 0;
+  __syncthreads();
+  for (int v = tid; v < V; v += blockDim.x) {
+    const float2 p = vpos[v];
+    const int x = (int)floorf(p.x * 16.0f), y = (int)floorf(p.y * 16.0f);
+    atomicMin(&s_box[0], x); atomicMin(&s_box[1], y); atomicMax(&s_box[2], x); atomicMax(&s_box[3], y);
+  }
+  __syncthreads();
+  const int x0 = s_box[0], y0 = s_box[1];
+  const long long wx = (long long)s_box[2] - x0 + 1, wy = (long long)s_box[3] - y0 + 1;
+#define FBT_BINX(p) (int)((((long long)floorf((p).x * 16.0f) - x0) * FBT_BINS) / wx)
+#define FBT_BINY(p) (int)((((long long)floorf((p).y * 16.0f) - y0) * FBT_BINS) / wy)
+  for (int v = tid; v < V; v += blockDim.x) atomicAdd(&s_col[FBT_BINX(vpos[v])], 1);
+  __syncthreads();
+  if (tid == 0) {  // strips of (nearly) equal count
+    int acc = 0, strip = 0;
+    for (int c = 0; c < FBT_BINS; ++c) {
+      while (strip < FBT_TX - 1 && acc >= (long long)(strip + 1) * V / FBT_TX) ++strip;
+      s_c2s[c] = strip;
+      acc += s_col[c];
+    }
+  }
+  __syncthreads();
+  for (int v = tid; v < V; v += blockDim.x) {
+    const float2 p = vpos[v];
+    atomicAdd(&s_row[s_c2s[FBT_BINX(p)]][FBT_BINY(p)], 1);
+  }
+  __syncthreads();
+  if (tid < FBT_TX) {  // each strip cut into parts of (nearly) equal count
+    int tot = 0;
+    for (int r = 0; r < FBT_BINS; ++r) tot += s_row[tid][r];
+    int acc = 0, part = 0;
+    for (int r = 0; r < FBT_BINS; ++r) {
+      while (part < FBT_TY - 1 && acc >= (long long)(part + 1) * tot / FBT_TY) ++part;
+      s_r2p[tid][r] = part;
+      acc += s_row[tid][r];
+    }
+  }
+  __syncthreads();
+  for (int v = tid; v < V; v += blockDim.x) {
+    const float2 p = vpos[v];
+    const int strip = s_c2s[FBT_BINX(p)];
+    const int t = strip * FBT_TY + s_r2p[strip][FBT_BINY(p)];
+    vtile[v] = t;
+    vloc[v] = atomicAdd(&s_cnt[t], 1);  // any order inside a tile: the arithmetic does not depend on it
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int t = 0; t < FBT_C; ++t) { s_off[t] = acc; acc += s_cnt[t]; }
+    s_off[FBT_C] = acc;
+  }
+  __syncthreads();
+  if (tid <= FBT_C) toff[tid] = s_off[tid];
+  for (int v = tid; v < V; v += blockDim.x) tlist[s_off[vtile[v]] + vloc[v]] = v;
+#undef FBT_BINX
+#undef FBT_BINY
+}
+
+// ------------------------------------------------------------------------------------ k_nltgv2_tile
+__device__ __forceinline__ float4 fbt_ld_cluster(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fbt_st_cluster(uint32_t a, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// Exclusive scan over the block (one value per thread), uniform total.
+__device__ __forceinline__ int fbt_block_scan(int v, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < nw ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  *total = s_warp[nw - 1];
+  return (wid ? s_warp[wid - 1] : 0) + incl - v;
+}
+
+struct TileArgs {
+  GraphView g;
+  const int32_t* vtile;
+  const int32_t* vloc;
+  const int32_t* tlist;
+  const int32_t* toff;
+  int32_t* lrow;
+  int* err;
+  int* derr;
+};
+
+__global__ void __launch_bounds__(FBT_THREADS, 1)
+k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float theta, float xmin, float xmax) {
+  extern __shared__ __align__(16) uint8_t fbt_smem[];
+  float4* s_bar = reinterpret_cast<float4*>(fbt_smem);           // [VCAP] extragradient points of the own vertices
+  float4* s_slot = s_bar + FBT_VCAP;                             // [SLOTCAP] K^T q contributions, CSR order per vertex
+  int* s_lrow = reinterpret_cast<int*>(s_slot + FBT_SLOTCAP);    // [VCAP+1] slot base
+  int* s_erow = s_lrow + FBT_VCAP + 1;                           // [VCAP+1] own-edge base
+  int* s_first = s_erow + FBT_VCAP + 1;                          // [VCAP] first out-edge (global id)
+  int* s_nin = s_first + FBT_VCAP;                               // [VCAP] in-degree
+  __shared__ int s_warp[32];
+  const GraphView& g = a.g;
+  const int tid = threadIdx.x;
+  const int r = (int)fbc_cluster_ctarank();
+  const int s = (g.only >= 0) ? g.only : (int)blockIdx.x / FBT_C;
+  const int nV = g.nV[s];
+  if (nV == 0) return;  // uniform over the cluster
+  const size_t vb = (size_t)s * g.maxV, eb = (size_t)s * g.maxE;
+  const int32_t* row = g.row + (size_t)s * (g.maxV + 1);
+  const int32_t* inc = g.inc + 2 * eb;
+  const int32_t* vtile = a.vtile + vb;
+  const int32_t* vloc = a.vloc + vb;
+  const int32_t* toff = a.toff + (size_t)s * (FBT_C + 1);
+  const int base = toff[r], nOwn = toff[r + 1] - base;
+  const int32_t* tl_ = a.tlist + vb + base;
+  int32_t* g_lrow = a.lrow + vb;
+
+  // ---- prologue 1: own vertices (state into registers, CSR bookkeeping into shared memory)
+  float vx[FBT_VPT], vw1[FBT_VPT], vw2[FBT_VPT], vz[FBT_VPT], vth[FBT_VPT];
+  int vid[FBT_VPT], vdeg[FBT_VPT], vrow[FBT_VPT];
+  int carry_s = 0, carry_e = 0;
+  const bool fits_v = nOwn <= FBT_VCAP;
+#pragma unroll
+  for (int k = 0; k < FBT_VPT; ++k) {
+    const int lv = tid + k * FBT_THREADS;
+    vid[k] = -1; vdeg[k] = 0; vrow[k] = 0;
+    vx[k] = vw1[k] = vw2[k] = vz[k] = vth[k] = 0.f;
+    int od = 0, nin = 0, first = 0;
+    if (fits_v && lv < nOwn) {
+      const int v = tl_[lv];
+      vid[k] = v;
+      const int r0 = row[v], r1 = row[v + 1];
+      vdeg[k] = r1 - r0;
+      while (nin < vdeg[k] && (inc[r0 + nin] & 1)) ++nin;  // in-edges come first (ascending edge id)
+      od = vdeg[k] - nin;
+      first = od ? (inc[r0 + nin] >> 1) : 0;
+      vx[k] = g.x[vb + v]; vw1[k] = g.w1[vb + v]; vw2[k] = g.w2[vb + v];
+      vz[k] = g.z[vb + v];
+      vth[k] = tl * g.wt[vb + v];
+      s_bar[lv] = g.vbar[vb + v];
+      s_first[lv] = first;
+      s_nin[lv] = nin;
+    }
+    int tot_s, tot_e;
+    // a vertex's slot block holds an odd number of 16-byte records: the gathers of a warp, whose
+    // lanes read their blocks at a stride of the (mostly equal) block size, then spread over all banks
+    const int ps = carry_s + fbt_block_scan(vdeg[k] ? (vdeg[k] | 1) : 0, s_warp, &tot_s);
+    const int pe = carry_e + fbt_block_scan(od, s_warp, &tot_e);
+    if (fits_v && lv < nOwn) {
+      s_lrow[lv] = ps;
+      s_erow[lv] = pe;
+      vrow[k] = ps;
+      g_lrow[vid[k]] = ps;
+    }
+    carry_s += tot_s;
+    carry_e += tot_e;
+  }
+  const int nSlot = carry_s, nEdge = carry_e;
+  if (tid == 0 && fits_v) { s_lrow[nOwn] = nSlot; s_erow[nOwn] = nEdge; }
+  if (tid == 0 && (!fits_v || nSlot > FBT_SLOTCAP || nEdge > FBT_ECAP)) {
+    atomicOr(a.derr, 1);
+    *reinterpret_cast<volatile int*>(a.err) = 1;
+  }
+  __threadfence();
+  fbc_cluster_sync();  // every tile's slot bases (global) and capacity verdict are visible
+  if (__ldcg(a.derr) != 0) return;  // uniform: nothing is solved once a tile did not fit (sticky, reported by the host)
+
+  // ---- prologue 2: own edges = the contiguous out-edge ranges of the own vertices
+  float q1[FBT_EPT], q2[FBT_EPT], q3[FBT_EPT], ea[FBT_EPT], ebt[FBT_EPT], dx[FBT_EPT], dy[FBT_EPT];
+  uint32_t a_bi[FBT_EPT], a_bj[FBT_EPT], a_sj[FBT_EPT];
+  int a_si[FBT_EPT], eid[FBT_EPT];
+  const uint32_t bar_u32 = fbc_smem_u32(s_bar), slot_u32 = fbc_smem_u32(s_slot);
+  const int kmax = (nEdge + FBT_THREADS - 1) / FBT_THREADS;  // uniform over the CTA
+#pragma unroll
+  for (int k = 0; k < FBT_EPT; ++k) {
+    eid[k] = -1;
+    q1[k] = q2[k] = q3[k] = ea[k] = ebt[k] = dx[k] = dy[k] = 0.f;
+    a_bi[k] = a_bj[k] = a_sj[k] = 0u;
+    a_si[k] = 0;
+    const int le = tid + k * FBT_THREADS;
+    if (le < nEdge) {
+      int lo = 0, hi = nOwn;  // largest lv with s_erow[lv] <= le
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_erow[mid] <= le) lo = mid; else hi = mid;
+      }
+      const int lv = lo, off = le - s_erow[lv];
+      const int e = s_first[lv] + off;
+      const int2 ij = g.eij[eb + e];
+      const float4 c = g.ec[eb + e];
+      const float4 q = g.q4[eb + e];
+      eid[k] = e;
+      ea[k] = c.x; ebt[k] = c.y; dx[k] = c.z; dy[k] = c.w;
+      q1[k] = q.x; q2[k] = q.y; q3[k] = q.z;
+      const int j = ij.y, tj = vtile[j], lj = vloc[j];
+      int pos = 0;  // position of e among j's incidences (in-edges, ascending edge id)
+      {
+        const int r0 = row[j], want = (e << 1) | 1;
+        while (inc[r0 + pos] != want) ++pos;
+      }
+      a_bi[k] = bar_u32 + 16u * (uint32_t)lv;
+      a_bj[k] = fbc_mapa(bar_u32 + 16u * (uint32_t)lj, (uint32_t)tj);
+      a_si[k] = s_lrow[lv] + s_nin[lv] + off;
+      a_sj[k] = fbc_mapa(slot_u32 + 16u * (uint32_t)(__ldcg(g_lrow + j) + pos), (uint32_t)tj);
+    }
+  }
+  fbc_cluster_sync();  // every tile's s_bar is filled before the first remote read
+
+  for (int it = 0; it < iters; ++it) {
+    // ---- dual half-step (nltgv2.cuh:k_dual_edges) + K^T q into the CSR slots of both endpoints
+    float4 bi[FBT_EPT], bj[FBT_EPT];
+#pragma unroll
+    for (int k = 0; k < FBT_EPT; ++k)
+      if (k < kmax && eid[k] >= 0) {
+        bi[k] = fbc_lds(a_bi[k]);
+        bj[k] = fbt_ld_cluster(a_bj[k]);
+      }
+#pragma unroll
+    for (int k = 0; k < FBT_EPT; ++k)
+      if (k < kmax && eid[k] >= 0) {
+        float t = bi[k].x - bj[k].x;
+        t = fmaf(-dx[k], bi[k].y, t);
+        t = fmaf(-dy[k], bi[k].z, t);
+        const float k1 = ea[k] * t;
+        const float k2 = ebt[k] * (bi[k].y - bj[k].y);
+        const float k3 = ebt[k] * (bi[k].z - bj[k].z);
+        q1[k] = fb_clamp1(fmaf(sigma, k1, q1[k]));
+        q2[k] = fb_clamp1(fmaf(sigma, k2, q2[k]));
+        q3[k] = fb_clamp1(fmaf(sigma, k3, q3[k]));
+        const float a1 = ea[k] * q1[k];
+        s_slot[a_si[k]] = make_float4(a1, fmaf(ebt[k], q2[k], -(dx[k] * a1)), fmaf(ebt[k], q3[k], -(dy[k] * a1)), 0.f);
+        fbt_st_cluster(a_sj[k], make_float4(-a1, -(ebt[k] * q2[k]), -(ebt[k] * q3[k]), 0.f));
+      }
+    fbc_cluster_sync();
+    // ---- primal half-step (nltgv2.cuh:k_primal_vertices): CSR-order sum, prox, box, extragradient
+#pragma unroll
+    for (int k = 0; k < FBT_VPT; ++k)
+      if (vid[k] >= 0) {
+        float gx = 0.f, g1 = 0.f, g2 = 0.f;
+        const float4* sl = s_slot + vrow[k];
+        for (int j = 0; j < vdeg[k]; ++j) {
+          const float4 c = sl[j];
+          gx += c.x;
+          g1 += c.y;
+          g2 += c.z;
+        }
+        const float xo = vx[k], w1o = vw1[k], w2o = vw2[k];
+        const float xp = fmaf(-tau, gx, xo);
+        const float w1n = fmaf(-tau, g1, w1o);
+        const float w2n = fmaf(-tau, g2, w2o);
+        const float d = xp - vz[k];
+        float xn = (d > vth[k]) ? (xp - vth[k]) : ((d < -vth[k]) ? (xp + vth[k]) : vz[k]);
+        xn = fminf(fmaxf(xn, xmin), xmax);
+        vx[k] = xn; vw1[k] = w1n; vw2[k] = w2n;
+        const float4 nb = make_float4(fmaf(theta, xn - xo, xn), fmaf(theta, w1n - w1o, w1n), fmaf(theta, w2n - w2o, w2n), 0.f);
+        s_bar[tid + k * FBT_THREADS] = nb;
+        if (it + 1 == iters) g.vbar[vb + vid[k]] = nb;
+      }
+    fbc_cluster_sync();
+  }
+#pragma unroll
+  for (int k = 0; k < FBT_EPT; ++k)
+    if (eid[k] >= 0) g.q4[eb + eid[k]] = make_float4(q1[k], q2[k], q3[k], 0.f);
+#pragma unroll
+  for (int k = 0; k < FBT_VPT; ++k)
+    if (vid[k] >= 0) {
+      const size_t v = vb + vid[k];
+      g.x[v] = vx[k]; g.w1[v] = vw1[k]; g.w2[v] = vw2[k];
+    }
+}

@@ -143,8 +143,11 @@ int fb_graph_x_get_all(fb_ctx* ctx, float* x_all);
  *          4 = plan-free resident kernel: one cluster per stream, state in registers, exchange
  *              through L2 behind the cluster barrier; needs no per-topology tables, so it serves
  *              graphs that change every frame (fb_update).
- * auto picks 3 when the batch fits, else 2, else 1 (4, else 1, for graphs built on the device by
- * fb_update).  All variants give bit-identical results. */
+ *          5 = tile-resident kernel planned on the device: a k-d split of the vertex positions
+ *              into 16 tiles (one small kernel), then one cluster of 16 CTAs per stream with the
+ *              state in registers and the exchange in (distributed) shared memory.
+ * auto picks 3 when the batch fits, else 2, else 1 (5, else 4, else 1, for graphs built on the device
+ * by fb_update).  All variants give bit-identical results. */
 int fb_nltgv2_solve(fb_ctx* ctx, int iters, const fb_nltgv2_params* p, int variant);
 /* nltgv2_total_{smoothness,data}_cost (/root/reference/src/utils.cc:131-136); synchronises. */
 int fb_costs(fb_ctx* ctx, int stream, float data_factor, double* smoothness, double* data);

@@ -85,6 +85,6 @@ def test_update_device_and_host_graph_paths_agree(capi, win, n_frames):
         assert np.array_equal(np.nan_to_num(a["fmap"], nan=-1), np.nan_to_num(b["fmap"], nan=-1)), "frame %d filtered" % k
         assert a["nv"] == b["nv"]
     assert n_upd >= n_frames - 5
-    assert res[0][-1]["variant"] == 4      # plan-free resident solver on the device-built graph
+    assert res[0][-1]["variant"] == 5      # device-planned tile-resident solver on the device-built graph
     if win == 8:
         assert res[0][-1]["nv"] > 3000

@@ -18,7 +18,7 @@ def linf(a, b):
     return max(float(np.max(np.abs(a[k] - b[k]))) for k in STATE_KEYS if len(a[k]))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("iters", [1, 10, 50])
 def test_small_graph_parity(capi, oracle, variant, iters):
     g = small_graph()
@@ -32,7 +32,7 @@ def test_small_graph_parity(capi, oracle, variant, iters):
     assert np.array_equal(ref["x"], got["x"]), "expected bit-exact x (same expression order)"
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 def test_c2_graph_parity_50_iters(capi, oracle, variant):
     g = synth.s_graph("C2")
     ref = run_oracle(oracle, g, 50)
@@ -175,7 +175,7 @@ def test_warm_start_roundtrip(capi, oracle):
     assert linf(ref, got) < TOL
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 def test_batched_streams_block_diagonal(capi, oracle, variant):
     """Different graphs in different streams of one context: one launch, independent results."""
     graphs = [small_graph(10 + 2 * s, 8 + s, 96, 72, seed=20 + s) for s in range(3)]
@@ -287,5 +287,26 @@ def test_plan_free_solver_two_instantiations_and_warm_restart(capi, oracle):
         ctx.nltgv2_solve(10, variant=4)
         ctx.nltgv2_solve(20, variant=4)
         assert ctx.last_solver_variant() == 4
+        got = ctx.graph_state_get(0)
+    assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
+
+
+def test_device_planned_tile_solver_on_irregular_graphs(capi, oracle):
+    """Variant 5 (k-d tiles cut on the device, CSR slots in distributed shared memory): clustered point
+    sets give unbalanced densities, hubs and long edges; consecutive launches re-use the tiles."""
+    rng = np.random.default_rng(7)
+    pts = np.concatenate([rng.normal([150, 120], 12, (900, 2)), rng.normal([480, 300], 60, (1500, 2)),
+                          rng.uniform(8, [632, 472], (1200, 2))]).astype(np.float32)
+    pts = np.clip(pts, 1, [638, 478]).astype(np.float32)
+    tris, edges = capi.delaunay(pts)
+    alpha, beta = synth.edge_weights(pts, edges)
+    z = (0.5 + 0.2 * pts[:, 0] / 640 + rng.laplace(0, 0.02, len(pts))).astype(np.float32)
+    g = dict(pos=pts, edges=edges, alpha=alpha, beta=beta, z=z, wt=np.ones(len(z), np.float32))
+    ref = run_oracle(oracle, g, 40)
+    with capi.Context(1, 640, 480, 2, 16, 4096, 12288) as ctx:
+        gpu_load_graph(ctx, 0, g)
+        ctx.nltgv2_solve(15, variant=5)
+        ctx.nltgv2_solve(25, variant=5)
+        assert ctx.last_solver_variant() == 5
         got = ctx.graph_state_get(0)
     assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
