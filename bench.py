@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="solver variant: 0 auto, 1 streaming, 2 cluster, 3 grid-resident")
     ap.add_argument("--no-single", action="store_true", help="skip the extra single-stream measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-update", action="store_true", help="skip the full-pipeline (fb_update) leg")
+    ap.add_argument("--update-streams", type=int, default=8, help="independent flame::Flame instances per GPU in the e2e_update leg")
+    ap.add_argument("--update-frames", type=int, default=36, help="timed frames per stream in the e2e_update leg")
     return ap.parse_args()
 
 
@@ -375,6 +378,29 @@ def gpu_main(args):
                   "solver_us_per_frame": 1e3 * ms1 / max(c1, 1),
                   "roofline_frac": (datas[0].algorithmic_bytes_per_iter() * iters / (1e6 * ms1 / max(c1, 1))) / peak}
 
+    upd = None
+    if not args.no_update:
+        u = update_leg_gpu(capi, args, rank, local_rank, barrier)
+        tu_all, tu_one = max_over_ranks(u["t_all"]), max_over_ranks(u["t_one"])
+        launches += u["launches"]
+        upd = {"value": world * u["S"] * u["K"] / tu_all, "unit": UNIT, "streams_per_gpu": u["S"],
+               "frames_per_stream": u["K"], "warmup_frames": WL.UPD_WARMUP,
+               "ms_per_frame_per_stream": 1e3 * tu_all / u["K"],
+               "single_stream": {"value": world * u["K"] / tu_one, "ms_per_frame": 1e3 * tu_one / u["K"], "unit": UNIT},
+               "h2d_bytes_per_frame": u["h2d"], "d2h_bytes_per_frame": u["d2h"],
+               "vertices": u["stats"].get("vertices"), "triangles": u["stats"].get("tris"),
+               "coverage": u["stats"].get("coverage"),
+               "solver_variant": {1: "streaming", 4: "plan-free resident (cluster, L2 exchange)",
+                                  5: "tile-resident, planned on the device (cluster of 16, DSMEM exchange)"}.get(u["stats"].get("variant"), u["stats"].get("variant")),
+               "call": "per frame and stream: fb_update(host gray image, pose, is_poseframe every 6th) = flame::Flame::update "
+                       "(/root/reference/src/flame_nodelet.cc:634), then fb_get_idepthmap(filter) = getFilteredInverseDepthMap "
+                       "(:682-683) into pinned host memory; one context + one host thread per stream; detection window 8 px "
+                       "(~5.5k Delaunay vertices), 50 PD iterations per frame, topology rebuilt on the device every frame"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            upd["cpu_baseline"] = cpu_update_baseline(u["datas"], frames=min(12, u["K"]))
+            upd["vs_cpu_baseline"] = upd["value"] / upd["cpu_baseline"]["value"]
+        del u
+
     t_res, t_e2e, t_sync = max_over_ranks(t_res), max_over_ranks(t_e2e), max_over_ranks(t_sync)
     launches_all = int(sum_over_ranks(launches))
     frames = world * S * args.steps
@@ -430,6 +456,8 @@ def gpu_main(args):
         }
         if single:
             out["single_stream"] = single
+        if upd:
+            out["e2e_update"] = upd
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # the CPU baseline is an N=1 figure
         out["cpu_baseline"] = cpu_baseline(args, datas, sample_steps=3)
     if world > 1:
@@ -438,6 +466,156 @@ def gpu_main(args):
     if rank == 0:
         print(json.dumps(out))
 
+
+
+# --------------------------------------------------------------------------------------- full pipeline (fb_update)
+class UpdateRun:
+    """The reference-facing call: one context per camera stream (= one flame::Flame), one host thread
+    each, every frame goes  host image -> fb_update (frame upload, epipolar update, projection, device
+    triangulation, graph sync, 50 NLTGV2 iterations, interpolation, detection on poseframes) ->
+    fb_get_idepthmap with the display filters (getFilteredInverseDepthMap) into host memory."""
+
+    def __init__(self, capi, datas, device, triangulator=0):
+        self.capi, self.datas, self.S = capi, datas, len(datas)
+        d0 = datas[0]
+        self.ctxs, self.h_frames, self.h_map = [], [], []
+        self.filter = capi.default_tri_filter_params()
+        up = capi.default_update_params()
+        up.detection_win_size, up.iters, up.triangulator = d0.win, d0.iters, triangulator
+        for d in datas:
+            ctx = capi.Context(1, d.W, d.H, WL.UPD_N_SLOTS, WL.UPD_MAX_FEATURES, WL.UPD_MAX_VERTICES,
+                               3 * WL.UPD_MAX_VERTICES, device=device)
+            ctx.set_intrinsics(0, d.K)
+            ctx.set_update_params(up)
+            hf = capi.PinnedBuffer((d.n_frames, d.H, d.W), np.uint8)   # frames as a capture driver delivers them
+            np.copyto(hf.array, d.frames)
+            self.ctxs.append(ctx)
+            self.h_frames.append(hf)
+            self.h_map.append(capi.PinnedBuffer((d.H, d.W), np.float32))
+        self.stats = [dict() for _ in datas]
+
+    def _frames(self, s, k0, k1):
+        ctx, d, hf, hm = self.ctxs[s], self.datas[s], self.h_frames[s].array, self.h_map[s].array
+        chk = 0.0
+        for k in range(k0, k1):
+            ok = ctx.update(0, k / 30.0, k, d.poses[k], hf[k], k % WL.UPD_POSEFRAME_EVERY == 0)
+            if ok:
+                ctx.get_idepthmap(0, self.filter, out=hm)
+                chk += float(hm[d.H // 2, d.W // 2] == hm[d.H // 2, d.W // 2])   # the consumer's read
+        self.stats[s] = dict(vertices=ctx.get_stat(0, "num_vtx"), tris=ctx.get_stat(0, "num_tris"),
+                             coverage=ctx.get_stat(0, "coverage"), variant=ctx.last_solver_variant())
+        return chk
+
+    def run(self, k0, k1, streams=None):
+        """Frames [k0, k1) of the chosen streams, one host thread per stream; returns wall seconds."""
+        from concurrent.futures import ThreadPoolExecutor
+        streams = list(range(self.S)) if streams is None else streams
+        if len(streams) == 1:
+            t0 = time.perf_counter()
+            self._frames(streams[0], k0, k1)
+            return time.perf_counter() - t0
+        with ThreadPoolExecutor(len(streams)) as ex:
+            t0 = time.perf_counter()
+            list(ex.map(lambda s: self._frames(s, k0, k1), streams))
+            return time.perf_counter() - t0
+
+    def launches(self):
+        return sum(c.launch_count() for c in self.ctxs)
+
+    def close(self):
+        for c in self.ctxs:
+            c.sync()
+            c.close()
+        for b in self.h_frames + self.h_map:
+            b.free()
+
+
+def update_leg_gpu(capi, args, rank, local_rank, barrier):
+    """e2e_update: frames/s through fb_update + getFilteredInverseDepthMap, host image in, dense map out."""
+    S, K = args.update_streams, args.update_frames
+    n_frames = WL.UPD_WARMUP + K
+    datas = WL.update_streams(args.config, [1000 + rank * S + s for s in range(S)], n_frames)
+    run = UpdateRun(capi, datas, local_rank)
+    run.run(0, WL.UPD_WARMUP)
+    barrier()
+    l0 = run.launches()
+    t_all = run.run(WL.UPD_WARMUP, n_frames)
+    launches = run.launches() - l0
+    stats = run.stats[0]
+    run.close()
+    # one camera alone (the reference's own use: a single flame::Flame)
+    run1 = UpdateRun(capi, datas[:1], local_rank)
+    run1.run(0, WL.UPD_WARMUP)
+    barrier()
+    t_one = run1.run(WL.UPD_WARMUP, n_frames)
+    run1.close()
+    d0 = datas[0]
+    return dict(S=S, K=K, t_all=t_all, t_one=t_one, launches=launches, stats=stats, datas=datas,
+                h2d=d0.W * d0.H + 28, d2h=4 * d0.W * d0.H)
+
+
+class CpuUpdateRun:
+    """The same frames through the oracle's C restatement of the whole pipeline (oracle/flame_pipeline.c):
+    one pipeline per stream, streams in parallel host threads x OpenMP threads inside the stages."""
+
+    def __init__(self, datas, cores):
+        from oracle import oracle as O
+        self.O, self.datas, self.S = O, datas, len(datas)
+        self.native = True
+        try:
+            O.load(native=True)
+        except Exception:
+            self.native = False
+            O.load()
+        self.par = min(self.S, cores)
+        self.nthreads = max(1, cores // self.par)
+        up = O.UpdateParams.default()
+        up.detection_win_size, up.iters = datas[0].win, datas[0].iters
+        self.filter = O.TriFilterParams.default()
+        self.pipes = [O.Pipeline(d.W, d.H, d.K, WL.UPD_N_SLOTS, WL.UPD_MAX_FEATURES, WL.UPD_MAX_VERTICES, up,
+                                 nthreads=self.nthreads, native=self.native) for d in datas]
+        self.stage = None
+
+    def _frames(self, s, k0, k1):
+        p, d = self.pipes[s], self.datas[s]
+        acc = {}
+        for k in range(k0, k1):
+            if p.update(k, d.poses[k], d.frames[k], k % WL.UPD_POSEFRAME_EVERY == 0):
+                p.idepthmap(self.filter)
+            for key, v in p.stage_ms().items():
+                acc[key] = acc.get(key, 0.0) + v
+        if s == 0:
+            self.stage = {k: v / max(1, k1 - k0) for k, v in acc.items()}
+
+    def run(self, k0, k1):
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(self.par) as ex:
+            t0 = time.perf_counter()
+            list(ex.map(lambda s: self._frames(s, k0, k1), range(self.S)))
+            return time.perf_counter() - t0
+
+    def close(self):
+        for p in self.pipes:
+            p.close()
+
+
+def cpu_update_baseline(datas, frames):
+    """Bounded sample of the e2e_update workload on the host cores: the same warm-up, then `frames`
+    timed frames per stream."""
+    cores = host_cores()
+    run = CpuUpdateRun(datas, cores)
+    run.run(0, WL.UPD_WARMUP)
+    dt = run.run(WL.UPD_WARMUP, WL.UPD_WARMUP + frames)
+    m = run.pipes[0].mesh()
+    out = {"value": len(datas) * frames / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "ms_per_frame_per_stream": 1e3 * dt / frames, "vertices": int(len(m["vtx"])),
+           "stage_ms_stream0": {k: round(v, 3) for k, v in (run.stage or {}).items()},
+           "sample": "%d timed frames x %d streams after the same %d warm-up frames; oracle/flame_pipeline.c "
+                     "(whole pipeline incl. its own Delaunay triangulator and getFilteredInverseDepthMap; %s), %d streams in "
+                     "parallel x %d OpenMP threads; this repo's restatement of FLaME, not robustrobotics/flame itself"
+                     % (frames, len(datas), WL.UPD_WARMUP, "-O3 -march=native" if run.native else "portable -O2", run.par, run.nthreads)}
+    run.close()
+    return out
 
 # --------------------------------------------------------------------------------------- CPU arm
 class CpuRun:
@@ -549,6 +727,13 @@ def reference_main(args):
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
+    if not args.no_update:
+        # the same full-pipeline workload as the GPU arm's e2e_update leg, on the host cores
+        Su = args.update_streams
+        frames = min(12, args.update_frames)
+        udatas = WL.update_streams(args.config, [1000 + s for s in range(Su)], WL.UPD_WARMUP + frames)
+        out["e2e_update"] = cpu_update_baseline(udatas, frames)
+        out["e2e_update"]["streams_per_gpu"] = Su
     print(json.dumps(out))
 
 

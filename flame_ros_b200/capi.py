@@ -466,8 +466,11 @@ class Context:
             raise FlameError("fb_delaunay_device: rc %d (%s)" % (rc, self._lib.fb_last_error(self._h).decode()))
         return tris[:nt.value].copy(), edges[:ne.value].copy()
 
-    def get_idepthmap(self, stream, filter_params=None):
-        out = np.zeros((self.H, self.W), np.float32)
+    def get_idepthmap(self, stream, filter_params=None, out=None):
+        """getInverseDepthMap / getFilteredInverseDepthMap; `out` may be a (pinned) float32 [H,W] array."""
+        if out is None:
+            out = np.zeros((self.H, self.W), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.H * self.W
         fp = C.byref(filter_params) if filter_params is not None else None
         self._ck(self._lib.fb_get_idepthmap(self._h, stream, fp, _ptr(out)))
         return out

@@ -64,3 +64,44 @@ def schedule(step):
 
 CMP_SLOT = 2
 N_SLOTS = 4   # 2 alternating poseframe slots + 2 alternating current-frame slots (pipelined uploads)
+
+
+# ---- the full-pipeline workload: flame::Flame::update driven frame by frame ------------------------
+UPD_WARMUP = 18        # frames until the graph is populated (3 poseframes at subsample factor 6)
+UPD_POSEFRAME_EVERY = 6   # poseframe_subsample_factor, /root/reference/cfg/flame_nodelet.yaml:6
+UPD_N_SLOTS = 8        # poseframe ring of 7 + the current frame
+UPD_MAX_FEATURES = 8192
+UPD_MAX_VERTICES = 8192
+
+
+def _render_stream(args):
+    config, seed, n_frames = args
+    W, H, K, win, nv, iters = CONFIGS[config]
+    sc = synth.Scene(seed, tex_size=1024)
+    poses = synth.stream_poses(n_frames)
+    return np.stack([sc.render(np.asarray(K, np.float32), poses[k], W, H)[0] for k in range(n_frames)]), poses
+
+
+class UpdateStreamData:
+    """Image + pose stream for the whole per-frame pipeline (detection .. dense map): the same scene,
+    camera and detection window as the hot-path workload, n_frames consecutive frames."""
+
+    def __init__(self, config, seed, n_frames, rendered=None):
+        W, H, K, win, nv, iters = CONFIGS[config]
+        self.W, self.H, self.K, self.win, self.iters = W, H, np.asarray(K, np.float32), win, iters
+        self.frames, self.poses = rendered if rendered is not None else _render_stream((config, seed, n_frames))
+        self.n_frames = n_frames
+
+
+def update_streams(config, seeds, n_frames, workers=None):
+    """Render several streams in parallel worker processes (the renderer is single-threaded numpy)."""
+    import concurrent.futures as cf
+    import os
+    jobs = [(config, s, n_frames) for s in seeds]
+    workers = workers or min(len(jobs), len(os.sched_getaffinity(0)))
+    if workers <= 1 or len(jobs) == 1:
+        res = [_render_stream(j) for j in jobs]
+    else:
+        with cf.ProcessPoolExecutor(workers) as ex:
+            res = list(ex.map(_render_stream, jobs))
+    return [UpdateStreamData(config, s, n_frames, rendered=r) for s, r in zip(seeds, res)]

@@ -210,6 +210,10 @@ void fo_rasterize_idepth(int W, int H, int V, const float* vtx, const float* ide
                          int T, const int32_t* tri, const uint8_t* valid /*NULL = all*/,
                          float* idepthmap /*[H][W]*/);
 
+/* Same result with the image cut into `nthreads` horizontal bands (OpenMP). */
+void fo_rasterize_idepth_mt(int W, int H, int V, const float* vtx, const float* idepth, int T,
+                            const int32_t* tri, const uint8_t* valid, float* idepthmap, int nthreads);
+
 /* ------------------------------------- triangulation (flame_pipeline.c)    */
 /*
  * Delaunay triangulation of n pixel positions (snapped to a 1/64 px lattice, exact predicates):

@@ -563,7 +563,7 @@ int fo_pipeline_update(fo_pipeline* P, int img_id, const float* pose, const uint
       fo_nltgv2_solve(V, nE, P->n_pos, P->n_edges, P->n_alpha, P->n_beta, P->n_z, P->n_wt, st[0], st[1], st[2], st[3],
                       st[4], st[5], st[6], st[7], st[8], &up->rparams, up->iters, P->nthreads);
     FO_LAP(FO_STAGE_SOLVE);
-    fo_rasterize_idepth(W, H, V, P->n_pos, st[0], nT, P->n_tris, NULL, P->idmap);
+    fo_rasterize_idepth_mt(W, H, V, P->n_pos, st[0], nT, P->n_tris, NULL, P->idmap, P->nthreads);
     FO_LAP(FO_STAGE_INTERP);
     /* commit */
     P->V = V; P->E = nE; P->T = nT; P->have_graph = 1;
@@ -618,7 +618,7 @@ void fo_pipeline_idepthmap(const fo_pipeline* P, const fo_tri_filter_params* fil
   }
   uint8_t* valid = (uint8_t*)malloc((size_t)P->T > 0 ? (size_t)P->T : 1);
   fo_triangle_validity(P->W, P->H, P->K, P->V, P->pos, P->x, P->T, P->tris, filter, valid);
-  fo_rasterize_idepth(P->W, P->H, P->V, P->pos, P->x, P->T, P->tris, valid, out);
+  fo_rasterize_idepth_mt(P->W, P->H, P->V, P->pos, P->x, P->T, P->tris, valid, out, P->nthreads);
   free(valid);
 }
 
