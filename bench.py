@@ -397,7 +397,7 @@ def gpu_main(args):
                        "(:682-683) into pinned host memory; one context + one host thread per stream; detection window 8 px "
                        "(~5.5k Delaunay vertices), 50 PD iterations per frame, topology rebuilt on the device every frame"}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            upd["cpu_baseline"] = cpu_update_baseline(u["datas"], frames=min(12, u["K"]))
+            upd["cpu_baseline"] = cpu_update_baseline(u["datas"], frames=u["K"])   # the same frames as the GPU leg
             upd["vs_cpu_baseline"] = upd["value"] / upd["cpu_baseline"]["value"]
         del u
 
@@ -730,7 +730,7 @@ def reference_main(args):
     if not args.no_update:
         # the same full-pipeline workload as the GPU arm's e2e_update leg, on the host cores
         Su = args.update_streams
-        frames = min(12, args.update_frames)
+        frames = args.update_frames
         udatas = WL.update_streams(args.config, [1000 + s for s in range(Su)], WL.UPD_WARMUP + frames)
         out["e2e_update"] = cpu_update_baseline(udatas, frames)
         out["e2e_update"]["streams_per_gpu"] = Su

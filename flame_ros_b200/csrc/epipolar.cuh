@@ -31,8 +31,8 @@ __device__ __forceinline__ void fb_quat_to_R(const float* q, float* R) {
 
 __global__ void k_epi_geometry(const float* __restrict__ poses, const float* __restrict__ Ks,
                                const int32_t* __restrict__ cmp_slot, int n_slots,
-                               float* __restrict__ geo) {
-  const int s = blockIdx.x, slot = threadIdx.x;
+                               float* __restrict__ geo, int s0 = 0) {
+  const int s = s0 + blockIdx.x, slot = threadIdx.x;  // s0: first stream of the launch
   if (slot >= n_slots) return;
   const int cs = cmp_slot[s];
   if (cs < 0) return;
@@ -123,6 +123,7 @@ struct EpiArgs {
   const int32_t* nF;
   int32_t* counters;
   int W, H, n_slots, maxF;
+  int s0;  // first stream of the launch (blockIdx.y counts from it)
   fb_epi_params p;
 };
 
@@ -279,7 +280,7 @@ __device__ int fb_epi_update_one(const EpiArgs& a, const uint8_t* __restrict__ i
 // dynamic smem = warps * FB_EPI_GROUPS * (2*max_search + 2*FB_MAX_WIN + 2) floats
 __global__ void __launch_bounds__(256) k_epipolar_search(EpiArgs a) {
   extern __shared__ float smem[];
-  const int s = blockIdx.y;
+  const int s = a.s0 + blockIdx.y;
   const int wlane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int group = wlane / FB_EPI_LANES, lane = wlane % FB_EPI_LANES;
   const unsigned gmask = (FB_EPI_LANES == 32 ? 0xffffffffu : ((1u << FB_EPI_LANES) - 1u)) << (group * FB_EPI_LANES);

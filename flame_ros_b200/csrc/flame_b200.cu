@@ -23,6 +23,7 @@
 static std::string g_create_error;
 static void update_free(fb_ctx* c);
 static void update_mark_host_graph(fb_ctx* c, int s);
+static void update_invalidate_graphs(fb_ctx* c);
 static void tile_plan_free(fb_ctx* c);
 static void tile_plan_mark(fb_ctx* c, int s);
 static bool fb_tile_failed(const fb_ctx* c);
@@ -243,6 +244,7 @@ extern "C" int fb_set_epi_params(fb_ctx* c, const fb_epi_params* p) {
       p->max_search_px < 8 || p->max_search_px > FB_MAX_SEARCH || p->ambiguity_radius < 0)
     FB_FAIL(c, FB_E_ARG, "fb_set_epi_params: win_size must be odd in [3,15], max_search_px in [8,256]");
   c->epi = *p;
+  update_invalidate_graphs(c);  // the parameters are baked into the captured frame
   return FB_OK;
 }
 
@@ -903,6 +905,7 @@ extern "C" int fb_idepth_update(fb_ctx* c, const int32_t* cmp_slot) {
   a.ref_slot = c->f_ref; a.mu = c->f_mu; a.var = c->f_var; a.dropouts = c->f_drop;
   a.alive = c->f_alive; a.status = c->f_status; a.u_cmp = c->f_ucmp; a.nF = c->nF;
   a.counters = c->counters; a.W = c->W; a.H = c->H; a.n_slots = c->n_slots; a.maxF = c->maxF;
+  a.s0 = 0;
   a.p = c->epi;
   const int wpb = 8;
   const size_t smem = sizeof(float) * wpb * FB_EPI_GROUPS * (2 * c->epi.max_search_px + 2 * FB_MAX_WIN + 2);
@@ -1262,6 +1265,15 @@ extern "C" void fb_default_update_params(fb_update_params* p) {
 static void update_mark_host_graph(fb_ctx* c, int s) {
   if (c->upd) c->upd->st[s].dev_graph = false;
 }
+static void update_invalidate_graphs(fb_ctx* c) {
+  if (!c->upd) return;
+  for (auto& st : c->upd->st)
+    for (int k = 0; k < 2; ++k)
+      if (st.frame_graph[k]) {
+        cudaGraphExecDestroy(st.frame_graph[k]);
+        st.frame_graph[k] = nullptr;
+      }
+}
 static bool any_device_graph(const fb_ctx* c) {
   if (!c->upd) return false;
   for (int s = 0; s < c->S; ++s)
@@ -1277,6 +1289,7 @@ extern "C" int fb_set_update_params(fb_ctx* c, const fb_update_params* p) {
   int rc = update_alloc(c);
   if (rc) return rc;
   c->upd->up = *p;
+  update_invalidate_graphs(c);
   return FB_OK;
 }
 

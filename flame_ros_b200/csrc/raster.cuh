@@ -91,7 +91,7 @@ k_raster_claim(int W, int H, const float2* __restrict__ vtx, int T,
   const int lane = threadIdx.x & 31;
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (Tdev) T = *Tdev;
-  if (t >= T || !valid[t]) return;
+  if (t >= T || (valid && !valid[t])) return;  // valid == NULL: every triangle (unfiltered map)
   const float2 A = vtx[tri[3 * t]], B = vtx[tri[3 * t + 1]], C = vtx[tri[3 * t + 2]];
   const float area = fb_edge_fn(A.x, A.y, B.x, B.y, C.x, C.y);
   if (area == 0.0f || !(area == area)) return;
