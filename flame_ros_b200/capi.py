@@ -68,7 +68,9 @@ class UpdateParams(C.Structure):
     _fields_ = [("detection_win_size", C.c_int), ("min_grad_mag", C.c_float), ("detection_border", C.c_int),
                 ("idepth_init", C.c_float), ("idepth_var_init", C.c_float), ("idepth_var_max_graph", C.c_float),
                 ("adaptive_data_weights", C.c_int), ("init_with_prediction", C.c_int), ("do_nltgv2", C.c_int),
-                ("iters", C.c_int), ("rparams", NLTGV2Params), ("triangulator", C.c_int)]
+                ("iters", C.c_int), ("rparams", NLTGV2Params), ("triangulator", C.c_int),
+                ("rescale_data", C.c_int), ("min_height", C.c_float), ("max_height", C.c_float),
+                ("check_sticky_obstacles", C.c_int), ("min_error", C.c_float), ("do_letterbox", C.c_int)]
 
 
 class StepDesc(C.Structure):

@@ -113,7 +113,26 @@ struct DsgSelect {
   const int32_t* valid;     // [maxF]
   float var_max;
   int maxF, maxV, W, H;
+  // height band (regularization/nltgv2/{min,max}_height): world z of the feature's 3-D point
+  int use_height;
+  const float* mu_cur;      // [maxF] projected idepth
+  const float* K;           // [9] intrinsics (device)
+  const float* pose_cur;    // [7] current camera-in-world pose (device: read per frame, so a captured frame stays valid)
+  float hmin, hmax;
 };
+// World z of the 3-D point of a feature seen at pixel u with inverse depth mu in the current camera
+// (fp32, fixed expression order: the oracle evaluates the same expressions).
+__host__ __device__ __forceinline__ float dsg_world_height(const float* K, const float* q, float ux, float uy, float mu) {
+  const float qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+  const float n = qx * qx + qy * qy + qz * qz + qw * qw;
+  const float s2 = 2.0f / n;
+  const float r20 = qx * qz * s2 - qw * qy * s2;
+  const float r21 = qy * qz * s2 + qw * qx * s2;
+  const float r22 = 1.0f - (qx * qx * s2 + qy * qy * s2);
+  const float zc = 1.0f / mu;
+  const float xc = ((ux - K[2]) / K[0]) * zc, yc = ((uy - K[5]) / K[4]) * zc;
+  return fmaf(r20, xc, fmaf(r21, yc, fmaf(r22, zc, q[6])));
+}
 // One CTA.  vfeat / vpos / f2v_new are the stream's slices.
 __global__ void __launch_bounds__(DSG_THREADS)
 k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t* f2v_new, int32_t* nV_out) {
@@ -138,7 +157,12 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
   int carry = 0;
   for (int base = 0; base < q.maxF; base += DSG_THREADS) {
     const int f = base + tid;
-    const int flag = (f < q.maxF && q.valid[f] && q.var_cur[f] < q.var_max) ? 1 : 0;
+    int flag = (f < q.maxF && q.valid[f] && q.var_cur[f] < q.var_max) ? 1 : 0;
+    if (flag && q.use_height) {
+      const float2 u = q.u_cur[f];
+      const float h = dsg_world_height(q.K, q.pose_cur, u.x, u.y, q.mu_cur[f]);
+      if (!(h >= q.hmin && h <= q.hmax)) flag = 0;
+    }
     int tot;
     const int rank = carry + dsg_block_scan(flag, s_warp, &tot);
     int v = -1;
@@ -469,4 +493,45 @@ k_ds_csr(DelGpu d, DsgCarry q, int s, int maxV, int maxE, const int32_t* __restr
     inc[r++] = (e << 1) | 1;
   }
   for (int e = e0; e < e1; ++e) inc[r++] = e << 1;
+}
+
+// ------------------------------------------------------------------------------------ rescale_data
+// regularization/nltgv2/rescale_data ("Rescale data to have mean 1"): scale = mean(z), accumulated in
+// double (exact for a few thousand fp32 values of similar magnitude, hence independent of the order).
+__global__ void __launch_bounds__(DSG_THREADS)
+k_rescale_mean(const int32_t* __restrict__ nV, int s, const float* __restrict__ z, float* __restrict__ scale) {
+  __shared__ double s_sum[32];
+  const int V = nV[s];
+  double acc = 0.0;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) acc += (double)z[v];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += s_sum[k];
+    float sc = V > 0 ? (float)(t / (double)V) : 1.0f;
+    if (!(sc > 0.0f)) sc = 1.0f;
+    *scale = sc;
+  }
+}
+// dir = 0: keep z aside, divide z, x, w, xbar by the scale; dir = 1: multiply back, restore z.
+__global__ void __launch_bounds__(256)
+k_rescale_apply(const int32_t* __restrict__ nV, int s, int dir, const float* __restrict__ scale, float* z,
+                float* z_keep, float* x, float* w1, float* w2, float4* vbar) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV[s]) return;
+  const float sc = *scale;
+  float4 b = vbar[v];
+  if (dir == 0) {
+    z_keep[v] = z[v];
+    z[v] = z[v] / sc;
+    x[v] = x[v] / sc; w1[v] = w1[v] / sc; w2[v] = w2[v] / sc;
+    b.x = b.x / sc; b.y = b.y / sc; b.z = b.z / sc;
+  } else {
+    z[v] = z_keep[v];
+    x[v] = x[v] * sc; w1[v] = w1[v] * sc; w2[v] = w2[v] * sc;
+    b.x = b.x * sc; b.y = b.y * sc; b.z = b.z * sc;
+  }
+  vbar[v] = b;
 }

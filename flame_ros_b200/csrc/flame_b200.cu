@@ -1258,6 +1258,13 @@ extern "C" void fb_default_update_params(fb_update_params* p) {
   p->iters = 50;
   fb_default_nltgv2_params(&p->rparams);
   p->triangulator = 0;
+  // /root/reference/cfg/flame_nodelet.yaml:67,70,83,90-92
+  p->rescale_data = 0;
+  p->min_height = -1e14f;
+  p->max_height = 1e14f;
+  p->check_sticky_obstacles = 0;
+  p->min_error = 100.0f;
+  p->do_letterbox = 0;
 }
 
 #include "flame_update.cuh"
@@ -1286,6 +1293,12 @@ extern "C" int fb_set_update_params(fb_ctx* c, const fb_update_params* p) {
   if (!p || p->detection_win_size < 4 || p->detection_win_size > 64 || p->iters < 0 || p->detection_border < 1 ||
       p->triangulator < 0 || p->triangulator > 1)
     FB_FAIL(c, FB_E_ARG, "fb_set_update_params: bad parameters (win in [4,64], border >= 1, triangulator 0|1)");
+  if (p->check_sticky_obstacles != 0)
+    FB_FAIL(c, FB_E_ARG, "fb_set_update_params: check_sticky_obstacles is not implemented (only 0 is accepted)");
+  if (p->min_error != 100.0f)
+    FB_FAIL(c, FB_E_ARG, "fb_set_update_params: the detector's photometric-error gate is not implemented (min_error must stay at its default 100)");
+  if (!(p->min_height <= p->max_height))
+    FB_FAIL(c, FB_E_ARG, "fb_set_update_params: min_height > max_height");
   int rc = update_alloc(c);
   if (rc) return rc;
   c->upd->up = *p;
@@ -1493,7 +1506,7 @@ extern "C" int fb_delaunay_device(fb_ctx* c, int s, int n, const float* pts, int
   FB_CUDA(c, cudaMemcpyAsync(U->f_valid + fb, valid.data(), sizeof(int32_t) * c->maxF, cudaMemcpyHostToDevice, st));
   if (n) FB_CUDA(c, cudaMemcpyAsync(U->f_ucur + fb, pts, sizeof(float2) * n, cudaMemcpyHostToDevice, st));
   FB_CUDA(c, cudaMemsetAsync(U->f_varcur + fb, 0, sizeof(float) * c->maxF, st));
-  DsgSelect q{U->f_ucur + fb, U->f_varcur + fb, U->f_valid + fb, 1.0f, c->maxF, c->maxV, c->W, c->H};
+  DsgSelect q{U->f_ucur + fb, U->f_varcur + fb, U->f_valid + fb, 1.0f, c->maxF, c->maxV, c->W, c->H, 0, nullptr, nullptr, nullptr, 0.f, 0.f};
   k_ds_prepare<<<1, DSG_THREADS, 0, st>>>(q, D, s, c->vfeat + vb, c->vpos + vb, D.f2v + fb, c->nV + s);
   k_ds_stars<<<fb_div_up(c->maxV, DSG_WARPS), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
   k_ds_scan<<<1, DSG_THREADS, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->row + (size_t)s * (c->maxV + 1), c->nE + s, c->nT + s);

@@ -328,7 +328,8 @@ static int update_detect(fb_ctx* c, int s, int img_slot, int ref) {
   const uint8_t* img = c->imgs + ((size_t)s * c->n_slots + img_slot) * npx;
   FB_CUDA(c, cudaMemsetAsync(U->occupied, 0, cells, st));
   k_mark_occupied<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(c->W, c->H, win, c->maxF, U->f_ucur + fb, U->f_valid + fb, U->occupied);
-  k_detect_features<<<fb_div_up(cells * 32, 256), 256, 0, st>>>(c->W, c->H, win, p.detection_border, p.min_grad_mag, img, U->occupied, U->det_xy, U->det_ok);
+  k_detect_features<<<fb_div_up(cells * 32, 256), 256, 0, st>>>(c->W, c->H, win, p.detection_border, p.min_grad_mag, img, U->occupied, U->det_xy, U->det_ok,
+                                                               p.do_letterbox ? c->H / 3 : 0, p.do_letterbox ? (2 * c->H) / 3 : c->H);
   k_scan_flags<<<1, 1024, 0, st>>>(cells, U->det_ok, U->det_rank, U->counts);
   k_scatter_ranked<<<fb_div_up(cells, 256), 256, 0, st>>>(cells, U->det_ok, U->det_rank, U->det_list);
   k_free_flags<<<fb_div_up(c->maxF, 256), 256, 0, st>>>(c->maxF, c->f_alive + fb, U->free_flag);
@@ -390,6 +391,23 @@ static int update_interpolate(fb_ctx* c, int s, const int32_t* Tdev, int32_t* co
   return FB_OK;
 }
 
+// regularization/nltgv2/rescale_data around the solve of stream s (dir 0 before, 1 after).
+static int update_rescale(fb_ctx* c, int s, int dir, float* z_keep) {
+  UpdateState* U = c->upd;
+  const size_t vb = (size_t)s * c->maxV;
+  cudaStream_t st = c->stream;
+  float* scale = reinterpret_cast<float*>(U->misc + 4 * s + 2);
+  if (dir == 0) {
+    k_rescale_mean<<<1, DSG_THREADS, 0, st>>>(c->nV, s, c->z + vb, scale);
+    c->launches++;
+  }
+  k_rescale_apply<<<fb_div_up(c->maxV, 256), 256, 0, st>>>(c->nV, s, dir, scale, c->z + vb, z_keep, c->x + vb, c->w1 + vb,
+                                                          c->w2 + vb, c->vbar + vb);
+  c->launches++;
+  FB_CUDA(c, cudaGetLastError());
+  return FB_OK;
+}
+
 // sync_graph + triangulate on the device (delaunay_gpu.cuh): six launches, no host involvement.
 static int update_graph_device(fb_ctx* c, int s) {
   UpdateState* U = c->upd;
@@ -402,7 +420,10 @@ static int update_graph_device(fb_ctx* c, int s) {
   const int par = (int)(S.builds & 1);
   DsgGraph gg{c->x, c->w1, c->w2, c->vbar, c->q4, c->eij};
   k_ds_stash<<<64, 256, 0, st>>>(gg, D, s, c->maxV, c->maxE);
-  DsgSelect q{U->f_ucur + fb, U->f_varcur + fb, U->f_valid + fb, p.idepth_var_max_graph, c->maxF, c->maxV, c->W, c->H};
+  const int use_height = (p.min_height > -1e13f || p.max_height < 1e13f) ? 1 : 0;
+  DsgSelect q{U->f_ucur + fb, U->f_varcur + fb, U->f_valid + fb, p.idepth_var_max_graph, c->maxF, c->maxV, c->W, c->H,
+              use_height, U->f_mucur + fb, c->d_K + 9 * s, c->d_pose + ((size_t)s * c->n_slots + (c->n_slots - 1)) * 7,
+              p.min_height, p.max_height};
   k_ds_prepare<<<1, DSG_THREADS, 0, st>>>(q, D, s, c->vfeat + vb, c->vpos + vb, D.f2v + par * nf + fb, c->nV + s);
   k_ds_stars<<<fb_div_up(c->maxV, DSG_WARPS), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
   k_ds_scan<<<1, DSG_THREADS, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->row + (size_t)s * (c->maxV + 1), c->nE + s, c->nT + s);
@@ -435,13 +456,18 @@ static int update_graph_host(fb_ctx* c, int s) {
   cudaStream_t st = c->stream;
   int rc;
   std::vector<float2> h_u(c->maxF);
-  std::vector<float> h_var(c->maxF);
+  std::vector<float> h_var(c->maxF), h_mu;
   std::vector<int32_t> h_valid(c->maxF);
+  const bool use_height = p.min_height > -1e13f || p.max_height < 1e13f;
   {
     StageTimer t(S.stats, "project_features");
     FB_CUDA(c, cudaMemcpyAsync(h_u.data(), U->f_ucur + fb, sizeof(float2) * c->maxF, cudaMemcpyDeviceToHost, st));
     FB_CUDA(c, cudaMemcpyAsync(h_var.data(), U->f_varcur + fb, sizeof(float) * c->maxF, cudaMemcpyDeviceToHost, st));
     FB_CUDA(c, cudaMemcpyAsync(h_valid.data(), U->f_valid + fb, sizeof(int32_t) * c->maxF, cudaMemcpyDeviceToHost, st));
+    if (use_height) {
+      h_mu.resize(c->maxF);
+      FB_CUDA(c, cudaMemcpyAsync(h_mu.data(), U->f_mucur + fb, sizeof(float) * c->maxF, cudaMemcpyDeviceToHost, st));
+    }
     FB_CUDA(c, cudaStreamSynchronize(st));
   }
   std::vector<int32_t> vfeat;
@@ -450,6 +476,10 @@ static int update_graph_host(fb_ctx* c, int s) {
   for (int f = 0; f < c->maxF; ++f) {
     n_valid += h_valid[f] ? 1 : 0;
     if (h_valid[f] && h_var[f] < p.idepth_var_max_graph && (int)vfeat.size() < c->maxV) {  // valid implies alive
+      if (use_height) {
+        const float h = dsg_world_height(&c->h_K[9 * s], &c->h_pose[((size_t)s * c->n_slots + (c->n_slots - 1)) * 7], h_u[f].x, h_u[f].y, h_mu[f]);
+        if (!(h >= p.min_height && h <= p.max_height)) continue;
+      }
       vfeat.push_back(f);
       pos.push_back(h_u[f].x);
       pos.push_back(h_u[f].y);
@@ -594,8 +624,11 @@ static int update_frame_enqueue(fb_ctx* c, int s, bool captured) {
   }
   if (p.do_nltgv2 && p.iters > 0) {
     StageTimer t(S.stats, "nltgv2");
+    float* z_keep = U->del.o_x + (size_t)s * c->maxV;  // free between k_ds_csr and the next frame's stash
+    if (p.rescale_data && (rc = update_rescale(c, s, 0, z_keep)) != 0) return rc;
     rc = fb_nltgv2_solve_stream(c, s, p.iters, &p.rparams);
     if (rc) return rc;
+    if (p.rescale_data && (rc = update_rescale(c, s, 1, z_keep)) != 0) return rc;
   }
   {
     StageTimer t(S.stats, "interpolate");
@@ -732,8 +765,10 @@ static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const f
       if (p.do_nltgv2 && p.iters > 0) {
         StageTimer t(S.stats, "nltgv2");
         // solve only this stream's graph: other streams of the context keep their own cadence
+        if (p.rescale_data && (rc = update_rescale(c, s, 0, U->o_x)) != 0) return rc;
         rc = fb_nltgv2_solve_stream(c, s, p.iters, &p.rparams);
         if (rc) return rc;
+        if (p.rescale_data && (rc = update_rescale(c, s, 1, U->o_x)) != 0) return rc;
       }
       {
         StageTimer t(S.stats, "interpolate");

@@ -55,7 +55,7 @@ k_mark_occupied(int W, int H, int win, int N, const float2* __restrict__ u_cur,
 __global__ void __launch_bounds__(256)
 k_detect_features(int W, int H, int win, int border, float min_grad_mag,
                   const uint8_t* __restrict__ img, const uint8_t* __restrict__ occupied,
-                  float2* __restrict__ det_xy, int32_t* __restrict__ det_ok) {
+                  float2* __restrict__ det_xy, int32_t* __restrict__ det_ok, int y_lo = 0, int y_hi = 1 << 30) {
   const int lane = threadIdx.x & 31;
   const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int cx = W / win, cy = H / win;
@@ -66,7 +66,7 @@ k_detect_features(int W, int H, int win, int border, float min_grad_mag,
   if (!(occupied && occupied[cell])) {
     for (int k = lane; k < win * win; k += 32) {  // ascending k per lane: first maximum is kept
       const int x = ci * win + k % win, y = cj * win + k / win;
-      if (x < border || y < border || x >= W - border || y >= H - border) continue;
+      if (x < border || y < border || x >= W - border || y >= H - border || y < y_lo || y >= y_hi) continue;  // rows: do_letterbox
       const float g = fb_grad_mag_at(img, W, H, x, y);
       if (g > best) {
         best = g;

@@ -63,6 +63,14 @@ class Flame {
     up.rparams.theta = params.rparams.theta;
     up.rparams.x_min = params.rparams.x_min;
     up.rparams.x_max = params.rparams.x_max;
+    // forwarded as the frontends set them (/root/reference/src/flame_nodelet.cc:225-231,251,260-263); options
+    // this library does not implement are rejected by fb_set_update_params instead of being ignored
+    up.rescale_data = params.rescale_data;
+    up.min_height = params.min_height;
+    up.max_height = params.max_height;
+    up.check_sticky_obstacles = params.check_sticky_obstacles;
+    up.min_error = params.min_error;
+    up.do_letterbox = params.do_letterbox;
     check(fb_set_update_params(ctx_, &up));
     fb_default_tri_filter_params(&filter_);
     filter_.do_oblique = params.do_oblique_triangle_filter;

@@ -258,6 +258,21 @@ typedef struct {
   int triangulator;           /* sync_graph + triangulate: 0 = on the device (per-vertex Delaunay stars,
                                  default, no host round trip), 1 = host (incremental Bowyer-Watson).
                                  Both give the same canonical mesh. */
+  /* regularization/nltgv2/{rescale_data,min_height,max_height,check_sticky_obstacles} and
+   * features/{do_letterbox,detection/min_error} (/root/reference/src/flame_nodelet.cc:225-231,251,260-263;
+   * defaults cfg/flame_nodelet.yaml:67,70,83,90-92).  The reference only names these options; the
+   * semantics below are this library's:
+   *   rescale_data   z, x and w are divided by mean(z) before the iterations and multiplied back after
+   *   min/max_height a feature enters the graph only when the world z of its 3-D point lies in the band
+   *   do_letterbox   detection only in the middle third of the rows [H/3, 2H/3)
+   *   min_error, check_sticky_obstacles: not implemented -- fb_set_update_params rejects any value
+   *   other than the defaults (100, 0) with FB_E_ARG instead of ignoring it. */
+  int rescale_data;           /* 0 */
+  float min_height;           /* -1e14 */
+  float max_height;           /* 1e14 */
+  int check_sticky_obstacles; /* 0 */
+  float min_error;            /* 100 */
+  int do_letterbox;           /* 0 */
 } fb_update_params;
 void fb_default_update_params(fb_update_params* p);
 int fb_set_update_params(fb_ctx* ctx, const fb_update_params* p);

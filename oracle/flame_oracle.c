@@ -496,8 +496,8 @@ void fo_pyr_down(int W, int H, const uint8_t* img, uint8_t* out) {
     }
 }
 
-int fo_detect_features(int W, int H, const float* mag, int win, int border, float min_grad_mag,
-                       const uint8_t* occupied, float* det_xy, int32_t* det_ok) {
+int fo_detect_features_rows(int W, int H, const float* mag, int win, int border, float min_grad_mag,
+                            const uint8_t* occupied, int y_lo, int y_hi, float* det_xy, int32_t* det_ok) {
   int cx = W / win, cy = H / win, n = 0;
   for (int j = 0; j < cy; ++j)
     for (int i = 0; i < cx; ++i) {
@@ -510,7 +510,7 @@ int fo_detect_features(int W, int H, const float* mag, int win, int border, floa
       int bx = -1, by = -1;
       for (int y = j * win; y < (j + 1) * win; ++y)
         for (int x = i * win; x < (i + 1) * win; ++x) {
-          if (x < border || y < border || x >= W - border || y >= H - border) continue;
+          if (x < border || y < border || x >= W - border || y >= H - border || y < y_lo || y >= y_hi) continue;
           float g = mag[y * W + x];
           if (g > best) {
             best = g;
@@ -526,6 +526,11 @@ int fo_detect_features(int W, int H, const float* mag, int win, int border, floa
       }
     }
   return n;
+}
+
+int fo_detect_features(int W, int H, const float* mag, int win, int border, float min_grad_mag,
+                       const uint8_t* occupied, float* det_xy, int32_t* det_ok) {
+  return fo_detect_features_rows(W, H, mag, win, border, min_grad_mag, occupied, 0, H, det_xy, det_ok);
 }
 
 /* ======================================================================== */

@@ -175,6 +175,10 @@ void fo_pyr_down(int W, int H, const uint8_t* img, uint8_t* out /*[H/2][W/2]*/);
 int fo_detect_features(int W, int H, const float* mag, int win, int border,
                        float min_grad_mag, const uint8_t* occupied,
                        float* det_xy, int32_t* det_ok);
+/* The same restricted to the rows [y_lo, y_hi) (features/do_letterbox). */
+int fo_detect_features_rows(int W, int H, const float* mag, int win, int border,
+                            float min_grad_mag, const uint8_t* occupied, int y_lo, int y_hi,
+                            float* det_xy, int32_t* det_ok);
 
 /* ------------------------------------- mesh -> dense inverse-depth map     */
 /*
@@ -239,6 +243,20 @@ typedef struct {
   int do_nltgv2;
   int iters;                  /* OUR CHOICE: iterations per frame, 50 */
   fo_nltgv2_params rparams;
+  /* regularization/nltgv2/{rescale_data,min_height,max_height,check_sticky_obstacles},
+   * features/{do_letterbox,detection/min_error} (/root/reference/src/flame_nodelet.cc:225-231,251,260-263).
+   * Semantics are OUR CHOICE (the reference only names them):
+   *   rescale_data  the data term, x and w are divided by mean(z) before the iterations and
+   *                 multiplied back after them ("Rescale data to have mean 1")
+   *   min/max_height  a feature enters the graph only when the world z of its 3-D point (current
+   *                 camera pose, depth 1/idepth) lies in [min_height, max_height]
+   *   do_letterbox  detection only in the middle third of the rows [H/3, 2H/3)
+   *   min_error, check_sticky_obstacles  not restated: only their defaults (100, 0) are accepted */
+  int rescale_data;
+  float min_height, max_height;
+  int check_sticky_obstacles;
+  float min_error;
+  int do_letterbox;
 } fo_update_params;
 void fo_default_update_params(fo_update_params* p);
 

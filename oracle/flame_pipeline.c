@@ -374,6 +374,13 @@ void fo_default_update_params(fo_update_params* p) {
   p->iters = 50;
   p->rparams.data_factor = 0.15f; p->rparams.step_x = 0.001f; p->rparams.step_q = 125.0f;
   p->rparams.theta = 0.25f; p->rparams.x_min = 0.0f; p->rparams.x_max = 10.0f;
+  /* /root/reference/cfg/flame_nodelet.yaml:67,70,83,90-92 */
+  p->rescale_data = 0;
+  p->min_height = -1e14f;
+  p->max_height = 1e14f;
+  p->check_sticky_obstacles = 0;
+  p->min_error = 100.0f;
+  p->do_letterbox = 0;
 }
 
 #define FO_ALLOC(ptr, type, count) ptr = (type*)calloc((size_t)(count) > 0 ? (size_t)(count) : 1, sizeof(type))
@@ -381,6 +388,7 @@ void fo_default_update_params(fo_update_params* p) {
 fo_pipeline* fo_pipeline_create(int W, int H, const float* K, int n_slots, int max_features, int max_vertices,
                                 const fo_update_params* up, const fo_epi_params* ep, int nthreads) {
   if (W < 16 || H < 16 || n_slots < 3 || max_features < 1 || max_vertices < 3 || !K || !up || !ep) return NULL;
+  if (up->check_sticky_obstacles != 0 || up->min_error != 100.0f) return NULL; /* not restated: defaults only */
   fo_pipeline* P = (fo_pipeline*)calloc(1, sizeof(fo_pipeline));
   P->W = W; P->H = H; P->n_slots = n_slots; P->maxF = max_features; P->maxV = max_vertices;
   P->nthreads = nthreads < 1 ? 1 : nthreads;
@@ -454,7 +462,8 @@ static void fo_new_poseframe(fo_pipeline* P, int img_id) {
     if (i >= 0 && j >= 0 && i < cx && j < cy) P->occ[j * cx + i] = 1;
   }
   fo_gradient_mag(W, H, P->imgs + (size_t)cur * npx, P->mag);
-  fo_detect_features(W, H, P->mag, win, up->detection_border, up->min_grad_mag, P->occ, P->det_xy, P->det_ok);
+  fo_detect_features_rows(W, H, P->mag, win, up->detection_border, up->min_grad_mag, P->occ,
+                          up->do_letterbox ? H / 3 : 0, up->do_letterbox ? (2 * H) / 3 : H, P->det_xy, P->det_ok);
   int f = 0;
   for (int c = 0; c < cells; ++c) {
     if (!P->det_ok[c]) continue;
@@ -504,8 +513,27 @@ int fo_pipeline_update(fo_pipeline* P, int img_id, const float* pose, const uint
   FO_LAP(FO_STAGE_PROJECT);
   /* ---- graph sync: vertex selection in ascending feature index */
   int V = 0;
+  const int use_height = up->min_height > -1e13f || up->max_height < 1e13f;
+  float r20 = 0.f, r21 = 0.f, r22 = 1.f;
+  {
+    /* third row of the camera-to-world rotation of the current pose, fp32, fixed expression order */
+    const float* q = P->poses + 7 * cur;
+    const float qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+    const float n = qx * qx + qy * qy + qz * qz + qw * qw;
+    const float s2 = 2.0f / n;
+    r20 = qx * qz * s2 - qw * qy * s2;
+    r21 = qy * qz * s2 + qw * qx * s2;
+    r22 = 1.0f - (qx * qx * s2 + qy * qy * s2);
+  }
   for (int f = 0; f < F && V < P->maxV; ++f)
     if (P->valid[f] && P->var_cur[f] < up->idepth_var_max_graph) {
+      if (use_height) {
+        const float zc = 1.0f / P->mu_cur[f];
+        const float xc = ((P->u_cur[2 * f] - P->K[2]) / P->K[0]) * zc;
+        const float yc = ((P->u_cur[2 * f + 1] - P->K[5]) / P->K[4]) * zc;
+        const float h = fmaf(r20, xc, fmaf(r21, yc, fmaf(r22, zc, P->poses[7 * cur + 6])));
+        if (!(h >= up->min_height && h <= up->max_height)) continue;
+      }
       P->n_vfeat[V] = f;
       P->n_pos[2 * V] = P->u_cur[2 * f];
       P->n_pos[2 * V + 1] = P->u_cur[2 * f + 1];
@@ -559,9 +587,29 @@ int fo_pipeline_update(fo_pipeline* P, int img_id, const float* pose, const uint
       }
     }
     FO_LAP(FO_STAGE_SYNC);
-    if (up->do_nltgv2 && up->iters > 0)
+    if (up->do_nltgv2 && up->iters > 0) {
+      float scale = 1.0f;
+      if (up->rescale_data) { /* mean of the data term, accumulated in double */
+        double sum = 0.0;
+        for (int k = 0; k < V; ++k) sum += (double)P->n_z[k];
+        scale = (float)(sum / (double)V);
+        if (!(scale > 0.0f)) scale = 1.0f;
+        for (int k = 0; k < V; ++k) {
+          P->n_wt[k] = P->n_wt[k]; /* weights are not rescaled */
+          st[0][k] /= scale; st[1][k] /= scale; st[2][k] /= scale;
+          st[3][k] /= scale; st[4][k] /= scale; st[5][k] /= scale;
+        }
+        memcpy(P->mag, P->n_z, sizeof(float) * (size_t)V); /* original data term kept aside (scratch) */
+        for (int k = 0; k < V; ++k) P->n_z[k] /= scale;
+      }
       fo_nltgv2_solve(V, nE, P->n_pos, P->n_edges, P->n_alpha, P->n_beta, P->n_z, P->n_wt, st[0], st[1], st[2], st[3],
                       st[4], st[5], st[6], st[7], st[8], &up->rparams, up->iters, P->nthreads);
+      if (up->rescale_data) {
+        for (int k = 0; k < V; ++k)
+          for (int a = 0; a < 6; ++a) st[a][k] *= scale;
+        memcpy(P->n_z, P->mag, sizeof(float) * (size_t)V);
+      }
+    }
     FO_LAP(FO_STAGE_SOLVE);
     fo_rasterize_idepth_mt(W, H, V, P->n_pos, st[0], nT, P->n_tris, NULL, P->idmap, P->nthreads);
     FO_LAP(FO_STAGE_INTERP);

@@ -168,3 +168,79 @@ def test_two_streams_in_one_context_are_independent(capi):
             assert np.array_equal(mesh["idepth"], solo[s][0]["idepth"])
             assert np.array_equal(np.nan_to_num(dm, nan=-1), np.nan_to_num(solo[s][1], nan=-1))
             assert np.array_equal(pool["alive"], solo[s][2]["alive"]) and np.array_equal(pool["mu"], solo[s][2]["mu"])
+
+
+@pytest.mark.parametrize("opts", [dict(rescale_data=1), dict(min_height=0.0, max_height=3.0), dict(do_letterbox=1),
+                                  dict(adaptive_data_weights=1, rescale_data=1, do_letterbox=1)],
+                         ids=["rescale_data", "height_band", "letterbox", "combined"])
+@pytest.mark.parametrize("tri", [0, 1], ids=["device-graph", "host-graph"])
+def test_update_options_match_oracle_pipeline(capi, oracle, opts, tri):
+    """regularization/nltgv2/{rescale_data,min_height,max_height}, features/do_letterbox
+    (/root/reference/src/flame_nodelet.cc:225-231,251,260-263) through fb_update against the oracle's C
+    restatement of the whole pipeline (oracle/flame_pipeline.c), frame by frame."""
+    W, H, K = 640, 480, synth.K_VGA
+    n_frames = 16
+    frames, poses = _stream(W, H, K, n_frames, seed=5, step=0.02)
+    up = capi.default_update_params()
+    up.detection_win_size, up.iters, up.triangulator, up.idepth_var_max_graph = 16, 30, tri, 0.05
+    for k, v in opts.items():
+        setattr(up, k, v)
+    oup = oracle.UpdateParams.like(up)
+    n_slots, maxF, maxV = 5, 4096, 4096
+    n_upd = 0
+    with capi.Context(1, W, H, n_slots, maxF, maxV, 3 * maxV) as ctx, \
+            oracle.Pipeline(W, H, K, n_slots, maxF, maxV, oup) as pipe:
+        ctx.set_intrinsics(0, K)
+        ctx.set_update_params(up)
+        for k in range(n_frames):
+            img = frames[k][0]
+            is_pf = (k % 4) == 0
+            got = ctx.update(0, k / 30.0, k, poses[k], img, is_pf)
+            ref = pipe.update(k, poses[k], img, is_pf)
+            assert got == ref, "frame %d" % k
+            pool, f = ctx.get_feature_pool(0), pipe.features()
+            assert np.array_equal(pool["alive"], f["alive"]), "frame %d" % k
+            live = f["alive"] == 1
+            assert np.array_equal(pool["u_ref"][live], f["u_ref"][live])
+            assert np.max(np.abs(pool["mu"][live] - f["mu"][live]), initial=0) < TOL
+            if got:
+                n_upd += 1
+                mesh, m = ctx.get_mesh(0), pipe.mesh()
+                assert np.array_equal(mesh["tris"], m["tris"]) and np.array_equal(mesh["edges"], m["edges"]), "frame %d" % k
+                assert np.max(np.abs(mesh["idepth"] - m["idepth"])) < TOL, "frame %d" % k
+                dm, rm = ctx.get_idepthmap(0), pipe.idepthmap()
+                assert np.array_equal(np.isnan(dm), np.isnan(rm))
+                ok = ~np.isnan(dm)
+                assert np.max(np.abs(dm[ok] - rm[ok]), initial=0) < TOL
+                fm, rfm = ctx.get_idepthmap(0, capi.default_tri_filter_params()), pipe.idepthmap(oracle.TriFilterParams.default())
+                assert np.array_equal(np.isnan(fm), np.isnan(rfm))
+        assert n_upd >= n_frames - 6
+        mesh = ctx.get_mesh(0)
+        if "max_height" in opts:   # the far plane (z = 4 m) is outside the band: its vertices are gone
+            depth = 1.0 / mesh["idepth"]
+            assert depth.max() < 3.6 and len(depth) > 50
+        if "do_letterbox" in opts:
+            pool = ctx.get_feature_pool(0)
+            live = pool["alive"] == 1
+            assert live.sum() > 50
+            assert np.all(pool["u_ref"][live][:, 1] >= H // 3) and np.all(pool["u_ref"][live][:, 1] < (2 * H) // 3)
+
+
+def test_unimplemented_options_are_rejected_not_ignored(capi):
+    """check_sticky_obstacles and a non-default detection/min_error have no restated semantics: the
+    setter refuses them ('silently ignored, not rejected')."""
+    with capi.Context(1, 320, 240, 4, 256, 256, 768) as ctx:
+        up = capi.default_update_params()
+        assert up.min_error == 100.0 and up.check_sticky_obstacles == 0 and up.rescale_data == 0
+        assert up.min_height < -1e13 and up.max_height > 1e13 and up.do_letterbox == 0
+        up.check_sticky_obstacles = 1
+        with pytest.raises(capi.FlameError):
+            ctx.set_update_params(up)
+        up = capi.default_update_params()
+        up.min_error = 50.0
+        with pytest.raises(capi.FlameError):
+            ctx.set_update_params(up)
+        up = capi.default_update_params()
+        up.min_height, up.max_height = 2.0, 1.0
+        with pytest.raises(capi.FlameError):
+            ctx.set_update_params(up)

@@ -71,3 +71,43 @@ def test_c_pipeline_equals_python_mirror(capi, oracle, W, H, win, iters, pf_ever
         assert n_upd >= n_frames - 5
         ms = pipe.stage_ms()
         assert ms["update"] > 0 and ms["triangulate"] > 0
+
+
+def test_pipeline_options_semantics(oracle):
+    """The options of SURVEY row a10 on the oracle pipeline: the height band removes the far plane's
+    vertices, the letterbox confines detections to the middle third, rescale_data changes the
+    transient (different effective step sizes) but not the scale of the answer."""
+    W, H, K = 320, 240, (synth.K_VGA * np.array([[0.5], [0.5], [1.0]], np.float32)).astype(np.float32)
+    n = 14
+    sc = synth.Scene(5, tex_size=1024)
+    poses = synth.stream_poses(n, step=0.02)
+    frames = [sc.render(K, poses[k], W, H)[0] for k in range(n)]
+
+    def run(**opts):
+        up = oracle.UpdateParams.default()
+        up.detection_win_size, up.iters, up.idepth_var_max_graph = 8, 30, 0.05
+        for k, v in opts.items():
+            setattr(up, k, v)
+        with oracle.Pipeline(W, H, K, 5, 4096, 4096, up) as p:
+            for k in range(n):
+                p.update(k, poses[k], frames[k], k % 4 == 0)
+            return p.mesh(), p.features(), p.idepthmap()
+
+    base, fb_, mb = run()
+    band, _, _ = run(min_height=0.0, max_height=3.0)
+    assert 50 < len(band["vtx"]) < len(base["vtx"])
+    assert (1.0 / band["idepth"]).max() < 3.6 < (1.0 / base["idepth"]).max()
+    _, fl, _ = run(do_letterbox=1)
+    live = fl["alive"] == 1
+    assert live.sum() > 30 and np.all(fl["u_ref"][live][:, 1] >= H // 3) and np.all(fl["u_ref"][live][:, 1] < (2 * H) // 3)
+    resc, _, mr = run(rescale_data=1)
+    # a different iteration (other effective step sizes; the dense prediction also seeds new features,
+    # so the feature sets drift apart), the same answer to first order
+    assert abs(len(resc["vtx"]) - len(base["vtx"])) < 0.1 * len(base["vtx"])
+    both = ~np.isnan(mr) & ~np.isnan(mb)
+    assert both.mean() > 0.5 and not np.array_equal(mr[both], mb[both])
+    assert np.median(np.abs(mr[both] - mb[both])) < 0.02
+    up = oracle.UpdateParams.default()
+    up.check_sticky_obstacles = 1
+    with pytest.raises(ValueError):
+        oracle.Pipeline(W, H, K, 5, 256, 256, up)
