@@ -286,7 +286,7 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
 
 // ------------------------------------------------------------------------------------ k_ds_stars
 #define DSG_WARPS 4  // vertices per CTA: one warp each (the candidate cache takes ~7 KB per warp)
-__global__ void __launch_bounds__(DSG_WARPS * 32)
+__global__ void __launch_bounds__(DSG_WARPS * 32, 4)
 k_ds_stars(DelGpu d, int s, int maxV) {
   __shared__ DsScratch s_scr[DSG_WARPS];
   int32_t* meta = d.meta + (size_t)s * DSG_META;

@@ -72,6 +72,20 @@ DS_FN int ds_incircle(DsPt a, DsPt b, DsPt c, DsPt p) {
   const int32_t iadx = a.x - p.x, iady = a.y - p.y, ibdx = b.x - p.x, ibdy = b.y - p.y;
   const int32_t icdx = c.x - p.x, icdy = c.y - p.y;
   {
+    // stage 1, fp32: the differences are exact (< 2^24); every product and sum rounds.  The bound is
+    // Shewchuk's "permanent" form: 10 eps (sum of the magnitudes of all terms), eps = 2^-24, rounded up
+    // to 1e-6.  Nearly every candidate is far from the circle and is decided here at fp32 latency.
+    const float adx = (float)iadx, ady = (float)iady, bdx = (float)ibdx, bdy = (float)ibdy, cdx = (float)icdx, cdy = (float)icdy;
+    const float bc1 = bdx * cdy, bc2 = bdy * cdx, ca1 = cdx * ady, ca2 = cdy * adx, ab1 = adx * bdy, ab2 = ady * bdx;
+    const float al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
+    const float det = al * (bc1 - bc2) + bl * (ca1 - ca2) + cl * (ab1 - ab2);
+    const float perm = al * (fabsf(bc1) + fabsf(bc2)) + bl * (fabsf(ca1) + fabsf(ca2)) + cl * (fabsf(ab1) + fabsf(ab2));
+    const float bound = 1e-6f * perm;
+    if (det > bound) return 1;
+    if (det < -bound) return -1;
+  }
+  {
+    // stage 2, fp64: squared lengths and 2x2 minors are exact, only the three-term sum rounds
     const double adx = iadx, ady = iady, bdx = ibdx, bdy = ibdy, cdx = icdx, cdy = icdy;
     const double al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;  // exact
     const double ma = bdx * cdy - bdy * cdx, mb = cdx * ady - cdy * adx, mc = adx * bdy - ady * bdx;  // exact
@@ -81,6 +95,7 @@ DS_FN int ds_incircle(DsPt a, DsPt b, DsPt c, DsPt p) {
     if (det > bound) return 1;
     if (det < -bound) return -1;
   }
+  // stage 3, exact: 128-bit integers (co-circular detections land here)
   const int64_t adx = iadx, ady = iady, bdx = ibdx, bdy = ibdy, cdx = icdx, cdy = icdy;
   const int64_t al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
   const int64_t ma = bdx * cdy - bdy * cdx, mb = cdx * ady - cdy * adx, mc = adx * bdy - ady * bdx;

@@ -174,6 +174,42 @@ struct TileArgs {
   int* derr;
 };
 
+// remote arrive on a peer CTA's mbarrier (release at cluster scope: the peer's acquire-wait then sees
+// everything this CTA wrote to its own shared memory before the CTA barrier that precedes the arrive)
+__device__ __forceinline__ void fbt_mbar_arrive_remote(uint32_t rmbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void fbt_mbar_wait_cluster(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  }
+}
+
+// Own edge number le of the tile -> (local source vertex, offset among its out-edges).
+__device__ __forceinline__ void fbt_edge_of(const int* s_erow, int nOwn, int le, int* lv, int* off) {
+  int lo = 0, hi = nOwn;  // largest lv with s_erow[lv] <= le
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (s_erow[mid] <= le) lo = mid; else hi = mid;
+  }
+  *lv = lo;
+  *off = le - s_erow[lo];
+}
+
+// Synchronisation inside the iteration is point to point (the cluster-wide barrier costs ~1 us per use
+// with release / acquire semantics: two of them were 80 % of an iteration):
+//   A  "the contributions for my vertices are complete": remote edge threads deliver them with
+//      st.async ... mbarrier::complete_tx::bytes on MY barrier; I expect 16 B per remote incidence.
+//   B  "the extragradient points I read from other tiles are refreshed": every tile that owns such
+//      points arrives (release.cluster) on my barrier after its primal half-step.
+// Neither can run ahead by more than one phase: a tile's next dual half-step needs B from exactly the
+// tiles whose A it feeds.
 __global__ void __launch_bounds__(FBT_THREADS, 1)
 k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float theta, float xmin, float xmax) {
   extern __shared__ __align__(16) uint8_t fbt_smem[];
@@ -184,6 +220,9 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
   int* s_first = s_erow + FBT_VCAP + 1;                          // [VCAP] first out-edge (global id)
   int* s_nin = s_first + FBT_VCAP;                               // [VCAP] in-degree
   __shared__ int s_warp[32];
+  __shared__ __align__(8) uint64_t s_mbar[2];                    // A, B
+  __shared__ int s_nrin;                                         // incidences filled by other tiles
+  __shared__ unsigned s_rmask, s_smask;                          // tiles that read my points / tiles whose points I read
   const GraphView& g = a.g;
   const int tid = threadIdx.x;
   const int r = (int)fbc_cluster_ctarank();
@@ -199,6 +238,8 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
   const int base = toff[r], nOwn = toff[r + 1] - base;
   const int32_t* tl_ = a.tlist + vb + base;
   int32_t* g_lrow = a.lrow + vb;
+  if (tid == 0) { s_nrin = 0; s_rmask = 0u; s_smask = 0u; }
+  __syncthreads();
 
   // ---- prologue 1: own vertices (state into registers, CSR bookkeeping into shared memory)
   float vx[FBT_VPT], vw1[FBT_VPT], vw2[FBT_VPT], vz[FBT_VPT], vth[FBT_VPT];
@@ -216,7 +257,14 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
       vid[k] = v;
       const int r0 = row[v], r1 = row[v + 1];
       vdeg[k] = r1 - r0;
-      while (nin < vdeg[k] && (inc[r0 + nin] & 1)) ++nin;  // in-edges come first (ascending edge id)
+      int nrem = 0;
+      unsigned mask = 0u;
+      while (nin < vdeg[k] && (inc[r0 + nin] & 1)) {  // in-edges come first (ascending edge id)
+        const int ts = vtile[g.eij[eb + (inc[r0 + nin] >> 1)].x];
+        if (ts != r) { ++nrem; mask |= 1u << ts; }
+        ++nin;
+      }
+      if (nrem) { atomicAdd(&s_nrin, nrem); atomicOr(&s_rmask, mask); }
       od = vdeg[k] - nin;
       first = od ? (inc[r0 + nin] >> 1) : 0;
       vx[k] = g.x[vb + v]; vw1[k] = g.w1[vb + v]; vw2[k] = g.w2[vb + v];
@@ -252,29 +300,24 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
 
   // ---- prologue 2: own edges = the contiguous out-edge ranges of the own vertices
   float q1[FBT_EPT], q2[FBT_EPT], q3[FBT_EPT], ea[FBT_EPT], ebt[FBT_EPT], dx[FBT_EPT], dy[FBT_EPT];
-  uint32_t a_bi[FBT_EPT], a_bj[FBT_EPT], a_sj[FBT_EPT];
-  int a_si[FBT_EPT], eid[FBT_EPT];
+  uint32_t a_bj[FBT_EPT], a_sj[FBT_EPT], pk[FBT_EPT];  // pk: lv | own slot << 10 | target tile << 23 | remote << 27
   const uint32_t bar_u32 = fbc_smem_u32(s_bar), slot_u32 = fbc_smem_u32(s_slot);
+  const uint32_t mbA = fbc_smem_u32(&s_mbar[0]), mbB = fbc_smem_u32(&s_mbar[1]);
   const int kmax = (nEdge + FBT_THREADS - 1) / FBT_THREADS;  // uniform over the CTA
+  uint32_t evalid = 0u;
 #pragma unroll
   for (int k = 0; k < FBT_EPT; ++k) {
-    eid[k] = -1;
     q1[k] = q2[k] = q3[k] = ea[k] = ebt[k] = dx[k] = dy[k] = 0.f;
-    a_bi[k] = a_bj[k] = a_sj[k] = 0u;
-    a_si[k] = 0;
+    a_bj[k] = a_sj[k] = pk[k] = 0u;
     const int le = tid + k * FBT_THREADS;
     if (le < nEdge) {
-      int lo = 0, hi = nOwn;  // largest lv with s_erow[lv] <= le
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s_erow[mid] <= le) lo = mid; else hi = mid;
-      }
-      const int lv = lo, off = le - s_erow[lv];
+      int lv, off;
+      fbt_edge_of(s_erow, nOwn, le, &lv, &off);
       const int e = s_first[lv] + off;
       const int2 ij = g.eij[eb + e];
       const float4 c = g.ec[eb + e];
       const float4 q = g.q4[eb + e];
-      eid[k] = e;
+      evalid |= 1u << k;
       ea[k] = c.x; ebt[k] = c.y; dx[k] = c.z; dy[k] = c.w;
       q1[k] = q.x; q2[k] = q.y; q3[k] = q.z;
       const int j = ij.y, tj = vtile[j], lj = vloc[j];
@@ -283,26 +326,36 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
         const int r0 = row[j], want = (e << 1) | 1;
         while (inc[r0 + pos] != want) ++pos;
       }
-      a_bi[k] = bar_u32 + 16u * (uint32_t)lv;
       a_bj[k] = fbc_mapa(bar_u32 + 16u * (uint32_t)lj, (uint32_t)tj);
-      a_si[k] = s_lrow[lv] + s_nin[lv] + off;
       a_sj[k] = fbc_mapa(slot_u32 + 16u * (uint32_t)(__ldcg(g_lrow + j) + pos), (uint32_t)tj);
+      pk[k] = (uint32_t)lv | ((uint32_t)(s_lrow[lv] + s_nin[lv] + off) << 10) | ((uint32_t)tj << 23) | (tj != r ? 1u << 27 : 0u);
+      if (tj != r) atomicOr(&s_smask, 1u << tj);
     }
   }
-  fbc_cluster_sync();  // every tile's s_bar is filled before the first remote read
+  __syncthreads();
+  const int nRin = s_nrin;
+  const unsigned rmask = s_rmask, smask = s_smask;
+  const bool hasA = nRin > 0, hasB = smask != 0u;
+  if (tid == 0) {
+    fbc_mbar_init(mbA, 1);
+    fbc_mbar_init(mbB, hasB ? (uint32_t)__popc(smask) : 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fbc_cluster_sync();  // every tile's s_bar is filled and its barriers exist before the first remote access
 
   for (int it = 0; it < iters; ++it) {
+    if (hasA && tid == 0) fbc_mbar_expect(mbA, 16u * (uint32_t)nRin);  // phase `it` of A
     // ---- dual half-step (nltgv2.cuh:k_dual_edges) + K^T q into the CSR slots of both endpoints
     float4 bi[FBT_EPT], bj[FBT_EPT];
 #pragma unroll
     for (int k = 0; k < FBT_EPT; ++k)
-      if (k < kmax && eid[k] >= 0) {
-        bi[k] = fbc_lds(a_bi[k]);
+      if (k < kmax && (evalid >> k) & 1u) {
+        bi[k] = fbc_lds(bar_u32 + ((pk[k] & 1023u) << 4));
         bj[k] = fbt_ld_cluster(a_bj[k]);
       }
 #pragma unroll
     for (int k = 0; k < FBT_EPT; ++k)
-      if (k < kmax && eid[k] >= 0) {
+      if (k < kmax && (evalid >> k) & 1u) {
         float t = bi[k].x - bj[k].x;
         t = fmaf(-dx[k], bi[k].y, t);
         t = fmaf(-dy[k], bi[k].z, t);
@@ -313,10 +366,13 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
         q2[k] = fb_clamp1(fmaf(sigma, k2, q2[k]));
         q3[k] = fb_clamp1(fmaf(sigma, k3, q3[k]));
         const float a1 = ea[k] * q1[k];
-        s_slot[a_si[k]] = make_float4(a1, fmaf(ebt[k], q2[k], -(dx[k] * a1)), fmaf(ebt[k], q3[k], -(dy[k] * a1)), 0.f);
-        fbt_st_cluster(a_sj[k], make_float4(-a1, -(ebt[k] * q2[k]), -(ebt[k] * q3[k]), 0.f));
+        s_slot[(pk[k] >> 10) & 8191u] = make_float4(a1, fmaf(ebt[k], q2[k], -(dx[k] * a1)), fmaf(ebt[k], q3[k], -(dy[k] * a1)), 0.f);
+        const float4 ct = make_float4(-a1, -(ebt[k] * q2[k]), -(ebt[k] * q3[k]), 0.f);
+        if (pk[k] >> 27) fbc_st_async(a_sj[k], ct, fbc_mapa(mbA, (pk[k] >> 23) & 15u));
+        else fbt_st_cluster(a_sj[k], ct);
       }
-    fbc_cluster_sync();
+    __syncthreads();                                   // the contributions produced in this tile
+    if (hasA) fbc_mbar_wait(mbA, (uint32_t)(it & 1));  // ... and those delivered by the other tiles
     // ---- primal half-step (nltgv2.cuh:k_primal_vertices): CSR-order sum, prox, box, extragradient
 #pragma unroll
     for (int k = 0; k < FBT_VPT; ++k)
@@ -341,15 +397,24 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
         s_bar[tid + k * FBT_THREADS] = nb;
         if (it + 1 == iters) g.vbar[vb + vid[k]] = nb;
       }
-    fbc_cluster_sync();
+    __syncthreads();  // the tile's points are refreshed, its slots are consumed
+    if (it + 1 < iters) {
+      if (tid < FBT_C && ((rmask >> tid) & 1u)) fbt_mbar_arrive_remote(fbc_mapa(mbB, (uint32_t)tid));
+      if (hasB) fbt_mbar_wait_cluster(mbB, (uint32_t)(it & 1));
+    }
   }
 #pragma unroll
   for (int k = 0; k < FBT_EPT; ++k)
-    if (eid[k] >= 0) g.q4[eb + eid[k]] = make_float4(q1[k], q2[k], q3[k], 0.f);
+    if ((evalid >> k) & 1u) {
+      int lv, off;
+      fbt_edge_of(s_erow, nOwn, tid + k * FBT_THREADS, &lv, &off);
+      g.q4[eb + s_first[lv] + off] = make_float4(q1[k], q2[k], q3[k], 0.f);
+    }
 #pragma unroll
   for (int k = 0; k < FBT_VPT; ++k)
     if (vid[k] >= 0) {
       const size_t v = vb + vid[k];
       g.x[v] = vx[k]; g.w1[v] = vw1[k]; g.w2[v] = vw2[k];
     }
+  fbc_cluster_sync();  // no tile retires while a peer could still address its shared memory
 }
