@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--no-single", action="store_true", help="skip the extra single-stream measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-update", action="store_true", help="skip the full-pipeline (fb_update) leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (1280x720, 20k vertices, 100 iterations) block")
+    ap.add_argument("--total-streams", type=int, default=8,
+                    help="strong-scaling leg (BASELINE configs[4] as written): this many streams in total, stream s -> rank s mod N")
     ap.add_argument("--update-streams", type=int, default=8, help="independent flame::Flame instances per GPU in the e2e_update leg")
     ap.add_argument("--update-frames", type=int, default=36, help="timed frames per stream in the e2e_update leg")
     return ap.parse_args()
@@ -62,6 +65,23 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def roofline_traffic(key):
+    """DRAM bytes per launch of the dominant kernel for workload `key` ("C2x8", "C2x1", "C4x1"), from the
+    `ncu --set full` capture of that workload (profiles/roofline_traffic.json: {key: {bytes, profile}});
+    None when that workload has not been captured -- a number is never reused across workloads."""
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        ent = json.load(open(tp)).get(key)
+        return int(ent["dram_bytes_per_launch"]) if ent else None
+    except Exception:
+        return None
+
+
+def dram_gbs(traffic, launch_us):
+    """Physical DRAM rate of the launch (measured bytes / measured duration), next to the algorithmic one."""
+    return (traffic / (launch_us * 1e-6) / 1e9) if (traffic and launch_us > 0) else None
 
 
 # --------------------------------------------------------------------------------------- clocks
@@ -230,8 +250,10 @@ class GpuRun:
         return int(h2d), int(d2h)
 
 
-def run_gpu_leg(torch, run, steps, warmup, flush_buf, mode, barrier):
-    """Returns (seconds over `steps` timed steps, launches in the timed region, solver ms, solver calls)."""
+def run_gpu_leg(torch, run, steps, warmup, flush_buf, mode, barrier, min_region_s=0.05):
+    """Returns (seconds over `steps` timed steps, launches in ONE timed block, solver ms, solver calls, blocks).
+    A block of `steps` steps is short (2 ms at the driver's --steps 20): when it is below `min_region_s`
+    the block is repeated and the MEDIAN block time is reported (steps stays what was asked for)."""
     ctx = run.ctx
     for k in range(warmup):
         run.step(k, mode)
@@ -241,39 +263,43 @@ def run_gpu_leg(torch, run, steps, warmup, flush_buf, mode, barrier):
     barrier()
     torch.cuda.synchronize()
     l0 = ctx.launch_count()
-    total = 0.0
-    if mode == "resident":
-        # K frames back to back from the device pool (> L2, so no frame is L2-resident when re-read);
-        # one CUDA event before the first and one after the last step on the launching stream, which
-        # is joined on the device with the library's auxiliary streams first
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    launches_block = None
+    times = []
+    k_next = warmup
+
+    def one_block(k0):
+        if mode == "resident":
+            # K frames back to back from the device pool (> L2, so no frame is L2-resident when re-read);
+            # one CUDA event before the first and one after the last step on the launching stream, which
+            # is joined on the device with the library's auxiliary streams first
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                run.step(k0 + i, mode)
+            ctx.pipeline_join()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e-3
+        if mode == "e2e_pipe":
+            # K steps back to back; every step uploads its frames from pinned host memory and its vertex
+            # idepths are read on the host two steps later (triple-buffered), like a streaming consumer:
+            # the host stays two frames ahead of the GPU so the next upload is already in flight
+            t0 = time.perf_counter()
+            for i in range(steps):
+                k = k0 + i
+                run.step(k, mode)
+                if i > 1:
+                    ctx.results_wait(2)
+                    run.consume(k - 2)
+            ctx.results_wait(1)
+            run.consume(k0 + steps - 2)
+            ctx.results_wait(0)
+            run.consume(k0 + steps - 1)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
+        total = 0.0
         for i in range(steps):
-            run.step(warmup + i, mode)
-        ctx.pipeline_join()
-        e1.record()
-        torch.cuda.synchronize()
-        total = e0.elapsed_time(e1) * 1e-3
-    elif mode == "e2e_pipe":
-        # K steps back to back; every step uploads its frames from pinned host memory and its vertex
-        # idepths are read on the host two steps later (triple-buffered), like a streaming consumer:
-        # the host stays two frames ahead of the GPU so the next upload is already in flight
-        t0 = time.perf_counter()
-        for i in range(steps):
-            k = warmup + i
-            run.step(k, mode)
-            if i > 1:
-                ctx.results_wait(2)
-                run.consume(k - 2)
-        ctx.results_wait(1)
-        run.consume(warmup + steps - 2)
-        ctx.results_wait(0)
-        run.consume(warmup + steps - 1)
-        torch.cuda.synchronize()
-        total = time.perf_counter() - t0
-    else:
-        for i in range(steps):
-            k = warmup + i
+            k = k0 + i
             flush_buf.zero_()                      # evict L2 between timed steps (outside the timed bracket)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -281,11 +307,22 @@ def run_gpu_leg(torch, run, steps, warmup, flush_buf, mode, barrier):
             run.consume(k)
             total += time.perf_counter() - t0
         torch.cuda.synchronize()
+        return total
+
+    spent = 0.0
+    while True:
+        t = one_block(k_next)
+        k_next += steps
+        if launches_block is None:
+            launches_block = ctx.launch_count() - l0
+        times.append(t)
+        spent += t
+        if mode == "e2e_sync" or spent >= min_region_s or len(times) >= 25:
+            break
     barrier()
-    launches = ctx.launch_count() - l0
     ms, calls, _ = ctx.profile_get(run.capi.PROF_SOLVE)
     ctx.profile_enable(False)
-    return total, launches, ms, calls
+    return float(np.median(times)), launches_block, ms, calls, len(times)
 
 
 def gpu_main(args):
@@ -304,27 +341,13 @@ def gpu_main(args):
             del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    from flame_ros_b200 import sharding
+    red = sharding.Reducer(dist if world > 1 else None, device="cuda")
+    barrier, max_over_ranks, sum_over_ranks = red.barrier, red.max, red.sum
 
     capi.load_library()
     S = args.streams
-    datas = [WL.StreamData(args.config, seed=rank * S + s) for s in range(S)]
+    datas = [WL.StreamData(args.config, seed=sid) for sid in sharding.stream_ids(rank, world, S)]   # weak: S streams per GPU
     # a dedicated (non-default) torch stream: the library enqueues on it and torch's events see it
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
@@ -351,12 +374,12 @@ def gpu_main(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()   # samples while the three timed legs below run (set-up is excluded)
-    t_res, launches, solve_ms, solve_calls = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "resident", barrier)
+    t_res, launches, solve_ms, solve_calls, blocks_res = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "resident", barrier)
     variant_used = run.ctx.last_solver_variant()
     cluster_size = run.ctx.last_cluster_size()
     transport = run.ctx.last_solver_transport()
-    t_sync, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "e2e_sync", barrier)
-    t_e2e, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "e2e_pipe", barrier)
+    t_sync, _, _, _, _ = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "e2e_sync", barrier)
+    t_e2e, _, _, _, blocks_e2e = run_gpu_leg(torch, run, args.steps, args.warmup, flush, "e2e_pipe", barrier)
     h2d, d2h = run.bytes_per_step()
     run_pool_mib = run.pool_copies * S * WL.POOL_FRAMES * datas[0].W * datas[0].H >> 20
     alg_bytes = sum(d.algorithmic_bytes_per_iter() for d in datas) * datas[0].iters
@@ -367,9 +390,9 @@ def gpu_main(args):
     single = None
     if not args.no_single and S > 1:
         run1 = GpuRun(capi, datas[:1], local_rank, stream_ptr, args.variant)
-        t1, _, ms1, c1 = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, "resident", barrier)
-        t1s, _, _, _ = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, "e2e_sync", barrier)
-        t1e, _, _, _ = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, "e2e_pipe", barrier)
+        t1, _, ms1, c1, _ = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, "resident", barrier)
+        t1s, _, _, _, _ = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, "e2e_sync", barrier)
+        t1e, _, _, _, _ = run_gpu_leg(torch, run1, args.steps, args.warmup, flush, "e2e_pipe", barrier)
         run1.close()
         t1, t1e, t1s = max_over_ranks(t1), max_over_ranks(t1e), max_over_ranks(t1s)
         single = {"streams_per_gpu": 1, "value": world * args.steps / t1, "e2e": world * args.steps / t1e,
@@ -401,6 +424,47 @@ def gpu_main(args):
             upd["vs_cpu_baseline"] = upd["value"] / upd["cpu_baseline"]["value"]
         del u
 
+    # ---- BASELINE configs[4] as written: a fixed batch of --total-streams streams, stream s -> rank s mod N
+    strong = None
+    T = args.total_streams
+    my_ids = sharding.strong_stream_ids(rank, world, T) if T >= world else []
+    if world > 1 and my_ids:
+        sdatas = [WL.StreamData(args.config, seed=sid) for sid in my_ids]
+        runs = GpuRun(capi, sdatas, local_rank, stream_ptr, args.variant)
+        ts, _, mss, cs, _ = run_gpu_leg(torch, runs, args.steps, args.warmup, flush, "resident", barrier)
+        tse, _, _, _, _ = run_gpu_leg(torch, runs, args.steps, args.warmup, flush, "e2e_pipe", barrier)
+        runs.close()
+        ts, tse = max_over_ranks(ts), max_over_ranks(tse)
+        strong = {"scaling": "strong", "streams_total": T, "streams_per_gpu": len(my_ids), "value": T * args.steps / ts,
+                  "e2e": T * args.steps / tse, "unit": UNIT, "ms_per_step": 1e3 * ts / args.steps,
+                  "solver_us_per_launch": 1e3 * mss / max(cs, 1),
+                  "note": "BASELINE configs[4] / SURVEY 8(e) as written: %d streams in total, stream s -> rank s mod %d; with one "
+                          "stream per GPU a step is latency-bound (one cluster of CTAs busy), so the curve flattens" % (T, world)}
+    elif world == 1:
+        strong = {"scaling": "strong", "streams_total": S, "streams_per_gpu": S, "value": None, "unit": UNIT,
+                  "note": "at 1 GPU the strong-scaling point is the headline itself (%d streams on one GPU)" % S}
+
+    # ---- C4 (BASELINE configs[3]: 1280x720, 20k vertices, 100 PD iterations, one stream): its own block
+    c4 = None
+    if not args.no_c4 and args.config != "C4":
+        d4 = [WL.StreamData("C4", seed=5000 + rank)]
+        run4 = GpuRun(capi, d4, local_rank, stream_ptr, args.variant)
+        t4, _, ms4, c4calls, _ = run_gpu_leg(torch, run4, args.steps, args.warmup, flush, "resident", barrier)
+        v4, tr4, cl4 = run4.ctx.last_solver_variant(), run4.ctx.last_solver_transport(), run4.ctx.last_cluster_size()
+        t4e, _, _, _, _ = run_gpu_leg(torch, run4, args.steps, args.warmup, flush, "e2e_pipe", barrier)
+        run4.close()
+        t4, t4e = max_over_ranks(t4), max_over_ranks(t4e)
+        us4 = 1e3 * ms4 / max(c4calls, 1)
+        alg4 = d4[0].algorithmic_bytes_per_iter() * d4[0].iters
+        ach4 = alg4 / (us4 * 1e-6) / 1e9 if us4 > 0 else 0.0
+        c4 = {"workload": "C4 (BASELINE configs[3]): 1280x720, %d vertices, %d edges, %d PD iterations, 1 stream per GPU" % (d4[0].V, d4[0].E, d4[0].iters),
+              "value": world * args.steps / t4, "e2e": world * args.steps / t4e, "unit": UNIT, "ms_per_step": 1e3 * t4 / args.steps,
+              "solver_variant": v4, "solver_transport": {1: "cluster (DSMEM)", 2: "L2 mailboxes"}.get(tr4), "ctas_per_stream": cl4,
+              "roofline": {"bound": "hbm", "achieved": ach4, "peak": peak, "unit": "GB/s", "frac": ach4 / peak,
+                           "algorithmic_bytes_per_launch": alg4, "launch_us": us4,
+                           "traffic": roofline_traffic("C4x1"), "dram_gbs": dram_gbs(roofline_traffic("C4x1"), us4)}}
+        del d4
+
     t_res, t_e2e, t_sync = max_over_ranks(t_res), max_over_ranks(t_e2e), max_over_ranks(t_sync)
     launches_all = int(sum_over_ranks(launches))
     frames = world * S * args.steps
@@ -409,13 +473,7 @@ def gpu_main(args):
 
     out = None
     if rank == 0:
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("solver_dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        traffic = roofline_traffic("%sx%d" % (args.config, S))
         out = {
             "metric": METRIC, "value": frames / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
@@ -445,10 +503,13 @@ def gpu_main(args):
             "e2e_sync": {"value": frames / t_sync, "unit": UNIT, "ms_per_step": 1e3 * t_sync / args.steps,
                          "mode": "blocking call per step, L2 flushed between steps"},
             "gpu_launches": launches_all,
+            "timed_blocks": {"value": blocks_res, "e2e": blocks_e2e,
+                             "note": "a block = --steps steps; blocks are repeated until >= 50 ms were timed and the median block is reported; gpu_launches counts one block"},
+            "host": {"cores": host_cores(), "ranks": world},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": {2: "k_nltgv2_cluster", 3: "k_nltgv2_grid"}.get(variant_used, "k_dual_edges+k_primal_vertices"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "dram_gbs": dram_gbs(traffic, 1e3 * solve_ms_per_launch), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_us": 1e3 * solve_ms_per_launch,
                          "note": "algorithmic = (40E+64V) B/iter x iters x streams (SURVEY 8d); the persistent solvers keep the "
                                  "graph in shared memory/registers across iterations, so achieved may exceed the HBM peak "
@@ -458,6 +519,10 @@ def gpu_main(args):
             out["single_stream"] = single
         if upd:
             out["e2e_update"] = upd
+        if strong:
+            out["strong_scaling"] = strong
+        if c4:
+            out["configs"] = {"C4": c4}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # the CPU baseline is an N=1 figure
         out["cpu_baseline"] = cpu_baseline(args, datas, sample_steps=3)
     if world > 1:

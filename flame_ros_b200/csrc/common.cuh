@@ -62,6 +62,8 @@ struct fb_ctx {
   float4* q4 = nullptr;     // (q1, q2, q3, 0)            [S*maxE]
   int32_t* row = nullptr;   // CSR row pointers           [S*(maxV+1)]
   int32_t* inc = nullptr;   // (edge<<1)|role             [S*2*maxE]
+  int32_t* epos = nullptr;  // position of edge e in its TARGET's CSR row [S*maxE] (variant 5's slot address)
+  int32_t* vnin = nullptr;  // in-degree of every vertex  [S*maxV]
   int32_t* nV = nullptr;    // device counts              [S]
   int32_t* nE = nullptr;
   std::vector<int32_t> hV, hE;       // host mirrors of the counts

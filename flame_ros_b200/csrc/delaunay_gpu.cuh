@@ -415,7 +415,8 @@ struct DsgCarry {
 __global__ void __launch_bounds__(128)
 k_ds_csr(DelGpu d, DsgCarry q, int s, int maxV, int maxE, const int32_t* __restrict__ vfeat,
          const float2* __restrict__ vpos, const int2* __restrict__ eij, const int32_t* __restrict__ row,
-         int32_t* __restrict__ inc, float* z, float* wt, float* x, float* w1, float* w2, float4* vbar, float4* q4) {
+         int32_t* __restrict__ inc, float* z, float* wt, float* x, float* w1, float* w2, float4* vbar, float4* q4,
+         int32_t* __restrict__ epos, int32_t* __restrict__ vnin) {
   int32_t* meta = d.meta + (size_t)s * DSG_META;
   const int V = meta[DSG_NV];
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -447,7 +448,10 @@ k_ds_csr(DelGpu d, DsgCarry q, int s, int maxV, int maxE, const int32_t* __restr
     w2[v] = 0.0f;
     vbar[v] = make_float4(x0, 0.0f, 0.0f, 0.0f);
   }
-  if (meta[DSG_NT] == 0) return;
+  if (meta[DSG_NT] == 0) {
+    vnin[v] = 0;
+    return;
+  }
   const int dg = d.deg[vb + v], deg = dg & 0xff;
   const int e0 = d.eoff[ob + v], e1 = d.eoff[ob + v + 1];
   // ---- out-edges: carry q over from the previous graph (both endpoints persisted, edge existed)
@@ -490,8 +494,10 @@ k_ds_csr(DelGpu d, DsgCarry q, int s, int maxV, int maxE, const int32_t* __restr
       atomicOr(&meta[DSG_ERR], 0x800);  // u does not list v
       e = 0;
     }
+    epos[e] = k;  // position of the edge in its target's row: the tile solver's slot address
     inc[r++] = (e << 1) | 1;
   }
+  vnin[v] = ni;
   for (int e = e0; e < e1; ++e) inc[r++] = e << 1;
 }
 

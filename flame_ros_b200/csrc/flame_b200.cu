@@ -91,7 +91,7 @@ extern "C" void fb_host_free(void* p) {
 static void free_all(fb_ctx* c) {
   cudaFree(c->vbar); cudaFree(c->x); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->z);
   cudaFree(c->wt); cudaFree(c->ec); cudaFree(c->eij); cudaFree(c->q4); cudaFree(c->row);
-  cudaFree(c->inc); cudaFree(c->nV); cudaFree(c->nE); cudaFree(c->vfeat); cudaFree(c->vpos);
+  cudaFree(c->inc); cudaFree(c->epos); cudaFree(c->vnin); cudaFree(c->nV); cudaFree(c->nE); cudaFree(c->vfeat); cudaFree(c->vpos);
   cudaFree(c->costs); cudaFree(c->imgs); cudaFree(c->d_pose); cudaFree(c->d_K);
   cudaFree(c->d_cmp); cudaFree(c->d_geo); cudaFree(c->pool); cudaFree(c->f_uref);
   cudaFree(c->f_mu); cudaFree(c->f_var); cudaFree(c->f_drop); cudaFree(c->f_alive);
@@ -163,6 +163,7 @@ extern "C" fb_ctx* fb_create(int device, int n_streams, int width, int height, i
   A(dalloc(&c->vbar, nv)); A(dalloc(&c->x, nv)); A(dalloc(&c->w1, nv)); A(dalloc(&c->w2, nv));
   A(dalloc(&c->z, nv)); A(dalloc(&c->wt, nv)); A(dalloc(&c->ec, ne)); A(dalloc(&c->eij, ne));
   A(dalloc(&c->q4, ne)); A(dalloc(&c->row, S * (max_vertices + 1))); A(dalloc(&c->inc, 2 * ne));
+  A(dalloc(&c->epos, ne)); A(dalloc(&c->vnin, nv));
   A(dalloc(&c->nV, S)); A(dalloc(&c->nE, S)); A(dalloc(&c->vfeat, nv)); A(dalloc(&c->vpos, nv));
   A(dalloc(&c->costs, 2 * S));
   A(dalloc(&c->imgs, S * n_slots * npx)); A(dalloc(&c->d_pose, S * n_slots * 7));
@@ -279,17 +280,27 @@ extern "C" int fb_graph_set(fb_ctx* c, int s, int V, int E, const float* pos,
       inc[fill[eij[e].y]++] = (e << 1) | 1;
     }
   }
+  // position of every edge in its target's row and the in-degrees (in-edges come first in a row:
+  // edges are sorted by (i,j) with i < j), used by the device-planned tile solver
+  std::vector<int32_t> epos(E), vnin(V, 0);
+  for (int v = 0; v < V; ++v)
+    for (int k = row[v]; k < row[v + 1] && (inc[k] & 1); ++k) {
+      epos[inc[k] >> 1] = k - row[v];
+      vnin[v]++;
+    }
   const size_t vb = (size_t)s * c->maxV, eb = (size_t)s * c->maxE;
   cudaStream_t st = c->stream;
   if (E) {
     FB_CUDA(c, cudaMemcpyAsync(c->ec + eb, ec.data(), sizeof(float4) * E, cudaMemcpyHostToDevice, st));
     FB_CUDA(c, cudaMemcpyAsync(c->eij + eb, eij.data(), sizeof(int2) * E, cudaMemcpyHostToDevice, st));
     FB_CUDA(c, cudaMemcpyAsync(c->inc + 2 * eb, inc.data(), sizeof(int32_t) * 2 * E, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(c->epos + eb, epos.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, st));
     FB_CUDA(c, cudaMemsetAsync(c->q4 + eb, 0, sizeof(float4) * E, st));
   }
   FB_CUDA(c, cudaMemcpyAsync(c->row + (size_t)s * (c->maxV + 1), row.data(), sizeof(int32_t) * (V + 1), cudaMemcpyHostToDevice, st));
   if (V) {
     FB_CUDA(c, cudaMemcpyAsync(c->vpos + vb, pos, sizeof(float2) * V, cudaMemcpyHostToDevice, st));
+    FB_CUDA(c, cudaMemcpyAsync(c->vnin + vb, vnin.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, st));
     FB_CUDA(c, cudaMemsetAsync(c->vbar + vb, 0, sizeof(float4) * V, st));
     FB_CUDA(c, cudaMemsetAsync(c->x + vb, 0, sizeof(float) * V, st));
     FB_CUDA(c, cudaMemsetAsync(c->w1 + vb, 0, sizeof(float) * V, st));

@@ -433,7 +433,7 @@ static int update_graph_device(fb_ctx* c, int s) {
               S.have_graph ? c->idmap + (size_t)s * npx : nullptr, c->W, c->H, p.adaptive_data_weights, p.init_with_prediction};
   k_ds_csr<<<fb_div_up(c->maxV, 128), 128, 0, st>>>(D, cq, s, c->maxV, c->maxE, c->vfeat + vb, c->vpos + vb, c->eij + eb,
                                                    c->row + (size_t)s * (c->maxV + 1), c->inc + 2 * eb, c->z + vb, c->wt + vb,
-                                                   c->x + vb, c->w1 + vb, c->w2 + vb, c->vbar + vb, c->q4 + eb);
+                                                   c->x + vb, c->w1 + vb, c->w2 + vb, c->vbar + vb, c->q4 + eb, c->epos + eb, c->vnin + vb);
   c->launches += 6;
   FB_CUDA(c, cudaGetLastError());
   S.builds++;

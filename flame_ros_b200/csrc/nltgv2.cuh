@@ -28,6 +28,8 @@ struct GraphView {
   float4* q4;
   const int32_t* row;
   const int32_t* inc;
+  const int32_t* epos;  // position of edge e in its target's CSR row
+  const int32_t* vnin;  // in-degree per vertex
   const int32_t* nV;
   const int32_t* nE;
   int maxV, maxE;
@@ -38,6 +40,7 @@ static GraphView graph_view(fb_ctx* c) {
   GraphView g;
   g.vbar = c->vbar; g.x = c->x; g.w1 = c->w1; g.w2 = c->w2; g.z = c->z; g.wt = c->wt;
   g.ec = c->ec; g.eij = c->eij; g.q4 = c->q4; g.row = c->row; g.inc = c->inc;
+  g.epos = c->epos; g.vnin = c->vnin;
   g.nV = c->nV; g.nE = c->nE; g.maxV = c->maxV; g.maxE = c->maxE;
   g.only = -1;
   return g;

@@ -259,10 +259,10 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
       vdeg[k] = r1 - r0;
       int nrem = 0;
       unsigned mask = 0u;
-      while (nin < vdeg[k] && (inc[r0 + nin] & 1)) {  // in-edges come first (ascending edge id)
-        const int ts = vtile[g.eij[eb + (inc[r0 + nin] >> 1)].x];
+      nin = g.vnin[vb + v];  // in-edges come first in the row (ascending edge id)
+      for (int j = 0; j < nin; ++j) {  // independent loads: the tiles of the in-edges' sources
+        const int ts = vtile[g.eij[eb + (inc[r0 + j] >> 1)].x];
         if (ts != r) { ++nrem; mask |= 1u << ts; }
-        ++nin;
       }
       if (nrem) { atomicAdd(&s_nrin, nrem); atomicOr(&s_rmask, mask); }
       od = vdeg[k] - nin;
@@ -321,13 +321,15 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
       ea[k] = c.x; ebt[k] = c.y; dx[k] = c.z; dy[k] = c.w;
       q1[k] = q.x; q2[k] = q.y; q3[k] = q.z;
       const int j = ij.y, tj = vtile[j], lj = vloc[j];
-      int pos = 0;  // position of e among j's incidences (in-edges, ascending edge id)
-      {
-        const int r0 = row[j], want = (e << 1) | 1;
-        while (inc[r0 + pos] != want) ++pos;
+      const int pos = g.epos[eb + e];  // position of e among j's incidences
+      // a target in this tile is addressed in the CTA's own window (plain ld/st.shared: full shared-memory
+      // bandwidth); only targets in other tiles go through the cluster window (DSMEM, ~20 B/clk per SM)
+      a_bj[k] = bar_u32 + 16u * (uint32_t)lj;
+      a_sj[k] = slot_u32 + 16u * (uint32_t)(__ldcg(g_lrow + j) + pos);
+      if (tj != r) {
+        a_bj[k] = fbc_mapa(a_bj[k], (uint32_t)tj);
+        a_sj[k] = fbc_mapa(a_sj[k], (uint32_t)tj);
       }
-      a_bj[k] = fbc_mapa(bar_u32 + 16u * (uint32_t)lj, (uint32_t)tj);
-      a_sj[k] = fbc_mapa(slot_u32 + 16u * (uint32_t)(__ldcg(g_lrow + j) + pos), (uint32_t)tj);
       pk[k] = (uint32_t)lv | ((uint32_t)(s_lrow[lv] + s_nin[lv] + off) << 10) | ((uint32_t)tj << 23) | (tj != r ? 1u << 27 : 0u);
       if (tj != r) atomicOr(&s_smask, 1u << tj);
     }
@@ -346,22 +348,17 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
   for (int it = 0; it < iters; ++it) {
     if (hasA && tid == 0) fbc_mbar_expect(mbA, 16u * (uint32_t)nRin);  // phase `it` of A
     // ---- dual half-step (nltgv2.cuh:k_dual_edges) + K^T q into the CSR slots of both endpoints
-    float4 bi[FBT_EPT], bj[FBT_EPT];
 #pragma unroll
     for (int k = 0; k < FBT_EPT; ++k)
       if (k < kmax && (evalid >> k) & 1u) {
-        bi[k] = fbc_lds(bar_u32 + ((pk[k] & 1023u) << 4));
-        bj[k] = fbt_ld_cluster(a_bj[k]);
-      }
-#pragma unroll
-    for (int k = 0; k < FBT_EPT; ++k)
-      if (k < kmax && (evalid >> k) & 1u) {
-        float t = bi[k].x - bj[k].x;
-        t = fmaf(-dx[k], bi[k].y, t);
-        t = fmaf(-dy[k], bi[k].z, t);
+        const float4 bik = fbc_lds(bar_u32 + ((pk[k] & 1023u) << 4));
+        const float4 bjk = (pk[k] >> 27) ? fbt_ld_cluster(a_bj[k]) : fbc_lds(a_bj[k]);
+        float t = bik.x - bjk.x;
+        t = fmaf(-dx[k], bik.y, t);
+        t = fmaf(-dy[k], bik.z, t);
         const float k1 = ea[k] * t;
-        const float k2 = ebt[k] * (bi[k].y - bj[k].y);
-        const float k3 = ebt[k] * (bi[k].z - bj[k].z);
+        const float k2 = ebt[k] * (bik.y - bjk.y);
+        const float k3 = ebt[k] * (bik.z - bjk.z);
         q1[k] = fb_clamp1(fmaf(sigma, k1, q1[k]));
         q2[k] = fb_clamp1(fmaf(sigma, k2, q2[k]));
         q3[k] = fb_clamp1(fmaf(sigma, k3, q3[k]));
@@ -369,7 +366,7 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
         s_slot[(pk[k] >> 10) & 8191u] = make_float4(a1, fmaf(ebt[k], q2[k], -(dx[k] * a1)), fmaf(ebt[k], q3[k], -(dy[k] * a1)), 0.f);
         const float4 ct = make_float4(-a1, -(ebt[k] * q2[k]), -(ebt[k] * q3[k]), 0.f);
         if (pk[k] >> 27) fbc_st_async(a_sj[k], ct, fbc_mapa(mbA, (pk[k] >> 23) & 15u));
-        else fbt_st_cluster(a_sj[k], ct);
+        else fbc_sts(a_sj[k], ct);
       }
     __syncthreads();                                   // the contributions produced in this tile
     if (hasA) fbc_mbar_wait(mbA, (uint32_t)(it & 1));  // ... and those delivered by the other tiles

@@ -19,6 +19,14 @@ def owner_of(stream_id, streams_per_rank):
     return stream_id // streams_per_rank
 
 
+def strong_stream_ids(rank, world, total_streams):
+    """BASELINE configs[4] as written: a FIXED batch of `total_streams`
+    streams, stream s -> rank s mod world (8 / 4 / 2 / 1 streams per GPU at 1 / 2 / 4 / 8 GPUs)."""
+    if not (0 <= rank < world) or total_streams < 1:
+        raise ValueError("bad rank/world/total_streams")
+    return [s for s in range(total_streams) if s % world == rank]
+
+
 class Reducer:
     """max / sum over ranks of python floats; identity when not distributed."""
 

@@ -10,6 +10,7 @@ from flame_ros_b200 import capi, synth
 
 W, H, win = 640, 480, int(sys.argv[1]) if len(sys.argv) > 1 else 8
 tri = int(sys.argv[2]) if len(sys.argv) > 2 else 0   # 0 = device sync_graph + triangulate, 1 = host
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 50
 n = 60
 sc = synth.Scene(0, tex_size=1024)
 poses = synth.stream_poses(n, step=0.01)
@@ -17,6 +18,7 @@ frames = [sc.render(synth.K_VGA, poses[k], W, H)[0] for k in range(n)]
 up = capi.default_update_params()
 up.detection_win_size = win
 up.triangulator = tri
+up.iters = iters
 with capi.Context(1, W, H, 8, 8192, 8192, 24576) as ctx:
     ctx.set_intrinsics(0, synth.K_VGA)
     ctx.set_update_params(up)

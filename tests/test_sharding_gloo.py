@@ -70,3 +70,9 @@ def test_stream_ids_cover_without_overlap():
         assert all(sharding.owner_of(s, 3) == s // 3 for s in seen)
     with pytest.raises(ValueError):
         sharding.stream_ids(2, 2, 1)
+    # BASELINE configs[4] as written: 8 streams in total, stream s -> rank s mod world
+    for world in (1, 2, 4, 8):
+        parts = [sharding.strong_stream_ids(r, world, 8) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(8))
+        assert all(len(p) == 8 // world for p in parts)
+        assert all(s % world == r for r, p in enumerate(parts) for s in p)
