@@ -180,9 +180,11 @@ class GpuRun:
             ctx.features_set(s, d.u_ref, np.zeros(d.V, np.int32), z0, np.full(d.V, WL.VAR0, np.float32))
         # e2e leg: the camera frames sit in pinned host memory (as a capture driver would deliver
         # them) and the vertex idepths come back into a pinned buffer
-        self.h_frames = capi.PinnedBuffer((self.S, WL.POOL_FRAMES, d0.H, d0.W), np.uint8)
+        # frame-major: the S frames of one step are contiguous (one multi-camera capture buffer), so a
+        # step's upload is a single transfer
+        self.h_frames = capi.PinnedBuffer((WL.POOL_FRAMES, self.S, d0.H, d0.W), np.uint8)
         for s, d in enumerate(datas):
-            np.copyto(self.h_frames.array[s], d.frames)
+            np.copyto(self.h_frames.array[:, s], d.frames)
         self.h_x = capi.PinnedBuffer((3, self.S, V), np.float32)   # triple-buffered results
         self.maxV = V
         self.cmp = np.full(self.S, WL.CMP_SLOT, np.int32)
@@ -208,8 +210,8 @@ class GpuRun:
             cmp_poses = np.ascontiguousarray(np.stack([d.poses[cmp_idx] for d in self.datas]), np.float32)
             ref_pool = np.array([(r * S + s) * WL.POOL_FRAMES + ref_idx for s in range(S)], np.int32)
             cmp_pool = np.array([(r * S + s) * WL.POOL_FRAMES + cmp_idx for s in range(S)], np.int32)
-            ref_ptr = (C.c_void_p * S)(*[self.h_frames.array[s, ref_idx].ctypes.data for s in range(S)])
-            cmp_ptr = (C.c_void_p * S)(*[self.h_frames.array[s, cmp_idx].ctypes.data for s in range(S)])
+            ref_ptr = (C.c_void_p * S)(*[self.h_frames.array[ref_idx, s].ctypes.data for s in range(S)])
+            cmp_ptr = (C.c_void_p * S)(*[self.h_frames.array[cmp_idx, s].ctypes.data for s in range(S)])
             self._keep += [ref_poses, cmp_poses, ref_pool, cmp_pool, ref_ptr, cmp_ptr]
             for mode in ("resident", "e2e_sync", "e2e_pipe"):
                 d = capi.StepDesc()
@@ -226,6 +228,10 @@ class GpuRun:
                 d.ref_poses = ref_poses.ctypes.data_as(C.POINTER(C.c_float))
                 d.cmp_poses = cmp_poses.ctypes.data_as(C.POINTER(C.c_float))
                 d.mu0, d.var0, d.adaptive_weights = WL.MU0, WL.VAR0, 0
+                # the poseframe of this epoch is the frame of the previous step, already on the device
+                # (table entry 0 also serves the very first call, which has no previous frame: it uploads)
+                if newpf and k > 0:
+                    d.ref_from_slot = 1 + (WL.CMP_SLOT + ((k - 1) % 2) if d.pipelined else WL.CMP_SLOT)
                 d.iters, d.variant, d.rparams = self.iters, self.variant, self.params
                 table[(k, mode)] = d
         return table, period
@@ -245,7 +251,7 @@ class GpuRun:
 
     def bytes_per_step(self):
         d = self.datas[0]
-        h2d = self.S * (d.W * d.H + 28) * (1.0 + 1.0 / WL.EPOCH)
+        h2d = self.S * (d.W * d.H + 28)   # one frame + pose per stream; poseframes are frames already uploaded
         d2h = self.S * self.maxV * 4
         return int(h2d), int(d2h)
 

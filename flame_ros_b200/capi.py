@@ -81,7 +81,7 @@ class StepDesc(C.Structure):
                 ("ref_poses", C.POINTER(C.c_float)), ("cmp_poses", C.POINTER(C.c_float)),
                 ("mu0", C.c_float), ("var0", C.c_float), ("adaptive_weights", C.c_int),
                 ("iters", C.c_int), ("variant", C.c_int), ("rparams", NLTGV2Params),
-                ("x_out", C.POINTER(C.c_float)), ("pipelined", C.c_int)]
+                ("x_out", C.POINTER(C.c_float)), ("pipelined", C.c_int), ("ref_from_slot", C.c_int)]
 
 
 _LIB = None

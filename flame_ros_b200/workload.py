@@ -32,6 +32,13 @@ class StreamData:
         self.poses = synth.stream_poses(POOL_FRAMES)
         # second epoch restarts from its own poseframe: same relative motion, different viewpoint
         self.frames = np.stack([sc.render(self.K, self.poses[k], W, H)[0] for k in range(POOL_FRAMES)])
+        # A poseframe is the current frame flagged is_poseframe (/root/reference/src/flame_nodelet.cc:634):
+        # each epoch's poseframe is the LAST frame of the previous epoch (the stream cycles), so a new
+        # poseframe never needs its own upload
+        half = POOL_FRAMES // 2
+        for dst, src in ((half, half - 1), (0, POOL_FRAMES - 1)):
+            self.frames[dst] = self.frames[src]
+            self.poses[dst] = self.poses[src]
         feats = synth.grid_features(W, H, win, border=8, seed=100 + seed)
         if len(feats) < nv:
             rng = np.random.default_rng(200 + seed)

@@ -98,7 +98,8 @@ class Flame {
     FLAME_ASSERT(img_new.rows == height_ && img_new.cols == width_);
     float pose[7];
     toPose(T_new, pose);
-    const int rc = fb_update(ctx_, 0, time, (int)img_id, pose, img_new.data, (int)img_new.step, is_poseframe ? 1 : 0);
+    const int rc = fb_update(ctx_, 0, time, (int)img_id, pose, reinterpret_cast<const uint8_t*>(img_new.data),
+                             (int)static_cast<size_t>(img_new.step), is_poseframe ? 1 : 0);  // cv::Mat::step is a MatStep
     if (rc < 0) throw std::runtime_error(std::string("flame::Flame::update: ") + fb_last_error(ctx_));
     refreshStats();
     return rc == 1;
@@ -126,13 +127,13 @@ class Flame {
   void getFilteredInverseDepthMap(Mat1f* idepthmap) {
     std::lock_guard<std::mutex> lock(mtx_);
     idepthmap->create(height_, width_);
-    check(fb_get_idepthmap(ctx_, 0, &filter_, idepthmap->ptr(0)));
+    check(fb_get_idepthmap(ctx_, 0, &filter_, reinterpret_cast<float*>(idepthmap->data)));  // cv::Mat::data is uchar*
   }
 
   Mat1f getInverseDepthMap() {
     std::lock_guard<std::mutex> lock(mtx_);
     Mat1f m(height_, width_);
-    check(fb_get_idepthmap(ctx_, 0, nullptr, m.ptr(0)));
+    check(fb_get_idepthmap(ctx_, 0, nullptr, reinterpret_cast<float*>(m.data)));
     return m;
   }
 
@@ -195,15 +196,22 @@ class Flame {
   void refreshStats() {
     // stage names = FlameStats.msg timing keys (/root/reference/src/utils.cc:143-156)
     static const char* const kTimings[] = {"update", "frame_creation", "update_idepths", "project_features",
-                                           "sync_graph", "triangulate", "nltgv2", "interpolate", "detection"};
+                                           "sync_graph", "triangulate", "nltgv2", "interpolate", "detection", "keyframe"};
     for (const char* k : kTimings) {
       double v = 0.0;
       if (fb_get_stat(ctx_, 0, k, &v) == FB_OK) stats_.setTiming(k, v);
     }
-    static const char* const kStats[] = {"num_vertices", "num_edges", "num_triangles"};
+    // the keys the wrapper looks up (/root/reference/src/utils.cc:117-122): num_feats, num_vtx, num_tris,
+    // num_edges, coverage; fps / fps_max (:138-139) from the update time
+    static const char* const kStats[] = {"num_feats", "num_vtx", "num_tris", "num_edges", "coverage",
+                                         "num_vertices", "num_triangles"};
     for (const char* k : kStats) {
       double v = 0.0;
       if (fb_get_stat(ctx_, 0, k, &v) == FB_OK) stats_.set(k, v);
+    }
+    {
+      double ms = 0.0;
+      if (fb_get_stat(ctx_, 0, "update", &ms) == FB_OK && ms > 0.0) stats_.set("fps_max", 1000.0 / ms);
     }
     int32_t c[FB_NUM_COUNTERS];
     if (fb_idepth_counters(ctx_, 0, c) == FB_OK) {  // /root/reference/src/utils.cc:124-129
@@ -214,7 +222,7 @@ class Flame {
       stats_.set("num_fail_max_var", c[FB_FAIL_MAX_VAR]);
       stats_.set("num_fail_max_dropouts", c[FB_FAIL_MAX_DROPOUTS]);
     }
-    double sm = 0.0, da = 0.0, nv = stats_.stats("num_vertices");
+    double sm = 0.0, da = 0.0, nv = stats_.stats("num_vtx");
     if (nv > 0 && fb_costs(ctx_, 0, params_.rparams.data_factor, &sm, &da) == FB_OK) {  // utils.cc:131-136
       stats_.set("nltgv2_total_smoothness_cost", sm);
       stats_.set("nltgv2_avg_smoothness_cost", sm / nv);

@@ -227,6 +227,10 @@ typedef struct {
                                        slots), the solve of frame k overlaps the epipolar update of
                                        frame k+1, x_out (pinned) is filled asynchronously and the
                                        call never blocks; fb_results_wait() waits for a frame's x_out. */
+  int ref_from_slot;                /* new_poseframe steps: 1 + slot whose frame BECOMES the poseframe (device
+                                       copy, no second upload) -- in the reference a poseframe is the current
+                                       frame flagged is_poseframe (/root/reference/src/flame_nodelet.cc:634), not
+                                       a separate image.  0 = upload ref_images / ref_pool_idx as before. */
 } fb_step_desc;
 int fb_hotpath_step(fb_ctx* ctx, const fb_step_desc* d);
 /* Waits until the x_out of the pipelined step issued `lag` calls ago (0 = the latest) has landed. */

@@ -81,6 +81,21 @@ int main() {
   int covered = 0;
   for (int i = 0; i < W * H; ++i) covered += std::isnan(raw.ptr(0)[i]) ? 0 : 1;
   flame::Mat3b dbg = sensor->getDebugImageInverseDepthMap();
+  // the stats keys the wrapper's fillStati / fillStatf look up (/root/reference/src/utils.cc:117-122,143-156)
+  const auto& sm = sensor->stats().stats();
+  const auto& tm = sensor->stats().timings();
+  int keys_ok = 1;
+  for (const char* k : {"num_feats", "num_vtx", "num_tris", "num_edges", "coverage", "num_idepth_updates",
+                        "num_fail_max_var", "num_fail_max_dropouts", "num_fail_ref_patch_grad",
+                        "num_fail_ambiguous_match", "num_fail_max_cost", "nltgv2_total_smoothness_cost",
+                        "nltgv2_avg_smoothness_cost", "nltgv2_total_data_cost", "nltgv2_avg_data_cost", "fps_max"})
+    if (!sm.count(k)) { std::printf("missing stat %s\n", k); keys_ok = 0; }
+  for (const char* k : {"update", "update_locking"})
+    if (!tm.count(k)) { std::printf("missing timing %s\n", k); keys_ok = 0; }
+  std::printf("{\"keys_ok\": %d, \"num_vtx\": %.0f, \"num_tris\": %.0f, \"num_feats\": %.0f, \"coverage\": %.4f}\n", keys_ok,
+              sensor->stats().stats("num_vtx"), sensor->stats().stats("num_tris"), sensor->stats().stats("num_feats"),
+              sensor->stats().stats("coverage"));
+  if (!keys_ok || sensor->stats().stats("num_vtx") != (double)vtx.size() || sensor->stats().stats("num_tris") != (double)tris.size()) return 2;
   std::printf("{\"updates\": %d, \"vertices\": %zu, \"triangles\": %zu, \"edges\": %zu, \"features\": %zu, "
               "\"median_idepth\": %.4f, \"covered\": %d, \"update_ms\": %.3f, \"num_idepth_updates\": %.0f, \"dbg_rows\": %d}\n",
               n_ok, vtx.size(), tris.size(), edges.size(), fpts.size(), med, covered,

@@ -52,3 +52,38 @@ def test_shim_runs_a_stream_on_the_gpu(capi):
     out = json.loads(res.stdout.strip().splitlines()[-1])
     assert out["updates"] >= 8 and out["vertices"] > 50 and abs(out["median_idepth"] - 0.5) < 0.05
     assert out["dbg_rows"] == 240 and out["num_idepth_updates"] > 0
+
+
+def test_shim_compiles_against_real_header_signatures():
+    """include/flame/flame.h down its real-headers branch (Eigen / Sophus / OpenCV) against stubs that
+    carry the real signatures (cv::Mat::data is uchar*, cv::Mat::step is a MatStep, Eigen's (w,x,y,z)
+    quaternion constructor ...), driven with the reference frontends' calls
+    (/root/reference/src/flame_nodelet.cc:523-527,634,669-688,721-723): compile-only, so a catkin
+    build is not the first to discover a mismatch."""
+    src = os.path.join(ROOT, "tests", "cpp", "shim_real_signatures.cc")
+    cmd = ["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "cpp", "stubs"),
+           "-I", os.path.join(ROOT, "include"), src]
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+
+
+def test_cmake_package_file_exports_what_the_reference_uses():
+    """cmake/flameConfig.cmake: `find_package(flame REQUIRED)` (/root/reference/CMakeLists.txt:57) must
+    end up with flame_INCLUDE_DIRS and flame_LIBRARIES (CMakeLists.txt:205, src/CMakeLists.txt:11)."""
+    txt = open(os.path.join(ROOT, "cmake", "flameConfig.cmake")).read()
+    for var in ("flame_INCLUDE_DIRS", "flame_LIBRARIES", "flame_FOUND"):
+        assert "set(%s" % var in txt
+    cmake = __import__("shutil").which("cmake")
+    if not cmake:
+        pytest.skip("cmake not on PATH")
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "CMakeLists.txt"), "w").write(
+            "cmake_minimum_required(VERSION 3.5)\nproject(probe NONE)\nfind_package(flame REQUIRED)\n"
+            "message(STATUS \"INC=${flame_INCLUDE_DIRS}\")\nmessage(STATUS \"LIB=${flame_LIBRARIES}\")\n")
+        res = subprocess.run([cmake, "-S", tmp, "-B", os.path.join(tmp, "b"), "-Dflame_DIR=" + os.path.join(ROOT, "cmake")],
+                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert res.returncode == 0, res.stdout
+        assert "INC=" + os.path.join(ROOT, "include") in res.stdout and "libflame_b200.so" in res.stdout
