@@ -46,6 +46,11 @@ struct fb_ctx {
   bool pipe_hold = false;                // inside a pipelined step: internal calls must not drain
   bool pipe_dirty = false;               // pipelined work may be in flight on the auxiliary streams
   std::vector<cudaEvent_t> ev_ready, ev_free;
+  // landing buffers of the pipelined step: S contiguous frames per buffer, so a step whose host
+  // frames are contiguous goes up as ONE linear transfer (8 separate 300 kB copies cost ~12 us each)
+  uint8_t* incoming = nullptr;            // [2][S][H*W]
+  std::vector<int> slot_landing;          // per slot: -1 = the frame is in its slot, else landing buffer index
+  const uint8_t* epi_cmp_frames = nullptr;  // consumed by the next fb_idepth_update
   cudaEvent_t ev_result[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t n_pipelined = 0;
   std::string err;

@@ -153,35 +153,50 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
     s_bad = 0;
   }
   __syncthreads();
-  // ---- selection in ascending feature index
+  // ---- selection in ascending feature index: every thread takes a run of consecutive features, so
+  // one block scan ranks them all
+  const int FI = (q.maxF + DSG_THREADS - 1) / DSG_THREADS;
   int carry = 0;
-  for (int base = 0; base < q.maxF; base += DSG_THREADS) {
-    const int f = base + tid;
-    int flag = (f < q.maxF && q.valid[f] && q.var_cur[f] < q.var_max) ? 1 : 0;
-    if (flag && q.use_height) {
-      const float2 u = q.u_cur[f];
-      const float h = dsg_world_height(q.K, q.pose_cur, u.x, u.y, q.mu_cur[f]);
-      if (!(h >= q.hmin && h <= q.hmax)) flag = 0;
+  {
+    const int f0 = tid * FI, f1 = min(q.maxF, f0 + FI);
+    int cnt = 0;
+    for (int f = f0; f < f1; ++f) {
+      int flag = (q.valid[f] && q.var_cur[f] < q.var_max) ? 1 : 0;
+      if (flag && q.use_height) {
+        const float2 u = q.u_cur[f];
+        const float h = dsg_world_height(q.K, q.pose_cur, u.x, u.y, q.mu_cur[f]);
+        if (!(h >= q.hmin && h <= q.hmax)) flag = 0;
+      }
+      cnt += flag;
     }
     int tot;
-    const int rank = carry + dsg_block_scan(flag, s_warp, &tot);
-    int v = -1;
-    if (flag && rank < q.maxV) {
-      v = rank;
-      const float2 u = q.u_cur[f];
-      int bad = 0;
-      DsPt l;
-      l.x = ds_lattice(u.x, &bad);
-      l.y = ds_lattice(u.y, &bad);
-      if (bad) s_bad = 1;
-      vfeat[v] = f;
-      vpos[v] = u;
-      vxy[v] = l;
-      atomicMin(&s_box[0], l.x); atomicMin(&s_box[1], l.y);
-      atomicMax(&s_box[2], l.x); atomicMax(&s_box[3], l.y);
+    int rank = dsg_block_scan(cnt, s_warp, &tot);
+    carry = tot;
+    for (int f = f0; f < f1; ++f) {
+      int flag = (q.valid[f] && q.var_cur[f] < q.var_max) ? 1 : 0;
+      if (flag && q.use_height) {
+        const float2 u = q.u_cur[f];
+        const float h = dsg_world_height(q.K, q.pose_cur, u.x, u.y, q.mu_cur[f]);
+        if (!(h >= q.hmin && h <= q.hmax)) flag = 0;
+      }
+      int v = -1;
+      if (flag && rank < q.maxV) {
+        v = rank;
+        const float2 u = q.u_cur[f];
+        int bad = 0;
+        DsPt l;
+        l.x = ds_lattice(u.x, &bad);
+        l.y = ds_lattice(u.y, &bad);
+        if (bad) s_bad = 1;
+        vfeat[v] = f;
+        vpos[v] = u;
+        vxy[v] = l;
+        atomicMin(&s_box[0], l.x); atomicMin(&s_box[1], l.y);
+        atomicMax(&s_box[2], l.x); atomicMax(&s_box[3], l.y);
+      }
+      f2v_new[f] = v;
+      rank += flag;
     }
-    if (f < q.maxF) f2v_new[f] = v;
-    carry += tot;
     __syncthreads();
   }
   const int V = carry < q.maxV ? carry : q.maxV;
@@ -211,18 +226,21 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
     slot[v] = atomicAdd(&s_cnt[c], 1);
   }
   __syncthreads();
-  // ---- exclusive scan of the cell counts (in place)
-  carry = 0;
-  for (int base = 0; base < cells; base += DSG_THREADS) {
-    const int c = base + tid;
-    const int n = c < cells ? s_cnt[c] : 0;
+  // ---- exclusive scan of the cell counts (in place): a run of cells per thread, one block scan
+  {
+    const int CI = (cells + DSG_THREADS - 1) / DSG_THREADS;
+    const int c0 = tid * CI, c1 = min(cells, c0 + CI);
+    int cnt = 0;
+    for (int c = c0; c < c1; ++c) cnt += s_cnt[c];
     int tot;
-    const int ex = carry + dsg_block_scan(n, s_warp, &tot);
-    if (c < cells) {
+    int ex = dsg_block_scan(cnt, s_warp, &tot);
+    for (int c = c0; c < c1; ++c) {
+      const int n = s_cnt[c];
       s_cnt[c] = ex;
       cell_start[c] = ex;
+      ex += n;
     }
-    carry += tot;
+    carry = tot;
     __syncthreads();
   }
   if (tid == 0) cell_start[cells] = carry;
@@ -254,25 +272,21 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
   // first they overlap with the bulk instead of forming the kernel's tail.
   {
     int32_t* vorder = d.vorder + vb;
-    int nb = 0;  // border vertices so far
-    for (int pass = 0; pass < 2; ++pass) {
-      carry = pass ? nb : 0;
-      for (int base = 0; base < V; base += DSG_THREADS) {
-        const int v = base + tid;
-        int flag = 0;
-        if (v < V) {
-          const DsPt l = vxy[v];
-          const int cx = ds_cellx(in, l.x), cy = ds_celly(in, l.y);
-          const int border = (cx == 0 || cy == 0 || cx == gx - 1 || cy == gy - 1) ? 1 : 0;
-          flag = pass ? 1 - border : border;
-        }
-        int tot;
-        const int rank = carry + dsg_block_scan(flag, s_warp, &tot);
-        if (flag) vorder[rank] = v;
-        carry += tot;
-        __syncthreads();
-      }
-      if (!pass) nb = carry;
+    const int VI = (V + DSG_THREADS - 1) / DSG_THREADS;
+    const int v0 = tid * VI, v1 = min(V, v0 + VI);
+    int nbo = 0, nin = 0;  // border / interior vertices of this thread's run
+    for (int v = v0; v < v1; ++v) {
+      const DsPt l = vxy[v];
+      const int cx = ds_cellx(in, l.x), cy = ds_celly(in, l.y);
+      if (cx == 0 || cy == 0 || cx == gx - 1 || cy == gy - 1) ++nbo; else ++nin;
+    }
+    int tot;
+    const int ex = dsg_block_scan(nbo | (nin << 16), s_warp, &tot);  // both ranks in one scan (V < 65536)
+    int rb = ex & 0xffff, ri = (tot & 0xffff) + (ex >> 16);
+    for (int v = v0; v < v1; ++v) {
+      const DsPt l = vxy[v];
+      const int cx = ds_cellx(in, l.x), cy = ds_celly(in, l.y);
+      if (cx == 0 || cy == 0 || cx == gx - 1 || cy == gy - 1) vorder[rb++] = v; else vorder[ri++] = v;
     }
   }
   if (tid == 0) {

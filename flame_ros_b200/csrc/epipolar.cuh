@@ -124,6 +124,8 @@ struct EpiArgs {
   int32_t* counters;
   int W, H, n_slots, maxF;
   int s0;  // first stream of the launch (blockIdx.y counts from it)
+  const uint8_t* cmp_frames;  // non-NULL: the comparison frames live here, stream-major and contiguous
+                              // (the landing buffer of a single host-to-device transfer), not in their slot
   fb_epi_params p;
 };
 
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(256) k_epipolar_search(EpiArgs a) {
   } else {
     const size_t fsz = (size_t)a.W * a.H;
     const uint8_t* iref = a.imgs + ((size_t)s * a.n_slots + r) * fsz;
-    const uint8_t* icmp = a.imgs + ((size_t)s * a.n_slots + cs) * fsz;
+    const uint8_t* icmp = a.cmp_frames ? a.cmp_frames + (size_t)s * fsz : a.imgs + ((size_t)s * a.n_slots + cs) * fsz;
     const float* G = a.geo + ((size_t)s * a.n_slots + r) * FB_GEO_STRIDE;
     const float2 u = a.u_ref[fb];
     st = fb_epi_update_one(a, iref, icmp, G, u.x, u.y, mu, var, ucmp, s_line, s_cost, s_ref, lane, gmask);

@@ -103,7 +103,7 @@ static void free_all(fb_ctx* c) {
   tile_plan_free(c);
   update_free(c);
   for (cudaGraphExec_t e : c->solve_exec) if (e) cudaGraphExecDestroy(e);
-  cudaFree(c->coop_contrib); cudaFree(c->idmap_scratch);
+  cudaFree(c->coop_contrib); cudaFree(c->idmap_scratch); cudaFree(c->incoming);
   if (c->coop_err) cudaFreeHost(c->coop_err);
   for (int k = 0; k < FB_PROF_NUM; ++k)
     for (cudaEvent_t e : c->sec[k].ev) cudaEventDestroy(e);
@@ -917,6 +917,8 @@ extern "C" int fb_idepth_update(fb_ctx* c, const int32_t* cmp_slot) {
   a.alive = c->f_alive; a.status = c->f_status; a.u_cmp = c->f_ucmp; a.nF = c->nF;
   a.counters = c->counters; a.W = c->W; a.H = c->H; a.n_slots = c->n_slots; a.maxF = c->maxF;
   a.s0 = 0;
+  a.cmp_frames = c->epi_cmp_frames;  // set by the pipelined step when the frames sit in a landing buffer
+  c->epi_cmp_frames = nullptr;
   a.p = c->epi;
   const int wpb = 8;
   const size_t smem = sizeof(float) * wpb * FB_EPI_GROUPS * (2 * c->epi.max_search_px + 2 * FB_MAX_WIN + 2);
@@ -991,6 +993,8 @@ static int pipeline_init(fb_ctx* c) {
   FB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   c->ev_ready.resize(c->n_slots);
   c->ev_free.resize(c->n_slots);
+  c->slot_landing.assign(c->n_slots, -1);
+  FB_CUDA(c, dalloc(&c->incoming, 2 * (size_t)c->S * c->W * c->H));
   for (int k = 0; k < c->n_slots; ++k) {
     FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_ready[k], cudaEventDisableTiming));
     FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_free[k], cudaEventDisableTiming));
@@ -1010,7 +1014,7 @@ static int pipeline_init(fb_ctx* c) {
 
 // Host image -> slot on the copy stream, ordered after the last kernel that read the slot.
 static int pipeline_upload(fb_ctx* c, int slot, const uint8_t* const* images, const int32_t* pool_idx,
-                           const float* poses) {
+                           const float* poses, bool allow_landing) {
   const size_t fsz = (size_t)c->W * c->H;
   FB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[slot], 0));
   for (int s = 0; s < c->S; ++s) {
@@ -1026,18 +1030,31 @@ static int pipeline_upload(fb_ctx* c, int slot, const uint8_t* const* images, co
   const size_t dpitch = (size_t)c->n_slots * fsz;
   ptrdiff_t stride = 0;
   // Host frames that sit back to back in (pinned) memory -- a multi-camera capture buffer -- go up as
-  // ONE transfer: a pitched copy whose source rows are contiguous (measured: 8 separate 300 kB copies
-  // cost ~12 us each, the e2e leg was bound by them).
-  bool uniform = c->S > 1 && (!images || images[1] - images[0] == (ptrdiff_t)fsz);
+  // ONE linear transfer into a landing buffer (the slots of the S streams are not adjacent in `imgs`,
+  // and 8 separate 300 kB copies cost ~12 us each: the e2e leg was bound by them); the epipolar
+  // kernel reads the comparison frames from there.
+  c->slot_landing[slot] = -1;
+  if (images && c->S > 1 && allow_landing) {  // poseframes must live in their slot: features refer to them for many frames
+    bool contiguous = true;
+    for (int s = 0; s + 1 < c->S; ++s) contiguous = contiguous && images[s + 1] - images[s] == (ptrdiff_t)fsz;
+    if (contiguous) {
+      const int lb = slot & 1;
+      FB_CUDA(c, cudaMemcpyAsync(c->incoming + (size_t)lb * c->S * fsz, images[0], (size_t)c->S * fsz, cudaMemcpyHostToDevice, c->copy_stream));
+      c->slot_landing[slot] = lb;
+      FB_CUDA(c, cudaEventRecord(c->ev_ready[slot], c->copy_stream));
+      FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_ready[slot], 0));
+      return FB_OK;
+    }
+  }
+  bool uniform = c->S > 1 && !images;
   for (int s = 0; s + 1 < c->S && uniform; ++s) {
-    const ptrdiff_t d = images ? (images[s + 1] - images[s]) : (ptrdiff_t)(pool_idx[s + 1] - pool_idx[s]) * (ptrdiff_t)fsz;
+    const ptrdiff_t d = (ptrdiff_t)(pool_idx[s + 1] - pool_idx[s]) * (ptrdiff_t)fsz;
     if (s == 0) stride = d;
     uniform = d == stride && d >= (ptrdiff_t)fsz && d < ((ptrdiff_t)1 << 30);
   }
   if (uniform) {
-    const uint8_t* src0 = images ? images[0] : c->pool + (size_t)pool_idx[0] * fsz;
-    FB_CUDA(c, cudaMemcpy2DAsync(dst0, dpitch, src0, (size_t)stride, fsz, (size_t)c->S,
-                                 images ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->copy_stream));
+    const uint8_t* src0 = c->pool + (size_t)pool_idx[0] * fsz;
+    FB_CUDA(c, cudaMemcpy2DAsync(dst0, dpitch, src0, (size_t)stride, fsz, (size_t)c->S, cudaMemcpyDeviceToDevice, c->copy_stream));
   } else {
     for (int s = 0; s < c->S; ++s) {
       uint8_t* dst = dst0 + (size_t)s * dpitch;
@@ -1113,14 +1130,16 @@ static int hotpath_step_pipelined(fb_ctx* c, const fb_step_desc* d) {
     const size_t fsz = (size_t)c->W * c->H, pitch = (size_t)c->n_slots * fsz;
     for (int s = 0; s < c->S; ++s)
       if ((rc = fb_frame_pose_set(c, s, d->ref_slot, d->ref_poses + 7 * s)) != 0) return rc;
-    FB_CUDA(c, cudaMemcpy2DAsync(c->imgs + (size_t)d->ref_slot * fsz, pitch, c->imgs + (size_t)from * fsz, pitch, fsz, (size_t)c->S,
+    const bool landed = c->slot_landing[from] >= 0;
+    const uint8_t* src = landed ? c->incoming + (size_t)c->slot_landing[from] * c->S * fsz : c->imgs + (size_t)from * fsz;
+    FB_CUDA(c, cudaMemcpy2DAsync(c->imgs + (size_t)d->ref_slot * fsz, pitch, src, landed ? fsz : pitch, fsz, (size_t)c->S,
                                  cudaMemcpyDeviceToDevice, c->stream));
     FB_CUDA(c, cudaEventRecord(c->ev_free[from], c->stream));  // the next upload into `from` waits for this read
   } else if (d->new_poseframe) {
-    rc = pipeline_upload(c, d->ref_slot, d->ref_images, d->ref_pool_idx, d->ref_poses);
+    rc = pipeline_upload(c, d->ref_slot, d->ref_images, d->ref_pool_idx, d->ref_poses, false);
     if (rc) return rc;
   }
-  rc = pipeline_upload(c, d->cmp_slot, d->cmp_images, d->cmp_pool_idx, d->cmp_poses);
+  rc = pipeline_upload(c, d->cmp_slot, d->cmp_images, d->cmp_pool_idx, d->cmp_poses, true);
   if (rc) return rc;
   if (d->new_poseframe) {
     std::fill(slots.begin(), slots.end(), d->ref_slot);
@@ -1128,6 +1147,7 @@ static int hotpath_step_pipelined(fb_ctx* c, const fb_step_desc* d) {
     if (rc) return rc;
   }
   std::fill(slots.begin(), slots.end(), d->cmp_slot);
+  if (c->slot_landing[d->cmp_slot] >= 0) c->epi_cmp_frames = c->incoming + (size_t)c->slot_landing[d->cmp_slot] * c->S * c->W * c->H;
   rc = fb_idepth_update(c, slots.data());
   if (rc) return rc;
   // the frames read by this update may be overwritten once the epipolar kernel has run

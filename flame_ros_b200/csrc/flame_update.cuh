@@ -585,6 +585,7 @@ static int update_idepths_enqueue(fb_ctx* c, int s, bool captured) {
     a.alive = c->f_alive; a.status = c->f_status; a.u_cmp = c->f_ucmp; a.nF = c->nF;
     a.counters = c->counters; a.W = c->W; a.H = c->H; a.n_slots = c->n_slots; a.maxF = c->maxF;
     a.s0 = s;
+    a.cmp_frames = nullptr;
     a.p = c->epi;
     const int wpb = 8;
     const size_t smem = sizeof(float) * wpb * FB_EPI_GROUPS * (2 * c->epi.max_search_px + 2 * FB_MAX_WIN + 2);

@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_nltgv2.py tests/test_gpu_update.py tests/test_gpu_delaunay.py -q -x 2>&1 | tail -4
-bash scripts/gpu_r2_launches.sh 2>&1 | tail -26
+timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
 bash scripts/gpu_r2_bench.sh 2>&1 | tail -60
