@@ -29,15 +29,24 @@ __device__ __forceinline__ void fb_quat_to_R(const float* q, float* R) {
   R[6] = xz - wy;          R[7] = yz + wx;          R[8] = 1.0f - (xx + yy);
 }
 
+// poses / cmp_slot may point into PINNED HOST memory (the staging ring): the kernel then reads the few
+// hundred bytes over the bus itself and leaves device copies in pose_out / cmp_out for the kernels that
+// follow.  A cudaMemcpyAsync for them would queue on the host-to-device copy engine behind the next
+// frame's 2.4 MB image upload and stall the compute stream for ~40 us per step (measured).
 __global__ void k_epi_geometry(const float* __restrict__ poses, const float* __restrict__ Ks,
                                const int32_t* __restrict__ cmp_slot, int n_slots,
-                               float* __restrict__ geo, int s0 = 0) {
+                               float* __restrict__ geo, int s0 = 0, float* pose_out = nullptr,
+                               int32_t* cmp_out = nullptr) {
   const int s = s0 + blockIdx.x, slot = threadIdx.x;  // s0: first stream of the launch
   if (slot >= n_slots) return;
-  const int cs = cmp_slot[s];
+  const int cs = cmp_slot[blockIdx.x + (cmp_out ? 0 : s0)];
+  const float* pr = poses + ((size_t)(cmp_out ? blockIdx.x : s) * n_slots + slot) * 7;
+  const float* pc = poses + ((size_t)(cmp_out ? blockIdx.x : s) * n_slots + (cs < 0 ? 0 : cs)) * 7;
+  if (cmp_out) {  // sources are indexed from the launch's first stream; publish device copies
+    if (slot == 0) cmp_out[s] = cs;
+    for (int k = 0; k < 7; ++k) pose_out[((size_t)s * n_slots + slot) * 7 + k] = pr[k];
+  }
   if (cs < 0) return;
-  const float* pr = poses + ((size_t)s * n_slots + slot) * 7;
-  const float* pc = poses + ((size_t)s * n_slots + cs) * 7;
   const float* K = Ks + (size_t)s * 9;
   float* G = geo + ((size_t)s * n_slots + slot) * FB_GEO_STRIDE;
   float Rr[9], Rc[9], R[9], t[3], d[3];

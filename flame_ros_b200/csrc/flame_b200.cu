@@ -867,10 +867,12 @@ static int upload_geometry(fb_ctx* c, const int32_t* cmp_slot) {
   if (!st) FB_FAIL(c, FB_E_NOMEM, "pinned staging allocation failed");
   memcpy(st, c->h_pose.data(), sizeof(float) * np);
   memcpy(st + sizeof(float) * np, cmp_slot, sizeof(int32_t) * c->S);
-  FB_CUDA(c, cudaMemcpyAsync(c->d_pose, st, sizeof(float) * np, cudaMemcpyHostToDevice, c->stream));
-  FB_CUDA(c, cudaMemcpyAsync(c->d_cmp, st + sizeof(float) * np, sizeof(int32_t) * c->S, cudaMemcpyHostToDevice, c->stream));
+  // the kernel reads the staged poses / slots from pinned host memory itself and publishes the device
+  // copies (see k_epi_geometry): no small copies on the host-to-device engine in front of the kernels
+  k_epi_geometry<<<c->S, std::max(32, c->n_slots), 0, c->stream>>>(reinterpret_cast<const float*>(st), c->d_K,
+                                                                   reinterpret_cast<const int32_t*>(st + sizeof(float) * np),
+                                                                   c->n_slots, c->d_geo, 0, c->d_pose, c->d_cmp);
   stage_commit(c);
-  k_epi_geometry<<<c->S, std::max(32, c->n_slots), 0, c->stream>>>(c->d_pose, c->d_K, c->d_cmp, c->n_slots, c->d_geo);
   c->launches++;
   FB_CUDA(c, cudaGetLastError());
   return FB_OK;
@@ -887,10 +889,10 @@ extern "C" int fb_features_reinit(fb_ctx* c, const int32_t* ref_slot, float mu0,
   uint8_t* st = stage_slot(c);
   if (!st) FB_FAIL(c, FB_E_NOMEM, "pinned staging allocation failed");
   memcpy(st, ref_slot, sizeof(int32_t) * c->S);
-  FB_CUDA(c, cudaMemcpyAsync(c->d_cmp, st, sizeof(int32_t) * c->S, cudaMemcpyHostToDevice, c->stream));
-  stage_commit(c);
   const dim3 grid(fb_div_up(c->maxF, 256), c->S);
-  k_features_reinit<<<grid, 256, 0, c->stream>>>(c->d_cmp, c->nF, c->maxF, mu0, var0, c->f_mu, c->f_var, c->f_drop, c->f_alive, c->f_ref);
+  // the per-stream slots are read from the pinned staging record (no copy on the H2D engine)
+  k_features_reinit<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const int32_t*>(st), c->nF, c->maxF, mu0, var0, c->f_mu, c->f_var, c->f_drop, c->f_alive, c->f_ref);
+  stage_commit(c);
   c->launches++;
   FB_CUDA(c, cudaGetLastError());
   return FB_OK;

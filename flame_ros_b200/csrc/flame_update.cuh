@@ -575,9 +575,9 @@ static int update_idepths_enqueue(fb_ctx* c, int s, bool captured) {
   } else {
     const size_t np = (size_t)c->n_slots * 7;
     const float* hg = U->h_geo + (size_t)s * (np + 1);
-    FB_CUDA(c, cudaMemcpyAsync(c->d_pose + (size_t)s * np, hg, sizeof(float) * np, cudaMemcpyHostToDevice, st));
-    FB_CUDA(c, cudaMemcpyAsync(c->d_cmp + s, hg + np, sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    k_epi_geometry<<<1, std::max(32, c->n_slots), 0, st>>>(c->d_pose, c->d_K, c->d_cmp, c->n_slots, c->d_geo, s);
+    // poses + comparison slot are read by the kernel from the pinned staging record of the frame graph
+    k_epi_geometry<<<1, std::max(32, c->n_slots), 0, st>>>(hg, c->d_K, reinterpret_cast<const int32_t*>(hg + np), c->n_slots,
+                                                           c->d_geo, s, c->d_pose, c->d_cmp);
     FB_CUDA(c, cudaMemsetAsync(c->counters + (size_t)s * FB_NUM_COUNTERS, 0, sizeof(int32_t) * FB_NUM_COUNTERS, st));
     EpiArgs a;
     a.imgs = c->imgs; a.geo = c->d_geo; a.cmp_slot = c->d_cmp; a.u_ref = c->f_uref;
