@@ -265,7 +265,7 @@ def run_gpu_leg(torch, run, steps, warmup, flush_buf, mode, barrier, min_region_
     for k in range(warmup):
         run.step(k, mode)
     ctx.sync()
-    ctx.profile_enable(True)      # event pairs around every solver launch (markers only: nothing blocks)
+    ctx.profile_enable(2 + run.capi.PROF_SOLVE)   # event pairs around every solver launch only (markers: nothing blocks)
     ctx.profile_reset()
     barrier()
     torch.cuda.synchronize()

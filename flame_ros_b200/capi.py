@@ -539,7 +539,8 @@ class Context:
 
     # ------------------------------------------------------------------ profiling
     def profile_enable(self, on=True):
-        self._ck(self._lib.fb_profile_enable(self._h, 1 if on else 0))
+        """True / False: all sections on / off; an int >= 2 = section (on - 2) only."""
+        self._ck(self._lib.fb_profile_enable(self._h, int(on) if not isinstance(on, bool) else (1 if on else 0)))
 
     def profile_reset(self):
         self._ck(self._lib.fb_profile_reset(self._h))

@@ -136,6 +136,7 @@ struct fb_ctx {
 
   // ---- profiling
   bool prof = false;
+  unsigned prof_mask = 0xffffffffu;  // sections that record events while prof is on (bit = section)
   std::vector<cudaEvent_t> prof_free;  // recycled timing events (creating one costs ~2 us of host time)
   ProfSection sec[FB_PROF_NUM];
   int64_t launches = 0;
@@ -180,7 +181,7 @@ struct ProfScope {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   int64_t l0;
   ProfScope(fb_ctx* ctx, int section) : c(ctx), sec(section), l0(ctx->launches) {
-    if (c->prof) {
+    if (c->prof && ((c->prof_mask >> section) & 1u)) {
       e0 = take(c);
       e1 = take(c);
       cudaEventRecord(e0, c->stream);
@@ -190,7 +191,7 @@ struct ProfScope {
     ProfSection& s = c->sec[sec];
     s.calls++;
     s.launches += c->launches - l0;
-    if (c->prof) {
+    if (e0) {
       cudaEventRecord(e1, c->stream);
       s.ev.push_back(e0);
       s.ev.push_back(e1);

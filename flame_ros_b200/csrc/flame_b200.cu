@@ -909,9 +909,16 @@ extern "C" int fb_idepth_update(fb_ctx* c, const int32_t* cmp_slot) {
   ProfScope ps(c, FB_PROF_IDEPTH);
   int rc = upload_geometry(c, cmp_slot);
   if (rc) return rc;
-  for (int s = 0; s < c->S; ++s)  // only the streams updated by this call: the others keep theirs
-    if (cmp_slot[s] >= 0)
-      FB_CUDA(c, cudaMemsetAsync(c->counters + (size_t)s * FB_NUM_COUNTERS, 0, sizeof(int32_t) * FB_NUM_COUNTERS, c->stream));
+  // only the streams updated by this call are cleared (the others keep their counters): one memset per
+  // run of consecutive active streams -- a batch step is a single call, not S of them (each costs ~3 us
+  // of host time, and the pipelined step is bound by the host's enqueue rate)
+  for (int s = 0; s < c->S;) {
+    if (cmp_slot[s] < 0) { ++s; continue; }
+    int e = s;
+    while (e < c->S && cmp_slot[e] >= 0) ++e;
+    FB_CUDA(c, cudaMemsetAsync(c->counters + (size_t)s * FB_NUM_COUNTERS, 0, sizeof(int32_t) * FB_NUM_COUNTERS * (e - s), c->stream));
+    s = e;
+  }
   if (maxf == 0) return FB_OK;
   EpiArgs a;
   a.imgs = c->imgs; a.geo = c->d_geo; a.cmp_slot = c->d_cmp; a.u_ref = c->f_uref;
@@ -1659,7 +1666,10 @@ extern "C" int fb_detect(fb_ctx* c, int s, int slot, int win, int border, float 
 // ------------------------------------------------------------------------------------ profiling
 extern "C" int fb_profile_enable(fb_ctx* c, int enable) {
   CHECK_CTX(c);
+  // enable: 0 = off, 1 = every section, 2 + section = that section only (two event records per call of
+  // a section cost ~5 us of host time: a tight loop that only wants the solver's duration asks for it alone)
   c->prof = enable != 0;
+  c->prof_mask = enable >= 2 ? (1u << (enable - 2)) : 0xffffffffu;
   return FB_OK;
 }
 

@@ -342,7 +342,7 @@ int fb_interpolate(fb_ctx* ctx, int stream, const fb_tri_filter_params* filter, 
  * 4 = interpolate. Times are accumulated between fb_profile_reset calls. */
 enum { FB_PROF_SOLVE = 0, FB_PROF_IDEPTH = 1, FB_PROF_UPLOAD = 2, FB_PROF_ASSEMBLY = 3,
        FB_PROF_INTERP = 4, FB_PROF_NUM = 5 };
-int fb_profile_enable(fb_ctx* ctx, int enable);
+int fb_profile_enable(fb_ctx* ctx, int enable); /* 0 = off, 1 = all sections, 2 + section = that section only */
 int fb_profile_reset(fb_ctx* ctx);
 /* Synchronises; total_ms = sum of device time of the section, launches = kernels launched. */
 int fb_profile_get(fb_ctx* ctx, int section, float* total_ms, int64_t* calls, int64_t* launches);
