@@ -36,8 +36,10 @@ __device__ __forceinline__ void fb_quat_to_R(const float* q, float* R) {
 __global__ void k_epi_geometry(const float* __restrict__ poses, const float* __restrict__ Ks,
                                const int32_t* __restrict__ cmp_slot, int n_slots,
                                float* __restrict__ geo, int s0 = 0, float* pose_out = nullptr,
-                               int32_t* cmp_out = nullptr) {
+                               int32_t* cmp_out = nullptr, int32_t* counters = nullptr) {
   const int s = s0 + blockIdx.x, slot = threadIdx.x;  // s0: first stream of the launch
+  // the status histogram of every stream this update touches starts from zero (one launch less than a memset)
+  if (counters && slot < FB_NUM_COUNTERS && cmp_slot[blockIdx.x + (cmp_out ? 0 : s0)] >= 0) counters[s * FB_NUM_COUNTERS + slot] = 0;
   if (slot >= n_slots) return;
   const int cs = cmp_slot[blockIdx.x + (cmp_out ? 0 : s0)];
   const float* pr = poses + ((size_t)(cmp_out ? blockIdx.x : s) * n_slots + slot) * 7;

@@ -861,7 +861,7 @@ static uint8_t* stage_slot(fb_ctx* c) {
 // Call after the copies from the slot returned by stage_slot() have been enqueued on c->stream.
 static void stage_commit(fb_ctx* c) { cudaEventRecord(c->stage_ev[c->stage_last], c->stream); }
 
-static int upload_geometry(fb_ctx* c, const int32_t* cmp_slot) {
+static int upload_geometry(fb_ctx* c, const int32_t* cmp_slot, bool zero_counters = false) {
   const size_t np = (size_t)c->S * c->n_slots * 7;
   uint8_t* st = stage_slot(c);
   if (!st) FB_FAIL(c, FB_E_NOMEM, "pinned staging allocation failed");
@@ -871,7 +871,7 @@ static int upload_geometry(fb_ctx* c, const int32_t* cmp_slot) {
   // copies (see k_epi_geometry): no small copies on the host-to-device engine in front of the kernels
   k_epi_geometry<<<c->S, std::max(32, c->n_slots), 0, c->stream>>>(reinterpret_cast<const float*>(st), c->d_K,
                                                                    reinterpret_cast<const int32_t*>(st + sizeof(float) * np),
-                                                                   c->n_slots, c->d_geo, 0, c->d_pose, c->d_cmp);
+                                                                   c->n_slots, c->d_geo, 0, c->d_pose, c->d_cmp, zero_counters ? c->counters : nullptr);
   stage_commit(c);
   c->launches++;
   FB_CUDA(c, cudaGetLastError());
@@ -907,18 +907,9 @@ extern "C" int fb_idepth_update(fb_ctx* c, const int32_t* cmp_slot) {
     if (cmp_slot[s] >= 0) maxf = std::max(maxf, c->hF[s]);
   }
   ProfScope ps(c, FB_PROF_IDEPTH);
-  int rc = upload_geometry(c, cmp_slot);
+  int rc = upload_geometry(c, cmp_slot, true);
   if (rc) return rc;
-  // only the streams updated by this call are cleared (the others keep their counters): one memset per
-  // run of consecutive active streams -- a batch step is a single call, not S of them (each costs ~3 us
-  // of host time, and the pipelined step is bound by the host's enqueue rate)
-  for (int s = 0; s < c->S;) {
-    if (cmp_slot[s] < 0) { ++s; continue; }
-    int e = s;
-    while (e < c->S && cmp_slot[e] >= 0) ++e;
-    FB_CUDA(c, cudaMemsetAsync(c->counters + (size_t)s * FB_NUM_COUNTERS, 0, sizeof(int32_t) * FB_NUM_COUNTERS * (e - s), c->stream));
-    s = e;
-  }
+  // (the counters of the streams this call updates were zeroed by k_epi_geometry; the others keep theirs)
   if (maxf == 0) return FB_OK;
   EpiArgs a;
   a.imgs = c->imgs; a.geo = c->d_geo; a.cmp_slot = c->d_cmp; a.u_ref = c->f_uref;
@@ -1170,8 +1161,8 @@ static int hotpath_step_pipelined(fb_ctx* c, const fb_step_desc* d) {
   // epipolar update of frame k+1, which does not depend on them (FB_PIPE_SINGLE_STAGE=1 disables).
   cudaStream_t main_stream = c->stream;
   if (c->solve_stream) {
-    FB_CUDA(c, cudaEventRecord(c->ev_epi, main_stream));
-    FB_CUDA(c, cudaStreamWaitEvent(c->solve_stream, c->ev_epi, 0));
+    // ev_free[cmp_slot] was recorded right after the epipolar kernel: the same point the second stage waits for
+    FB_CUDA(c, cudaStreamWaitEvent(c->solve_stream, c->ev_free[d->cmp_slot], 0));
     c->stream = c->solve_stream;
   }
   rc = fb_graph_data_from_features(c, d->adaptive_weights);

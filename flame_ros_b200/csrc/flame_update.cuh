@@ -577,8 +577,7 @@ static int update_idepths_enqueue(fb_ctx* c, int s, bool captured) {
     const float* hg = U->h_geo + (size_t)s * (np + 1);
     // poses + comparison slot are read by the kernel from the pinned staging record of the frame graph
     k_epi_geometry<<<1, std::max(32, c->n_slots), 0, st>>>(hg, c->d_K, reinterpret_cast<const int32_t*>(hg + np), c->n_slots,
-                                                           c->d_geo, s, c->d_pose, c->d_cmp);
-    FB_CUDA(c, cudaMemsetAsync(c->counters + (size_t)s * FB_NUM_COUNTERS, 0, sizeof(int32_t) * FB_NUM_COUNTERS, st));
+                                                           c->d_geo, s, c->d_pose, c->d_cmp, c->counters);
     EpiArgs a;
     a.imgs = c->imgs; a.geo = c->d_geo; a.cmp_slot = c->d_cmp; a.u_ref = c->f_uref;
     a.ref_slot = c->f_ref; a.mu = c->f_mu; a.var = c->f_var; a.dropouts = c->f_drop;
