@@ -29,7 +29,6 @@
 
 #include <math.h>
 #include <stdint.h>
-#include <string.h>
 
 #ifdef __CUDACC__
 #define DS_FN __host__ __device__ __forceinline__
@@ -44,16 +43,6 @@
 #define DS_COORD_LIM (1 << 20)
 
 typedef __int128 ds_i128;
-
-#ifdef __CUDA_ARCH__
-#define DS_F2I(f) __float_as_int(f)
-#define DS_I2F(i) __int_as_float(i)
-#else
-static inline int ds_f2i_(float f) { int i; memcpy(&i, &f, 4); return i; }
-static inline float ds_i2f_(int i) { float f; memcpy(&f, &i, 4); return f; }
-#define DS_F2I(f) ds_f2i_(f)
-#define DS_I2F(i) ds_i2f_(i)
-#endif
 
 struct DsPt {
   int32_t x, y;
@@ -155,10 +144,7 @@ extern long long ds_stat_visits, ds_stat_passes, ds_stat_iters32;
 extern int ds_dbg_p;
 #define DS_STAT_PASS(blk, S) { if (ds_dbg_p >= 0) printf("  pass block [%d..%d]x[%d..%d] rows %d cache %d\n", (blk).x0, (blk).x1, (blk).y0, (blk).y1, (blk).nrows, (blk).ncache); ++ds_stat_passes; int t_ = 0; if ((blk).ncache >= 0) t_ = ((blk).ncache + 31) / 32; else for (int r_ = 0; r_ < (blk).nrows; ++r_) t_ += ((S)->rowcnt[r_] + 31) / 32; ds_stat_iters32 += t_; }
 #define DS_STAT_VISIT ++ds_stat_visits;
-#define DS_STAT_FALLBACK ++ds_stat_fallbacks;
-extern long long ds_stat_fallbacks;
 #else
-#define DS_STAT_FALLBACK
 #define DS_STAT_PASS(blk, S)
 #define DS_STAT_VISIT
 #endif
@@ -329,59 +315,6 @@ DS_FN bool ds_halfplane_region(const DsIn& in, DsPt p, DsPt cur, int dir, int64_
 }
 
 // ------------------------------------------------------------------------------------ sweep step
-// Exact selection of the sweep step's best candidate by pairwise in-circle comparisons (the fallback of
-// the keyed selection in ds_next).  One pass finds the best candidate AND whether other candidates lie
-// on its circle: on the sweep side the discs through the chord (p, cur) are nested, so a candidate on
-// the FINAL circle is either compared with a best that already has that circle (in-circle == 0: tie
-// recorded) or becomes best itself and meets the others later; a strictly better candidate shrinks the
-// circle and clears the flag.
-template <class W>
-DS_FN int ds_select_exact(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, const DsBlock& blk,
-                          DsScratch* S, DsPt* best_xy, bool* tie_out) {
-  int bid = -1;
-  bool tie = false;
-  DsPt bxy = {0, 0};
-  DS_FOR_CAND(W, in, S, blk, 0, id, c, {
-    if (id < 0 || id == p || id == curid) continue;
-    if (!ds_side(pp, cur, c, dir)) continue;
-    if (bid < 0) {
-      bid = id;
-      bxy = c;
-      continue;
-    }
-    const int r = ds_inside(pp, cur, bxy, c, dir);
-    if (r > 0) {
-      bid = id;
-      bxy = c;
-      tie = false;
-    } else if (r == 0) {
-      tie = true;
-    }
-  })
-  for (int o = W::LANES >> 1; o > 0; o >>= 1) {
-    const int oid = W::shfl_xor(bid, o);
-    const int otie = W::shfl_xor(tie ? 1 : 0, o);
-    DsPt oxy;
-    oxy.x = W::shfl_xor(bxy.x, o);
-    oxy.y = W::shfl_xor(bxy.y, o);
-    if (oid < 0 || oid == bid) continue;
-    if (bid < 0) {
-      bid = oid; bxy = oxy; tie = otie != 0;
-      continue;
-    }
-    const int r = ds_inside(pp, cur, bxy, oxy, dir);
-    if (r > 0) { bid = oid; bxy = oxy; tie = otie != 0; }
-    else if (r == 0) tie = true;
-  }
-  bid = W::bcast(bid, 0);  // tied lanes may disagree on the representative: lane 0 decides
-  bxy.x = W::bcast(bxy.x, 0);
-  bxy.y = W::bcast(bxy.y, 0);
-  *tie_out = W::bcast(tie ? 1 : 0, 0) != 0;
-  *best_xy = bxy;
-  return bid;
-}
-
-
 // Next neighbour of p after cur in direction dir; -1 when there is none (hull end).  All lanes
 // return the same value; *nxy receives its coordinates.  *err is set on an invariant violation.
 template <class W>
@@ -396,45 +329,50 @@ DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, 
     ds_block_rows<W>(in, blk, S);
   }
   for (int guard = 0; guard < 4 * DS_MAXROWS; ++guard) {
-    // Keyed selection.  Among the candidates c on the sweep side, the one whose circle (p, cur, c) is
-    // empty sees the chord (p, cur) under the LARGEST inscribed angle, i.e. has the smallest
-    // cot = <p-c, cur-c> / ((p-c) x (cur-c)): a scalar key per candidate, so the lanes reduce with
-    // plain float minima instead of pairwise in-circle tests (which made the reduction cost more than
-    // the scan).  The key is fp32 and only proposes; the exact pass below disposes.
+    // One pass finds the best candidate AND whether other candidates lie on its circle: on the sweep
+    // side the discs through the chord (p, cur) are nested, so a candidate on the FINAL circle is
+    // either compared with a best that already has that circle (in-circle == 0: tie recorded) or
+    // becomes best itself and meets the others later.  A strictly better candidate shrinks the
+    // circle and clears the flag.
     int bid = -1;
     bool tie = false;
     DsPt bxy = {0, 0};
-    {
-      float bkey = 3.0e38f;
-      DS_FOR_CAND(W, in, S, blk, 0, id, c, {
-        if (id < 0 || id == p || id == curid) continue;
-        const int64_t cr = ds_orient(pp, cur, c) * dir;   // exact side test
-        if (cr <= 0) continue;
-        const float ux = (float)(pp.x - c.x), uy = (float)(pp.y - c.y), vx = (float)(cur.x - c.x), vy = (float)(cur.y - c.y);
-        const float key = (ux * vx + uy * vy) / (float)cr;
-        if (key < bkey || (key == bkey && id < bid)) { bkey = key; bid = id; bxy = c; }
-      })
-      for (int o = W::LANES >> 1; o > 0; o >>= 1) {
-        const int okb = W::shfl_xor(DS_F2I(bkey), o);
-        const int oid = W::shfl_xor(bid, o), ox = W::shfl_xor(bxy.x, o), oy = W::shfl_xor(bxy.y, o);
-        const float okey = DS_I2F(okb);
-        if (oid >= 0 && (bid < 0 || okey < bkey || (okey == bkey && oid < bid))) { bkey = okey; bid = oid; bxy.x = ox; bxy.y = oy; }
+    DS_FOR_CAND(W, in, S, blk, 0, id, c, {
+      if (id < 0 || id == p || id == curid) continue;
+      if (!ds_side(pp, cur, c, dir)) continue;
+      if (bid < 0) {
+        bid = id;
+        bxy = c;
+        continue;
       }
+      const int r = ds_inside(pp, cur, bxy, c, dir);
+      if (r > 0) {
+        bid = id;
+        bxy = c;
+        tie = false;
+      } else if (r == 0) {
+        tie = true;
+      }
+    })
+    for (int o = W::LANES >> 1; o > 0; o >>= 1) {
+      const int oid = W::shfl_xor(bid, o);
+      const int otie = W::shfl_xor(tie ? 1 : 0, o);
+      DsPt oxy;
+      oxy.x = W::shfl_xor(bxy.x, o);
+      oxy.y = W::shfl_xor(bxy.y, o);
+      if (oid < 0 || oid == bid) continue;
+      if (bid < 0) {
+        bid = oid; bxy = oxy; tie = otie != 0;
+        continue;
+      }
+      const int r = ds_inside(pp, cur, bxy, oxy, dir);
+      if (r > 0) { bid = oid; bxy = oxy; tie = otie != 0; }
+      else if (r == 0) tie = true;
     }
-    if (bid >= 0) {
-      // exact pass: nobody strictly inside the proposed circle (else the key mis-ordered two
-      // near-equal candidates: redo the step with pairwise comparisons), anybody ON it is a tie
-      bool better = false;
-      DS_FOR_CAND(W, in, S, blk, 0, id, c, {
-        if (id < 0 || id == p || id == curid || id == bid) continue;
-        if (!ds_side(pp, cur, c, dir)) continue;
-        const int r = ds_inside(pp, cur, bxy, c, dir);
-        if (r > 0) better = true;
-        else if (r == 0) tie = true;
-      })
-      if (W::any(better)) { DS_STAT_FALLBACK bid = ds_select_exact<W>(in, p, pp, curid, cur, dir, blk, S, &bxy, &tie); }
-      else tie = W::any(tie);
-    }
+    bid = W::bcast(bid, 0);  // tied lanes may disagree on the representative: lane 0 decides
+    bxy.x = W::bcast(bxy.x, 0);
+    bxy.y = W::bcast(bxy.y, 0);
+    tie = W::bcast(tie ? 1 : 0, 0) != 0;
     int64_t reg[4];
     if (bid < 0) {
       if (ds_block_all(in, blk) || !ds_halfplane_region(in, pp, cur, dir, reg)) return -1;

@@ -10,7 +10,6 @@
 #ifdef DS_STATS
 long long ds_stat_visits = 0, ds_stat_passes = 0, ds_stat_iters32 = 0;
 int ds_dbg_p = -1;
-long long ds_stat_fallbacks = 0;
 #endif
 #include "../../flame_ros_b200/csrc/delaunay_star.h"
 
@@ -99,9 +98,6 @@ extern "C" int star_sim_delaunay(int n, const float* pts, int cell_px, int32_t* 
     T += t;
     sumdeg += deg[p];
   }
-#ifdef DS_STATS
-  if (getenv("DS_STATS_DUMP")) fprintf(stderr, "fallbacks %lld passes %lld visits %lld\n", ds_stat_fallbacks, ds_stat_passes, ds_stat_visits);
-#endif
   *n_tris = T;
   *n_edges = E;
   if (sumdeg != 2ll * E) return 100;  // asymmetric stars
