@@ -29,6 +29,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define DS_FN __host__ __device__ __forceinline__
@@ -114,6 +115,12 @@ DS_FN int ds_inside(DsPt p, DsPt cur, DsPt b, DsPt c, int dir) {
 }
 
 // ------------------------------------------------------------------------------------ lanes
+#ifdef __CUDA_ARCH__
+#define DS_F2U(f) __float_as_uint(f)
+#else
+static inline unsigned ds_f2u_host(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+#define DS_F2U(f) ds_f2u_host(f)
+#endif
 struct DsSeq {  // host simulation: one lane
   static const int LANES = 1;
   DS_MEM int lane() { return 0; }
@@ -121,6 +128,8 @@ struct DsSeq {  // host simulation: one lane
   DS_MEM long long shfl_xor(long long v, int) { return v; }
   DS_MEM int bcast(int v, int) { return v; }
   DS_MEM bool any(bool p) { return p; }
+  DS_MEM unsigned min_u32(unsigned v) { return v; }
+  DS_MEM int first(bool) { return 0; }
   DS_MEM void sync() {}
 };
 #ifdef __CUDACC__
@@ -133,6 +142,9 @@ struct DsW32 {
   __device__ __forceinline__ static long long shfl_xor(long long v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
   __device__ __forceinline__ static int bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
   __device__ __forceinline__ static bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+  __device__ __forceinline__ static unsigned min_u32(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }  // redux.sync
+  // lowest lane whose predicate holds (the caller guarantees there is one)
+  __device__ __forceinline__ static int first(bool p) { return __ffs(__ballot_sync(0xffffffffu, p)) - 1; }
   __device__ __forceinline__ static void sync() { __syncwarp(); }
 };
 #endif
@@ -258,7 +270,7 @@ DS_FN bool ds_block_all(const DsIn& in, const DsBlock& b) {
 // chord's endpoints and those of the circle's four axis-extreme points that are on the sweep side.
 // (Only sweep-side points can contradict `best`; for a sliver near the hull the segment is a thin
 // cap while the whole disc would cover half the image.)  Conservative: rounded outward.
-DS_FN void ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir, int64_t* r) {
+DS_FN void ds_circle_region_f64(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir, int64_t* r) {
   // (p, a, b) counter-clockwise
   const DsPt a = dir > 0 ? cur : best, b = dir > 0 ? best : cur;
   const double ax = (double)(a.x - p.x), ay = (double)(a.y - p.y), bx = (double)(b.x - p.x), by = (double)(b.y - p.y);
@@ -281,6 +293,44 @@ DS_FN void ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir
   x0 = fmax((double)p.x + x0 - m, (double)in.bx0); y0 = fmax((double)p.y + y0 - m, (double)in.by0);
   x1 = fmin((double)p.x + x1 + m, (double)in.bx1); y1 = fmin((double)p.y + y1 + m, (double)in.by1);
   r[0] = (int64_t)floor(x0); r[1] = (int64_t)floor(y0); r[2] = (int64_t)ceil(x1); r[3] = (int64_t)ceil(y1);
+}
+
+// The same region at fp32 cost.  Only the circumcentre's numerators and denominator need the exact
+// (double) products -- they cancel for slivers; everything after the division only has to be
+// CONSERVATIVE, so it runs in fp32 with margins that cover every rounding (relative 2^-22 on the
+// centre and radius, against 2e-6 here).  Circles too large for that (radius > 1e12 lattice units)
+// take the double path.  The region never decides a predicate: a looser box only means more
+// candidates are looked at, so host and device may round differently here without consequence.
+DS_FN void ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir, int64_t* r) {
+  const DsPt a = dir > 0 ? cur : best, b = dir > 0 ? best : cur;  // (p, a, b) counter-clockwise
+  const double ax = (double)(a.x - p.x), ay = (double)(a.y - p.y), bx = (double)(b.x - p.x), by = (double)(b.y - p.y);
+  const double d = 2.0 * (ax * by - ay * bx);  // > 0, exact
+  const double a2 = ax * ax + ay * ay, b2 = bx * bx + by * by;
+  const float fd = (float)d;
+  const float ux = (float)(by * a2 - ay * b2) / fd, uy = (float)(ax * b2 - bx * a2) / fd;  // centre - p
+  const float rad = sqrtf(ux * ux + uy * uy);
+  if (!(rad < 1e12f)) {
+    ds_circle_region_f64(in, p, cur, best, dir, r);
+    return;
+  }
+  const float ext = rad + fabsf(ux) + fabsf(uy);
+  const float m = 2.0f + ext * 2e-6f;
+  const float cx = (float)(cur.x - p.x), cy = (float)(cur.y - p.y);  // chord, exact
+  const float tol = 4e-6f * (fabsf(cx) + fabsf(cy)) * ext + 4.0f;
+  const float fdir = (float)dir;
+  float x0 = cx < 0.0f ? cx : 0.0f, x1 = cx > 0.0f ? cx : 0.0f, y0 = cy < 0.0f ? cy : 0.0f, y1 = cy > 0.0f ? cy : 0.0f;
+  // the circle's axis-extreme points that lie on the sweep side of the chord
+  const bool w = (cx * uy - cy * (ux - rad)) * fdir > -tol, e = (cx * uy - cy * (ux + rad)) * fdir > -tol;
+  const bool n = (cx * (uy - rad) - cy * ux) * fdir > -tol, t = (cx * (uy + rad) - cy * ux) * fdir > -tol;
+  if (w) x0 = fminf(x0, ux - rad);
+  if (e) x1 = fmaxf(x1, ux + rad);
+  if (n) y0 = fminf(y0, uy - rad);
+  if (t) y1 = fmaxf(y1, uy + rad);
+  if (w || e) { y0 = fminf(y0, uy); y1 = fmaxf(y1, uy); }
+  if (n || t) { x0 = fminf(x0, ux); x1 = fmaxf(x1, ux); }
+  x0 = fmaxf((float)p.x + x0 - m, (float)in.bx0); y0 = fmaxf((float)p.y + y0 - m, (float)in.by0);
+  x1 = fminf((float)p.x + x1 + m, (float)in.bx1); y1 = fminf((float)p.y + y1 + m, (float)in.by1);
+  r[0] = (int64_t)floorf(x0); r[1] = (int64_t)floorf(y0); r[2] = (int64_t)ceilf(x1); r[3] = (int64_t)ceilf(y1);
 }
 
 // Bounding box of (half-plane on the sweep side of p->cur) clipped to the bounding box of all
@@ -354,25 +404,56 @@ DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, 
         tie = true;
       }
     })
-    for (int o = W::LANES >> 1; o > 0; o >>= 1) {
-      const int oid = W::shfl_xor(bid, o);
-      const int otie = W::shfl_xor(tie ? 1 : 0, o);
-      DsPt oxy;
-      oxy.x = W::shfl_xor(bxy.x, o);
-      oxy.y = W::shfl_xor(bxy.y, o);
-      if (oid < 0 || oid == bid) continue;
-      if (bid < 0) {
-        bid = oid; bxy = oxy; tie = otie != 0;
-        continue;
+    if (W::LANES > 1) {
+      // Across lanes: the lane bests' inscribed angles over the chord (p, cur) PROPOSE a winner (fp32
+      // cotangent, one redux.sync), one exact in-circle per lane DISPOSES: the proposal stands iff no
+      // lane's best lies strictly inside its circle (the lanes' own candidates are then outside too,
+      // the sweep-side discs being nested); bests ON the circle are the ties.  A refuted proposal
+      // (fp32 misordering two nearly co-circular candidates) falls back to the pairwise tournament.
+      unsigned ukey = 0xffffffffu;
+      if (bid >= 0) {
+        const float ux = (float)(pp.x - bxy.x), uy = (float)(pp.y - bxy.y), vx = (float)(cur.x - bxy.x), vy = (float)(cur.y - bxy.y);
+        const float key = (ux * vx + uy * vy) / fabsf(ux * vy - uy * vx);
+        const unsigned kb = DS_F2U(key);
+        ukey = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);  // order-preserving
+        if (ukey == 0xffffffffu) ukey = 0xfffffffeu;
       }
-      const int r = ds_inside(pp, cur, bxy, oxy, dir);
-      if (r > 0) { bid = oid; bxy = oxy; tie = otie != 0; }
-      else if (r == 0) tie = true;
+      const unsigned umin = W::min_u32(ukey);
+      if (umin != 0xffffffffu) {
+        const int src = W::first(ukey == umin);
+        const int wid = W::bcast(bid, src);
+        DsPt wxy;
+        wxy.x = W::bcast(bxy.x, src);
+        wxy.y = W::bcast(bxy.y, src);
+        int r = -1;
+        if (bid >= 0 && bid != wid) r = ds_inside(pp, cur, wxy, bxy, dir);
+        if (!W::any(r > 0)) {
+          tie = W::any(bid >= 0 && (bid == wid ? tie : r == 0));
+          bid = wid;
+          bxy = wxy;
+        } else {
+          for (int o = W::LANES >> 1; o > 0; o >>= 1) {
+            const int oid = W::shfl_xor(bid, o);
+            const int otie = W::shfl_xor(tie ? 1 : 0, o);
+            DsPt oxy;
+            oxy.x = W::shfl_xor(bxy.x, o);
+            oxy.y = W::shfl_xor(bxy.y, o);
+            if (oid < 0 || oid == bid) continue;
+            if (bid < 0) {
+              bid = oid; bxy = oxy; tie = otie != 0;
+              continue;
+            }
+            const int r2 = ds_inside(pp, cur, bxy, oxy, dir);
+            if (r2 > 0) { bid = oid; bxy = oxy; tie = otie != 0; }
+            else if (r2 == 0) tie = true;
+          }
+          bid = W::bcast(bid, 0);  // tied lanes may disagree on the representative: lane 0 decides
+          bxy.x = W::bcast(bxy.x, 0);
+          bxy.y = W::bcast(bxy.y, 0);
+          tie = W::bcast(tie ? 1 : 0, 0) != 0;
+        }
+      }
     }
-    bid = W::bcast(bid, 0);  // tied lanes may disagree on the representative: lane 0 decides
-    bxy.x = W::bcast(bxy.x, 0);
-    bxy.y = W::bcast(bxy.y, 0);
-    tie = W::bcast(tie ? 1 : 0, 0) != 0;
     int64_t reg[4];
     if (bid < 0) {
       if (ds_block_all(in, blk) || !ds_halfplane_region(in, pp, cur, dir, reg)) return -1;
@@ -438,10 +519,22 @@ DS_FN int ds_star(const DsIn& in, int p, DsScratch* S, int* star, int* deg_out, 
       const long long dx = c.x - pp.x, dy = c.y - pp.y, d2 = dx * dx + dy * dy;
       if (d2 < bd || (d2 == bd && id < bid)) { bd = d2; bid = id; bxy = c; }
     })
-    for (int o = W::LANES >> 1; o > 0; o >>= 1) {
-      const long long od = W::shfl_xor(bd, o);
-      const int oid = W::shfl_xor(bid, o), ox = W::shfl_xor(bxy.x, o), oy = W::shfl_xor(bxy.y, o);
-      if (oid >= 0 && (od < bd || (od == bd && oid < bid))) { bd = od; bid = oid; bxy.x = ox; bxy.y = oy; }
+    if (W::LANES > 1) {
+      // min over lanes of (d2, id): three redux.sync (high word, low word among those, id among those)
+      const unsigned hi = (unsigned)((unsigned long long)bd >> 32), lo = (unsigned)bd;
+      const unsigned mh = W::min_u32(hi);
+      const unsigned ml = W::min_u32(hi == mh ? lo : 0xffffffffu);
+      const bool mine = bid >= 0 && hi == mh && lo == ml;
+      const unsigned mid = W::min_u32(mine ? (unsigned)bid : 0xffffffffu);
+      if (mid == 0xffffffffu) {
+        bid = -1;
+      } else {
+        const int src = W::first(mine && (unsigned)bid == mid);
+        bid = (int)mid;
+        bxy.x = W::bcast(bxy.x, src);
+        bxy.y = W::bcast(bxy.y, src);
+        bd = ((long long)mh << 32) | (long long)ml;
+      }
     }
     if (bid < 0) {
       if (ds_block_all(in, blk)) return DS_OK;  // the only point
