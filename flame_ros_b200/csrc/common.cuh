@@ -199,3 +199,12 @@ struct ProfScope {
   }
 };
 
+#ifdef DSG_CLOCKS  // -DDSG_CLOCKS: thread 0 prints the cycles spent in every phase (debug builds only)
+#define DSG_CLK_DECL long long clk_[12]; int nclk_ = 0;
+#define DSG_CLK { if (threadIdx.x == 0 && nclk_ < 12) clk_[nclk_++] = clock64(); }
+#define DSG_CLK_PRINT(name) { if (threadIdx.x == 0) { printf("%s cycles:", name); for (int i_ = 1; i_ < nclk_; ++i_) printf(" %lld", clk_[i_] - clk_[i_ - 1]); printf("\n"); } }
+#else
+#define DSG_CLK_DECL
+#define DSG_CLK
+#define DSG_CLK_PRINT(name)
+#endif

@@ -79,6 +79,32 @@ __device__ __forceinline__ int dsg_block_scan(int v, int* s_warp, int* total) {
   return (wid ? s_warp[wid - 1] : 0) + incl - v;
 }
 
+// The same for a 64-bit value (three packed 21-bit counters).
+__device__ __forceinline__ unsigned long long dsg_block_scan64(unsigned long long v, unsigned long long* s_warp, unsigned long long* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned long long incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned long long w = lane < nw ? s_warp[lane] : 0ull;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  *total = s_warp[nw - 1];
+  return (wid ? s_warp[wid - 1] : 0ull) + incl - v;
+}
+
 // ------------------------------------------------------------------------------------ k_ds_stash
 struct DsgGraph {
   float* x; float* w1; float* w2; float4* vbar; float4* q4; int2* eij;
@@ -134,13 +160,33 @@ __host__ __device__ __forceinline__ float dsg_world_height(const float* K, const
   return fmaf(r20, xc, fmaf(r21, yc, fmaf(r22, zc, q[6])));
 }
 // One CTA.  vfeat / vpos / f2v_new are the stream's slices.
+//
+// Every phase is a pass over <= 64k items by 1024 threads.  Written naively (load, use, next item)
+// a pass costs items/1024 memory latencies and the kernel is bound by nothing else (46 us at 5.6k
+// vertices); so each pass takes its items DSG_B at a time: all loads of a batch are issued before
+// the first use, and the items are strided by the block size so that a warp's loads coalesce.
+#define DSG_B 8
+#define DSG_WORDS 2048  // ballot words: 65536 items
+__device__ __forceinline__ int dsg_select_flag(const DsgSelect& q, int f, int valid, float var) {
+  int flag = (valid && var < q.var_max) ? 1 : 0;
+  if (flag && q.use_height) {
+    const float2 u = q.u_cur[f];
+    const float h = dsg_world_height(q.K, q.pose_cur, u.x, u.y, q.mu_cur[f]);
+    if (!(h >= q.hmin && h <= q.hmax)) flag = 0;
+  }
+  return flag;
+}
 __global__ void __launch_bounds__(DSG_THREADS)
 k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t* f2v_new, int32_t* nV_out) {
   __shared__ int s_warp[32];
   __shared__ int s_cnt[DSG_MAXCELLS];
+  __shared__ unsigned s_word[DSG_WORDS];
+  __shared__ int s_wpre[DSG_WORDS];
   __shared__ int s_box[4];
   __shared__ int s_bad;
-  const int tid = threadIdx.x;
+  DSG_CLK_DECL
+  DSG_CLK
+  const int tid = threadIdx.x, lane = tid & 31;
   int32_t* meta = d.meta + (size_t)s * DSG_META;
   const size_t vb = (size_t)s * q.maxV;
   DsPt* vxy = d.vxy + vb;
@@ -152,54 +198,91 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
     s_box[2] = s_box[3] = -0x7fffffff;
     s_bad = 0;
   }
-  __syncthreads();
-  // ---- selection in ascending feature index: every thread takes a run of consecutive features, so
-  // one block scan ranks them all
-  const int FI = (q.maxF + DSG_THREADS - 1) / DSG_THREADS;
+  // ---- selection in ascending feature index: a warp's 32 flags become one ballot word, a block scan
+  // over the words' popcounts ranks them (rounds of 65536 features)
   int carry = 0;
   {
-    const int f0 = tid * FI, f1 = min(q.maxF, f0 + FI);
-    int cnt = 0;
-    for (int f = f0; f < f1; ++f) {
-      int flag = (q.valid[f] && q.var_cur[f] < q.var_max) ? 1 : 0;
-      if (flag && q.use_height) {
-        const float2 u = q.u_cur[f];
-        const float h = dsg_world_height(q.K, q.pose_cur, u.x, u.y, q.mu_cur[f]);
-        if (!(h >= q.hmin && h <= q.hmax)) flag = 0;
+    int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
+    for (int base = 0; base < q.maxF; base += 32 * DSG_WORDS) {
+      __syncthreads();
+      const int nf = min(q.maxF - base, 32 * DSG_WORDS);
+      for (int b0 = 0; b0 < nf; b0 += DSG_B * DSG_THREADS) {
+        int va[DSG_B];
+        float vr[DSG_B];
+#pragma unroll
+        for (int k = 0; k < DSG_B; ++k) {
+          const int f = b0 + k * DSG_THREADS + tid;
+          va[k] = 0; vr[k] = 0.f;
+          if (f < nf) { va[k] = q.valid[base + f]; vr[k] = q.var_cur[base + f]; }
+        }
+#pragma unroll
+        for (int k = 0; k < DSG_B; ++k) {
+          const int f = b0 + k * DSG_THREADS + tid;
+          const int flag = f < nf ? dsg_select_flag(q, base + f, va[k], vr[k]) : 0;
+          const unsigned word = __ballot_sync(0xffffffffu, flag);
+          if (lane == 0 && (f & ~31) < nf) s_word[f >> 5] = word;
+        }
       }
-      cnt += flag;
+      __syncthreads();
+      const int nw = (nf + 31) >> 5;
+      DSG_CLK  // selection: flags
+      {  // exclusive prefix of the words' popcounts: two consecutive words per thread
+        const int w0 = 2 * tid, c0 = w0 < nw ? __popc(s_word[w0]) : 0, c1 = w0 + 1 < nw ? __popc(s_word[w0 + 1]) : 0;
+        int tot;
+        const int ex = dsg_block_scan(c0 + c1, s_warp, &tot);
+        s_wpre[w0] = carry + ex;
+        s_wpre[w0 + 1] = carry + ex + c0;
+        __syncthreads();
+        carry += tot;
+      }
+      DSG_CLK  // selection: word scan
+      for (int b0 = 0; b0 < nf; b0 += DSG_B * DSG_THREADS) {
+        float2 u[DSG_B];
+        int rank[DSG_B];
+#pragma unroll
+        for (int k = 0; k < DSG_B; ++k) {
+          const int f = b0 + k * DSG_THREADS + tid;
+          rank[k] = -1;
+          u[k] = make_float2(0.f, 0.f);
+          if (f < nf) {
+            const unsigned word = s_word[f >> 5];
+            if ((word >> lane) & 1u) {
+              const int r = s_wpre[f >> 5] + __popc(word & ((1u << lane) - 1u));
+              if (r < q.maxV) { rank[k] = r; u[k] = q.u_cur[base + f]; }
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < DSG_B; ++k) {
+          const int f = b0 + k * DSG_THREADS + tid;
+          if (f >= nf) continue;
+          const int v = rank[k];
+          if (v >= 0) {
+            int bad = 0;
+            DsPt l;
+            l.x = ds_lattice(u[k].x, &bad);
+            l.y = ds_lattice(u[k].y, &bad);
+            if (bad) s_bad = 1;
+            vfeat[v] = base + f;
+            vpos[v] = u[k];
+            vxy[v] = l;
+            bx0 = min(bx0, l.x); by0 = min(by0, l.y);
+            bx1 = max(bx1, l.x); by1 = max(by1, l.y);
+          }
+          f2v_new[base + f] = v;
+        }
+      }
     }
-    int tot;
-    int rank = dsg_block_scan(cnt, s_warp, &tot);
-    carry = tot;
-    for (int f = f0; f < f1; ++f) {
-      int flag = (q.valid[f] && q.var_cur[f] < q.var_max) ? 1 : 0;
-      if (flag && q.use_height) {
-        const float2 u = q.u_cur[f];
-        const float h = dsg_world_height(q.K, q.pose_cur, u.x, u.y, q.mu_cur[f]);
-        if (!(h >= q.hmin && h <= q.hmax)) flag = 0;
-      }
-      int v = -1;
-      if (flag && rank < q.maxV) {
-        v = rank;
-        const float2 u = q.u_cur[f];
-        int bad = 0;
-        DsPt l;
-        l.x = ds_lattice(u.x, &bad);
-        l.y = ds_lattice(u.y, &bad);
-        if (bad) s_bad = 1;
-        vfeat[v] = f;
-        vpos[v] = u;
-        vxy[v] = l;
-        atomicMin(&s_box[0], l.x); atomicMin(&s_box[1], l.y);
-        atomicMax(&s_box[2], l.x); atomicMax(&s_box[3], l.y);
-      }
-      f2v_new[f] = v;
-      rank += flag;
+    bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+    bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+    if (lane == 0) {
+      atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0);
+      atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1);
     }
     __syncthreads();
   }
   const int V = carry < q.maxV ? carry : q.maxV;
+  DSG_CLK  // selection
   // ---- cell grid: ~2 mean spacings per cell, at most DS_MAXROWS rows and DSG_MAXCELLS cells
   int shift = 9, gx = 1, gy = 1;
   if (V > 0) {
@@ -220,13 +303,25 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
   // slot inside the cell (any order is fine: the stars do not depend on it); parked in `od`, which
   // k_ds_stars overwrites later
   int32_t* slot = d.od + vb;
-  for (int v = tid; v < V; v += DSG_THREADS) {
-    const DsPt l = vxy[v];
-    const int c = ds_celly(in, l.y) * gx + ds_cellx(in, l.x);
-    slot[v] = atomicAdd(&s_cnt[c], 1);
+  for (int b0 = 0; b0 < V; b0 += DSG_B * DSG_THREADS) {
+    DsPt l[DSG_B];
+#pragma unroll
+    for (int k = 0; k < DSG_B; ++k) {
+      const int v = b0 + k * DSG_THREADS + tid;
+      l[k].x = l[k].y = 0;
+      if (v < V) l[k] = vxy[v];
+    }
+#pragma unroll
+    for (int k = 0; k < DSG_B; ++k) {
+      const int v = b0 + k * DSG_THREADS + tid;
+      if (v >= V) continue;
+      const int c = ds_celly(in, l[k].y) * gx + ds_cellx(in, l[k].x);
+      slot[v] = atomicAdd(&s_cnt[c], 1);
+    }
   }
   __syncthreads();
   // ---- exclusive scan of the cell counts (in place): a run of cells per thread, one block scan
+  DSG_CLK  // cell counts
   {
     const int CI = (cells + DSG_THREADS - 1) / DSG_THREADS;
     const int c0 = tid * CI, c1 = min(cells, c0 + CI);
@@ -240,53 +335,76 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
       cell_start[c] = ex;
       ex += n;
     }
-    carry = tot;
     __syncthreads();
   }
-  if (tid == 0) cell_start[cells] = carry;
-  // ---- scatter (slot -> sorted position)
-  for (int v = tid; v < V; v += DSG_THREADS) {
-    const DsPt l = vxy[v];
-    const int c = ds_celly(in, l.y) * gx + ds_cellx(in, l.x);
-    const int k = s_cnt[c] + slot[v];
-    sxy[k] = l;
-    sid[k] = v;
+  if (tid == 0) cell_start[cells] = V;
+  DSG_CLK  // cell scan
+  // ---- scatter (slot -> sorted position); on the way, the ballot words of "vertex lies in a border cell"
+  for (int b0 = 0; b0 < V; b0 += DSG_B * DSG_THREADS) {
+    DsPt l[DSG_B];
+    int sl[DSG_B];
+#pragma unroll
+    for (int k = 0; k < DSG_B; ++k) {
+      const int v = b0 + k * DSG_THREADS + tid;
+      l[k].x = l[k].y = 0; sl[k] = 0;
+      if (v < V) { l[k] = vxy[v]; sl[k] = slot[v]; }
+    }
+#pragma unroll
+    for (int k = 0; k < DSG_B; ++k) {
+      const int v = b0 + k * DSG_THREADS + tid;
+      int border = 0;
+      if (v < V) {
+        const int cx = ds_cellx(in, l[k].x), cy = ds_celly(in, l[k].y);
+        const int pos = s_cnt[cy * gx + cx] + sl[k];
+        sxy[pos] = l[k];
+        sid[pos] = v;
+        border = (cx == 0 || cy == 0 || cx == gx - 1 || cy == gy - 1) ? 1 : 0;
+      }
+      const unsigned word = __ballot_sync(0xffffffffu, border);
+      if (lane == 0 && (v & ~31) < V) s_word[v >> 5] = word;
+    }
   }
   __syncthreads();
-  // ---- duplicates: a point with an identical point of smaller index is left out (sid = ~id)
-  for (int v = tid; v < V; v += DSG_THREADS) {
-    const DsPt l = vxy[v];
+  // ---- duplicates: a point with an identical point of smaller index is left out (sid = ~id).  One
+  DSG_CLK  // scatter
+  // thread per sorted entry: its cell's entries are consecutive (one miss, then L1)
+  for (int k = tid; k < V; k += DSG_THREADS) {
+    const DsPt l = sxy[k];
+    const int raw0 = sid[k], id = raw0 < 0 ? ~raw0 : raw0;
     const int c = ds_celly(in, l.y) * gx + ds_cellx(in, l.x);
     const int beg = s_cnt[c], end = (c + 1 < cells) ? s_cnt[c + 1] : V;
     bool dup = false;
-    int me = -1;
-    for (int k = beg; k < end; ++k) {
-      const int raw = sid[k], id = raw < 0 ? ~raw : raw;
-      if (id == v) me = k;
-      else if (id < v && sxy[k].x == l.x && sxy[k].y == l.y) dup = true;
+    for (int m = beg; m < end; ++m) {
+      const int raw = sid[m], im = raw < 0 ? ~raw : raw;   // the owner may be marking it right now: same id either way
+      const DsPt o = sxy[m];
+      if (im < id && o.x == l.x && o.y == l.y) dup = true;
     }
-    if (dup && me >= 0) sid[me] = ~v;
+    if (dup) sid[k] = ~id;
   }
-  // ---- processing order of the star kernel: the vertices of the grid's border cells first.  Hull
+  __syncthreads();
+  DSG_CLK  // duplicates
   // vertices and their neighbours scan long strips of border cells (10x the median work); started
-  // first they overlap with the bulk instead of forming the kernel's tail.
+  // first they overlap with the bulk instead of forming the kernel's tail.  Both classes in ascending
+  // vertex index: ranks from the ballot words (border count | interior count << 16 in one scan).
   {
     int32_t* vorder = d.vorder + vb;
-    const int VI = (V + DSG_THREADS - 1) / DSG_THREADS;
-    const int v0 = tid * VI, v1 = min(V, v0 + VI);
-    int nbo = 0, nin = 0;  // border / interior vertices of this thread's run
-    for (int v = v0; v < v1; ++v) {
-      const DsPt l = vxy[v];
-      const int cx = ds_cellx(in, l.x), cy = ds_celly(in, l.y);
-      if (cx == 0 || cy == 0 || cx == gx - 1 || cy == gy - 1) ++nbo; else ++nin;
-    }
+    const int nw = (V + 31) >> 5;
+    const int w0 = 2 * tid;
+    int c0 = 0, c1 = 0;
+    if (w0 < nw) { const int nb = __popc(s_word[w0]), nv = min(32, V - 32 * w0); c0 = nb | ((nv - nb) << 16); }
+    if (w0 + 1 < nw) { const int nb = __popc(s_word[w0 + 1]), nv = min(32, V - 32 * (w0 + 1)); c1 = nb | ((nv - nb) << 16); }
     int tot;
-    const int ex = dsg_block_scan(nbo | (nin << 16), s_warp, &tot);  // both ranks in one scan (V < 65536)
-    int rb = ex & 0xffff, ri = (tot & 0xffff) + (ex >> 16);
-    for (int v = v0; v < v1; ++v) {
-      const DsPt l = vxy[v];
-      const int cx = ds_cellx(in, l.x), cy = ds_celly(in, l.y);
-      if (cx == 0 || cy == 0 || cx == gx - 1 || cy == gy - 1) vorder[rb++] = v; else vorder[ri++] = v;
+    const int ex = dsg_block_scan(c0 + c1, s_warp, &tot);  // V < 65536
+    s_wpre[w0] = ex;
+    s_wpre[w0 + 1] = ex + c0;
+    __syncthreads();
+    const int nborder = tot & 0xffff;
+    for (int v = tid; v < V; v += DSG_THREADS) {
+      const unsigned word = s_word[v >> 5];
+      const int pre = s_wpre[v >> 5];
+      const unsigned below = (1u << lane) - 1u;
+      if ((word >> lane) & 1u) vorder[(pre & 0xffff) + __popc(word & below)] = v;
+      else vorder[nborder + (pre >> 16) + __popc(~word & below)] = v;
     }
   }
   if (tid == 0) {
@@ -296,6 +414,8 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
     meta[DSG_ERR] = s_bad ? 0x100 : 0;
     *nV_out = V;
   }
+  DSG_CLK  // order
+  DSG_CLK_PRINT("k_ds_prepare")
 }
 
 // ------------------------------------------------------------------------------------ k_ds_stars
@@ -348,28 +468,28 @@ k_ds_stars(DelGpu d, int s, int maxV) {
 // One CTA: offsets of edges / triangles / CSR rows, counts, consistency.
 __global__ void __launch_bounds__(DSG_THREADS)
 k_ds_scan(DelGpu d, int s, int maxV, int maxE, int maxT, int32_t* row, int32_t* nE_out, int32_t* nT_out) {
-  __shared__ int s_warp[32];
+  __shared__ unsigned long long s_warp[32];
   int32_t* meta = d.meta + (size_t)s * DSG_META;
   const int V = meta[DSG_NV];
   const size_t vb = (size_t)s * maxV, ob = (size_t)s * (maxV + 1);
-  int ce = 0, ct = 0, cr = 0;
-  for (int base = 0; base < V; base += DSG_THREADS) {
-    const int v = base + threadIdx.x;
-    const int o = v < V ? d.od[vb + v] : 0, t = v < V ? d.tc[vb + v] : 0, g = v < V ? (d.deg[vb + v] & 0xff) : 0;
-    int te, tt, tr;
-    const int ee = ce + dsg_block_scan(o, s_warp, &te);
-    __syncthreads();
-    const int et = ct + dsg_block_scan(t, s_warp, &tt);
-    __syncthreads();
-    const int er = cr + dsg_block_scan(g, s_warp, &tr);
-    __syncthreads();
-    if (v < V) {
-      d.eoff[ob + v] = ee;
-      d.toff[ob + v] = et;
-      row[v] = er;
-    }
-    ce += te; ct += tt; cr += tr;
+  // every thread takes a run of consecutive vertices; (out-degree, triangles, degree) share one
+  // 64-bit scan, 21 bits each (sums <= 6 V < 2^21 for V < 2^18)
+  const int VI = (V + DSG_THREADS - 1) / DSG_THREADS;
+  const int v0 = min(V, (int)threadIdx.x * VI), v1 = min(V, v0 + VI);
+  unsigned long long acc = 0ull;
+#pragma unroll 4
+  for (int v = v0; v < v1; ++v)
+    acc += (unsigned long long)d.od[vb + v] | ((unsigned long long)d.tc[vb + v] << 21) | ((unsigned long long)(d.deg[vb + v] & 0xff) << 42);
+  unsigned long long tot;
+  unsigned long long ex = dsg_block_scan64(acc, s_warp, &tot);
+#pragma unroll 4
+  for (int v = v0; v < v1; ++v) {
+    d.eoff[ob + v] = (int)(ex & 0x1fffffull);
+    d.toff[ob + v] = (int)((ex >> 21) & 0x1fffffull);
+    row[v] = (int)(ex >> 42);
+    ex += (unsigned long long)d.od[vb + v] | ((unsigned long long)d.tc[vb + v] << 21) | ((unsigned long long)(d.deg[vb + v] & 0xff) << 42);
   }
+  const int ce = (int)(tot & 0x1fffffull), ct = (int)((tot >> 21) & 0x1fffffull), cr = (int)(tot >> 42);
   if (threadIdx.x == 0) {
     d.eoff[ob + V] = ce;
     d.toff[ob + V] = ct;
@@ -389,31 +509,43 @@ k_ds_scan(DelGpu d, int s, int maxV, int maxE, int maxT, int32_t* row, int32_t* 
 }
 
 // ------------------------------------------------------------------------------------ k_ds_emit
+// One warp per vertex, lane k = star entry k (DS_MAXD == 32): the canonical rank of an out-edge /
+// triangle is the number of smaller ones in the star (shuffles), and all gathers of a vertex are in
+// flight together.  Same order as ds_emit: out-neighbours ascending, triangles (v, a, b) ascending a.
+static_assert(DS_MAXD == 32, "k_ds_emit maps star entries to lanes");
 __global__ void __launch_bounds__(128)
 k_ds_emit(DelGpu d, int s, int maxV, int maxE, int maxT, const float2* __restrict__ vpos, int2* __restrict__ eij,
           float4* __restrict__ ec, int32_t* __restrict__ tri) {
   const int32_t* meta = d.meta + (size_t)s * DSG_META;
   const int V = meta[DSG_NV];
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (v >= V || meta[DSG_NT] == 0) return;
   const size_t vb = (size_t)s * maxV, ob = (size_t)s * (maxV + 1);
   const int dg = d.deg[vb + v], deg = dg & 0xff, closed = dg >> 8;
   if (deg == 0) return;
-  int st[DS_MAXD], outs[DS_MAXD], tr[3 * DS_MAXD], ntri = 0;
-  const int32_t* star = d.star + (vb + v) * DS_MAXD;
-  for (int k = 0; k < deg; ++k) st[k] = star[k];
-  const int no = ds_emit(v, st, deg, closed, outs, tr, &ntri);
   const int e0 = d.eoff[ob + v], t0 = d.toff[ob + v];
   const float2 pv = vpos[v];
-  for (int k = 0; k < no; ++k) {
-    const int w = outs[k];
+  const int w = lane < deg ? d.star[(vb + v) * DS_MAXD + lane] : -1;
+  const int b = __shfl_sync(0xffffffffu, w, lane + 1 == deg ? 0 : ((lane + 1) & 31));  // next neighbour counter-clockwise
+  const int pairs = closed ? deg : deg - 1;
+  const bool is_out = w > v, is_tri = lane < pairs && w > v && b > v;
+  int epos = 0, tpos = 0;
+  for (int m = 0; m < deg; ++m) {
+    const int u = __shfl_sync(0xffffffffu, w, m), ub = __shfl_sync(0xffffffffu, b, m);
+    epos += (u > v && u < w) ? 1 : 0;
+    tpos += (m < pairs && u > v && ub > v && u < w) ? 1 : 0;
+  }
+  if (is_out) {
     const float2 pw = vpos[w];
     // dx = pos_i - pos_j in fp32, alpha = 1/|delta|, beta = 1 (same expressions as the host path)
     const float dx = pv.x - pw.x, dy = pv.y - pw.y;
-    eij[e0 + k] = make_int2(v, w);
-    ec[e0 + k] = make_float4(1.0f / sqrtf(dx * dx + dy * dy), 1.0f, dx, dy);
+    eij[e0 + epos] = make_int2(v, w);
+    ec[e0 + epos] = make_float4(1.0f / sqrtf(dx * dx + dy * dy), 1.0f, dx, dy);
   }
-  for (int k = 0; k < 3 * ntri; ++k) tri[3 * t0 + k] = tr[k];
+  if (is_tri) {
+    int32_t* t = tri + 3 * (size_t)(t0 + tpos);
+    t[0] = v; t[1] = w; t[2] = b;
+  }
 }
 
 // ------------------------------------------------------------------------------------ k_ds_csr
@@ -424,8 +556,9 @@ struct DsgCarry {
   const float* idmap;       // previous dense map (prediction) or NULL
   int W, H, adaptive, use_prediction;
 };
-// One thread per vertex: CSR incidence (ascending edge id = in-edges by source, then out-edges),
-// data term, state carry-over for the vertex and its out-edges.
+// Thread t serves vertex t (data term, state carry-over, in-degree) and edge t (dual carry-over, its
+// two places in the CSR incidence: ascending edge id = in-edges by source, then out-edges).  Edge-
+// parallel because the per-vertex version was one long chain of dependent loads per incident edge.
 __global__ void __launch_bounds__(128)
 k_ds_csr(DelGpu d, DsgCarry q, int s, int maxV, int maxE, const int32_t* __restrict__ vfeat,
          const float2* __restrict__ vpos, const int2* __restrict__ eij, const int32_t* __restrict__ row,
@@ -433,86 +566,78 @@ k_ds_csr(DelGpu d, DsgCarry q, int s, int maxV, int maxE, const int32_t* __restr
          int32_t* __restrict__ epos, int32_t* __restrict__ vnin) {
   int32_t* meta = d.meta + (size_t)s * DSG_META;
   const int V = meta[DSG_NV];
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= V) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t vb = (size_t)s * maxV, eb = (size_t)s * maxE, ob = (size_t)s * (maxV + 1);
-  // ---- data term + vertex state
-  const int f = vfeat[v];
-  const float zz = q.mu_cur[f];
-  z[v] = zz;
-  wt[v] = q.adaptive ? (1.0f / q.var_cur[f]) : 1.0f;
   const int oV = meta[DSG_OLD_NV], oE = meta[DSG_OLD_NE];
-  const int ov = oV > 0 ? q.f2v_old[f] : -1;
-  if (ov >= 0 && ov < oV) {
-    x[v] = d.o_x[vb + ov];
-    w1[v] = d.o_w1[vb + ov];
-    w2[v] = d.o_w2[vb + ov];
-    vbar[v] = d.o_vbar[vb + ov];
-  } else {
-    float x0 = zz;
-    if (q.use_prediction && q.idmap) {
-      const int px = (int)rintf(vpos[v].x), py = (int)rintf(vpos[v].y);
-      if (px >= 0 && py >= 0 && px < q.W && py < q.H) {
-        const float p = q.idmap[py * q.W + px];
-        if (p == p && p > 0.0f) x0 = p;
+  const bool mesh = meta[DSG_NT] != 0;
+  if (t < V) {
+    // ---- data term + vertex state
+    const int v = t;
+    const int f = vfeat[v];
+    const float zz = q.mu_cur[f];
+    z[v] = zz;
+    wt[v] = q.adaptive ? (1.0f / q.var_cur[f]) : 1.0f;
+    const int ov = oV > 0 ? q.f2v_old[f] : -1;
+    if (ov >= 0 && ov < oV) {
+      x[v] = d.o_x[vb + ov];
+      w1[v] = d.o_w1[vb + ov];
+      w2[v] = d.o_w2[vb + ov];
+      vbar[v] = d.o_vbar[vb + ov];
+    } else {
+      float x0 = zz;
+      if (q.use_prediction && q.idmap) {
+        const int px = (int)rintf(vpos[v].x), py = (int)rintf(vpos[v].y);
+        if (px >= 0 && py >= 0 && px < q.W && py < q.H) {
+          const float p = q.idmap[py * q.W + px];
+          if (p == p && p > 0.0f) x0 = p;
+        }
       }
+      x[v] = x0;
+      w1[v] = 0.0f;
+      w2[v] = 0.0f;
+      vbar[v] = make_float4(x0, 0.0f, 0.0f, 0.0f);
     }
-    x[v] = x0;
-    w1[v] = 0.0f;
-    w2[v] = 0.0f;
-    vbar[v] = make_float4(x0, 0.0f, 0.0f, 0.0f);
+    // in-degree = neighbours with a smaller index = degree - out-degree
+    vnin[v] = mesh ? (d.deg[vb + v] & 0xff) - (d.eoff[ob + v + 1] - d.eoff[ob + v]) : 0;
   }
-  if (meta[DSG_NT] == 0) {
-    vnin[v] = 0;
+  if (!mesh || t >= meta[DSG_NE]) return;
+  const int e = t;
+  const int2 vw = eij[e];
+  const int v = vw.x, w = vw.y;
+  // ---- carry q over from the previous graph (both endpoints persisted, edge existed)
+  float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (oV > 0) {
+    const int ov = q.f2v_old[vfeat[v]], ow = q.f2v_old[vfeat[w]];
+    if (ov >= 0 && ov < oV && ow >= 0 && ow < oV) {
+      const int b = d.o_eoff[ob + ov], en = d.o_eoff[ob + ov + 1];
+      for (int k = b; k < en && k < oE; ++k)
+        if (d.o_eij[eb + k].y == ow) {
+          qq = d.o_q4[eb + k];
+          break;
+        }
+    }
+  }
+  q4[e] = qq;
+  // ---- out-edge of v: after v's in-edges, in edge order
+  const int e0 = d.eoff[ob + v], odv = d.eoff[ob + v + 1] - e0;
+  const int niv = (d.deg[vb + v] & 0xff) - odv;
+  inc[row[v] + niv + (e - e0)] = e << 1;
+  // ---- in-edge of w: its rank among w's smaller neighbours (ascending source)
+  const int degw = d.deg[vb + w] & 0xff;
+  const int32_t* __restrict__ star = d.star + (vb + w) * DS_MAXD;
+  int k = 0;
+  bool listed = false;
+  for (int m = 0; m < degw; ++m) {
+    const int u = star[m];
+    k += u < v ? 1 : 0;
+    listed = listed || u == v;
+  }
+  if (!listed) {
+    atomicOr(&meta[DSG_ERR], 0x800);  // w does not list v
     return;
   }
-  const int dg = d.deg[vb + v], deg = dg & 0xff;
-  const int e0 = d.eoff[ob + v], e1 = d.eoff[ob + v + 1];
-  // ---- out-edges: carry q over from the previous graph (both endpoints persisted, edge existed)
-  for (int e = e0; e < e1; ++e) {
-    float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ov >= 0 && ov < oV) {
-      const int ow = q.f2v_old[vfeat[eij[e].y]];
-      if (ow >= 0 && ow < oV) {
-        const int b = d.o_eoff[ob + ov], en = d.o_eoff[ob + ov + 1];
-        for (int k = b; k < en && k < oE; ++k)
-          if (d.o_eij[eb + k].y == ow) {
-            qq = d.o_q4[eb + k];
-            break;
-          }
-      }
-    }
-    q4[e] = qq;
-  }
-  // ---- CSR: in-edges (neighbours u < v, ascending u), then out-edges (ascending target)
-  int ins[DS_MAXD], ni = 0;
-  const int32_t* star = d.star + (vb + v) * DS_MAXD;
-  for (int k = 0; k < deg; ++k) {
-    const int u = star[k];
-    if (u >= v) continue;
-    int pos = ni++;
-    while (pos > 0 && ins[pos - 1] > u) { ins[pos] = ins[pos - 1]; --pos; }
-    ins[pos] = u;
-  }
-  int r = row[v];
-  for (int k = 0; k < ni; ++k) {
-    const int u = ins[k];
-    const int b = d.eoff[ob + u], en = d.eoff[ob + u + 1];
-    int e = -1;
-    for (int m = b; m < en; ++m)
-      if (eij[m].y == v) {
-        e = m;
-        break;
-      }
-    if (e < 0) {
-      atomicOr(&meta[DSG_ERR], 0x800);  // u does not list v
-      e = 0;
-    }
-    epos[e] = k;  // position of the edge in its target's row: the tile solver's slot address
-    inc[r++] = (e << 1) | 1;
-  }
-  vnin[v] = ni;
-  for (int e = e0; e < e1; ++e) inc[r++] = e << 1;
+  epos[e] = k;  // position of the edge in its target's row: the tile solver's slot address
+  inc[row[w] + k] = (e << 1) | 1;
 }
 
 // ------------------------------------------------------------------------------------ rescale_data

@@ -1346,6 +1346,8 @@ extern "C" int fb_set_update_params(fb_ctx* c, const fb_update_params* p) {
   if (!p || p->detection_win_size < 4 || p->detection_win_size > 64 || p->iters < 0 || p->detection_border < 1 ||
       p->triangulator < 0 || p->triangulator > 1)
     FB_FAIL(c, FB_E_ARG, "fb_set_update_params: bad parameters (win in [4,64], border >= 1, triangulator 0|1)");
+  if (p->triangulator == 0 && c->maxV > 65535)
+    FB_FAIL(c, FB_E_ARG, "fb_set_update_params: the device triangulation packs vertex ranks in 16 bits (max_vertices <= 65535); set triangulator = 1");
   if (p->check_sticky_obstacles != 0)
     FB_FAIL(c, FB_E_ARG, "fb_set_update_params: check_sticky_obstacles is not implemented (only 0 is accepted)");
   if (p->min_error != 100.0f)
@@ -1547,6 +1549,7 @@ extern "C" int fb_delaunay_device(fb_ctx* c, int s, int n, const float* pts, int
   CHECK_STREAM(c, s);
   if (n < 0 || (n > 0 && !pts) || !tris || !n_tris || !edges || !n_edges) FB_FAIL(c, FB_E_ARG, "fb_delaunay_device: bad argument");
   if (n > c->maxF || n > c->maxV) FB_FAIL(c, FB_E_NOMEM, "fb_delaunay_device: n exceeds max_features / max_vertices");
+  if (c->maxV > 65535) FB_FAIL(c, FB_E_ARG, "fb_delaunay_device: max_vertices <= 65535");
   int rc = update_alloc(c);
   if (rc) return rc;
   UpdateState* U = c->upd;
@@ -1563,7 +1566,7 @@ extern "C" int fb_delaunay_device(fb_ctx* c, int s, int n, const float* pts, int
   k_ds_prepare<<<1, DSG_THREADS, 0, st>>>(q, D, s, c->vfeat + vb, c->vpos + vb, D.f2v + fb, c->nV + s);
   k_ds_stars<<<fb_div_up(c->maxV, DSG_WARPS), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
   k_ds_scan<<<1, DSG_THREADS, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->row + (size_t)s * (c->maxV + 1), c->nE + s, c->nT + s);
-  k_ds_emit<<<fb_div_up(c->maxV, 128), 128, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->vpos + vb, c->eij + eb, c->ec + eb,
+  k_ds_emit<<<fb_div_up(c->maxV, 4), 128, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->vpos + vb, c->eij + eb, c->ec + eb,
                                                     c->tri + (size_t)s * c->maxT * 3);
   c->launches += 4;
   FB_CUDA(c, cudaGetLastError());

@@ -374,7 +374,6 @@ static int update_interpolate(fb_ctx* c, int s, const int32_t* Tdev, int32_t* co
   const int T = Tdev ? c->maxT : c->hT[s];
   const size_t npx = (size_t)c->W * c->H, vb = (size_t)s * c->maxV;
   int32_t* owner = c->owner + (size_t)s * npx;
-  uint8_t* valid = c->tri_valid + (size_t)s * c->maxT;
   const int32_t* tri = c->tri + (size_t)s * c->maxT * 3;
   cudaStream_t st = c->stream;
   ProfScope ps(c, FB_PROF_INTERP);
@@ -384,7 +383,6 @@ static int update_interpolate(fb_ctx* c, int s, const int32_t* Tdev, int32_t* co
     k_raster_claim<<<fb_div_up(T * 32, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, T, tri, nullptr, owner, Tdev);
     c->launches += 1;
   }
-  (void)valid;
   k_raster_shade<<<fb_div_up((int)npx, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, c->x + vb, tri, owner, c->idmap + (size_t)s * npx, Tdev, covered);
   c->launches++;
   FB_CUDA(c, cudaGetLastError());
@@ -427,11 +425,11 @@ static int update_graph_device(fb_ctx* c, int s) {
   k_ds_prepare<<<1, DSG_THREADS, 0, st>>>(q, D, s, c->vfeat + vb, c->vpos + vb, D.f2v + par * nf + fb, c->nV + s);
   k_ds_stars<<<fb_div_up(c->maxV, DSG_WARPS), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
   k_ds_scan<<<1, DSG_THREADS, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->row + (size_t)s * (c->maxV + 1), c->nE + s, c->nT + s);
-  k_ds_emit<<<fb_div_up(c->maxV, 128), 128, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->vpos + vb, c->eij + eb, c->ec + eb,
+  k_ds_emit<<<fb_div_up(c->maxV, 4), 128, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->vpos + vb, c->eij + eb, c->ec + eb,
                                                     c->tri + (size_t)s * c->maxT * 3);
   DsgCarry cq{U->f_mucur + fb, U->f_varcur + fb, D.f2v + (1 - par) * nf + fb,
               S.have_graph ? c->idmap + (size_t)s * npx : nullptr, c->W, c->H, p.adaptive_data_weights, p.init_with_prediction};
-  k_ds_csr<<<fb_div_up(c->maxV, 128), 128, 0, st>>>(D, cq, s, c->maxV, c->maxE, c->vfeat + vb, c->vpos + vb, c->eij + eb,
+  k_ds_csr<<<fb_div_up(c->maxE > c->maxV ? c->maxE : c->maxV, 128), 128, 0, st>>>(D, cq, s, c->maxV, c->maxE, c->vfeat + vb, c->vpos + vb, c->eij + eb,
                                                    c->row + (size_t)s * (c->maxV + 1), c->inc + 2 * eb, c->z + vb, c->wt + vb,
                                                    c->x + vb, c->w1 + vb, c->w2 + vb, c->vbar + vb, c->q4 + eb, c->epos + eb, c->vnin + vb);
   c->launches += 6;

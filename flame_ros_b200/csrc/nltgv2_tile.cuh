@@ -35,6 +35,7 @@
 #define FBT_TX 4
 #define FBT_TY 4
 #define FBT_BINS 64
+#define FBT_APT 16                         // k_tile_assign: vertices per thread (16 tiles x 1024 vertices / 1024 threads)
 
 struct TilePlan {
   int32_t* vtile = nullptr;  // [S*maxV] tile of every vertex
@@ -54,6 +55,18 @@ static inline size_t fbt_smem_bytes() {
 }
 
 // ------------------------------------------------------------------------------------ k_tile_assign
+// Exclusive prefix of 64 shared-memory counters by one warp: lane l returns the sum before counter 2 l.
+static_assert(FBT_BINS == 64, "fbt_scan64: two bins per lane");
+__device__ __forceinline__ int fbt_scan64(const int* cnt, int lane) {
+  const int n = cnt[2 * lane] + cnt[2 * lane + 1];
+  int incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  return incl - n;
+}
 __global__ void __launch_bounds__(1024)
 k_tile_assign(int s, int maxV, const int32_t* __restrict__ nV, const float2* __restrict__ vpos, int32_t* vtile,
               int32_t* vloc, int32_t* tlist, int32_t* toff) {
@@ -61,71 +74,126 @@ k_tile_assign(int s, int maxV, const int32_t* __restrict__ nV, const float2* __r
   __shared__ int s_col[FBT_BINS], s_row[FBT_TX][FBT_BINS];
   __shared__ int s_c2s[FBT_BINS];               // bin column -> strip
   __shared__ int s_r2p[FBT_TX][FBT_BINS];       // (strip, bin row) -> part
-  __shared__ int s_cnt[FBT_C], s_off[FBT_C + 1];
-  const int tid = threadIdx.x;
+  __shared__ int s_wcnt[32][FBT_C];             // vertices of tile t seen by warp w (then: exclusive prefix over warps)
+  __shared__ int s_off[FBT_C + 1];
+  DSG_CLK_DECL
+  DSG_CLK
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int V = nV[s];
   const size_t vb = (size_t)s * maxV;
   vpos += vb; vtile += vb; vloc += vb; tlist += vb; toff += (size_t)s * (FBT_C + 1);
   if (tid == 0) { s_box[0] = s_box[1] = 0x7fffffff; s_box[2] = s_box[3] = -0x7fffffff; }
   for (int k = tid; k < FBT_BINS; k += blockDim.x) s_col[k] = 0;
   for (int k = tid; k < FBT_TX * FBT_BINS; k += blockDim.x) (&s_row[0][0])[k] = 0;
-  if (tid < FBT_C) s_cnt[tid] = 0;
+  for (int k = tid; k < 32 * FBT_C; k += blockDim.x) (&s_wcnt[0][0])[k] = 0;
   __syncthreads();
-  for (int v = tid; v < V; v += blockDim.x) {
-    const float2 p = vpos[v];
-    const int x = (int)floorf(p.x * 16.0f), y = (int)floorf(p.y * 16.0f);
-    atomicMin(&s_box[0], x); atomicMin(&s_box[1], y); atomicMax(&s_box[2], x); atomicMax(&s_box[3], y);
+  // The kernel is one CTA and every pass used to be a chain of dependent loads (load, atomic, next
+  // element): it was bound by memory latency times V / 1024.  Now a thread's vertices (v = tid + 1024 k,
+  // at most FBT_APT) are loaded once, all loads in flight together, and stay in registers.
+  if (V > FBT_APT * 1024) {   // more than 16 full tiles: let the solver see an overfull tile and decline
+    if (tid <= FBT_C) toff[tid] = tid ? V : 0;
+    return;
+  }
+  int px[FBT_APT], py[FBT_APT];
+  DSG_CLK  // init
+#pragma unroll
+  for (int k = 0; k < FBT_APT; ++k) {
+    const int v = tid + k * 1024;
+    float2 p = make_float2(0.f, 0.f);
+    if (v < V) p = vpos[v];
+    px[k] = (int)floorf(p.x * 16.0f);
+    py[k] = (int)floorf(p.y * 16.0f);
+  }
+  {  // bounding box in 1/16 px: per-thread, then one redux per warp, then 32 atomics
+    int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < FBT_APT; ++k)
+      if (tid + k * 1024 < V) { bx0 = min(bx0, px[k]); by0 = min(by0, py[k]); bx1 = max(bx1, px[k]); by1 = max(by1, py[k]); }
+    bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+    bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+    if (lane == 0) { atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0); atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1); }
   }
   __syncthreads();
   const int x0 = s_box[0], y0 = s_box[1];
-  const long long wx = (long long)s_box[2] - x0 + 1, wy = (long long)s_box[3] - y0 + 1;
-#define FBT_BINX(p) (int)((((long long)floorf((p).x * 16.0f) - x0) * FBT_BINS) / wx)
-#define FBT_BINY(p) (int)((((long long)floorf((p).y * 16.0f) - y0) * FBT_BINS) / wy)
-  for (int v = tid; v < V; v += blockDim.x) atomicAdd(&s_col[FBT_BINX(vpos[v])], 1);
-  __syncthreads();
-  if (tid == 0) {  // strips of (nearly) equal count
-    int acc = 0, strip = 0;
-    for (int c = 0; c < FBT_BINS; ++c) {
-      while (strip < FBT_TX - 1 && acc >= (long long)(strip + 1) * V / FBT_TX) ++strip;
-      s_c2s[c] = strip;
-      acc += s_col[c];
-    }
+  DSG_CLK  // load + box
+  // histogram bins: any monotone map onto [0, FBT_BINS) will do (the split only balances the tiles,
+  // the solver's arithmetic does not depend on it), so one float multiply instead of a 64-bit division
+  const float sx = (float)FBT_BINS / (float)(s_box[2] - x0 + 1), sy = (float)FBT_BINS / (float)(s_box[3] - y0 + 1);
+#pragma unroll
+  for (int k = 0; k < FBT_APT; ++k) {
+    if (tid + k * 1024 >= V) continue;
+    px[k] = min(FBT_BINS - 1, (int)((float)(px[k] - x0) * sx));   // from here on: the bins
+    py[k] = min(FBT_BINS - 1, (int)((float)(py[k] - y0) * sy));
+    atomicAdd(&s_col[px[k]], 1);
   }
   __syncthreads();
-  for (int v = tid; v < V; v += blockDim.x) {
-    const float2 p = vpos[v];
-    atomicAdd(&s_row[s_c2s[FBT_BINX(p)]][FBT_BINY(p)], 1);
+  DSG_CLK  // column histogram
+  // strips of (nearly) equal count: column c belongs to the last strip k whose quota k V / 4 the
+  // columns before c have filled (a warp scan; the serial loop with its divisions cost 6 us)
+  if (wid == 0) {
+    const int ex = fbt_scan64(s_col, lane);
+    const int a0 = ex, a1 = ex + s_col[2 * lane];
+    int k0 = 0, k1 = 0;
+    for (int k = 1; k < FBT_TX; ++k) { k0 += a0 >= k * V / FBT_TX ? 1 : 0; k1 += a1 >= k * V / FBT_TX ? 1 : 0; }
+    s_c2s[2 * lane] = k0;
+    s_c2s[2 * lane + 1] = k1;
   }
   __syncthreads();
-  if (tid < FBT_TX) {  // each strip cut into parts of (nearly) equal count
-    int tot = 0;
-    for (int r = 0; r < FBT_BINS; ++r) tot += s_row[tid][r];
-    int acc = 0, part = 0;
-    for (int r = 0; r < FBT_BINS; ++r) {
-      while (part < FBT_TY - 1 && acc >= (long long)(part + 1) * tot / FBT_TY) ++part;
-      s_r2p[tid][r] = part;
-      acc += s_row[tid][r];
-    }
+#pragma unroll
+  for (int k = 0; k < FBT_APT; ++k) {
+    if (tid + k * 1024 >= V) continue;
+    px[k] = s_c2s[px[k]];                                          // from here on: the strip
+    atomicAdd(&s_row[px[k]][py[k]], 1);
   }
   __syncthreads();
-  for (int v = tid; v < V; v += blockDim.x) {
-    const float2 p = vpos[v];
-    const int strip = s_c2s[FBT_BINX(p)];
-    const int t = strip * FBT_TY + s_r2p[strip][FBT_BINY(p)];
-    vtile[v] = t;
-    vloc[v] = atomicAdd(&s_cnt[t], 1);  // any order inside a tile: the arithmetic does not depend on it
+  DSG_CLK  // strips + row histogram
+  if (wid < FBT_TX) {  // each strip cut into parts of (nearly) equal count: one warp per strip, same rule
+    const int ex = fbt_scan64(s_row[wid], lane);
+    const int n0 = s_row[wid][2 * lane], n1 = s_row[wid][2 * lane + 1];
+    const int tot = __shfl_sync(0xffffffffu, ex + n0 + n1, 31);
+    const int a0 = ex, a1 = ex + n0;
+    int k0 = 0, k1 = 0;
+    for (int k = 1; k < FBT_TY; ++k) { k0 += a0 >= k * tot / FBT_TY ? 1 : 0; k1 += a1 >= k * tot / FBT_TY ? 1 : 0; }
+    s_r2p[wid][2 * lane] = k0;
+    s_r2p[wid][2 * lane + 1] = k1;
+  }
+  __syncthreads();
+  // rank inside the tile (any order: the arithmetic does not depend on it): counters per (warp, tile)
+  DSG_CLK  // parts
+  // keep the atomics' contention inside the warp, a prefix over the warps makes the ranks global
+#pragma unroll
+  for (int k = 0; k < FBT_APT; ++k) {
+    if (tid + k * 1024 >= V) continue;
+    const int t = px[k] * FBT_TY + s_r2p[px[k]][py[k]];
+    px[k] = t;                                                     // the tile
+    py[k] = atomicAdd(&s_wcnt[wid][t], 1);                         // rank among this warp's vertices of the tile
+  }
+  __syncthreads();
+  if (tid < FBT_C) {
+    int acc = 0;
+    for (int w = 0; w < 32; ++w) { const int n = s_wcnt[w][tid]; s_wcnt[w][tid] = acc; acc += n; }
+    s_off[tid + 1] = acc;   // tile sizes, turned into offsets below
   }
   __syncthreads();
   if (tid == 0) {
     int acc = 0;
-    for (int t = 0; t < FBT_C; ++t) { s_off[t] = acc; acc += s_cnt[t]; }
-    s_off[FBT_C] = acc;
+    s_off[0] = 0;
+    for (int t = 0; t < FBT_C; ++t) { acc += s_off[t + 1]; s_off[t + 1] = acc; }
   }
   __syncthreads();
   if (tid <= FBT_C) toff[tid] = s_off[tid];
-  for (int v = tid; v < V; v += blockDim.x) tlist[s_off[vtile[v]] + vloc[v]] = v;
-#undef FBT_BINX
-#undef FBT_BINY
+  DSG_CLK  // ranks + prefix
+#pragma unroll
+  for (int k = 0; k < FBT_APT; ++k) {
+    const int v = tid + k * 1024;
+    if (v >= V) continue;
+    const int t = px[k], l = py[k] + s_wcnt[wid][t];
+    vtile[v] = t;
+    vloc[v] = l;
+    tlist[s_off[t] + l] = v;
+  }
+  DSG_CLK  // write
+  DSG_CLK_PRINT("k_tile_assign")
 }
 
 // ------------------------------------------------------------------------------------ k_nltgv2_tile
