@@ -30,7 +30,7 @@
 
 // meta record of one stream (device ints)
 enum { DSG_GX = 0, DSG_GY, DSG_SHIFT, DSG_BX0, DSG_BY0, DSG_BX1, DSG_BY1, DSG_NV, DSG_NE, DSG_NT, DSG_ERR,
-       DSG_SUMDEG, DSG_OLD_NV, DSG_OLD_NE, DSG_HAVE, DSG_META };
+       DSG_SUMDEG, DSG_OLD_NV, DSG_OLD_NE, DSG_HAVE, DSG_WORK, DSG_META };
 
 struct DelGpu {
   DsPt* vxy = nullptr;          // [S*maxV] lattice coordinates by vertex
@@ -411,6 +411,7 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
     meta[DSG_GX] = gx; meta[DSG_GY] = gy; meta[DSG_SHIFT] = shift;
     meta[DSG_BX0] = s_box[0]; meta[DSG_BY0] = s_box[1]; meta[DSG_BX1] = s_box[2]; meta[DSG_BY1] = s_box[3];
     meta[DSG_NV] = V;
+    meta[DSG_WORK] = 0;
     meta[DSG_ERR] = s_bad ? 0x100 : 0;
     *nV_out = V;
   }
@@ -426,9 +427,7 @@ k_ds_stars(DelGpu d, int s, int maxV) {
   int32_t* meta = d.meta + (size_t)s * DSG_META;
   const int V = meta[DSG_NV];
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (blockIdx.x * DSG_WARPS + g >= V) return;
   const size_t vb = (size_t)s * maxV;
-  const int p = d.vorder[vb + blockIdx.x * DSG_WARPS + g];
   DsIn in;
   in.n = V;
   in.vxy = d.vxy + vb;
@@ -437,6 +436,15 @@ k_ds_stars(DelGpu d, int s, int maxV) {
   in.sxy = d.sxy + vb;
   in.sid = d.sid + vb;
   in.bx0 = meta[DSG_BX0]; in.by0 = meta[DSG_BY0]; in.bx1 = meta[DSG_BX1]; in.by1 = meta[DSG_BY1];
+  // Warps fetch vertices from a shared counter (zeroed by k_ds_prepare): a star costs between 0.3x and
+  // 10x the median, and with a fixed vertex per warp a CTA's slot stayed occupied until its slowest
+  // warp was done (SMs 26 % idle over the launch).
+  for (;;) {
+  int item = 0;
+  if (lane == 0) item = atomicAdd(&meta[DSG_WORK], 1);
+  item = __shfl_sync(0xffffffffu, item, 0);
+  if (item >= V) break;
+  const int p = d.vorder[vb + item];
   int32_t* star = d.star + (vb + p) * DS_MAXD;
   int deg = 0, closed = 0, od = 0, tc = 0;
   // a duplicate point has no star: find its own entry flag through its cell
@@ -462,6 +470,16 @@ k_ds_stars(DelGpu d, int s, int maxV) {
     d.od[vb + p] = od;
     d.tc[vb + p] = tc;
   }
+  }
+}
+
+// Persistent grid of the star kernel: four CTAs per SM (its register limit), never more than the vertices need.
+static inline int dsg_stars_grid(int device, int maxV) {
+  static int sms[64] = {0};
+  int& n = sms[device & 63];
+  if (n == 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { cudaGetLastError(); n = 148; }
+  const int need = (maxV + DSG_WARPS - 1) / DSG_WARPS;
+  return need < 4 * n ? need : 4 * n;
 }
 
 // ------------------------------------------------------------------------------------ k_ds_scan

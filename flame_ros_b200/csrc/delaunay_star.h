@@ -34,9 +34,11 @@
 #ifdef __CUDACC__
 #define DS_FN __host__ __device__ __forceinline__
 #define DS_MEM __host__ __device__ __forceinline__ static
+#define DS_COLD __host__ __device__ __noinline__
 #else
 #define DS_FN static inline
 #define DS_MEM static inline
+#define DS_COLD static
 #endif
 
 #define DS_MAXD 32      // largest star (error above)
@@ -69,22 +71,9 @@ DS_FN int64_t ds_orient(DsPt a, DsPt b, DsPt c) {
 // > 0 iff p lies strictly inside the circumcircle of the counter-clockwise triangle (a, b, c);
 // 0 iff on it.  |coordinates| < 2^20: differences < 2^21, squared lengths and 2x2 minors < 2^43 are
 // exact in double; the three-term sum is decided by a static error bound, else exactly in 128 bits.
-DS_FN int ds_incircle(DsPt a, DsPt b, DsPt c, DsPt p) {
-  const int32_t iadx = a.x - p.x, iady = a.y - p.y, ibdx = b.x - p.x, ibdy = b.y - p.y;
-  const int32_t icdx = c.x - p.x, icdy = c.y - p.y;
-  {
-    // stage 1, fp32: the differences are exact (< 2^24); every product and sum rounds.  The bound is
-    // Shewchuk's "permanent" form: 10 eps (sum of the magnitudes of all terms), eps = 2^-24, rounded up
-    // to 1e-6.  Nearly every candidate is far from the circle and is decided here at fp32 latency.
-    const float adx = (float)iadx, ady = (float)iady, bdx = (float)ibdx, bdy = (float)ibdy, cdx = (float)icdx, cdy = (float)icdy;
-    const float bc1 = bdx * cdy, bc2 = bdy * cdx, ca1 = cdx * ady, ca2 = cdy * adx, ab1 = adx * bdy, ab2 = ady * bdx;
-    const float al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
-    const float det = al * (bc1 - bc2) + bl * (ca1 - ca2) + cl * (ab1 - ab2);
-    const float perm = al * (fabsf(bc1) + fabsf(bc2)) + bl * (fabsf(ca1) + fabsf(ca2)) + cl * (fabsf(ab1) + fabsf(ab2));
-    const float bound = 1e-6f * perm;
-    if (det > bound) return 1;
-    if (det < -bound) return -1;
-  }
+// Stages 2 and 3 of the in-circle test, out of line: one copy in the kernel instead of one per call
+// site (the fp32 stage decides nearly every candidate; the star kernel stalled on instruction fetch).
+DS_COLD int ds_incircle_exact(int32_t iadx, int32_t iady, int32_t ibdx, int32_t ibdy, int32_t icdx, int32_t icdy) {
   {
     // stage 2, fp64: squared lengths and 2x2 minors are exact, only the three-term sum rounds
     const double adx = iadx, ady = iady, bdx = ibdx, bdy = ibdy, cdx = icdx, cdy = icdy;
@@ -103,6 +92,24 @@ DS_FN int ds_incircle(DsPt a, DsPt b, DsPt c, DsPt p) {
   const ds_i128 d = (ds_i128)al * (ds_i128)ma + (ds_i128)bl * (ds_i128)mb + (ds_i128)cl * (ds_i128)mc;
   return d > 0 ? 1 : (d < 0 ? -1 : 0);
 }
+DS_FN int ds_incircle(DsPt a, DsPt b, DsPt c, DsPt p) {
+  const int32_t iadx = a.x - p.x, iady = a.y - p.y, ibdx = b.x - p.x, ibdy = b.y - p.y;
+  const int32_t icdx = c.x - p.x, icdy = c.y - p.y;
+  {
+    // stage 1, fp32: the differences are exact (< 2^24); every product and sum rounds.  The bound is
+    // Shewchuk's "permanent" form: 10 eps (sum of the magnitudes of all terms), eps = 2^-24, rounded up
+    // to 1e-6.  Nearly every candidate is far from the circle and is decided here at fp32 latency.
+    const float adx = (float)iadx, ady = (float)iady, bdx = (float)ibdx, bdy = (float)ibdy, cdx = (float)icdx, cdy = (float)icdy;
+    const float bc1 = bdx * cdy, bc2 = bdy * cdx, ca1 = cdx * ady, ca2 = cdy * adx, ab1 = adx * bdy, ab2 = ady * bdx;
+    const float al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
+    const float det = al * (bc1 - bc2) + bl * (ca1 - ca2) + cl * (ab1 - ab2);
+    const float perm = al * (fabsf(bc1) + fabsf(bc2)) + bl * (fabsf(ca1) + fabsf(ca2)) + cl * (fabsf(ab1) + fabsf(ab2));
+    const float bound = 1e-6f * perm;
+    if (det > bound) return 1;
+    if (det < -bound) return -1;
+  }
+  return ds_incircle_exact(iadx, iady, ibdx, ibdy, icdx, icdy);
+}
 
 // dir = +1: counter-clockwise sweep (candidates strictly left of p->cur), -1: clockwise (right).
 DS_FN bool ds_side(DsPt p, DsPt cur, DsPt c, int dir) {
@@ -111,7 +118,8 @@ DS_FN bool ds_side(DsPt p, DsPt cur, DsPt c, int dir) {
 }
 // > 0: c strictly inside the circle (p, cur, b); 0: on it.  b and c are on the sweep side.
 DS_FN int ds_inside(DsPt p, DsPt cur, DsPt b, DsPt c, int dir) {
-  return dir > 0 ? ds_incircle(p, cur, b, c) : ds_incircle(p, b, cur, c);
+  const DsPt u = dir > 0 ? cur : b, v = dir > 0 ? b : cur;  // (p, u, v) counter-clockwise; one in-circle call site
+  return ds_incircle(p, u, v, c);
 }
 
 // ------------------------------------------------------------------------------------ lanes
@@ -564,32 +572,32 @@ DS_FN int ds_star(const DsIn& in, int p, DsScratch* S, int* star, int* deg_out, 
   if (W::lane() == 0) S->ccw[0] = n0;
   int curid = n0;
   DsPt cur = n0xy;
+  // one loop for both sweeps (a single inlined copy of ds_next): counter-clockwise until the star
+  // closes at n0 or the hull ends it, then -- hull vertex -- clockwise from n0 again
+  int dir = +1;
   for (;;) {
     DsPt nxy;
-    const int nx = ds_next<W>(in, p, pp, curid, cur, +1, blk, S, &nxy, &err);
+    const int nx = ds_next<W>(in, p, pp, curid, cur, dir, blk, S, &nxy, &err);
     if (err) return err;
-    if (nx < 0) break;
-    if (nx == n0) { closed = 1; break; }
-    if (nccw >= DS_MAXD) return DS_E_DEGREE;
-    if (W::lane() == 0) S->ccw[nccw] = nx;
-    ++nccw;
-    curid = nx;
-    cur = nxy;
-  }
-  if (!closed) {  // hull vertex: clockwise sweep from n0
-    curid = n0;
-    cur = n0xy;
-    for (;;) {
-      DsPt nxy;
-      const int nx = ds_next<W>(in, p, pp, curid, cur, -1, blk, S, &nxy, &err);
-      if (err) return err;
+    if (dir > 0) {
+      if (nx < 0) {
+        dir = -1;
+        curid = n0;
+        cur = n0xy;
+        continue;
+      }
+      if (nx == n0) { closed = 1; break; }
+      if (nccw >= DS_MAXD) return DS_E_DEGREE;
+      if (W::lane() == 0) S->ccw[nccw] = nx;
+      ++nccw;
+    } else {
       if (nx < 0) break;
       if (nccw + ncw >= DS_MAXD) return DS_E_DEGREE;
       if (W::lane() == 0) S->cw[ncw] = nx;
       ++ncw;
-      curid = nx;
-      cur = nxy;
     }
+    curid = nx;
+    cur = nxy;
   }
   W::sync();
   if (W::lane() == 0) {

@@ -51,10 +51,20 @@ static inline void pipeline_drain(fb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->pipe_dirty = false;
 }
+// The current CUDA device is per host thread: a context created on device 1 and then driven from a
+// worker thread (whose current device is still 0) would launch on streams that do not exist there
+// ("invalid resource handle": found by the 2-GPU bench, rank 1).  Every entry point therefore makes
+// the context's device current for the calling thread first.
+static inline void bind_device(const fb_ctx* c) {
+  int d = -1;
+  if (cudaGetDevice(&d) != cudaSuccess || d != c->device) cudaSetDevice(c->device);
+}
 #define CHECK_CTX_NODRAIN(c) \
-  if (!(c)) return FB_E_ARG
+  if (!(c)) return FB_E_ARG; \
+  bind_device(c)
 #define CHECK_CTX(c)           \
   if (!(c)) return FB_E_ARG;   \
+  bind_device(c);              \
   pipeline_drain(c)
 #define CHECK_STREAM(c, s) \
   if ((s) < 0 || (s) >= (c)->S) FB_FAIL(c, FB_E_ARG, "stream index out of range")
@@ -1564,7 +1574,7 @@ extern "C" int fb_delaunay_device(fb_ctx* c, int s, int n, const float* pts, int
   FB_CUDA(c, cudaMemsetAsync(U->f_varcur + fb, 0, sizeof(float) * c->maxF, st));
   DsgSelect q{U->f_ucur + fb, U->f_varcur + fb, U->f_valid + fb, 1.0f, c->maxF, c->maxV, c->W, c->H, 0, nullptr, nullptr, nullptr, 0.f, 0.f};
   k_ds_prepare<<<1, DSG_THREADS, 0, st>>>(q, D, s, c->vfeat + vb, c->vpos + vb, D.f2v + fb, c->nV + s);
-  k_ds_stars<<<fb_div_up(c->maxV, DSG_WARPS), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
+  k_ds_stars<<<dsg_stars_grid(c->device, c->maxV), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
   k_ds_scan<<<1, DSG_THREADS, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->row + (size_t)s * (c->maxV + 1), c->nE + s, c->nT + s);
   k_ds_emit<<<fb_div_up(c->maxV, 4), 128, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->vpos + vb, c->eij + eb, c->ec + eb,
                                                     c->tri + (size_t)s * c->maxT * 3);

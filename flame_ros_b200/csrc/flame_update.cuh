@@ -423,7 +423,7 @@ static int update_graph_device(fb_ctx* c, int s) {
               use_height, U->f_mucur + fb, c->d_K + 9 * s, c->d_pose + ((size_t)s * c->n_slots + (c->n_slots - 1)) * 7,
               p.min_height, p.max_height};
   k_ds_prepare<<<1, DSG_THREADS, 0, st>>>(q, D, s, c->vfeat + vb, c->vpos + vb, D.f2v + par * nf + fb, c->nV + s);
-  k_ds_stars<<<fb_div_up(c->maxV, DSG_WARPS), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
+  k_ds_stars<<<dsg_stars_grid(c->device, c->maxV), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
   k_ds_scan<<<1, DSG_THREADS, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->row + (size_t)s * (c->maxV + 1), c->nE + s, c->nT + s);
   k_ds_emit<<<fb_div_up(c->maxV, 4), 128, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->vpos + vb, c->eij + eb, c->ec + eb,
                                                     c->tri + (size_t)s * c->maxT * 3);
