@@ -34,6 +34,9 @@ struct fb_ctx {
   bool own_stream = false;
   // pipelined fb_hotpath_step: uploads on a copy stream, per-slot ready/free events, result events
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t out_stream = nullptr;     // D2H of the vertex idepths of frame k (off the solve stream's critical path)
+  cudaEvent_t ev_solved = nullptr;
+  float* x_stage[2] = {nullptr, nullptr}; // device snapshots of x the result copies read (the next solve is free to write x)
   cudaStream_t solve_stream = nullptr;   // assembly + solver of frame k run here while `stream` already
                                          // processes the epipolar update of frame k+1
   cudaEvent_t ev_epi = nullptr, ev_asm = nullptr, ev_join = nullptr, ev_join2 = nullptr;
@@ -50,6 +53,7 @@ struct fb_ctx {
   // frames are contiguous goes up as ONE linear transfer (8 separate 300 kB copies cost ~12 us each)
   uint8_t* incoming = nullptr;            // [2][S][H*W]
   std::vector<int> slot_landing;          // per slot: -1 = the frame is in its slot, else landing buffer index
+  std::vector<char> slot_is_ref;          // per slot: holds a poseframe that features may still refer to
   const uint8_t* epi_cmp_frames = nullptr;  // consumed by the next fb_idepth_update
   cudaEvent_t ev_result[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t n_pipelined = 0;

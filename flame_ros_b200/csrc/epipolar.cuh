@@ -33,10 +33,10 @@ __device__ __forceinline__ void fb_quat_to_R(const float* q, float* R) {
 // hundred bytes over the bus itself and leaves device copies in pose_out / cmp_out for the kernels that
 // follow.  A cudaMemcpyAsync for them would queue on the host-to-device copy engine behind the next
 // frame's 2.4 MB image upload and stall the compute stream for ~40 us per step (measured).
-__global__ void k_epi_geometry(const float* __restrict__ poses, const float* __restrict__ Ks,
-                               const int32_t* __restrict__ cmp_slot, int n_slots,
-                               float* __restrict__ geo, int s0 = 0, float* pose_out = nullptr,
-                               int32_t* cmp_out = nullptr, int32_t* counters = nullptr) {
+__device__ __forceinline__ void epi_geometry_body(const float* __restrict__ poses, const float* __restrict__ Ks,
+                                                  const int32_t* __restrict__ cmp_slot, int n_slots,
+                                                  float* __restrict__ geo, int s0, float* pose_out,
+                                                  int32_t* cmp_out, int32_t* counters) {
   const int s = s0 + blockIdx.x, slot = threadIdx.x;  // s0: first stream of the launch
   // the status histogram of every stream this update touches starts from zero (one launch less than a memset)
   if (counters && slot < FB_NUM_COUNTERS && cmp_slot[blockIdx.x + (cmp_out ? 0 : s0)] >= 0) counters[s * FB_NUM_COUNTERS + slot] = 0;
@@ -88,6 +88,26 @@ __global__ void k_epi_geometry(const float* __restrict__ poses, const float* __r
   G[13] = fy * c3[1] + cy * c3[2];
   G[14] = c3[2];
   G[15] = 0.0f;
+}
+__global__ void k_epi_geometry(const float* __restrict__ poses, const float* __restrict__ Ks,
+                               const int32_t* __restrict__ cmp_slot, int n_slots,
+                               float* __restrict__ geo, int s0 = 0, float* pose_out = nullptr,
+                               int32_t* cmp_out = nullptr, int32_t* counters = nullptr) {
+  epi_geometry_body(poses, Ks, cmp_slot, n_slots, geo, s0, pose_out, cmp_out, counters);
+}
+// The same with the poses and slots travelling IN the launch (kernel parameters, < 4 KB): reading
+// them from pinned host memory costs a PCIe round trip per access, and under a saturated host-to-device
+// link (the e2e leg uploads 2.4 MB per step) those reads stretched the step's critical path
+// (epipolar update k -> assembly k -> epipolar update k+1) by ~20 us.
+#define FB_GEO_REC_FLOATS 896
+#define FB_GEO_REC_STREAMS 32
+struct GeoRecord {
+  float poses[FB_GEO_REC_FLOATS];
+  int32_t cmp[FB_GEO_REC_STREAMS];
+};
+__global__ void k_epi_geometry_rec(const __grid_constant__ GeoRecord rec, const float* __restrict__ Ks, int n_slots,
+                                   float* __restrict__ geo, int s0, float* pose_out, int32_t* cmp_out, int32_t* counters) {
+  epi_geometry_body(rec.poses, Ks, rec.cmp, n_slots, geo, s0, pose_out, cmp_out, counters);
 }
 
 // ---- image sampling ---------------------------------------------------------------------------
@@ -386,6 +406,23 @@ k_features_reinit(const int32_t* __restrict__ new_ref, const int32_t* __restrict
   const int s = blockIdx.y;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = new_ref[s];
+  if (r < 0 || f >= nF[s]) return;
+  const size_t fb = (size_t)s * maxF + f;
+  mu[fb] = mu0;
+  var[fb] = var0;
+  dropouts[fb] = 0;
+  alive[fb] = 1;
+  ref_slot[fb] = r;
+}
+// The same with the slots in the launch (see k_epi_geometry_rec).
+struct SlotRecord { int32_t v[FB_GEO_REC_STREAMS]; };
+__global__ void __launch_bounds__(256)
+k_features_reinit_rec(const __grid_constant__ SlotRecord new_ref, const int32_t* __restrict__ nF, int maxF,
+                      float mu0, float var0, float* mu, float* var, int32_t* dropouts, int32_t* alive,
+                      int32_t* ref_slot) {
+  const int s = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = new_ref.v[s];
   if (r < 0 || f >= nF[s]) return;
   const size_t fb = (size_t)s * maxF + f;
   mu[fb] = mu0;

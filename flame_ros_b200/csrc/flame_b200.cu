@@ -48,6 +48,7 @@ static inline void pipeline_drain(fb_ctx* c) {
   if (!c->pipe_dirty || c->pipe_hold) return;
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->solve_stream) cudaStreamSynchronize(c->solve_stream);
+  if (c->out_stream) cudaStreamSynchronize(c->out_stream);
   cudaStreamSynchronize(c->stream);
   c->pipe_dirty = false;
 }
@@ -114,6 +115,7 @@ static void free_all(fb_ctx* c) {
   update_free(c);
   for (cudaGraphExec_t e : c->solve_exec) if (e) cudaGraphExecDestroy(e);
   cudaFree(c->coop_contrib); cudaFree(c->idmap_scratch); cudaFree(c->incoming);
+  cudaFree(c->x_stage[0]); cudaFree(c->x_stage[1]);
   if (c->coop_err) cudaFreeHost(c->coop_err);
   for (int k = 0; k < FB_PROF_NUM; ++k)
     for (cudaEvent_t e : c->sec[k].ev) cudaEventDestroy(e);
@@ -129,6 +131,8 @@ static void free_all(fb_ctx* c) {
   for (cudaEvent_t e : c->stage_ev) if (e) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->solve_stream) cudaStreamDestroy(c->solve_stream);
+  if (c->out_stream) cudaStreamDestroy(c->out_stream);
+  if (c->ev_solved) cudaEventDestroy(c->ev_solved);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -873,12 +877,23 @@ static void stage_commit(fb_ctx* c) { cudaEventRecord(c->stage_ev[c->stage_last]
 
 static int upload_geometry(fb_ctx* c, const int32_t* cmp_slot, bool zero_counters = false) {
   const size_t np = (size_t)c->S * c->n_slots * 7;
+  if (np <= FB_GEO_REC_FLOATS && c->S <= FB_GEO_REC_STREAMS && !getenv("FB_GEO_PINNED")) {
+    // poses and slots as kernel parameters (see k_epi_geometry_rec)
+    GeoRecord rec;
+    memcpy(rec.poses, c->h_pose.data(), sizeof(float) * np);
+    memcpy(rec.cmp, cmp_slot, sizeof(int32_t) * c->S);
+    k_epi_geometry_rec<<<c->S, std::max(32, c->n_slots), 0, c->stream>>>(rec, c->d_K, c->n_slots, c->d_geo, 0, c->d_pose, c->d_cmp,
+                                                                         zero_counters ? c->counters : nullptr);
+    c->launches++;
+    FB_CUDA(c, cudaGetLastError());
+    return FB_OK;
+  }
   uint8_t* st = stage_slot(c);
   if (!st) FB_FAIL(c, FB_E_NOMEM, "pinned staging allocation failed");
   memcpy(st, c->h_pose.data(), sizeof(float) * np);
   memcpy(st + sizeof(float) * np, cmp_slot, sizeof(int32_t) * c->S);
-  // the kernel reads the staged poses / slots from pinned host memory itself and publishes the device
-  // copies (see k_epi_geometry): no small copies on the host-to-device engine in front of the kernels
+  // larger batches: the kernel reads the staged poses / slots from pinned host memory itself and
+  // publishes the device copies: no small copies on the host-to-device engine in front of the kernels
   k_epi_geometry<<<c->S, std::max(32, c->n_slots), 0, c->stream>>>(reinterpret_cast<const float*>(st), c->d_K,
                                                                    reinterpret_cast<const int32_t*>(st + sizeof(float) * np),
                                                                    c->n_slots, c->d_geo, 0, c->d_pose, c->d_cmp, zero_counters ? c->counters : nullptr);
@@ -895,7 +910,15 @@ extern "C" int fb_features_reinit(fb_ctx* c, const int32_t* ref_slot, float mu0,
     if (ref_slot[s] >= c->n_slots) FB_FAIL(c, FB_E_ARG, "fb_features_reinit: ref_slot out of range");
   if (c->maxF == 0) return FB_OK;
   ProfScope ps(c, FB_PROF_ASSEMBLY);
-  // d_cmp doubles as the per-stream argument buffer (consumed by the kernel enqueued right after)
+  const dim3 grid_rec(fb_div_up(c->maxF, 256), c->S);
+  if (c->S <= FB_GEO_REC_STREAMS && !getenv("FB_GEO_PINNED")) {
+    SlotRecord rec;
+    memcpy(rec.v, ref_slot, sizeof(int32_t) * c->S);
+    k_features_reinit_rec<<<grid_rec, 256, 0, c->stream>>>(rec, c->nF, c->maxF, mu0, var0, c->f_mu, c->f_var, c->f_drop, c->f_alive, c->f_ref);
+    c->launches++;
+    FB_CUDA(c, cudaGetLastError());
+    return FB_OK;
+  }
   uint8_t* st = stage_slot(c);
   if (!st) FB_FAIL(c, FB_E_NOMEM, "pinned staging allocation failed");
   memcpy(st, ref_slot, sizeof(int32_t) * c->S);
@@ -1004,6 +1027,7 @@ static int pipeline_init(fb_ctx* c) {
   c->ev_ready.resize(c->n_slots);
   c->ev_free.resize(c->n_slots);
   c->slot_landing.assign(c->n_slots, -1);
+  c->slot_is_ref.assign(c->n_slots, 1);  // unknown history: treat every slot as a poseframe once
   FB_CUDA(c, dalloc(&c->incoming, 2 * (size_t)c->S * c->W * c->H));
   for (int k = 0; k < c->n_slots; ++k) {
     FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_ready[k], cudaEventDisableTiming));
@@ -1018,8 +1042,53 @@ static int pipeline_init(fb_ctx* c) {
     FB_CUDA(c, cudaStreamCreateWithPriority(&c->solve_stream, cudaStreamNonBlocking, hi));
     FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_epi, cudaEventDisableTiming));
     FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_asm, cudaEventDisableTiming));
+    FB_CUDA(c, cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+    FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_solved, cudaEventDisableTiming));
+    FB_CUDA(c, dalloc(&c->x_stage[0], (size_t)c->S * c->maxV));
+    FB_CUDA(c, dalloc(&c->x_stage[1], (size_t)c->S * c->maxV));
   }
   return FB_OK;
+}
+
+// FB_PIPE_TRACE=<steps>: timing events around the stages of the pipelined step, printed once after
+// <steps> steps (diagnosis of the overlap; the events themselves cost a few us of host time per step).
+struct PipeTrace {
+  int n = 0, cap = 0;
+  std::vector<cudaEvent_t> ev;  // [cap][10]: h2d0 h2d1 epi0 epi1 asm0 asm1 solve1 d2h1 pfcopy0 pfcopy1
+  cudaEvent_t at(int k, int j) { return ev[(size_t)k * 10 + j]; }
+};
+static PipeTrace* pipe_trace() {
+  static PipeTrace* t = nullptr;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    const char* e = getenv("FB_PIPE_TRACE");
+    if (e && atoi(e) > 0) {
+      t = new PipeTrace();
+      t->cap = atoi(e);
+      t->ev.resize((size_t)t->cap * 10);
+      for (auto& x : t->ev) cudaEventCreate(&x);
+    }
+  }
+  return t;
+}
+static void pipe_trace_mark(PipeTrace* t, int j, cudaStream_t st) {
+  if (t && t->n < t->cap) cudaEventRecord(t->at(t->n, j), st);
+}
+static void pipe_trace_step_done(PipeTrace* t) {
+  if (!t || t->n >= t->cap) return;
+  if (++t->n < t->cap) return;
+  cudaDeviceSynchronize();
+  static const char* name[10] = {"h2d0", "h2d1", "epi0", "epi1", "asm0", "asm1", "solve1", "d2h1", "pfcopy0", "pfcopy1"};
+  for (int k = 1; k < t->cap; ++k) {
+    fprintf(stderr, "[pipe-trace] step %2d:", k);
+    for (int j = 0; j < 10; ++j) {
+      float ms = -1.f;
+      if (cudaEventElapsedTime(&ms, t->at(1, 2), t->at(k, j)) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
+      fprintf(stderr, " %s %7.1f", name[j], ms * 1e3f);
+    }
+    fprintf(stderr, "\n");
+  }
 }
 
 // Host image -> slot on the copy stream, ordered after the last kernel that read the slot.
@@ -1049,7 +1118,9 @@ static int pipeline_upload(fb_ctx* c, int slot, const uint8_t* const* images, co
     for (int s = 0; s + 1 < c->S; ++s) contiguous = contiguous && images[s + 1] - images[s] == (ptrdiff_t)fsz;
     if (contiguous) {
       const int lb = slot & 1;
+      if (allow_landing) pipe_trace_mark(pipe_trace(), 0, c->copy_stream);
       FB_CUDA(c, cudaMemcpyAsync(c->incoming + (size_t)lb * c->S * fsz, images[0], (size_t)c->S * fsz, cudaMemcpyHostToDevice, c->copy_stream));
+      if (allow_landing) pipe_trace_mark(pipe_trace(), 1, c->copy_stream);
       c->slot_landing[slot] = lb;
       FB_CUDA(c, cudaEventRecord(c->ev_ready[slot], c->copy_stream));
       FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_ready[slot], 0));
@@ -1128,6 +1199,7 @@ static int hotpath_step_inline(fb_ctx* c, const fb_step_desc* d) {
 static int hotpath_step_pipelined(fb_ctx* c, const fb_step_desc* d) {
   int rc = pipeline_init(c);
   if (rc) return rc;
+  PipeTrace* tr = pipe_trace();
   if ((rc = check_slot(c, 0, d->cmp_slot)) != 0) return rc;
   if (d->new_poseframe && (rc = check_slot(c, 0, d->ref_slot)) != 0) return rc;
   c->pipe_dirty = true;
@@ -1142,8 +1214,10 @@ static int hotpath_step_pipelined(fb_ctx* c, const fb_step_desc* d) {
       if ((rc = fb_frame_pose_set(c, s, d->ref_slot, d->ref_poses + 7 * s)) != 0) return rc;
     const bool landed = c->slot_landing[from] >= 0;
     const uint8_t* src = landed ? c->incoming + (size_t)c->slot_landing[from] * c->S * fsz : c->imgs + (size_t)from * fsz;
+    pipe_trace_mark(tr, 8, c->stream);
     FB_CUDA(c, cudaMemcpy2DAsync(c->imgs + (size_t)d->ref_slot * fsz, pitch, src, landed ? fsz : pitch, fsz, (size_t)c->S,
                                  cudaMemcpyDeviceToDevice, c->stream));
+    pipe_trace_mark(tr, 9, c->stream);
     FB_CUDA(c, cudaEventRecord(c->ev_free[from], c->stream));  // the next upload into `from` waits for this read
   } else if (d->new_poseframe) {
     rc = pipeline_upload(c, d->ref_slot, d->ref_images, d->ref_pool_idx, d->ref_poses, false);
@@ -1158,14 +1232,22 @@ static int hotpath_step_pipelined(fb_ctx* c, const fb_step_desc* d) {
   }
   std::fill(slots.begin(), slots.end(), d->cmp_slot);
   if (c->slot_landing[d->cmp_slot] >= 0) c->epi_cmp_frames = c->incoming + (size_t)c->slot_landing[d->cmp_slot] * c->S * c->W * c->H;
+  pipe_trace_mark(tr, 2, c->stream);
   rc = fb_idepth_update(c, slots.data());
   if (rc) return rc;
+  pipe_trace_mark(tr, 3, c->stream);
   // the frames read by this update may be overwritten once the epipolar kernel has run
   FB_CUDA(c, cudaEventRecord(c->ev_free[d->cmp_slot], c->stream));
   if (d->new_poseframe) {
-    // the OTHER poseframe slots are no longer referenced by any feature after the re-init
+    // the OTHER poseframe slots are no longer referenced by any feature after the re-init.  Only slots
+    // that held a poseframe: re-recording the event of the other COMPARISON slot here made the next
+    // frame's upload wait for this frame's epipolar update (52 us of exposed H2D every epoch).
     for (int k = 0; k < c->n_slots; ++k)
-      if (k != d->cmp_slot && k != d->ref_slot) FB_CUDA(c, cudaEventRecord(c->ev_free[k], c->stream));
+      if (k != d->cmp_slot && k != d->ref_slot && c->slot_is_ref[k]) {
+        FB_CUDA(c, cudaEventRecord(c->ev_free[k], c->stream));
+        c->slot_is_ref[k] = 0;
+      }
+    c->slot_is_ref[d->ref_slot] = 1;
   }
   // Second stage on its own (high-priority) stream: assembly + solve + D2H of frame k overlap the
   // epipolar update of frame k+1, which does not depend on them (FB_PIPE_SINGLE_STAGE=1 disables).
@@ -1175,19 +1257,39 @@ static int hotpath_step_pipelined(fb_ctx* c, const fb_step_desc* d) {
     FB_CUDA(c, cudaStreamWaitEvent(c->solve_stream, c->ev_free[d->cmp_slot], 0));
     c->stream = c->solve_stream;
   }
+  pipe_trace_mark(tr, 4, c->stream);
   rc = fb_graph_data_from_features(c, d->adaptive_weights);
+  pipe_trace_mark(tr, 5, c->stream);
   if (!rc && c->solve_stream) {
     // the next frame's filter update may touch the feature table once the assembly has read it
     if (cudaEventRecord(c->ev_asm, c->stream) != cudaSuccess || cudaStreamWaitEvent(main_stream, c->ev_asm, 0) != cudaSuccess) rc = FB_E_CUDA;
   }
   if (!rc) rc = fb_nltgv2_solve(c, d->iters, &d->rparams, d->variant);
+  pipe_trace_mark(tr, 6, c->stream);
   if (!rc && d->x_out) {
-    if (cudaMemcpyAsync(d->x_out, c->x, sizeof(float) * (size_t)c->S * c->maxV, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-        cudaEventRecord(c->ev_result[c->n_pipelined & 3], c->stream) != cudaSuccess)
+    // The read-back runs on a stream of its own from a device snapshot of x.  Queued on the solve
+    // stream, or reading x itself (the next solve then has to wait for the copy), its ~12 us of DMA
+    // latency sat on the critical path of every step (88 us per step against 78 without read-back).
+    const size_t bytes = sizeof(float) * (size_t)c->S * c->maxV;
+    const int n = c->n_pipelined;
+    if (c->out_stream) {
+      float* snap = c->x_stage[n & 1];
+      if ((n >= 2 && cudaStreamWaitEvent(c->stream, c->ev_result[(n - 2) & 3], 0) != cudaSuccess) ||  // the copy that last read this snapshot
+          cudaMemcpyAsync(snap, c->x, bytes, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess ||
+          cudaEventRecord(c->ev_solved, c->stream) != cudaSuccess || cudaStreamWaitEvent(c->out_stream, c->ev_solved, 0) != cudaSuccess ||
+          cudaMemcpyAsync(d->x_out, snap, bytes, cudaMemcpyDeviceToHost, c->out_stream) != cudaSuccess ||
+          cudaEventRecord(c->ev_result[n & 3], c->out_stream) != cudaSuccess)
+        rc = FB_E_CUDA;
+    } else if (cudaMemcpyAsync(d->x_out, c->x, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+               cudaEventRecord(c->ev_result[n & 3], c->stream) != cudaSuccess) {
       rc = FB_E_CUDA;
+    }
+    cudaStream_t os = c->out_stream ? c->out_stream : c->stream;
     c->n_pipelined++;
+    pipe_trace_mark(tr, 7, os);
   }
   c->stream = main_stream;
+  pipe_trace_step_done(tr);
   if (rc == FB_E_CUDA) c->err = "fb_hotpath_step: CUDA error in the pipelined step";
   return rc;
 }
@@ -1219,6 +1321,7 @@ extern "C" int fb_pipeline_join(fb_ctx* c) {
     FB_CUDA(c, cudaEventRecord(c->ev_join2, c->solve_stream));
     FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join2, 0));
   }
+  if (c->out_stream && c->n_pipelined > 0) FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_result[(c->n_pipelined - 1) & 3], 0));
   return FB_OK;
 }
 
