@@ -149,6 +149,10 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+RESULT_LAG = 3            # e2e leg: steps between a step's enqueue and the host's read of its result
+RESULT_BUFFERS = RESULT_LAG + 1
+
+
 class GpuRun:
     """One context with S streams of the workload; runs steps in `resident` or `e2e` mode."""
 
@@ -165,7 +169,7 @@ class GpuRun:
         # than the 126 MB L2 (a frame is re-read only after > L2 bytes of other frames went by)
         fbytes = d0.W * d0.H
         self.pool_copies = max(1, -(-(160 << 20) // (self.S * WL.POOL_FRAMES * fbytes)))
-        self.pool_copies = 3 * -(-self.pool_copies // 3)   # schedule period divisible by the 3 result buffers
+        self.pool_copies = 2 * -(-self.pool_copies // 2)   # schedule period (10 x copies) divisible by the 4 result buffers
         ctx.pool_reserve(self.pool_copies * self.S * WL.POOL_FRAMES)
         for s, d in enumerate(datas):
             ctx.set_intrinsics(s, d.K)
@@ -185,7 +189,7 @@ class GpuRun:
         self.h_frames = capi.PinnedBuffer((WL.POOL_FRAMES, self.S, d0.H, d0.W), np.uint8)
         for s, d in enumerate(datas):
             np.copyto(self.h_frames.array[:, s], d.frames)
-        self.h_x = capi.PinnedBuffer((3, self.S, V), np.float32)   # triple-buffered results
+        self.h_x = capi.PinnedBuffer((RESULT_BUFFERS, self.S, V), np.float32)   # ring of result buffers
         self.maxV = V
         self.cmp = np.full(self.S, WL.CMP_SLOT, np.int32)
         ctx.sync()
@@ -220,7 +224,7 @@ class GpuRun:
                     d.ref_images = C.cast(ref_ptr, C.POINTER(C.c_void_p))
                     d.cmp_images = C.cast(cmp_ptr, C.POINTER(C.c_void_p))
                     if not os.environ.get("FB_BENCH_NO_XOUT"):   # diagnosis only
-                        d.x_out = self.h_x.array[k % 3].ctypes.data_as(C.POINTER(C.c_float))
+                        d.x_out = self.h_x.array[k % RESULT_BUFFERS].ctypes.data_as(C.POINTER(C.c_float))
                 if mode in ("e2e_pipe", "resident"):
                     d.pipelined = 1
                     d.cmp_slot = WL.CMP_SLOT + (k % 2)   # frames alternate between two slots
@@ -248,7 +252,7 @@ class GpuRun:
 
     def consume(self, k):
         """Touch the result of step k (the application's read of the vertex inverse depths)."""
-        return float(self.h_x.array[k % 3, 0, 0])
+        return float(self.h_x.array[k % RESULT_BUFFERS, 0, 0])
 
     def bytes_per_step(self):
         d = self.datas[0]
@@ -289,19 +293,20 @@ def run_gpu_leg(torch, run, steps, warmup, flush_buf, mode, barrier, min_region_
             return e0.elapsed_time(e1) * 1e-3
         if mode == "e2e_pipe":
             # K steps back to back; every step uploads its frames from pinned host memory and its vertex
-            # idepths are read on the host two steps later (triple-buffered), like a streaming consumer:
-            # the host stays two frames ahead of the GPU so the next upload is already in flight
+            # idepths are read on the host RESULT_LAG steps later (a ring of RESULT_LAG + 1 pinned buffers),
+            # like a streaming consumer.  From the enqueue of a step to its result the chain is upload (52 us)
+            # -> epipolar update -> assembly -> solve -> read-back, ~220 us: with a lag of 2 the host could
+            # not start the next upload early enough and the upload sat on the critical path (90 us per step).
             t0 = time.perf_counter()
             for i in range(steps):
                 k = k0 + i
                 run.step(k, mode)
-                if i > 1:
-                    ctx.results_wait(2)
-                    run.consume(k - 2)
-            ctx.results_wait(1)
-            run.consume(k0 + steps - 2)
-            ctx.results_wait(0)
-            run.consume(k0 + steps - 1)
+                if i >= RESULT_LAG:
+                    ctx.results_wait(RESULT_LAG)
+                    run.consume(k - RESULT_LAG)
+            for lag in range(min(RESULT_LAG, steps) - 1, -1, -1):
+                ctx.results_wait(lag)
+                run.consume(k0 + steps - 1 - lag)
             torch.cuda.synchronize()
             return time.perf_counter() - t0
         total = 0.0

@@ -36,6 +36,13 @@ struct fb_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t out_stream = nullptr;     // D2H of the vertex idepths of frame k (off the solve stream's critical path)
   cudaEvent_t ev_solved = nullptr;
+  // pipelined step: the data term is double-buffered so that the assembly of frame k+1 (main stream)
+  // overlaps the solve of frame k (solve stream); z / wt point at the buffer of the latest assembly
+  float* z_buf[2] = {nullptr, nullptr};
+  float* wt_buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev_zfree[2] = {nullptr, nullptr};  // recorded after the solve that read buffer b
+  bool zfree_valid[2] = {false, false};
+  int64_t n_pipe_steps = 0;
   float* x_stage[2] = {nullptr, nullptr}; // device snapshots of x the result copies read (the next solve is free to write x)
   cudaStream_t solve_stream = nullptr;   // assembly + solver of frame k run here while `stream` already
                                          // processes the epipolar update of frame k+1
@@ -122,7 +129,8 @@ struct fb_ctx {
 
   // ---- CUDA-graph cache for the streaming solver: one executable per value of `only` (index
   // only + 1; fb_update on a batch context solves one stream at a time, round robin)
-  std::vector<cudaGraphExec_t> solve_exec;
+  std::vector<cudaGraphExec_t> solve_exec;   // [2 * (S + 1)]: per `only` and per data-term buffer
+  std::vector<const float*> solve_z;
   std::vector<int> solve_iters;
   std::vector<fb_nltgv2_params> solve_params;
   // ---- plan-free resident solver (variant 4, nltgv2_coop.cuh)

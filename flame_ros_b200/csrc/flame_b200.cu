@@ -100,6 +100,9 @@ extern "C" void fb_host_free(void* p) {
 }
 
 static void free_all(fb_ctx* c) {
+  if (c->z_buf[0]) { c->z = c->z_buf[0]; c->wt = c->wt_buf[0]; }  // the originals; the second buffers below
+  cudaFree(c->z_buf[1]); cudaFree(c->wt_buf[1]);
+  for (int b = 0; b < 2; ++b) if (c->ev_zfree[b]) cudaEventDestroy(c->ev_zfree[b]);
   cudaFree(c->vbar); cudaFree(c->x); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->z);
   cudaFree(c->wt); cudaFree(c->ec); cudaFree(c->eij); cudaFree(c->q4); cudaFree(c->row);
   cudaFree(c->inc); cudaFree(c->epos); cudaFree(c->vnin); cudaFree(c->nV); cudaFree(c->nE); cudaFree(c->vfeat); cudaFree(c->vpos);
@@ -424,12 +427,14 @@ static int solve_streaming(fb_ctx* c, int iters, const fb_nltgv2_params* p, int 
   // survives topology changes.
   static_assert(sizeof(fb_nltgv2_params) == 24, "params layout");
   if (c->solve_exec.empty()) {
-    c->solve_exec.assign(c->S + 1, nullptr);
-    c->solve_iters.assign(c->S + 1, 0);
-    c->solve_params.assign(c->S + 1, fb_nltgv2_params{});
+    c->solve_exec.assign(2 * (c->S + 1), nullptr);
+    c->solve_iters.assign(2 * (c->S + 1), 0);
+    c->solve_params.assign(2 * (c->S + 1), fb_nltgv2_params{});
+    c->solve_z.assign(2 * (c->S + 1), nullptr);
   }
-  const int slot = only + 1;
-  const bool reuse = c->solve_exec[slot] && c->solve_iters[slot] == iters &&
+  // the captured launches hold the data-term pointers: one cached graph per buffer of the pipelined step
+  const int slot = 2 * (only + 1) + ((c->z_buf[1] && c->z == c->z_buf[1]) ? 1 : 0);
+  const bool reuse = c->solve_exec[slot] && c->solve_iters[slot] == iters && c->solve_z[slot] == c->z &&
                      memcmp(&c->solve_params[slot], p, sizeof(*p)) == 0;
   if (!reuse) {
     if (c->solve_exec[slot]) { cudaGraphExecDestroy(c->solve_exec[slot]); c->solve_exec[slot] = nullptr; }
@@ -449,6 +454,7 @@ static int solve_streaming(fb_ctx* c, int iters, const fb_nltgv2_params* p, int 
     if (e != cudaSuccess) { c->solve_exec[slot] = nullptr; FB_FAIL(c, FB_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
     c->solve_iters[slot] = iters;
     c->solve_params[slot] = *p;
+    c->solve_z[slot] = c->z;
   }
   ProfScope ps(c, FB_PROF_SOLVE);
   FB_CUDA(c, cudaGraphLaunch(c->solve_exec[slot], c->stream));
@@ -1044,6 +1050,16 @@ static int pipeline_init(fb_ctx* c) {
     FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_asm, cudaEventDisableTiming));
     FB_CUDA(c, cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
     FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_solved, cudaEventDisableTiming));
+    if (!getenv("FB_PIPE_SINGLE_DATA")) {
+      const size_t nv = (size_t)c->S * c->maxV;
+      c->z_buf[0] = c->z; c->wt_buf[0] = c->wt;
+      FB_CUDA(c, dalloc(&c->z_buf[1], nv));
+      FB_CUDA(c, dalloc(&c->wt_buf[1], nv));
+      // dead / unbound vertices keep whatever z holds (their weight is 0, the value never matters, but it must be finite)
+      FB_CUDA(c, cudaMemcpy(c->z_buf[1], c->z, sizeof(float) * nv, cudaMemcpyDeviceToDevice));
+      FB_CUDA(c, cudaMemcpy(c->wt_buf[1], c->wt, sizeof(float) * nv, cudaMemcpyDeviceToDevice));
+      for (int b = 0; b < 2; ++b) FB_CUDA(c, cudaEventCreateWithFlags(&c->ev_zfree[b], cudaEventDisableTiming));
+    }
     FB_CUDA(c, dalloc(&c->x_stage[0], (size_t)c->S * c->maxV));
     FB_CUDA(c, dalloc(&c->x_stage[1], (size_t)c->S * c->maxV));
   }
@@ -1249,10 +1265,19 @@ static int hotpath_step_pipelined(fb_ctx* c, const fb_step_desc* d) {
       }
     c->slot_is_ref[d->ref_slot] = 1;
   }
-  // Second stage on its own (high-priority) stream: assembly + solve + D2H of frame k overlap the
-  // epipolar update of frame k+1, which does not depend on them (FB_PIPE_SINGLE_STAGE=1 disables).
+  // Second stage on its own (high-priority) stream: the solve + D2H of frame k overlap the epipolar
+  // update AND the assembly of frame k+1 (FB_PIPE_SINGLE_STAGE=1 disables).  The assembly snapshots mu
+  // into the data term z / wt, which is double-buffered: it runs on the main stream right behind the
+  // epipolar update into the buffer the running solve does not read (on the solve stream its 8 us sat
+  // in the cycle that bounds the step: assembly + solve).
   cudaStream_t main_stream = c->stream;
-  if (c->solve_stream) {
+  const bool dbuf = c->solve_stream && c->z_buf[1];
+  const int zb = (int)(c->n_pipe_steps & 1);
+  if (dbuf) {
+    c->z = c->z_buf[zb];
+    c->wt = c->wt_buf[zb];
+    if (c->zfree_valid[zb]) FB_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_zfree[zb], 0));  // the solve of frame k-2 read this buffer
+  } else if (c->solve_stream) {
     // ev_free[cmp_slot] was recorded right after the epipolar kernel: the same point the second stage waits for
     FB_CUDA(c, cudaStreamWaitEvent(c->solve_stream, c->ev_free[d->cmp_slot], 0));
     c->stream = c->solve_stream;
@@ -1260,7 +1285,10 @@ static int hotpath_step_pipelined(fb_ctx* c, const fb_step_desc* d) {
   pipe_trace_mark(tr, 4, c->stream);
   rc = fb_graph_data_from_features(c, d->adaptive_weights);
   pipe_trace_mark(tr, 5, c->stream);
-  if (!rc && c->solve_stream) {
+  if (!rc && dbuf) {
+    if (cudaEventRecord(c->ev_asm, main_stream) != cudaSuccess || cudaStreamWaitEvent(c->solve_stream, c->ev_asm, 0) != cudaSuccess) rc = FB_E_CUDA;
+    c->stream = c->solve_stream;
+  } else if (!rc && c->solve_stream) {
     // the next frame's filter update may touch the feature table once the assembly has read it
     if (cudaEventRecord(c->ev_asm, c->stream) != cudaSuccess || cudaStreamWaitEvent(main_stream, c->ev_asm, 0) != cudaSuccess) rc = FB_E_CUDA;
   }
@@ -1288,6 +1316,11 @@ static int hotpath_step_pipelined(fb_ctx* c, const fb_step_desc* d) {
     c->n_pipelined++;
     pipe_trace_mark(tr, 7, os);
   }
+  if (!rc && dbuf) {
+    if (cudaEventRecord(c->ev_zfree[zb], c->stream) != cudaSuccess) rc = FB_E_CUDA;
+    c->zfree_valid[zb] = true;
+  }
+  c->n_pipe_steps++;
   c->stream = main_stream;
   pipe_trace_step_done(tr);
   if (rc == FB_E_CUDA) c->err = "fb_hotpath_step: CUDA error in the pipelined step";

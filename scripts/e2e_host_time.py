@@ -18,13 +18,13 @@ datas = [WL.StreamData("C2", seed=s) for s in range(8)]
 run = B.GpuRun(capi, datas, 0, ts.cuda_stream, 0)
 ctx = run.ctx
 import ctypes as C
-variants = [("resident", "resident", None), ("resident + result read-back", "resident", True), ("e2e without result read-back", "e2e_pipe", False), ("e2e_pipe", "e2e_pipe", None)]
+variants = [("resident", "resident", None), ("resident + result read-back", "resident", True), ("e2e without result read-back", "e2e_pipe", False), ("e2e_pipe", "e2e_pipe", True)]
 for label, mode, xout in variants:
     run.step(0, mode)   # builds the descriptor table
     for (kk, mm), d in run._table.items():
         if mm != mode or xout is None:
             continue
-        d.x_out = run.h_x.array[kk % 3].ctypes.data_as(C.POINTER(C.c_float)) if xout else None
+        d.x_out = run.h_x.array[kk % B.RESULT_BUFFERS].ctypes.data_as(C.POINTER(C.c_float)) if xout else None
     for k in range(30):
         run.step(k, mode)
     ctx.sync(); torch.cuda.synchronize()
@@ -35,8 +35,8 @@ for label, mode, xout in variants:
             a = time.perf_counter()
             run.step(30 + i, mode)
             b = time.perf_counter()
-            if (mode == "e2e_pipe" and xout is not False or xout) and i > 1:
-                ctx.results_wait(2)
+            if (mode == "e2e_pipe" and xout is not False or xout) and i >= B.RESULT_LAG:
+                ctx.results_wait(B.RESULT_LAG)
             c = time.perf_counter()
             enq.append(b - a); wait.append(c - b)
         if (mode == "e2e_pipe" and xout is not False) or xout:

@@ -18,7 +18,7 @@ run = B.GpuRun(capi, datas, 0, ts.cuda_stream, 0)
 mode = sys.argv[1] if len(sys.argv) > 1 else "e2e_pipe"
 for i in range(60):
     run.step(i, mode)
-    if mode == "e2e_pipe" and i > 1:
-        run.ctx.results_wait(2)
+    if mode == "e2e_pipe" and i >= B.RESULT_LAG:
+        run.ctx.results_wait(B.RESULT_LAG)
 run.ctx.sync()
 run.close()
