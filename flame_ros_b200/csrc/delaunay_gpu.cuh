@@ -112,7 +112,8 @@ struct DsgGraph {
 __global__ void __launch_bounds__(256)
 k_ds_stash(DsgGraph g, DelGpu d, int s, int maxV, int maxE) {
   int32_t* meta = d.meta + (size_t)s * DSG_META;
-  const int V = meta[DSG_NV], E = meta[DSG_NE];
+  // counts of the PREVIOUS graph, left by k_ds_prepare (which has already stored the new vertex count)
+  const int V = meta[DSG_OLD_NV], E = meta[DSG_OLD_NE];
   const size_t vb = (size_t)s * maxV, eb = (size_t)s * maxE, ob = (size_t)s * (maxV + 1);
   const int n = blockDim.x * gridDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   for (int v = t0; v < V; v += n) {
@@ -125,10 +126,6 @@ k_ds_stash(DsgGraph g, DelGpu d, int s, int maxV, int maxE) {
   for (int e = t0; e < E; e += n) {
     d.o_q4[eb + e] = g.q4[eb + e];
     d.o_eij[eb + e] = g.eij[eb + e];
-  }
-  if (t0 == 0) {
-    meta[DSG_OLD_NV] = meta[DSG_HAVE] ? V : 0;
-    meta[DSG_OLD_NE] = meta[DSG_HAVE] ? E : 0;
   }
 }
 
@@ -197,6 +194,9 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
     s_box[0] = s_box[1] = 0x7fffffff;
     s_box[2] = s_box[3] = -0x7fffffff;
     s_bad = 0;
+    // counts of the graph this one replaces, for k_ds_stash / k_ds_csr (NV is overwritten below)
+    meta[DSG_OLD_NV] = meta[DSG_HAVE] ? meta[DSG_NV] : 0;
+    meta[DSG_OLD_NE] = meta[DSG_HAVE] ? meta[DSG_NE] : 0;
   }
   // ---- selection in ascending feature index: a warp's 32 flags become one ballot word, a block scan
   // over the words' popcounts ranks them (rounds of 65536 features)

@@ -26,6 +26,7 @@ static void update_mark_host_graph(fb_ctx* c, int s);
 static void update_invalidate_graphs(fb_ctx* c);
 static void tile_plan_free(fb_ctx* c);
 static void tile_plan_mark(fb_ctx* c, int s);
+static void tile_assign_early(fb_ctx* c, int s, cudaStream_t st);
 static bool fb_tile_failed(const fb_ctx* c);
 
 // ------------------------------------------------------------------------------------ helpers
@@ -475,6 +476,7 @@ static void tile_plan_mark(fb_ctx* c, int s) {
   if (c->tplan && s < (int)c->tplan->dirty.size()) c->tplan->dirty[s] = 1;
 }
 static bool fb_tile_failed(const fb_ctx* c) { return c->tplan && c->tplan->err && *c->tplan->err != 0; }
+static bool tile_available(fb_ctx* c);
 // Allocates the plan and probes the launch configuration (cluster of 16, ~148 KB shared memory).
 static bool tile_available(fb_ctx* c) {
   if (c->tplan && c->tplan->available >= 0) return c->tplan->available == 1;
@@ -514,6 +516,17 @@ static bool tile_available(fb_ctx* c) {
   if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) { cudaGetLastError(); n = 0; }
   T->available = n >= 1 ? 1 : 0;
   return T->available == 1;
+}
+
+// The tiles of one stream cut ahead of the solve, on a side stream (fb_update: beside the star kernel).
+// A no-op when the tile-resident solver is not the one fb_update will pick.
+static void tile_assign_early(fb_ctx* c, int s, cudaStream_t st) {
+  if (!tile_available(c)) return;
+  TilePlan* T = c->tplan;
+  if (!T->dirty[s]) return;
+  k_tile_assign<<<1, 1024, 0, st>>>(s, c->maxV, c->nV, c->vpos, T->vtile, T->vloc, T->tlist, T->toff);
+  c->launches++;
+  T->dirty[s] = 0;
 }
 
 static int solve_tile(fb_ctx* c, int iters, const fb_nltgv2_params* p, int only = -1) {

@@ -77,6 +77,10 @@ struct UpdateState {
   DelGpu del;                    // device-side sync_graph + triangulate (delaunay_gpu.cuh)
   int32_t* misc = nullptr;       // [S*4] device: covered pixels, live projected features, 0, 0
   int32_t* h_read = nullptr;     // pinned [S*(DSG_META+4)]: per-frame readback of meta + misc
+  // side branch of the graph build: the old state is set aside and the solver's tiles are cut while
+  // the star kernel runs (fork after k_ds_prepare, join before k_ds_scan)
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint8_t* h_img = nullptr;      // pinned [S][H*W]: staging of the frame the graph uploads
   float* h_geo = nullptr;        // pinned [S][n_slots*7 + 1]: poses + comparison slot the graph uploads
   bool use_graph = true;         // FB_UPDATE_GRAPH=0 disables
@@ -263,6 +267,11 @@ static int update_alloc(fb_ctx* c) {
   A(dalloc(&D.o_q4, ne)); A(dalloc(&D.o_eij, ne)); A(dalloc(&D.o_eoff, S * (c->maxV + 1)));
   A(dalloc(&U->misc, S * 4));
   A(cudaMallocHost((void**)&U->h_read, sizeof(int32_t) * S * (DSG_META + 4)));
+  if (!getenv("FB_UPDATE_NO_FORK")) {
+    A(cudaStreamCreateWithFlags(&U->aux, cudaStreamNonBlocking));
+    A(cudaEventCreateWithFlags(&U->ev_fork, cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&U->ev_join, cudaEventDisableTiming));
+  }
   A(cudaMallocHost((void**)&U->h_img, S * (size_t)c->W * c->H));
   A(cudaMallocHost((void**)&U->h_geo, sizeof(float) * S * ((size_t)c->n_slots * 7 + 1)));
   if (const char* e = getenv("FB_UPDATE_GRAPH")) U->use_graph = atoi(e) != 0;
@@ -295,6 +304,9 @@ static void update_free(fb_ctx* c) {
   cudaFree(D.f2v); cudaFree(D.o_x); cudaFree(D.o_w1); cudaFree(D.o_w2); cudaFree(D.o_vbar);
   cudaFree(D.o_q4); cudaFree(D.o_eij); cudaFree(D.o_eoff);
   cudaFree(U->misc);
+  if (U->aux) cudaStreamDestroy(U->aux);
+  if (U->ev_fork) cudaEventDestroy(U->ev_fork);
+  if (U->ev_join) cudaEventDestroy(U->ev_join);
   if (U->h_read) cudaFreeHost(U->h_read);
   if (U->h_img) cudaFreeHost(U->h_img);
   if (U->h_geo) cudaFreeHost(U->h_geo);
@@ -417,13 +429,29 @@ static int update_graph_device(fb_ctx* c, int s) {
   cudaStream_t st = c->stream;
   const int par = (int)(S.builds & 1);
   DsgGraph gg{c->x, c->w1, c->w2, c->vbar, c->q4, c->eij};
-  k_ds_stash<<<64, 256, 0, st>>>(gg, D, s, c->maxV, c->maxE);
   const int use_height = (p.min_height > -1e13f || p.max_height < 1e13f) ? 1 : 0;
   DsgSelect q{U->f_ucur + fb, U->f_varcur + fb, U->f_valid + fb, p.idepth_var_max_graph, c->maxF, c->maxV, c->W, c->H,
               use_height, U->f_mucur + fb, c->d_K + 9 * s, c->d_pose + ((size_t)s * c->n_slots + (c->n_slots - 1)) * 7,
               p.min_height, p.max_height};
   k_ds_prepare<<<1, DSG_THREADS, 0, st>>>(q, D, s, c->vfeat + vb, c->vpos + vb, D.f2v + par * nf + fb, c->nV + s);
+  // per-topology tables of the resident solvers (variants 2 / 3) do not describe this graph
+  if (c->plan && s < (int)c->plan->topo.size()) { c->plan->topo[s].V = 0; c->plan->topo[s].dirty = true; }
+  if (c->gplan) { c->gplan->topo[s].dirty = true; c->gplan->topo[s].planned = 0; c->gplan->version++; }
+  tile_plan_mark(c, s);  // positions moved: the tiles of variant 5 are re-cut (one small kernel)
+  // Side branch while the stars are computed (they take the whole GPU for ~75 us, these two a few SMs
+  // for ~17 us): the previous graph's state aside (k_ds_prepare left its counts in OLD_NV / OLD_NE; the
+  // copy must be through before k_ds_scan rewrites the edge offsets) and the solver's tiles from the
+  // new vertex positions.  Inside a captured frame the events become fork / join edges of the graph.
+  cudaStream_t side = U->aux ? U->aux : st;
+  if (U->aux) {
+    FB_CUDA(c, cudaEventRecord(U->ev_fork, st));
+    FB_CUDA(c, cudaStreamWaitEvent(U->aux, U->ev_fork, 0));
+  }
+  k_ds_stash<<<64, 256, 0, side>>>(gg, D, s, c->maxV, c->maxE);
+  tile_assign_early(c, s, side);
+  if (U->aux) FB_CUDA(c, cudaEventRecord(U->ev_join, U->aux));
   k_ds_stars<<<dsg_stars_grid(c->device, c->maxV), DSG_WARPS * 32, 0, st>>>(D, s, c->maxV);
+  if (U->aux) FB_CUDA(c, cudaStreamWaitEvent(st, U->ev_join, 0));
   k_ds_scan<<<1, DSG_THREADS, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->row + (size_t)s * (c->maxV + 1), c->nE + s, c->nT + s);
   k_ds_emit<<<fb_div_up(c->maxV, 4), 128, 0, st>>>(D, s, c->maxV, c->maxE, c->maxT, c->vpos + vb, c->eij + eb, c->ec + eb,
                                                     c->tri + (size_t)s * c->maxT * 3);
@@ -436,10 +464,6 @@ static int update_graph_device(fb_ctx* c, int s) {
   FB_CUDA(c, cudaGetLastError());
   S.builds++;
   S.dev_graph = true;
-  // per-topology tables of the resident solvers (variants 2 / 3) do not describe this graph
-  if (c->plan && s < (int)c->plan->topo.size()) { c->plan->topo[s].V = 0; c->plan->topo[s].dirty = true; }
-  if (c->gplan) { c->gplan->topo[s].dirty = true; c->gplan->topo[s].planned = 0; c->gplan->version++; }
-  tile_plan_mark(c, s);  // positions moved: the tiles of variant 5 are re-cut (one small kernel)
   return FB_OK;
 }
 

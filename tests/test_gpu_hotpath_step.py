@@ -30,11 +30,19 @@ def _make(capi, datas):
     return ctx
 
 
-def _run(capi, datas, mode, steps):
+def _run(capi, datas, mode, steps, frame_major=False):
+    """frame_major: the S frames of a step are contiguous in host memory (a multi-camera capture buffer):
+    the pipelined mode then uploads them as one transfer into its landing buffer."""
     S = len(datas)
     ctx = _make(capi, datas)
     V = ctx.max_vertices
-    frames = capi.PinnedBuffer((S, WL.POOL_FRAMES, datas[0].H, datas[0].W), np.uint8)
+    if frame_major:
+        store = capi.PinnedBuffer((WL.POOL_FRAMES, S, datas[0].H, datas[0].W), np.uint8)
+        frames_array = store.array.transpose(1, 0, 2, 3)   # indexed [stream, frame] like the other layout
+    else:
+        store = capi.PinnedBuffer((S, WL.POOL_FRAMES, datas[0].H, datas[0].W), np.uint8)
+        frames_array = store.array
+    frames = type("Frames", (), {"array": frames_array, "free": store.free})()
     for s, d in enumerate(datas):
         np.copyto(frames.array[s], d.frames)
     xbuf = capi.PinnedBuffer((2, S, V), np.float32)
@@ -118,3 +126,21 @@ def test_modes_agree_and_match_the_oracle(capi, oracle):
             oracle.nltgv2_solve(d.u_ref, d.edges, d.alpha, d.beta, z, wt, st, oracle.NLTGV2Params.default(), d.iters)
             assert np.max(np.abs(res[k][s, :V] - st["x"])) < TOL, "stream %d step %d" % (s, k)
         assert np.array_equal(fr[s]["alive"], alive) and np.max(np.abs(fr[s]["mu"] - mu)) < TOL
+
+
+@pytest.mark.parametrize("env", [{}, {"FB_GEO_PINNED": "1"}, {"FB_PIPE_SINGLE_DATA": "1"}, {"FB_PIPE_SINGLE_STAGE": "1"}])
+def test_pipelined_variants_are_bit_identical(capi, monkeypatch, env):
+    """The pipelined step's optional mechanisms -- one-transfer upload into the landing buffer (frames of
+    a step contiguous on the host), poses / slots as kernel parameters vs read from pinned memory,
+    double-buffered data term, second stage on its own stream -- never change a bit of the result."""
+    datas = [WL.StreamData("tiny", seed=10 + s) for s in range(3)]
+    steps = 12
+    res, fr = _run(capi, datas, "resident", steps)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    pip, fp = _run(capi, datas, "pipe", steps, frame_major=True)
+    for k in range(steps):
+        assert np.array_equal(res[k], pip[k]), "pipelined mode %s differs at step %d" % (env, k)
+    for s in range(3):
+        for key in ("mu", "var", "alive", "status"):
+            assert np.array_equal(fr[s][key], fp[s][key])
