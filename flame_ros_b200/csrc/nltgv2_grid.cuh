@@ -284,8 +284,27 @@ k_nltgv2_grid(GridArgs a, int iters, float sigma, float tau, float tl, float the
     F.idx[k] = dummy << 16;
   }
   F.store = 0u;
+  // The part's slice of the vertex table (vertex id, CSR slot rows and s_bar entry, push range: 16 B per
+  // vertex, contiguous) comes in as ONE TMA bulk copy into the slot area, which is idle until the first
+  // dual half-step; completion is signalled on an mbarrier.  (Tiny graphs whose slot area is smaller
+  // than the slice read the table directly.)
+  __shared__ __align__(8) uint64_t s_tma;
+  const bool tma = nOwn <= a.capSlot;  // uniform over the CTA
+  if (tma) {
+    const uint32_t mbt = fbc_smem_u32(&s_tma);
+    if (tid == 0) {
+      fbc_mbar_init(mbt, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      fbc_mbar_expect(mbt, 16u * (uint32_t)nOwn);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot_base),
+                   "l"(a.vplan + vb + c0.x), "r"(16u * (uint32_t)nOwn), "r"(mbt)
+                   : "memory");
+    }
+    __syncthreads();  // the barrier is initialised before anyone waits on it
+    fbc_mbar_wait(mbt, 0);
+  }
   if (tid < nOwn) {
-    const int4 pt = a.vplan[vb + c0.x + tid];
+    const int4 pt = tma ? reinterpret_cast<const int4*>(s_slot)[tid] : a.vplan[vb + c0.x + tid];
     const int v = pt.x;
     v_sl = (uint32_t)pt.y;
     v_push = (uint32_t)pt.z;
