@@ -278,7 +278,8 @@ DS_FN bool ds_block_all(const DsIn& in, const DsBlock& b) {
 // chord's endpoints and those of the circle's four axis-extreme points that are on the sweep side.
 // (Only sweep-side points can contradict `best`; for a sliver near the hull the segment is a thin
 // cap while the whole disc would cover half the image.)  Conservative: rounded outward.
-DS_FN void ds_circle_region_f64(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir, int64_t* r) {
+struct DsBox { int64_t r[4]; int ok; };
+DS_FN void ds_circle_region_f64_impl(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir, int64_t* r) {
   // (p, a, b) counter-clockwise
   const DsPt a = dir > 0 ? cur : best, b = dir > 0 ? best : cur;
   const double ax = (double)(a.x - p.x), ay = (double)(a.y - p.y), bx = (double)(b.x - p.x), by = (double)(b.y - p.y);
@@ -303,6 +304,14 @@ DS_FN void ds_circle_region_f64(const DsIn& in, DsPt p, DsPt cur, DsPt best, int
   r[0] = (int64_t)floor(x0); r[1] = (int64_t)floor(y0); r[2] = (int64_t)ceil(x1); r[3] = (int64_t)ceil(y1);
 }
 
+// Out of line (returned by value): rare, and inlined its double-precision code was hoisted in front of
+// every sweep step by loop-invariant code motion.
+DS_COLD DsBox ds_circle_region_f64(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir) {
+  DsBox b;
+  ds_circle_region_f64_impl(in, p, cur, best, dir, b.r);
+  b.ok = 1;
+  return b;
+}
 // The same region at fp32 cost.  Only the circumcentre's numerators and denominator need the exact
 // (double) products -- they cancel for slivers; everything after the division only has to be
 // CONSERVATIVE, so it runs in fp32 with margins that cover every rounding (relative 2^-22 on the
@@ -318,7 +327,8 @@ DS_FN void ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir
   const float ux = (float)(by * a2 - ay * b2) / fd, uy = (float)(ax * b2 - bx * a2) / fd;  // centre - p
   const float rad = sqrtf(ux * ux + uy * uy);
   if (!(rad < 1e12f)) {
-    ds_circle_region_f64(in, p, cur, best, dir, r);
+    const DsBox b = ds_circle_region_f64(in, p, cur, best, dir);
+    r[0] = b.r[0]; r[1] = b.r[1]; r[2] = b.r[2]; r[3] = b.r[3];
     return;
   }
   const float ext = rad + fabsf(ux) + fabsf(uy);
@@ -343,7 +353,7 @@ DS_FN void ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir
 
 // Bounding box of (half-plane on the sweep side of p->cur) clipped to the bounding box of all
 // points; false when the intersection is empty.
-DS_FN bool ds_halfplane_region(const DsIn& in, DsPt p, DsPt cur, int dir, int64_t* r) {
+DS_FN bool ds_halfplane_region_impl(const DsIn& in, DsPt p, DsPt cur, int dir, int64_t* r) {
   const DsPt c[4] = {{in.bx0, in.by0}, {in.bx1, in.by0}, {in.bx1, in.by1}, {in.bx0, in.by1}};
   int64_t o[4];
   for (int k = 0; k < 4; ++k) o[k] = ds_orient(p, cur, c[k]) * dir;
@@ -370,6 +380,15 @@ DS_FN bool ds_halfplane_region(const DsIn& in, DsPt p, DsPt cur, int dir, int64_
   x1 = fmin(x1, (double)in.bx1); y1 = fmin(y1, (double)in.by1);
   r[0] = (int64_t)floor(x0); r[1] = (int64_t)floor(y0); r[2] = (int64_t)ceil(x1); r[3] = (int64_t)ceil(y1);
   return true;
+}
+
+// Out of line for the same reason: it depends only on (p, cur, dir), so inlined it was computed (four
+// double divisions) at the top of EVERY sweep step -- 22 % of the star kernel's instructions -- although
+// only a step that finds no candidate (a hull end) needs it.
+DS_COLD DsBox ds_halfplane_region(const DsIn& in, DsPt p, DsPt cur, int dir) {
+  DsBox b;
+  b.ok = ds_halfplane_region_impl(in, p, cur, dir, b.r) ? 1 : 0;
+  return b;
 }
 
 // ------------------------------------------------------------------------------------ sweep step
@@ -464,7 +483,10 @@ DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, 
     }
     int64_t reg[4];
     if (bid < 0) {
-      if (ds_block_all(in, blk) || !ds_halfplane_region(in, pp, cur, dir, reg)) return -1;
+      if (ds_block_all(in, blk)) return -1;
+      const DsBox hb = ds_halfplane_region(in, pp, cur, dir);
+      if (!hb.ok) return -1;
+      reg[0] = hb.r[0]; reg[1] = hb.r[1]; reg[2] = hb.r[2]; reg[3] = hb.r[3];
       if (!ds_block_cover(in, blk, reg[0], reg[1], reg[2], reg[3])) return -1;
       ds_block_rows<W>(in, blk, S);
       continue;
