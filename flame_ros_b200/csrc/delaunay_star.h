@@ -318,7 +318,9 @@ DS_COLD DsBox ds_circle_region_f64(const DsIn& in, DsPt p, DsPt cur, DsPt best, 
 // centre and radius, against 2e-6 here).  Circles too large for that (radius > 1e12 lattice units)
 // take the double path.  The region never decides a predicate: a looser box only means more
 // candidates are looked at, so host and device may round differently here without consequence.
-DS_FN void ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir, int64_t* r) {
+// Returns true when the WHOLE disc already lies inside the block's cells (the common case for an
+// interior vertex: nothing to refine, nothing to grow); otherwise r receives the segment's box.
+DS_FN bool ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir, const DsBlock& blk, int64_t* r) {
   const DsPt a = dir > 0 ? cur : best, b = dir > 0 ? best : cur;  // (p, a, b) counter-clockwise
   const double ax = (double)(a.x - p.x), ay = (double)(a.y - p.y), bx = (double)(b.x - p.x), by = (double)(b.y - p.y);
   const double d = 2.0 * (ax * by - ay * bx);  // > 0, exact
@@ -329,10 +331,19 @@ DS_FN void ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir
   if (!(rad < 1e12f)) {
     const DsBox b = ds_circle_region_f64(in, p, cur, best, dir);
     r[0] = b.r[0]; r[1] = b.r[1]; r[2] = b.r[2]; r[3] = b.r[3];
-    return;
+    return false;
   }
   const float ext = rad + fabsf(ux) + fabsf(uy);
   const float m = 2.0f + ext * 2e-6f;
+  {
+    // the disc's own box against the block's extent in lattice units (a border cell extends to infinity:
+    // ds_cellx / ds_celly clamp)
+    const float big = 3.0e38f, dm = rad + m;
+    const float lx = blk.x0 == 0 ? -big : (float)((int64_t)blk.x0 << in.shift), hx = blk.x1 == in.gx - 1 ? big : (float)((((int64_t)blk.x1 + 1) << in.shift) - 1);
+    const float ly = blk.y0 == 0 ? -big : (float)((int64_t)blk.y0 << in.shift), hy = blk.y1 == in.gy - 1 ? big : (float)((((int64_t)blk.y1 + 1) << in.shift) - 1);
+    const float qx = (float)p.x + ux, qy = (float)p.y + uy;
+    if (qx - dm >= lx && qx + dm <= hx && qy - dm >= ly && qy + dm <= hy) return true;
+  }
   const float cx = (float)(cur.x - p.x), cy = (float)(cur.y - p.y);  // chord, exact
   const float tol = 4e-6f * (fabsf(cx) + fabsf(cy)) * ext + 4.0f;
   const float fdir = (float)dir;
@@ -349,6 +360,7 @@ DS_FN void ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir
   x0 = fmaxf((float)p.x + x0 - m, (float)in.bx0); y0 = fmaxf((float)p.y + y0 - m, (float)in.by0);
   x1 = fminf((float)p.x + x1 + m, (float)in.bx1); y1 = fminf((float)p.y + y1 + m, (float)in.by1);
   r[0] = (int64_t)floorf(x0); r[1] = (int64_t)floorf(y0); r[2] = (int64_t)ceilf(x1); r[3] = (int64_t)ceilf(y1);
+  return false;
 }
 
 // Bounding box of (half-plane on the sweep side of p->cur) clipped to the bounding box of all
@@ -492,8 +504,7 @@ DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, 
       continue;
     }
     if (!ds_block_all(in, blk)) {
-      ds_circle_region(in, pp, cur, bxy, dir, reg);
-      if (ds_block_cover(in, blk, reg[0], reg[1], reg[2], reg[3])) {
+      if (!ds_circle_region(in, pp, cur, bxy, dir, blk, reg) && ds_block_cover(in, blk, reg[0], reg[1], reg[2], reg[3])) {
         ds_block_rows<W>(in, blk, S);
         continue;
       }
