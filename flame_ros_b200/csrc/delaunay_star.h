@@ -158,7 +158,9 @@ struct DsW32 {
 #endif
 
 // ------------------------------------------------------------------------------------ cell blocks
-#define DS_CACHE 512  // candidates of a block held in the group's scratch (larger blocks are re-read)
+#ifndef DS_CACHE
+#define DS_CACHE 512  // candidates of a block held in the group's scratch (larger blocks are re-read, narrowed row by row)
+#endif
 #ifdef DS_STATS
 extern long long ds_stat_visits, ds_stat_passes, ds_stat_iters32;
 extern int ds_dbg_p;
@@ -212,10 +214,28 @@ DS_FN int ds_celly(const DsIn& in, int64_t y) {
   return c < 0 ? 0 : (c >= in.gy ? in.gy - 1 : (int)c);
 }
 
+// What a block that is too large for the cache is scanned FOR: the sweep side of the chord p->cur
+// (A (x - px) < B (y - py)) and, once a best candidate exists, the disc through (p, cur, best).  Such
+// blocks belong to hull vertices and slivers, whose regions are thin diagonal strips or caps inside a
+// large bounding rectangle: every cell row is narrowed to the part the region can reach.  Only
+// uncached blocks are narrowed -- they are dropped at the next sweep step, so no later step inherits
+// a block that was not scanned in full.
+struct DsClip {
+  int mode;            // 0: none, 1: half-plane, 2: half-plane and disc
+  float px, py, A, B;  // half-plane
+  float qx, qy, rr;    // disc centre (absolute lattice coordinates), radius incl. margin
+};
+DS_FN void ds_clip_halfplane(DsClip* c, DsPt p, DsPt cur, int dir) {
+  c->mode = 1;
+  c->px = (float)p.x; c->py = (float)p.y;
+  c->A = (float)(cur.y - p.y) * (float)dir;
+  c->B = (float)(cur.x - p.x) * (float)dir;
+  c->qx = c->qy = c->rr = 0.0f;
+}
 // Row table of a block: contiguous ranges of the cell-sorted arrays (cells are sorted row-major);
 // small blocks are copied into the scratch cache.
 template <class W>
-DS_FN void ds_block_rows(const DsIn& in, DsBlock& b, DsScratch* S) {
+DS_FN void ds_block_rows(const DsIn& in, DsBlock& b, DsScratch* S, const DsClip* clip = nullptr) {
   W::sync();
   if (b.x0 == 0 && b.x1 == in.gx - 1) {
     b.nrows = 1;
@@ -247,14 +267,53 @@ DS_FN void ds_block_rows(const DsIn& in, DsBlock& b, DsScratch* S) {
     }
     b.ncache = total;
     W::sync();
+  } else if (clip && clip->mode) {
+    // every cell row narrowed to what the region can reach in it (conservative: margins cover the fp32 roundings)
+    W::sync();
+    b.nrows = b.y1 - b.y0 + 1;
+    const float lim = 4194304.0f;  // 2^22: beyond every lattice coordinate
+    for (int r = W::lane(); r < b.nrows; r += W::LANES) {
+      const int Y = b.y0 + r;
+      // lattice extent of the row's cells; the first / last row hold everything below / above
+      const float ya = Y == 0 ? (float)in.by0 : (float)((int64_t)Y << in.shift);
+      const float yb = Y == in.gy - 1 ? (float)in.by1 : (float)((((int64_t)Y + 1) << in.shift) - 1);
+      float xlo = -lim, xhi = lim;
+      bool empty = false;
+      if (clip->A != 0.0f) {
+        const float t0 = clip->B * (ya - clip->py) / clip->A, t1 = clip->B * (yb - clip->py) / clip->A;
+        if (clip->A > 0.0f) {
+          const float t = fmaxf(t0, t1);
+          xhi = fminf(xhi, clip->px + t + 2.0f + 1e-6f * fabsf(t));
+        } else {
+          const float t = fminf(t0, t1);
+          xlo = fmaxf(xlo, clip->px + t - 2.0f - 1e-6f * fabsf(t));
+        }
+      }
+      if (clip->mode == 2) {
+        const float dy = clip->qy < ya ? ya - clip->qy : (clip->qy > yb ? clip->qy - yb : 0.0f);
+        if (dy > clip->rr + 2.0f) {
+          empty = true;
+        } else {
+          const float w = sqrtf(fmaxf(clip->rr * clip->rr - dy * dy, 0.0f) + 1e-6f * clip->rr * clip->rr) + 2.0f + 1e-6f * fabsf(clip->qx);
+          xlo = fmaxf(xlo, clip->qx - w);
+          xhi = fminf(xhi, clip->qx + w);
+        }
+      }
+      int beg = 0, cnt = 0;
+      if (!empty && xlo <= xhi) {
+        const int ca = ds_cellx(in, (int64_t)floorf(fmaxf(xlo, -lim))), cb = ds_cellx(in, (int64_t)ceilf(fminf(xhi, lim)));
+        const int xa = ca > b.x0 ? ca : b.x0, xb = cb < b.x1 ? cb : b.x1;
+        if (xa <= xb) {
+          beg = in.cell_start[Y * in.gx + xa];
+          cnt = in.cell_start[Y * in.gx + xb + 1] - beg;
+        }
+      }
+      S->rowbeg[r] = beg;
+      S->rowcnt[r] = cnt;
+    }
+    W::sync();
   }
 }
-
-// Grow the block toward the lattice rectangle [rx0,rx1]x[ry0,ry1], each side by at most the block's
-// current extent (the rectangle usually comes from a provisional circle -- the best candidate of a
-// block that is still too small -- and shrinks drastically once nearer candidates are seen, so
-// jumping to it would scan a large part of the image for nothing).  True when the block changed,
-// false when it already covers the rectangle.
 DS_FN bool ds_block_cover(const DsIn& in, DsBlock& b, int64_t rx0, int64_t ry0, int64_t rx1, int64_t ry1) {
   const int nx0 = ds_cellx(in, rx0), nx1 = ds_cellx(in, rx1), ny0 = ds_celly(in, ry0), ny1 = ds_celly(in, ry1);
   const int sx = b.x1 - b.x0 + 1, sy = b.y1 - b.y0 + 1;
@@ -320,7 +379,8 @@ DS_COLD DsBox ds_circle_region_f64(const DsIn& in, DsPt p, DsPt cur, DsPt best, 
 // candidates are looked at, so host and device may round differently here without consequence.
 // Returns true when the WHOLE disc already lies inside the block's cells (the common case for an
 // interior vertex: nothing to refine, nothing to grow); otherwise r receives the segment's box.
-DS_FN bool ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir, const DsBlock& blk, int64_t* r) {
+DS_FN bool ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir, const DsBlock& blk, int64_t* r, DsClip* clip) {
+  ds_clip_halfplane(clip, p, cur, dir);
   const DsPt a = dir > 0 ? cur : best, b = dir > 0 ? best : cur;  // (p, a, b) counter-clockwise
   const double ax = (double)(a.x - p.x), ay = (double)(a.y - p.y), bx = (double)(b.x - p.x), by = (double)(b.y - p.y);
   const double d = 2.0 * (ax * by - ay * bx);  // > 0, exact
@@ -344,6 +404,8 @@ DS_FN bool ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir
     const float qx = (float)p.x + ux, qy = (float)p.y + uy;
     if (qx - dm >= lx && qx + dm <= hx && qy - dm >= ly && qy + dm <= hy) return true;
   }
+  clip->mode = 2;
+  clip->qx = (float)p.x + ux; clip->qy = (float)p.y + uy; clip->rr = rad + m;
   const float cx = (float)(cur.x - p.x), cy = (float)(cur.y - p.y);  // chord, exact
   const float tol = 4e-6f * (fabsf(cx) + fabsf(cy)) * ext + 4.0f;
   const float fdir = (float)dir;
@@ -500,12 +562,15 @@ DS_FN int ds_next(const DsIn& in, int p, DsPt pp, int curid, DsPt cur, int dir, 
       if (!hb.ok) return -1;
       reg[0] = hb.r[0]; reg[1] = hb.r[1]; reg[2] = hb.r[2]; reg[3] = hb.r[3];
       if (!ds_block_cover(in, blk, reg[0], reg[1], reg[2], reg[3])) return -1;
-      ds_block_rows<W>(in, blk, S);
+      DsClip clip;
+      ds_clip_halfplane(&clip, pp, cur, dir);
+      ds_block_rows<W>(in, blk, S, &clip);
       continue;
     }
     if (!ds_block_all(in, blk)) {
-      if (!ds_circle_region(in, pp, cur, bxy, dir, blk, reg) && ds_block_cover(in, blk, reg[0], reg[1], reg[2], reg[3])) {
-        ds_block_rows<W>(in, blk, S);
+      DsClip clip;
+      if (!ds_circle_region(in, pp, cur, bxy, dir, blk, reg, &clip) && ds_block_cover(in, blk, reg[0], reg[1], reg[2], reg[3])) {
+        ds_block_rows<W>(in, blk, S, &clip);
         continue;
       }
     }
