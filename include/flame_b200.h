@@ -14,6 +14,11 @@
  * (the caller's, or one the context creates); calls return after enqueueing unless documented as
  * synchronising.  Host pointers are caller-owned and may be pageable (pinned is faster).
  *
+ * Threads and devices: a context belongs to the device it was created on; every entry point makes
+ * that device current for the CALLING host thread (and leaves it current), so a context may be driven
+ * from any thread -- one thread at a time per context; different contexts are independent (the
+ * reference runs one flame::Flame per camera thread).
+ *
  * Return values: 0 = OK, negative = error (FB_E_*); fb_last_error() returns a description.
  * There is NO CPU fallback: without a CUDA device fb_create() fails.
  */
