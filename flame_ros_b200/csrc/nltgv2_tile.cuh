@@ -50,8 +50,10 @@ struct TilePlan {
   size_t smem = 0;
 };
 
+#define FBT_HCAP 1024                      // halo records of a tile: one per out-edge whose target lives in another tile
+#define FBT_PCAP 1024                      // push list of a tile: one entry per such edge of the OTHER tiles
 static inline size_t fbt_smem_bytes() {
-  return sizeof(float4) * (FBT_VCAP + FBT_SLOTCAP) + sizeof(int) * (2 * (FBT_VCAP + 1) + 2 * FBT_VCAP) + 64;
+  return sizeof(float4) * (FBT_VCAP + FBT_SLOTCAP + FBT_HCAP) + sizeof(uint2) * FBT_PCAP + sizeof(int) * (2 * (FBT_VCAP + 1) + 2 * FBT_VCAP) + 64;
 }
 
 // ------------------------------------------------------------------------------------ k_tile_assign
@@ -205,6 +207,14 @@ __device__ __forceinline__ float4 fbt_ld_cluster(uint32_t a) {
 __device__ __forceinline__ void fbt_st_cluster(uint32_t a, float4 v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void fbt_st_cluster_v2(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint32_t fbt_atom_add_cluster(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
 // Exclusive scan over the block (one value per thread), uniform total.
 __device__ __forceinline__ int fbt_block_scan(int v, int* s_warp, int* total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -274,8 +284,13 @@ __device__ __forceinline__ void fbt_edge_of(const int* s_erow, int nOwn, int le,
 // with release / acquire semantics: two of them were 80 % of an iteration):
 //   A  "the contributions for my vertices are complete": remote edge threads deliver them with
 //      st.async ... mbarrier::complete_tx::bytes on MY barrier; I expect 16 B per remote incidence.
-//   B  "the extragradient points I read from other tiles are refreshed": every tile that owns such
-//      points arrives (release.cluster) on my barrier after its primal half-step.
+//   B  "the extragradient points I read from other tiles are refreshed": the OWNER pushes them.  In the
+//      prologue every out-edge with a target in another tile reserves a halo record in its own tile and
+//      registers (target vertex, record address) in the owner's push list through DSMEM; after its primal
+//      half-step the owner sends each listed point with st.async ... complete_tx on the reader's barrier
+//      (16 B per record expected).  The dual half-step then reads only LOCAL shared memory.  (The first
+//      version announced the refresh with a remote mbarrier arrive and the readers pulled the points with
+//      ld.shared::cluster: one more one-way latency plus a round trip in every iteration.)
 // Neither can run ahead by more than one phase: a tile's next dual half-step needs B from exactly the
 // tiles whose A it feeds.
 __global__ void __launch_bounds__(FBT_THREADS, 1)
@@ -283,14 +298,16 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
   extern __shared__ __align__(16) uint8_t fbt_smem[];
   float4* s_bar = reinterpret_cast<float4*>(fbt_smem);           // [VCAP] extragradient points of the own vertices
   float4* s_slot = s_bar + FBT_VCAP;                             // [SLOTCAP] K^T q contributions, CSR order per vertex
-  int* s_lrow = reinterpret_cast<int*>(s_slot + FBT_SLOTCAP);    // [VCAP+1] slot base
+  float4* s_halo = s_slot + FBT_SLOTCAP;                         // [HCAP] points of other tiles' vertices, pushed by their owners
+  uint2* s_plist = reinterpret_cast<uint2*>(s_halo + FBT_HCAP);  // [PCAP] {own vertex | reader tile << 16, reader's record address}
+  int* s_lrow = reinterpret_cast<int*>(s_plist + FBT_PCAP);      // [VCAP+1] slot base
   int* s_erow = s_lrow + FBT_VCAP + 1;                           // [VCAP+1] own-edge base
   int* s_first = s_erow + FBT_VCAP + 1;                          // [VCAP] first out-edge (global id)
   int* s_nin = s_first + FBT_VCAP;                               // [VCAP] in-degree
   __shared__ int s_warp[32];
   __shared__ __align__(8) uint64_t s_mbar[2];                    // A, B
   __shared__ int s_nrin;                                         // incidences filled by other tiles
-  __shared__ unsigned s_rmask, s_smask;                          // tiles that read my points / tiles whose points I read
+  __shared__ unsigned s_nhalo, s_npush;                          // halo records reserved here / push entries registered here
   const GraphView& g = a.g;
   const int tid = threadIdx.x;
   const int r = (int)fbc_cluster_ctarank();
@@ -306,7 +323,7 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
   const int base = toff[r], nOwn = toff[r + 1] - base;
   const int32_t* tl_ = a.tlist + vb + base;
   int32_t* g_lrow = a.lrow + vb;
-  if (tid == 0) { s_nrin = 0; s_rmask = 0u; s_smask = 0u; }
+  if (tid == 0) { s_nrin = 0; s_nhalo = 0u; s_npush = 0u; }
   __syncthreads();
 
   // ---- prologue 1: own vertices (state into registers, CSR bookkeeping into shared memory)
@@ -326,13 +343,12 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
       const int r0 = row[v], r1 = row[v + 1];
       vdeg[k] = r1 - r0;
       int nrem = 0;
-      unsigned mask = 0u;
       nin = g.vnin[vb + v];  // in-edges come first in the row (ascending edge id)
       for (int j = 0; j < nin; ++j) {  // independent loads: the tiles of the in-edges' sources
         const int ts = vtile[g.eij[eb + (inc[r0 + j] >> 1)].x];
-        if (ts != r) { ++nrem; mask |= 1u << ts; }
+        if (ts != r) ++nrem;
       }
-      if (nrem) { atomicAdd(&s_nrin, nrem); atomicOr(&s_rmask, mask); }
+      if (nrem) atomicAdd(&s_nrin, nrem);
       od = vdeg[k] - nin;
       first = od ? (inc[r0 + nin] >> 1) : 0;
       vx[k] = g.x[vb + v]; vw1[k] = g.w1[vb + v]; vw2[k] = g.w2[vb + v];
@@ -369,7 +385,8 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
   // ---- prologue 2: own edges = the contiguous out-edge ranges of the own vertices
   float q1[FBT_EPT], q2[FBT_EPT], q3[FBT_EPT], ea[FBT_EPT], ebt[FBT_EPT], dx[FBT_EPT], dy[FBT_EPT];
   uint32_t a_bj[FBT_EPT], a_sj[FBT_EPT], pk[FBT_EPT];  // pk: lv | own slot << 10 | target tile << 23 | remote << 27
-  const uint32_t bar_u32 = fbc_smem_u32(s_bar), slot_u32 = fbc_smem_u32(s_slot);
+  const uint32_t bar_u32 = fbc_smem_u32(s_bar), slot_u32 = fbc_smem_u32(s_slot), halo_u32 = fbc_smem_u32(s_halo);
+  const uint32_t plist_u32 = fbc_smem_u32(s_plist), npush_u32 = fbc_smem_u32(&s_npush);
   const uint32_t mbA = fbc_smem_u32(&s_mbar[0]), mbB = fbc_smem_u32(&s_mbar[1]);
   const int kmax = (nEdge + FBT_THREADS - 1) / FBT_THREADS;  // uniform over the CTA
   uint32_t evalid = 0u;
@@ -395,32 +412,56 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
       a_bj[k] = bar_u32 + 16u * (uint32_t)lj;
       a_sj[k] = slot_u32 + 16u * (uint32_t)(__ldcg(g_lrow + j) + pos);
       if (tj != r) {
-        a_bj[k] = fbc_mapa(a_bj[k], (uint32_t)tj);
         a_sj[k] = fbc_mapa(a_sj[k], (uint32_t)tj);
+        // the target's point is read from a halo record of THIS tile; its owner is told where to push it
+        const uint32_t h = atomicAdd(&s_nhalo, 1u);
+        a_bj[k] = halo_u32 + 16u * (h < FBT_HCAP ? h : 0u);
+        if (h < FBT_HCAP) {
+          const uint32_t idx = fbt_atom_add_cluster(fbc_mapa(npush_u32, (uint32_t)tj), 1u);
+          if (idx < FBT_PCAP) {
+            fbt_st_cluster_v2(fbc_mapa(plist_u32 + 8u * idx, (uint32_t)tj), (uint32_t)lj | ((uint32_t)r << 16), a_bj[k]);
+          } else {  // the owner's push list is full: capacity verdict, nothing is solved
+            atomicOr(a.derr, 1);
+            *reinterpret_cast<volatile int*>(a.err) = 1;
+          }
+        }
       }
       pk[k] = (uint32_t)lv | ((uint32_t)(s_lrow[lv] + s_nin[lv] + off) << 10) | ((uint32_t)tj << 23) | (tj != r ? 1u << 27 : 0u);
-      if (tj != r) atomicOr(&s_smask, 1u << tj);
     }
   }
   __syncthreads();
   const int nRin = s_nrin;
-  const unsigned rmask = s_rmask, smask = s_smask;
-  const bool hasA = nRin > 0, hasB = smask != 0u;
+  const uint32_t nHalo = s_nhalo;
+  const bool hasA = nRin > 0, hasB = nHalo > 0u;
   if (tid == 0) {
     fbc_mbar_init(mbA, 1);
-    fbc_mbar_init(mbB, hasB ? (uint32_t)__popc(smask) : 1u);
+    fbc_mbar_init(mbB, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (nHalo > FBT_HCAP) {  // capacity verdict of this tile's halo (the owners check their push lists below)
+      atomicOr(a.derr, 1);
+      *reinterpret_cast<volatile int*>(a.err) = 1;
+    }
+    if (hasB && nHalo <= FBT_HCAP) fbc_mbar_expect(mbB, 16u * nHalo);  // phase 0 of B: the initial points
   }
-  fbc_cluster_sync();  // every tile's s_bar is filled and its barriers exist before the first remote access
+  __threadfence();
+  fbc_cluster_sync();  // every tile's s_bar is filled, its barriers exist and its push list is complete
+  if (__ldcg(a.derr) != 0) return;  // uniform over the cluster: a halo or a push list did not fit
+  const uint32_t nPush = s_npush;
+  // initial halo: the owners push the points iteration 0 reads
+  for (uint32_t i = tid; i < nPush; i += FBT_THREADS) {
+    const uint2 e = s_plist[i];
+    fbc_st_async(fbc_mapa(e.y, e.x >> 16), s_bar[e.x & 0xffffu], fbc_mapa(mbB, e.x >> 16));
+  }
 
   for (int it = 0; it < iters; ++it) {
     if (hasA && tid == 0) fbc_mbar_expect(mbA, 16u * (uint32_t)nRin);  // phase `it` of A
+    if (hasB) fbc_mbar_wait(mbB, (uint32_t)(it & 1));                  // the halo of this iteration has landed
     // ---- dual half-step (nltgv2.cuh:k_dual_edges) + K^T q into the CSR slots of both endpoints
 #pragma unroll
     for (int k = 0; k < FBT_EPT; ++k)
       if (k < kmax && (evalid >> k) & 1u) {
         const float4 bik = fbc_lds(bar_u32 + ((pk[k] & 1023u) << 4));
-        const float4 bjk = (pk[k] >> 27) ? fbt_ld_cluster(a_bj[k]) : fbc_lds(a_bj[k]);
+        const float4 bjk = fbc_lds(a_bj[k]);  // own tile: s_bar; other tile: the halo record its owner refreshed
         float t = bik.x - bjk.x;
         t = fmaf(-dx[k], bik.y, t);
         t = fmaf(-dy[k], bik.z, t);
@@ -437,6 +478,8 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
         else fbc_sts(a_sj[k], ct);
       }
     __syncthreads();                                   // the contributions produced in this tile
+    // every thread is past this iteration's halo wait: the next phase of B may be armed
+    if (hasB && tid == 0 && it + 1 < iters) fbc_mbar_expect(mbB, 16u * nHalo);
     if (hasA) fbc_mbar_wait(mbA, (uint32_t)(it & 1));  // ... and those delivered by the other tiles
     // ---- primal half-step (nltgv2.cuh:k_primal_vertices): CSR-order sum, prox, box, extragradient
 #pragma unroll
@@ -463,9 +506,11 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
         if (it + 1 == iters) g.vbar[vb + vid[k]] = nb;
       }
     __syncthreads();  // the tile's points are refreshed, its slots are consumed
-    if (it + 1 < iters) {
-      if (tid < FBT_C && ((rmask >> tid) & 1u)) fbt_mbar_arrive_remote(fbc_mapa(mbB, (uint32_t)tid));
-      if (hasB) fbt_mbar_wait_cluster(mbB, (uint32_t)(it & 1));
+    if (it + 1 < iters) {  // hand the refreshed points to the tiles that read them
+      for (uint32_t i = tid; i < nPush; i += FBT_THREADS) {
+        const uint2 e = s_plist[i];
+        fbc_st_async(fbc_mapa(e.y, e.x >> 16), s_bar[e.x & 0xffffu], fbc_mapa(mbB, e.x >> 16));
+      }
     }
   }
 #pragma unroll
