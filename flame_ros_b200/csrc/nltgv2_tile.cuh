@@ -53,7 +53,7 @@ struct TilePlan {
 #define FBT_HCAP 1024                      // halo records of a tile: one per out-edge whose target lives in another tile
 #define FBT_PCAP 1024                      // push list of a tile: one entry per such edge of the OTHER tiles
 static inline size_t fbt_smem_bytes() {
-  return sizeof(float4) * (FBT_VCAP + FBT_SLOTCAP + FBT_HCAP) + sizeof(uint2) * FBT_PCAP + sizeof(int) * (2 * (FBT_VCAP + 1) + 2 * FBT_VCAP) + 64;
+  return sizeof(float4) * (FBT_VCAP + FBT_SLOTCAP + FBT_HCAP) + sizeof(uint2) * (FBT_PCAP + FBT_ECAP) + sizeof(int) * (2 * (FBT_VCAP + 1) + 2 * FBT_VCAP) + 64;
 }
 
 // ------------------------------------------------------------------------------------ k_tile_assign
@@ -300,7 +300,8 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
   float4* s_slot = s_bar + FBT_VCAP;                             // [SLOTCAP] K^T q contributions, CSR order per vertex
   float4* s_halo = s_slot + FBT_SLOTCAP;                         // [HCAP] points of other tiles' vertices, pushed by their owners
   uint2* s_plist = reinterpret_cast<uint2*>(s_halo + FBT_HCAP);  // [PCAP] {own vertex | reader tile << 16, reader's record address}
-  int* s_lrow = reinterpret_cast<int*>(s_plist + FBT_PCAP);      // [VCAP+1] slot base
+  uint2* s_perm = s_plist + FBT_PCAP;                            // [ECAP] edge slot -> {edge id, source vertex | offset << 10}
+  int* s_lrow = reinterpret_cast<int*>(s_perm + FBT_ECAP);       // [VCAP+1] slot base
   int* s_erow = s_lrow + FBT_VCAP + 1;                           // [VCAP+1] own-edge base
   int* s_first = s_erow + FBT_VCAP + 1;                          // [VCAP] first out-edge (global id)
   int* s_nin = s_first + FBT_VCAP;                               // [VCAP] in-degree
@@ -308,6 +309,7 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
   __shared__ __align__(8) uint64_t s_mbar[2];                    // A, B
   __shared__ int s_nrin;                                         // incidences filled by other tiles
   __shared__ unsigned s_nhalo, s_npush;                          // halo records reserved here / push entries registered here
+  __shared__ unsigned s_nrem, s_cloc, s_crem;                    // out-edges with a target in another tile; slot counters of the two classes
   const GraphView& g = a.g;
   const int tid = threadIdx.x;
   const int r = (int)fbc_cluster_ctarank();
@@ -323,7 +325,7 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
   const int base = toff[r], nOwn = toff[r + 1] - base;
   const int32_t* tl_ = a.tlist + vb + base;
   int32_t* g_lrow = a.lrow + vb;
-  if (tid == 0) { s_nrin = 0; s_nhalo = 0u; s_npush = 0u; }
+  if (tid == 0) { s_nrin = 0; s_nhalo = 0u; s_npush = 0u; s_nrem = 0u; s_cloc = 0u; s_crem = 0u; }
   __syncthreads();
 
   // ---- prologue 1: own vertices (state into registers, CSR bookkeeping into shared memory)
@@ -389,6 +391,48 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
   const uint32_t plist_u32 = fbc_smem_u32(s_plist), npush_u32 = fbc_smem_u32(&s_npush);
   const uint32_t mbA = fbc_smem_u32(&s_mbar[0]), mbB = fbc_smem_u32(&s_mbar[1]);
   const int kmax = (nEdge + FBT_THREADS - 1) / FBT_THREADS;  // uniform over the CTA
+  // Edge slots (thread tid, round k) are handed out by class: a thread's round 0 holds edges whose target
+  // is in this tile, the edges into OTHER tiles follow from slot min(512, #local) on, the remaining local
+  // edges last.  In the dual half-step the first round then needs no halo (it runs while the owners'
+  // pushes are still in flight), and the contributions to other tiles are sent before the last round is
+  // computed (they fly meanwhile).  Which local edge lands in which slot is decided by atomics; every
+  // edge's arithmetic and every slot address is independent of it.
+#pragma unroll 1
+  for (int le = tid; le < nEdge; le += FBT_THREADS) {
+    int lv, off;
+    fbt_edge_of(s_erow, nOwn, le, &lv, &off);
+    const int e = s_first[lv] + off;
+    const bool rem = vtile[g.eij[eb + e].y] != r;
+    s_perm[le] = make_uint2((uint32_t)e | (rem ? 0x80000000u : 0u), (uint32_t)lv | ((uint32_t)off << 10));  // natural order, class in bit 31
+    const unsigned m = __ballot_sync(__activemask(), rem);
+    if (rem && (m & ((1u << (tid & 31)) - 1u)) == 0u) atomicAdd(&s_nrem, (unsigned)__popc(m));
+  }
+  __syncthreads();
+  const int nRem = (int)s_nrem, nLoc = nEdge - nRem;
+  const int remBase = nLoc < FBT_THREADS ? nLoc : FBT_THREADS;  // first slot of the remote class
+  const int kB = remBase / FBT_THREADS;                         // the round in which the halo is first read
+  uint2 mine[FBT_EPT];
+#pragma unroll
+  for (int k = 0; k < FBT_EPT; ++k) {
+    const int le = tid + k * FBT_THREADS;
+    mine[k] = le < nEdge ? s_perm[le] : make_uint2(0u, 0u);
+  }
+  __syncthreads();  // the natural-order records are in registers: the table is rewritten in slot order
+#pragma unroll
+  for (int k = 0; k < FBT_EPT; ++k) {
+    const int le = tid + k * FBT_THREADS;
+    if (le < nEdge) {
+      int p;
+      if (mine[k].x & 0x80000000u) {
+        p = remBase + (int)atomicAdd(&s_crem, 1u);
+      } else {
+        const int i = (int)atomicAdd(&s_cloc, 1u);
+        p = i < remBase ? i : i + nRem;
+      }
+      s_perm[p] = make_uint2(mine[k].x & 0x7fffffffu, mine[k].y);
+    }
+  }
+  __syncthreads();
   uint32_t evalid = 0u;
 #pragma unroll
   for (int k = 0; k < FBT_EPT; ++k) {
@@ -396,9 +440,8 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
     a_bj[k] = a_sj[k] = pk[k] = 0u;
     const int le = tid + k * FBT_THREADS;
     if (le < nEdge) {
-      int lv, off;
-      fbt_edge_of(s_erow, nOwn, le, &lv, &off);
-      const int e = s_first[lv] + off;
+      const uint2 pe = s_perm[le];
+      const int e = (int)pe.x, lv = (int)(pe.y & 1023u), off = (int)(pe.y >> 10);
       const int2 ij = g.eij[eb + e];
       const float4 c = g.ec[eb + e];
       const float4 q = g.q4[eb + e];
@@ -455,10 +498,10 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
 
   for (int it = 0; it < iters; ++it) {
     if (hasA && tid == 0) fbc_mbar_expect(mbA, 16u * (uint32_t)nRin);  // phase `it` of A
-    if (hasB) fbc_mbar_wait(mbB, (uint32_t)(it & 1));                  // the halo of this iteration has landed
     // ---- dual half-step (nltgv2.cuh:k_dual_edges) + K^T q into the CSR slots of both endpoints
 #pragma unroll
-    for (int k = 0; k < FBT_EPT; ++k)
+    for (int k = 0; k < FBT_EPT; ++k) {
+      if (hasB && k == kB) fbc_mbar_wait(mbB, (uint32_t)(it & 1));  // the halo of this iteration has landed (first round that reads it)
       if (k < kmax && (evalid >> k) & 1u) {
         const float4 bik = fbc_lds(bar_u32 + ((pk[k] & 1023u) << 4));
         const float4 bjk = fbc_lds(a_bj[k]);  // own tile: s_bar; other tile: the halo record its owner refreshed
@@ -477,6 +520,7 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
         if (pk[k] >> 27) fbc_st_async(a_sj[k], ct, fbc_mapa(mbA, (pk[k] >> 23) & 15u));
         else fbc_sts(a_sj[k], ct);
       }
+    }
     __syncthreads();                                   // the contributions produced in this tile
     // every thread is past this iteration's halo wait: the next phase of B may be armed
     if (hasB && tid == 0 && it + 1 < iters) fbc_mbar_expect(mbB, 16u * nHalo);
@@ -515,11 +559,7 @@ k_nltgv2_tile(TileArgs a, int iters, float sigma, float tau, float tl, float the
   }
 #pragma unroll
   for (int k = 0; k < FBT_EPT; ++k)
-    if ((evalid >> k) & 1u) {
-      int lv, off;
-      fbt_edge_of(s_erow, nOwn, tid + k * FBT_THREADS, &lv, &off);
-      g.q4[eb + s_first[lv] + off] = make_float4(q1[k], q2[k], q3[k], 0.f);
-    }
+    if ((evalid >> k) & 1u) g.q4[eb + s_perm[tid + k * FBT_THREADS].x] = make_float4(q1[k], q2[k], q3[k], 0.f);
 #pragma unroll
   for (int k = 0; k < FBT_VPT; ++k)
     if (vid[k] >= 0) {
