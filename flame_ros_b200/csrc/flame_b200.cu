@@ -28,6 +28,7 @@ static void tile_plan_free(fb_ctx* c);
 static void tile_plan_mark(fb_ctx* c, int s);
 static void tile_assign_early(fb_ctx* c, int s, cudaStream_t st);
 static bool fb_tile_failed(const fb_ctx* c);
+static void tile_clear_failure(fb_ctx* c, bool disable);
 
 // ------------------------------------------------------------------------------------ helpers
 
@@ -243,7 +244,10 @@ extern "C" int fb_sync(fb_ctx* c) {
   CHECK_CTX(c);
   FB_CUDA(c, cudaStreamSynchronize(c->stream));
   if (grid_watchdog_fired(c)) FB_FAIL(c, FB_E_STATE, "grid-resident solver: mailbox exchange timed out (watchdog)");
-  if (fb_tile_failed(c)) FB_FAIL(c, FB_E_STATE, "tile-resident solver: a tile exceeded its capacity (nothing was solved)");
+  if (fb_tile_failed(c)) {
+    tile_clear_failure(c, false);
+    FB_FAIL(c, FB_E_STATE, "tile-resident solver: a tile exceeded its capacity (nothing was solved)");
+  }
   return FB_OK;
 }
 
@@ -407,7 +411,10 @@ extern "C" int fb_graph_state_get(fb_ctx* c, int s, float* x, float* w, float* q
   if (xbar) FB_CUDA(c, cudaMemcpyAsync(vb4.data(), c->vbar + vb, sizeof(float4) * V, cudaMemcpyDeviceToHost, st));
   FB_CUDA(c, cudaStreamSynchronize(st));
   if (grid_watchdog_fired(c)) FB_FAIL(c, FB_E_STATE, "grid-resident solver: mailbox exchange timed out (watchdog)");
-  if (fb_tile_failed(c)) FB_FAIL(c, FB_E_STATE, "tile-resident solver: a tile exceeded its capacity (nothing was solved)");
+  if (fb_tile_failed(c)) {
+    tile_clear_failure(c, false);
+    FB_FAIL(c, FB_E_STATE, "tile-resident solver: a tile exceeded its capacity (nothing was solved)");
+  }
   if (w) for (int v = 0; v < V; ++v) { w[2 * v] = w1[v]; w[2 * v + 1] = w2[v]; }
   if (q) for (int e = 0; e < E; ++e) { q[3 * e] = q4[e].x; q[3 * e + 1] = q4[e].y; q[3 * e + 2] = q4[e].z; }
   if (xbar) for (int v = 0; v < V; ++v) { xbar[3 * v] = vb4[v].x; xbar[3 * v + 1] = vb4[v].y; xbar[3 * v + 2] = vb4[v].z; }
@@ -476,6 +483,18 @@ static void tile_plan_mark(fb_ctx* c, int s) {
   if (c->tplan && s < (int)c->tplan->dirty.size()) c->tplan->dirty[s] = 1;
 }
 static bool fb_tile_failed(const fb_ctx* c) { return c->tplan && c->tplan->err && *c->tplan->err != 0; }
+// A capacity verdict is reported ONCE (the launch that raised it solved nothing); the flags are then
+// cleared so the context stays usable.  disable: fb_update stops choosing this solver for the context
+// (its frames fall back to the plan-free / streaming kernels) and drops the captured frames that hold it.
+static void tile_clear_failure(fb_ctx* c, bool disable) {
+  if (!c->tplan) return;
+  if (c->tplan->err) *c->tplan->err = 0;
+  if (c->tplan->derr) cudaMemsetAsync(c->tplan->derr, 0, sizeof(int), c->stream);
+  if (disable) {
+    c->tplan->available = 0;
+    update_invalidate_graphs(c);
+  }
+}
 static bool tile_available(fb_ctx* c);
 // Allocates the plan and probes the launch configuration (cluster of 16, ~148 KB shared memory).
 static bool tile_available(fb_ctx* c) {

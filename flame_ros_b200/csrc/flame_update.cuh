@@ -757,7 +757,12 @@ static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const f
       if (rc) return rc;
     }
     FB_CUDA(c, cudaStreamSynchronize(st));
-    if (fb_coop_failed(c) || fb_tile_failed(c)) FB_FAIL(c, FB_E_STATE, "fb_update: resident solver rejected the graph size");
+    if (fb_tile_failed(c)) {
+      // this frame was not solved; the following ones use the next solver in line
+      tile_clear_failure(c, true);
+      FB_FAIL(c, FB_E_STATE, "fb_update: the tile-resident solver rejected this frame's graph (a tile exceeded its capacity); it is disabled for this context");
+    }
+    if (fb_coop_failed(c)) FB_FAIL(c, FB_E_STATE, "fb_update: resident solver rejected the graph size");
     const int err = h[DSG_ERR];
     c->hV[s] = h[DSG_NV];
     c->hE[s] = h[DSG_NE];

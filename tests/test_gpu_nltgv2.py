@@ -310,3 +310,41 @@ def test_device_planned_tile_solver_on_irregular_graphs(capi, oracle):
         assert ctx.last_solver_variant() == 5
         got = ctx.graph_state_get(0)
     assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
+
+
+@pytest.mark.timeout(120)
+def test_tile_solver_capacity_verdict_is_reported_once_and_recoverable(capi, oracle):
+    """A non-planar graph whose edges almost all cross tiles overflows the tile solver's halo / push lists
+    (1024 records per tile): the launch must solve nothing, the next synchronising call must report it
+    ONCE, and the context must stay usable -- the streaming kernels then solve the same graph to the
+    oracle's bits, and variant 5 still serves a graph that fits."""
+    rng = np.random.default_rng(11)
+    V, E = 8000, 24000
+    pos = rng.uniform(4, [636, 476], (V, 2)).astype(np.float32)
+    i = rng.integers(0, V, 3 * E)
+    j = rng.integers(0, V, 3 * E)
+    keep = i < j
+    edges = np.unique(np.stack([i[keep], j[keep]], 1), axis=0)[:E].astype(np.int32)
+    d = pos[edges[:, 0]] - pos[edges[:, 1]]
+    alpha = (1.0 / np.maximum(np.hypot(d[:, 0], d[:, 1]), 1.0)).astype(np.float32)
+    beta = np.ones(len(edges), np.float32)
+    z = (0.5 + 0.2 * pos[:, 0] / 640 + rng.laplace(0, 0.02, V)).astype(np.float32)
+    g = dict(pos=pos, edges=edges, alpha=alpha, beta=beta, z=z, wt=np.ones(V, np.float32))
+    ref = run_oracle(oracle, g, 8)
+    with capi.Context(1, 640, 480, 2, 16, V, len(edges)) as ctx:
+        gpu_load_graph(ctx, 0, g)
+        ctx.nltgv2_solve(8, variant=5)
+        with pytest.raises(capi.FlameError, match="exceeded its capacity"):
+            ctx.graph_state_get(0)
+        untouched = ctx.graph_state_get(0)          # reported once; nothing was solved
+        assert np.array_equal(untouched["x"], g["z"])
+        ctx.nltgv2_solve(8, variant=1)
+        got = ctx.graph_state_get(0)
+        assert all(np.array_equal(ref[k], got[k]) for k in STATE_KEYS)
+        g2 = synth.s_graph("C2")
+        ref2 = run_oracle(oracle, g2, 6)
+        gpu_load_graph(ctx, 0, g2)
+        ctx.nltgv2_solve(6, variant=5)
+        got2 = ctx.graph_state_get(0)
+        assert ctx.last_solver_variant() == 5
+    assert all(np.array_equal(ref2[k], got2[k]) for k in STATE_KEYS)
