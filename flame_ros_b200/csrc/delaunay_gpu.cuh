@@ -456,6 +456,9 @@ k_ds_stars(DelGpu d, int s, int maxV) {
       if (in.sid[k] == ~p) dup = true;
     dup = DsW32::any(dup);
   }
+#ifdef DSG_CLOCKS
+  const long long clk0_ = clock64();
+#endif
   if (!dup) {
     const int rc = ds_star<DsW32>(in, p, &s_scr[g], star, &deg, &closed);
     if (rc) {
@@ -465,6 +468,9 @@ k_ds_stars(DelGpu d, int s, int maxV) {
     DsW32::sync();
     if (lane == 0) ds_counts(p, star, deg, closed, &od, &tc);
   }
+#ifdef DSG_CLOCKS
+  if (lane == 0 && clock64() - clk0_ > 40000) printf("star item %d vertex %d: %lld cycles, degree %d, closed %d\n", item, p, clock64() - clk0_, deg, closed);
+#endif
   if (lane == 0) {
     d.deg[vb + p] = deg | (closed << 8);
     d.od[vb + p] = od;
