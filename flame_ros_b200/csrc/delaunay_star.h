@@ -399,8 +399,9 @@ DS_FN bool ds_circle_region(const DsIn& in, DsPt p, DsPt cur, DsPt best, int dir
     // the disc's own box against the block's extent in lattice units (a border cell extends to infinity:
     // ds_cellx / ds_celly clamp)
     const float big = 3.0e38f, dm = rad + m;
-    const float lx = blk.x0 == 0 ? -big : (float)((int64_t)blk.x0 << in.shift), hx = blk.x1 == in.gx - 1 ? big : (float)((((int64_t)blk.x1 + 1) << in.shift) - 1);
-    const float ly = blk.y0 == 0 ? -big : (float)((int64_t)blk.y0 << in.shift), hy = blk.y1 == in.gy - 1 ? big : (float)((((int64_t)blk.y1 + 1) << in.shift) - 1);
+    // (cell index << shift stays below 2^22: 32-bit arithmetic, exact in fp32)
+    const float lx = blk.x0 == 0 ? -big : (float)(blk.x0 << in.shift), hx = blk.x1 == in.gx - 1 ? big : (float)(((blk.x1 + 1) << in.shift) - 1);
+    const float ly = blk.y0 == 0 ? -big : (float)(blk.y0 << in.shift), hy = blk.y1 == in.gy - 1 ? big : (float)(((blk.y1 + 1) << in.shift) - 1);
     const float qx = (float)p.x + ux, qy = (float)p.y + uy;
     if (qx - dm >= lx && qx + dm <= hx && qy - dm >= ly && qy + dm <= hy) return true;
   }
