@@ -630,13 +630,11 @@ static int update_frame_enqueue(fb_ctx* c, int s, bool captured) {
   UpdateState* U = c->upd;
   UpdateStream& S = U->st[s];
   const fb_update_params& p = U->up;
-  const int cur = c->n_slots - 1;
-  const size_t npx = (size_t)c->W * c->H;
   cudaStream_t st = c->stream;
   int32_t* misc = U->misc + 4 * s;
   int rc;
-  if (captured)
-    FB_CUDA(c, cudaMemcpyAsync(c->imgs + ((size_t)s * c->n_slots + cur) * npx, U->h_img + (size_t)s * npx, npx, cudaMemcpyHostToDevice, st));
+  // (the frame itself is uploaded by the caller in front of the graph launch: its source is the caller's
+  // buffer when that is pinned, so it cannot be a node with a fixed address)
   rc = update_idepths_enqueue(c, s, captured);
   if (rc) return rc;
   {
@@ -730,8 +728,20 @@ static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const f
         // the capture advanced the build counter and marked the plans; undo the double count
         S.builds--;
       }
-      // inputs of the graph: the frame and the poses in their pinned staging buffers
-      memcpy(U->h_img + (size_t)s * npx, gray, npx);
+      // inputs of the graph: the frame, uploaded in front of it -- straight from the caller's buffer when
+      // that is pinned / registered memory (a capture driver's ring), through the staging buffer otherwise
+      // (copying 300 kB on the host costs ~15 us during which the GPU has nothing to do) -- and the poses
+      // in their pinned staging record
+      {
+        const uint8_t* src = gray;
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, gray) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+          cudaGetLastError();
+          memcpy(U->h_img + (size_t)s * npx, gray, npx);
+          src = U->h_img + (size_t)s * npx;
+        }
+        FB_CUDA(c, cudaMemcpyAsync(c->imgs + ((size_t)s * c->n_slots + cur) * npx, src, npx, cudaMemcpyHostToDevice, st));
+      }
       float* hg = U->h_geo + (size_t)s * ((size_t)c->n_slots * 7 + 1);
       memcpy(hg, &c->h_pose[(size_t)s * c->n_slots * 7], sizeof(float) * c->n_slots * 7);
       const int32_t cur32 = cur;

@@ -244,3 +244,35 @@ def test_unimplemented_options_are_rejected_not_ignored(capi):
         up.min_height, up.max_height = 2.0, 1.0
         with pytest.raises(capi.FlameError):
             ctx.set_update_params(up)
+
+
+def test_pinned_and_pageable_frames_give_the_same_bits(capi):
+    """fb_update uploads the frame straight from the caller's buffer when that is pinned (a capture driver's
+    ring) and through its own staging buffer otherwise: same results, frame by frame, also across the switch
+    from ordinary launches to the replayed frame graph."""
+    W, H = 320, 240
+    K = (synth.K_VGA * np.array([[0.5], [0.5], [1.0]], np.float32)).astype(np.float32)
+    up = capi.default_update_params()
+    up.iters, up.idepth_var_max_graph = 12, 0.05
+    n = 14
+    frames, poses = _stream(W, H, K, n, seed=3, step=0.02)
+    pinned = capi.PinnedBuffer((n, H, W), np.uint8)
+    for k in range(n):
+        np.copyto(pinned.array[k], frames[k][0])
+    outs = []
+    for src in ("pageable", "pinned"):
+        per_frame = []
+        with capi.Context(1, W, H, 4, 1024, 1024, 3072) as ctx:
+            ctx.set_intrinsics(0, K)
+            ctx.set_update_params(up)
+            for k in range(n):
+                img = frames[k][0] if src == "pageable" else pinned.array[k]
+                ok = ctx.update(0, k / 30.0, k, poses[k], img, k % 3 == 0)
+                per_frame.append((ok, ctx.get_mesh(0)["idepth"].copy() if ok else None))
+        outs.append(per_frame)
+    pinned.free()
+    assert sum(1 for ok, _ in outs[0] if ok) >= 8
+    for (ok_a, x_a), (ok_b, x_b) in zip(*outs):
+        assert ok_a == ok_b
+        if ok_a:
+            assert np.array_equal(x_a, x_b)
