@@ -421,7 +421,11 @@ k_ds_prepare(DsgSelect q, DelGpu d, int s, int32_t* vfeat, float2* vpos, int32_t
 
 // ------------------------------------------------------------------------------------ k_ds_stars
 #define DSG_WARPS 4  // vertices per CTA: one warp each (the candidate cache takes ~7 KB per warp)
-__global__ void __launch_bounds__(DSG_WARPS * 32, 4)
+#ifndef DSG_STARS_MINB
+#define DSG_STARS_MINB 5  // resident CTAs per SM (96 registers per thread, ~50 B of spills): same single-camera frame time as 4
+                           // (128 registers), +6 % with eight cameras sharing the GPU (scripts/gpu_ab_stars_occ.sh)
+#endif
+__global__ void __launch_bounds__(DSG_WARPS * 32, DSG_STARS_MINB)
 k_ds_stars(DelGpu d, int s, int maxV) {
   __shared__ DsScratch s_scr[DSG_WARPS];
   int32_t* meta = d.meta + (size_t)s * DSG_META;
@@ -485,7 +489,7 @@ static inline int dsg_stars_grid(int device, int maxV) {
   int& n = sms[device & 63];
   if (n == 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { cudaGetLastError(); n = 148; }
   const int need = (maxV + DSG_WARPS - 1) / DSG_WARPS;
-  return need < 4 * n ? need : 4 * n;
+  return need < DSG_STARS_MINB * n ? need : DSG_STARS_MINB * n;
 }
 
 // ------------------------------------------------------------------------------------ k_ds_scan

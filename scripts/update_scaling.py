@@ -15,8 +15,11 @@ K = 36
 n_frames = WL.UPD_WARMUP + K
 datas = WL.update_streams("C2", [1000 + s for s in range(8)], n_frames)
 out = {}
-for mode in ("full", "no_map"):
-    for S in (1, 2, 4, 8):
+import os
+MODES = os.environ.get("UPD_SCALING_MODES", "full,no_map").split(",")
+STREAMS = [int(x) for x in os.environ.get("UPD_SCALING_S", "1,2,4,8").split(",")]
+for mode in MODES:
+    for S in STREAMS:
         run = B.UpdateRun(capi, datas[:S], 0)
         if mode == "no_map":
             for c in run.ctxs:
