@@ -276,3 +276,40 @@ def test_pinned_and_pageable_frames_give_the_same_bits(capi):
         assert ok_a == ok_b
         if ok_a:
             assert np.array_equal(x_a, x_b)
+
+
+def test_long_horizon_stream_stays_bit_identical_to_the_oracle_pipeline(capi, oracle):
+    """120 frames of one stream (40 poseframes: the ring of 7 evicts, features die and are re-detected, the
+    topology changes every frame, the frame graph is replayed from frame ~5 on): every frame's mesh
+    (triangles, edges) and vertex inverse depths must equal the C oracle pipeline's, and at the end the
+    dense map must still describe the scene."""
+    W, H = 320, 240
+    K = (synth.K_VGA * np.array([[0.5], [0.5], [1.0]], np.float32)).astype(np.float32)
+    sc = synth.Scene(5, tex_size=1024)
+    n = 120
+    poses = synth.stream_poses(n, step=0.01)
+    up = capi.default_update_params()
+    up.detection_win_size, up.iters, up.idepth_var_max_graph = 12, 15, 0.05
+    n_upd, worst, truth = 0, 0.0, None
+    with capi.Context(1, W, H, 8, 4096, 4096, 12288) as ctx, \
+            oracle.Pipeline(W, H, K, 8, 4096, 4096, oracle.UpdateParams.like(up)) as pipe:
+        ctx.set_intrinsics(0, K)
+        ctx.set_update_params(up)
+        for k in range(n):
+            img, truth = sc.render(K, poses[k], W, H)
+            is_pf = k % 3 == 0
+            got = ctx.update(0, k / 30.0, k, poses[k], img, is_pf)
+            ref = pipe.update(k, poses[k], img, is_pf)
+            assert got == ref, "frame %d: update() disagrees with the oracle pipeline" % k
+            if not got:
+                continue
+            n_upd += 1
+            if k % 4 == 0 or k > n - 4:   # the getters synchronise: not every frame
+                mesh, m = ctx.get_mesh(0), pipe.mesh()
+                assert np.array_equal(mesh["tris"], m["tris"]) and np.array_equal(mesh["edges"], m["edges"]), "mesh differs (frame %d)" % k
+                worst = max(worst, float(np.max(np.abs(mesh["idepth"] - m["idepth"]))))
+        assert n_upd >= n - 8 and worst < TOL, (n_upd, worst)
+        dm = ctx.get_idepthmap(0)
+        cov = ~np.isnan(dm)
+        assert cov.mean() > 0.5
+        assert np.median(np.abs(dm[cov] - truth[cov])) < 0.05
