@@ -421,10 +421,18 @@ class Context:
 
     def interpolate(self, stream, filter_params=None):
         out = np.zeros((self.H, self.W), np.float32)
-        valid = np.zeros(max(self._nT[stream], 1), np.uint8)
+        # sized for the context's triangle capacity (2 * max_vertices): after fb_update the triangle count lives
+        # in the library, not in this mirror
+        valid = np.zeros(2 * self.max_vertices, np.uint8)
         fp = C.byref(filter_params) if filter_params is not None else None
         self._ck(self._lib.fb_interpolate(self._h, stream, fp, _ptr(out), _ptr(valid)))
-        return out, valid[:self._nT[stream]]
+        nt = self._nT[stream]
+        if nt == 0:
+            try:
+                nt = int(self.get_stat(stream, "num_tris"))
+            except Exception:
+                nt = 0
+        return out, valid[:nt]
 
     # ------------------------------------------------------------------ flame::Flame::update + getters
     def set_update_params(self, p):

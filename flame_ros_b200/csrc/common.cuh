@@ -139,6 +139,10 @@ struct fb_ctx {
   int coop_cluster = -1;           // cluster size: -1 not probed, 0 unavailable
   int coop_ept = 0, coop_vpt = 0;  // edges / vertices per thread of the instantiation in use
   float* idmap_scratch = nullptr;  // [H*W] filtered maps of getter calls (never the prediction source)
+  // fb_update renders the filtered map the getters last asked for beside the unfiltered one (flame_update.cuh)
+  float* idmap_f = nullptr;        // [S*H*W]
+  int32_t* owner2 = nullptr;       // [S*H*W] second ownership map, kept clean by the shading kernel
+  uint64_t mut_epoch = 0;          // counts the entry points that may change what a getter returns
   int last_variant = 0;
   int last_cluster = 0;  // cluster size of the last variant-2 launch / parts per stream of variant 3
   bool grid_disabled = false;  // variant 3 launch refused once by the device: auto stops trying it

@@ -68,6 +68,13 @@ static inline void bind_device(const fb_ctx* c) {
 #define CHECK_CTX(c)           \
   if (!(c)) return FB_E_ARG;   \
   bind_device(c);              \
+  ++(c)->mut_epoch;            \
+  pipeline_drain(c)
+// read-only entry points (getters): they leave the epoch alone, so the filtered map fb_update rendered
+// stays current across them
+#define CHECK_CTX_RO(c)        \
+  if (!(c)) return FB_E_ARG;   \
+  bind_device(c);              \
   pipeline_drain(c)
 #define CHECK_STREAM(c, s) \
   if ((s) < 0 || (s) >= (c)->S) FB_FAIL(c, FB_E_ARG, "stream index out of range")
@@ -121,6 +128,7 @@ static void free_all(fb_ctx* c) {
   for (cudaGraphExec_t e : c->solve_exec) if (e) cudaGraphExecDestroy(e);
   cudaFree(c->coop_contrib); cudaFree(c->idmap_scratch); cudaFree(c->incoming);
   cudaFree(c->x_stage[0]); cudaFree(c->x_stage[1]);
+  cudaFree(c->idmap_f); cudaFree(c->owner2);
   if (c->coop_err) cudaFreeHost(c->coop_err);
   for (int k = 0; k < FB_PROF_NUM; ++k)
     for (cudaEvent_t e : c->sec[k].ev) cudaEventDestroy(e);
@@ -241,7 +249,7 @@ extern "C" void fb_destroy(fb_ctx* c) {
 }
 
 extern "C" int fb_sync(fb_ctx* c) {
-  CHECK_CTX(c);
+  CHECK_CTX_RO(c);
   FB_CUDA(c, cudaStreamSynchronize(c->stream));
   if (grid_watchdog_fired(c)) FB_FAIL(c, FB_E_STATE, "grid-resident solver: mailbox exchange timed out (watchdog)");
   if (fb_tile_failed(c)) {
@@ -754,7 +762,7 @@ extern "C" int fb_last_cluster_size(const fb_ctx* c) { return c ? c->last_cluste
 extern "C" int fb_last_solver_transport(const fb_ctx* c) { return c ? c->last_transport : 0; }
 
 extern "C" int fb_costs(fb_ctx* c, int s, float data_factor, double* smooth, double* data) {
-  CHECK_CTX(c);
+  CHECK_CTX_RO(c);
   CHECK_STREAM(c, s);
   FB_CUDA(c, cudaMemsetAsync(c->costs, 0, sizeof(double) * 2 * c->S, c->stream));
   const dim3 grid(std::max(1, std::min(64, fb_div_up(std::max(c->maxE, c->maxV), 256))), c->S);
@@ -1561,7 +1569,7 @@ extern "C" int fb_get_mesh_sizes(fb_ctx* c, int s, int32_t* V, int32_t* T, int32
 extern "C" int fb_get_mesh(fb_ctx* c, int s, const fb_tri_filter_params* filter, float* vtx_xy,
                            float* idepth, float* normals, int32_t* tris, uint8_t* tri_valid,
                            int32_t* edges) {
-  CHECK_CTX(c);
+  CHECK_CTX_RO(c);
   CHECK_STREAM(c, s);
   if (!c->upd || !c->upd->st[s].have_graph) FB_FAIL(c, FB_E_STATE, "fb_get_mesh: no mesh yet");
   UpdateStream& S = c->upd->st[s];
@@ -1611,7 +1619,7 @@ extern "C" int fb_get_mesh(fb_ctx* c, int s, const fb_tri_filter_params* filter,
 }
 
 extern "C" int fb_get_idepthmap(fb_ctx* c, int s, const fb_tri_filter_params* filter, float* out) {
-  CHECK_CTX(c);
+  CHECK_CTX_RO(c);
   CHECK_STREAM(c, s);
   if (!out) FB_FAIL(c, FB_E_ARG, "fb_get_idepthmap: null output");
   if (!c->upd || !c->upd->st[s].have_graph) {
@@ -1619,17 +1627,40 @@ extern "C" int fb_get_idepthmap(fb_ctx* c, int s, const fb_tri_filter_params* fi
     std::fill(out, out + (size_t)c->W * c->H, qnan);
     return FB_OK;
   }
+  const size_t npx = (size_t)c->W * c->H;
   if (!filter) {  // rendered by the last fb_update; no need to rasterise again
-    const size_t npx = (size_t)c->W * c->H;
     FB_CUDA(c, cudaMemcpyAsync(out, c->idmap + (size_t)s * npx, sizeof(float) * npx, cudaMemcpyDeviceToHost, c->stream));
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
     return FB_OK;
   }
-  return fb_interpolate(c, s, filter, out, nullptr);
+  UpdateStream& S = c->upd->st[s];
+  const bool same = S.spec_on && memcmp(&S.spec_filter, filter, sizeof(*filter)) == 0;
+  if (same && S.spec_epoch == c->mut_epoch && c->idmap_f) {
+    // the last fb_update rendered exactly this map beside the unfiltered one, and nothing has touched the
+    // context since (read-only getters aside)
+    FB_CUDA(c, cudaMemcpyAsync(out, c->idmap_f + (size_t)s * npx, sizeof(float) * npx, cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    S.stats["filtered_maps_reused"] += 1.0;
+    return FB_OK;
+  }
+  const int rc = fb_interpolate(c, s, filter, out, nullptr);
+  if (rc == FB_OK && !same && !getenv("FB_NO_SPEC_MAP")) {
+    // remember the filter: from the next frame on fb_update renders this map in its own raster pass
+    if (!c->idmap_f) {
+      FB_CUDA(c, dalloc(&c->idmap_f, (size_t)c->S * npx));
+      FB_CUDA(c, dalloc(&c->owner2, (size_t)c->S * npx));
+      FB_CUDA(c, cudaMemsetAsync(c->owner2, 0x7f, sizeof(int32_t) * (size_t)c->S * npx, c->stream));
+    }
+    S.spec_on = true;
+    S.spec_filter = *filter;
+    S.spec_epoch = ~0ull;
+    update_invalidate_graphs(c);  // the captured frames do not hold the second map yet
+  }
+  return rc;
 }
 
 extern "C" int fb_get_raw_idepths(fb_ctx* c, int s, int32_t* N, float* xy, float* mu, float* var) {
-  CHECK_CTX(c);
+  CHECK_CTX_RO(c);
   CHECK_STREAM(c, s);
   if (!N) FB_FAIL(c, FB_E_ARG, "fb_get_raw_idepths: null count");
   *N = 0;
@@ -1658,7 +1689,7 @@ extern "C" int fb_get_raw_idepths(fb_ctx* c, int s, int32_t* N, float* xy, float
 }
 
 extern "C" int fb_get_stat(fb_ctx* c, int s, const char* key, double* value) {
-  CHECK_CTX(c);
+  CHECK_CTX_RO(c);
   CHECK_STREAM(c, s);
   if (!key || !value || !c->upd) FB_FAIL(c, FB_E_ARG, "fb_get_stat: bad argument");
   auto& m = c->upd->st[s].stats;

@@ -42,6 +42,11 @@ struct UpdateStream {
   // launches serialise on the driver's context lock; replayed as a graph a frame is ONE launch.
   cudaGraphExec_t frame_graph[2] = {nullptr, nullptr};
   int64_t graph_launches[2] = {0, 0};
+  // the display filter of the last getFilteredInverseDepthMap call: once known, every update renders that map too
+  // (one claim + one shading pass for both maps instead of a second rasterisation per getter call)
+  bool spec_on = false;
+  fb_tri_filter_params spec_filter{};
+  uint64_t spec_epoch = ~0ull;     // c->mut_epoch right after the update that rendered idmap_f
   // stats of the last update (names follow msg/FlameStats.msg)
   std::unordered_map<std::string, double> stats;
 };
@@ -388,15 +393,29 @@ static int update_interpolate(fb_ctx* c, int s, const int32_t* Tdev, int32_t* co
   int32_t* owner = c->owner + (size_t)s * npx;
   const int32_t* tri = c->tri + (size_t)s * c->maxT * 3;
   cudaStream_t st = c->stream;
+  const UpdateStream& S = c->upd->st[s];
+  const bool spec = S.spec_on && c->owner2 && c->idmap_f;
+  uint8_t* valid = c->tri_valid + (size_t)s * c->maxT;
+  int32_t* owner2 = spec ? c->owner2 + (size_t)s * npx : nullptr;
+  float* map2 = spec ? c->idmap_f + (size_t)s * npx : nullptr;
   ProfScope ps(c, FB_PROF_INTERP);
   FB_CUDA(c, cudaMemsetAsync(owner, 0x7f, sizeof(int32_t) * npx, st));
   if (covered) FB_CUDA(c, cudaMemsetAsync(covered, 0, sizeof(int32_t), st));
-  if (T) {  // unfiltered: every triangle is valid, no validity pass
-    k_raster_claim<<<fb_div_up(T * 32, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, T, tri, nullptr, owner, Tdev);
+  if (T) {  // unfiltered: every triangle is valid, no validity pass; the filtered map rides along when asked for
+    if (spec) {
+      const float cos_thresh = (float)cos((double)S.spec_filter.oblique_normal_thresh);
+      k_tri_validity<<<fb_div_up(T, 256), 256, 0, st>>>(c->W, c->d_K + 9 * s, c->vpos + vb, c->x + vb, T, tri, S.spec_filter, cos_thresh, 1, valid, Tdev);
+      c->launches += 1;
+    }
+    k_raster_claim<<<fb_div_up(T * 32, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, T, tri, nullptr, owner, Tdev, spec ? valid : nullptr, owner2);
     c->launches += 1;
   }
   k_raster_shade<<<fb_div_up((int)npx, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, c->x + vb, tri, owner, c->idmap + (size_t)s * npx, Tdev, covered);
   c->launches++;
+  if (spec && T) {  // (one shading pass writing both maps was measured 3x slower than this second launch)
+    k_raster_shade<<<fb_div_up((int)npx, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, c->x + vb, tri, owner2, map2, Tdev, nullptr, 1);
+    c->launches++;
+  }
   FB_CUDA(c, cudaGetLastError());
   return FB_OK;
 }
@@ -784,6 +803,8 @@ static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const f
     }
     updated = h[DSG_NT] > 0 ? 1 : 0;
     if (updated) S.have_graph = true;
+    // the filtered map rendered beside the unfiltered one belongs to this state of the context
+    S.spec_epoch = (updated && S.spec_on && c->idmap_f) ? c->mut_epoch : ~0ull;
     S.stats["num_feats"] = h[DSG_META + 1];
     S.stats["num_vtx"] = h[DSG_NV];
     S.stats["num_edges"] = h[DSG_NE];
@@ -823,6 +844,7 @@ static int fb_update_impl(fb_ctx* c, int s, double /*time*/, int img_id, const f
     FB_CUDA(c, cudaMemcpyAsync(h + DSG_META, misc, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA(c, cudaStreamSynchronize(st));
     if (updated) S.stats["coverage"] = (double)h[DSG_META] / (double)npx;
+    S.spec_epoch = (updated && c->hT[s] > 0 && S.spec_on && c->idmap_f) ? c->mut_epoch : ~0ull;
     if (!S.stats.count("num_edges")) { S.stats["num_edges"] = 0.0; S.stats["num_tris"] = 0.0; }
   }
   // aliases of round 1 (kept for callers of fb_get_stat)

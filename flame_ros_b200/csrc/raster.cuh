@@ -87,11 +87,15 @@ k_tri_validity(int W, const float* __restrict__ K, const float2* __restrict__ vt
 __global__ void __launch_bounds__(256)
 k_raster_claim(int W, int H, const float2* __restrict__ vtx, int T,
                const int32_t* __restrict__ tri, const uint8_t* __restrict__ valid,
-               int32_t* __restrict__ owner, const int32_t* __restrict__ Tdev = nullptr) {
+               int32_t* __restrict__ owner, const int32_t* __restrict__ Tdev = nullptr,
+               const uint8_t* __restrict__ valid2 = nullptr, int32_t* __restrict__ owner2 = nullptr) {
+  // owner2 != NULL: a second ownership map over the triangles that pass `valid2` is claimed in the same
+  // pass (fb_update renders the filtered map of the next getter call beside the unfiltered one)
   const int lane = threadIdx.x & 31;
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (Tdev) T = *Tdev;
   if (t >= T || (valid && !valid[t])) return;  // valid == NULL: every triangle (unfiltered map)
+  const bool second = owner2 && valid2[t];
   const float2 A = vtx[tri[3 * t]], B = vtx[tri[3 * t + 1]], C = vtx[tri[3 * t + 2]];
   const float area = fb_edge_fn(A.x, A.y, B.x, B.y, C.x, C.y);
   if (area == 0.0f || !(area == area)) return;
@@ -108,30 +112,37 @@ k_raster_claim(int W, int H, const float2* __restrict__ vtx, int T,
     const float w0 = fb_edge_fn(B.x, B.y, C.x, C.y, px, py) * inv;
     const float w1 = fb_edge_fn(C.x, C.y, A.x, A.y, px, py) * inv;
     const float w2 = fb_edge_fn(A.x, A.y, B.x, B.y, px, py) * inv;
-    if (w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f) atomicMin(&owner[y * W + x], t);
+    if (w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f) {
+      atomicMin(&owner[y * W + x], t);
+      if (second) atomicMin(&owner2[y * W + x], t);
+    }
   }
+}
+
+__device__ __forceinline__ float fb_shade_one(int W, const float2* __restrict__ vtx, const float* __restrict__ idepth,
+                                              const int32_t* __restrict__ tri, int t, int i) {
+  const int a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
+  const float2 A = vtx[a], B = vtx[b], C = vtx[c];
+  const float inv = 1.0f / fb_edge_fn(A.x, A.y, B.x, B.y, C.x, C.y);
+  const float px = (float)(i % W), py = (float)(i / W);
+  const float w0 = fb_edge_fn(B.x, B.y, C.x, C.y, px, py) * inv;
+  const float w1 = fb_edge_fn(C.x, C.y, A.x, A.y, px, py) * inv;
+  const float w2 = fb_edge_fn(A.x, A.y, B.x, B.y, px, py) * inv;
+  return fmaf(w0, idepth[a], fmaf(w1, idepth[b], w2 * idepth[c]));
 }
 
 __global__ void __launch_bounds__(256)
 k_raster_shade(int W, int H, const float2* __restrict__ vtx, const float* __restrict__ idepth,
-               const int32_t* __restrict__ tri, const int32_t* __restrict__ owner,
+               const int32_t* __restrict__ tri, int32_t* __restrict__ owner,
                float* __restrict__ map, const int32_t* __restrict__ Tdev = nullptr,
-               int32_t* __restrict__ covered = nullptr) {
+               int32_t* __restrict__ covered = nullptr, int reset_owner = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (Tdev && *Tdev == 0) return;  // no mesh this frame: the previous map stays
   if (i >= W * H) return;
   const int t = owner[i];
+  if (reset_owner) owner[i] = FB_OWNER_NONE;  // the second ownership map is left clean for the next frame
   float out = __int_as_float(0x7fc00000);
-  if (t != FB_OWNER_NONE) {
-    const int a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
-    const float2 A = vtx[a], B = vtx[b], C = vtx[c];
-    const float inv = 1.0f / fb_edge_fn(A.x, A.y, B.x, B.y, C.x, C.y);
-    const float px = (float)(i % W), py = (float)(i / W);
-    const float w0 = fb_edge_fn(B.x, B.y, C.x, C.y, px, py) * inv;
-    const float w1 = fb_edge_fn(C.x, C.y, A.x, A.y, px, py) * inv;
-    const float w2 = fb_edge_fn(A.x, A.y, B.x, B.y, px, py) * inv;
-    out = fmaf(w0, idepth[a], fmaf(w1, idepth[b], w2 * idepth[c]));
-  }
+  if (t != FB_OWNER_NONE) out = fb_shade_one(W, vtx, idepth, tri, t, i);
   map[i] = out;
   if (covered) {  // `coverage` stat (/root/reference/src/utils.cc:122): pixels with a depth
     const unsigned m = __ballot_sync(__activemask(), out == out);

@@ -11,6 +11,7 @@ from flame_ros_b200 import capi, synth
 W, H, win = 640, 480, int(sys.argv[1]) if len(sys.argv) > 1 else 8
 tri = int(sys.argv[2]) if len(sys.argv) > 2 else 0   # 0 = device sync_graph + triangulate, 1 = host
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 50
+getter = len(sys.argv) > 4 and sys.argv[4] == "getter"   # also fetch the filtered dense map every frame
 n = 60
 sc = synth.Scene(0, tex_size=1024)
 poses = synth.stream_poses(n, step=0.01)
@@ -26,9 +27,13 @@ with capi.Context(1, W, H, 8, 8192, 8192, 24576) as ctx:
             "interpolate", "detection", "num_vertices"]
     acc = {k: [] for k in keys}
     wall = []
+    flt = capi.default_tri_filter_params()
+    hmap = capi.PinnedBuffer((H, W), np.float32)
     for k in range(n):
         t0 = time.perf_counter()
         ok = ctx.update(0, k / 30.0, k, poses[k], frames[k], k % 6 == 0)
+        if getter and ok:
+            ctx.get_idepthmap(0, flt, out=hmap.array)
         wall.append(time.perf_counter() - t0)
         for key in keys:
             try:

@@ -313,3 +313,43 @@ def test_long_horizon_stream_stays_bit_identical_to_the_oracle_pipeline(capi, or
         cov = ~np.isnan(dm)
         assert cov.mean() > 0.5
         assert np.median(np.abs(dm[cov] - truth[cov])) < 0.05
+
+
+@pytest.mark.parametrize("tri", [0, 1], ids=["device-graph", "host-graph"])
+def test_filtered_map_rendered_by_update_equals_the_getter_render(capi, tri):
+    """After the first getFilteredInverseDepthMap call fb_update renders that filtered map in its own raster
+    pass (one claim + one shading pass for both maps); the getter then only copies it.  It must be the map a
+    fresh render gives (fb_interpolate always renders), for every frame, also when the filter changes and
+    when other calls sit between update and getter."""
+    W, H = 320, 240
+    K = (synth.K_VGA * np.array([[0.5], [0.5], [1.0]], np.float32)).astype(np.float32)
+    up = capi.default_update_params()
+    up.iters, up.idepth_var_max_graph, up.triangulator = 12, 0.05, tri
+    n = 16
+    frames, poses = _stream(W, H, K, n, seed=4, step=0.02)
+    f1 = capi.default_tri_filter_params()
+    f2 = capi.default_tri_filter_params()
+    f2.edge_length_thresh = 0.05
+    f2.min_triangle_idepth = 0.2
+    checked = 0
+    with capi.Context(1, W, H, 4, 1024, 1024, 3072) as ctx:
+        ctx.set_intrinsics(0, K)
+        ctx.set_update_params(up)
+        for k in range(n):
+            ok = ctx.update(0, k / 30.0, k, poses[k], frames[k][0], k % 3 == 0)
+            if not ok:
+                continue
+            flt = f1 if k < 10 else f2                      # the filter changes at frame 10
+            if k % 4 == 1:
+                ctx.get_mesh(0)                             # a read-only call in between
+            if k % 5 == 2:
+                ctx.set_update_params(up)                   # a mutating call in between: the getter must render
+            got = ctx.get_idepthmap(0, flt)
+            ref = ctx.interpolate(0, flt)[0]
+            assert np.array_equal(np.isnan(got), np.isnan(ref)), "frame %d" % k
+            m = ~np.isnan(ref)
+            assert np.array_equal(got[m], ref[m]), "frame %d" % k
+            un = ctx.get_idepthmap(0)
+            assert np.all(~np.isnan(un[m]))                 # the filtered map is a subset of the unfiltered one
+            checked += 1
+    assert checked >= 10
