@@ -427,7 +427,7 @@ def gpu_main(args):
                "coverage": u["stats"].get("coverage"),
                "solver_variant": {1: "streaming", 4: "plan-free resident (cluster, L2 exchange)",
                                   5: "tile-resident, planned on the device (cluster of 16, DSMEM exchange)"}.get(u["stats"].get("variant"), u["stats"].get("variant")),
-               "call": "per frame and stream: fb_update(host gray image, pose, is_poseframe every 6th) = flame::Flame::update "
+               "call": "per frame and stream (loop in C, fb_update_run): fb_update(host gray image, pose, is_poseframe every 6th) = flame::Flame::update "
                        "(/root/reference/src/flame_nodelet.cc:634), then fb_get_idepthmap(filter) = getFilteredInverseDepthMap "
                        "(:682-683) into pinned host memory; one context + one host thread per stream; detection window 8 px "
                        "(~5.5k Delaunay vertices), 50 PD iterations per frame, topology rebuilt on the device every frame"}
@@ -570,15 +570,23 @@ class UpdateRun:
             self.h_frames.append(hf)
             self.h_map.append(capi.PinnedBuffer((d.H, d.W), np.float32))
         self.stats = [dict() for _ in datas]
+        self.poses = [np.ascontiguousarray(d.poses, np.float32) for d in datas]
 
     def _frames(self, s, k0, k1):
         ctx, d, hf, hm = self.ctxs[s], self.datas[s], self.h_frames[s].array, self.h_map[s].array
-        chk = 0.0
-        for k in range(k0, k1):
-            ok = ctx.update(0, k / 30.0, k, d.poses[k], hf[k], k % WL.UPD_POSEFRAME_EVERY == 0)
-            if ok:
-                ctx.get_idepthmap(0, self.filter, out=hm)
-                chk += float(hm[d.H // 2, d.W // 2] == hm[d.H // 2, d.W // 2])   # the consumer's read
+        # the per-camera loop (fb_update, then fb_get_idepthmap with the display filters, per frame) runs in C
+        # (fb_update_run), as a C++ frontend's camera thread would drive the library: with the loop in Python
+        # eight camera threads spend a tenth of their time queueing for the interpreter lock
+        if os.environ.get("FB_BENCH_PY_LOOP"):
+            chk = 0.0
+            for k in range(k0, k1):
+                ok = ctx.update(0, k / 30.0, k, d.poses[k], hf[k], k % WL.UPD_POSEFRAME_EVERY == 0)
+                if ok:
+                    ctx.get_idepthmap(0, self.filter, out=hm)
+                    chk += float(hm[d.H // 2, d.W // 2] == hm[d.H // 2, d.W // 2])   # the consumer's read
+        else:
+            chk = float(ctx.update_run(0, k0, k1, hf, self.poses[s], WL.UPD_POSEFRAME_EVERY, self.filter, hm))
+            chk += float(hm[d.H // 2, d.W // 2] == hm[d.H // 2, d.W // 2])
         self.stats[s] = dict(vertices=ctx.get_stat(0, "num_vtx"), tris=ctx.get_stat(0, "num_tris"),
                              coverage=ctx.get_stat(0, "coverage"), variant=ctx.last_solver_variant())
         return chk

@@ -28,7 +28,7 @@ SYMBOLS = [
     "fb_project_features", "fb_graph_bind_features", "fb_graph_data_from_features", "fb_mesh_set",
     "fb_interpolate", "fb_profile_enable", "fb_profile_reset", "fb_profile_get", "fb_launch_count",
     "fb_last_solver_variant", "fb_last_cluster_size", "fb_last_solver_transport", "fb_grid_plan_verify", "fb_delaunay", "fb_hotpath_step", "fb_results_wait", "fb_pipeline_join", "fb_default_update_params",
-    "fb_set_update_params", "fb_update", "fb_get_mesh_sizes", "fb_get_mesh", "fb_get_idepthmap",
+    "fb_set_update_params", "fb_update", "fb_update_run", "fb_get_mesh_sizes", "fb_get_mesh", "fb_get_idepthmap",
     "fb_get_raw_idepths", "fb_get_stat", "fb_update_poseframe_poses", "fb_prune_poseframes",
     "fb_frame_gradient", "fb_frame_pyr_down", "fb_detect", "fb_get_feature_pool", "fb_delaunay_device",
 ]
@@ -139,7 +139,7 @@ def load_library(build_if_missing=True):
         "fb_last_solver_variant": [P], "fb_last_cluster_size": [P], "fb_last_solver_transport": [P], "fb_grid_plan_verify": [I, I, P, P, I, I, P], "fb_version": [], "fb_delaunay": [I, P, P, P, P, P], "fb_hotpath_step": [P, P], "fb_results_wait": [P, I], "fb_pipeline_join": [P],
         "fb_set_update_params": [P, P], "fb_update": [P, I, C.c_double, I, P, P, I, I],
         "fb_get_mesh_sizes": [P, I, P, P, P], "fb_get_mesh": [P, I, P, P, P, P, P, P, P],
-        "fb_get_idepthmap": [P, I, P, P], "fb_get_raw_idepths": [P, I, P, P, P, P],
+        "fb_get_idepthmap": [P, I, P, P], "fb_update_run": [P, I, I, I, P, C.c_size_t, P, I, P, P], "fb_get_raw_idepths": [P, I, P, P, P, P],
         "fb_get_stat": [P, I, C.c_char_p, P], "fb_update_poseframe_poses": [P, I, I, P, P],
         "fb_prune_poseframes": [P, I, I, P], "fb_frame_gradient": [P, I, I, P],
         "fb_frame_pyr_down": [P, I, I, P], "fb_detect": [P, I, I, I, I, C.c_float, P, P, P, P],
@@ -492,6 +492,16 @@ class Context:
         var = np.zeros(self.max_features, np.float32)
         self._ck(self._lib.fb_get_raw_idepths(self._h, stream, C.byref(n), _ptr(xy), _ptr(mu), _ptr(var)))
         return xy[:n.value].copy(), mu[:n.value].copy(), var[:n.value].copy()
+
+    def update_run(self, stream, k0, k1, frames, poses, poseframe_every, filter_params, out_map):
+        """fb_update_run: frames [k0, k1) of a (n, H, W) uint8 array through update + filtered map, looped in C."""
+        assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"] and poses.dtype == np.float32 and poses.flags["C_CONTIGUOUS"]
+        fp = C.byref(filter_params) if filter_params is not None else None
+        n = self._lib.fb_update_run(self._h, stream, k0, k1, _ptr(frames), frames.shape[1] * frames.shape[2], _ptr(poses),
+                                    poseframe_every, fp, _ptr(out_map))
+        if n < 0:
+            self._ck(n)
+        return n
 
     def get_stat(self, stream, key):
         v = C.c_double(0)

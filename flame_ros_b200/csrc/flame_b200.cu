@@ -1659,6 +1659,23 @@ extern "C" int fb_get_idepthmap(fb_ctx* c, int s, const fb_tri_filter_params* fi
   return rc;
 }
 
+extern "C" int fb_update_run(fb_ctx* c, int s, int k0, int k1, const uint8_t* frames, size_t frame_stride,
+                             const float* poses, int poseframe_every, const fb_tri_filter_params* filter, float* out_map) {
+  if (!c) return FB_E_ARG;
+  if (!frames || !poses || !out_map || k1 < k0 || poseframe_every < 1) FB_FAIL(c, FB_E_ARG, "fb_update_run: bad argument");
+  int n = 0;
+  for (int k = k0; k < k1; ++k) {
+    int rc = fb_update(c, s, (double)k / 30.0, k, poses + 7 * (size_t)k, frames + (size_t)k * frame_stride, c->W, k % poseframe_every == 0);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      rc = fb_get_idepthmap(c, s, filter, out_map);
+      if (rc < 0) return rc;
+      ++n;
+    }
+  }
+  return n;
+}
+
 extern "C" int fb_get_raw_idepths(fb_ctx* c, int s, int32_t* N, float* xy, float* mu, float* var) {
   CHECK_CTX_RO(c);
   CHECK_STREAM(c, s);

@@ -25,6 +25,7 @@
 #ifndef FLAME_B200_H_
 #define FLAME_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -296,6 +297,14 @@ int fb_get_mesh(fb_ctx* ctx, int stream, const fb_tri_filter_params* filter, flo
 /* getInverseDepthMap / getFilteredInverseDepthMap (/root/reference/src/flame_nodelet.cc:682-688):
  * filter == NULL -> unfiltered. out[H*W], NaN = no depth. Synchronises. */
 int fb_get_idepthmap(fb_ctx* ctx, int stream, const fb_tri_filter_params* filter, float* out);
+/* A camera thread's loop in one call: for k in [k0, k1): fb_update(time = k / 30, img_id = k, poses + 7 k,
+ * frames + k * frame_stride, pitch = W, is_poseframe = (k % poseframe_every == 0)) and, when it returns 1,
+ * fb_get_idepthmap(filter, out_map) -- exactly what the nodelet does per image
+ * (/root/reference/src/flame_nodelet.cc:634,682-683), driven from C so that a host in another language
+ * (bench.py: Python, one thread per camera) does not pay interpreter time and lock contention per frame.
+ * Returns the number of frames that produced a map, or a negative error. */
+int fb_update_run(fb_ctx* ctx, int stream, int k0, int k1, const uint8_t* frames, size_t frame_stride,
+                  const float* poses, int poseframe_every, const fb_tri_filter_params* filter, float* out_map);
 /* getRawIDepths (/root/reference/src/flame_nodelet.cc:721-723): live features projected into the
  * current frame. Arrays sized max_features; *N receives the count. Synchronises. */
 int fb_get_raw_idepths(fb_ctx* ctx, int stream, int32_t* N, float* xy, float* mu, float* var);
