@@ -353,3 +353,34 @@ def test_filtered_map_rendered_by_update_equals_the_getter_render(capi, tri):
             assert np.all(~np.isnan(un[m]))                 # the filtered map is a subset of the unfiltered one
             checked += 1
     assert checked >= 10
+
+
+def test_update_run_equals_the_per_frame_calls(capi):
+    """fb_update_run (a camera thread's loop in one C call) = fb_update + fb_get_idepthmap(filter) per frame."""
+    W, H = 320, 240
+    K = (synth.K_VGA * np.array([[0.5], [0.5], [1.0]], np.float32)).astype(np.float32)
+    up = capi.default_update_params()
+    up.iters, up.idepth_var_max_graph = 12, 0.05
+    n = 12
+    frames, poses = _stream(W, H, K, n, seed=6, step=0.02)
+    imgs = np.ascontiguousarray(np.stack([f[0] for f in frames]), np.uint8)
+    poses = np.ascontiguousarray(poses, np.float32)
+    flt = capi.default_tri_filter_params()
+    res = []
+    for mode in ("calls", "run"):
+        with capi.Context(1, W, H, 4, 1024, 1024, 3072) as ctx:
+            ctx.set_intrinsics(0, K)
+            ctx.set_update_params(up)
+            out = np.full((H, W), -7.0, np.float32)
+            if mode == "calls":
+                nmaps = 0
+                for k in range(n):
+                    if ctx.update(0, k / 30.0, k, poses[k], imgs[k], k % 3 == 0):
+                        ctx.get_idepthmap(0, flt, out=out)
+                        nmaps += 1
+            else:
+                nmaps = ctx.update_run(0, 0, n, imgs, poses, 3, flt, out)
+            res.append((nmaps, out.copy(), ctx.get_mesh(0)["idepth"].copy()))
+    assert res[0][0] == res[1][0] >= 8
+    assert np.array_equal(np.nan_to_num(res[0][1], nan=-1), np.nan_to_num(res[1][1], nan=-1))
+    assert np.array_equal(res[0][2], res[1][2])
