@@ -337,12 +337,48 @@ def run_gpu_leg(torch, run, steps, warmup, flush_buf, mode, barrier, min_region_
     return float(np.median(times)), launches_block, ms, calls, len(times)
 
 
+PINNING = {"mode": "none"}
+HOST_CORES_TOTAL = [None]   # cores of the process before any pinning (what the JSON line reports as host.cores)
+
+
+def pin_rank_to_its_cores(local_rank, world):
+    """Several ranks on one host: every rank gets its own share of the cores NVML names as local to its GPU
+    (same socket / NUMA node), before any buffer is allocated or any thread started -- pinned host buffers
+    then sit in local memory and the ranks' host threads do not migrate over each other.  Best effort:
+    silently skipped when NVML or sched_setaffinity is unavailable."""
+    HOST_CORES_TOTAL[0] = host_cores()
+    if world <= 1 or os.environ.get("FB_BENCH_NO_PIN"):
+        return
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        avail = sorted(os.sched_getaffinity(0))
+        nwords = (max(avail) + 64) // 64
+
+        def cpus_of(dev):
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(dev), nwords)
+            return tuple(i for i in avail if (words[i // 64] >> (i % 64)) & 1)
+
+        mine_all = cpus_of(local_rank)
+        peers = [r for r in range(world) if cpus_of(r) == mine_all]
+        share = len(mine_all) // len(peers)
+        if share < 1:
+            return
+        k = peers.index(local_rank)
+        mine = mine_all[k * share:(k + 1) * share]
+        os.sched_setaffinity(0, mine)
+        PINNING.update(mode="nvml", cores_per_rank=len(mine), gpu_local_cores=len(mine_all))
+    except Exception as exc:   # no NVML, no permission, odd topology: run unpinned
+        PINNING.update(mode="none", reason=str(exc)[:80])
+
+
 def gpu_main(args):
+    rank, local_rank, world = dist_env()
+    pin_rank_to_its_cores(local_rank, world)
     import torch
     import torch.distributed as dist
     from flame_ros_b200 import capi
 
-    rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
@@ -517,7 +553,7 @@ def gpu_main(args):
             "gpu_launches": launches_all,
             "timed_blocks": {"value": blocks_res, "e2e": blocks_e2e,
                              "note": "a block = --steps steps; blocks are repeated until >= 50 ms were timed and the median block is reported; gpu_launches counts one block"},
-            "host": {"cores": host_cores(), "ranks": world},
+            "host": {"cores": HOST_CORES_TOTAL[0] or host_cores(), "ranks": world, "pinning": PINNING},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": {2: "k_nltgv2_cluster", 3: "k_nltgv2_grid"}.get(variant_used, "k_dual_edges+k_primal_vertices"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -618,8 +654,10 @@ class UpdateRun:
 def update_leg_gpu(capi, args, rank, local_rank, barrier):
     """e2e_update: frames/s through fb_update + getFilteredInverseDepthMap, host image in, dense map out."""
     S, K = args.update_streams, args.update_frames
+    # one host thread per camera: no more cameras per GPU than this rank has cores (they spin in the frame's sync)
+    S = max(1, min(S, host_cores()))
     n_frames = WL.UPD_WARMUP + K
-    datas = WL.update_streams(args.config, [1000 + rank * S + s for s in range(S)], n_frames)
+    datas = WL.update_streams(args.config, [1000 + rank * args.update_streams + s for s in range(S)], n_frames)
     run = UpdateRun(capi, datas, local_rank)
     run.run(0, WL.UPD_WARMUP)
     barrier()
