@@ -12,11 +12,12 @@
 //                  else in parallel from the CSR arrays already on the device (own edges = the
 //                  contiguous out-edge ranges of the own vertices, slot of every incidence = CSR
 //                  position), then all iterations run with the state in registers and the exchange in
-//                  shared memory: an edge thread reads the two extragradient points (the target's
-//                  through DSMEM when it lives in another tile) and stores the two K^T q contributions
-//                  into the CSR slots of its endpoints (the target's through DSMEM); a vertex thread
-//                  sums its slots in CSR order.  Two cluster barriers per iteration, no global memory
-//                  traffic inside the loop.
+//                  shared memory: an edge thread reads the two extragradient points (the target's from
+//                  a halo record of its own tile when the target lives in another one: the owner pushes
+//                  it there after every primal half-step) and stores the two K^T q contributions into
+//                  the CSR slots of its endpoints (the target's through DSMEM, st.async + mbarrier
+//                  complete_tx); a vertex thread sums its slots in CSR order.  Point-to-point mbarriers,
+//                  two CTA barriers per iteration, no global memory traffic inside the loop.
 // Arithmetic and summation order are those of nltgv2.cuh: results are bit-identical.
 #pragma once
 
@@ -199,14 +200,6 @@ k_tile_assign(int s, int maxV, const int32_t* __restrict__ nV, const float2* __r
 }
 
 // ------------------------------------------------------------------------------------ k_nltgv2_tile
-__device__ __forceinline__ float4 fbt_ld_cluster(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fbt_st_cluster(uint32_t a, float4 v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 __device__ __forceinline__ void fbt_st_cluster_v2(uint32_t a, uint32_t x, uint32_t y) {
   asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
@@ -252,22 +245,6 @@ struct TileArgs {
   int* derr;
 };
 
-// remote arrive on a peer CTA's mbarrier (release at cluster scope: the peer's acquire-wait then sees
-// everything this CTA wrote to its own shared memory before the CTA barrier that precedes the arrive)
-__device__ __forceinline__ void fbt_mbar_arrive_remote(uint32_t rmbar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rmbar) : "memory");
-}
-__device__ __forceinline__ void fbt_mbar_wait_cluster(uint32_t mbar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(mbar), "r"(parity)
-        : "memory");
-  }
-}
 
 // Own edge number le of the tile -> (local source vertex, offset among its out-edges).
 __device__ __forceinline__ void fbt_edge_of(const int* s_erow, int nOwn, int le, int* lv, int* off) {
