@@ -476,9 +476,9 @@ k_ds_stars(DelGpu d, int s, int maxV) {
   if (lane == 0 && clock64() - clk0_ > 40000) printf("star item %d vertex %d: %lld cycles, degree %d, closed %d\n", item, p, clock64() - clk0_, deg, closed);
 #endif
   if (lane == 0) {
-    d.deg[vb + p] = deg | (closed << 8);
-    d.od[vb + p] = od;
-    d.tc[vb + p] = tc;
+    // one record per vertex: degree | closed << 8 | out-degree << 16 | started triangles << 24 (all <= 32):
+    // the scan that follows reads one array instead of three
+    d.deg[vb + p] = deg | (closed << 8) | (od << 16) | (tc << 24);
   }
   }
 }
@@ -490,6 +490,11 @@ static inline int dsg_stars_grid(int device, int maxV) {
   if (n == 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { cudaGetLastError(); n = 148; }
   const int need = (maxV + DSG_WARPS - 1) / DSG_WARPS;
   return need < DSG_STARS_MINB * n ? need : DSG_STARS_MINB * n;
+}
+
+// (out-degree, started triangles, degree) of a vertex record as three 21-bit counters for the packed scan
+__device__ __forceinline__ unsigned long long dsg_scan_pack(int rec) {
+  return (unsigned long long)((rec >> 16) & 0xff) | ((unsigned long long)((rec >> 24) & 0xff) << 21) | ((unsigned long long)(rec & 0xff) << 42);
 }
 
 // ------------------------------------------------------------------------------------ k_ds_scan
@@ -507,7 +512,7 @@ k_ds_scan(DelGpu d, int s, int maxV, int maxE, int maxT, int32_t* row, int32_t* 
   unsigned long long acc = 0ull;
 #pragma unroll 4
   for (int v = v0; v < v1; ++v)
-    acc += (unsigned long long)d.od[vb + v] | ((unsigned long long)d.tc[vb + v] << 21) | ((unsigned long long)(d.deg[vb + v] & 0xff) << 42);
+    acc += dsg_scan_pack(d.deg[vb + v]);
   unsigned long long tot;
   unsigned long long ex = dsg_block_scan64(acc, s_warp, &tot);
 #pragma unroll 4
@@ -515,7 +520,7 @@ k_ds_scan(DelGpu d, int s, int maxV, int maxE, int maxT, int32_t* row, int32_t* 
     d.eoff[ob + v] = (int)(ex & 0x1fffffull);
     d.toff[ob + v] = (int)((ex >> 21) & 0x1fffffull);
     row[v] = (int)(ex >> 42);
-    ex += (unsigned long long)d.od[vb + v] | ((unsigned long long)d.tc[vb + v] << 21) | ((unsigned long long)(d.deg[vb + v] & 0xff) << 42);
+    ex += dsg_scan_pack(d.deg[vb + v]);
   }
   const int ce = (int)(tot & 0x1fffffull), ct = (int)((tot >> 21) & 0x1fffffull), cr = (int)(tot >> 42);
   if (threadIdx.x == 0) {
@@ -549,7 +554,7 @@ k_ds_emit(DelGpu d, int s, int maxV, int maxE, int maxT, const float2* __restric
   const int v = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (v >= V || meta[DSG_NT] == 0) return;
   const size_t vb = (size_t)s * maxV, ob = (size_t)s * (maxV + 1);
-  const int dg = d.deg[vb + v], deg = dg & 0xff, closed = dg >> 8;
+  const int dg = d.deg[vb + v], deg = dg & 0xff, closed = (dg >> 8) & 1;
   if (deg == 0) return;
   const int e0 = d.eoff[ob + v], t0 = d.toff[ob + v];
   const float2 pv = vpos[v];
