@@ -202,6 +202,7 @@ extern "C" fb_ctx* fb_create(int device, int n_streams, int width, int height, i
   A(dalloc(&c->counters, S * FB_NUM_COUNTERS));
   A(dalloc(&c->tri, S * (size_t)c->maxT * 3)); A(dalloc(&c->nT, S));
   A(dalloc(&c->tri_valid, S * (size_t)c->maxT)); A(dalloc(&c->owner, S * npx));
+  A(cudaMemset(c->owner, 0x7f, sizeof(int32_t) * S * npx));  // FB_OWNER_NONE; every shading pass leaves it that way
   A(dalloc(&c->idmap, S * npx));
   if (!ok) {
     free_all(c);
@@ -1459,7 +1460,6 @@ extern "C" int fb_interpolate(fb_ctx* c, int s, const fb_tri_filter_params* filt
   const int32_t* tri = c->tri + (size_t)s * c->maxT * 3;
   {
     ProfScope ps(c, FB_PROF_INTERP);
-    FB_CUDA(c, cudaMemsetAsync(owner, 0x7f, sizeof(int32_t) * npx, c->stream));
     if (T) {
       fb_tri_filter_params fp;
       fb_default_tri_filter_params(&fp);

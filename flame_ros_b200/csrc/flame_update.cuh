@@ -399,21 +399,21 @@ static int update_interpolate(fb_ctx* c, int s, const int32_t* Tdev, int32_t* co
   int32_t* owner2 = spec ? c->owner2 + (size_t)s * npx : nullptr;
   float* map2 = spec ? c->idmap_f + (size_t)s * npx : nullptr;
   ProfScope ps(c, FB_PROF_INTERP);
-  FB_CUDA(c, cudaMemsetAsync(owner, 0x7f, sizeof(int32_t) * npx, st));
-  if (covered) FB_CUDA(c, cudaMemsetAsync(covered, 0, sizeof(int32_t), st));
+  // (the ownership maps are kept clean by the shading pass; the coverage counter is zeroed by the claim pass)
+  if (covered && !T) FB_CUDA(c, cudaMemsetAsync(covered, 0, sizeof(int32_t), st));
   if (T) {  // unfiltered: every triangle is valid, no validity pass; the filtered map rides along when asked for
     if (spec) {
       const float cos_thresh = (float)cos((double)S.spec_filter.oblique_normal_thresh);
       k_tri_validity<<<fb_div_up(T, 256), 256, 0, st>>>(c->W, c->d_K + 9 * s, c->vpos + vb, c->x + vb, T, tri, S.spec_filter, cos_thresh, 1, valid, Tdev);
       c->launches += 1;
     }
-    k_raster_claim<<<fb_div_up(T * 32, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, T, tri, nullptr, owner, Tdev, spec ? valid : nullptr, owner2);
+    k_raster_claim<<<fb_div_up(T * 32, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, T, tri, nullptr, owner, Tdev, spec ? valid : nullptr, owner2, covered);
     c->launches += 1;
   }
   k_raster_shade<<<fb_div_up((int)npx, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, c->x + vb, tri, owner, c->idmap + (size_t)s * npx, Tdev, covered);
   c->launches++;
   if (spec && T) {  // (one shading pass writing both maps was measured 3x slower than this second launch)
-    k_raster_shade<<<fb_div_up((int)npx, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, c->x + vb, tri, owner2, map2, Tdev, nullptr, 1);
+    k_raster_shade<<<fb_div_up((int)npx, 256), 256, 0, st>>>(c->W, c->H, c->vpos + vb, c->x + vb, tri, owner2, map2, Tdev, nullptr);
     c->launches++;
   }
   FB_CUDA(c, cudaGetLastError());

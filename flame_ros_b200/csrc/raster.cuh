@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(256)
 k_raster_claim(int W, int H, const float2* __restrict__ vtx, int T,
                const int32_t* __restrict__ tri, const uint8_t* __restrict__ valid,
                int32_t* __restrict__ owner, const int32_t* __restrict__ Tdev = nullptr,
-               const uint8_t* __restrict__ valid2 = nullptr, int32_t* __restrict__ owner2 = nullptr) {
+               const uint8_t* __restrict__ valid2 = nullptr, int32_t* __restrict__ owner2 = nullptr,
+               int32_t* __restrict__ covered_zero = nullptr) {
+  // the shading pass that follows counts covered pixels into this word: zeroed here instead of by a memset node
+  if (covered_zero && blockIdx.x == 0 && threadIdx.x == 0) *covered_zero = 0;
   // owner2 != NULL: a second ownership map over the triangles that pass `valid2` is claimed in the same
   // pass (fb_update renders the filtered map of the next getter call beside the unfiltered one)
   const int lane = threadIdx.x & 31;
@@ -135,12 +138,12 @@ __global__ void __launch_bounds__(256)
 k_raster_shade(int W, int H, const float2* __restrict__ vtx, const float* __restrict__ idepth,
                const int32_t* __restrict__ tri, int32_t* __restrict__ owner,
                float* __restrict__ map, const int32_t* __restrict__ Tdev = nullptr,
-               int32_t* __restrict__ covered = nullptr, int reset_owner = 0) {
+               int32_t* __restrict__ covered = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (Tdev && *Tdev == 0) return;  // no mesh this frame: the previous map stays
   if (i >= W * H) return;
   const int t = owner[i];
-  if (reset_owner) owner[i] = FB_OWNER_NONE;  // the second ownership map is left clean for the next frame
+  owner[i] = FB_OWNER_NONE;  // the ownership map is left clean for the next claim pass (no memset per frame)
   float out = __int_as_float(0x7fc00000);
   if (t != FB_OWNER_NONE) out = fb_shade_one(W, vtx, idepth, tri, t, i);
   map[i] = out;
