@@ -149,6 +149,7 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+BASELINE_CONFIG = {"tiny": "smoke-sized, not a BASELINE config", "C2": "configs[1]", "C3": "configs[2]", "C4": "configs[3]"}
 RESULT_LAG = 3            # e2e leg: steps between a step's enqueue and the host's read of its result
 RESULT_BUFFERS = RESULT_LAG + 1
 
@@ -526,9 +527,9 @@ def gpu_main(args):
             "metric": METRIC, "value": frames / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s (BASELINE configs[1]): synthetic %dx%d stream, %d features = %d Delaunay vertices, "
+            "config": {"workload": "%s (BASELINE %s): synthetic %dx%d stream, %d features = %d Delaunay vertices, "
                                    "%d PD iters/frame; x %d independent streams per GPU, one batched launch"
-                                   % (args.config, datas[0].W, datas[0].H, datas[0].V, datas[0].V, iters, S),
+                                   % (args.config, BASELINE_CONFIG.get(args.config, "-"), datas[0].W, datas[0].H, datas[0].V, datas[0].V, iters, S),
                        "streams_per_gpu": S, "vertices": datas[0].V, "edges": datas[0].E, "pd_iters": iters,
                        "solver_variant": {1: "streaming (2 kernels/iter, CUDA graph)", 2: "persistent cluster (DSMEM)",
                                           3: "resident, one exchange per iteration (%s)" % {1: "cluster of CTAs, DSMEM st.async hand-over",
@@ -842,9 +843,9 @@ def reference_main(args):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
            "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "%s (BASELINE configs[1]) x %d independent streams, CPU oracle restatement of the "
+           "config": {"workload": "%s (BASELINE %s) x %d independent streams, CPU oracle restatement of the "
                                   "reference algorithm (robustrobotics/flame source is not in /root/reference)"
-                                  % (args.config, S), "streams_per_gpu": S, "vertices": datas[0].V,
+                                  % (args.config, BASELINE_CONFIG.get(args.config, "-"), S), "streams_per_gpu": S, "vertices": datas[0].V,
                       "edges": datas[0].E, "pd_iters": datas[0].iters},
            "solver_iters_per_second": frames * datas[0].iters / dt,
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
